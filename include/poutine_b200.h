@@ -1,0 +1,176 @@
+/*
+ * poutine_b200.h — C ABI of libpoutine_b200.so
+ *
+ * B200-native (sm_100a) replacement for the ONE hot path of POUTINE's Homoplasy_Counter:
+ *     count_all_homoplasy_events(tree, seg_sites, physical_poss)   HC.java:1402  (called HC.java:299)
+ *     assoc(all_events, phenos)                                    HC.java:2029  (called HC.java:314)
+ * ("HC.java" = /root/reference/src/Homoplasy_Counter.java).  The reference has no plugin/FFI
+ * surface (both are private methods of one class), so the boundary is cut at those two calls:
+ * the Java host keeps CLI, loaders and the TSV writer, flattens its NewickTree / Fasta records
+ * into the plain arrays below and binds these entry points through FFM or JNI
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain C, no callbacks, no C++/torch types; every pointer is caller-owned host memory,
+ *     copied during the call and never retained (exception: none).
+ *   - return 0 on success, negative pb_status on failure; pb_last_error() gives the message.
+ *     The reference's convention is "print, stack trace to the log, System.exit(-1)"
+ *     (e.g. HC.java:3267-3271); the host maps a negative status onto that.
+ *   - there is NO CPU fallback: a missing sm_100 device or a failed launch is an error.
+ *   - one context per host thread / per GPU; calls on a context are serialised by the caller.
+ */
+#ifndef POUTINE_B200_H
+#define POUTINE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_ctx pb_ctx;
+
+typedef enum {
+    PB_OK = 0,
+    PB_ERR_INVALID = -1,         /* bad argument / call order */
+    PB_ERR_CUDA = -2,            /* CUDA runtime error (incl. no sm_100 device) */
+    PB_ERR_NO_INFORMATIVE = -3,  /* min_hcount filtered out every site — HC.java:3866-3869 */
+    PB_ERR_NCCL = -4,
+    PB_ERR_OOM = -5
+} pb_status;
+
+enum { PB_MODE_PHILOX = 0, PB_MODE_REPLAY = 1 };
+
+/* label codes of pb_set_labels (pheno file column 2, HC.java:3747-3751) */
+enum { PB_LABEL_CONTROL = 0, PB_LABEL_CASE = 1, PB_LABEL_MISSING = 2 };
+
+/* site classes (switch at HC.java:1443-1473) */
+enum { PB_SITE_NO_ALLELE = 0, PB_SITE_MONO = 1, PB_SITE_BI = 2, PB_SITE_TRI = 3, PB_SITE_QUAD = 4 };
+
+typedef struct {
+    int32_t device;          /* CUDA ordinal */
+    int32_t mode;            /* PB_MODE_PHILOX | PB_MODE_REPLAY */
+    int64_t n_replicates;    /* m: --num-replicates, default 100000 (HC.java:89) */
+    int32_t min_hcount;      /* default 1 (HC.java:98) */
+    int32_t reserved0;
+    uint64_t seed;           /* Philox key; every rank of a sharded run must pass the same seed */
+    int64_t site_offset;     /* global index of this context's first site (site sharding, 64-aligned) */
+    double maxt_tau;         /* 0 = auto.  Candidate threshold of the maxT pass (test hook) */
+    uint32_t flags;          /* PB_FLAG_* */
+    uint32_t reserved1;
+} pb_config;
+
+enum {
+    PB_FLAG_FORCE_GENERAL_NULL = 1u,  /* disable the all-labelled bit-sliced fast path (test hook) */
+    PB_FLAG_KEEP_RAW_EVENTS = 2u      /* keep the raw MRCA event list for pb_get_raw_events */
+};
+
+/* One record per site of this context, field-for-field Homoplasy_Events (HC.java:5531-5550);
+ * physical_pos stays on the host (it is only echoed into the output rows). */
+typedef struct {
+    int32_t segsite_id;   /* 1-based global id (HC.java:1419) */
+    int32_t site_class;   /* PB_SITE_*; all fields below are 0 unless PB_SITE_BI */
+    int32_t allele1;      /* char: major allele (HC.java:1712-1743) */
+    int32_t allele2;      /* char: minor allele */
+    int32_t a1_count;     /* |allele1_MRCAs| after the <2 clearing (HC.java:1954-1962) */
+    int32_t a2_count;
+    int32_t a1_extant;    /* a1_count_extant_only (HC.java:5586-5600) */
+    int32_t a2_extant;
+} pb_site_out;
+
+/* # bi-allelic / monomorphic / tri / quad sites, HC.java:1477-1480 (+ the ">4"/no-allele default arm) */
+typedef struct {
+    int64_t n_no_allele, n_mono, n_bi, n_tri, n_quad;
+    int64_t n_raw_events;     /* MRCA nodes found over all sites, before the <2 clearing, root excluded */
+} pb_class_counts;
+
+/* One record per homoplasically informative site, Binomial_Test_Stat (HC.java:5876-5887)
+ * + obs_counts (HC.java:3042); sentinels -1 / NaN as in its constructor (HC.java:5891-5906). */
+typedef struct {
+    int32_t site_index;       /* 0-based index into this context's sites */
+    int32_t segsite_id;
+    int32_t a1_in_use, a2_in_use;
+    int32_t obs_counts[4];    /* a1case, a1ctrl, a2case, a2ctrl */
+    int32_t r_a1, r_a2, r_maxT_a1, r_maxT_a2;
+    double obs_p_a1, obs_p_a2, pointwise_a1, pointwise_a2, familywise_a1, familywise_a2;
+} pb_stat_out;
+
+/* Device time of the last pb_run_events / pb_run_assoc, CUDA events on the library's stream. */
+typedef struct {
+    float ms_events_kernel;   /* K1 main kernel only (the HBM-bound plane sweep) */
+    float ms_events_total;    /* K1 + count + finalize + compaction */
+    float ms_tally;           /* K2 */
+    float ms_ptable;          /* p-value table + thresholds */
+    float ms_null_gen;        /* K3a label bit-matrix generation */
+    float ms_null_count;      /* K3b replicate counting */
+    float ms_null_fallback;   /* maxT fallback pass (normally 0) */
+    float ms_allreduce;       /* NCCL all-reduce(min) of maxT */
+    float ms_pvalues;         /* K4: sort maxT + pointwise/familywise */
+    float ms_assoc_total;
+    int64_t n_launches;       /* kernels launched by the last events+assoc pair */
+    int64_t k1_algorithmic_bytes;  /* 3*N*W*8 plane bytes + 32 B/site + 8 B/raw event */
+    int64_t n_informative, n_alleles_in_use, n_extant_events;  /* S_inf, A, E of SURVEY §8 */
+    int64_t n_fast_alleles;   /* alleles handled by the bit-sliced threshold path */
+    int64_t n_maxt_fallback_reps;
+} pb_timings;
+
+int pb_create(const pb_config* cfg, pb_ctx** out);
+void pb_destroy(pb_ctx* ctx);
+/* ctx may be NULL: returns the calling thread's last pb_create error. */
+const char* pb_last_error(pb_ctx* ctx);
+
+/* NewickTree flattened by the host: parent index per node (root = -1), leaf flags.
+ * Any node order; the host keeps the name table.  Replaces the tree argument of HC.java:1402. */
+int pb_set_tree(pb_ctx* ctx, int32_t n_nodes, const int32_t* parent, const uint8_t* is_leaf);
+
+/* `phenos` (HC.java:1972-2019) flattened: one entry per pheno-file row in file order:
+ * the leaf's node index and its label code.  Leaves without a row are simply absent. */
+int pb_set_labels(pb_ctx* ctx, int32_t n_samples, const int32_t* sample_node, const uint8_t* label);
+
+/* Number of sites this context holds; (re)allocates the device planes. */
+int pb_set_sites(pb_ctx* ctx, int64_t n_sites);
+
+/* Node-major bit planes of `seg_sites` (HC.java:1241-1306): 2-bit base code A0 C1 G2 T3 in
+ * (B1,B0), V = genotype is an upper-case ACGT.  Bit j of word w = site 64*w+j.  Uploads the
+ * column tile [word_begin, word_begin+n_words) of all nodes; row v of each source starts at
+ * src + v*src_pitch_words.  Streamable: call once per tile. */
+int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
+                  const uint64_t* B0, const uint64_t* B1, const uint64_t* V);
+
+/* count_all_homoplasy_events (HC.java:1402).  per_site (n_sites records) and counts may be NULL. */
+int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts);
+
+/* assoc (HC.java:2029 -> 3013-3186): observed tallies, permutation null, point-wise and
+ * family-wise p-values.  replay_perms: m*P uint32 (required iff PB_MODE_REPLAY): in replicate r
+ * sample j receives label[replay_perms[r*P+j]].  per_inf_site has room for `cap` records
+ * (n_inf is always written; PB_ERR_INVALID if cap is too small).  maxT_sorted (m doubles) may be NULL. */
+int pb_run_assoc(pb_ctx* ctx, const uint32_t* replay_perms, pb_stat_out* per_inf_site, int64_t cap,
+                 int64_t* n_inf, double* maxT_sorted);
+
+/* Introspection used by the parity tests. */
+int pb_get_sites(pb_ctx* ctx, pb_site_out* per_site);
+int pb_get_raw_events(pb_ctx* ctx, int64_t cap, int32_t* site, int32_t* node, int64_t* n);
+int pb_get_event_csr(pb_ctx* ctx, int64_t* offsets /* 2*n_inf+1 */, int32_t* sample_index /* E */, int64_t cap);
+int pb_get_maxT_unsorted(pb_ctx* ctx, double* out /* m */);
+int pb_get_ptable(pb_ctx* ctx, int32_t* n_max, double* out, int64_t cap);
+int pb_get_timings(pb_ctx* ctx, pb_timings* out);
+
+/* Multi-GPU: one context per GPU, sites sharded; the only exchange is an NCCL all-reduce(min)
+ * of maxT[m] inside pb_run_assoc.  Rank 0 creates the id, the host broadcasts its 128 bytes. */
+int pb_comm_unique_id(void* id128);
+int pb_comm_init(pb_ctx* ctx, const void* id128, int32_t rank, int32_t world);
+
+/* Host-side helpers (no GPU work). */
+/* Pack `seg_sites` chars (node-major, row v at seq + v*seq_pitch) into bit planes — the
+ * Fasta_Record -> plane step of the host (HC.java:1252-1266). */
+int pb_pack_chars(const char* seq, int64_t n_nodes, int64_t n_sites, int64_t seq_pitch,
+                  uint64_t* B0, uint64_t* B1, uint64_t* V, int64_t pitch_words);
+/* Pinned host allocations for streaming uploads. */
+int pb_host_alloc(void** out, uint64_t bytes);
+int pb_host_free(void* p);
+int pb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POUTINE_B200_H */
