@@ -47,6 +47,7 @@ def lib():
         L.or_binomial_test.restype = d; L.or_binomial_test.argtypes = [C.c_int, C.c_int, d]
         L.or_binomial_table.restype = None; L.or_binomial_table.argtypes = [C.c_int, d, vp]
         L.or_java_shuffle_perms.restype = None; L.or_java_shuffle_perms.argtypes = [i64, i64, i32, vp]
+        L.or_java_random_ints.restype = None; L.or_java_random_ints.argtypes = [i64, i32, i32, vp]
         L.or_philox_labels.restype = None; L.or_philox_labels.argtypes = [u64, u64, i32, i32, i32, vp]
         L.or_create.restype = vp; L.or_create.argtypes = [i32, vp, i32, vp]
         L.or_destroy.restype = None; L.or_destroy.argtypes = [vp]
@@ -81,6 +82,12 @@ def binomial_table(n_max, p):
 def java_shuffle_perms(base_seed, m, P):
     out = np.empty((m, P), dtype=np.uint32)
     lib().or_java_shuffle_perms(int(base_seed), int(m), int(P), _p(out))
+    return out
+
+
+def java_random_ints(seed, n, bound=0):
+    out = np.empty(n, dtype=np.int32)
+    lib().or_java_random_ints(int(seed), int(n), int(bound), _p(out))
     return out
 
 

@@ -76,6 +76,12 @@ struct JavaRandom {
     }
 };
 
+// out[i] = nextInt(bound) (bound > 0) or nextInt() (bound == 0) of `new Random(seed)` — known-answer tests
+void or_java_random_ints(int64_t seed, int32_t n, int32_t bound, int32_t* out) {
+    JavaRandom rnd(seed);
+    for (int32_t i = 0; i < n; i++) out[i] = bound > 0 ? rnd.nextInt(bound) : rnd.next(32);
+}
+
 // perms[rep*P + i] = index (into the pheno-file order) of the label that sample i receives in
 // replicate rep.  Replicate rep uses `new Random(base_seed + rep)` and Collections.shuffle:
 //   for (i = size; i > 1; i--) swap(list, i-1, rnd.nextInt(i));
@@ -153,7 +159,7 @@ struct or_site_t {  // mirrors Homoplasy_Events (HC.java:5531-5550), 32 bytes
     int32_t a1_count, a2_count, a1_extant, a2_extant;
 };
 
-struct or_stat_t {  // mirrors Binomial_Test_Stat (HC.java:5876-5887) + obs_counts, 88 bytes
+struct or_stat_t {  // mirrors Binomial_Test_Stat (HC.java:5876-5887) + obs_counts, 96 bytes
     int32_t event_index;  // index into the biallelic-site list (all_events)
     int32_t segsite_id;
     int32_t a1_in_use, a2_in_use;

@@ -1,0 +1,208 @@
+"""Host-side mirror of the two reference entry points this library replaces.
+
+    Homoplasy_Counter.count_all_homoplasy_events(tree, seg_sites, physical_poss)   HC.java:1402
+    Homoplasy_Counter.assoc(all_events, phenos)                                    HC.java:2029
+
+Same names, argument meaning and error behaviour as the reference (which has no plugin API of its
+own — both are private methods called from call(), HC.java:299 / 314).  All compute happens in
+libpoutine_b200.so on the GPU; this module only flattens/packs inputs and shapes outputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SITE_DTYPE, STAT_DTYPE, PbClassCounts, PbConfig, PbTimings, ptr
+
+
+class PoutineError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"[pb status {status}] {msg}")
+        self.status = status
+
+
+class NoInformativeSites(PoutineError):
+    """'min_hcount = .. is set too high and has filtered out all segregating sites' (HC.java:3866-3869);
+    the reference prints that and calls System.exit(-1)."""
+
+
+def pack_chars(seq: np.ndarray, pitch_words: int | None = None):
+    """seg_sites chars (N, S) -> planes (B0, B1, V) uint64[N][W]  (host packer, csrc/packer.cpp)."""
+    seq = np.ascontiguousarray(seq)
+    assert seq.ndim == 2 and seq.dtype.itemsize == 1
+    N, S = seq.shape
+    W = (S + 63) // 64
+    pw = pitch_words or W
+    B0 = np.empty((N, pw), dtype=np.uint64)
+    B1 = np.empty((N, pw), dtype=np.uint64)
+    V = np.empty((N, pw), dtype=np.uint64)
+    rc = _lib.lib().pb_pack_chars(ptr(seq), N, S, seq.strides[0], ptr(B0), ptr(B1), ptr(V), pw)
+    if rc != 0:
+        raise PoutineError(rc, "pb_pack_chars: invalid arguments")
+    return B0, B1, V
+
+
+class HomoplasyCounter:
+    """One GPU context.  Usage mirrors Homoplasy_Counter.call() (HC.java:296-314):
+
+        hc = HomoplasyCounter(num_replicates=100000, min_hcount=1)
+        hc.set_tree(parent, is_leaf)
+        hc.set_planes(B0, B1, V, n_sites)          # or set_seg_sites(chars)
+        all_events, class_counts = hc.count_all_homoplasy_events()
+        hc.set_phenos(sample_node, label)
+        stats, maxT_sorted = hc.assoc()
+    """
+
+    def __init__(self, num_replicates=100000, min_hcount=1, device=0, seed=0, replay=False, site_offset=0,
+                 maxt_tau=0.0, force_general_null=False):
+        self._h = None
+        L = _lib.lib()
+        cfg = PbConfig(device=device, mode=_lib.PB_MODE_REPLAY if replay else _lib.PB_MODE_PHILOX,
+                       n_replicates=int(num_replicates), min_hcount=int(min_hcount), seed=int(seed),
+                       site_offset=int(site_offset), maxt_tau=float(maxt_tau),
+                       flags=_lib.PB_FLAG_FORCE_GENERAL_NULL if force_general_null else 0)
+        h = C.c_void_p()
+        rc = L.pb_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise PoutineError(rc, L.pb_last_error(None).decode())
+        self._h = h
+        self.m = int(num_replicates)
+        self.n_sites = 0
+        self.n_nodes = 0
+        self.n_samples = 0
+        self.n_informative = 0
+
+    def close(self):
+        if self._h is not None:
+            _lib.lib().pb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = _lib.lib().pb_last_error(self._h).decode()
+            if rc == _lib.PB_ERR_NO_INFORMATIVE:
+                raise NoInformativeSites(rc, msg)
+            raise PoutineError(rc, msg)
+
+    # ---- inputs --------------------------------------------------------------------------------
+    def set_tree(self, parent, is_leaf):
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        is_leaf = np.ascontiguousarray(is_leaf, dtype=np.uint8)
+        self._check(_lib.lib().pb_set_tree(self._h, len(parent), ptr(parent), ptr(is_leaf)))
+        self.n_nodes = len(parent)
+
+    def set_phenos(self, sample_node, label):
+        sample_node = np.ascontiguousarray(sample_node, dtype=np.int32)
+        label = np.ascontiguousarray(label, dtype=np.uint8)
+        self._check(_lib.lib().pb_set_labels(self._h, len(label), ptr(sample_node), ptr(label)))
+        self.n_samples = len(label)
+
+    def set_sites(self, n_sites):
+        self._check(_lib.lib().pb_set_sites(self._h, int(n_sites)))
+        self.n_sites = int(n_sites)
+
+    def put_planes(self, B0, B1, V, word_begin=0):
+        """Upload a column tile of the node-major planes (any row pitch)."""
+        for a in (B0, B1, V):
+            assert a.dtype == np.uint64 and a.ndim == 2 and a.shape[0] == self.n_nodes and a.strides[1] == 8
+        assert B0.strides == B1.strides == V.strides
+        self._check(_lib.lib().pb_put_planes(self._h, int(word_begin), B0.shape[1], B0.strides[0] // 8, ptr(B0), ptr(B1), ptr(V)))
+
+    def set_planes(self, B0, B1, V, n_sites, tile_words=None):
+        self.set_sites(n_sites)
+        W = (n_sites + 63) // 64
+        tw = tile_words or W
+        for w0 in range(0, W, tw):
+            w1 = min(W, w0 + tw)
+            self.put_planes(B0[:, w0:w1], B1[:, w0:w1], V[:, w0:w1], w0)
+
+    def set_seg_sites(self, chars):
+        B0, B1, V = pack_chars(chars)
+        self.set_planes(B0, B1, V, chars.shape[1])
+
+    # ---- the two reference entry points ----------------------------------------------------------
+    def count_all_homoplasy_events(self, fetch_sites=True):
+        """-> (all_events, class_counts).  all_events = structured array over the BIALLELIC sites in
+        site order (the reference's ArrayList<Homoplasy_Events>), fields as Homoplasy_Events."""
+        cc = PbClassCounts()
+        sites = np.empty(self.n_sites, dtype=SITE_DTYPE) if fetch_sites else None
+        self._check(_lib.lib().pb_run_events(self._h, ptr(sites), C.byref(cc)))
+        counts = dict(no_allele=cc.n_no_allele, mono=cc.n_mono, bi=cc.n_bi, tri=cc.n_tri, quad=cc.n_quad,
+                      raw_events=cc.n_raw_events)
+        self.class_counts = counts
+        self.sites = sites
+        if not fetch_sites:
+            return None, counts
+        return sites[sites["site_class"] == 2], counts
+
+    def assoc(self, replay_perms=None, fetch=True, want_maxT=True):
+        """-> (stats, maxT_sorted).  stats = one record per homoplasically informative site
+        (Binomial_Test_Stat + obs_counts)."""
+        L = _lib.lib()
+        tm = self.timings()
+        cap = max(int(tm["n_informative"]), 1)
+        stats = np.empty(cap, dtype=STAT_DTYPE) if fetch else None
+        maxT = np.empty(self.m, dtype=np.float64) if (fetch and want_maxT) else None
+        n_inf = C.c_int64(0)
+        perms = None
+        if replay_perms is not None:
+            perms = np.ascontiguousarray(replay_perms, dtype=np.uint32)
+            assert perms.shape == (self.m, self.n_samples)
+        self._check(L.pb_run_assoc(self._h, ptr(perms), ptr(stats), cap, C.byref(n_inf), ptr(maxT)))
+        self.n_informative = n_inf.value
+        return (stats[:n_inf.value] if fetch else None), maxT
+
+    # ---- introspection ------------------------------------------------------------------------------
+    def timings(self):
+        t = PbTimings()
+        self._check(_lib.lib().pb_get_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def raw_events(self):
+        n = C.c_int64(0)
+        self._check(_lib.lib().pb_get_raw_events(self._h, 0, None, None, C.byref(n)))
+        site = np.empty(n.value, dtype=np.int32)
+        node = np.empty(n.value, dtype=np.int32)
+        self._check(_lib.lib().pb_get_raw_events(self._h, n.value, ptr(site), ptr(node), C.byref(n)))
+        return site, node
+
+    def event_csr(self):
+        tm = self.timings()
+        n_inf, E = int(tm["n_informative"]), int(tm["n_extant_events"])
+        off = np.empty(2 * n_inf + 1, dtype=np.int64)
+        idx = np.empty(max(E, 1), dtype=np.int32)
+        self._check(_lib.lib().pb_get_event_csr(self._h, ptr(off), ptr(idx), max(E, 1)))
+        return off, idx[:E]
+
+    def maxT_unsorted(self):
+        out = np.empty(self.m, dtype=np.float64)
+        self._check(_lib.lib().pb_get_maxT_unsorted(self._h, ptr(out)))
+        return out
+
+    def ptable(self):
+        nm = C.c_int32(0)
+        self._check(_lib.lib().pb_get_ptable(self._h, C.byref(nm), None, 0))
+        total = (nm.value + 1) * (nm.value + 2) // 2
+        out = np.empty(total, dtype=np.float64)
+        self._check(_lib.lib().pb_get_ptable(self._h, C.byref(nm), ptr(out), total))
+        return nm.value, out
+
+    def comm_init(self, id128: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(id128, 128)
+        self._check(_lib.lib().pb_comm_init(self._h, buf, rank, world))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = _lib.lib().pb_comm_unique_id(buf)
+    if rc != 0:
+        raise PoutineError(rc, _lib.lib().pb_last_error(None).decode())
+    return buf.raw

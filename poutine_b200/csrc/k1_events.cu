@@ -1,0 +1,503 @@
+// K1 — homoplasy event detection over node-major bit planes (sm_100a).
+//
+// Replaces count_all_homoplasy_events / identify_homoplasy_events_for_seg_site
+// (HC.java:1402-1511, 1647-1698) and the per-site allele census (get_alleles HC.java:1593-1603,
+// identify_major_minor_alleles HC.java:1712-1743).
+//
+// Closed form of the reference's leaf->root walks: node v is an MRCA iff
+//     v != root  &&  parent(v) != root  &&  geno(v) in ACGT  &&  geno(parent(v)) != geno(v)
+// plus the root itself; v goes to bucket a1 iff geno(v) == allele1, else a2; a bucket with
+// fewer than 2 members is emptied.  The test is edge-local, so K1 streams every plane word
+// once: one thread owns one 64-site word column and walks a host-built edge schedule.
+//   * MRCA mask of an edge:  Vc & (~Vp | (B0c^B0p) | (B1c^B1p))     (3 LOP3 per 32-bit half)
+//   * events are sparse (~2.5 per site per tree): set bits are peeled with ffs and appended to a
+//     per-block shared-memory queue, flushed with ONE global atomic per block;
+//   * the leaf census (how many leaves carry A/C/G/T) is dense: bit-sliced vertical counters,
+//     a Harley-Seal carry-save tree over groups of 8 leaves (2 LOP3 per CSA per half).
+// HBM traffic = each plane bit once (parents re-hit L1/L2 thanks to the DFS edge order).
+#include <stdio.h>
+
+#include "pb_internal.h"
+
+struct K1Params {
+    const uint64_t* __restrict__ B0;
+    const uint64_t* __restrict__ B1;
+    const uint64_t* __restrict__ V;
+    int64_t Wp, W;
+    const EdgeOp* __restrict__ leaf_ops;
+    const EdgeOp* __restrict__ int_ops;
+    const int32_t* __restrict__ chunk_lg;
+    const int32_t* __restrict__ chunk_io;
+    uint64_t* __restrict__ census;  // [chunk][4][KS][W]
+    raw_event_t* __restrict__ raw;
+    unsigned long long* raw_cursor;
+    unsigned long long raw_cap;
+};
+
+__device__ __forceinline__ void csa(uint64_t& h, uint64_t& l, uint64_t a, uint64_t b, uint64_t c) {
+    const uint64_t u = a ^ b;
+    h = (a & b) | (u & c);
+    l = u ^ c;
+}
+
+__device__ __forceinline__ void emit_events(uint64_t mrca, uint64_t b0, uint64_t b1, uint32_t site_base, uint32_t node_tag,
+                                            raw_event_t* s_queue, unsigned int* s_count, const K1Params& p) {
+    while (mrca) {
+        const int b = __ffsll((long long)mrca) - 1;
+        mrca &= mrca - 1;
+        const uint32_t base = (uint32_t)((b0 >> b) & 1ull) | ((uint32_t)((b1 >> b) & 1ull) << 1);
+        const raw_event_t rec = (raw_event_t)(site_base + (uint32_t)b) | ((raw_event_t)(node_tag | (base << 29)) << 32);
+        const unsigned int slot = atomicAdd(s_count, 1u);
+        if (slot < PB_K1_QCAP) {
+            s_queue[slot] = rec;
+        } else {  // queue full: slow path straight to global (correct for arbitrarily dense inputs)
+            const unsigned long long pos = atomicAdd(p.raw_cursor, 1ull);
+            if (pos < p.raw_cap) p.raw[pos] = rec;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PB_K1_THREADS) k1_events_kernel(const K1Params p) {
+    extern __shared__ raw_event_t s_queue[];
+    __shared__ unsigned int s_count;
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+
+    const int64_t w = (int64_t)blockIdx.x * PB_K1_THREADS + tid;
+    const int chunk = blockIdx.y;
+    if (w < p.W) {
+        const uint64_t* __restrict__ pV = p.V + w;
+        const uint64_t* __restrict__ pB0 = p.B0 + w;
+        const uint64_t* __restrict__ pB1 = p.B1 + w;
+        const uint32_t site_base = (uint32_t)(w * 64);
+
+        // census state: per base (A,C,G,T by 2-bit code) ones/twos/fours + high slices
+        uint64_t ones[4] = {0, 0, 0, 0}, twos[4] = {0, 0, 0, 0}, fours[4] = {0, 0, 0, 0};
+        uint64_t hi[4][PB_K1_KHI];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int j = 0; j < PB_K1_KHI; j++) hi[c][j] = 0;
+
+        const int lg0 = p.chunk_lg[chunk], lg1 = p.chunk_lg[chunk + 1];
+        for (int g = lg0; g < lg1; ++g) {
+            const int2* __restrict__ ops = reinterpret_cast<const int2*>(p.leaf_ops + (int64_t)g * 8);
+            uint64_t f4[2][4];  // "fours" carry of each half, per base
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                uint64_t cv[4], c0[4], c1[4], pv[4], p0[4], p1[4];
+                int2 op[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) op[i] = __ldg(ops + half * 4 + i);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (op[i].x >= 0) {
+                        const int64_t o = (int64_t)op[i].x * p.Wp;
+                        cv[i] = __ldg(pV + o); c0[i] = __ldg(pB0 + o); c1[i] = __ldg(pB1 + o);
+                    } else { cv[i] = 0; c0[i] = 0; c1[i] = 0; }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (op[i].y >= 0) {
+                        const int64_t o = (int64_t)op[i].y * p.Wp;
+                        pv[i] = __ldg(pV + o); p0[i] = __ldg(pB0 + o); p1[i] = __ldg(pB1 + o);
+                    } else { pv[i] = 0; p0[i] = 0; p1[i] = 0; }
+                }
+                uint64_t x[4][4];  // [base][leaf]
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (op[i].y >= 0) {
+                        const uint64_t mrca = cv[i] & (~pv[i] | (c0[i] ^ p0[i]) | (c1[i] ^ p1[i]));
+                        if (mrca) emit_events(mrca, c0[i], c1[i], site_base, (uint32_t)op[i].x | 0x80000000u, s_queue, &s_count, p);
+                    }
+                    x[0][i] = cv[i] & ~c0[i] & ~c1[i];
+                    x[1][i] = cv[i] & c0[i] & ~c1[i];
+                    x[2][i] = cv[i] & ~c0[i] & c1[i];
+                    x[3][i] = cv[i] & c0[i] & c1[i];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint64_t t2a, t2b;
+                    csa(t2a, ones[c], ones[c], x[c][0], x[c][1]);
+                    csa(t2b, ones[c], ones[c], x[c][2], x[c][3]);
+                    csa(f4[half][c], twos[c], twos[c], t2a, t2b);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint64_t carry;
+                csa(carry, fours[c], fours[c], f4[0][c], f4[1][c]);
+#pragma unroll
+                for (int j = 0; j < PB_K1_KHI; j++) {
+                    const uint64_t t = hi[c][j] & carry;
+                    hi[c][j] ^= carry;
+                    carry = t;
+                }
+            }
+        }
+
+        // internal-node edges: MRCA test only
+        const int io0 = p.chunk_io[chunk], io1 = p.chunk_io[chunk + 1];
+        const int2* __restrict__ iops = reinterpret_cast<const int2*>(p.int_ops);
+        int i0 = io0;
+        for (; i0 + 4 <= io1; i0 += 4) {
+            int2 op[4];
+            uint64_t cv[4], c0[4], c1[4], pv[4], p0[4], p1[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) op[i] = __ldg(iops + i0 + i);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int64_t o = (int64_t)op[i].x * p.Wp;
+                cv[i] = __ldg(pV + o); c0[i] = __ldg(pB0 + o); c1[i] = __ldg(pB1 + o);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int64_t o = (int64_t)op[i].y * p.Wp;
+                pv[i] = __ldg(pV + o); p0[i] = __ldg(pB0 + o); p1[i] = __ldg(pB1 + o);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint64_t mrca = cv[i] & (~pv[i] | (c0[i] ^ p0[i]) | (c1[i] ^ p1[i]));
+                if (mrca) emit_events(mrca, c0[i], c1[i], site_base, (uint32_t)op[i].x, s_queue, &s_count, p);
+            }
+        }
+        for (; i0 < io1; i0++) {
+            const int2 op = __ldg(iops + i0);
+            const int64_t oc = (int64_t)op.x * p.Wp, opp = (int64_t)op.y * p.Wp;
+            const uint64_t cv = __ldg(pV + oc), c0 = __ldg(pB0 + oc), c1 = __ldg(pB1 + oc);
+            const uint64_t pv = __ldg(pV + opp), p0 = __ldg(pB0 + opp), p1 = __ldg(pB1 + opp);
+            const uint64_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
+            if (mrca) emit_events(mrca, c0, c1, site_base, (uint32_t)op.x, s_queue, &s_count, p);
+        }
+
+        // partial census of this chunk: [chunk][base][slice][W]
+        uint64_t* out = p.census + ((int64_t)chunk * 4 * PB_K1_KS) * p.W + w;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            out[((int64_t)c * PB_K1_KS + 0) * p.W] = ones[c];
+            out[((int64_t)c * PB_K1_KS + 1) * p.W] = twos[c];
+            out[((int64_t)c * PB_K1_KS + 2) * p.W] = fours[c];
+#pragma unroll
+            for (int j = 0; j < PB_K1_KHI; j++) out[((int64_t)c * PB_K1_KS + 3 + j) * p.W] = hi[c][j];
+        }
+    }
+
+    // flush the block's event queue with one global atomic
+    __syncthreads();
+    const unsigned int n = min(s_count, (unsigned int)PB_K1_QCAP);
+    if (tid == 0 && n) s_base = atomicAdd(p.raw_cursor, (unsigned long long)n);
+    __syncthreads();
+    for (unsigned int i = tid; i < n; i += PB_K1_THREADS) {
+        const unsigned long long pos = s_base + i;
+        if (pos < p.raw_cap) p.raw[pos] = s_queue[i];
+    }
+}
+
+// ---- per-site event counters -------------------------------------------------------------------
+__global__ void k1_count_events_kernel(const raw_event_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ node_sample,
+                                       uint32_t* __restrict__ cnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const raw_event_t e = raw[i];
+    const uint32_t site = (uint32_t)e, hi = (uint32_t)(e >> 32);
+    const uint32_t base = (hi >> 29) & 3u, node = hi & PB_EV_NODE_MASK;
+    uint32_t* c = cnt + (int64_t)site * PB_CNT_STRIDE;
+    atomicAdd(c + base, 1u);
+    if (hi & 0x80000000u) {
+        atomicAdd(c + 4 + base, 1u);
+        if (node_sample[node] >= 0) atomicAdd(c + 8 + base, 1u);
+    }
+}
+
+// ---- per-site finalisation: census -> class / major-minor; counters -> Homoplasy_Events -----------
+__global__ void k1_finalize_kernel(const uint64_t* __restrict__ census, int n_chunks, int64_t W, int64_t S,
+                                   const uint64_t* __restrict__ B0, const uint64_t* __restrict__ B1, const uint64_t* __restrict__ V,
+                                   int64_t Wp, int32_t root, const uint32_t* __restrict__ cnt, int32_t min_hcount, int64_t site_offset,
+                                   pb_site_out* __restrict__ sites, uint8_t* __restrict__ flags, uint64_t* __restrict__ scan_in,
+                                   unsigned long long* __restrict__ class_counts) {
+    __shared__ unsigned int s_cls[5];
+    if (threadIdx.x < 5) s_cls[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) {
+        const int64_t w = s >> 6;
+        const int b = (int)(s & 63);
+        uint32_t leafcnt[4] = {0, 0, 0, 0};  // by 2-bit code: A C G T
+        for (int ch = 0; ch < n_chunks; ch++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int j = 0; j < PB_K1_KS; j++)
+                    v |= (uint32_t)((census[(((int64_t)ch * 4 + c) * PB_K1_KS + j) * W + w] >> b) & 1ull) << j;
+                leafcnt[c] += v;
+            }
+        // HashMap<Character,..> iteration order A, C, T, G  (buckets 'A'&15=1, 'C'&15=3, 'T'&15=4, 'G'&15=7)
+        const int order[4] = {0, 1, 3, 2};
+        int n_alleles = 0, first = -1, second = -1;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (leafcnt[order[i]] > 0) {
+                if (n_alleles == 0) first = order[i];
+                else if (n_alleles == 1) second = order[i];
+                n_alleles++;
+            }
+        pb_site_out o;
+        o.segsite_id = (int32_t)(site_offset + s + 1);
+        o.site_class = n_alleles;
+        o.allele1 = o.allele2 = o.a1_count = o.a2_count = o.a1_extant = o.a2_extant = 0;
+        uint8_t fl = 0;
+        uint64_t scan = 0;
+        if (n_alleles == 2) {
+            // identify_major_minor_alleles: first-in-order wins ties (>=, HC.java:1725)
+            int a1, a2;
+            if (leafcnt[first] >= leafcnt[second]) { a1 = first; a2 = second; } else { a1 = second; a2 = first; }
+            const char L4[4] = {'A', 'C', 'G', 'T'};
+            const uint32_t* c = cnt + s * PB_CNT_STRIDE;
+            const int64_t ro = (int64_t)root * Wp + w;
+            const bool rvalid = (V[ro] >> b) & 1ull;
+            const int rcode = (int)((B0[ro] >> b) & 1ull) | ((int)((B1[ro] >> b) & 1ull) << 1);
+            const bool root_a1 = rvalid && rcode == a1;   // add_MRCA(root): a1 iff geno(root)==allele1 (HC.java:1689, 1861)
+            uint32_t m_all = c[0] + c[1] + c[2] + c[3], x_all = c[4] + c[5] + c[6] + c[7], xs_all = c[8] + c[9] + c[10] + c[11];
+            uint32_t a1c = c[a1] + (root_a1 ? 1u : 0u);
+            uint32_t a2c = (m_all - c[a1]) + (root_a1 ? 0u : 1u);
+            uint32_t a1x = c[4 + a1], a2x = x_all - c[4 + a1];
+            uint32_t a1s = c[8 + a1], a2s = xs_all - c[8 + a1];
+            if (a1c < 2) { a1c = 0; a1x = 0; a1s = 0; }   // remove_non_homoplasic_mutations (HC.java:1954-1962)
+            if (a2c < 2) { a2c = 0; a2x = 0; a2s = 0; }
+            o.allele1 = L4[a1]; o.allele2 = L4[a2];
+            o.a1_count = (int32_t)a1c; o.a2_count = (int32_t)a2c; o.a1_extant = (int32_t)a1x; o.a2_extant = (int32_t)a2x;
+            // subset_by_min_hcount with EXTANT_NODES_ONLY (HC.java:3783-3905)
+            const bool u1 = (int32_t)a1x >= min_hcount, u2 = (int32_t)a2x >= min_hcount;
+            fl = PB_SF_BI | (u1 ? PB_SF_A1_USE : 0) | (u2 ? PB_SF_A2_USE : 0) | (uint8_t)(a1 << PB_SF_A1_CODE_SHIFT);
+            if (u1 || u2) scan = (1ull << 38) | (uint64_t)((u1 ? a1s : 0u) + (u2 ? a2s : 0u));
+        }
+        sites[s] = o;
+        flags[s] = fl;
+        scan_in[s] = scan;
+        atomicAdd(&s_cls[n_alleles], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && s_cls[threadIdx.x]) atomicAdd(class_counts + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
+}
+
+// ---- exclusive scan (3 phases) -------------------------------------------------------------------
+#define SCAN_BLOCK 1024
+__global__ void scan_block_sums(const uint64_t* __restrict__ in, int64_t n, uint64_t* __restrict__ sums) {
+    __shared__ uint64_t sh[32];
+    const int64_t i = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    uint64_t v = i < n ? in[i] : 0;
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = sh[threadIdx.x];
+        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) sums[blockIdx.x] = v;
+    }
+}
+__global__ void scan_sums_serial(uint64_t* sums, int64_t nb, uint64_t* total) {
+    // single block; nb <= a few thousand
+    __shared__ uint64_t sh[SCAN_BLOCK];
+    uint64_t carry = 0;
+    for (int64_t base = 0; base < nb; base += SCAN_BLOCK) {
+        const int64_t i = base + threadIdx.x;
+        uint64_t v = i < nb ? sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+            uint64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nb) sums[i] = carry + sh[threadIdx.x] - v;  // exclusive
+        const uint64_t blk_total = sh[SCAN_BLOCK - 1];
+        __syncthreads();
+        carry += blk_total;
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void scan_apply(const uint64_t* __restrict__ in, int64_t n, const uint64_t* __restrict__ sums, uint64_t* __restrict__ out) {
+    __shared__ uint64_t sh[SCAN_BLOCK];
+    const int64_t i = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint64_t v = i < n ? in[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+        uint64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (i < n) out[i] = sums[blockIdx.x] + sh[threadIdx.x] - v;
+}
+
+static uint64_t* g_scan_tmp = nullptr;  // per-process scratch (contexts are single-threaded per device)
+static int64_t g_scan_tmp_cap = 0;
+static int g_scan_tmp_dev = -1;
+
+int pbk_exclusive_scan_u64(pb_ctx* ctx, const uint64_t* in, uint64_t* out, int64_t n, uint64_t* d_total) {
+    const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (nb > g_scan_tmp_cap || g_scan_tmp_dev != ctx->device) {
+        if (g_scan_tmp && g_scan_tmp_dev == ctx->device) cudaFree(g_scan_tmp);
+        PB_CUDA(cudaMalloc(&g_scan_tmp, (size_t)(nb + 1) * 8));
+        g_scan_tmp_cap = nb;
+        g_scan_tmp_dev = ctx->device;
+    }
+    if (n == 0) { PB_CUDA(cudaMemsetAsync(d_total, 0, 8, ctx->stream)); return PB_OK; }
+    scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, g_scan_tmp);
+    scan_sums_serial<<<1, SCAN_BLOCK, 0, ctx->stream>>>(g_scan_tmp, nb, d_total);
+    scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, g_scan_tmp, out);
+    ctx->tm.n_launches += 3;
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// ---- informative-site compaction + CSR of extant events ---------------------------------------------
+__global__ void k1_scatter_sites_kernel(int64_t S, const uint8_t* __restrict__ flags, const uint64_t* __restrict__ scan,
+                                        const uint64_t* __restrict__ scan_in, const uint32_t* __restrict__ cnt,
+                                        const pb_site_out* __restrict__ sites, int32_t* __restrict__ inf_site, AlleleMeta* __restrict__ alleles,
+                                        unsigned long long* __restrict__ class_counts /* [5]=n_max, [6]=A_inuse */) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    if (!(scan_in[s] >> 38)) return;
+    const uint8_t fl = flags[s];
+    const int64_t i = (int64_t)(scan[s] >> 38);
+    const int64_t off = (int64_t)(scan[s] & ((1ull << 38) - 1));
+    const int a1 = (fl >> PB_SF_A1_CODE_SHIFT) & 3;
+    const uint32_t* c = cnt + s * PB_CNT_STRIDE;
+    const uint32_t xs_all = c[8] + c[9] + c[10] + c[11];
+    const bool u1 = fl & PB_SF_A1_USE, u2 = fl & PB_SF_A2_USE;
+    // an in-use allele keeps all its leaf events unless its bucket was emptied by the <2 rule
+    // (possible only with min_hcount == 0, where in_use does not imply a surviving bucket)
+    const pb_site_out so = sites[s];
+    const uint32_t n1 = (u1 && so.a1_count >= 2) ? c[8 + a1] : 0u, n2 = (u2 && so.a2_count >= 2) ? xs_all - c[8 + a1] : 0u;
+    inf_site[i] = (int32_t)s;
+    AlleleMeta m1{}, m2{};
+    m1.off = off; m1.n = (int32_t)n1; m1.flags = u1 ? PB_AF_IN_USE : 0;
+    m2.off = off + n1; m2.n = (int32_t)n2; m2.flags = u2 ? PB_AF_IN_USE : 0;
+    alleles[2 * i] = m1;
+    alleles[2 * i + 1] = m2;
+    atomicMax(class_counts + 5, (unsigned long long)max(n1, n2));
+    atomicAdd(class_counts + 6, (unsigned long long)((u1 ? 1 : 0) + (u2 ? 1 : 0)));
+}
+
+__global__ void k1_scatter_events_kernel(const raw_event_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ node_sample,
+                                         const uint8_t* __restrict__ flags, const uint64_t* __restrict__ scan,
+                                         const uint64_t* __restrict__ scan_in, const pb_site_out* __restrict__ sites,
+                                         const AlleleMeta* __restrict__ alleles, uint32_t* __restrict__ cursor, int32_t* __restrict__ csr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const raw_event_t e = raw[i];
+    const uint32_t hi = (uint32_t)(e >> 32);
+    if (!(hi & 0x80000000u)) return;                 // extant (leaf) events only (EXTANT_NODES_ONLY, HC.java:173)
+    const int32_t smp = node_sample[hi & PB_EV_NODE_MASK];
+    if (smp < 0) return;                              // leaf without a pheno row: never tallied (HC.java:3743)
+    const uint32_t site = (uint32_t)e;
+    if (!(scan_in[site] >> 38)) return;
+    const uint8_t fl = flags[site];
+    const uint32_t base = (hi >> 29) & 3u;
+    const int a = (base == ((fl >> PB_SF_A1_CODE_SHIFT) & 3u)) ? 0 : 1;
+    if (!(fl & (a == 0 ? PB_SF_A1_USE : PB_SF_A2_USE))) return;
+    // bucket emptied by the <2 rule?  (in_use with min_hcount 0 keeps n = 0)
+    const pb_site_out so = sites[site];
+    if ((a == 0 ? so.a1_count : so.a2_count) < 2) return;
+    const int64_t slot = 2 * (int64_t)(scan[site] >> 38) + a;
+    const uint32_t k = atomicAdd(cursor + slot, 1u);
+    csr[alleles[slot].off + k] = smp;
+}
+
+// =================================================================================================
+int pbk_events(pb_ctx* ctx) {
+    K1Params p;
+    p.B0 = ctx->d_B0; p.B1 = ctx->d_B1; p.V = ctx->d_V;
+    p.Wp = ctx->Wp; p.W = ctx->W;
+    p.leaf_ops = ctx->d_leaf_ops; p.int_ops = ctx->d_int_ops;
+    p.chunk_lg = ctx->d_chunk_lg; p.chunk_io = ctx->d_chunk_io;
+    p.census = ctx->d_census;
+    p.raw = ctx->d_raw; p.raw_cursor = ctx->d_raw_cursor; p.raw_cap = (unsigned long long)ctx->raw_cap;
+    const size_t smem = (size_t)PB_K1_QCAP * sizeof(raw_event_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(k1_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((ctx->W + PB_K1_THREADS - 1) / PB_K1_THREADS), (unsigned)ctx->n_chunks);
+    PB_CUDA(cudaMemsetAsync(ctx->d_raw_cursor, 0, 8, ctx->stream));
+    PB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    k1_events_kernel<<<grid, PB_K1_THREADS, smem, ctx->stream>>>(p);
+    PB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->tm.n_launches += 1;
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts) {
+    const int64_t S = ctx->S;
+    const int T = 256;
+    PB_CUDA(cudaMemsetAsync(ctx->d_cnt, 0, (size_t)S * PB_CNT_STRIDE * 4, ctx->stream));
+    PB_CUDA(cudaMemsetAsync(ctx->d_class_counts, 0, 16 * 8, ctx->stream));
+    if (ctx->n_raw > 0) {
+        k1_count_events_kernel<<<(unsigned)((ctx->n_raw + T - 1) / T), T, 0, ctx->stream>>>(ctx->d_raw, ctx->n_raw, ctx->d_node_sample, ctx->d_cnt);
+        ctx->tm.n_launches += 1;
+    }
+    k1_finalize_kernel<<<(unsigned)((S + T - 1) / T), T, 0, ctx->stream>>>(
+        ctx->d_census, ctx->n_chunks, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->d_cnt, ctx->cfg.min_hcount,
+        ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan /* reused as scan input */, ctx->d_class_counts);
+    ctx->tm.n_launches += 1;
+    PB_CUDA(cudaGetLastError());
+    // scan: d_site_scan (input) -> d_site_scan_out.  We keep input in the first half of a 2*S buffer.
+    uint64_t* scan_in = ctx->d_site_scan;
+    uint64_t* scan_out = ctx->d_site_scan + S;
+    int rc = pbk_exclusive_scan_u64(ctx, scan_in, scan_out, S, (uint64_t*)(ctx->d_class_counts + 7));
+    if (rc) return rc;
+    unsigned long long h[16];
+    PB_CUDA(cudaMemcpyAsync(h, ctx->d_class_counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->S_inf = (int64_t)(h[7] >> 38);
+    ctx->E = (int64_t)(h[7] & ((1ull << 38) - 1));
+    if (counts) {
+        counts->n_no_allele = (int64_t)h[0]; counts->n_mono = (int64_t)h[1]; counts->n_bi = (int64_t)h[2];
+        counts->n_tri = (int64_t)h[3]; counts->n_quad = (int64_t)h[4]; counts->n_raw_events = ctx->n_raw;
+    }
+    // (re)allocate compaction outputs
+    if (ctx->S_inf > ctx->inf_cap) {
+        cudaFree(ctx->d_inf_site); cudaFree(ctx->d_alleles); cudaFree(ctx->d_csr_cursor); cudaFree(ctx->d_pobs); cudaFree(ctx->d_r);
+        ctx->d_inf_site = nullptr; ctx->d_alleles = nullptr; ctx->d_csr_cursor = nullptr; ctx->d_pobs = nullptr; ctx->d_r = nullptr;
+        const int64_t cap = ctx->S_inf + ctx->S_inf / 8 + 1024;
+        PB_CUDA(cudaMalloc(&ctx->d_inf_site, (size_t)cap * 4));
+        PB_CUDA(cudaMalloc(&ctx->d_alleles, (size_t)cap * 2 * sizeof(AlleleMeta)));
+        PB_CUDA(cudaMalloc(&ctx->d_csr_cursor, (size_t)cap * 2 * 4));
+        PB_CUDA(cudaMalloc(&ctx->d_pobs, (size_t)cap * 2 * 8));
+        PB_CUDA(cudaMalloc(&ctx->d_r, (size_t)cap * 2 * 4));
+        ctx->inf_cap = cap;
+    }
+    if (ctx->E > ctx->csr_cap) {
+        cudaFree(ctx->d_csr); ctx->d_csr = nullptr;
+        const int64_t cap = ctx->E + ctx->E / 8 + 1024;
+        PB_CUDA(cudaMalloc(&ctx->d_csr, (size_t)cap * 4));
+        ctx->csr_cap = cap;
+    }
+    ctx->n_max = 0; ctx->A_inuse = 0;
+    if (ctx->S_inf > 0) {
+        PB_CUDA(cudaMemsetAsync(ctx->d_csr_cursor, 0, (size_t)ctx->S_inf * 2 * 4, ctx->stream));
+        k1_scatter_sites_kernel<<<(unsigned)((S + T - 1) / T), T, 0, ctx->stream>>>(S, ctx->d_site_flags, scan_out, scan_in, ctx->d_cnt,
+                                                                                   ctx->d_sites, ctx->d_inf_site, ctx->d_alleles, ctx->d_class_counts);
+        ctx->tm.n_launches += 1;
+        if (ctx->n_raw > 0) {
+            k1_scatter_events_kernel<<<(unsigned)((ctx->n_raw + T - 1) / T), T, 0, ctx->stream>>>(
+                ctx->d_raw, ctx->n_raw, ctx->d_node_sample, ctx->d_site_flags, scan_out, scan_in, ctx->d_sites, ctx->d_alleles,
+                ctx->d_csr_cursor, ctx->d_csr);
+            ctx->tm.n_launches += 1;
+        }
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaMemcpyAsync(h, ctx->d_class_counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->n_max = (int32_t)h[5];
+        ctx->A_inuse = (int64_t)h[6];
+    }
+    return PB_OK;
+}

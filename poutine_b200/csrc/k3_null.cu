@@ -1,0 +1,443 @@
+// K2 + K3 — observed tallies and the phenotype-permutation null (sm_100a).
+//
+// Replaces count_homoplasies/counts_by_allele (HC.java:3695-3761), Replicate.run
+// (HC.java:3229-3272), permute_phenos (HC.java:4890-4923) and
+// calc_binomial_test_stats_memoization_concurrent (HC.java:4196-4280).
+//
+// Reference semantics per replicate: permute the P pheno-file labels uniformly over the P samples,
+// recount (n_r, k_r) = (#labelled, #case) over each in-use allele's extant MRCA leaves, look up
+// p_r = f(n_r, k_r) (one-sided binomial, commons-math), r_a += (p_r <= p_obs), maxT[rep] = min p_r.
+//
+// B200 design: replicates are bit-parallel.
+//   K3a  builds the label bit-matrix X[sample][replicate] (64 replicates per word), either from
+//        counter-based Philox4x32-10 streams (one thread = one replicate, sequential draw without
+//        replacement, warp ballot -> words) or from explicit replay permutations.
+//   K3b  one warp = 32 words (2048 replicates) x a chunk of alleles.  Per allele the n sample rows are
+//        gathered (coalesced 256 B per row, L2-resident) and summed with bit-sliced vertical
+//        counters; "p_r <= p_obs" is a bit-sliced compare k_r >= k* (valid because f(n,.) is checked
+//        to be an up-set on the host of the table), popcounted and warp-reduced (REDUX) into one
+//        atomic per allele per 2048 replicates.  maxT uses a candidate threshold tau: only replicates
+//        whose p-value can be <= tau are extracted to scalars and atomically min-ed; replicates left
+//        without a candidate are recomputed exactly by a fallback kernel.
+//        Replicates in which one of the allele's leaves drew a *missing* label (n_r < n) and alleles
+//        whose table row is not monotone take the exact scalar path bit by bit.
+#include "pb_internal.h"
+
+// ---------------------------------------------------------------------------------------------------
+// K2: observed tallies
+// ---------------------------------------------------------------------------------------------------
+__global__ void k2_tally_kernel(AlleleMeta* __restrict__ alleles, int64_t n_slots, const int32_t* __restrict__ csr,
+                                const uint8_t* __restrict__ label) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_slots) return;
+    AlleleMeta m = alleles[a];
+    int cs = 0, ct = 0;
+    if (m.flags & PB_AF_IN_USE)
+        for (int e = 0; e < m.n; e++) {
+            const uint8_t l = label[csr[m.off + e]];
+            cs += l == PB_LABEL_CASE;    // pheno.equals("1") -> case   (HC.java:3747)
+            ct += l == PB_LABEL_CONTROL; // pheno.equals("0") -> control (HC.java:3749)
+        }
+    alleles[a].obs_case = cs;
+    alleles[a].obs_ctrl = ct;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3a: label bit-matrix
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+#define GEN_THREADS 256
+#define GEN_ROWS 128
+
+// mode 0: Philox (sampling spec in DESIGN.md §K3a; restated by oracle/oracle.cpp or_philox_labels)
+// mode 1: replay (sample j gets label[perms[rep*P + j]])
+template <int MODE>
+__global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
+                                                             int32_t n_ctrl, const uint8_t* __restrict__ label,
+                                                             const uint32_t* __restrict__ perms, uint32_t* __restrict__ Xc32,
+                                                             uint32_t* __restrict__ Xm32, int64_t Rw32) {
+    __shared__ uint32_t sc[GEN_ROWS][8], sm[GEN_ROWS][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t rep_local = (int64_t)blockIdx.x * GEN_THREADS + tid;
+    const bool active = rep_local < n_reps;
+    const uint64_t rep = (uint64_t)(rep_base + rep_local);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), r0 = (uint32_t)rep, r1 = (uint32_t)(rep >> 32);
+    uint32_t rem_case = (uint32_t)n_case, rem_ctrl = (uint32_t)n_ctrl, q = 0;
+    uint32_t w[4] = {0, 0, 0, 0};
+    const uint32_t* prow = (MODE == 1 && active) ? perms + rep_local * (int64_t)P : nullptr;
+
+    for (int i0 = 0; i0 < P; i0 += GEN_ROWS) {
+        const int rows = min(GEN_ROWS, P - i0);
+        for (int ii = 0; ii < rows; ii++) {
+            const int i = i0 + ii;
+            uint32_t lab;
+            if (MODE == 0) {
+                if ((i & 3) == 0) philox4x32_10((uint32_t)(i >> 2), r0, r1, 0u, k0, k1, w);
+                const uint32_t range = (uint32_t)(P - i);
+                uint32_t x = w[i & 3];
+                uint64_t prod = (uint64_t)x * range;
+                uint32_t lo = (uint32_t)prod;
+                if (lo < range) {  // Lemire: exact rejection, taken with probability < range / 2^32
+                    const uint32_t t = (0u - range) % range;
+                    while (lo < t) {
+                        uint32_t rw[4];
+                        philox4x32_10(q >> 2, r0, r1, 1u, k0, k1, rw);
+                        x = rw[q & 3];
+                        q++;
+                        prod = (uint64_t)x * range;
+                        lo = (uint32_t)prod;
+                    }
+                }
+                const uint32_t u = (uint32_t)(prod >> 32);
+                if (u < rem_case) { lab = 1; rem_case--; }
+                else if (u < rem_case + rem_ctrl) { lab = 0; rem_ctrl--; }
+                else lab = 2;
+            } else {
+                lab = active ? label[prow[i]] : 0;
+            }
+            const uint32_t bc = __ballot_sync(0xffffffffu, active && lab == 1);
+            const uint32_t bm = __ballot_sync(0xffffffffu, active && lab == 2);
+            if (lane == 0) { sc[ii][warp] = bc; sm[ii][warp] = bm; }
+        }
+        __syncthreads();
+        for (int t = tid; t < rows * 8; t += GEN_THREADS) {
+            const int row = t >> 3, wd = t & 7;
+            const int64_t o = (int64_t)(i0 + row) * Rw32 + (int64_t)blockIdx.x * 8 + wd;
+            Xc32[o] = sc[row][wd];
+            if (Xm32) Xm32[o] = sm[row][wd];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3b: replicate counting
+// ---------------------------------------------------------------------------------------------------
+struct K3Params {
+    const AlleleMeta* __restrict__ alleles;
+    int64_t n_slots;
+    int32_t slots_per_chunk;
+    const int32_t* __restrict__ csr;
+    const double* __restrict__ pobs;      // [n_slots]
+    const double* __restrict__ ptable;    // triangular
+    const int32_t* __restrict__ ktau;     // [n_max+1]
+    const double* __restrict__ tau;
+    const uint64_t* __restrict__ Xc;
+    const uint64_t* __restrict__ Xm;      // nullptr when the pheno file has no missing labels
+    int64_t Rw;                           // pitch in 64-bit words
+    int64_t rep_base, n_reps;             // this tile
+    uint32_t* __restrict__ r;
+    unsigned long long* __restrict__ maxT;  // [m] double bits, global replicate index
+};
+
+template <int NB>
+__device__ __forceinline__ uint64_t ge_const(const uint64_t (&c)[NB], int T) {
+    // bit-sliced (k >= T) for a warp-uniform constant 0 < T < 2^NB
+    uint64_t gt = 0, eq = ~0ull;
+#pragma unroll
+    for (int j = NB - 1; j >= 0; j--) {
+        if ((T >> j) & 1) eq &= c[j];
+        else { gt |= eq & c[j]; eq &= ~c[j]; }
+    }
+    return gt | eq;
+}
+
+template <int NB>
+__device__ __forceinline__ int extract(const uint64_t (&c)[NB], int b) {
+    int v = 0;
+#pragma unroll
+    for (int j = 0; j < NB; j++) v |= (int)((c[j] >> b) & 1ull) << j;
+    return v;
+}
+
+template <int NB>
+__device__ __forceinline__ void process_allele(const K3Params& p, const AlleleMeta& m, int64_t slot, int64_t word, uint64_t valid,
+                                               double tau) {
+    const int n = m.n;
+    uint64_t c[NB], u[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) { c[j] = 0; u[j] = 0; }
+    const int32_t* __restrict__ ev = p.csr + m.off;
+    const bool has_miss = p.Xm != nullptr;
+    if (valid) {
+        for (int e = 0; e < n; e++) {
+            const int64_t o = (int64_t)ev[e] * p.Rw + word;
+            uint64_t x = p.Xc[o];
+#pragma unroll
+            for (int j = 0; j < NB; j++) { const uint64_t t = c[j] & x; c[j] ^= x; x = t; }
+            if (has_miss) {
+                uint64_t y = p.Xm[o];
+#pragma unroll
+                for (int j = 0; j < NB; j++) { const uint64_t t = u[j] & y; u[j] ^= y; y = t; }
+            }
+        }
+    }
+    uint64_t exc = 0;
+    if (has_miss) {
+#pragma unroll
+        for (int j = 0; j < NB; j++) exc |= u[j];
+    }
+    const bool fast = m.flags & PB_AF_FAST;
+    if (!fast) exc = ~0ull;
+    exc &= valid;
+    const uint64_t fastmask = valid & ~exc;
+    const double pobs = p.pobs[slot];
+    const int kstar = m.kstar;
+    uint64_t ge = (kstar <= 0) ? ~0ull : (kstar > n ? 0ull : ge_const<NB>(c, kstar));
+    unsigned int rcount = (unsigned int)__popcll(ge & fastmask);
+    const int kt = p.ktau[n];
+    uint64_t cand = (kt <= 0) ? ~0ull : (kt > n ? 0ull : ge_const<NB>(c, kt));
+    uint64_t todo = (cand & fastmask) | exc;
+    const double* __restrict__ row_n = p.ptable + (int64_t)n * (n + 1) / 2;
+    while (todo) {
+        const int b = __ffsll((long long)todo) - 1;
+        todo &= todo - 1;
+        const int k = extract<NB>(c, b);
+        double pv;
+        if ((exc >> b) & 1ull) {
+            const int nr = n - (has_miss ? extract<NB>(u, b) : 0);
+            pv = p.ptable[(int64_t)nr * (nr + 1) / 2 + k];
+            rcount += (pv <= pobs) ? 1u : 0u;   // HC.java:4239 / 4273
+        } else {
+            pv = row_n[k];
+        }
+        if (pv <= tau) atomicMin(p.maxT + (p.rep_base + word * 64 + b), (unsigned long long)__double_as_longlong(pv));
+    }
+    rcount = __reduce_add_sync(0xffffffffu, rcount);
+    if ((threadIdx.x & 31) == 0 && rcount) atomicAdd(p.r + slot, rcount);
+}
+
+#define K3_THREADS 128
+__global__ void __launch_bounds__(K3_THREADS) k3_count_kernel(const K3Params p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t word = ((int64_t)blockIdx.x * (K3_THREADS / 32) + warp) * 32 + lane;
+    const int64_t rep0 = word * 64;  // tile-local
+    uint64_t valid = 0;
+    if (rep0 < p.n_reps) valid = (p.n_reps - rep0 >= 64) ? ~0ull : ((1ull << (p.n_reps - rep0)) - 1);
+    if (__all_sync(0xffffffffu, valid == 0)) return;
+    const double tau = *p.tau;
+    const int64_t s0 = (int64_t)blockIdx.y * p.slots_per_chunk;
+    const int64_t s1 = min(p.n_slots, s0 + p.slots_per_chunk);
+    for (int64_t slot = s0; slot < s1; slot++) {
+        const AlleleMeta m = p.alleles[slot];
+        if (!(m.flags & PB_AF_IN_USE)) continue;
+        const int n = m.n;
+        if (n < 2) process_allele<1>(p, m, slot, word, valid, tau);
+        else if (n < 4) process_allele<2>(p, m, slot, word, valid, tau);
+        else if (n < 8) process_allele<3>(p, m, slot, word, valid, tau);
+        else if (n < 16) process_allele<4>(p, m, slot, word, valid, tau);
+        else if (n < 32) process_allele<5>(p, m, slot, word, valid, tau);
+        else if (n < 64) process_allele<6>(p, m, slot, word, valid, tau);
+        else if (n < 256) process_allele<8>(p, m, slot, word, valid, tau);
+        else if (n < 4096) process_allele<12>(p, m, slot, word, valid, tau);
+        else process_allele<17>(p, m, slot, word, valid, tau);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// maxT fallback: replicates whose min could not be certified (> tau) are recomputed exactly
+// ---------------------------------------------------------------------------------------------------
+__global__ void k3_collect_fallback_kernel(const unsigned long long* __restrict__ maxT, int64_t rep_base, int64_t n_reps,
+                                           const double* __restrict__ tau, int32_t* __restrict__ list, unsigned int* __restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reps) return;
+    const double v = __longlong_as_double((long long)maxT[rep_base + i]);
+    if (!(v <= *tau)) list[atomicAdd(count, 1u)] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(256) k3_fallback_kernel(const K3Params p, const int32_t* __restrict__ list) {
+    __shared__ double smin[256];
+    const int64_t rl = list[blockIdx.x];
+    const int64_t word = rl >> 6;
+    const int b = (int)(rl & 63);
+    double best = __longlong_as_double(0x7FF0000000000000ll);
+    for (int64_t slot = threadIdx.x; slot < p.n_slots; slot += blockDim.x) {
+        const AlleleMeta m = p.alleles[slot];
+        if (!(m.flags & PB_AF_IN_USE)) continue;
+        int k = 0, u = 0;
+        for (int e = 0; e < m.n; e++) {
+            const int64_t o = (int64_t)p.csr[m.off + e] * p.Rw + word;
+            k += (int)((p.Xc[o] >> b) & 1ull);
+            if (p.Xm) u += (int)((p.Xm[o] >> b) & 1ull);
+        }
+        const int nr = m.n - u;
+        const double pv = p.ptable[(int64_t)nr * (nr + 1) / 2 + k];
+        best = fmin(best, pv);
+    }
+    smin[threadIdx.x] = best;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) smin[threadIdx.x] = fmin(smin[threadIdx.x], smin[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) p.maxT[p.rep_base + rl] = (unsigned long long)__double_as_longlong(smin[0]);
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, int64_t n, unsigned long long v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ===================================================================================================
+static int ensure(pb_ctx* ctx, void** ptr, int64_t* cap, int64_t need_bytes) {
+    if (need_bytes <= *cap) return PB_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    const int64_t bytes = need_bytes + need_bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+        *cap = 0;
+        return PB_ERR_OOM;
+    }
+    *cap = bytes;
+    return PB_OK;
+}
+
+int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
+    const int64_t m = ctx->cfg.n_replicates;
+    const int64_t n_slots = 2 * ctx->S_inf;
+    const int T = 256;
+    cudaStream_t st = ctx->stream;
+    int rc;
+
+    // ---- K2 observed tallies
+    PB_CUDA(cudaEventRecord(ctx->ev[2], st));
+    k2_tally_kernel<<<(unsigned)((n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_csr, ctx->d_label);
+    ctx->tm.n_launches += 1;
+    PB_CUDA(cudaEventRecord(ctx->ev[3], st));
+
+    // ---- p-table, observed p-values, thresholds
+    if ((rc = pbk_ptable(ctx))) return rc;
+    if ((rc = pbk_thresholds(ctx))) return rc;
+    PB_CUDA(cudaEventRecord(ctx->ev[4], st));
+
+    // ---- null distribution, tiled over replicates
+    {
+        int64_t mcap_bytes = ctx->maxT_cap * 8;
+        void* pm = ctx->d_maxT;
+        if ((rc = ensure(ctx, &pm, &mcap_bytes, m * 8))) return rc;
+        ctx->d_maxT = (unsigned long long*)pm; ctx->maxT_cap = mcap_bytes / 8;
+    }
+    fill_u64_kernel<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(ctx->d_maxT, m, 0x7FF0000000000000ull);
+    PB_CUDA(cudaMemsetAsync(ctx->d_r, 0, (size_t)n_slots * 4, st));
+    ctx->tm.n_launches += 1;
+
+    const bool has_miss = ctx->n_miss > 0;
+    // tile size: keep each label matrix <= 4 GiB and a multiple of 2048 replicates
+    int64_t tile = (int64_t)((4ll << 30) / ((int64_t)ctx->P / 8 + 1));
+    tile = (tile / 2048) * 2048;
+    if (tile < 2048) tile = 2048;
+    const int64_t m_pad = ((m + 255) / 256) * 256;
+    if (tile > m_pad) tile = m_pad;
+    const int64_t Rw32 = ((tile + 255) / 256) * 8;  // uint32 pitch
+    const int64_t Rw = Rw32 / 2;
+    {
+        const int64_t need = (int64_t)ctx->P * Rw * 8;
+        void* pc = ctx->d_Xcase;
+        if ((rc = ensure(ctx, &pc, &ctx->X_cap, need))) { ctx->d_Xcase = nullptr; return rc; }
+        ctx->d_Xcase = (uint64_t*)pc;
+        if (has_miss) {
+            void* pmx = ctx->d_Xmiss;
+            if ((rc = ensure(ctx, &pmx, &ctx->Xm_cap, need))) { ctx->d_Xmiss = nullptr; return rc; }
+            ctx->d_Xmiss = (uint64_t*)pmx;
+        }
+        void* pl = ctx->d_fb_reps;
+        if ((rc = ensure(ctx, &pl, &ctx->fb_cap, (tile + 256) * 4))) { ctx->d_fb_reps = nullptr; return rc; }
+        ctx->d_fb_reps = (int32_t*)pl;
+    }
+    float ms_gen = 0, ms_cnt = 0, ms_fb = 0;
+    ctx->tm.n_maxt_fallback_reps = 0;
+    for (int64_t base = 0; base < m; base += tile) {
+        const int64_t nr = (m - base < tile) ? (m - base) : tile;
+        const unsigned gblocks = (unsigned)((nr + GEN_THREADS - 1) / GEN_THREADS);
+        PB_CUDA(cudaEventRecord(ctx->ev[5], st));
+        if (ctx->cfg.mode == PB_MODE_REPLAY) {
+            const int64_t bytes = nr * (int64_t)ctx->P * 4;
+            int64_t cap = ctx->perms_cap;
+            void* pp = ctx->d_perms;
+            if ((rc = ensure(ctx, &pp, &cap, bytes))) { ctx->d_perms = nullptr; ctx->perms_cap = 0; return rc; }
+            ctx->d_perms = (uint32_t*)pp; ctx->perms_cap = cap;
+            PB_CUDA(cudaMemcpyAsync(ctx->d_perms, replay_perms + base * (int64_t)ctx->P, (size_t)bytes, cudaMemcpyHostToDevice, st));
+            k3_gen_kernel<1><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
+                                                             ctx->d_perms, (uint32_t*)ctx->d_Xcase,
+                                                             has_miss ? (uint32_t*)ctx->d_Xmiss : nullptr, Rw32);
+        } else {
+            k3_gen_kernel<0><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
+                                                             nullptr, (uint32_t*)ctx->d_Xcase,
+                                                             has_miss ? (uint32_t*)ctx->d_Xmiss : nullptr, Rw32);
+        }
+        ctx->tm.n_launches += 1;
+        PB_CUDA(cudaEventRecord(ctx->ev[6], st));
+
+        K3Params p;
+        p.alleles = ctx->d_alleles; p.n_slots = n_slots; p.csr = ctx->d_csr; p.pobs = ctx->d_pobs; p.ptable = ctx->d_ptable;
+        p.ktau = ctx->d_ktau; p.tau = ctx->d_tau; p.Xc = ctx->d_Xcase; p.Xm = has_miss ? ctx->d_Xmiss : nullptr; p.Rw = Rw;
+        p.rep_base = base; p.n_reps = nr; p.r = ctx->d_r; p.maxT = ctx->d_maxT;
+        const int64_t words = (nr + 63) / 64;
+        const unsigned gx = (unsigned)((words + (K3_THREADS / 32) * 32 - 1) / ((K3_THREADS / 32) * 32));
+        int64_t want_blocks = (int64_t)ctx->sm_count * 32;
+        int64_t gy = (want_blocks + gx - 1) / gx;
+        if (gy < 1) gy = 1;
+        int64_t spc = (n_slots + gy - 1) / gy;
+        if (spc < 64) spc = 64;
+        spc = (spc + 1) & ~1ll;
+        gy = (n_slots + spc - 1) / spc;
+        if (gy > 65535) { gy = 65535; spc = ((n_slots + gy - 1) / gy + 1) & ~1ll; gy = (n_slots + spc - 1) / spc; }
+        p.slots_per_chunk = (int32_t)spc;
+        k3_count_kernel<<<dim3(gx, (unsigned)gy), K3_THREADS, 0, st>>>(p);
+        ctx->tm.n_launches += 1;
+        PB_CUDA(cudaEventRecord(ctx->ev[7], st));
+
+        // fallback for uncertified replicates
+        PB_CUDA(cudaMemsetAsync(ctx->d_fb_count, 0, 4, st));
+        k3_collect_fallback_kernel<<<(unsigned)((nr + T - 1) / T), T, 0, st>>>(ctx->d_maxT, base, nr, ctx->d_tau, ctx->d_fb_reps, ctx->d_fb_count);
+        ctx->tm.n_launches += 1;
+        unsigned int n_fb = 0;
+        PB_CUDA(cudaMemcpyAsync(&n_fb, ctx->d_fb_count, 4, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        if (n_fb) {
+            k3_fallback_kernel<<<n_fb, 256, 0, st>>>(p, ctx->d_fb_reps);
+            ctx->tm.n_launches += 1;
+            ctx->tm.n_maxt_fallback_reps += n_fb;
+        }
+        PB_CUDA(cudaEventRecord(ctx->ev[8], st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        PB_CUDA(cudaGetLastError());
+        float t;
+        cudaEventElapsedTime(&t, ctx->ev[5], ctx->ev[6]); ms_gen += t;
+        cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]); ms_cnt += t;
+        cudaEventElapsedTime(&t, ctx->ev[7], ctx->ev[8]); ms_fb += t;
+    }
+    ctx->tm.ms_null_gen = ms_gen; ctx->tm.ms_null_count = ms_cnt; ctx->tm.ms_null_fallback = ms_fb;
+
+    // ---- the one collective: all-reduce(min) of maxT over site shards
+    PB_CUDA(cudaEventRecord(ctx->ev[9], st));
+    if (ctx->world > 1) {
+        if ((rc = pbn_allreduce_min_f64(ctx, (double*)ctx->d_maxT, m))) return rc;
+    }
+    PB_CUDA(cudaEventRecord(ctx->ev[10], st));
+
+    // ---- K4
+    if ((rc = pbk_pvalues(ctx))) return rc;
+    PB_CUDA(cudaEventRecord(ctx->ev[11], st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    float t;
+    cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]); ctx->tm.ms_tally = t;
+    cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4]); ctx->tm.ms_ptable = t;
+    cudaEventElapsedTime(&t, ctx->ev[9], ctx->ev[10]); ctx->tm.ms_allreduce = t;
+    cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[11]); ctx->tm.ms_pvalues = t;
+    cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[11]); ctx->tm.ms_assoc_total = t;
+    return PB_OK;
+}

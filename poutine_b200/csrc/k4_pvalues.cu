@@ -1,0 +1,269 @@
+// K4 — binomial p-value table, observed statistics, thresholds, and the point-wise / family-wise
+// empirical p-values (sm_100a; FP64, compiled with --fmad=false).
+//
+// Replaces: observed binomialTest calls (HC.java:3047-3057), the "n_k" p-value cache
+// (HC.java:4226-4236), calc_pointwise_estimate_binom (HC.java:4812-4838) and
+// calc_familywise_estimates_binom_combined_nulldists (HC.java:4558-4654).
+#include "binom_device.cuh"
+#include "pb_internal.h"
+
+// ---- f[n][k] = binomialTest(n, k, p, GREATER_THAN), triangular layout n*(n+1)/2 + k -------------
+__global__ void k4_ptable_kernel(double* __restrict__ tab, int32_t n_max, double p) {
+    const int64_t total = (int64_t)(n_max + 1) * (n_max + 2) / 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    // invert idx = n(n+1)/2 + k
+    int64_t n = (int64_t)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while (n * (n + 1) / 2 > idx) n--;
+    while ((n + 1) * (n + 2) / 2 <= idx) n++;
+    const int k = (int)(idx - n * (n + 1) / 2);
+    tab[idx] = pbm::binomial_test_greater((int)n, k, p);
+}
+
+// ---- observed p-value, k* and the n-histogram -------------------------------------------------------
+__global__ void k4_observed_kernel(AlleleMeta* __restrict__ alleles, int64_t n_slots, const double* __restrict__ tab,
+                                   double* __restrict__ pobs, unsigned int* __restrict__ n_hist, int force_general,
+                                   unsigned long long* __restrict__ n_fast) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_slots) return;
+    AlleleMeta m = alleles[a];
+    if (!(m.flags & PB_AF_IN_USE)) {
+        pobs[a] = __longlong_as_double(0x7FF8000000000000ll);  // Double.NaN sentinel (HC.java:5891-5906)
+        return;
+    }
+    const int no = m.obs_case + m.obs_ctrl;
+    const double po = tab[(int64_t)no * (no + 1) / 2 + m.obs_case];  // HC.java:3050 / 3056
+    pobs[a] = po;
+    atomicAdd(n_hist + m.n, 1u);
+    // k* = min{k : f(n,k) <= p_obs}; fast path only if {k : f(n,k) <= p_obs} = [k*, n]
+    const double* row = tab + (int64_t)m.n * (m.n + 1) / 2;
+    int kstar = m.n + 1;
+    bool upset = true;
+    for (int k = 0; k <= m.n; k++) {
+        const bool le = row[k] <= po;
+        if (le && kstar > m.n) kstar = k;
+        if (!le && kstar <= m.n) upset = false;
+    }
+    uint32_t fl = m.flags & ~PB_AF_FAST;
+    if (upset && !force_general) { fl |= PB_AF_FAST; atomicAdd(n_fast, 1ull); }
+    alleles[a].flags = fl;
+    alleles[a].kstar = kstar;
+}
+
+// ---- candidate threshold tau for the maxT pass ----------------------------------------------------
+// expected #candidate alleles per replicate at tau_j = 2^-j:  sum_n hist[n] * f(n, ktau_n(tau_j))
+#define TAU_LEVELS 64
+__global__ void k4_tau_expect_kernel(const double* __restrict__ tab, const unsigned int* __restrict__ n_hist, int32_t n_max,
+                                     double* __restrict__ expect) {
+    __shared__ double sh[256];
+    const int j = blockIdx.x;
+    const double tau = ldexp(1.0, -j);
+    double acc = 0;
+    for (int n = threadIdx.x; n <= n_max; n += blockDim.x) {
+        const unsigned int h = n_hist[n];
+        if (!h) continue;
+        const double* row = tab + (int64_t)n * (n + 1) / 2;
+        for (int k = 0; k <= n; k++)
+            if (row[k] <= tau) { acc += (double)h * row[k]; break; }
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) expect[j] = sh[0];
+}
+__global__ void k4_tau_pick_kernel(const double* __restrict__ expect, double target, double user_tau, double* __restrict__ tau) {
+    if (user_tau > 0) { *tau = user_tau; return; }
+    int best = 0;
+    for (int j = 0; j < TAU_LEVELS; j++)
+        if (expect[j] >= target) best = j;
+    *tau = ldexp(1.0, -best);
+}
+// ktau[n] = min{k : f(n,k) <= tau} (n+1 if none): {k >= ktau[n]} is a superset of {k : f(n,k) <= tau}
+__global__ void k4_ktau_kernel(const double* __restrict__ tab, int32_t n_max, const double* __restrict__ tau, int32_t* __restrict__ ktau) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n > n_max) return;
+    const double t = *tau;
+    const double* row = tab + (int64_t)n * (n + 1) / 2;
+    int kt = n + 1;
+    for (int k = 0; k <= n; k++)
+        if (row[k] <= t) { kt = k; break; }
+    ktau[n] = kt;
+}
+
+// ---- bitonic sort of maxT (m doubles in [0,1]; padded with +inf to a power of two) -----------------
+__global__ void k4_sort_init_kernel(const unsigned long long* __restrict__ maxT, int64_t m, int64_t n_pad, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) out[i] = i < m ? __longlong_as_double((long long)maxT[i]) : __longlong_as_double(0x7FF0000000000000ll);
+}
+__global__ void k4_bitonic_step_kernel(double* __restrict__ a, int64_t n_pad, int64_t j, int64_t k) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    const int64_t l = i ^ j;
+    if (l > i) {
+        const double x = a[i], y = a[l];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) { a[i] = y; a[l] = x; }
+    }
+}
+// all steps with j < 1024 of one k-phase, inside shared memory (2048 elements per block)
+#define BSORT_TILE 2048
+__global__ void __launch_bounds__(1024) k4_bitonic_smem_kernel(double* __restrict__ a, int64_t k, int64_t j_start) {
+    __shared__ double sh[BSORT_TILE];
+    const int64_t base = (int64_t)blockIdx.x * BSORT_TILE;
+    sh[threadIdx.x] = a[base + threadIdx.x];
+    sh[threadIdx.x + 1024] = a[base + threadIdx.x + 1024];
+    __syncthreads();
+    for (int64_t j = j_start; j > 0; j >>= 1) {
+        // each thread handles one compare-exchange pair
+        const int t = threadIdx.x;
+        const int lo = (int)(((t / j) * 2 * j) + (t % j));
+        const int hi = lo + (int)j;
+        const double x = sh[lo], y = sh[hi];
+        const bool up = ((base + lo) & k) == 0;
+        if ((x > y) == up) { sh[lo] = y; sh[hi] = x; }
+        __syncthreads();
+    }
+    a[base + threadIdx.x] = sh[threadIdx.x];
+    a[base + threadIdx.x + 1024] = sh[threadIdx.x + 1024];
+}
+
+// ---- final per-site statistics -----------------------------------------------------------------------
+__global__ void k4_stats_kernel(const int32_t* __restrict__ inf_site, int64_t S_inf, const AlleleMeta* __restrict__ alleles,
+                                const double* __restrict__ pobs, const uint32_t* __restrict__ r, const double* __restrict__ maxT_sorted,
+                                int64_t m, int64_t site_offset, pb_stat_out* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S_inf) return;
+    const double NaN = __longlong_as_double(0x7FF8000000000000ll);
+    pb_stat_out o;
+    o.site_index = inf_site[i];
+    o.segsite_id = (int32_t)(site_offset + inf_site[i] + 1);
+    int32_t rr[2], rm[2];
+    double pw[2], fw[2], po[2];
+    for (int a = 0; a < 2; a++) {
+        const AlleleMeta mt = alleles[2 * i + a];
+        const bool use = mt.flags & PB_AF_IN_USE;
+        o.obs_counts[2 * a] = use ? mt.obs_case : 0;
+        o.obs_counts[2 * a + 1] = use ? mt.obs_ctrl : 0;
+        if (!use) { rr[a] = -1; rm[a] = -1; pw[a] = fw[a] = po[a] = NaN; continue; }
+        po[a] = pobs[2 * i + a];
+        rr[a] = (int32_t)r[2 * i + a];
+        pw[a] = ((double)(rr[a] + 1)) / ((double)(m + 1));  // HC.java:4829-4833
+        // r_maxT = #{rep : maxT[rep] <= p_obs}  (HC.java:4630): upper bound in the sorted array
+        int64_t lo = 0, hi = m;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (maxT_sorted[mid] <= po[a]) lo = mid + 1; else hi = mid;
+        }
+        rm[a] = (int32_t)lo;
+        fw[a] = ((double)lo + 1) / ((double)m + 1);        // HC.java:4632
+    }
+    o.a1_in_use = (alleles[2 * i].flags & PB_AF_IN_USE) ? 1 : 0;
+    o.a2_in_use = (alleles[2 * i + 1].flags & PB_AF_IN_USE) ? 1 : 0;
+    o.r_a1 = rr[0]; o.r_a2 = rr[1]; o.r_maxT_a1 = rm[0]; o.r_maxT_a2 = rm[1];
+    o.obs_p_a1 = po[0]; o.obs_p_a2 = po[1]; o.pointwise_a1 = pw[0]; o.pointwise_a2 = pw[1];
+    o.familywise_a1 = fw[0]; o.familywise_a2 = fw[1];
+    out[i] = o;
+}
+
+// =====================================================================================================
+static int ensure_bytes(pb_ctx* ctx, void** ptr, int64_t* cap, int64_t need) {
+    if (need <= *cap) return PB_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    const int64_t bytes = need + need / 8 + 256;
+    cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); *cap = 0; return PB_ERR_OOM; }
+    *cap = bytes;
+    return PB_OK;
+}
+
+int pbk_ptable(pb_ctx* ctx) {
+    // table rows 0..n_max for this context's p (the table is a pure function of (n_max, p): cached)
+    const int32_t n_max = ctx->n_max;
+    const double p = (double)ctx->n_case / (double)(ctx->n_case + ctx->n_ctrl);  // calc_background_p_success (HC.java:3335)
+    if (ctx->ptable_nmax >= n_max && ctx->p_success == p && ctx->d_ptable) return PB_OK;
+    ctx->p_success = p;
+    const int64_t total = (int64_t)(n_max + 1) * (n_max + 2) / 2;
+    int rc;
+    int64_t cap = ctx->ptable_cap;
+    void* pt = ctx->d_ptable;
+    if ((rc = ensure_bytes(ctx, &pt, &cap, total * 8))) { ctx->d_ptable = nullptr; ctx->ptable_cap = 0; return rc; }
+    ctx->d_ptable = (double*)pt; ctx->ptable_cap = cap;
+    k4_ptable_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ptable, n_max, p);
+    ctx->tm.n_launches += 1;
+    PB_CUDA(cudaGetLastError());
+    ctx->ptable_nmax = n_max;
+    return PB_OK;
+}
+
+int pbk_thresholds(pb_ctx* ctx) {
+    const int64_t n_slots = 2 * ctx->S_inf;
+    const int32_t n_max = ctx->n_max;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    // one scratch allocation: [expect 64 f64][tau f64][n_fast u64][ktau i32 x (n_max+1)][hist u32 x (n_max+1)]
+    const int64_t n1 = (int64_t)n_max + 1;
+    const int64_t need = TAU_LEVELS * 8 + 8 + 8 + n1 * 4 + n1 * 4;
+    if ((rc = ensure_bytes(ctx, &ctx->d_thr, &ctx->thr_cap, need))) return rc;
+    char* base = (char*)ctx->d_thr;
+    double* d_expect = (double*)base;
+    ctx->d_tau = (double*)(base + TAU_LEVELS * 8);
+    unsigned long long* d_nfast = (unsigned long long*)(base + TAU_LEVELS * 8 + 8);
+    ctx->d_ktau = (int32_t*)(base + TAU_LEVELS * 8 + 16);
+    unsigned int* d_hist = (unsigned int*)(base + TAU_LEVELS * 8 + 16 + n1 * 4);
+    PB_CUDA(cudaMemsetAsync(ctx->d_thr, 0, (size_t)need, st));
+    const int T = 256;
+    const int force_general = (ctx->cfg.flags & PB_FLAG_FORCE_GENERAL_NULL) ? 1 : 0;
+    k4_observed_kernel<<<(unsigned)((n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ptable, ctx->d_pobs, d_hist,
+                                                                      force_general, d_nfast);
+    k4_tau_expect_kernel<<<TAU_LEVELS, 256, 0, st>>>(ctx->d_ptable, d_hist, n_max, d_expect);
+    k4_tau_pick_kernel<<<1, 1, 0, st>>>(d_expect, 64.0, ctx->cfg.maxt_tau, ctx->d_tau);
+    k4_ktau_kernel<<<(unsigned)((n1 + T - 1) / T), T, 0, st>>>(ctx->d_ptable, n_max, ctx->d_tau, ctx->d_ktau);
+    ctx->tm.n_launches += 4;
+    PB_CUDA(cudaGetLastError());
+    unsigned long long nf = 0;
+    PB_CUDA(cudaMemcpyAsync(&nf, d_nfast, 8, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    ctx->tm.n_fast_alleles = (int64_t)nf;
+    return PB_OK;
+}
+
+int pbk_pvalues(pb_ctx* ctx) {
+    const int64_t m = ctx->cfg.n_replicates;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    int64_t n_pad = BSORT_TILE;
+    while (n_pad < m) n_pad <<= 1;
+    {
+        int64_t cap = ctx->sorted_cap * 8;
+        void* ps = ctx->d_maxT_sorted;
+        if ((rc = ensure_bytes(ctx, &ps, &cap, n_pad * 8))) { ctx->d_maxT_sorted = nullptr; ctx->sorted_cap = 0; return rc; }
+        ctx->d_maxT_sorted = (double*)ps; ctx->sorted_cap = cap / 8;
+    }
+    const int T = 256;
+    k4_sort_init_kernel<<<(unsigned)((n_pad + T - 1) / T), T, 0, st>>>(ctx->d_maxT, m, n_pad, ctx->d_maxT_sorted);
+    ctx->tm.n_launches += 1;
+    for (int64_t k = 2; k <= n_pad; k <<= 1) {
+        int64_t j = k >> 1;
+        for (; j >= BSORT_TILE / 2 * 2; j >>= 1) {  // strides that cross a 2048-element tile: global steps
+            k4_bitonic_step_kernel<<<(unsigned)((n_pad + T - 1) / T), T, 0, st>>>(ctx->d_maxT_sorted, n_pad, j, k);
+            ctx->tm.n_launches += 1;
+        }
+        k4_bitonic_smem_kernel<<<(unsigned)(n_pad / BSORT_TILE), 1024, 0, st>>>(ctx->d_maxT_sorted, k, j);
+        ctx->tm.n_launches += 1;
+    }
+    {
+        int64_t cap = ctx->stats_cap * (int64_t)sizeof(pb_stat_out);
+        void* ps = ctx->d_stats;
+        if ((rc = ensure_bytes(ctx, &ps, &cap, ctx->S_inf * (int64_t)sizeof(pb_stat_out)))) { ctx->d_stats = nullptr; ctx->stats_cap = 0; return rc; }
+        ctx->d_stats = (pb_stat_out*)ps; ctx->stats_cap = cap / (int64_t)sizeof(pb_stat_out);
+    }
+    k4_stats_kernel<<<(unsigned)((ctx->S_inf + T - 1) / T), T, 0, st>>>(ctx->d_inf_site, ctx->S_inf, ctx->d_alleles, ctx->d_pobs, ctx->d_r,
+                                                                      ctx->d_maxT_sorted, m, ctx->cfg.site_offset, ctx->d_stats);
+    ctx->tm.n_launches += 1;
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}

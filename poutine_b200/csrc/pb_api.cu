@@ -1,0 +1,428 @@
+// C ABI of libpoutine_b200.so — context, uploads, orchestration (see include/poutine_b200.h).
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "pb_internal.h"
+
+static thread_local std::string g_create_err;
+
+#define CHECK_CTX(ctx) do { if (!(ctx)) return PB_ERR_INVALID; } while (0)
+#define FAIL(ctx, code, msg) do { (ctx)->err = (msg); return (code); } while (0)
+
+extern "C" int pb_version(void) { return 100; }
+
+extern "C" const char* pb_last_error(pb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+static void free_all(pb_ctx* c) {
+    void* ptrs[] = {c->d_leaf_ops, c->d_int_ops, c->d_chunk_lg, c->d_chunk_io, c->d_node_sample, c->d_label, c->d_B0, c->d_B1, c->d_V,
+                    c->d_census, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
+                    c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT,
+                    c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count};
+    for (void* p : ptrs) if (p) cudaFree(p);
+}
+
+extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
+    if (!cfg || !out) { g_create_err = "pb_create: null argument"; return PB_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->n_replicates < 1 || cfg->min_hcount < 0 || (cfg->mode != PB_MODE_PHILOX && cfg->mode != PB_MODE_REPLAY) ||
+        (cfg->site_offset & 63) != 0) {
+        g_create_err = "pb_create: invalid config (n_replicates >= 1, min_hcount >= 0, mode, site_offset % 64 == 0)";
+        return PB_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("pb_create: no CUDA device (") + cudaGetErrorString(e) + ") — there is no CPU fallback";
+        return PB_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "pb_create: device ordinal out of range"; return PB_ERR_INVALID; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) { g_create_err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e); return PB_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_err = "pb_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                       ", this library carries sm_100a code only — there is no fallback";
+        return PB_ERR_CUDA;
+    }
+    pb_ctx* ctx = new pb_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    ctx->sm_count = prop.multiProcessorCount;
+    auto fail = [&](const char* what, cudaError_t ce) {
+        g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
+        free_all(ctx);
+        delete ctx;
+        return PB_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->d_raw_cursor, 8)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_class_counts, 16 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_fb_count, 4)) != cudaSuccess) return fail("cudaMalloc", e);
+    *out = ctx;
+    return PB_OK;
+}
+
+extern "C" void pb_destroy(pb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    pbn_destroy(ctx);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_all(ctx);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+template <typename T>
+static int upload(pb_ctx* ctx, T** dptr, const std::vector<T>& h) {
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    PB_CUDA(cudaMalloc(dptr, bytes));
+    if (!h.empty()) PB_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+// Edge schedule of K1.  Edges are emitted parent by parent in a depth-first expansion that enters the
+// smaller subtree first, so a parent's row is re-read from L1/L2 shortly after it was first loaded;
+// leaf edges (census + MRCA test) and internal edges (MRCA test only) go to separate streams that the
+// kernel consumes chunk by chunk.
+static int build_schedule(pb_ctx* ctx) {
+    const int32_t N = ctx->N;
+    std::vector<int32_t> nchild(N, 0), first(N + 1, 0), kids(N > 1 ? N - 1 : 0);
+    for (int32_t v = 0; v < N; v++) if (ctx->parent[v] >= 0) nchild[ctx->parent[v]]++;
+    for (int32_t v = 0; v < N; v++) first[v + 1] = first[v] + nchild[v];
+    {
+        std::vector<int32_t> fill(first.begin(), first.end() - 1);
+        for (int32_t v = 0; v < N; v++) if (ctx->parent[v] >= 0) kids[fill[ctx->parent[v]]++] = v;
+    }
+    // subtree sizes via reverse BFS order
+    std::vector<int32_t> order; order.reserve(N);
+    order.push_back(ctx->root);
+    for (size_t i = 0; i < order.size(); i++) {
+        const int32_t u = order[i];
+        for (int32_t j = first[u]; j < first[u + 1]; j++) order.push_back(kids[j]);
+    }
+    if ((int32_t)order.size() != N) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: parent[] does not describe one tree (cycle or several roots)");
+    std::vector<int32_t> sz(N, 1);
+    for (int32_t i = N - 1; i > 0; i--) sz[ctx->parent[order[i]]] += sz[order[i]];
+
+    std::vector<EdgeOp> leaf_ops, int_ops;
+    leaf_ops.reserve(ctx->L + 8); int_ops.reserve(N);
+    std::vector<int32_t> stack; stack.push_back(ctx->root);
+    std::vector<int32_t> tmp;
+    while (!stack.empty()) {
+        const int32_t u = stack.back(); stack.pop_back();
+        const int32_t par = (u == ctx->root) ? -1 : u;
+        tmp.clear();
+        for (int32_t j = first[u]; j < first[u + 1]; j++) {
+            const int32_t c = kids[j];
+            if (ctx->is_leaf[c]) leaf_ops.push_back({c, par});
+            else {
+                if (par >= 0) int_ops.push_back({c, par});
+                tmp.push_back(c);
+            }
+        }
+        std::sort(tmp.begin(), tmp.end(), [&](int32_t a, int32_t b) { return sz[a] > sz[b]; });  // largest pushed first -> popped last
+        for (int32_t c : tmp) stack.push_back(c);
+    }
+    while (leaf_ops.size() % 8) leaf_ops.push_back({-1, -1});
+    ctx->n_leaf_groups = (int32_t)(leaf_ops.size() / 8);
+    ctx->n_int_ops = (int32_t)int_ops.size();
+
+    int rc;
+    if ((rc = upload(ctx, &ctx->d_leaf_ops, leaf_ops))) return rc;
+    if ((rc = upload(ctx, &ctx->d_int_ops, int_ops))) return rc;
+    return PB_OK;
+}
+
+// chunking of the schedule: enough blocks to fill the GPU several times over, <= 2040 leaves per chunk
+static int build_chunks(pb_ctx* ctx) {
+    // needs W (set_sites) and the schedule (set_tree)
+    if (ctx->N == 0 || ctx->W == 0) return PB_OK;
+    const int64_t blocks_x = (ctx->W + PB_K1_THREADS - 1) / PB_K1_THREADS;
+    int64_t target_blocks = (int64_t)ctx->sm_count * 24;
+    if (const char* e = getenv("PB_K1_TARGET_BLOCKS")) target_blocks = atoll(e);
+    int64_t n_chunks = (target_blocks + blocks_x - 1) / blocks_x;
+    const int64_t min_chunks = (ctx->n_leaf_groups * 8 + PB_K1_MAX_LEAVES_PER_CHUNK - 1) / PB_K1_MAX_LEAVES_PER_CHUNK;
+    int64_t max_chunks = std::max<int64_t>(1, ctx->N / 64);
+    if (const char* e = getenv("PB_K1_CHUNKS")) n_chunks = atoll(e);
+    n_chunks = std::min(n_chunks, max_chunks);
+    n_chunks = std::max<int64_t>(n_chunks, std::max<int64_t>(min_chunks, 1));
+    n_chunks = std::min<int64_t>(n_chunks, 65535);
+    ctx->n_chunks = (int32_t)n_chunks;
+    std::vector<int32_t> lg(n_chunks + 1), io(n_chunks + 1);
+    for (int64_t c = 0; c <= n_chunks; c++) {
+        lg[c] = (int32_t)((int64_t)ctx->n_leaf_groups * c / n_chunks);
+        io[c] = (int32_t)((int64_t)ctx->n_int_ops * c / n_chunks);
+    }
+    for (int64_t c = 0; c < n_chunks; c++)
+        if ((lg[c + 1] - lg[c]) * 8 > PB_K1_MAX_LEAVES_PER_CHUNK) FAIL(ctx, PB_ERR_INVALID, "internal: chunk exceeds census width");
+    int rc;
+    if ((rc = upload(ctx, &ctx->d_chunk_lg, lg))) return rc;
+    if ((rc = upload(ctx, &ctx->d_chunk_io, io))) return rc;
+    if (ctx->d_census) { cudaFree(ctx->d_census); ctx->d_census = nullptr; }
+    PB_CUDA(cudaMalloc(&ctx->d_census, (size_t)n_chunks * 4 * PB_K1_KS * ctx->W * 8));
+    return PB_OK;
+}
+
+static int build_node_sample(pb_ctx* ctx) {
+    if (ctx->N == 0) return PB_OK;
+    std::vector<int32_t> ns(ctx->N, -1);
+    for (int32_t j = 0; j < ctx->P; j++) ns[ctx->sample_node[j]] = j;
+    return upload(ctx, &ctx->d_node_sample, ns);
+}
+
+extern "C" int pb_set_tree(pb_ctx* ctx, int32_t n_nodes, const int32_t* parent, const uint8_t* is_leaf) {
+    CHECK_CTX(ctx);
+    if (n_nodes < 2 || !parent || !is_leaf) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: need >= 2 nodes, parent[] and is_leaf[]");
+    if (n_nodes > (int32_t)PB_EV_NODE_MASK) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: too many nodes (limit 2^29-1)");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    int32_t root = -1, L = 0;
+    std::vector<int32_t> nchild(n_nodes, 0);
+    for (int32_t v = 0; v < n_nodes; v++) {
+        if (parent[v] < 0) { if (root >= 0) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: more than one root"); root = v; }
+        else if (parent[v] >= n_nodes || parent[v] == v) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: parent index out of range");
+        else nchild[parent[v]]++;
+    }
+    if (root < 0) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: no root (parent == -1)");
+    for (int32_t v = 0; v < n_nodes; v++) {
+        if ((nchild[v] == 0) != (is_leaf[v] != 0)) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: is_leaf[] disagrees with parent[]");
+        L += is_leaf[v] != 0;
+    }
+    if (is_leaf[root]) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: the root is a leaf");
+    ctx->N = n_nodes; ctx->L = L; ctx->root = root;
+    ctx->parent.assign(parent, parent + n_nodes);
+    ctx->is_leaf.assign(is_leaf, is_leaf + n_nodes);
+    ctx->events_done = ctx->assoc_done = false;
+    ctx->P = 0; ctx->sample_node.clear(); ctx->label.clear();
+    int rc;
+    if ((rc = build_schedule(ctx))) return rc;
+    if ((rc = build_node_sample(ctx))) return rc;
+    if ((rc = build_chunks(ctx))) return rc;
+    // planes depend on N: force re-allocation
+    if (ctx->S) { const int64_t S = ctx->S; ctx->S = 0; return pb_set_sites(ctx, S); }
+    return PB_OK;
+}
+
+extern "C" int pb_set_labels(pb_ctx* ctx, int32_t n_samples, const int32_t* sample_node, const uint8_t* label) {
+    CHECK_CTX(ctx);
+    if (ctx->N == 0) FAIL(ctx, PB_ERR_INVALID, "pb_set_labels: call pb_set_tree first");
+    if (n_samples < 1 || !sample_node || !label) FAIL(ctx, PB_ERR_INVALID, "pb_set_labels: empty phenotype table");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    std::vector<uint8_t> seen(ctx->N, 0);
+    int32_t nc = 0, nt = 0, nm = 0;
+    for (int32_t j = 0; j < n_samples; j++) {
+        const int32_t v = sample_node[j];
+        // check_sample_names (HC.java:367-404): every pheno sample must be a leaf of the tree
+        if (v < 0 || v >= ctx->N || !ctx->is_leaf[v]) FAIL(ctx, PB_ERR_INVALID, "pb_set_labels: sample_node is not a leaf of the tree");
+        if (seen[v]) FAIL(ctx, PB_ERR_INVALID, "pb_set_labels: duplicate sample (HashMap keys are unique)");
+        seen[v] = 1;
+        if (label[j] == PB_LABEL_CASE) nc++; else if (label[j] == PB_LABEL_CONTROL) nt++; else if (label[j] == PB_LABEL_MISSING) nm++;
+        else FAIL(ctx, PB_ERR_INVALID, "pb_set_labels: label code must be 0, 1 or 2");
+    }
+    ctx->P = n_samples; ctx->n_case = nc; ctx->n_ctrl = nt; ctx->n_miss = nm;
+    ctx->sample_node.assign(sample_node, sample_node + n_samples);
+    ctx->label.assign(label, label + n_samples);
+    ctx->events_done = ctx->assoc_done = false;  // the CSR only keeps leaves that have a pheno row
+    int rc;
+    if ((rc = upload(ctx, &ctx->d_label, ctx->label))) return rc;
+    return build_node_sample(ctx);
+}
+
+extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
+    CHECK_CTX(ctx);
+    if (ctx->N == 0) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: call pb_set_tree first");
+    if (n_sites < 1 || n_sites >= (1ll << 32)) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: n_sites out of range");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    ctx->events_done = ctx->assoc_done = false;
+    if (n_sites == ctx->S && ctx->d_B0) return PB_OK;
+    for (uint64_t** p : {&ctx->d_B0, &ctx->d_B1, &ctx->d_V}) if (*p) { cudaFree(*p); *p = nullptr; }
+    for (void** p : {(void**)&ctx->d_cnt, (void**)&ctx->d_sites, (void**)&ctx->d_site_flags, (void**)&ctx->d_site_scan, (void**)&ctx->d_raw})
+        if (*p) { cudaFree(*p); *p = nullptr; }
+    ctx->S = n_sites;
+    ctx->W = (n_sites + 63) / 64;
+    ctx->Wp = (ctx->W + 15) & ~15ll;  // rows padded to 128 B
+    const size_t plane = (size_t)ctx->N * ctx->Wp * 8;
+    cudaError_t e;
+    if ((e = cudaMalloc(&ctx->d_B0, plane)) != cudaSuccess || (e = cudaMalloc(&ctx->d_B1, plane)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_V, plane)) != cudaSuccess) {
+        ctx->err = std::string("pb_set_sites: cudaMalloc of 3 x ") + std::to_string(plane) + " B planes: " + cudaGetErrorString(e);
+        ctx->S = 0;
+        return PB_ERR_OOM;
+    }
+    PB_CUDA(cudaMemsetAsync(ctx->d_B0, 0, plane, ctx->stream));
+    PB_CUDA(cudaMemsetAsync(ctx->d_B1, 0, plane, ctx->stream));
+    PB_CUDA(cudaMemsetAsync(ctx->d_V, 0, plane, ctx->stream));
+    PB_CUDA(cudaMalloc(&ctx->d_cnt, (size_t)n_sites * PB_CNT_STRIDE * 4));
+    PB_CUDA(cudaMalloc(&ctx->d_sites, (size_t)n_sites * sizeof(pb_site_out)));
+    PB_CUDA(cudaMalloc(&ctx->d_site_flags, (size_t)n_sites));
+    PB_CUDA(cudaMalloc(&ctx->d_site_scan, (size_t)n_sites * 2 * 8));
+    ctx->raw_cap = std::max<int64_t>(4 * n_sites, 1 << 20);
+    PB_CUDA(cudaMalloc(&ctx->d_raw, (size_t)ctx->raw_cap * sizeof(raw_event_t)));
+    return build_chunks(ctx);
+}
+
+extern "C" int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* B0,
+                             const uint64_t* B1, const uint64_t* V) {
+    CHECK_CTX(ctx);
+    if (!ctx->d_B0) FAIL(ctx, PB_ERR_INVALID, "pb_put_planes: call pb_set_sites first");
+    if (!B0 || !B1 || !V || word_begin < 0 || n_words < 1 || word_begin + n_words > ctx->W || src_pitch_words < n_words)
+        FAIL(ctx, PB_ERR_INVALID, "pb_put_planes: tile out of range");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    ctx->events_done = ctx->assoc_done = false;
+    const uint64_t* src[3] = {B0, B1, V};
+    uint64_t* dst[3] = {ctx->d_B0, ctx->d_B1, ctx->d_V};
+    for (int i = 0; i < 3; i++)
+        PB_CUDA(cudaMemcpy2DAsync(dst[i] + word_begin, (size_t)ctx->Wp * 8, src[i], (size_t)src_pitch_words * 8, (size_t)n_words * 8,
+                                  (size_t)ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers are caller-owned: do not retain them past return
+    return PB_OK;
+}
+
+extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts) {
+    CHECK_CTX(ctx);
+    if (!ctx->d_B0 || ctx->N == 0) FAIL(ctx, PB_ERR_INVALID, "pb_run_events: tree and planes must be set");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    ctx->tm = pb_timings{};
+    int rc;
+    PB_CUDA(cudaEventRecord(ctx->ev[12], ctx->stream));
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if ((rc = pbk_events(ctx))) return rc;
+        unsigned long long cur = 0;
+        PB_CUDA(cudaMemcpyAsync(&cur, ctx->d_raw_cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        PB_CUDA(cudaGetLastError());
+        if ((int64_t)cur <= ctx->raw_cap) { ctx->n_raw = (int64_t)cur; break; }
+        // event list larger than the buffer (dense / adversarial input): grow to the exact need and redo
+        cudaFree(ctx->d_raw); ctx->d_raw = nullptr;
+        ctx->raw_cap = (int64_t)cur + (int64_t)cur / 16 + 1024;
+        cudaError_t e = cudaMalloc(&ctx->d_raw, (size_t)ctx->raw_cap * sizeof(raw_event_t));
+        if (e != cudaSuccess) { ctx->err = "pb_run_events: cannot allocate the event list"; ctx->raw_cap = 0; return PB_ERR_OOM; }
+        if (attempt == 2) FAIL(ctx, PB_ERR_CUDA, "pb_run_events: event list kept overflowing");
+    }
+    if ((rc = pbk_finalize_events(ctx, counts))) return rc;
+    PB_CUDA(cudaEventRecord(ctx->ev[13], ctx->stream));
+    if (per_site) PB_CUDA(cudaMemcpyAsync(per_site, ctx->d_sites, (size_t)ctx->S * sizeof(pb_site_out), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float t;
+    cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]); ctx->tm.ms_events_kernel = t;
+    cudaEventElapsedTime(&t, ctx->ev[12], ctx->ev[13]); ctx->tm.ms_events_total = t;
+    ctx->tm.k1_algorithmic_bytes = 3ll * ctx->N * ctx->W * 8 + 32ll * ctx->S + 8ll * ctx->n_raw;
+    ctx->tm.n_informative = ctx->S_inf; ctx->tm.n_alleles_in_use = ctx->A_inuse; ctx->tm.n_extant_events = ctx->E;
+    ctx->events_done = true;
+    ctx->assoc_done = false;
+    return PB_OK;
+}
+
+extern "C" int pb_run_assoc(pb_ctx* ctx, const uint32_t* replay_perms, pb_stat_out* per_inf_site, int64_t cap, int64_t* n_inf,
+                            double* maxT_sorted) {
+    CHECK_CTX(ctx);
+    if (!ctx->events_done) FAIL(ctx, PB_ERR_INVALID, "pb_run_assoc: call pb_run_events first");
+    if (ctx->P == 0) FAIL(ctx, PB_ERR_INVALID, "pb_run_assoc: call pb_set_labels first");
+    if (ctx->cfg.mode == PB_MODE_REPLAY && !replay_perms) FAIL(ctx, PB_ERR_INVALID, "pb_run_assoc: replay mode needs replay_perms");
+    if (ctx->n_case + ctx->n_ctrl == 0) FAIL(ctx, PB_ERR_INVALID, "pb_run_assoc: phenotype file has neither cases nor controls");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    if (n_inf) *n_inf = ctx->S_inf;
+    // subset_by_min_hcount: "min_hcount ... has filtered out all segregating sites" (HC.java:3866-3869).
+    // In a sharded run an empty shard is legal: it still has to join the all-reduce.
+    if (ctx->S_inf == 0 && ctx->world == 1) FAIL(ctx, PB_ERR_NO_INFORMATIVE, "min_hcount is set too high and has filtered out all segregating sites");
+    if (per_inf_site && cap < ctx->S_inf) FAIL(ctx, PB_ERR_INVALID, "pb_run_assoc: per_inf_site too small");
+    int rc;
+    if ((rc = pbk_assoc(ctx, replay_perms))) return rc;
+    if (per_inf_site && ctx->S_inf)
+        PB_CUDA(cudaMemcpyAsync(per_inf_site, ctx->d_stats, (size_t)ctx->S_inf * sizeof(pb_stat_out), cudaMemcpyDeviceToHost, ctx->stream));
+    if (maxT_sorted)
+        PB_CUDA(cudaMemcpyAsync(maxT_sorted, ctx->d_maxT_sorted, (size_t)ctx->cfg.n_replicates * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->assoc_done = true;
+    return PB_OK;
+}
+
+// ---- introspection -------------------------------------------------------------------------------------
+extern "C" int pb_get_sites(pb_ctx* ctx, pb_site_out* per_site) {
+    CHECK_CTX(ctx);
+    if (!ctx->events_done || !per_site) FAIL(ctx, PB_ERR_INVALID, "pb_get_sites: no results");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    PB_CUDA(cudaMemcpy(per_site, ctx->d_sites, (size_t)ctx->S * sizeof(pb_site_out), cudaMemcpyDeviceToHost));
+    return PB_OK;
+}
+
+extern "C" int pb_get_raw_events(pb_ctx* ctx, int64_t cap, int32_t* site, int32_t* node, int64_t* n) {
+    CHECK_CTX(ctx);
+    if (!ctx->events_done) FAIL(ctx, PB_ERR_INVALID, "pb_get_raw_events: no results");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    if (n) *n = ctx->n_raw;
+    if (!site || !node) return PB_OK;
+    if (cap < ctx->n_raw) FAIL(ctx, PB_ERR_INVALID, "pb_get_raw_events: buffer too small");
+    std::vector<raw_event_t> h((size_t)ctx->n_raw);
+    if (ctx->n_raw) PB_CUDA(cudaMemcpy(h.data(), ctx->d_raw, (size_t)ctx->n_raw * 8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < ctx->n_raw; i++) { site[i] = (int32_t)(uint32_t)h[i]; node[i] = (int32_t)((uint32_t)(h[i] >> 32) & PB_EV_NODE_MASK); }
+    return PB_OK;
+}
+
+extern "C" int pb_get_event_csr(pb_ctx* ctx, int64_t* offsets, int32_t* sample_index, int64_t cap) {
+    CHECK_CTX(ctx);
+    if (!ctx->events_done) FAIL(ctx, PB_ERR_INVALID, "pb_get_event_csr: no results");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    if (cap < ctx->E) FAIL(ctx, PB_ERR_INVALID, "pb_get_event_csr: buffer too small");
+    std::vector<AlleleMeta> h((size_t)(2 * ctx->S_inf));
+    if (ctx->S_inf) PB_CUDA(cudaMemcpy(h.data(), ctx->d_alleles, h.size() * sizeof(AlleleMeta), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < 2 * ctx->S_inf; i++) offsets[i] = h[i].off;
+    offsets[2 * ctx->S_inf] = ctx->E;
+    if (ctx->E && sample_index) PB_CUDA(cudaMemcpy(sample_index, ctx->d_csr, (size_t)ctx->E * 4, cudaMemcpyDeviceToHost));
+    return PB_OK;
+}
+
+extern "C" int pb_get_maxT_unsorted(pb_ctx* ctx, double* out) {
+    CHECK_CTX(ctx);
+    if (!ctx->assoc_done || !out) FAIL(ctx, PB_ERR_INVALID, "pb_get_maxT_unsorted: no results");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    PB_CUDA(cudaMemcpy(out, ctx->d_maxT, (size_t)ctx->cfg.n_replicates * 8, cudaMemcpyDeviceToHost));
+    return PB_OK;
+}
+
+extern "C" int pb_get_ptable(pb_ctx* ctx, int32_t* n_max, double* out, int64_t cap) {
+    CHECK_CTX(ctx);
+    if (!ctx->assoc_done) FAIL(ctx, PB_ERR_INVALID, "pb_get_ptable: no results");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    if (n_max) *n_max = ctx->ptable_nmax;
+    const int64_t total = (int64_t)(ctx->ptable_nmax + 1) * (ctx->ptable_nmax + 2) / 2;
+    if (out) {
+        if (cap < total) FAIL(ctx, PB_ERR_INVALID, "pb_get_ptable: buffer too small");
+        PB_CUDA(cudaMemcpy(out, ctx->d_ptable, (size_t)total * 8, cudaMemcpyDeviceToHost));
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_get_timings(pb_ctx* ctx, pb_timings* out) {
+    CHECK_CTX(ctx);
+    if (!out) return PB_ERR_INVALID;
+    *out = ctx->tm;
+    return PB_OK;
+}
+
+extern "C" int pb_comm_unique_id(void* id128) {
+    std::string err;
+    int rc = pbn_unique_id(id128, err);
+    if (rc) g_create_err = err;
+    return rc;
+}
+
+extern "C" int pb_comm_init(pb_ctx* ctx, const void* id128, int32_t rank, int32_t world) {
+    CHECK_CTX(ctx);
+    if (!id128 || world < 1 || rank < 0 || rank >= world) FAIL(ctx, PB_ERR_INVALID, "pb_comm_init: bad rank/world");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    return pbn_init(ctx, id128, rank, world);
+}
+
+extern "C" int pb_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return PB_ERR_INVALID;
+    cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { g_create_err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); return PB_ERR_OOM; }
+    return PB_OK;
+}
+extern "C" int pb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? PB_OK : PB_ERR_CUDA; }

@@ -1,0 +1,152 @@
+// Internal declarations shared by the translation units of libpoutine_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/poutine_b200.h"
+
+// ---- device-side record layouts -------------------------------------------------------------
+struct EdgeOp {        // one tree edge of the K1 schedule
+    int32_t child;     // node index; < 0 = padding slot of a leaf group
+    int32_t parent;    // node index; < 0 = edge hangs off the root: no MRCA test (HC.java:1674)
+};
+
+// raw MRCA event: lo = site (context-local), hi = node | base<<29 | is_leaf<<31
+typedef unsigned long long raw_event_t;
+#define PB_EV_NODE_MASK 0x1FFFFFFFu
+
+// per-site event counters filled by k1_count_events: [0..3] all MRCAs by own base code,
+// [4..7] leaf MRCAs, [8..11] leaf MRCAs that have a pheno row
+#define PB_CNT_STRIDE 12
+
+// site flags byte written by k1_finalize
+#define PB_SF_BI 1u
+#define PB_SF_A1_USE 2u
+#define PB_SF_A2_USE 4u
+#define PB_SF_A1_CODE_SHIFT 3  // 2 bits
+
+// census: 4 per-base counters, bit-sliced; slices 0..2 = ones/twos/fours, 3.. = high part
+#define PB_K1_KHI 8
+#define PB_K1_KS (3 + PB_K1_KHI)
+#define PB_K1_MAX_LEAVES_PER_CHUNK 2040
+#define PB_K1_THREADS 128
+#define PB_K1_QCAP 3072  // per-block event queue (24 KB)
+
+// allele flags
+#define PB_AF_IN_USE 1u
+#define PB_AF_FAST 2u   // {k : f(n,k) <= p_obs} is an up-set and no missing labels: threshold path
+
+struct AlleleMeta {      // one per allele slot (2 per informative site), 32 bytes
+    int64_t off;         // CSR offset of its sample list
+    int32_t n;           // # extant MRCA leaves with a pheno row
+    uint32_t flags;
+    int32_t kstar;       // min k with f(n,k) <= p_obs (fast path)
+    int32_t obs_case, obs_ctrl;
+    int32_t pad;
+};
+
+struct pb_ctx {
+    pb_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int sm_count = 148;
+
+    // tree
+    int32_t N = 0, L = 0, root = -1;
+    std::vector<int32_t> parent;
+    std::vector<uint8_t> is_leaf;
+    EdgeOp* d_leaf_ops = nullptr;   // padded to groups of 8
+    EdgeOp* d_int_ops = nullptr;
+    int32_t n_leaf_groups = 0, n_int_ops = 0;
+    int32_t n_chunks = 0;
+    int32_t* d_chunk_lg = nullptr;  // n_chunks+1 leaf-group boundaries
+    int32_t* d_chunk_io = nullptr;  // n_chunks+1 internal-op boundaries
+    int32_t* d_node_sample = nullptr;  // N: sample index of a leaf with a pheno row, else -1
+
+    // labels
+    int32_t P = 0, n_case = 0, n_ctrl = 0, n_miss = 0;
+    std::vector<int32_t> sample_node;
+    std::vector<uint8_t> label;
+    uint8_t* d_label = nullptr;
+
+    // sites / planes
+    int64_t S = 0, W = 0, Wp = 0;
+    uint64_t *d_B0 = nullptr, *d_B1 = nullptr, *d_V = nullptr;
+
+    // K1 outputs
+    uint64_t* d_census = nullptr;      // [n_chunks][4][KS][W]
+    raw_event_t* d_raw = nullptr;
+    int64_t raw_cap = 0;
+    unsigned long long* d_raw_cursor = nullptr;
+    int64_t n_raw = 0;
+    uint32_t* d_cnt = nullptr;         // [S][PB_CNT_STRIDE]
+    pb_site_out* d_sites = nullptr;    // [S]
+    uint8_t* d_site_flags = nullptr;   // [S]
+    uint64_t* d_site_scan = nullptr;   // [S] exclusive prefix: inf count << 38 | event count
+    unsigned long long* d_class_counts = nullptr;  // 5 + n_max + scan totals ...
+    bool events_done = false;
+
+    // informative sites / CSR
+    int64_t S_inf = 0, E = 0, A_inuse = 0;
+    int32_t n_max = 0;
+    int32_t* d_inf_site = nullptr;     // [S_inf]
+    AlleleMeta* d_alleles = nullptr;   // [2*S_inf]
+    int32_t* d_csr = nullptr;          // [E]
+    uint32_t* d_csr_cursor = nullptr;  // [2*S_inf]
+    int64_t inf_cap = 0, csr_cap = 0;
+
+    // assoc
+    double p_success = 0;
+    double* d_ptable = nullptr;  int64_t ptable_cap = 0;  int32_t ptable_nmax = -1;
+    void* d_thr = nullptr; int64_t thr_cap = 0;  // threshold scratch (expect, tau, ktau, n-histogram)
+    int32_t* d_ktau = nullptr;   // [n_max+1]   (inside d_thr)
+    double* d_tau = nullptr;     // 1           (inside d_thr)
+    double* d_pobs = nullptr;    // [2*S_inf]
+    uint32_t* d_r = nullptr;     // [2*S_inf]
+    unsigned long long* d_maxT = nullptr;  // [m] (double bits)
+    double* d_maxT_sorted = nullptr;       // [pow2 >= m]
+    int64_t maxT_cap = 0, sorted_cap = 0;
+    uint64_t *d_Xcase = nullptr, *d_Xmiss = nullptr;  // [P][Rw]
+    int64_t X_cap = 0, Xm_cap = 0, fb_cap = 0;
+    uint32_t* d_perms = nullptr; int64_t perms_cap = 0;
+    pb_stat_out* d_stats = nullptr; int64_t stats_cap = 0;
+    int32_t* d_fb_reps = nullptr;  // fallback replicate list
+    unsigned int* d_fb_count = nullptr;
+    bool assoc_done = false;
+
+    // nccl
+    void* nccl_comm = nullptr;
+    int32_t rank = 0, world = 1;
+
+    // timing
+    pb_timings tm{};
+    cudaEvent_t ev[16]{};
+};
+
+#define PB_CUDA(call)                                                                             \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
+            return PB_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------------------------
+int pbk_events(pb_ctx* ctx);                                   // k1_events.cu
+int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts); // k1_events.cu
+int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms);      // k3_null.cu (+ k4)
+int pbk_ptable(pb_ctx* ctx);                                   // k4_pvalues.cu
+int pbk_thresholds(pb_ctx* ctx);                               // k4_pvalues.cu
+int pbk_pvalues(pb_ctx* ctx);                                  // k4_pvalues.cu
+int pbk_exclusive_scan_u64(pb_ctx* ctx, const uint64_t* in, uint64_t* out, int64_t n, uint64_t* d_total);  // k1_events.cu
+
+// nccl_dyn.cpp
+int pbn_unique_id(void* id128, std::string& err);
+int pbn_init(pb_ctx* ctx, const void* id128, int rank, int world);
+int pbn_allreduce_min_f64(pb_ctx* ctx, double* buf, int64_t n);
+void pbn_destroy(pb_ctx* ctx);

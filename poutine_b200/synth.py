@@ -137,7 +137,7 @@ def random_tree(n_leaves: int, seed: int, polytomy: float = 0.2, root_leaf_child
     for _ in range(k0):
         parent.append(0)
         tips.append(len(parent) - 1)
-    protected = set(tips[:root_leaf_children])  # stay leaves attached to the root
+    protected = set(tips[:min(root_leaf_children, k0 - 1)])  # stay leaves attached to the root
     while len(tips) < n_leaves:
         cand = [t for t in tips if t not in protected]
         v = cand[int(rng.integers(len(cand)))]

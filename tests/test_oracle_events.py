@@ -1,0 +1,115 @@
+"""The oracle's event detection / association: hand-derived fixture, independent closed form,
+invariants of the reference code, JDK RNG known answers, and the frozen C1 slice."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from poutine_b200 import synth
+from tests.helpers import closed_form_events
+
+
+def test_hand_derived_fixture(oracle_mod, golden_dir):
+    with open(os.path.join(golden_dir, "events_hand.json")) as f:
+        fx = json.load(f)
+    chars = np.array([[ord(s["column"][v]) for s in fx["sites"]] for v in range(len(fx["names"]))], dtype=np.uint8)
+    o = oracle_mod.Oracle(fx["parent"], fx["leaves"])
+    ev, cc = o.count_all_homoplasy_events(chars)
+    got = {int(e["segsite_id"]): e for e in ev}
+    for i, s in enumerate(fx["sites"]):
+        if s["expected"] is None:
+            assert i + 1 not in got, s["name"]
+        else:
+            e = got[i + 1]
+            tup = [chr(e["allele1"]), chr(e["allele2"]), int(e["a1_count"]), int(e["a2_count"]), int(e["a1_extant"]), int(e["a2_extant"])]
+            assert tup == s["expected"], s["name"]
+    assert cc == fx["class_counts"]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_literal_walk_equals_closed_form(oracle_mod, seed):
+    tree = synth.random_tree(12 + 5 * seed, 100 + seed, polytomy=0.3, root_leaf_children=seed % 3)
+    chars = synth.simulate_chars(tree, 60, 200 + seed, nasty=True)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    ev, cc = o.count_all_homoplasy_events(chars)
+    ref, rcc = closed_form_events(tree.parent, tree.leaf_nodes, chars)
+    assert cc == rcc
+    assert len(ev) == len(ref)
+    for i, (e, r) in enumerate(zip(ev, ref)):
+        for f in ("segsite_id", "a1_count", "a2_count", "a1_extant", "a2_extant"):
+            assert int(e[f]) == r[f], (seed, i, f)
+        assert (int(e["allele1"]), int(e["allele2"])) == (r["allele1"], r["allele2"])
+        assert list(o.mrca(i, 0)) == r["mrca"][0] and list(o.mrca(i, 1)) == r["mrca"][1]
+
+
+def test_reference_invariants(oracle_mod):
+    tree = synth.yule_tree(200, 7)
+    chars = synth.simulate_chars(tree, 300, 8, nasty=True)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    ev, _ = o.count_all_homoplasy_events(chars)
+    assert np.all((ev["a1_count"] == 0) | (ev["a1_count"] >= 2))          # (i)
+    assert np.all((ev["a2_count"] == 0) | (ev["a2_count"] >= 2))
+    assert np.all(ev["a1_extant"] <= ev["a1_count"]) and np.all(ev["a2_extant"] <= ev["a2_count"])  # (ii)
+    sn, lab = synth.simulate_phenotypes(tree, 9)                         # every leaf labelled 0/1
+    m = 50
+    perms = oracle_mod.java_shuffle_perms(1, m, len(lab))
+    st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=perms)
+    evs = ev[st["event_index"]]
+    tot = st["obs_counts"].sum(axis=1)
+    expect = np.where(st["a1_in_use"] == 1, evs["a1_extant"], 0) + np.where(st["a2_in_use"] == 1, evs["a2_extant"], 0)
+    np.testing.assert_array_equal(tot, expect)                           # (iii) check_extant_nodes_only_code, HC.java:4345-4369
+    for a in ("a1", "a2"):
+        r = st["r_" + a]
+        use = st[a + "_in_use"] == 1
+        assert np.all((r[use] >= 0) & (r[use] <= m)) and np.all(r[~use] == -1)   # (iv)
+        np.testing.assert_array_equal(st["pointwise_" + a][use], (r[use] + 1.0) / (m + 1.0))  # (v)
+        assert np.all(np.isnan(st["pointwise_" + a][~use]))
+    assert np.all(np.diff(mt_s) >= 0) and sorted(mt_u) == list(mt_s)
+
+
+def test_min_hcount_filters_everything(oracle_mod):
+    tree = synth.yule_tree(50, 3)
+    chars = synth.simulate_chars(tree, 40, 4, nasty=False)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    o.count_all_homoplasy_events(chars)
+    sn, lab = synth.simulate_phenotypes(tree, 5)
+    st, _, _ = o.assoc(sn, lab, 10, 1000, perms=oracle_mod.java_shuffle_perms(1, 10, len(lab)))
+    assert st is None   # HC.java:3866-3869
+
+
+def test_java_util_random_known_answers(oracle_mod):
+    # JDK-documented LCG: values every Java programmer can reproduce
+    assert list(oracle_mod.java_random_ints(0, 2)) == [-1155484576, -723955400]
+    assert list(oracle_mod.java_random_ints(42, 2)) == [-1170105035, 234785527]
+    assert list(oracle_mod.java_random_ints(42, 5, 10)) == [0, 3, 8, 4, 0]
+    p = oracle_mod.java_shuffle_perms(123, 4, 37)
+    assert all(sorted(row) == list(range(37)) for row in p.tolist())
+    assert len({tuple(r) for r in p.tolist()}) == 4
+
+
+def test_philox_labels_are_exact_arrangements(oracle_mod):
+    P, nc, nt = 203, 70, 120
+    seen = set()
+    for rep in range(200):
+        lab = oracle_mod.philox_labels(99, rep, P, nc, nt)
+        assert (lab == 1).sum() == nc and (lab == 0).sum() == nt and (lab == 2).sum() == P - nc - nt
+        seen.add(lab.tobytes())
+    assert len(seen) == 200
+    # marginal: each sample is a case with probability nc/P
+    tot = sum(oracle_mod.philox_labels(5, rep, P, nc, nt).astype(np.int64) == 1 for rep in range(4000))
+    assert abs(tot.mean() / 4000 - nc / P) < 0.01
+    assert tot.std() / 4000 < 0.02
+
+
+def test_c1_slice_regression(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "c1_slice.npz"))
+    S, m = int(z["n_sites"]), int(z["m"])
+    chars = synth.planes_to_chars(z["B0"], z["B1"], z["V"], 0, S)
+    o = oracle_mod.Oracle(z["parent"], z["leaf_nodes"])
+    ev, cc = o.count_all_homoplasy_events(chars, np.arange(S, dtype=np.int32) * 7 + 11)
+    assert ev.tobytes() == z["events"].tobytes()
+    perms = oracle_mod.java_shuffle_perms(int(z["perm_seed"]), m, len(z["label"]))
+    st, mt_s, mt_u = o.assoc(z["sample_node"], z["label"], m, 1, perms=perms, n_threads=3)  # threads must not change results
+    assert st.tobytes() == z["stats"].tobytes()
+    np.testing.assert_array_equal(mt_u, z["maxT_unsorted"])
