@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — sites/sec of the homoplasy hot path (count_all_homoplasy_events + assoc) on B200.
+
+    python bench.py --gpus 1 --steps K --warmup W                      # this repo (CUDA via the C ABI)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                               # CPU port of the reference path
+
+One "step" = one full pass of the hot path over the workload: K1 event detection, K2 tallies,
+K3 permutation null (m replicates), K4 p-values.  N = 1 runs BASELINE.json configs[1]
+(5,000 leaves x 1,000,000 sites, m = 1e5); at N > 1 every rank holds its own 1M-site shard of the
+same tree/phenotypes (weak scaling; sites shard, the one collective is the NCCL all-reduce(min) of
+maxT[m] inside pb_run_assoc).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sites/sec (homoplasy count + null resampling)"
+CPU_SAMPLE_SITES = 4096
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[4:8]):
+                if v == "Active":
+                    reasons.add(n)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_pass(tree, chars, sn, lab, m, seed, threads):
+    """One pass of the CPU port over a site sample: (sites/sec, seconds L4, seconds L5).  oracle/ is test
+    infrastructure; this is the one place bench.py may execute it (cpu_baseline / --impl reference)."""
+    import oracle
+    o = oracle.Oracle(tree.parent, tree.leaf_nodes)
+    t0 = time.perf_counter()
+    o.count_all_homoplasy_events(chars, n_threads=threads)
+    t1 = time.perf_counter()
+    o.assoc(sn, lab, m, 1, perms=None, seed=seed, n_threads=threads)
+    t2 = time.perf_counter()
+    return chars.shape[1] / (t2 - t0), t1 - t0, t2 - t1
+
+
+def workload(args, rank, world):
+    from poutine_b200 import synth
+    cfg = dict(synth.CONFIGS[args.config])
+    S = args.sites or cfg["n_sites"]
+    m = args.replicates or cfg["m"]
+    tree = synth.yule_tree(cfg["n_leaves"], cfg["seed"])
+    sn, lab = synth.simulate_phenotypes(tree, cfg["seed"] + 1000, na_frac=cfg.get("na_frac", 0.0))
+    return cfg, S, m, tree, sn, lab
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from poutine_b200 import synth
+    cfg, S, m, tree, sn, lab = workload(args, 0, 1)
+    n = min(CPU_SAMPLE_SITES, S)
+    planes = synth.simulate_planes(tree, n, cfg["seed"] + 2000 + 7919, leaf_gap=cfg.get("leaf_gap", False),
+                                   multiallelic_frac=cfg.get("multiallelic_frac", 0.0),
+                                   third_allele_internal_frac=cfg.get("third_allele_internal_frac", 0.0))
+    chars = synth.planes_to_chars(*planes, 0, n)
+    threads = host_cores()
+    for _ in range(args.warmup):
+        cpu_reference_pass(tree, chars, sn, lab, max(m // 50, 1), 1, threads)   # short warm-up passes (page-in, thread spin-up)
+    t0 = time.perf_counter()
+    l4 = l5 = 0.0
+    for _ in range(args.steps):
+        _, a, b = cpu_reference_pass(tree, chars, sn, lab, m, 1, threads)
+        l4 += a; l5 += b
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = ("%d-site slice of the %s workload at the full m=%d per step; C++ port of HC.java:1402-1511 + 3013-3186 "
+              "(oracle/oracle.cpp) on %d threads (site loop threaded although the reference runs it on one thread); "
+              "no JVM in this image, so the Java reference itself cannot run") % (n, args.config, m, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 bit planes / int32 counts / f64 p-values", "data": "synthetic",
+            "config": bench_config(args, cfg, S, m, tree, 1),
+            "cpu_baseline": {"value": value, "unit": "sites/s", "cores": threads, "kind": "port", "sample": sample,
+                             "seconds_events": l4 / args.steps, "seconds_assoc": l5 / args.steps},
+            "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def bench_config(args, cfg, S, m, tree, world):
+    return {"workload": "%s: %d-leaf Yule tree (%d nodes) x %d biallelic sites per GPU, binary phenotype (38%% cases), "
+                        "m=%d null replicates, Philox mode" % (args.config, tree.n_leaves, tree.n_nodes, S, m),
+            "baseline_config": "configs[1]" if args.config == "C2" else args.config,
+            "sites_per_gpu": S, "sites_total": S * world, "leaves": tree.n_leaves, "nodes": tree.n_nodes, "replicates": m,
+            "parallelism": "site-sharded x%d, all-reduce(min) of maxT[m]" % world if world > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2 (bit planes %.2f GB per GPU vs 126 MB L2)" % (3 * tree.n_nodes * ((S + 63) // 64) * 8 / 1e9)}
+
+
+def run_b200(args):
+    import torch
+    import poutine_b200 as pb
+    from poutine_b200 import _lib, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not os.path.exists(pb.LIB_PATH):
+        pb.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    cfg, S, m, tree, sn, lab = workload(args, rank, world)
+    W = (S + 63) // 64
+    N = tree.n_nodes
+    t_gen = time.perf_counter()
+    B0, B1, V = synth.simulate_planes(tree, S, cfg["seed"] + 2000 + 7919 * (rank + 1), leaf_gap=cfg.get("leaf_gap", False),
+                                      multiallelic_frac=cfg.get("multiallelic_frac", 0.0),
+                                      third_allele_internal_frac=cfg.get("third_allele_internal_frac", 0.0))
+    # pinned staging copies: the e2e leg uploads from these every step
+    pinned = []
+    host_planes = []
+    for a in (B0, B1, V):
+        h, p = _lib.pinned_empty((N, W), np.uint64)
+        h[...] = a
+        pinned.append(p)
+        host_planes.append(h)
+    cpu_chars = synth.planes_to_chars(B0, B1, V, 0, min(CPU_SAMPLE_SITES, S)) if rank == 0 and world == 1 else None
+    del B0, B1, V
+    t_gen = time.perf_counter() - t_gen
+
+    hc = pb.HomoplasyCounter(num_replicates=m, min_hcount=1, device=local_rank, seed=20260, site_offset=rank * (W * 64))
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_sites(S)
+    if world > 1:
+        ids = [pb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        hc.comm_init(ids[0], rank, world)
+    hc.put_planes(*host_planes)
+
+    def step_resident():
+        hc.count_all_homoplasy_events(fetch_sites=False)
+        hc.assoc(fetch=False)
+        return hc.timings()
+
+    def step_e2e():
+        hc.put_planes(*host_planes)                      # H2D of this step's inputs (pinned host memory)
+        ev, cc = hc.count_all_homoplasy_events()         # D2H: per-site Homoplasy_Events records
+        st, mt = hc.assoc()                              # D2H: per-informative-site statistics + sorted maxT
+        return hc.timings(), ev, st, mt
+
+    for _ in range(args.warmup):
+        tm = step_resident()
+
+    # ---- timed: inputs resident in HBM ---------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    k1_ms, launches, parts = [], 0, {}
+    barrier()
+    t0 = time.perf_counter()
+    hc.stopwatch_start()
+    for _ in range(args.steps):
+        tm = step_resident()
+        k1_ms.append(tm["ms_events_kernel"])
+        launches += int(tm["n_launches"])
+        for k in ("ms_events_kernel", "ms_events_total", "ms_tally", "ms_ptable", "ms_null_gen", "ms_null_count",
+                  "ms_null_fallback", "ms_allreduce", "ms_pvalues", "ms_assoc_total"):
+            parts[k] = parts.get(k, 0.0) + tm[k] / args.steps
+    dev_ms = hc.stopwatch_stop_ms()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    total_sites = S * world
+    value = total_sites * args.steps / (dev_ms / 1e3)
+
+    # ---- timed: end to end through the public API with host buffers ------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tm_e, ev, st, mt = step_e2e()
+    barrier()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    h2d = 3 * N * W * 8
+    d2h = S * _lib.SITE_DTYPE.itemsize + len(st) * _lib.STAT_DTYPE.itemsize + m * 8
+    e2e_value = total_sites * args.steps / (e2e_ms / 1e3)
+    n_draws = sum_over_ranks(tm["n_alleles_in_use"]) * m
+
+    # ---- roofline of the HBM-bound counting kernel (K1) -----------------------------------------------
+    peak, peak_src = measured_hbm_peak()
+    k1_avg = float(np.mean(k1_ms))
+    alg_bytes = int(tm["k1_algorithmic_bytes"])
+    achieved = alg_bytes / (k1_avg / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            tj = json.load(f)
+            if tj.get("sites") == S and tj.get("nodes") == N:
+                traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"kernel": "k1_events_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k1_avg, "peak_source": peak_src,
+                "frac_of_nominal_8TBps": achieved / 8000.0}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_cores()
+        v, l4, l5 = cpu_reference_pass(tree, cpu_chars, sn, lab, m, 20260, threads)
+        cpu_baseline = {"value": v, "unit": "sites/s", "cores": threads, "kind": "port",
+                        "sample": "%d-site slice of this workload at the full m=%d (C++ port oracle/oracle.cpp; events %.2f s + assoc %.2f s)"
+                                  % (cpu_chars.shape[1], m, l4, l5)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64 bit planes / int32 counts / f64 p-values", "data": "synthetic",
+                "config": bench_config(args, cfg, S, m, tree, world),
+                "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / args.steps, "timer": "host wall clock around synchronous C-ABI calls, max over ranks"},
+                "gpu_launches": launches,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+                "replicate_draws_per_sec": n_draws * args.steps / (dev_ms / 1e3),
+                "wall_ms_per_step": wall_ms / args.steps,
+                "breakdown_ms": parts,
+                "counts": {"informative_sites": int(tm["n_informative"]), "alleles_in_use": int(tm["n_alleles_in_use"]),
+                           "extant_events": int(tm["n_extant_events"]), "fast_alleles": int(tm["n_fast_alleles"]),
+                           "maxt_fallback_reps": int(tm["n_maxt_fallback_reps"])},
+                "synth_seconds": t_gen}
+        print(json.dumps(line), flush=True)
+    hc.close()
+    for p in pinned:
+        _lib.pinned_free(p)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--sites", type=int, default=0, help="override sites per GPU (scaled-down runs)")
+    ap.add_argument("--replicates", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)
+    sys.exit(run_reference(args) if args.impl == "reference" else run_b200(args))
+
+
+if __name__ == "__main__":
+    main()

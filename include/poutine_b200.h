@@ -154,6 +154,10 @@ int pb_get_event_csr(pb_ctx* ctx, int64_t* offsets /* 2*n_inf+1 */, int32_t* sam
 int pb_get_maxT_unsorted(pb_ctx* ctx, double* out /* m */);
 int pb_get_ptable(pb_ctx* ctx, int32_t* n_max, double* out, int64_t cap);
 int pb_get_timings(pb_ctx* ctx, pb_timings* out);
+/* Stopwatch on the library's own stream (CUDA events): which = 0 records the start mark, 1 the stop
+ * mark; pb_stopwatch_ms synchronises on the stop mark and returns the device time between them. */
+int pb_stopwatch_mark(pb_ctx* ctx, int32_t which);
+int pb_stopwatch_ms(pb_ctx* ctx, float* ms);
 
 /* Multi-GPU: one context per GPU, sites sharded; the only exchange is an NCCL all-reduce(min)
  * of maxT[m] inside pb_run_assoc.  Rank 0 creates the id, the host broadcasts its 128 bytes. */

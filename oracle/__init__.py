@@ -52,6 +52,8 @@ def lib():
         L.or_create.restype = vp; L.or_create.argtypes = [i32, vp, i32, vp]
         L.or_destroy.restype = None; L.or_destroy.argtypes = [vp]
         L.or_count_all_homoplasy_events.restype = i64; L.or_count_all_homoplasy_events.argtypes = [vp, i64, vp, vp]
+        L.or_count_all_homoplasy_events_mt.restype = i64
+        L.or_count_all_homoplasy_events_mt.argtypes = [vp, i64, vp, vp, C.c_int]
         L.or_get_events.restype = None; L.or_get_events.argtypes = [vp, vp]
         L.or_get_class_counts.restype = None; L.or_get_class_counts.argtypes = [vp, vp]
         L.or_get_mrca.restype = i64; L.or_get_mrca.argtypes = [vp, i64, C.c_int, vp, i64]
@@ -113,13 +115,13 @@ class Oracle:
             lib().or_destroy(self._h)
             self._h = None
 
-    def count_all_homoplasy_events(self, seq, physical_poss=None):
+    def count_all_homoplasy_events(self, seq, physical_poss=None, n_threads=1):
         """seq: (N, S) array of bytes/chars (node-major)."""
         seq = np.ascontiguousarray(seq)
         assert seq.ndim == 2 and seq.shape[0] == len(self.parent) and seq.dtype.itemsize == 1
         S = seq.shape[1]
         pp = None if physical_poss is None else np.ascontiguousarray(physical_poss, dtype=np.int32)
-        self.n_events = lib().or_count_all_homoplasy_events(self._h, S, _p(seq), _p(pp))
+        self.n_events = lib().or_count_all_homoplasy_events_mt(self._h, S, _p(seq), _p(pp), int(n_threads))
         ev = np.empty(self.n_events, dtype=SITE_DTYPE)
         lib().or_get_events(self._h, _p(ev))
         cc = np.empty(5, dtype=np.int64)

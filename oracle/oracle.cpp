@@ -198,12 +198,15 @@ void* or_create(int32_t N, const int32_t* parent, int32_t L, const int32_t* leaf
 void or_destroy(void* h) { delete (Oracle*)h; }
 
 // seq is node-major: genotype of node v at site i = seq[v*S + i]  (HashMap<String,char[]> seg_sites)
-int64_t or_count_all_homoplasy_events(void* h, int64_t S, const char* seq, const int32_t* physical_poss) {
-    Oracle& o = *(Oracle*)h;
-    o.events.clear(); o.mrca[0].clear(); o.mrca[1].clear();
-    o.n_mono = o.n_bi = o.n_tri = o.n_quad = o.n_other = 0;
+struct L4Part {
+    std::vector<or_site_t> events;
+    std::vector<std::vector<int32_t>> mrca[2];
+    int64_t n_mono = 0, n_bi = 0, n_tri = 0, n_quad = 0, n_other = 0;
+};
+
+static void l4_range(const Oracle& o, int64_t S, const char* seq, const int32_t* physical_poss, int64_t i0, int64_t i1, L4Part& out) {
     const int32_t root = o.root;
-    for (int64_t i = 0; i < S; i++) {                       // HC.java:1418
+    for (int64_t i = i0; i < i1; i++) {                     // HC.java:1418
         auto geno = [&](int32_t v) -> char { return seq[(int64_t)v * S + i]; };  // get_node_genotype, HC.java:1823-1830
         // get_alleles (HC.java:1593-1603): leaf genotypes in [ACGT] grouped by allele.
         // HashMap<Character,...> iteration order = bucket order (c & 15): A(1) C(3) T(4) G(7).
@@ -216,11 +219,11 @@ int64_t or_count_all_homoplasy_events(void* h, int64_t S, const char* seq, const
         int n_alleles = 0;
         for (int c = 0; c < 4; c++) n_alleles += cnt[c] > 0;
         switch (n_alleles) {                                 // HC.java:1443-1473
-            case 2: o.n_bi++; break;
-            case 1: o.n_mono++; continue;
-            case 3: o.n_tri++; continue;
-            case 4: o.n_quad++; continue;
-            default: o.n_other++; continue;
+            case 2: out.n_bi++; break;
+            case 1: out.n_mono++; continue;
+            case 3: out.n_tri++; continue;
+            case 4: out.n_quad++; continue;
+            default: out.n_other++; continue;
         }
         // identify_major_minor_alleles (HC.java:1712-1743)
         int first = -1, second = -1;
@@ -260,11 +263,39 @@ int64_t or_count_all_homoplasy_events(void* h, int64_t S, const char* seq, const
         for (int32_t v : a2_order) e.a2_extant += o.is_leaf[v];
         std::sort(a1_order.begin(), a1_order.end());
         std::sort(a2_order.begin(), a2_order.end());
-        o.events.push_back(e);
-        o.mrca[0].push_back(std::move(a1_order));
-        o.mrca[1].push_back(std::move(a2_order));
+        out.events.push_back(e);
+        out.mrca[0].push_back(std::move(a1_order));
+        out.mrca[1].push_back(std::move(a2_order));
+    }
+}
+
+// n_threads > 1 splits the site loop into contiguous ranges (sites are independent, HC.java:1418 carries
+// only the class counters) and concatenates in site order.  The reference itself runs this loop on ONE
+// thread (README.md:127); the threaded form exists so the CPU baseline can use every host core.
+int64_t or_count_all_homoplasy_events_mt(void* h, int64_t S, const char* seq, const int32_t* physical_poss, int n_threads) {
+    Oracle& o = *(Oracle*)h;
+    o.events.clear(); o.mrca[0].clear(); o.mrca[1].clear();
+    o.n_mono = o.n_bi = o.n_tri = o.n_quad = o.n_other = 0;
+    if (n_threads < 1) n_threads = 1;
+    if ((int64_t)n_threads > S) n_threads = (int)(S > 0 ? S : 1);
+    std::vector<L4Part> parts(n_threads);
+    if (n_threads == 1) l4_range(o, S, seq, physical_poss, 0, S, parts[0]);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back([&, t] { l4_range(o, S, seq, physical_poss, S * t / n_threads, S * (t + 1) / n_threads, parts[t]); });
+        for (auto& t : th) t.join();
+    }
+    for (L4Part& p : parts) {
+        o.n_mono += p.n_mono; o.n_bi += p.n_bi; o.n_tri += p.n_tri; o.n_quad += p.n_quad; o.n_other += p.n_other;
+        o.events.insert(o.events.end(), p.events.begin(), p.events.end());
+        for (int a = 0; a < 2; a++)
+            for (auto& v : p.mrca[a]) o.mrca[a].push_back(std::move(v));
     }
     return (int64_t)o.events.size();
+}
+int64_t or_count_all_homoplasy_events(void* h, int64_t S, const char* seq, const int32_t* physical_poss) {
+    return or_count_all_homoplasy_events_mt(h, S, seq, physical_poss, 1);
 }
 
 void or_get_events(void* h, or_site_t* out) {

@@ -52,7 +52,7 @@ class PbTimings(C.Structure):
 
 EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_set_tree", "pb_set_labels", "pb_set_sites", "pb_put_planes",
            "pb_run_events", "pb_run_assoc", "pb_get_sites", "pb_get_raw_events", "pb_get_event_csr",
-           "pb_get_maxT_unsorted", "pb_get_ptable", "pb_get_timings", "pb_comm_unique_id", "pb_comm_init",
+           "pb_get_maxT_unsorted", "pb_get_ptable", "pb_get_timings", "pb_stopwatch_mark", "pb_stopwatch_ms", "pb_comm_unique_id", "pb_comm_init",
            "pb_pack_chars", "pb_host_alloc", "pb_host_free", "pb_version"]
 
 
@@ -92,6 +92,8 @@ def lib():
         L.pb_get_maxT_unsorted.argtypes = [vp, vp]
         L.pb_get_ptable.argtypes = [vp, C.POINTER(i32), vp, i64]
         L.pb_get_timings.argtypes = [vp, C.POINTER(PbTimings)]
+        L.pb_stopwatch_mark.argtypes = [vp, i32]
+        L.pb_stopwatch_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.pb_comm_unique_id.argtypes = [vp]
         L.pb_comm_init.argtypes = [vp, vp, i32, i32]
         L.pb_pack_chars.argtypes = [vp, i64, i64, i64, vp, vp, vp, i64]

@@ -166,6 +166,16 @@ class HomoplasyCounter:
         self._check(_lib.lib().pb_get_timings(self._h, C.byref(t)))
         return t.as_dict()
 
+    def stopwatch_start(self):
+        self._check(_lib.lib().pb_stopwatch_mark(self._h, 0))
+
+    def stopwatch_stop_ms(self):
+        """device milliseconds between the two marks (CUDA events on the library's stream)"""
+        self._check(_lib.lib().pb_stopwatch_mark(self._h, 1))
+        ms = C.c_float(0)
+        self._check(_lib.lib().pb_stopwatch_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def raw_events(self):
         n = C.c_int64(0)
         self._check(_lib.lib().pb_get_raw_events(self._h, 0, None, None, C.byref(n)))

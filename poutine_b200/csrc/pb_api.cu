@@ -405,6 +405,23 @@ extern "C" int pb_get_timings(pb_ctx* ctx, pb_timings* out) {
     return PB_OK;
 }
 
+extern "C" int pb_stopwatch_mark(pb_ctx* ctx, int32_t which) {
+    CHECK_CTX(ctx);
+    if (which != 0 && which != 1) FAIL(ctx, PB_ERR_INVALID, "pb_stopwatch_mark: which must be 0 or 1");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    PB_CUDA(cudaEventRecord(ctx->ev[14 + which], ctx->stream));
+    return PB_OK;
+}
+
+extern "C" int pb_stopwatch_ms(pb_ctx* ctx, float* ms) {
+    CHECK_CTX(ctx);
+    if (!ms) return PB_ERR_INVALID;
+    PB_CUDA(cudaSetDevice(ctx->device));
+    PB_CUDA(cudaEventSynchronize(ctx->ev[15]));
+    PB_CUDA(cudaEventElapsedTime(ms, ctx->ev[14], ctx->ev[15]));
+    return PB_OK;
+}
+
 extern "C" int pb_comm_unique_id(void* id128) {
     std::string err;
     int rc = pbn_unique_id(id128, err);

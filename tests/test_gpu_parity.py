@@ -1,0 +1,370 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(libpoutine_b200.so via poutine_b200.HomoplasyCounter), against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): event counts, descendant tallies, observed statistics and — in
+replay mode and in Philox mode alike, since the oracle restates the sampling spec — r / maxT counts are
+BIT-EXACT; binomial p-values are compared bit-for-bit as well (the device chain is the same
+commons-math restatement compiled without FMA), which is stricter than the stated 1e-12 relative.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import poutine_b200 as pb
+from poutine_b200 import synth
+from tests.helpers import assert_stats_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    pb.build()
+
+
+def run_gpu_events(tree, chars=None, planes=None, n_sites=None, **kw):
+    hc = pb.HomoplasyCounter(**kw)
+    hc.set_tree(tree.parent if hasattr(tree, "parent") else tree[0], tree.is_leaf if hasattr(tree, "is_leaf") else tree[1])
+    if chars is not None:
+        hc.set_seg_sites(chars)
+    else:
+        hc.set_planes(*planes, n_sites)
+    ev, cc = hc.count_all_homoplasy_events()
+    return hc, ev, cc
+
+
+def assert_events_equal(gpu_ev, gpu_cc, or_ev, or_cc):
+    assert gpu_cc["mono"] == or_cc["mono"] and gpu_cc["bi"] == or_cc["bi"] and gpu_cc["tri"] == or_cc["tri"]
+    assert gpu_cc["quad"] == or_cc["quad"] and gpu_cc["no_allele"] == or_cc["other"]
+    assert len(gpu_ev) == len(or_ev)
+    for f in ("segsite_id", "allele1", "allele2", "a1_count", "a2_count", "a1_extant", "a2_extant"):
+        np.testing.assert_array_equal(gpu_ev[f], or_ev[f], err_msg=f)
+
+
+def gpu_mrca_sets(hc, tree, ev_all):
+    """Rebuild the per-site MRCA buckets from the raw device event list (+ the root rule)."""
+    site, node = hc.raw_events()
+    return site, node
+
+
+# -------------------------------------------------------------------------------------------------
+# K1: events
+# -------------------------------------------------------------------------------------------------
+def test_hand_fixture_events(oracle_mod, golden_dir):
+    with open(os.path.join(golden_dir, "events_hand.json")) as f:
+        fx = json.load(f)
+    N = len(fx["names"])
+    chars = np.array([[ord(s["column"][v]) for s in fx["sites"]] for v in range(N)], dtype=np.uint8)
+    parent = np.array(fx["parent"], dtype=np.int32)
+    is_leaf = np.zeros(N, dtype=np.uint8)
+    is_leaf[fx["leaves"]] = 1
+    hc, ev, cc = run_gpu_events((parent, is_leaf), chars=chars, num_replicates=10)
+    got = {int(e["segsite_id"]): e for e in ev}
+    for i, s in enumerate(fx["sites"]):
+        if s["expected"] is None:
+            assert i + 1 not in got, s["name"]
+        else:
+            e = got[i + 1]
+            tup = [chr(e["allele1"]), chr(e["allele2"]), int(e["a1_count"]), int(e["a2_count"]), int(e["a1_extant"]), int(e["a2_extant"])]
+            assert tup == s["expected"], s["name"]
+    want = fx["class_counts"]
+    assert (cc["mono"], cc["bi"], cc["tri"], cc["quad"], cc["no_allele"]) == (want["mono"], want["bi"], want["tri"], want["quad"], want["other"])
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_events_nasty_random_trees(oracle_mod, seed):
+    """polytomies, leaves on the root, shuffled node ids; gaps, lowercase, third alleles, ties, N at root"""
+    tree = synth.random_tree(15 + 23 * seed, 300 + seed, polytomy=0.3, root_leaf_children=seed % 3)
+    S = [1, 63, 64, 65, 200, 777, 1000, 129, 640, 2049][seed]
+    chars = synth.simulate_chars(tree, S, 400 + seed, nasty=True)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(chars)
+    hc, ev, cc = run_gpu_events(tree, chars=chars, num_replicates=10)
+    assert_events_equal(ev, cc, or_ev, or_cc)
+    # MRCA node sets, not only their sizes: raw events (pre-clearing, root excluded) vs the oracle's buckets
+    site, node = hc.raw_events()
+    gpu_sets = {}
+    for s, v in zip(site.tolist(), node.tolist()):
+        gpu_sets.setdefault(s + 1, set()).add(v)
+    assert len(site) == sum(len(v) for v in gpu_sets.values()), "duplicate raw events"
+    root = tree.root
+    for i, e in enumerate(or_ev):
+        want = set(o.mrca(i, 0).tolist()) | set(o.mrca(i, 1).tolist())
+        have = gpu_sets.get(int(e["segsite_id"]), set())
+        # oracle buckets are post-clearing: every surviving member other than the root must be a raw event
+        assert want - {root} <= have, (seed, i)
+        if e["a1_count"] >= 2 and e["a2_count"] >= 2:
+            assert want - {root} == have, (seed, i)
+
+
+def test_events_c1_slice_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "c1_slice.npz"))
+    S = int(z["n_sites"])
+    hc, ev, cc = run_gpu_events((z["parent"], z["is_leaf"]), planes=(z["B0"], z["B1"], z["V"]), n_sites=S, num_replicates=10)
+    gold = z["events"]
+    assert_events_equal(ev, cc, gold, dict(zip(("mono", "bi", "tri", "quad", "other"), z["class_counts"].tolist())))
+
+
+def test_events_tiled_upload_and_pitch(oracle_mod):
+    """pb_put_planes column tiles with a foreign row pitch give the same result as one upload."""
+    tree = synth.yule_tree(120, 5)
+    S = 64 * 37 + 11
+    B0, B1, V = synth.simulate_planes(tree, S, 6, leaf_gap=True, multiallelic_frac=0.05, third_allele_internal_frac=0.05)
+    hc1, ev1, cc1 = run_gpu_events(tree, planes=(B0, B1, V), n_sites=S, num_replicates=10)
+    hc2 = pb.HomoplasyCounter(num_replicates=10)
+    hc2.set_tree(tree.parent, tree.is_leaf)
+    hc2.set_planes(B0, B1, V, S, tile_words=5)   # slices of a wider array: pitch != n_words
+    ev2, cc2 = hc2.count_all_homoplasy_events()
+    assert ev1.tobytes() == ev2.tobytes() and cc1 == cc2
+    chars = synth.planes_to_chars(B0, B1, V, 0, S)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(chars)
+    assert_events_equal(ev1, cc1, or_ev, or_cc)
+    assert cc1["tri"] + cc1["quad"] > 0
+
+
+def test_events_many_chunks_and_site_offset(oracle_mod, monkeypatch):
+    """force the edge schedule into many chunks (census partials are summed across chunks)"""
+    tree = synth.yule_tree(700, 11)
+    S = 500
+    B0, B1, V = synth.simulate_planes(tree, S, 12, leaf_gap=True)
+    chars = synth.planes_to_chars(B0, B1, V, 0, S)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(chars)
+    for chunks in ("1", "7", "21"):
+        monkeypatch.setenv("PB_K1_CHUNKS", chunks)
+        hc, ev, cc = run_gpu_events(tree, planes=(B0, B1, V), n_sites=S, num_replicates=10, site_offset=6400)
+        ev = ev.copy()
+        ev["segsite_id"] -= 6400
+        assert_events_equal(ev, cc, or_ev, or_cc)
+
+
+def test_events_dense_overflowing_queue(oracle_mod):
+    """every edge an event at every site: shared queue overflow path + event-buffer regrow"""
+    tree = synth.yule_tree(300, 21)
+    S = 64 * 40
+    rng = np.random.default_rng(3)
+    N = tree.n_nodes
+    chars = np.frombuffer(b"AC", dtype=np.uint8)[rng.integers(0, 2, size=(N, S))]
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(chars)
+    hc, ev, cc = run_gpu_events(tree, chars=chars, num_replicates=10)
+    assert_events_equal(ev, cc, or_ev, or_cc)
+    assert cc["raw_events"] > 4 * S
+
+
+# -------------------------------------------------------------------------------------------------
+# K2/K3/K4: association
+# -------------------------------------------------------------------------------------------------
+def _assoc_case(oracle_mod, n_leaves, S, m, seed, na_frac, no_row_frac, min_hcount=1, nasty=False, **kw):
+    tree = synth.yule_tree(n_leaves, seed)
+    if nasty:
+        chars = synth.simulate_chars(tree, S, seed + 1, nasty=True)
+    else:
+        chars = synth.planes_to_chars(*synth.simulate_planes(tree, S, seed + 1), 0, S)
+    sn, lab = synth.simulate_phenotypes(tree, seed + 2, na_frac=na_frac, no_row_frac=no_row_frac)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, _ = o.count_all_homoplasy_events(chars)
+    hc = pb.HomoplasyCounter(num_replicates=m, min_hcount=min_hcount, **kw)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_seg_sites(chars)
+    hc.count_all_homoplasy_events()
+    hc.set_phenos(sn, lab)
+    hc.count_all_homoplasy_events()   # labels reset the CSR: events must be re-run (documented call order)
+    return tree, o, hc, sn, lab
+
+
+@pytest.mark.parametrize("na_frac,no_row_frac,force_general,min_hcount", [
+    (0.0, 0.0, False, 1),     # all labelled: bit-sliced threshold path
+    (0.0, 0.0, True, 1),      # same inputs through the general scalar path
+    (0.05, 0.03, False, 1),   # missing labels + leaves without a pheno row
+    (0.0, 0.1, False, 2),
+    (0.05, 0.0, False, 0),    # min_hcount 0: every biallelic site informative, n may be 0
+])
+def test_assoc_replay_bit_exact(oracle_mod, na_frac, no_row_frac, force_general, min_hcount):
+    m = 700
+    tree, o, hc, sn, lab = _assoc_case(oracle_mod, 150, 900, m, 31, na_frac, no_row_frac, min_hcount=min_hcount,
+                                       replay=True, force_general_null=force_general)
+    perms = oracle_mod.java_shuffle_perms(77, m, len(lab))
+    st, mt_s, mt_u = o.assoc(sn, lab, m, min_hcount, perms=perms)
+    g_st, g_mt = hc.assoc(replay_perms=perms)
+    assert_stats_equal(g_st, st)
+    np.testing.assert_array_equal(g_mt.view(np.uint64), mt_s.view(np.uint64))
+    np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), mt_u.view(np.uint64))
+    tm = hc.timings()
+    if force_general:
+        assert tm["n_fast_alleles"] == 0
+    elif na_frac == 0:
+        assert tm["n_fast_alleles"] > 0
+
+
+@pytest.mark.parametrize("na_frac", [0.0, 0.04])
+def test_assoc_philox_bit_exact(oracle_mod, na_frac):
+    """Philox mode: the oracle restates the sampling spec, so r/maxT are bit-exact here too."""
+    m = 1500
+    tree, o, hc, sn, lab = _assoc_case(oracle_mod, 200, 1200, m, 41, na_frac, 0.02, seed=0xC0FFEE1234)
+    st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=None, seed=0xC0FFEE1234, n_threads=4)
+    g_st, g_mt = hc.assoc()
+    assert_stats_equal(g_st, st)
+    np.testing.assert_array_equal(g_mt.view(np.uint64), mt_s.view(np.uint64))
+    np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), mt_u.view(np.uint64))
+
+
+def test_assoc_nasty_inputs_replay(oracle_mod):
+    m = 300
+    tree, o, hc, sn, lab = _assoc_case(oracle_mod, 90, 700, m, 51, 0.05, 0.05, nasty=True, replay=True)
+    perms = oracle_mod.java_shuffle_perms(5, m, len(lab))
+    st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=perms)
+    g_st, g_mt = hc.assoc(replay_perms=perms)
+    assert_stats_equal(g_st, st)
+    np.testing.assert_array_equal(g_mt.view(np.uint64), mt_s.view(np.uint64))
+
+
+@pytest.mark.parametrize("tau", [1e-300, 1.0])
+def test_assoc_maxt_threshold_extremes(oracle_mod, tau):
+    """tau tiny: every replicate goes through the maxT fallback kernel; tau = 1: every allele is a candidate."""
+    m = 256
+    tree, o, hc, sn, lab = _assoc_case(oracle_mod, 120, 600, m, 61, 0.0, 0.0, replay=True, maxt_tau=tau)
+    perms = oracle_mod.java_shuffle_perms(9, m, len(lab))
+    st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=perms)
+    g_st, g_mt = hc.assoc(replay_perms=perms)
+    assert_stats_equal(g_st, st)
+    np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), mt_u.view(np.uint64))
+    if tau < 1e-100:
+        assert hc.timings()["n_maxt_fallback_reps"] == m
+
+
+def test_assoc_c1_slice_golden(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "c1_slice.npz"))
+    S, m = int(z["n_sites"]), int(z["m"])
+    hc = pb.HomoplasyCounter(num_replicates=m, replay=True)
+    hc.set_tree(z["parent"], z["is_leaf"])
+    hc.set_phenos(z["sample_node"], z["label"])
+    hc.set_planes(z["B0"], z["B1"], z["V"], S)
+    hc.count_all_homoplasy_events()
+    perms = oracle_mod.java_shuffle_perms(int(z["perm_seed"]), m, len(z["label"]))
+    g_st, g_mt = hc.assoc(replay_perms=perms)
+    assert_stats_equal(g_st, z["stats"])
+    np.testing.assert_array_equal(g_mt.view(np.uint64), z["maxT_sorted"].view(np.uint64))
+    np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), z["maxT_unsorted"].view(np.uint64))
+
+
+def test_ptable_bit_exact_vs_commons_math_port(oracle_mod, golden_dir):
+    """device f[n][k] == the oracle's commons-math restatement (itself pinned to the jar bytecode)."""
+    m = 64
+    tree, o, hc, sn, lab = _assoc_case(oracle_mod, 400, 800, m, 71, 0.0, 0.0)
+    hc.assoc()
+    n_max, tab = hc.ptable()
+    p = float((lab == 1).sum()) / float((lab == 1).sum() + (lab == 0).sum())
+    ref = oracle_mod.binomial_table(n_max, p)
+    np.testing.assert_array_equal(tab.view(np.uint64), ref.view(np.uint64))
+    assert n_max >= 2
+
+
+def test_ptable_golden_values_on_device(oracle_mod, golden_dir):
+    """the minijvm-generated golden vectors (commons-math 3.6.1 bytecode) at p = 0.379, through the device table"""
+    with open(os.path.join(golden_dir, "binom_golden.json")) as f:
+        t = json.load(f)["table"]
+    p, g_nmax = float.fromhex(t["p"]), t["n_max"]
+    assert p == 0.379
+    gold = np.array([float.fromhex(x) for x in t["f"]])
+    # 379 cases of 1000 samples -> calc_background_p_success = 379/1000 = 0.379 exactly as a double
+    tree = synth.yule_tree(1000, 81)
+    chars = synth.planes_to_chars(*synth.simulate_planes(tree, 3000, 82, mean_extra_mut=6.0), 0, 3000)
+    lab = np.zeros(1000, dtype=np.uint8)
+    lab[:379] = 1
+    hc = pb.HomoplasyCounter(num_replicates=32)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(tree.leaf_nodes, lab)
+    hc.set_seg_sites(chars)
+    hc.count_all_homoplasy_events()
+    hc.assoc()
+    n_max, tab = hc.ptable()
+    n_cmp = min(n_max, g_nmax)
+    assert n_cmp >= 4
+    cnt = (n_cmp + 1) * (n_cmp + 2) // 2
+    np.testing.assert_array_equal(tab[:cnt].view(np.uint64), gold[:cnt].view(np.uint64))
+
+
+def test_no_informative_sites_error(oracle_mod):
+    tree = synth.yule_tree(50, 3)
+    chars = synth.simulate_chars(tree, 40, 4, nasty=False)
+    sn, lab = synth.simulate_phenotypes(tree, 5)
+    hc = pb.HomoplasyCounter(num_replicates=10, min_hcount=1000)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_seg_sites(chars)
+    hc.count_all_homoplasy_events()
+    with pytest.raises(pb.NoInformativeSites):      # HC.java:3866-3869
+        hc.assoc()
+
+
+def test_call_order_errors():
+    hc = pb.HomoplasyCounter(num_replicates=10)
+    with pytest.raises(pb.PoutineError):
+        hc.set_sites(100)                            # no tree yet
+    tree = synth.yule_tree(20, 1)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    with pytest.raises(pb.PoutineError):
+        hc.set_phenos(np.array([0], dtype=np.int32), np.array([1], dtype=np.uint8))   # node 0 is the root, not a leaf
+    hc.set_sites(100)
+    hc.count_all_homoplasy_events()
+    with pytest.raises(pb.PoutineError):
+        hc.assoc()                                   # no labels
+
+
+# -------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE config C2 shape, scaled in S to keep the test short)
+# -------------------------------------------------------------------------------------------------
+def test_large_properties_and_slice_parity(oracle_mod):
+    tree = synth.yule_tree(5000, 20262)
+    S = 200_000
+    B0, B1, V = synth.simulate_planes(tree, S, 20262 + 2000)
+    sn, lab = synth.simulate_phenotypes(tree, 20262 + 1000)
+    m = 20_000
+    hc = pb.HomoplasyCounter(num_replicates=m, seed=7)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_planes(B0, B1, V, S)
+    ev, cc = hc.count_all_homoplasy_events()
+    assert cc["mono"] + cc["bi"] + cc["tri"] + cc["quad"] + cc["no_allele"] == S
+    # invariants of the reference code (SURVEY §4 i-iii)
+    assert np.all((ev["a1_count"] == 0) | (ev["a1_count"] >= 2)) and np.all((ev["a2_count"] == 0) | (ev["a2_count"] >= 2))
+    assert np.all(ev["a1_extant"] <= ev["a1_count"]) and np.all(ev["a2_extant"] <= ev["a2_count"])
+    st, mt = hc.assoc()
+    evs = hc.sites[st["site_index"]]
+    expect = np.where(st["a1_in_use"] == 1, evs["a1_extant"], 0) + np.where(st["a2_in_use"] == 1, evs["a2_extant"], 0)
+    np.testing.assert_array_equal(st["obs_counts"].sum(axis=1), expect)     # check_extant_nodes_only_code (HC.java:4345-4369)
+    for a in ("a1", "a2"):
+        use = st[a + "_in_use"] == 1
+        r = st["r_" + a]
+        assert np.all((r[use] >= 0) & (r[use] <= m)) and np.all(r[~use] == -1)
+        np.testing.assert_array_equal(st["pointwise_" + a][use], (r[use] + 1.0) / (m + 1.0))
+        np.testing.assert_array_equal(st["familywise_" + a][use], (st["r_maxT_" + a][use] + 1.0) / (m + 1.0))
+        # pooled min over all alleles <= this allele's own p  =>  r_maxT >= r
+        assert np.all(st["r_maxT_" + a][use] >= r[use])
+    assert np.all(np.diff(mt) >= 0) and mt[0] > 0 and mt[-1] <= 1
+    # a 1,536-site slice through the literal oracle: events bit-exact
+    s0, s1 = 64 * 1000, 64 * 1024
+    chars = synth.planes_to_chars(B0, B1, V, s0, s1)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, _ = o.count_all_homoplasy_events(chars)
+    sl = hc.sites[s0:s1]
+    sl = sl[sl["site_class"] == 2].copy()
+    sl["segsite_id"] -= s0
+    for f in ("segsite_id", "allele1", "allele2", "a1_count", "a2_count", "a1_extant", "a2_extant"):
+        np.testing.assert_array_equal(sl[f], or_ev[f], err_msg=f)
+    # Monte-Carlo acceptance of the point-wise p-values against the exact hypergeometric tail
+    # (all labels present: k_r ~ Hypergeom(P, cases, n)); 6-sigma binomial band at m replicates
+    from scipy.stats import hypergeom
+    P, K = len(lab), int((lab == 1).sum())
+    use = st["a1_in_use"] == 1
+    n = st["obs_counts"][use][:, 0] + st["obs_counts"][use][:, 1]
+    k = st["obs_counts"][use][:, 0]
+    exact = hypergeom.sf(k - 1, P, K, n)
+    mc = st["r_a1"][use] / m
+    sd = np.sqrt(np.maximum(exact * (1 - exact), 1e-12) / m)
+    # the statistic is f(n,k) <= f(n,k_obs) <=> k >= k_obs when f(n,.) is strictly decreasing (true for 0<p<1)
+    assert np.all(np.abs(mc - exact) < 6 * sd + 2.0 / m)
