@@ -120,7 +120,6 @@ def pinned_empty(shape, dtype):
         raise MemoryError(lib().pb_last_error(None).decode())
     buf = (C.c_char * max(n, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    arr._pb_base = p  # type: ignore[attr-defined]
     return arr, p
 
 

@@ -158,13 +158,13 @@ def test_events_dense_overflowing_queue(oracle_mod):
 # -------------------------------------------------------------------------------------------------
 # K2/K3/K4: association
 # -------------------------------------------------------------------------------------------------
-def _assoc_case(oracle_mod, n_leaves, S, m, seed, na_frac, no_row_frac, min_hcount=1, nasty=False, **kw):
-    tree = synth.yule_tree(n_leaves, seed)
+def _assoc_case(oracle_mod, n_leaves, S, m, tseed, na_frac, no_row_frac, min_hcount=1, nasty=False, **kw):
+    tree = synth.yule_tree(n_leaves, tseed)
     if nasty:
-        chars = synth.simulate_chars(tree, S, seed + 1, nasty=True)
+        chars = synth.simulate_chars(tree, S, tseed + 1, nasty=True)
     else:
-        chars = synth.planes_to_chars(*synth.simulate_planes(tree, S, seed + 1), 0, S)
-    sn, lab = synth.simulate_phenotypes(tree, seed + 2, na_frac=na_frac, no_row_frac=no_row_frac)
+        chars = synth.planes_to_chars(*synth.simulate_planes(tree, S, tseed + 1), 0, S)
+    sn, lab = synth.simulate_phenotypes(tree, tseed + 2, na_frac=na_frac, no_row_frac=no_row_frac)
     o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
     or_ev, _ = o.count_all_homoplasy_events(chars)
     hc = pb.HomoplasyCounter(num_replicates=m, min_hcount=min_hcount, **kw)
