@@ -232,10 +232,17 @@ def run_b200(args):
         hc.assoc(fetch=False)
         return hc.timings()
 
+    e2e_parts = {"put_planes": 0.0, "events": 0.0, "assoc": 0.0}
+
     def step_e2e():
+        t0 = time.perf_counter()
         hc.put_planes(*host_planes)                      # H2D of this step's inputs (pinned host memory)
+        t1 = time.perf_counter()
         ev, cc = hc.count_all_homoplasy_events()         # D2H: per-site Homoplasy_Events records
+        t2 = time.perf_counter()
         st, mt = hc.assoc()                              # D2H: per-informative-site statistics + sorted maxT
+        t3 = time.perf_counter()
+        e2e_parts["put_planes"] += 1e3 * (t1 - t0); e2e_parts["events"] += 1e3 * (t2 - t1); e2e_parts["assoc"] += 1e3 * (t3 - t2)
         return hc.timings(), ev, st, mt
 
     for _ in range(args.warmup):
@@ -267,6 +274,8 @@ def run_b200(args):
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     barrier()
+    for k in e2e_parts:
+        e2e_parts[k] = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         tm_e, ev, st, mt = step_e2e()
@@ -308,7 +317,8 @@ def run_b200(args):
                 "dtype": "u64 bit planes / int32 counts / f64 p-values", "data": "synthetic",
                 "config": bench_config(args, cfg, S, m, tree, world),
                 "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / args.steps, "timer": "host wall clock around synchronous C-ABI calls, max over ranks"},
+                        "ms_per_step": e2e_ms / args.steps,
+                        "breakdown_ms": {k: v / args.steps for k, v in e2e_parts.items()}, "timer": "host wall clock around synchronous C-ABI calls, max over ranks"},
                 "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "replicate_draws_per_sec": n_draws * args.steps / (dev_ms / 1e3),

@@ -7,14 +7,19 @@
 // Closed form of the reference's leaf->root walks: node v is an MRCA iff
 //     v != root  &&  parent(v) != root  &&  geno(v) in ACGT  &&  geno(parent(v)) != geno(v)
 // plus the root itself; v goes to bucket a1 iff geno(v) == allele1, else a2; a bucket with
-// fewer than 2 members is emptied.  The test is edge-local, so K1 streams every plane word
-// once: one thread owns one 64-site word column and walks a host-built edge schedule.
-//   * MRCA mask of an edge:  Vc & (~Vp | (B0c^B0p) | (B1c^B1p))     (3 LOP3 per 32-bit half)
-//   * events are sparse (~2.5 per site per tree): set bits are peeled with ffs and appended to a
-//     per-block shared-memory queue, flushed with ONE global atomic per block;
-//   * the leaf census (how many leaves carry A/C/G/T) is dense: bit-sliced vertical counters,
-//     a Harley-Seal carry-save tree over groups of 8 leaves (2 LOP3 per CSA per half).
-// HBM traffic = each plane bit once (parents re-hit L1/L2 thanks to the DFS edge order).
+// fewer than 2 members is emptied.  The test is edge-local, so K1 streams every plane row ONCE:
+//   * a block owns 128 word columns (8,192 sites) and one chunk of the host-built DFS edge program;
+//   * a producer warp (one elected lane) moves each row segment (3 planes x 1 KB) into an 8-stage
+//     shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx); the four
+//     consumer warps wait on the stage's full barrier, pull their 64-bit words into registers and
+//     release the stage at once (empty barrier) — memory-level parallelism comes from the ring,
+//     not from registers;
+//   * the DFS order keeps the parent row in registers: MRCA mask of an edge =
+//     Vc & (~Vp | (B0c^B0p) | (B1c^B1p)) (3 LOP3 per 32-bit half);
+//   * events are sparse (~2.5 per site per tree): set bits are peeled with ffs into a per-block
+//     shared queue, drained with one global atomic per drain;
+//   * the leaf census (how many leaves carry A/C/G/T per site) is dense: bit-sliced vertical counters,
+//     Harley-Seal carry-save levels 1/2/4 in registers, slices 8.. in shared memory.
 #include <stdio.h>
 
 #include "pb_internal.h"
@@ -24,11 +29,10 @@ struct K1Params {
     const uint64_t* __restrict__ B1;
     const uint64_t* __restrict__ V;
     int64_t Wp, W;
-    const EdgeOp* __restrict__ leaf_ops;
-    const EdgeOp* __restrict__ int_ops;
-    const int32_t* __restrict__ chunk_lg;
-    const int32_t* __restrict__ chunk_io;
-    uint64_t* __restrict__ census;  // [chunk][4][KS][W]
+    uint64_t last_mask;                    // valid site bits of word W-1
+    const uint32_t* __restrict__ ops;
+    const int32_t* __restrict__ chunk_op;
+    uint64_t* __restrict__ census;         // [flush][4][KS][W]
     raw_event_t* __restrict__ raw;
     unsigned long long* raw_cursor;
     unsigned long long raw_cap;
@@ -39,6 +43,32 @@ __device__ __forceinline__ void csa(uint64_t& h, uint64_t& l, uint64_t a, uint64
     h = (a & b) | (u & c);
     l = u ^ c;
 }
+
+// ---- mbarrier / TMA bulk-copy primitives (inline PTX) ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PB_K1_COLS) : "memory"); }
 
 __device__ __forceinline__ void emit_events(uint64_t mrca, uint64_t b0, uint64_t b1, uint32_t site_base, uint32_t node_tag,
                                             raw_event_t* s_queue, unsigned int* s_count, const K1Params& p) {
@@ -57,142 +87,177 @@ __device__ __forceinline__ void emit_events(uint64_t mrca, uint64_t b0, uint64_t
     }
 }
 
-__global__ void __launch_bounds__(PB_K1_THREADS) k1_events_kernel(const K1Params p) {
-    extern __shared__ raw_event_t s_queue[];
+// consumers only: move the block's queued events to the global list (one global atomic)
+__device__ __forceinline__ void drain_queue(raw_event_t* s_queue, unsigned int* s_count, unsigned long long* s_base, int tid,
+                                            unsigned int threshold, const K1Params& p) {
+    consumer_bar_sync();
+    const unsigned int n = min(*s_count, (unsigned int)PB_K1_QCAP);
+    if (n >= threshold && n > 0) {   // block-uniform
+        if (tid == 0) *s_base = atomicAdd(p.raw_cursor, (unsigned long long)n);
+        consumer_bar_sync();
+        const unsigned long long base = *s_base;
+        for (unsigned int i = tid; i < n; i += PB_K1_COLS) {
+            const unsigned long long pos = base + i;
+            if (pos < p.raw_cap) p.raw[pos] = s_queue[i];
+        }
+        consumer_bar_sync();
+        if (tid == 0) *s_count = 0;
+        consumer_bar_sync();
+    }
+}
+
+#define K1_ROW_BYTES (PB_K1_COLS * 8)
+#define K1_STAGE_BYTES (3 * K1_ROW_BYTES)
+#define K1_SMEM_RING (PB_K1_STAGES * K1_STAGE_BYTES)
+#define K1_SMEM_HI ((PB_K1_KHI + 1) * 4 * PB_K1_COLS * 8)   // high slices + the pending fours-level input
+#define K1_SMEM_QUEUE (PB_K1_QCAP * 8)
+#define K1_SMEM_TOTAL (K1_SMEM_RING + K1_SMEM_HI + K1_SMEM_QUEUE)
+
+__global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const K1Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* ring = reinterpret_cast<uint64_t*>(smem);                                    // [stage][plane][col]
+    uint64_t* s_hi = reinterpret_cast<uint64_t*>(smem + K1_SMEM_RING);                    // [slice][base][col]
+    raw_event_t* s_queue = reinterpret_cast<raw_event_t*>(smem + K1_SMEM_RING + K1_SMEM_HI);
+    __shared__ __align__(8) uint64_t s_full[PB_K1_STAGES], s_empty[PB_K1_STAGES];
     __shared__ unsigned int s_count;
     __shared__ unsigned long long s_base;
+
     const int tid = threadIdx.x;
-    if (tid == 0) s_count = 0;
-    __syncthreads();
-
-    const int64_t w = (int64_t)blockIdx.x * PB_K1_THREADS + tid;
     const int chunk = blockIdx.y;
-    if (w < p.W) {
-        const uint64_t* __restrict__ pV = p.V + w;
-        const uint64_t* __restrict__ pB0 = p.B0 + w;
-        const uint64_t* __restrict__ pB1 = p.B1 + w;
-        const uint32_t site_base = (uint32_t)(w * 64);
+    const int64_t col0 = (int64_t)blockIdx.x * PB_K1_COLS;
+    const int op0 = p.chunk_op[chunk], op1 = p.chunk_op[chunk + 1];
 
-        // census state: per base (A,C,G,T by 2-bit code) ones/twos/fours + high slices
-        uint64_t ones[4] = {0, 0, 0, 0}, twos[4] = {0, 0, 0, 0}, fours[4] = {0, 0, 0, 0};
-        uint64_t hi[4][PB_K1_KHI];
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-#pragma unroll
-            for (int j = 0; j < PB_K1_KHI; j++) hi[c][j] = 0;
+    if (tid == 0) {
+        s_count = 0;
+        for (int s = 0; s < PB_K1_STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], PB_K1_COLS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (tid < PB_K1_COLS)
+        for (int i = 0; i < PB_K1_KHI * 4; i++) s_hi[i * PB_K1_COLS + tid] = 0;
+    __syncthreads();
 
-        const int lg0 = p.chunk_lg[chunk], lg1 = p.chunk_lg[chunk + 1];
-        for (int g = lg0; g < lg1; ++g) {
-            const int2* __restrict__ ops = reinterpret_cast<const int2*>(p.leaf_ops + (int64_t)g * 8);
-            uint64_t f4[2][4];  // "fours" carry of each half, per base
+    if (tid >= PB_K1_COLS) {
+        // ================= producer warp: one lane feeds the ring =================
+        if (tid == PB_K1_COLS) {
+            const int64_t cols = min((int64_t)PB_K1_COLS, p.Wp - col0);   // Wp is a multiple of 16 words -> 128 B granules
+            const uint32_t bytes = (uint32_t)(cols * 8);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = op0; i < op1; i++) {
+                const uint32_t op = __ldg(p.ops + i);
+                const uint32_t node = op & PB_OP_NODE_MASK;
+                if ((op & PB_OP_FLUSH) == PB_OP_FLUSH || node == PB_OP_NULL) continue;
+                mbar_wait(&s_empty[stage], phase ^ 1);                   // consumers have drained this stage
+                mbar_arrive_expect_tx(&s_full[stage], 3 * bytes);
+                const int64_t off = (int64_t)node * p.Wp + col0;
+                uint64_t* dst = ring + (int64_t)stage * (3 * PB_K1_COLS);
+                tma_bulk_g2s(dst, p.V + off, bytes, &s_full[stage]);
+                tma_bulk_g2s(dst + PB_K1_COLS, p.B0 + off, bytes, &s_full[stage]);
+                tma_bulk_g2s(dst + 2 * PB_K1_COLS, p.B1 + off, bytes, &s_full[stage]);
+                if (++stage == PB_K1_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ================= consumer warps =================
+    const int lane = tid & 31;
+    const int64_t w = col0 + tid;
+    const uint64_t vmask = (w >= p.W) ? 0ull : (w == p.W - 1 ? p.last_mask : ~0ull);
+    const uint32_t site_base = (uint32_t)(w * 64);
+
+    uint64_t ones[4] = {0, 0, 0, 0}, twos[4] = {0, 0, 0, 0}, fours[4] = {0, 0, 0, 0};
+    uint64_t b1[4] = {0, 0, 0, 0}, b2[4] = {0, 0, 0, 0};   // pending carry-save inputs (the fours-level one lives in s_hi)
+    uint64_t* s_b4 = s_hi + (PB_K1_KHI * 4) * PB_K1_COLS + tid;
+    uint64_t pv = 0, p0 = 0, p1 = 0;   // current parent row
+    int nleaf = 0;
+    int stage = 0;
+    uint32_t phase = 0;
+
+    for (int i = op0; i < op1; i++) {
+        if (((i - op0) & 63) == 63) drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p);
+        {
+            const uint32_t op = __ldg(p.ops + i);
+            const uint32_t node = op & PB_OP_NODE_MASK;
+            if ((op & PB_OP_FLUSH) == PB_OP_FLUSH) {
+                // census partial `node`: [flush][base][slice][W]
+                if (w < p.W) {
+                    uint64_t* out = p.census + ((int64_t)node * 4 * PB_K1_KS) * p.W + w;
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-                uint64_t cv[4], c0[4], c1[4], pv[4], p0[4], p1[4];
-                int2 op[4];
+                    for (int c = 0; c < 4; c++) {
+                        out[((int64_t)c * PB_K1_KS + 0) * p.W] = ones[c];
+                        out[((int64_t)c * PB_K1_KS + 1) * p.W] = twos[c];
+                        out[((int64_t)c * PB_K1_KS + 2) * p.W] = fours[c];
 #pragma unroll
-                for (int i = 0; i < 4; i++) op[i] = __ldg(ops + half * 4 + i);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (op[i].x >= 0) {
-                        const int64_t o = (int64_t)op[i].x * p.Wp;
-                        cv[i] = __ldg(pV + o); c0[i] = __ldg(pB0 + o); c1[i] = __ldg(pB1 + o);
-                    } else { cv[i] = 0; c0[i] = 0; c1[i] = 0; }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (op[i].y >= 0) {
-                        const int64_t o = (int64_t)op[i].y * p.Wp;
-                        pv[i] = __ldg(pV + o); p0[i] = __ldg(pB0 + o); p1[i] = __ldg(pB1 + o);
-                    } else { pv[i] = 0; p0[i] = 0; p1[i] = 0; }
-                }
-                uint64_t x[4][4];  // [base][leaf]
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (op[i].y >= 0) {
-                        const uint64_t mrca = cv[i] & (~pv[i] | (c0[i] ^ p0[i]) | (c1[i] ^ p1[i]));
-                        if (mrca) emit_events(mrca, c0[i], c1[i], site_base, (uint32_t)op[i].x | 0x80000000u, s_queue, &s_count, p);
+                        for (int j = 0; j < PB_K1_KHI; j++) out[((int64_t)c * PB_K1_KS + 3 + j) * p.W] = s_hi[(j * 4 + c) * PB_K1_COLS + tid];
                     }
-                    x[0][i] = cv[i] & ~c0[i] & ~c1[i];
-                    x[1][i] = cv[i] & c0[i] & ~c1[i];
-                    x[2][i] = cv[i] & ~c0[i] & c1[i];
-                    x[3][i] = cv[i] & c0[i] & c1[i];
                 }
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    uint64_t t2a, t2b;
-                    csa(t2a, ones[c], ones[c], x[c][0], x[c][1]);
-                    csa(t2b, ones[c], ones[c], x[c][2], x[c][3]);
-                    csa(f4[half][c], twos[c], twos[c], t2a, t2b);
+                for (int c = 0; c < 4; c++) { ones[c] = twos[c] = fours[c] = 0; b1[c] = b2[c] = 0; }
+#pragma unroll
+                for (int j = 0; j < PB_K1_KHI * 4; j++) s_hi[j * PB_K1_COLS + tid] = 0;
+                nleaf = 0;
+                continue;
+            }
+            uint64_t cv = 0, c0 = 0, c1 = 0;
+            if (node != PB_OP_NULL) {
+                mbar_wait(&s_full[stage], phase);                        // TMA bytes have landed
+                const uint64_t* src = ring + (int64_t)stage * (3 * PB_K1_COLS) + tid;
+                cv = src[0] & vmask; c0 = src[PB_K1_COLS]; c1 = src[2 * PB_K1_COLS];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[stage]);              // stage is free again
+                if (++stage == PB_K1_STAGES) { stage = 0; phase ^= 1; }
+                if (op & PB_OP_TEST) {
+                    const uint64_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
+                    if (mrca) emit_events(mrca, c0, c1, site_base, node | (op & PB_OP_LEAF), s_queue, &s_count, p);
+                }
+                if (op & PB_OP_SETCUR) { pv = cv; p0 = c0; p1 = c1; }
+            } else if (!(op & PB_OP_LEAF)) {
+                continue;                                                // padding
+            }
+            if (op & PB_OP_LEAF) {
+                uint64_t x[4];
+                x[0] = cv & ~c0 & ~c1; x[1] = cv & c0 & ~c1; x[2] = cv & ~c0 & c1; x[3] = cv & c0 & c1;
+                const int ph = nleaf & 7;                                // block-uniform
+                nleaf++;
+                if (!(ph & 1)) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) b1[c] = x[c];
+                } else {
+                    uint64_t t2[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) csa(t2[c], ones[c], ones[c], b1[c], x[c]);
+                    if (!(ph & 2)) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) b2[c] = t2[c];
+                    } else {
+                        uint64_t t4[4];
+#pragma unroll
+                        for (int c = 0; c < 4; c++) csa(t4[c], twos[c], twos[c], b2[c], t2[c]);
+                        if (!(ph & 4)) {
+#pragma unroll
+                            for (int c = 0; c < 4; c++) s_b4[c * PB_K1_COLS] = t4[c];
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                uint64_t carry;
+                                csa(carry, fours[c], fours[c], s_b4[c * PB_K1_COLS], t4[c]);
+#pragma unroll
+                                for (int j = 0; j < PB_K1_KHI; j++) {
+                                    uint64_t* hp = s_hi + (j * 4 + c) * PB_K1_COLS + tid;
+                                    const uint64_t h = *hp;
+                                    *hp = h ^ carry;
+                                    carry &= h;
+                                }
+                            }
+                        }
+                    }
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                uint64_t carry;
-                csa(carry, fours[c], fours[c], f4[0][c], f4[1][c]);
-#pragma unroll
-                for (int j = 0; j < PB_K1_KHI; j++) {
-                    const uint64_t t = hi[c][j] & carry;
-                    hi[c][j] ^= carry;
-                    carry = t;
-                }
-            }
-        }
-
-        // internal-node edges: MRCA test only
-        const int io0 = p.chunk_io[chunk], io1 = p.chunk_io[chunk + 1];
-        const int2* __restrict__ iops = reinterpret_cast<const int2*>(p.int_ops);
-        int i0 = io0;
-        for (; i0 + 4 <= io1; i0 += 4) {
-            int2 op[4];
-            uint64_t cv[4], c0[4], c1[4], pv[4], p0[4], p1[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) op[i] = __ldg(iops + i0 + i);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int64_t o = (int64_t)op[i].x * p.Wp;
-                cv[i] = __ldg(pV + o); c0[i] = __ldg(pB0 + o); c1[i] = __ldg(pB1 + o);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int64_t o = (int64_t)op[i].y * p.Wp;
-                pv[i] = __ldg(pV + o); p0[i] = __ldg(pB0 + o); p1[i] = __ldg(pB1 + o);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint64_t mrca = cv[i] & (~pv[i] | (c0[i] ^ p0[i]) | (c1[i] ^ p1[i]));
-                if (mrca) emit_events(mrca, c0[i], c1[i], site_base, (uint32_t)op[i].x, s_queue, &s_count, p);
-            }
-        }
-        for (; i0 < io1; i0++) {
-            const int2 op = __ldg(iops + i0);
-            const int64_t oc = (int64_t)op.x * p.Wp, opp = (int64_t)op.y * p.Wp;
-            const uint64_t cv = __ldg(pV + oc), c0 = __ldg(pB0 + oc), c1 = __ldg(pB1 + oc);
-            const uint64_t pv = __ldg(pV + opp), p0 = __ldg(pB0 + opp), p1 = __ldg(pB1 + opp);
-            const uint64_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
-            if (mrca) emit_events(mrca, c0, c1, site_base, (uint32_t)op.x, s_queue, &s_count, p);
-        }
-
-        // partial census of this chunk: [chunk][base][slice][W]
-        uint64_t* out = p.census + ((int64_t)chunk * 4 * PB_K1_KS) * p.W + w;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            out[((int64_t)c * PB_K1_KS + 0) * p.W] = ones[c];
-            out[((int64_t)c * PB_K1_KS + 1) * p.W] = twos[c];
-            out[((int64_t)c * PB_K1_KS + 2) * p.W] = fours[c];
-#pragma unroll
-            for (int j = 0; j < PB_K1_KHI; j++) out[((int64_t)c * PB_K1_KS + 3 + j) * p.W] = hi[c][j];
         }
     }
-
-    // flush the block's event queue with one global atomic
-    __syncthreads();
-    const unsigned int n = min(s_count, (unsigned int)PB_K1_QCAP);
-    if (tid == 0 && n) s_base = atomicAdd(p.raw_cursor, (unsigned long long)n);
-    __syncthreads();
-    for (unsigned int i = tid; i < n; i += PB_K1_THREADS) {
-        const unsigned long long pos = s_base + i;
-        if (pos < p.raw_cap) p.raw[pos] = s_queue[i];
-    }
+    drain_queue(s_queue, &s_count, &s_base, tid, 1, p);
 }
 
 // ---- per-site event counters -------------------------------------------------------------------
@@ -211,8 +276,39 @@ __global__ void k1_count_events_kernel(const raw_event_t* __restrict__ raw, int6
     }
 }
 
+// ---- census reduction: sum the bit-sliced partials of all flushes -----------------------------------
+// thread = (word column, base); total[base][PB_K1_KT][W]
+__global__ void k1_census_reduce_kernel(const uint64_t* __restrict__ census, int n_flush, int64_t W, uint64_t* __restrict__ total) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (w >= W) return;
+    uint64_t acc[PB_K1_KT];
+#pragma unroll
+    for (int j = 0; j < PB_K1_KT; j++) acc[j] = 0;
+    for (int f = 0; f < n_flush; f++) {
+        const uint64_t* in = census + (((int64_t)f * 4 + c) * PB_K1_KS) * W + w;
+        uint64_t carry = 0;
+#pragma unroll
+        for (int j = 0; j < PB_K1_KS; j++) {
+            const uint64_t b = in[(int64_t)j * W];
+            const uint64_t a = acc[j], u = a ^ b;
+            acc[j] = u ^ carry;
+            carry = (a & b) | (u & carry);
+        }
+#pragma unroll
+        for (int j = PB_K1_KS; j < PB_K1_KT; j++) {
+            const uint64_t a = acc[j];
+            acc[j] = a ^ carry;
+            carry &= a;
+        }
+    }
+    uint64_t* out = total + ((int64_t)c * PB_K1_KT) * W + w;
+#pragma unroll
+    for (int j = 0; j < PB_K1_KT; j++) out[(int64_t)j * W] = acc[j];
+}
+
 // ---- per-site finalisation: census -> class / major-minor; counters -> Homoplasy_Events -----------
-__global__ void k1_finalize_kernel(const uint64_t* __restrict__ census, int n_chunks, int64_t W, int64_t S,
+__global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, int kt_used, int64_t W, int64_t S,
                                    const uint64_t* __restrict__ B0, const uint64_t* __restrict__ B1, const uint64_t* __restrict__ V,
                                    int64_t Wp, int32_t root, const uint32_t* __restrict__ cnt, int32_t min_hcount, int64_t site_offset,
                                    pb_site_out* __restrict__ sites, uint8_t* __restrict__ flags, uint64_t* __restrict__ scan_in,
@@ -225,15 +321,10 @@ __global__ void k1_finalize_kernel(const uint64_t* __restrict__ census, int n_ch
         const int64_t w = s >> 6;
         const int b = (int)(s & 63);
         uint32_t leafcnt[4] = {0, 0, 0, 0};  // by 2-bit code: A C G T
-        for (int ch = 0; ch < n_chunks; ch++)
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int j = 0; j < PB_K1_KS; j++)
-                    v |= (uint32_t)((census[(((int64_t)ch * 4 + c) * PB_K1_KS + j) * W + w] >> b) & 1ull) << j;
-                leafcnt[c] += v;
-            }
+        for (int c = 0; c < 4; c++)
+            for (int j = 0; j < kt_used; j++)
+                leafcnt[c] |= (uint32_t)((total[((int64_t)c * PB_K1_KT + j) * W + w] >> b) & 1ull) << j;
         // HashMap<Character,..> iteration order A, C, T, G  (buckets 'A'&15=1, 'C'&15=3, 'T'&15=4, 'G'&15=7)
         const int order[4] = {0, 1, 3, 2};
         int n_alleles = 0, first = -1, second = -1;
@@ -361,28 +452,36 @@ __global__ void k1_scatter_sites_kernel(int64_t S, const uint8_t* __restrict__ f
                                         const uint64_t* __restrict__ scan_in, const uint32_t* __restrict__ cnt,
                                         const pb_site_out* __restrict__ sites, int32_t* __restrict__ inf_site, AlleleMeta* __restrict__ alleles,
                                         unsigned long long* __restrict__ class_counts /* [5]=n_max, [6]=A_inuse */) {
+    __shared__ unsigned int s_nmax, s_ause;
+    if (threadIdx.x == 0) { s_nmax = 0; s_ause = 0; }
+    __syncthreads();
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    if (!(scan_in[s] >> 38)) return;
-    const uint8_t fl = flags[s];
-    const int64_t i = (int64_t)(scan[s] >> 38);
-    const int64_t off = (int64_t)(scan[s] & ((1ull << 38) - 1));
-    const int a1 = (fl >> PB_SF_A1_CODE_SHIFT) & 3;
-    const uint32_t* c = cnt + s * PB_CNT_STRIDE;
-    const uint32_t xs_all = c[8] + c[9] + c[10] + c[11];
-    const bool u1 = fl & PB_SF_A1_USE, u2 = fl & PB_SF_A2_USE;
-    // an in-use allele keeps all its leaf events unless its bucket was emptied by the <2 rule
-    // (possible only with min_hcount == 0, where in_use does not imply a surviving bucket)
-    const pb_site_out so = sites[s];
-    const uint32_t n1 = (u1 && so.a1_count >= 2) ? c[8 + a1] : 0u, n2 = (u2 && so.a2_count >= 2) ? xs_all - c[8 + a1] : 0u;
-    inf_site[i] = (int32_t)s;
-    AlleleMeta m1{}, m2{};
-    m1.off = off; m1.n = (int32_t)n1; m1.flags = u1 ? PB_AF_IN_USE : 0;
-    m2.off = off + n1; m2.n = (int32_t)n2; m2.flags = u2 ? PB_AF_IN_USE : 0;
-    alleles[2 * i] = m1;
-    alleles[2 * i + 1] = m2;
-    atomicMax(class_counts + 5, (unsigned long long)max(n1, n2));
-    atomicAdd(class_counts + 6, (unsigned long long)((u1 ? 1 : 0) + (u2 ? 1 : 0)));
+    if (s < S && (scan_in[s] >> 38)) {
+        const uint8_t fl = flags[s];
+        const int64_t i = (int64_t)(scan[s] >> 38);
+        const int64_t off = (int64_t)(scan[s] & ((1ull << 38) - 1));
+        const int a1 = (fl >> PB_SF_A1_CODE_SHIFT) & 3;
+        const uint32_t* c = cnt + s * PB_CNT_STRIDE;
+        const uint32_t xs_all = c[8] + c[9] + c[10] + c[11];
+        const bool u1 = fl & PB_SF_A1_USE, u2 = fl & PB_SF_A2_USE;
+        // an in-use allele keeps all its leaf events unless its bucket was emptied by the <2 rule
+        // (possible only with min_hcount == 0, where in_use does not imply a surviving bucket)
+        const pb_site_out so = sites[s];
+        const uint32_t n1 = (u1 && so.a1_count >= 2) ? c[8 + a1] : 0u, n2 = (u2 && so.a2_count >= 2) ? xs_all - c[8 + a1] : 0u;
+        inf_site[i] = (int32_t)s;
+        AlleleMeta m1{}, m2{};
+        m1.off = off; m1.n = (int32_t)n1; m1.flags = u1 ? PB_AF_IN_USE : 0;
+        m2.off = off + n1; m2.n = (int32_t)n2; m2.flags = u2 ? PB_AF_IN_USE : 0;
+        alleles[2 * i] = m1;
+        alleles[2 * i + 1] = m2;
+        atomicMax(&s_nmax, max(n1, n2));
+        atomicAdd(&s_ause, (unsigned int)((u1 ? 1 : 0) + (u2 ? 1 : 0)));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_ause) {
+        atomicMax(class_counts + 5, (unsigned long long)s_nmax);
+        atomicAdd(class_counts + 6, (unsigned long long)s_ause);
+    }
 }
 
 __global__ void k1_scatter_events_kernel(const raw_event_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ node_sample,
@@ -415,17 +514,17 @@ int pbk_events(pb_ctx* ctx) {
     K1Params p;
     p.B0 = ctx->d_B0; p.B1 = ctx->d_B1; p.V = ctx->d_V;
     p.Wp = ctx->Wp; p.W = ctx->W;
-    p.leaf_ops = ctx->d_leaf_ops; p.int_ops = ctx->d_int_ops;
-    p.chunk_lg = ctx->d_chunk_lg; p.chunk_io = ctx->d_chunk_io;
+    p.last_mask = (ctx->S & 63) ? ((1ull << (ctx->S & 63)) - 1) : ~0ull;
+    p.ops = ctx->d_ops; p.chunk_op = ctx->d_chunk_op;
     p.census = ctx->d_census;
     p.raw = ctx->d_raw; p.raw_cursor = ctx->d_raw_cursor; p.raw_cap = (unsigned long long)ctx->raw_cap;
-    const size_t smem = (size_t)PB_K1_QCAP * sizeof(raw_event_t);
+    const size_t smem = (size_t)K1_SMEM_TOTAL;
     static bool attr_set = false;
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(k1_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    dim3 grid((unsigned)((ctx->W + PB_K1_THREADS - 1) / PB_K1_THREADS), (unsigned)ctx->n_chunks);
+    dim3 grid((unsigned)((ctx->W + PB_K1_COLS - 1) / PB_K1_COLS), (unsigned)ctx->n_chunks);
     PB_CUDA(cudaMemsetAsync(ctx->d_raw_cursor, 0, 8, ctx->stream));
     PB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     k1_events_kernel<<<grid, PB_K1_THREADS, smem, ctx->stream>>>(p);
@@ -444,10 +543,14 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts) {
         k1_count_events_kernel<<<(unsigned)((ctx->n_raw + T - 1) / T), T, 0, ctx->stream>>>(ctx->d_raw, ctx->n_raw, ctx->d_node_sample, ctx->d_cnt);
         ctx->tm.n_launches += 1;
     }
+    k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), 4), 128, 0, ctx->stream>>>(ctx->d_census, ctx->n_flush, ctx->W,
+                                                                                              ctx->d_census_total);
+    int kt_used = 1;
+    while ((1ll << kt_used) <= (int64_t)ctx->L) kt_used++;
     k1_finalize_kernel<<<(unsigned)((S + T - 1) / T), T, 0, ctx->stream>>>(
-        ctx->d_census, ctx->n_chunks, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->d_cnt, ctx->cfg.min_hcount,
+        ctx->d_census_total, kt_used, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->d_cnt, ctx->cfg.min_hcount,
         ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan /* reused as scan input */, ctx->d_class_counts);
-    ctx->tm.n_launches += 1;
+    ctx->tm.n_launches += 2;
     PB_CUDA(cudaGetLastError());
     // scan: d_site_scan (input) -> d_site_scan_out.  We keep input in the first half of a 2*S buffer.
     uint64_t* scan_in = ctx->d_site_scan;

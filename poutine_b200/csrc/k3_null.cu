@@ -21,6 +21,8 @@
 //        without a candidate are recomputed exactly by a fallback kernel.
 //        Replicates in which one of the allele's leaves drew a *missing* label (n_r < n) and alleles
 //        whose table row is not monotone take the exact scalar path bit by bit.
+#include <stdlib.h>
+
 #include "pb_internal.h"
 
 // ---------------------------------------------------------------------------------------------------
@@ -161,87 +163,118 @@ __device__ __forceinline__ int extract(const uint64_t (&c)[NB], int b) {
     return v;
 }
 
+// One warp sweeps ONE allele over every replicate word of the tile: lane l owns words l, l+32, ...
+// The allele's sample rows are streamed (coalesced 256 B per row per step, L2-resident matrix),
+// r is accumulated in registers and written once — no atomics on r.
 template <int NB>
-__device__ __forceinline__ void process_allele(const K3Params& p, const AlleleMeta& m, int64_t slot, int64_t word, uint64_t valid,
-                                               double tau) {
+__device__ __forceinline__ void sweep_allele(const K3Params& p, const AlleleMeta& m, int64_t slot, int lane, double tau) {
+    constexpr int NREG = (NB <= 3) ? ((1 << NB) - 1) : 1;   // small lists live in registers
     const int n = m.n;
-    uint64_t c[NB], u[NB];
-#pragma unroll
-    for (int j = 0; j < NB; j++) { c[j] = 0; u[j] = 0; }
     const int32_t* __restrict__ ev = p.csr + m.off;
+    int32_t evr[NREG];
+    if (NB <= 3) {
+#pragma unroll
+        for (int e = 0; e < NREG; e++) evr[e] = (e < n) ? __ldg(ev + e) : 0;
+    }
     const bool has_miss = p.Xm != nullptr;
-    if (valid) {
-        for (int e = 0; e < n; e++) {
-            const int64_t o = (int64_t)ev[e] * p.Rw + word;
-            uint64_t x = p.Xc[o];
-#pragma unroll
-            for (int j = 0; j < NB; j++) { const uint64_t t = c[j] & x; c[j] ^= x; x = t; }
-            if (has_miss) {
-                uint64_t y = p.Xm[o];
-#pragma unroll
-                for (int j = 0; j < NB; j++) { const uint64_t t = u[j] & y; u[j] ^= y; y = t; }
-            }
-        }
-    }
-    uint64_t exc = 0;
-    if (has_miss) {
-#pragma unroll
-        for (int j = 0; j < NB; j++) exc |= u[j];
-    }
     const bool fast = m.flags & PB_AF_FAST;
-    if (!fast) exc = ~0ull;
-    exc &= valid;
-    const uint64_t fastmask = valid & ~exc;
     const double pobs = p.pobs[slot];
     const int kstar = m.kstar;
-    uint64_t ge = (kstar <= 0) ? ~0ull : (kstar > n ? 0ull : ge_const<NB>(c, kstar));
-    unsigned int rcount = (unsigned int)__popcll(ge & fastmask);
     const int kt = p.ktau[n];
-    uint64_t cand = (kt <= 0) ? ~0ull : (kt > n ? 0ull : ge_const<NB>(c, kt));
-    uint64_t todo = (cand & fastmask) | exc;
     const double* __restrict__ row_n = p.ptable + (int64_t)n * (n + 1) / 2;
-    while (todo) {
-        const int b = __ffsll((long long)todo) - 1;
-        todo &= todo - 1;
-        const int k = extract<NB>(c, b);
-        double pv;
-        if ((exc >> b) & 1ull) {
-            const int nr = n - (has_miss ? extract<NB>(u, b) : 0);
-            pv = p.ptable[(int64_t)nr * (nr + 1) / 2 + k];
-            rcount += (pv <= pobs) ? 1u : 0u;   // HC.java:4239 / 4273
+    const int64_t words = (p.n_reps + 63) >> 6;
+    const int tail = (int)(p.n_reps & 63);
+    unsigned int rcount = 0;
+#pragma unroll 2
+    for (int64_t w = lane; w < words; w += 32) {
+        const uint64_t valid = (w == words - 1 && tail) ? ((1ull << tail) - 1) : ~0ull;
+        uint64_t c[NB], u[NB];
+#pragma unroll
+        for (int j = 0; j < NB; j++) { c[j] = 0; u[j] = 0; }
+        if (NB <= 3) {
+#pragma unroll
+            for (int e = 0; e < NREG; e++) {
+                if (e < n) {
+                    const int64_t o = (int64_t)evr[e] * p.Rw + w;
+                    uint64_t x = __ldg(p.Xc + o);
+#pragma unroll
+                    for (int j = 0; j < NB; j++) { const uint64_t t = c[j] & x; c[j] ^= x; x = t; }
+                    if (has_miss) {
+                        uint64_t y = __ldg(p.Xm + o);
+#pragma unroll
+                        for (int j = 0; j < NB; j++) { const uint64_t t = u[j] & y; u[j] ^= y; y = t; }
+                    }
+                }
+            }
         } else {
-            pv = row_n[k];
+            for (int e = 0; e < n; e++) {
+                const int64_t o = (int64_t)__ldg(ev + e) * p.Rw + w;
+                uint64_t x = __ldg(p.Xc + o);
+#pragma unroll
+                for (int j = 0; j < NB; j++) { const uint64_t t = c[j] & x; c[j] ^= x; x = t; }
+                if (has_miss) {
+                    uint64_t y = __ldg(p.Xm + o);
+#pragma unroll
+                    for (int j = 0; j < NB; j++) { const uint64_t t = u[j] & y; u[j] ^= y; y = t; }
+                }
+            }
         }
-        if (pv <= tau) atomicMin(p.maxT + (p.rep_base + word * 64 + b), (unsigned long long)__double_as_longlong(pv));
+        uint64_t exc = 0;
+        if (has_miss) {
+#pragma unroll
+            for (int j = 0; j < NB; j++) exc |= u[j];
+        }
+        if (!fast) exc = ~0ull;
+        exc &= valid;
+        const uint64_t fastmask = valid & ~exc;
+        const uint64_t ge = (kstar <= 0) ? ~0ull : (kstar > n ? 0ull : ge_const<NB>(c, kstar));
+        rcount += (unsigned int)__popcll(ge & fastmask);
+        const uint64_t cand = (kt <= 0) ? ~0ull : (kt > n ? 0ull : ge_const<NB>(c, kt));
+        uint64_t todo = (cand & fastmask) | exc;
+        while (todo) {
+            const int b = __ffsll((long long)todo) - 1;
+            todo &= todo - 1;
+            const int k = extract<NB>(c, b);
+            double pv;
+            if ((exc >> b) & 1ull) {
+                const int nr = n - (has_miss ? extract<NB>(u, b) : 0);
+                pv = p.ptable[(int64_t)nr * (nr + 1) / 2 + k];
+                rcount += (pv <= pobs) ? 1u : 0u;   // HC.java:4239 / 4273
+            } else {
+                pv = row_n[k];
+            }
+            if (pv <= tau) atomicMin(p.maxT + (p.rep_base + w * 64 + b), (unsigned long long)__double_as_longlong(pv));
+        }
     }
     rcount = __reduce_add_sync(0xffffffffu, rcount);
-    if ((threadIdx.x & 31) == 0 && rcount) atomicAdd(p.r + slot, rcount);
+    if (lane == 0 && rcount) p.r[slot] += rcount;   // this warp is the slot's only writer in this launch
 }
 
-#define K3_THREADS 128
-__global__ void __launch_bounds__(K3_THREADS) k3_count_kernel(const K3Params p) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t word = ((int64_t)blockIdx.x * (K3_THREADS / 32) + warp) * 32 + lane;
-    const int64_t rep0 = word * 64;  // tile-local
-    uint64_t valid = 0;
-    if (rep0 < p.n_reps) valid = (p.n_reps - rep0 >= 64) ? ~0ull : ((1ull << (p.n_reps - rep0)) - 1);
-    if (__all_sync(0xffffffffu, valid == 0)) return;
+#define K3_THREADS 256
+// LARGE = false: alleles with n < 8 (the vast majority; event lists in registers, few registers per thread);
+// LARGE = true : the long-list tail.  Two instantiations so the common case keeps high occupancy.
+template <bool LARGE>
+__global__ void __launch_bounds__(K3_THREADS, LARGE ? 1 : 3) k3_count_kernel(const K3Params p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
     const double tau = *p.tau;
-    const int64_t s0 = (int64_t)blockIdx.y * p.slots_per_chunk;
-    const int64_t s1 = min(p.n_slots, s0 + p.slots_per_chunk);
-    for (int64_t slot = s0; slot < s1; slot++) {
+    for (int64_t slot = gwarp; slot < p.n_slots; slot += nwarps) {
         const AlleleMeta m = p.alleles[slot];
         if (!(m.flags & PB_AF_IN_USE)) continue;
         const int n = m.n;
-        if (n < 2) process_allele<1>(p, m, slot, word, valid, tau);
-        else if (n < 4) process_allele<2>(p, m, slot, word, valid, tau);
-        else if (n < 8) process_allele<3>(p, m, slot, word, valid, tau);
-        else if (n < 16) process_allele<4>(p, m, slot, word, valid, tau);
-        else if (n < 32) process_allele<5>(p, m, slot, word, valid, tau);
-        else if (n < 64) process_allele<6>(p, m, slot, word, valid, tau);
-        else if (n < 256) process_allele<8>(p, m, slot, word, valid, tau);
-        else if (n < 4096) process_allele<12>(p, m, slot, word, valid, tau);
-        else process_allele<17>(p, m, slot, word, valid, tau);
+        if (!LARGE) {
+            if (n < 2) sweep_allele<1>(p, m, slot, lane, tau);
+            else if (n < 4) sweep_allele<2>(p, m, slot, lane, tau);
+            else if (n < 8) sweep_allele<3>(p, m, slot, lane, tau);
+        } else {
+            if (n < 8) continue;
+            if (n < 16) sweep_allele<4>(p, m, slot, lane, tau);
+            else if (n < 64) sweep_allele<6>(p, m, slot, lane, tau);
+            else if (n < 256) sweep_allele<8>(p, m, slot, lane, tau);
+            else if (n < 4096) sweep_allele<12>(p, m, slot, lane, tau);
+            else sweep_allele<17>(p, m, slot, lane, tau);
+        }
     }
 }
 
@@ -335,8 +368,10 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     ctx->tm.n_launches += 1;
 
     const bool has_miss = ctx->n_miss > 0;
-    // tile size: keep each label matrix <= 4 GiB and a multiple of 2048 replicates
-    int64_t tile = (int64_t)((4ll << 30) / ((int64_t)ctx->P / 8 + 1));
+    // tile size: the label matrices of one tile stay L2-resident (126 MB L2): <= 48 MB in total by default
+    int64_t l2_budget = 48ll << 20;
+    if (const char* e = getenv("PB_K3_TILE_MB")) l2_budget = atoll(e) << 20;
+    int64_t tile = (l2_budget * 8) / ((int64_t)ctx->P * (has_miss ? 2 : 1));
     tile = (tile / 2048) * 2048;
     if (tile < 2048) tile = 2048;
     const int64_t m_pad = ((m + 255) / 256) * 256;
@@ -385,18 +420,17 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
         p.alleles = ctx->d_alleles; p.n_slots = n_slots; p.csr = ctx->d_csr; p.pobs = ctx->d_pobs; p.ptable = ctx->d_ptable;
         p.ktau = ctx->d_ktau; p.tau = ctx->d_tau; p.Xc = ctx->d_Xcase; p.Xm = has_miss ? ctx->d_Xmiss : nullptr; p.Rw = Rw;
         p.rep_base = base; p.n_reps = nr; p.r = ctx->d_r; p.maxT = ctx->d_maxT;
-        const int64_t words = (nr + 63) / 64;
-        const unsigned gx = (unsigned)((words + (K3_THREADS / 32) * 32 - 1) / ((K3_THREADS / 32) * 32));
-        int64_t want_blocks = (int64_t)ctx->sm_count * 32;
-        int64_t gy = (want_blocks + gx - 1) / gx;
-        if (gy < 1) gy = 1;
-        int64_t spc = (n_slots + gy - 1) / gy;
-        if (spc < 64) spc = 64;
-        spc = (spc + 1) & ~1ll;
-        gy = (n_slots + spc - 1) / spc;
-        if (gy > 65535) { gy = 65535; spc = ((n_slots + gy - 1) / gy + 1) & ~1ll; gy = (n_slots + spc - 1) / spc; }
-        p.slots_per_chunk = (int32_t)spc;
-        k3_count_kernel<<<dim3(gx, (unsigned)gy), K3_THREADS, 0, st>>>(p);
+        int64_t blocks = (int64_t)ctx->sm_count * 8;
+        if (const char* e = getenv("PB_K3_BLOCKS_PER_SM")) blocks = (int64_t)ctx->sm_count * atoll(e);
+        const int64_t max_blocks = (n_slots + (K3_THREADS / 32) - 1) / (K3_THREADS / 32);
+        if (blocks > max_blocks) blocks = max_blocks;
+        if (blocks < 1) blocks = 1;
+        p.slots_per_chunk = 0;
+        k3_count_kernel<false><<<(unsigned)blocks, K3_THREADS, 0, st>>>(p);
+        if (ctx->n_max >= 8) {
+            k3_count_kernel<true><<<(unsigned)blocks, K3_THREADS, 0, st>>>(p);
+            ctx->tm.n_launches += 1;
+        }
         ctx->tm.n_launches += 1;
         PB_CUDA(cudaEventRecord(ctx->ev[7], st));
 

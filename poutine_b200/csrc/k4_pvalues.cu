@@ -21,33 +21,44 @@ __global__ void k4_ptable_kernel(double* __restrict__ tab, int32_t n_max, double
 }
 
 // ---- observed p-value, k* and the n-histogram -------------------------------------------------------
+#define OBS_SH 256
 __global__ void k4_observed_kernel(AlleleMeta* __restrict__ alleles, int64_t n_slots, const double* __restrict__ tab,
                                    double* __restrict__ pobs, unsigned int* __restrict__ n_hist, int force_general,
                                    unsigned long long* __restrict__ n_fast) {
+    // block-local histogram of the common small n (global atomics only for the tail and once per block)
+    __shared__ unsigned int s_hist[OBS_SH], s_fast;
+    for (int i = threadIdx.x; i < OBS_SH; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_fast = 0;
+    __syncthreads();
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n_slots) return;
-    AlleleMeta m = alleles[a];
-    if (!(m.flags & PB_AF_IN_USE)) {
-        pobs[a] = __longlong_as_double(0x7FF8000000000000ll);  // Double.NaN sentinel (HC.java:5891-5906)
-        return;
+    if (a < n_slots) {
+        AlleleMeta m = alleles[a];
+        if (!(m.flags & PB_AF_IN_USE)) {
+            pobs[a] = __longlong_as_double(0x7FF8000000000000ll);  // Double.NaN sentinel (HC.java:5891-5906)
+        } else {
+            const int no = m.obs_case + m.obs_ctrl;
+            const double po = tab[(int64_t)no * (no + 1) / 2 + m.obs_case];  // HC.java:3050 / 3056
+            pobs[a] = po;
+            if (m.n < OBS_SH) atomicAdd(&s_hist[m.n], 1u); else atomicAdd(n_hist + m.n, 1u);
+            // k* = min{k : f(n,k) <= p_obs}; fast path only if {k : f(n,k) <= p_obs} = [k*, n]
+            const double* row = tab + (int64_t)m.n * (m.n + 1) / 2;
+            int kstar = m.n + 1;
+            bool upset = true;
+            for (int k = 0; k <= m.n; k++) {
+                const bool le = row[k] <= po;
+                if (le && kstar > m.n) kstar = k;
+                if (!le && kstar <= m.n) upset = false;
+            }
+            uint32_t fl = m.flags & ~PB_AF_FAST;
+            if (upset && !force_general) { fl |= PB_AF_FAST; atomicAdd(&s_fast, 1u); }
+            alleles[a].flags = fl;
+            alleles[a].kstar = kstar;
+        }
     }
-    const int no = m.obs_case + m.obs_ctrl;
-    const double po = tab[(int64_t)no * (no + 1) / 2 + m.obs_case];  // HC.java:3050 / 3056
-    pobs[a] = po;
-    atomicAdd(n_hist + m.n, 1u);
-    // k* = min{k : f(n,k) <= p_obs}; fast path only if {k : f(n,k) <= p_obs} = [k*, n]
-    const double* row = tab + (int64_t)m.n * (m.n + 1) / 2;
-    int kstar = m.n + 1;
-    bool upset = true;
-    for (int k = 0; k <= m.n; k++) {
-        const bool le = row[k] <= po;
-        if (le && kstar > m.n) kstar = k;
-        if (!le && kstar <= m.n) upset = false;
-    }
-    uint32_t fl = m.flags & ~PB_AF_FAST;
-    if (upset && !force_general) { fl |= PB_AF_FAST; atomicAdd(n_fast, 1ull); }
-    alleles[a].flags = fl;
-    alleles[a].kstar = kstar;
+    __syncthreads();
+    for (int i = threadIdx.x; i < OBS_SH; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(n_hist + i, s_hist[i]);
+    if (threadIdx.x == 0 && s_fast) atomicAdd(n_fast, (unsigned long long)s_fast);
 }
 
 // ---- candidate threshold tau for the maxT pass ----------------------------------------------------
@@ -220,7 +231,7 @@ int pbk_thresholds(pb_ctx* ctx) {
     k4_observed_kernel<<<(unsigned)((n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ptable, ctx->d_pobs, d_hist,
                                                                       force_general, d_nfast);
     k4_tau_expect_kernel<<<TAU_LEVELS, 256, 0, st>>>(ctx->d_ptable, d_hist, n_max, d_expect);
-    k4_tau_pick_kernel<<<1, 1, 0, st>>>(d_expect, 64.0, ctx->cfg.maxt_tau, ctx->d_tau);
+    k4_tau_pick_kernel<<<1, 1, 0, st>>>(d_expect, 16.0, ctx->cfg.maxt_tau, ctx->d_tau);
     k4_ktau_kernel<<<(unsigned)((n1 + T - 1) / T), T, 0, st>>>(ctx->d_ptable, n_max, ctx->d_tau, ctx->d_ktau);
     ctx->tm.n_launches += 4;
     PB_CUDA(cudaGetLastError());

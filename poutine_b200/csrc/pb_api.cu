@@ -16,8 +16,8 @@ extern "C" int pb_version(void) { return 100; }
 extern "C" const char* pb_last_error(pb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 static void free_all(pb_ctx* c) {
-    void* ptrs[] = {c->d_leaf_ops, c->d_int_ops, c->d_chunk_lg, c->d_chunk_io, c->d_node_sample, c->d_label, c->d_B0, c->d_B1, c->d_V,
-                    c->d_census, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
+    void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_node_sample, c->d_label, c->d_B0, c->d_B1, c->d_V,
+                    c->d_census, c->d_census_total, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
                     c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT,
                     c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -86,10 +86,11 @@ static int upload(pb_ctx* ctx, T** dptr, const std::vector<T>& h) {
     return PB_OK;
 }
 
-// Edge schedule of K1.  Edges are emitted parent by parent in a depth-first expansion that enters the
-// smaller subtree first, so a parent's row is re-read from L1/L2 shortly after it was first loaded;
-// leaf edges (census + MRCA test) and internal edges (MRCA test only) go to separate streams that the
-// kernel consumes chunk by chunk.
+// Logical edge list of K1: every non-root node once, as (child, parent), in a DFS preorder that lists a
+// node's leaf children first and its internal children by ascending subtree size.  A child row is
+// visited right after its parent row, so the kernel keeps the parent in registers; coming back from a
+// (small) first subtree the parent row is re-read — from L1/L2, because the subtree entered first is the
+// smaller one.  Iterative: caterpillar trees are as deep as they are large.
 static int build_schedule(pb_ctx* ctx) {
     const int32_t N = ctx->N;
     std::vector<int32_t> nchild(N, 0), first(N + 1, 0), kids(N > 1 ? N - 1 : 0);
@@ -99,7 +100,6 @@ static int build_schedule(pb_ctx* ctx) {
         std::vector<int32_t> fill(first.begin(), first.end() - 1);
         for (int32_t v = 0; v < N; v++) if (ctx->parent[v] >= 0) kids[fill[ctx->parent[v]]++] = v;
     }
-    // subtree sizes via reverse BFS order
     std::vector<int32_t> order; order.reserve(N);
     order.push_back(ctx->root);
     for (size_t i = 0; i < order.size(); i++) {
@@ -109,63 +109,92 @@ static int build_schedule(pb_ctx* ctx) {
     if ((int32_t)order.size() != N) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: parent[] does not describe one tree (cycle or several roots)");
     std::vector<int32_t> sz(N, 1);
     for (int32_t i = N - 1; i > 0; i--) sz[ctx->parent[order[i]]] += sz[order[i]];
-
-    std::vector<EdgeOp> leaf_ops, int_ops;
-    leaf_ops.reserve(ctx->L + 8); int_ops.reserve(N);
-    std::vector<int32_t> stack; stack.push_back(ctx->root);
-    std::vector<int32_t> tmp;
+    for (int32_t u = 0; u < N; u++)
+        std::sort(kids.begin() + first[u], kids.begin() + first[u + 1], [&](int32_t a, int32_t b) {
+            if (sz[a] != sz[b]) return sz[a] < sz[b];   // leaves (size 1) first, then ascending subtree size
+            return a < b;
+        });
+    ctx->lop_child.clear(); ctx->lop_parent.clear();
+    ctx->lop_child.reserve(N); ctx->lop_parent.reserve(N);
+    std::vector<std::pair<int32_t, int32_t>> stack;
+    stack.push_back({ctx->root, first[ctx->root]});
     while (!stack.empty()) {
-        const int32_t u = stack.back(); stack.pop_back();
-        const int32_t par = (u == ctx->root) ? -1 : u;
-        tmp.clear();
-        for (int32_t j = first[u]; j < first[u + 1]; j++) {
-            const int32_t c = kids[j];
-            if (ctx->is_leaf[c]) leaf_ops.push_back({c, par});
-            else {
-                if (par >= 0) int_ops.push_back({c, par});
-                tmp.push_back(c);
-            }
-        }
-        std::sort(tmp.begin(), tmp.end(), [&](int32_t a, int32_t b) { return sz[a] > sz[b]; });  // largest pushed first -> popped last
-        for (int32_t c : tmp) stack.push_back(c);
+        auto& top = stack.back();
+        const int32_t u = top.first;
+        if (top.second == first[u + 1]) { stack.pop_back(); continue; }
+        const int32_t c = kids[top.second++];
+        ctx->lop_child.push_back(c);
+        ctx->lop_parent.push_back(u);
+        if (!ctx->is_leaf[c]) stack.push_back({c, first[c]});
     }
-    while (leaf_ops.size() % 8) leaf_ops.push_back({-1, -1});
-    ctx->n_leaf_groups = (int32_t)(leaf_ops.size() / 8);
-    ctx->n_int_ops = (int32_t)int_ops.size();
-
-    int rc;
-    if ((rc = upload(ctx, &ctx->d_leaf_ops, leaf_ops))) return rc;
-    if ((rc = upload(ctx, &ctx->d_int_ops, int_ops))) return rc;
     return PB_OK;
 }
 
-// chunking of the schedule: enough blocks to fill the GPU several times over, <= 2040 leaves per chunk
+// Cut the logical edge list into n_chunks equal pieces (grid.y) and lower each piece to the kernel's op
+// stream: SETCUR reloads where the tracked parent row is not the edge's parent, census segments closed
+// by FLUSH ops (leaf count padded to a multiple of 8 with null leaves: the carry-save tree works in
+// groups of 8), chunks padded to a multiple of 4 ops.
 static int build_chunks(pb_ctx* ctx) {
-    // needs W (set_sites) and the schedule (set_tree)
     if (ctx->N == 0 || ctx->W == 0) return PB_OK;
-    const int64_t blocks_x = (ctx->W + PB_K1_THREADS - 1) / PB_K1_THREADS;
-    int64_t target_blocks = (int64_t)ctx->sm_count * 24;
-    if (const char* e = getenv("PB_K1_TARGET_BLOCKS")) target_blocks = atoll(e);
-    int64_t n_chunks = (target_blocks + blocks_x - 1) / blocks_x;
-    const int64_t min_chunks = (ctx->n_leaf_groups * 8 + PB_K1_MAX_LEAVES_PER_CHUNK - 1) / PB_K1_MAX_LEAVES_PER_CHUNK;
-    int64_t max_chunks = std::max<int64_t>(1, ctx->N / 64);
-    if (const char* e = getenv("PB_K1_CHUNKS")) n_chunks = atoll(e);
-    n_chunks = std::min(n_chunks, max_chunks);
-    n_chunks = std::max<int64_t>(n_chunks, std::max<int64_t>(min_chunks, 1));
-    n_chunks = std::min<int64_t>(n_chunks, 65535);
-    ctx->n_chunks = (int32_t)n_chunks;
-    std::vector<int32_t> lg(n_chunks + 1), io(n_chunks + 1);
-    for (int64_t c = 0; c <= n_chunks; c++) {
-        lg[c] = (int32_t)((int64_t)ctx->n_leaf_groups * c / n_chunks);
-        io[c] = (int32_t)((int64_t)ctx->n_int_ops * c / n_chunks);
+    const int64_t n_lops = (int64_t)ctx->lop_child.size();
+    const int64_t blocks_x = (ctx->W + PB_K1_COLS - 1) / PB_K1_COLS;
+    // grid.y: ~4 waves of 4 resident blocks per SM, picking the chunk count whose last wave is fullest
+    int64_t slots = (int64_t)ctx->sm_count * 4;
+    if (const char* e = getenv("PB_K1_TARGET_BLOCKS")) slots = atoll(e);
+    int64_t n_chunks = 1;
+    {
+        const int64_t lo = std::max<int64_t>(1, (3 * slots + blocks_x - 1) / blocks_x), hi = std::max<int64_t>(lo, 5 * slots / blocks_x);
+        double best = -1;
+        for (int64_t n = lo; n <= hi; n++) {
+            const int64_t blocks = blocks_x * n, waves = (blocks + slots - 1) / slots;
+            const double eff = (double)blocks / (double)(waves * slots);
+            if (eff > best + 1e-9) { best = eff; n_chunks = n; }
+        }
     }
-    for (int64_t c = 0; c < n_chunks; c++)
-        if ((lg[c + 1] - lg[c]) * 8 > PB_K1_MAX_LEAVES_PER_CHUNK) FAIL(ctx, PB_ERR_INVALID, "internal: chunk exceeds census width");
+    if (const char* e = getenv("PB_K1_CHUNKS")) n_chunks = atoll(e);
+    n_chunks = std::min<int64_t>(n_chunks, std::max<int64_t>(1, n_lops / 32));
+    n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, 65535));
+    ctx->n_chunks = (int32_t)n_chunks;
+
+    std::vector<uint32_t> ops;
+    ops.reserve((size_t)n_lops * 5 / 4 + 64 * n_chunks);
+    std::vector<int32_t> chunk_op(n_chunks + 1, 0);
+    int32_t n_flush = 0;
+    for (int64_t c = 0; c < n_chunks; c++) {
+        const int64_t l0 = n_lops * c / n_chunks, l1 = n_lops * (c + 1) / n_chunks;
+        int32_t cur = -1;       // node whose row the kernel holds as "current parent"
+        int32_t seg_leaves = 0;
+        auto flush = [&]() {
+            while (seg_leaves % 8) { ops.push_back(PB_OP_LEAF | PB_OP_NULL); seg_leaves++; }
+            ops.push_back(PB_OP_FLUSH | (uint32_t)n_flush++);
+            seg_leaves = 0;
+        };
+        for (int64_t i = l0; i < l1; i++) {
+            const int32_t child = ctx->lop_child[i], par = ctx->lop_parent[i];
+            const bool test = par != ctx->root;     // edges hanging off the root are never tested (HC.java:1674)
+            if (test && cur != par) { ops.push_back(PB_OP_SETCUR | (uint32_t)par); cur = par; }
+            if (ctx->is_leaf[child]) {
+                if (seg_leaves == PB_K1_SEG_LEAVES) flush();
+                ops.push_back(PB_OP_LEAF | (test ? PB_OP_TEST : 0u) | (uint32_t)child);
+                seg_leaves++;
+            } else {
+                ops.push_back(PB_OP_SETCUR | (test ? PB_OP_TEST : 0u) | (uint32_t)child);
+                cur = child;
+            }
+        }
+        flush();   // every chunk ends with a flush (possibly of an all-zero census)
+        while (ops.size() % 4) ops.push_back(PB_OP_NULL);
+        chunk_op[c + 1] = (int32_t)ops.size();
+    }
+    ctx->n_flush = n_flush;
+    ctx->n_ops = (int64_t)ops.size();
     int rc;
-    if ((rc = upload(ctx, &ctx->d_chunk_lg, lg))) return rc;
-    if ((rc = upload(ctx, &ctx->d_chunk_io, io))) return rc;
+    if ((rc = upload(ctx, &ctx->d_ops, ops))) return rc;
+    if ((rc = upload(ctx, &ctx->d_chunk_op, chunk_op))) return rc;
     if (ctx->d_census) { cudaFree(ctx->d_census); ctx->d_census = nullptr; }
-    PB_CUDA(cudaMalloc(&ctx->d_census, (size_t)n_chunks * 4 * PB_K1_KS * ctx->W * 8));
+    PB_CUDA(cudaMalloc(&ctx->d_census, (size_t)n_flush * 4 * PB_K1_KS * ctx->W * 8));
+    if (ctx->d_census_total) { cudaFree(ctx->d_census_total); ctx->d_census_total = nullptr; }
+    PB_CUDA(cudaMalloc(&ctx->d_census_total, (size_t)4 * PB_K1_KT * ctx->W * 8));
     return PB_OK;
 }
 
@@ -179,7 +208,7 @@ static int build_node_sample(pb_ctx* ctx) {
 extern "C" int pb_set_tree(pb_ctx* ctx, int32_t n_nodes, const int32_t* parent, const uint8_t* is_leaf) {
     CHECK_CTX(ctx);
     if (n_nodes < 2 || !parent || !is_leaf) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: need >= 2 nodes, parent[] and is_leaf[]");
-    if (n_nodes > (int32_t)PB_EV_NODE_MASK) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: too many nodes (limit 2^29-1)");
+    if (n_nodes >= (int32_t)PB_EV_NODE_MASK) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: too many nodes (limit 2^29-2)");
     PB_CUDA(cudaSetDevice(ctx->device));
     int32_t root = -1, L = 0;
     std::vector<int32_t> nchild(n_nodes, 0);
@@ -194,6 +223,7 @@ extern "C" int pb_set_tree(pb_ctx* ctx, int32_t n_nodes, const int32_t* parent, 
         L += is_leaf[v] != 0;
     }
     if (is_leaf[root]) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: the root is a leaf");
+    if (L >= (1 << PB_K1_KT)) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: too many leaves (limit 2^24-1)");
     ctx->N = n_nodes; ctx->L = L; ctx->root = root;
     ctx->parent.assign(parent, parent + n_nodes);
     ctx->is_leaf.assign(is_leaf, is_leaf + n_nodes);

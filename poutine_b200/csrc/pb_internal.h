@@ -8,11 +8,17 @@
 
 #include "../../include/poutine_b200.h"
 
-// ---- device-side record layouts -------------------------------------------------------------
-struct EdgeOp {        // one tree edge of the K1 schedule
-    int32_t child;     // node index; < 0 = padding slot of a leaf group
-    int32_t parent;    // node index; < 0 = edge hangs off the root: no MRCA test (HC.java:1674)
-};
+// ---- K1 edge program -----------------------------------------------------------------------------
+// One 32-bit op per tree row visit, in DFS preorder (pb_api.cu build_program):
+//   bits 0..28 node index (PB_OP_NULL = no row), bit 29 TEST (MRCA test against the current parent row),
+//   bit 30 SETCUR (this row becomes the current parent row), bit 31 LEAF (leaf census).
+//   TEST|SETCUR|LEAF together = FLUSH: write the census partial number <node field> and clear it.
+#define PB_OP_NODE_MASK 0x1FFFFFFFu
+#define PB_OP_NULL 0x1FFFFFFFu
+#define PB_OP_TEST 0x20000000u
+#define PB_OP_SETCUR 0x40000000u
+#define PB_OP_LEAF 0x80000000u
+#define PB_OP_FLUSH 0xE0000000u
 
 // raw MRCA event: lo = site (context-local), hi = node | base<<29 | is_leaf<<31
 typedef unsigned long long raw_event_t;
@@ -28,12 +34,16 @@ typedef unsigned long long raw_event_t;
 #define PB_SF_A2_USE 4u
 #define PB_SF_A1_CODE_SHIFT 3  // 2 bits
 
-// census: 4 per-base counters, bit-sliced; slices 0..2 = ones/twos/fours, 3.. = high part
-#define PB_K1_KHI 8
+// census: 4 per-base leaf counters, bit-sliced: slices 0..2 (ones/twos/fours) in registers,
+// PB_K1_KHI high slices in shared memory; a census segment holds at most PB_K1_SEG_LEAVES leaves
+#define PB_K1_KHI 6
 #define PB_K1_KS (3 + PB_K1_KHI)
-#define PB_K1_MAX_LEAVES_PER_CHUNK 2040
-#define PB_K1_THREADS 128
-#define PB_K1_QCAP 3072  // per-block event queue (24 KB)
+#define PB_K1_SEG_LEAVES 504
+#define PB_K1_KT 24         // slices of the reduced census (leaf counts < 2^24)
+#define PB_K1_COLS 128      // 64-site word columns per block = consumer threads
+#define PB_K1_THREADS 160   // 4 consumer warps + 1 TMA producer warp
+#define PB_K1_STAGES 6      // row ring (3 planes x 1 KB per stage)
+#define PB_K1_QCAP 768      // per-block event queue (6 KB)
 
 // allele flags
 #define PB_AF_IN_USE 1u
@@ -59,12 +69,11 @@ struct pb_ctx {
     int32_t N = 0, L = 0, root = -1;
     std::vector<int32_t> parent;
     std::vector<uint8_t> is_leaf;
-    EdgeOp* d_leaf_ops = nullptr;   // padded to groups of 8
-    EdgeOp* d_int_ops = nullptr;
-    int32_t n_leaf_groups = 0, n_int_ops = 0;
-    int32_t n_chunks = 0;
-    int32_t* d_chunk_lg = nullptr;  // n_chunks+1 leaf-group boundaries
-    int32_t* d_chunk_io = nullptr;  // n_chunks+1 internal-op boundaries
+    std::vector<int32_t> lop_child, lop_parent;  // logical edge list in DFS preorder (host)
+    uint32_t* d_ops = nullptr;      // K1 program
+    int32_t* d_chunk_op = nullptr;  // n_chunks+1 op boundaries (multiples of 4)
+    int32_t n_chunks = 0, n_flush = 0;
+    int64_t n_ops = 0;
     int32_t* d_node_sample = nullptr;  // N: sample index of a leaf with a pheno row, else -1
 
     // labels
@@ -78,7 +87,8 @@ struct pb_ctx {
     uint64_t *d_B0 = nullptr, *d_B1 = nullptr, *d_V = nullptr;
 
     // K1 outputs
-    uint64_t* d_census = nullptr;      // [n_chunks][4][KS][W]
+    uint64_t* d_census = nullptr;      // [n_flush][4][KS][W]
+    uint64_t* d_census_total = nullptr;  // [4][KT][W]
     raw_event_t* d_raw = nullptr;
     int64_t raw_cap = 0;
     unsigned long long* d_raw_cursor = nullptr;
