@@ -23,6 +23,8 @@
 //        whose table row is not monotone take the exact scalar path bit by bit.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "pb_internal.h"
 
 // ---------------------------------------------------------------------------------------------------
@@ -64,60 +66,68 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 // mode 0: Philox (sampling spec in DESIGN.md §K3a; restated by oracle/oracle.cpp or_philox_labels)
 // mode 1: replay (sample j gets label[perms[rep*P + j]])
-template <int MODE>
+// One thread = one replicate; a warp ballot turns 32 replicates' labels of one sample into a matrix word.
+template <int MODE, bool MISS>
 __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
                                                              int32_t n_ctrl, const uint8_t* __restrict__ label,
                                                              const uint32_t* __restrict__ perms, uint32_t* __restrict__ Xc32,
                                                              uint32_t* __restrict__ Xm32, int64_t Rw32) {
-    __shared__ uint32_t sc[GEN_ROWS][8], sm[GEN_ROWS][8];
+    __shared__ uint32_t sc[GEN_ROWS][8], sm[MISS ? GEN_ROWS : 1][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rep_local = (int64_t)blockIdx.x * GEN_THREADS + tid;
     const bool active = rep_local < n_reps;
     const uint64_t rep = (uint64_t)(rep_base + rep_local);
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), r0 = (uint32_t)rep, r1 = (uint32_t)(rep >> 32);
     uint32_t rem_case = (uint32_t)n_case, rem_ctrl = (uint32_t)n_ctrl, q = 0;
-    uint32_t w[4] = {0, 0, 0, 0};
     const uint32_t* prow = (MODE == 1 && active) ? perms + rep_local * (int64_t)P : nullptr;
 
-    for (int i0 = 0; i0 < P; i0 += GEN_ROWS) {
+    for (int i0 = 0; i0 < P; i0 += GEN_ROWS) {          // GEN_ROWS is a multiple of 4
         const int rows = min(GEN_ROWS, P - i0);
-        for (int ii = 0; ii < rows; ii++) {
-            const int i = i0 + ii;
-            uint32_t lab;
-            if (MODE == 0) {
-                if ((i & 3) == 0) philox4x32_10((uint32_t)(i >> 2), r0, r1, 0u, k0, k1, w);
-                const uint32_t range = (uint32_t)(P - i);
-                uint32_t x = w[i & 3];
-                uint64_t prod = (uint64_t)x * range;
-                uint32_t lo = (uint32_t)prod;
-                if (lo < range) {  // Lemire: exact rejection, taken with probability < range / 2^32
-                    const uint32_t t = (0u - range) % range;
-                    while (lo < t) {
-                        uint32_t rw[4];
-                        philox4x32_10(q >> 2, r0, r1, 1u, k0, k1, rw);
-                        x = rw[q & 3];
-                        q++;
-                        prod = (uint64_t)x * range;
-                        lo = (uint32_t)prod;
+        for (int ii = 0; ii < rows; ii += 4) {
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (MODE == 0) philox4x32_10((uint32_t)((i0 + ii) >> 2), r0, r1, 0u, k0, k1, w);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = i0 + ii + j;
+                if (i < P) {                              // block-uniform
+                    uint32_t lab;
+                    if (MODE == 0) {
+                        const uint32_t range = (uint32_t)(P - i);
+                        uint64_t prod = (uint64_t)w[j] * range;
+                        uint32_t lo = (uint32_t)prod;
+                        if (lo < range) {  // Lemire: exact rejection, taken with probability < range / 2^32
+                            const uint32_t t = (0u - range) % range;
+                            while (lo < t) {
+                                uint32_t rw[4];
+                                philox4x32_10(q >> 2, r0, r1, 1u, k0, k1, rw);
+                                const uint32_t x = (q & 2) ? ((q & 1) ? rw[3] : rw[2]) : ((q & 1) ? rw[1] : rw[0]);
+                                q++;
+                                prod = (uint64_t)x * range;
+                                lo = (uint32_t)prod;
+                            }
+                        }
+                        const uint32_t u = (uint32_t)(prod >> 32);
+                        if (u < rem_case) { lab = 1; rem_case--; }
+                        else if (u < rem_case + rem_ctrl) { lab = 0; rem_ctrl--; }
+                        else lab = 2;
+                    } else {
+                        lab = active ? label[prow[i]] : 0;
+                    }
+                    const uint32_t bc = __ballot_sync(0xffffffffu, active && lab == 1);
+                    if (lane == 0) sc[ii + j][warp] = bc;
+                    if (MISS) {
+                        const uint32_t bm = __ballot_sync(0xffffffffu, active && lab == 2);
+                        if (lane == 0) sm[ii + j][warp] = bm;
                     }
                 }
-                const uint32_t u = (uint32_t)(prod >> 32);
-                if (u < rem_case) { lab = 1; rem_case--; }
-                else if (u < rem_case + rem_ctrl) { lab = 0; rem_ctrl--; }
-                else lab = 2;
-            } else {
-                lab = active ? label[prow[i]] : 0;
             }
-            const uint32_t bc = __ballot_sync(0xffffffffu, active && lab == 1);
-            const uint32_t bm = __ballot_sync(0xffffffffu, active && lab == 2);
-            if (lane == 0) { sc[ii][warp] = bc; sm[ii][warp] = bm; }
         }
         __syncthreads();
         for (int t = tid; t < rows * 8; t += GEN_THREADS) {
             const int row = t >> 3, wd = t & 7;
             const int64_t o = (int64_t)(i0 + row) * Rw32 + (int64_t)blockIdx.x * 8 + wd;
             Xc32[o] = sc[row][wd];
-            if (Xm32) Xm32[o] = sm[row][wd];
+            if (MISS) Xm32[o] = sm[row][wd];
         }
         __syncthreads();
     }
@@ -250,32 +260,127 @@ __device__ __forceinline__ void sweep_allele(const K3Params& p, const AlleleMeta
     if (lane == 0 && rcount) p.r[slot] += rcount;   // this warp is the slot's only writer in this launch
 }
 
+// ---- tight sweeps for the common case ---------------------------------------------------------------
+// Preconditions (checked by k4_classify_kernel): PB_AF_FAST, no missing labels in the pheno file, no maxT
+// candidate possible (ktau[n] > n), 1 <= kstar <= N == m.n.  Padding replicate bits of the matrix are zero,
+// and k* >= 1, so they never count.  r += #{replicates : k_r >= k*}.
+template <int N, int K>
+__device__ __forceinline__ uint64_t at_least(const uint64_t (&x)[N]) {
+    if (N == 1) return x[0];
+    if (N == 2) return K == 1 ? (x[0] | x[1]) : (x[0] & x[1]);
+    if (N == 3) return K == 1 ? (x[0] | x[1] | x[2]) : K == 2 ? ((x[0] & x[1]) | (x[2] & (x[0] | x[1]))) : (x[0] & x[1] & x[2]);
+    return 0;
+}
+
+template <int N, int K>
+__device__ __forceinline__ unsigned int sweep_fixed(const K3Params& p, const AlleleMeta& m, int lane, int words) {
+    const uint64_t* __restrict__ rp[N];
+#pragma unroll
+    for (int e = 0; e < N; e++) rp[e] = p.Xc + (int64_t)__ldg(p.csr + m.off + e) * p.Rw + lane;
+    unsigned int rc = 0;
+#pragma unroll 4
+    for (int w = lane, off = 0; w < words; w += 32, off += 32) {
+        uint64_t x[N];
+#pragma unroll
+        for (int e = 0; e < N; e++) x[e] = __ldg(rp[e] + off);
+        rc += (unsigned int)__popcll(at_least<N, K>(x));
+    }
+    return rc;
+}
+
+// 4 <= n <= 7: bit-sliced 3-bit count, k >= k* with a warp-uniform k*
+__device__ __forceinline__ unsigned int sweep_upto7(const K3Params& p, const AlleleMeta& m, int lane, int words) {
+    const int n = m.n, kstar = m.kstar;
+    const uint64_t* __restrict__ rp[7];
+#pragma unroll
+    for (int e = 0; e < 7; e++) rp[e] = p.Xc + (int64_t)((e < n) ? __ldg(p.csr + m.off + e) : 0) * p.Rw + lane;
+    unsigned int rc = 0;
+#pragma unroll 2
+    for (int w = lane, off = 0; w < words; w += 32, off += 32) {
+        uint64_t c[3] = {0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 7; e++) {
+            if (e < n) {
+                uint64_t x = __ldg(rp[e] + off);
+#pragma unroll
+                for (int j = 0; j < 3; j++) { const uint64_t t = c[j] & x; c[j] ^= x; x = t; }
+            }
+        }
+        rc += (unsigned int)__popcll(ge_const<3>(c, kstar));
+    }
+    return rc;
+}
+
 #define K3_THREADS 256
-// LARGE = false: alleles with n < 8 (the vast majority; event lists in registers, few registers per thread);
-// LARGE = true : the long-list tail.  Two instantiations so the common case keeps high occupancy.
-template <bool LARGE>
-__global__ void __launch_bounds__(K3_THREADS, LARGE ? 1 : 3) k3_count_kernel(const K3Params p) {
+// work list B: alleles with 2 <= n < 8 (plus every small allele that needs the general path)
+__global__ void __launch_bounds__(K3_THREADS, 4) k3_count_small_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
     const double tau = *p.tau;
-    for (int64_t slot = gwarp; slot < p.n_slots; slot += nwarps) {
+    const int words = (int)((p.n_reps + 63) >> 6);
+    for (int64_t i = gwarp; i < n_list; i += nwarps) {
+        const int64_t slot = list[i];
         const AlleleMeta m = p.alleles[slot];
-        if (!(m.flags & PB_AF_IN_USE)) continue;
-        const int n = m.n;
-        if (!LARGE) {
+        const int n = m.n, ks = m.kstar;
+        const bool tight = (m.flags & PB_AF_FAST) && p.Xm == nullptr && p.ktau[n] > n;
+        if (tight) {
+            unsigned int rc;
+            if (ks <= 0) rc = (lane == 0) ? (unsigned int)p.n_reps : 0u;   // every replicate counts
+            else if (ks > n) rc = 0;
+            else if (n == 1) rc = sweep_fixed<1, 1>(p, m, lane, words);
+            else if (n == 2) rc = ks == 1 ? sweep_fixed<2, 1>(p, m, lane, words) : sweep_fixed<2, 2>(p, m, lane, words);
+            else if (n == 3) rc = ks == 1 ? sweep_fixed<3, 1>(p, m, lane, words) : ks == 2 ? sweep_fixed<3, 2>(p, m, lane, words)
+                                                                                           : sweep_fixed<3, 3>(p, m, lane, words);
+            else rc = sweep_upto7(p, m, lane, words);
+            rc = __reduce_add_sync(0xffffffffu, rc);
+            if (lane == 0 && rc) p.r[slot] += rc;
+        } else {
             if (n < 2) sweep_allele<1>(p, m, slot, lane, tau);
             else if (n < 4) sweep_allele<2>(p, m, slot, lane, tau);
-            else if (n < 8) sweep_allele<3>(p, m, slot, lane, tau);
-        } else {
-            if (n < 8) continue;
-            if (n < 16) sweep_allele<4>(p, m, slot, lane, tau);
-            else if (n < 64) sweep_allele<6>(p, m, slot, lane, tau);
-            else if (n < 256) sweep_allele<8>(p, m, slot, lane, tau);
-            else if (n < 4096) sweep_allele<12>(p, m, slot, lane, tau);
-            else sweep_allele<17>(p, m, slot, lane, tau);
+            else sweep_allele<3>(p, m, slot, lane, tau);
         }
     }
+}
+
+// work list C: the long-list tail (n >= 8)
+__global__ void __launch_bounds__(K3_THREADS, 1) k3_count_large_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
+    const double tau = *p.tau;
+    for (int64_t i = gwarp; i < n_list; i += nwarps) {
+        const int64_t slot = list[i];
+        const AlleleMeta m = p.alleles[slot];
+        const int n = m.n;
+        if (n < 16) sweep_allele<4>(p, m, slot, lane, tau);
+        else if (n < 64) sweep_allele<6>(p, m, slot, lane, tau);
+        else if (n < 256) sweep_allele<8>(p, m, slot, lane, tau);
+        else if (n < 4096) sweep_allele<12>(p, m, slot, lane, tau);
+        else sweep_allele<17>(p, m, slot, lane, tau);
+    }
+}
+
+// work list A: n <= 1 alleles of the tight class need no sweep at all — the per-sample column popcount is shared
+__global__ void k3_colpop_kernel(const uint64_t* __restrict__ Xc, int64_t Rw, int64_t words, uint32_t* __restrict__ colpop) {
+    __shared__ unsigned int sh[4];
+    const uint64_t* row = Xc + (int64_t)blockIdx.x * Rw;
+    unsigned int c = 0;
+    for (int64_t w = threadIdx.x; w < words; w += blockDim.x) c += (unsigned int)__popcll(row[w]);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) colpop[blockIdx.x] = sh[0] + sh[1] + sh[2] + sh[3];
+}
+__global__ void k3_trivial_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list, const uint32_t* __restrict__ colpop) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    const int64_t slot = list[i];
+    const AlleleMeta m = p.alleles[slot];
+    unsigned int rc = 0;
+    if (m.kstar <= 0) rc = (unsigned int)p.n_reps;
+    else if (m.n == 1 && m.kstar == 1) rc = colpop[p.csr[m.off]];
+    if (rc) p.r[slot] += rc;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -368,8 +473,9 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     ctx->tm.n_launches += 1;
 
     const bool has_miss = ctx->n_miss > 0;
-    // tile size: the label matrices of one tile stay L2-resident (126 MB L2): <= 48 MB in total by default
-    int64_t l2_budget = 48ll << 20;
+    // tile size: label matrices of one tile <= 512 MB by default (measured: K3b is insensitive to L2 residency,
+    // K3a wants as many replicates per launch as possible)
+    int64_t l2_budget = 512ll << 20;
     if (const char* e = getenv("PB_K3_TILE_MB")) l2_budget = atoll(e) << 20;
     int64_t tile = (l2_budget * 8) / ((int64_t)ctx->P * (has_miss ? 2 : 1));
     tile = (tile / 2048) * 2048;
@@ -388,6 +494,12 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             if ((rc = ensure(ctx, &pmx, &ctx->Xm_cap, need))) { ctx->d_Xmiss = nullptr; return rc; }
             ctx->d_Xmiss = (uint64_t*)pmx;
         }
+        if (!ctx->d_colpop || ctx->colpop_cap < ctx->P) {
+            if (ctx->d_colpop) cudaFree(ctx->d_colpop);
+            ctx->d_colpop = nullptr;
+            PB_CUDA(cudaMalloc(&ctx->d_colpop, (size_t)ctx->P * 4));
+            ctx->colpop_cap = ctx->P;
+        }
         void* pl = ctx->d_fb_reps;
         if ((rc = ensure(ctx, &pl, &ctx->fb_cap, (tile + 256) * 4))) { ctx->d_fb_reps = nullptr; return rc; }
         ctx->d_fb_reps = (int32_t*)pl;
@@ -405,13 +517,19 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             if ((rc = ensure(ctx, &pp, &cap, bytes))) { ctx->d_perms = nullptr; ctx->perms_cap = 0; return rc; }
             ctx->d_perms = (uint32_t*)pp; ctx->perms_cap = cap;
             PB_CUDA(cudaMemcpyAsync(ctx->d_perms, replay_perms + base * (int64_t)ctx->P, (size_t)bytes, cudaMemcpyHostToDevice, st));
-            k3_gen_kernel<1><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
-                                                             ctx->d_perms, (uint32_t*)ctx->d_Xcase,
-                                                             has_miss ? (uint32_t*)ctx->d_Xmiss : nullptr, Rw32);
+            if (has_miss)
+                k3_gen_kernel<1, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
+                                                                       ctx->d_perms, (uint32_t*)ctx->d_Xcase, (uint32_t*)ctx->d_Xmiss, Rw32);
+            else
+                k3_gen_kernel<1, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
+                                                                        ctx->d_perms, (uint32_t*)ctx->d_Xcase, nullptr, Rw32);
         } else {
-            k3_gen_kernel<0><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
-                                                             nullptr, (uint32_t*)ctx->d_Xcase,
-                                                             has_miss ? (uint32_t*)ctx->d_Xmiss : nullptr, Rw32);
+            if (has_miss)
+                k3_gen_kernel<0, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
+                                                                       nullptr, (uint32_t*)ctx->d_Xcase, (uint32_t*)ctx->d_Xmiss, Rw32);
+            else
+                k3_gen_kernel<0, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
+                                                                        nullptr, (uint32_t*)ctx->d_Xcase, nullptr, Rw32);
         }
         ctx->tm.n_launches += 1;
         PB_CUDA(cudaEventRecord(ctx->ev[6], st));
@@ -420,18 +538,26 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
         p.alleles = ctx->d_alleles; p.n_slots = n_slots; p.csr = ctx->d_csr; p.pobs = ctx->d_pobs; p.ptable = ctx->d_ptable;
         p.ktau = ctx->d_ktau; p.tau = ctx->d_tau; p.Xc = ctx->d_Xcase; p.Xm = has_miss ? ctx->d_Xmiss : nullptr; p.Rw = Rw;
         p.rep_base = base; p.n_reps = nr; p.r = ctx->d_r; p.maxT = ctx->d_maxT;
-        int64_t blocks = (int64_t)ctx->sm_count * 8;
-        if (const char* e = getenv("PB_K3_BLOCKS_PER_SM")) blocks = (int64_t)ctx->sm_count * atoll(e);
-        const int64_t max_blocks = (n_slots + (K3_THREADS / 32) - 1) / (K3_THREADS / 32);
-        if (blocks > max_blocks) blocks = max_blocks;
-        if (blocks < 1) blocks = 1;
         p.slots_per_chunk = 0;
-        k3_count_kernel<false><<<(unsigned)blocks, K3_THREADS, 0, st>>>(p);
-        if (ctx->n_max >= 8) {
-            k3_count_kernel<true><<<(unsigned)blocks, K3_THREADS, 0, st>>>(p);
+        const int64_t nA = ctx->n_work[0], nB = ctx->n_work[1], nC = ctx->n_work[2];
+        const int64_t words = (nr + 63) / 64;
+        int64_t bps = 16;
+        if (const char* e = getenv("PB_K3_BLOCKS_PER_SM")) bps = atoll(e);
+        if (nA > 0) {
+            k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(ctx->d_Xcase, Rw, words, ctx->d_colpop);
+            k3_trivial_kernel<<<(unsigned)((nA + T - 1) / T), T, 0, st>>>(p, ctx->d_work, nA, ctx->d_colpop);
+            ctx->tm.n_launches += 2;
+        }
+        if (nB > 0) {
+            int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * bps, (nB + (K3_THREADS / 32) - 1) / (K3_THREADS / 32));
+            k3_count_small_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, nB);
             ctx->tm.n_launches += 1;
         }
-        ctx->tm.n_launches += 1;
+        if (nC > 0) {
+            int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * 4, (nC + (K3_THREADS / 32) - 1) / (K3_THREADS / 32));
+            k3_count_large_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + 2 * n_slots, nC);
+            ctx->tm.n_launches += 1;
+        }
         PB_CUDA(cudaEventRecord(ctx->ev[7], st));
 
         // fallback for uncertified replicates

@@ -104,6 +104,31 @@ __global__ void k4_ktau_kernel(const double* __restrict__ tab, int32_t n_max, co
     ktau[n] = kt;
 }
 
+// ---- work lists for K3b: A = no sweep needed, B = short lists (n < 8), C = long lists -----------------
+__global__ void k4_classify_kernel(const AlleleMeta* __restrict__ alleles, int64_t n_slots, const int32_t* __restrict__ ktau, int has_miss,
+                                   int32_t* __restrict__ lists, unsigned int* __restrict__ counts) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cls = -1;
+    if (a < n_slots) {
+        const AlleleMeta m = alleles[a];
+        if (m.flags & PB_AF_IN_USE) {
+            const bool tight = (m.flags & PB_AF_FAST) && !has_miss && ktau[m.n] > m.n;
+            cls = (tight && (m.n <= 1 || m.kstar <= 0 || m.kstar > m.n)) ? 0 : (m.n < 8 ? 1 : 2);
+        }
+    }
+    const unsigned int lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const unsigned int mask = __ballot_sync(0xffffffffu, cls == c);
+        if (!mask) continue;
+        const int leader = __ffs(mask) - 1;
+        unsigned int base = 0;
+        if ((int)lane == leader) base = atomicAdd(counts + c, (unsigned int)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (cls == c) lists[(int64_t)c * n_slots + base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)a;
+    }
+}
+
 // ---- bitonic sort of maxT (m doubles in [0,1]; padded with +inf to a power of two) -----------------
 __global__ void k4_sort_init_kernel(const unsigned long long* __restrict__ maxT, int64_t m, int64_t n_pad, double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -215,16 +240,17 @@ int pbk_thresholds(pb_ctx* ctx) {
     const int32_t n_max = ctx->n_max;
     cudaStream_t st = ctx->stream;
     int rc;
-    // one scratch allocation: [expect 64 f64][tau f64][n_fast u64][ktau i32 x (n_max+1)][hist u32 x (n_max+1)]
+    // one scratch allocation: [expect 64 f64][tau f64][n_fast u64][list counts 4 x u32][ktau i32 x (n_max+1)][hist u32 x (n_max+1)]
     const int64_t n1 = (int64_t)n_max + 1;
-    const int64_t need = TAU_LEVELS * 8 + 8 + 8 + n1 * 4 + n1 * 4;
+    const int64_t need = TAU_LEVELS * 8 + 8 + 8 + 16 + n1 * 4 + n1 * 4;
     if ((rc = ensure_bytes(ctx, &ctx->d_thr, &ctx->thr_cap, need))) return rc;
     char* base = (char*)ctx->d_thr;
     double* d_expect = (double*)base;
     ctx->d_tau = (double*)(base + TAU_LEVELS * 8);
     unsigned long long* d_nfast = (unsigned long long*)(base + TAU_LEVELS * 8 + 8);
-    ctx->d_ktau = (int32_t*)(base + TAU_LEVELS * 8 + 16);
-    unsigned int* d_hist = (unsigned int*)(base + TAU_LEVELS * 8 + 16 + n1 * 4);
+    unsigned int* d_lcount = (unsigned int*)(base + TAU_LEVELS * 8 + 16);
+    ctx->d_ktau = (int32_t*)(base + TAU_LEVELS * 8 + 32);
+    unsigned int* d_hist = (unsigned int*)(base + TAU_LEVELS * 8 + 32 + n1 * 4);
     PB_CUDA(cudaMemsetAsync(ctx->d_thr, 0, (size_t)need, st));
     const int T = 256;
     const int force_general = (ctx->cfg.flags & PB_FLAG_FORCE_GENERAL_NULL) ? 1 : 0;
@@ -233,12 +259,22 @@ int pbk_thresholds(pb_ctx* ctx) {
     k4_tau_expect_kernel<<<TAU_LEVELS, 256, 0, st>>>(ctx->d_ptable, d_hist, n_max, d_expect);
     k4_tau_pick_kernel<<<1, 1, 0, st>>>(d_expect, 16.0, ctx->cfg.maxt_tau, ctx->d_tau);
     k4_ktau_kernel<<<(unsigned)((n1 + T - 1) / T), T, 0, st>>>(ctx->d_ptable, n_max, ctx->d_tau, ctx->d_ktau);
-    ctx->tm.n_launches += 4;
+    if (n_slots > ctx->work_cap) {
+        if (ctx->d_work) cudaFree(ctx->d_work);
+        ctx->d_work = nullptr;
+        ctx->work_cap = n_slots + n_slots / 8 + 1024;
+        PB_CUDA(cudaMalloc(&ctx->d_work, (size_t)ctx->work_cap * 3 * 4));
+    }
+    if (n_slots > 0)
+        k4_classify_kernel<<<(unsigned)((n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ktau, ctx->n_miss > 0 ? 1 : 0,
+                                                                          ctx->d_work, d_lcount);
+    ctx->tm.n_launches += 5;
     PB_CUDA(cudaGetLastError());
-    unsigned long long nf = 0;
-    PB_CUDA(cudaMemcpyAsync(&nf, d_nfast, 8, cudaMemcpyDeviceToHost, st));
+    struct { unsigned long long nf; unsigned int lc[4]; } h;
+    PB_CUDA(cudaMemcpyAsync(&h, d_nfast, sizeof(h), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
-    ctx->tm.n_fast_alleles = (int64_t)nf;
+    ctx->tm.n_fast_alleles = (int64_t)h.nf;
+    for (int c = 0; c < 3; c++) ctx->n_work[c] = (int64_t)h.lc[c];
     return PB_OK;
 }
 
