@@ -25,10 +25,7 @@
 #include "pb_internal.h"
 
 struct K1Params {
-    const uint64_t* __restrict__ B0;
-    const uint64_t* __restrict__ B1;
-    const uint64_t* __restrict__ V;
-    int64_t Wp, W;
+    int64_t W;
     uint64_t last_mask;                    // valid site bits of word W-1
     const uint32_t* __restrict__ ops;
     const int32_t* __restrict__ chunk_op;
@@ -44,29 +41,28 @@ __device__ __forceinline__ void csa(uint64_t& h, uint64_t& l, uint64_t a, uint64
     l = u ^ c;
 }
 
-// ---- mbarrier / TMA bulk-copy primitives (inline PTX) ---------------------------------------------
+// ---- mbarrier / TMA primitives (inline PTX; barrier and ring addresses are 32-bit shared-window offsets) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "K1_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra K1_WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// one 3-D tiled TMA load: box (128 words, 1 node, 3 planes) at (col0, node, 0) -> 3 KB in shared memory
+__device__ __forceinline__ void tma_load_row(uint32_t dst, const CUtensorMap* tmap, int32_t col0, int32_t node, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tmap), "r"(col0), "r"(node), "r"(0), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PB_K1_COLS) : "memory"); }
 
@@ -88,17 +84,17 @@ __device__ __forceinline__ void emit_events(uint64_t mrca, uint64_t b0, uint64_t
 }
 
 // consumers only: move the block's queued events to the global list (one global atomic)
-__device__ __forceinline__ void drain_queue(raw_event_t* s_queue, unsigned int* s_count, unsigned long long* s_base, int tid,
-                                            unsigned int threshold, const K1Params& p) {
+__device__ __noinline__ void drain_queue(raw_event_t* s_queue, unsigned int* s_count, unsigned long long* s_base, int tid,
+                                         unsigned int threshold, raw_event_t* raw, unsigned long long* raw_cursor, unsigned long long raw_cap) {
     consumer_bar_sync();
     const unsigned int n = min(*s_count, (unsigned int)PB_K1_QCAP);
     if (n >= threshold && n > 0) {   // block-uniform
-        if (tid == 0) *s_base = atomicAdd(p.raw_cursor, (unsigned long long)n);
+        if (tid == 0) *s_base = atomicAdd(raw_cursor, (unsigned long long)n);
         consumer_bar_sync();
         const unsigned long long base = *s_base;
         for (unsigned int i = tid; i < n; i += PB_K1_COLS) {
             const unsigned long long pos = base + i;
-            if (pos < p.raw_cap) p.raw[pos] = s_queue[i];
+            if (pos < raw_cap) raw[pos] = s_queue[i];
         }
         consumer_bar_sync();
         if (tid == 0) *s_count = 0;
@@ -106,30 +102,30 @@ __device__ __forceinline__ void drain_queue(raw_event_t* s_queue, unsigned int* 
     }
 }
 
-#define K1_ROW_BYTES (PB_K1_COLS * 8)
-#define K1_STAGE_BYTES (3 * K1_ROW_BYTES)
+#define K1_STAGE_BYTES (3 * PB_K1_COLS * 8)
 #define K1_SMEM_RING (PB_K1_STAGES * K1_STAGE_BYTES)
 #define K1_SMEM_HI ((PB_K1_KHI + 1) * 4 * PB_K1_COLS * 8)   // high slices + the pending fours-level input
 #define K1_SMEM_QUEUE (PB_K1_QCAP * 8)
-#define K1_SMEM_TOTAL (K1_SMEM_RING + K1_SMEM_HI + K1_SMEM_QUEUE)
+#define K1_SMEM_BARS (2 * PB_K1_STAGES * 8)
+#define K1_SMEM_TOTAL (K1_SMEM_RING + K1_SMEM_HI + K1_SMEM_QUEUE + K1_SMEM_BARS)
 
-__global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const K1Params p) {
+__global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* ring = reinterpret_cast<uint64_t*>(smem);                                    // [stage][plane][col]
     uint64_t* s_hi = reinterpret_cast<uint64_t*>(smem + K1_SMEM_RING);                    // [slice][base][col]
     raw_event_t* s_queue = reinterpret_cast<raw_event_t*>(smem + K1_SMEM_RING + K1_SMEM_HI);
-    __shared__ __align__(8) uint64_t s_full[PB_K1_STAGES], s_empty[PB_K1_STAGES];
     __shared__ unsigned int s_count;
     __shared__ unsigned long long s_base;
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y;
-    const int64_t col0 = (int64_t)blockIdx.x * PB_K1_COLS;
+    const int32_t col0 = (int32_t)blockIdx.x * PB_K1_COLS;
     const int op0 = p.chunk_op[chunk], op1 = p.chunk_op[chunk + 1];
+    const uint32_t ring0 = smem_u32(smem);
+    const uint32_t full0 = ring0 + K1_SMEM_RING + K1_SMEM_HI + K1_SMEM_QUEUE, empty0 = full0 + 8 * PB_K1_STAGES;
 
     if (tid == 0) {
         s_count = 0;
-        for (int s = 0; s < PB_K1_STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], PB_K1_COLS / 32); }
+        for (int s = 0; s < PB_K1_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, PB_K1_COLS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -138,24 +134,18 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const K1Par
     __syncthreads();
 
     if (tid >= PB_K1_COLS) {
-        // ================= producer warp: one lane feeds the ring =================
+        // ================= producer warp: one lane feeds the ring with TMA =================
         if (tid == PB_K1_COLS) {
-            const int64_t cols = min((int64_t)PB_K1_COLS, p.Wp - col0);   // Wp is a multiple of 16 words -> 128 B granules
-            const uint32_t bytes = (uint32_t)(cols * 8);
-            int stage = 0;
-            uint32_t phase = 0;
+            uint32_t soff = 0, boff = 0, phase = 0;
             for (int i = op0; i < op1; i++) {
                 const uint32_t op = __ldg(p.ops + i);
                 const uint32_t node = op & PB_OP_NODE_MASK;
-                if ((op & PB_OP_FLUSH) == PB_OP_FLUSH || node == PB_OP_NULL) continue;
-                mbar_wait(&s_empty[stage], phase ^ 1);                   // consumers have drained this stage
-                mbar_arrive_expect_tx(&s_full[stage], 3 * bytes);
-                const int64_t off = (int64_t)node * p.Wp + col0;
-                uint64_t* dst = ring + (int64_t)stage * (3 * PB_K1_COLS);
-                tma_bulk_g2s(dst, p.V + off, bytes, &s_full[stage]);
-                tma_bulk_g2s(dst + PB_K1_COLS, p.B0 + off, bytes, &s_full[stage]);
-                tma_bulk_g2s(dst + 2 * PB_K1_COLS, p.B1 + off, bytes, &s_full[stage]);
-                if (++stage == PB_K1_STAGES) { stage = 0; phase ^= 1; }
+                if (op >= PB_OP_FLUSH || node == PB_OP_NULL) continue;
+                mbar_wait(empty0 + boff, phase ^ 1);                     // consumers have drained this stage
+                mbar_arrive_expect_tx(full0 + boff, K1_STAGE_BYTES);
+                tma_load_row(ring0 + soff, &tmap, col0, (int32_t)node, full0 + boff);
+                soff += K1_STAGE_BYTES; boff += 8;
+                if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
             }
         }
         return;
@@ -163,101 +153,95 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const K1Par
 
     // ================= consumer warps =================
     const int lane = tid & 31;
-    const int64_t w = col0 + tid;
-    const uint64_t vmask = (w >= p.W) ? 0ull : (w == p.W - 1 ? p.last_mask : ~0ull);
+    const int64_t w = (int64_t)col0 + tid;
+    const bool edge_block = (int64_t)col0 + PB_K1_COLS >= p.W;          // block-uniform: holds word W-1 (TMA zero-fills beyond W)
     const uint32_t site_base = (uint32_t)(w * 64);
+    const unsigned char* my_ring = smem + tid * 8;
 
+    // leaf census, bit-sliced with deferred carries: level L holds a counter slice and the OR of the carries the
+    // level below produced since its last update (two consecutive half-add carries are mutually exclusive:
+    // after a carry the slice bit is 0), and is updated every 2^L leaves.  No buffers to copy, 2 LOP3 per level-1 add.
     uint64_t ones[4] = {0, 0, 0, 0}, twos[4] = {0, 0, 0, 0}, fours[4] = {0, 0, 0, 0};
-    uint64_t b1[4] = {0, 0, 0, 0}, b2[4] = {0, 0, 0, 0};   // pending carry-save inputs (the fours-level one lives in s_hi)
-    uint64_t* s_b4 = s_hi + (PB_K1_KHI * 4) * PB_K1_COLS + tid;
+    uint64_t pend2[4] = {0, 0, 0, 0}, pend4[4] = {0, 0, 0, 0};   // pending carries into twos / fours (pend8 lives in s_hi)
+    uint64_t* s_p8 = s_hi + (PB_K1_KHI * 4) * PB_K1_COLS + tid;
     uint64_t pv = 0, p0 = 0, p1 = 0;   // current parent row
     int nleaf = 0;
-    int stage = 0;
-    uint32_t phase = 0;
+    uint32_t soff = 0, boff = 0, phase = 0;
+    const uint64_t edge_mask = (edge_block && w == p.W - 1) ? p.last_mask : ~0ull;
 
+#pragma unroll 1
     for (int i = op0; i < op1; i++) {
-        if (((i - op0) & 63) == 63) drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p);
-        {
-            const uint32_t op = __ldg(p.ops + i);
-            const uint32_t node = op & PB_OP_NODE_MASK;
-            if ((op & PB_OP_FLUSH) == PB_OP_FLUSH) {
-                // census partial `node`: [flush][base][slice][W]
-                if (w < p.W) {
-                    uint64_t* out = p.census + ((int64_t)node * 4 * PB_K1_KS) * p.W + w;
+        const uint32_t op = __ldg(p.ops + i);
+        const uint32_t node = op & PB_OP_NODE_MASK;
+        if (op >= PB_OP_FLUSH) {
+            // census partial `node`: [flush][base][slice][W]   (segments are padded to 8 leaves: nothing is pending)
+            if (w < p.W) {
+                uint64_t* out = p.census + ((int64_t)node * 4 * PB_K1_KS) * p.W + w;
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        out[((int64_t)c * PB_K1_KS + 0) * p.W] = ones[c];
-                        out[((int64_t)c * PB_K1_KS + 1) * p.W] = twos[c];
-                        out[((int64_t)c * PB_K1_KS + 2) * p.W] = fours[c];
+                for (int c = 0; c < 4; c++) {
+                    out[((int64_t)c * PB_K1_KS + 0) * p.W] = ones[c];
+                    out[((int64_t)c * PB_K1_KS + 1) * p.W] = twos[c];
+                    out[((int64_t)c * PB_K1_KS + 2) * p.W] = fours[c];
 #pragma unroll
-                        for (int j = 0; j < PB_K1_KHI; j++) out[((int64_t)c * PB_K1_KS + 3 + j) * p.W] = s_hi[(j * 4 + c) * PB_K1_COLS + tid];
-                    }
+                    for (int j = 0; j < PB_K1_KHI; j++) out[((int64_t)c * PB_K1_KS + 3 + j) * p.W] = s_hi[(j * 4 + c) * PB_K1_COLS + tid];
                 }
-#pragma unroll
-                for (int c = 0; c < 4; c++) { ones[c] = twos[c] = fours[c] = 0; b1[c] = b2[c] = 0; }
-#pragma unroll
-                for (int j = 0; j < PB_K1_KHI * 4; j++) s_hi[j * PB_K1_COLS + tid] = 0;
-                nleaf = 0;
-                continue;
             }
-            uint64_t cv = 0, c0 = 0, c1 = 0;
-            if (node != PB_OP_NULL) {
-                mbar_wait(&s_full[stage], phase);                        // TMA bytes have landed
-                const uint64_t* src = ring + (int64_t)stage * (3 * PB_K1_COLS) + tid;
-                cv = src[0] & vmask; c0 = src[PB_K1_COLS]; c1 = src[2 * PB_K1_COLS];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[stage]);              // stage is free again
-                if (++stage == PB_K1_STAGES) { stage = 0; phase ^= 1; }
-                if (op & PB_OP_TEST) {
-                    const uint64_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
-                    if (mrca) emit_events(mrca, c0, c1, site_base, node | (op & PB_OP_LEAF), s_queue, &s_count, p);
-                }
-                if (op & PB_OP_SETCUR) { pv = cv; p0 = c0; p1 = c1; }
-            } else if (!(op & PB_OP_LEAF)) {
-                continue;                                                // padding
+#pragma unroll
+            for (int c = 0; c < 4; c++) { ones[c] = twos[c] = fours[c] = 0; pend2[c] = pend4[c] = 0; }
+#pragma unroll
+            for (int j = 0; j < (PB_K1_KHI + 1) * 4; j++) s_hi[j * PB_K1_COLS + tid] = 0;
+            nleaf = 0;
+            continue;
+        }
+        uint64_t cv = 0, c0 = 0, c1 = 0;
+        if (node != PB_OP_NULL) {
+            mbar_wait(full0 + boff, phase);                              // TMA bytes have landed
+            const uint64_t* src = reinterpret_cast<const uint64_t*>(my_ring + soff);
+            cv = src[0]; c0 = src[PB_K1_COLS]; c1 = src[2 * PB_K1_COLS];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + boff);                   // stage is free again
+            soff += K1_STAGE_BYTES; boff += 8;
+            if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
+            if (edge_block) cv &= edge_mask;                             // caller's padding bits of the last word never count
+            if (op & PB_OP_TEST) {
+                const uint64_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
+                if (mrca) emit_events(mrca, c0, c1, site_base, node | (op & PB_OP_LEAF), s_queue, &s_count, p);
             }
-            if (op & PB_OP_LEAF) {
-                uint64_t x[4];
-                x[0] = cv & ~c0 & ~c1; x[1] = cv & c0 & ~c1; x[2] = cv & ~c0 & c1; x[3] = cv & c0 & c1;
-                const int ph = nleaf & 7;                                // block-uniform
-                nleaf++;
-                if (!(ph & 1)) {
+            if (op & PB_OP_SETCUR) { pv = cv; p0 = c0; p1 = c1; }
+        }
+        if (op & PB_OP_LEAF) {
+            const uint64_t x[4] = {cv & ~c0 & ~c1, cv & c0 & ~c1, cv & ~c0 & c1, cv & c0 & c1};
+            const int ph = nleaf & 7;                                    // block-uniform
+            nleaf++;
 #pragma unroll
-                    for (int c = 0; c < 4; c++) b1[c] = x[c];
-                } else {
-                    uint64_t t2[4];
+            for (int c = 0; c < 4; c++) { pend2[c] |= ones[c] & x[c]; ones[c] ^= x[c]; }
+            if (ph & 1) {
 #pragma unroll
-                    for (int c = 0; c < 4; c++) csa(t2[c], ones[c], ones[c], b1[c], x[c]);
-                    if (!(ph & 2)) {
+                for (int c = 0; c < 4; c++) { pend4[c] |= twos[c] & pend2[c]; twos[c] ^= pend2[c]; pend2[c] = 0; }
+                if (ph & 2) {
+                    if (!(ph & 4)) {
 #pragma unroll
-                        for (int c = 0; c < 4; c++) b2[c] = t2[c];
+                        for (int c = 0; c < 4; c++) { s_p8[c * PB_K1_COLS] = fours[c] & pend4[c]; fours[c] ^= pend4[c]; pend4[c] = 0; }
                     } else {
-                        uint64_t t4[4];
 #pragma unroll
-                        for (int c = 0; c < 4; c++) csa(t4[c], twos[c], twos[c], b2[c], t2[c]);
-                        if (!(ph & 4)) {
+                        for (int c = 0; c < 4; c++) {
+                            uint64_t carry = s_p8[c * PB_K1_COLS] | (fours[c] & pend4[c]);
+                            fours[c] ^= pend4[c]; pend4[c] = 0;
 #pragma unroll
-                            for (int c = 0; c < 4; c++) s_b4[c * PB_K1_COLS] = t4[c];
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 4; c++) {
-                                uint64_t carry;
-                                csa(carry, fours[c], fours[c], s_b4[c * PB_K1_COLS], t4[c]);
-#pragma unroll
-                                for (int j = 0; j < PB_K1_KHI; j++) {
-                                    uint64_t* hp = s_hi + (j * 4 + c) * PB_K1_COLS + tid;
-                                    const uint64_t h = *hp;
-                                    *hp = h ^ carry;
-                                    carry &= h;
-                                }
+                            for (int j = 0; j < PB_K1_KHI; j++) {
+                                uint64_t* hp = s_hi + (j * 4 + c) * PB_K1_COLS + tid;
+                                const uint64_t h = *hp;
+                                *hp = h ^ carry;
+                                carry &= h;
                             }
                         }
                     }
                 }
             }
         }
+        if (((i - op0) & 63) == 63) drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
     }
-    drain_queue(s_queue, &s_count, &s_base, tid, 1, p);
+    drain_queue(s_queue, &s_count, &s_base, tid, 1, p.raw, p.raw_cursor, p.raw_cap);
 }
 
 // ---- per-site event counters -------------------------------------------------------------------
@@ -512,8 +496,7 @@ __global__ void k1_scatter_events_kernel(const raw_event_t* __restrict__ raw, in
 // =================================================================================================
 int pbk_events(pb_ctx* ctx) {
     K1Params p;
-    p.B0 = ctx->d_B0; p.B1 = ctx->d_B1; p.V = ctx->d_V;
-    p.Wp = ctx->Wp; p.W = ctx->W;
+    p.W = ctx->W;
     p.last_mask = (ctx->S & 63) ? ((1ull << (ctx->S & 63)) - 1) : ~0ull;
     p.ops = ctx->d_ops; p.chunk_op = ctx->d_chunk_op;
     p.census = ctx->d_census;
@@ -527,7 +510,7 @@ int pbk_events(pb_ctx* ctx) {
     dim3 grid((unsigned)((ctx->W + PB_K1_COLS - 1) / PB_K1_COLS), (unsigned)ctx->n_chunks);
     PB_CUDA(cudaMemsetAsync(ctx->d_raw_cursor, 0, 8, ctx->stream));
     PB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    k1_events_kernel<<<grid, PB_K1_THREADS, smem, ctx->stream>>>(p);
+    k1_events_kernel<<<grid, PB_K1_THREADS, smem, ctx->stream>>>(ctx->tmap, p);
     PB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());

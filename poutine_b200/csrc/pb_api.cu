@@ -16,7 +16,7 @@ extern "C" int pb_version(void) { return 100; }
 extern "C" const char* pb_last_error(pb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 static void free_all(pb_ctx* c) {
-    void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_node_sample, c->d_label, c->d_B0, c->d_B1, c->d_V,
+    void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_node_sample, c->d_label, c->d_planes,
                     c->d_census, c->d_census_total, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
                     c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT,
                     c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop};
@@ -269,24 +269,43 @@ extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
     if (n_sites < 1 || n_sites >= (1ll << 32)) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: n_sites out of range");
     PB_CUDA(cudaSetDevice(ctx->device));
     ctx->events_done = ctx->assoc_done = false;
-    if (n_sites == ctx->S && ctx->d_B0) return PB_OK;
-    for (uint64_t** p : {&ctx->d_B0, &ctx->d_B1, &ctx->d_V}) if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n_sites == ctx->S && ctx->d_planes) return PB_OK;
+    if (ctx->d_planes) { cudaFree(ctx->d_planes); ctx->d_planes = nullptr; }
+    ctx->d_B0 = ctx->d_B1 = ctx->d_V = nullptr;
     for (void** p : {(void**)&ctx->d_cnt, (void**)&ctx->d_sites, (void**)&ctx->d_site_flags, (void**)&ctx->d_site_scan, (void**)&ctx->d_raw})
         if (*p) { cudaFree(*p); *p = nullptr; }
     ctx->S = n_sites;
     ctx->W = (n_sites + 63) / 64;
     ctx->Wp = (ctx->W + 15) & ~15ll;  // rows padded to 128 B
     const size_t plane = (size_t)ctx->N * ctx->Wp * 8;
-    cudaError_t e;
-    if ((e = cudaMalloc(&ctx->d_B0, plane)) != cudaSuccess || (e = cudaMalloc(&ctx->d_B1, plane)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_V, plane)) != cudaSuccess) {
+    cudaError_t e = cudaMalloc(&ctx->d_planes, 3 * plane);
+    if (e != cudaSuccess) {
         ctx->err = std::string("pb_set_sites: cudaMalloc of 3 x ") + std::to_string(plane) + " B planes: " + cudaGetErrorString(e);
         ctx->S = 0;
         return PB_ERR_OOM;
     }
-    PB_CUDA(cudaMemsetAsync(ctx->d_B0, 0, plane, ctx->stream));
-    PB_CUDA(cudaMemsetAsync(ctx->d_B1, 0, plane, ctx->stream));
-    PB_CUDA(cudaMemsetAsync(ctx->d_V, 0, plane, ctx->stream));
+    ctx->d_V = ctx->d_planes;
+    ctx->d_B0 = ctx->d_planes + (size_t)ctx->N * ctx->Wp;
+    ctx->d_B1 = ctx->d_planes + 2 * (size_t)ctx->N * ctx->Wp;
+    PB_CUDA(cudaMemsetAsync(ctx->d_planes, 0, 3 * plane, ctx->stream));
+    {
+        // TMA descriptor: dims (word column, node, plane); one box = the 3 KB a block needs of one tree row
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        PB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(ctx, PB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        const cuuint64_t gdim[3] = {(cuuint64_t)ctx->W, (cuuint64_t)ctx->N, 3};
+        const cuuint64_t gstride[2] = {(cuuint64_t)ctx->Wp * 8, (cuuint64_t)plane};
+        const cuuint32_t box[3] = {PB_K1_COLS, 1, 3};
+        const cuuint32_t estride[3] = {1, 1, 1};
+        CUresult cr = ((encode_fn)fn)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, ctx->d_planes, gdim, gstride, box, estride,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) FAIL(ctx, PB_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)cr) + ")");
+    }
     PB_CUDA(cudaMalloc(&ctx->d_cnt, (size_t)n_sites * PB_CNT_STRIDE * 4));
     PB_CUDA(cudaMalloc(&ctx->d_sites, (size_t)n_sites * sizeof(pb_site_out)));
     PB_CUDA(cudaMalloc(&ctx->d_site_flags, (size_t)n_sites));

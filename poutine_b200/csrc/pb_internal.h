@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libpoutine_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -42,7 +43,7 @@ typedef unsigned long long raw_event_t;
 #define PB_K1_KT 24         // slices of the reduced census (leaf counts < 2^24)
 #define PB_K1_COLS 128      // 64-site word columns per block = consumer threads
 #define PB_K1_THREADS 160   // 4 consumer warps + 1 TMA producer warp
-#define PB_K1_STAGES 6      // row ring (3 planes x 1 KB per stage)
+#define PB_K1_STAGES 6      // row ring (one 3 KB TMA box per stage: 3 planes x 128 words)
 #define PB_K1_QCAP 768      // per-block event queue (6 KB)
 
 // allele flags
@@ -84,7 +85,9 @@ struct pb_ctx {
 
     // sites / planes
     int64_t S = 0, W = 0, Wp = 0;
-    uint64_t *d_B0 = nullptr, *d_B1 = nullptr, *d_V = nullptr;
+    uint64_t* d_planes = nullptr;   // one allocation [3][N][Wp]: plane 0 = V, 1 = B0, 2 = B1
+    uint64_t *d_B0 = nullptr, *d_B1 = nullptr, *d_V = nullptr;   // views into d_planes
+    CUtensorMap tmap{};             // 3-D TMA descriptor over d_planes: box = 128 words x 1 node x 3 planes
 
     // K1 outputs
     uint64_t* d_census = nullptr;      // [n_flush][4][KS][W]
