@@ -102,12 +102,60 @@ __device__ __noinline__ void drain_queue(raw_event_t* s_queue, unsigned int* s_c
     }
 }
 
-#define K1_STAGE_BYTES (3 * PB_K1_COLS * 8)
+#define K1_ROW_BYTES (3 * PB_K1_COLS * 8)
+#define K1_STAGE_BYTES (2 * K1_ROW_BYTES)
 #define K1_SMEM_RING (PB_K1_STAGES * K1_STAGE_BYTES)
-#define K1_SMEM_HI ((PB_K1_KHI + 1) * 4 * PB_K1_COLS * 8)   // high slices + the pending fours-level input
+#define K1_SMEM_HI ((PB_K1_KHI + 1) * 4 * PB_K1_COLS * 8)   // high slices + the pending carries into slice 8
 #define K1_SMEM_QUEUE (PB_K1_QCAP * 8)
 #define K1_SMEM_BARS (2 * PB_K1_STAGES * 8)
 #define K1_SMEM_TOTAL (K1_SMEM_RING + K1_SMEM_HI + K1_SMEM_QUEUE + K1_SMEM_BARS)
+
+// consumer-thread state of the leaf census (see k1_events_kernel)
+struct Census {
+    uint64_t ones[4], twos[4], fours[4], pend2[4], pend4[4];
+    int nleaf;
+};
+
+// one tree row: MRCA test against the current parent row, optional parent update, optional leaf census
+__device__ __forceinline__ void k1_row(uint32_t op, uint64_t cv, uint64_t c0, uint64_t c1, uint64_t& pv, uint64_t& p0, uint64_t& p1,
+                                       Census& cs, uint64_t* s_hi, uint64_t* s_p8, int tid, uint32_t site_base, raw_event_t* s_queue,
+                                       unsigned int* s_count, const K1Params& p) {
+    if (op & PB_OP_TEST) {
+        const uint64_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
+        if (mrca) emit_events(mrca, c0, c1, site_base, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), s_queue, s_count, p);
+    }
+    if (op & PB_OP_SETCUR) { pv = cv; p0 = c0; p1 = c1; }
+    if (op & PB_OP_LEAF) {
+        const uint64_t x[4] = {cv & ~c0 & ~c1, cv & c0 & ~c1, cv & ~c0 & c1, cv & c0 & c1};
+        const int ph = cs.nleaf & 7;                                 // block-uniform
+        cs.nleaf++;
+#pragma unroll
+        for (int c = 0; c < 4; c++) { cs.pend2[c] |= cs.ones[c] & x[c]; cs.ones[c] ^= x[c]; }
+        if (ph & 1) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) { cs.pend4[c] |= cs.twos[c] & cs.pend2[c]; cs.twos[c] ^= cs.pend2[c]; cs.pend2[c] = 0; }
+            if (ph & 2) {
+                if (!(ph & 4)) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { s_p8[c * PB_K1_COLS] = cs.fours[c] & cs.pend4[c]; cs.fours[c] ^= cs.pend4[c]; cs.pend4[c] = 0; }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint64_t carry = s_p8[c * PB_K1_COLS] | (cs.fours[c] & cs.pend4[c]);
+                        cs.fours[c] ^= cs.pend4[c]; cs.pend4[c] = 0;
+#pragma unroll
+                        for (int j = 0; j < PB_K1_KHI; j++) {
+                            uint64_t* hp = s_hi + (j * 4 + c) * PB_K1_COLS + tid;
+                            const uint64_t h = *hp;
+                            *hp = h ^ carry;
+                            carry &= h;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -119,7 +167,8 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y;
     const int32_t col0 = (int32_t)blockIdx.x * PB_K1_COLS;
-    const int op0 = p.chunk_op[chunk], op1 = p.chunk_op[chunk + 1];
+    const int r0 = p.chunk_op[chunk], r1 = p.chunk_op[chunk + 1];
+    const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(p.ops);
     const uint32_t ring0 = smem_u32(smem);
     const uint32_t full0 = ring0 + K1_SMEM_RING + K1_SMEM_HI + K1_SMEM_QUEUE, empty0 = full0 + 8 * PB_K1_STAGES;
 
@@ -130,20 +179,22 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (tid < PB_K1_COLS)
-        for (int i = 0; i < PB_K1_KHI * 4; i++) s_hi[i * PB_K1_COLS + tid] = 0;
+        for (int i = 0; i < (PB_K1_KHI + 1) * 4; i++) s_hi[i * PB_K1_COLS + tid] = 0;
     __syncthreads();
 
     if (tid >= PB_K1_COLS) {
         // ================= producer warp: one lane feeds the ring with TMA =================
         if (tid == PB_K1_COLS) {
             uint32_t soff = 0, boff = 0, phase = 0;
-            for (int i = op0; i < op1; i++) {
-                const uint32_t op = __ldg(p.ops + i);
-                const uint32_t node = op & PB_OP_NODE_MASK;
-                if (op >= PB_OP_FLUSH || node == PB_OP_NULL) continue;
+            for (int i = r0; i < r1; i++) {
+                const uint4 rec = __ldg(recs + i);
+                const uint32_t na = rec.x & PB_OP_NODE_MASK, nb = rec.y & PB_OP_NODE_MASK;
+                const uint32_t nreal = (na != PB_OP_NULL ? 1u : 0u) + (nb != PB_OP_NULL ? 1u : 0u);
+                if (nreal == 0) continue;
                 mbar_wait(empty0 + boff, phase ^ 1);                     // consumers have drained this stage
-                mbar_arrive_expect_tx(full0 + boff, K1_STAGE_BYTES);
-                tma_load_row(ring0 + soff, &tmap, col0, (int32_t)node, full0 + boff);
+                mbar_arrive_expect_tx(full0 + boff, nreal * K1_ROW_BYTES);
+                if (na != PB_OP_NULL) tma_load_row(ring0 + soff, &tmap, col0, (int32_t)na, full0 + boff);
+                if (nb != PB_OP_NULL) tma_load_row(ring0 + soff + K1_ROW_BYTES, &tmap, col0, (int32_t)nb, full0 + boff);
                 soff += K1_STAGE_BYTES; boff += 8;
                 if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
             }
@@ -161,85 +212,53 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
     // leaf census, bit-sliced with deferred carries: level L holds a counter slice and the OR of the carries the
     // level below produced since its last update (two consecutive half-add carries are mutually exclusive:
     // after a carry the slice bit is 0), and is updated every 2^L leaves.  No buffers to copy, 2 LOP3 per level-1 add.
-    uint64_t ones[4] = {0, 0, 0, 0}, twos[4] = {0, 0, 0, 0}, fours[4] = {0, 0, 0, 0};
-    uint64_t pend2[4] = {0, 0, 0, 0}, pend4[4] = {0, 0, 0, 0};   // pending carries into twos / fours (pend8 lives in s_hi)
-    uint64_t* s_p8 = s_hi + (PB_K1_KHI * 4) * PB_K1_COLS + tid;
+    Census cs;
+#pragma unroll
+    for (int c = 0; c < 4; c++) { cs.ones[c] = cs.twos[c] = cs.fours[c] = 0; cs.pend2[c] = cs.pend4[c] = 0; }
+    cs.nleaf = 0;
+    uint64_t* s_p8 = s_hi + (PB_K1_KHI * 4) * PB_K1_COLS + tid;       // pending carries into slice 8
     uint64_t pv = 0, p0 = 0, p1 = 0;   // current parent row
-    int nleaf = 0;
     uint32_t soff = 0, boff = 0, phase = 0;
     const uint64_t edge_mask = (edge_block && w == p.W - 1) ? p.last_mask : ~0ull;
 
 #pragma unroll 1
-    for (int i = op0; i < op1; i++) {
-        const uint32_t op = __ldg(p.ops + i);
-        const uint32_t node = op & PB_OP_NODE_MASK;
-        if (op >= PB_OP_FLUSH) {
-            // census partial `node`: [flush][base][slice][W]   (segments are padded to 8 leaves: nothing is pending)
+    for (int i = r0; i < r1; i++) {
+        const uint4 rec = __ldg(recs + i);
+        const bool ra = (rec.x & PB_OP_NODE_MASK) != PB_OP_NULL, rb = (rec.y & PB_OP_NODE_MASK) != PB_OP_NULL;
+        uint64_t av = 0, a0 = 0, a1 = 0, bv = 0, b0 = 0, b1 = 0;
+        if (ra | rb) {
+            mbar_wait(full0 + boff, phase);                              // TMA bytes have landed
+            const uint64_t* src = reinterpret_cast<const uint64_t*>(my_ring + soff);
+            if (ra) { av = src[0]; a0 = src[PB_K1_COLS]; a1 = src[2 * PB_K1_COLS]; }
+            if (rb) { bv = src[3 * PB_K1_COLS]; b0 = src[4 * PB_K1_COLS]; b1 = src[5 * PB_K1_COLS]; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + boff);                   // stage is free again
+            soff += K1_STAGE_BYTES; boff += 8;
+            if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
+            if (edge_block) { av &= edge_mask; bv &= edge_mask; }        // caller's padding bits of the last word never count
+        }
+        k1_row(rec.x, av, a0, a1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, s_queue, &s_count, p);
+        k1_row(rec.y, bv, b0, b1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, s_queue, &s_count, p);
+        if (rec.z != PB_REC_NOFLUSH) {
+            // census partial rec.z: [flush][base][slice][W]   (segments are padded to 8 leaves: nothing is pending)
             if (w < p.W) {
-                uint64_t* out = p.census + ((int64_t)node * 4 * PB_K1_KS) * p.W + w;
+                uint64_t* out = p.census + ((int64_t)rec.z * 4 * PB_K1_KS) * p.W + w;
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    out[((int64_t)c * PB_K1_KS + 0) * p.W] = ones[c];
-                    out[((int64_t)c * PB_K1_KS + 1) * p.W] = twos[c];
-                    out[((int64_t)c * PB_K1_KS + 2) * p.W] = fours[c];
+                    out[((int64_t)c * PB_K1_KS + 0) * p.W] = cs.ones[c];
+                    out[((int64_t)c * PB_K1_KS + 1) * p.W] = cs.twos[c];
+                    out[((int64_t)c * PB_K1_KS + 2) * p.W] = cs.fours[c];
 #pragma unroll
                     for (int j = 0; j < PB_K1_KHI; j++) out[((int64_t)c * PB_K1_KS + 3 + j) * p.W] = s_hi[(j * 4 + c) * PB_K1_COLS + tid];
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 4; c++) { ones[c] = twos[c] = fours[c] = 0; pend2[c] = pend4[c] = 0; }
+            for (int c = 0; c < 4; c++) { cs.ones[c] = cs.twos[c] = cs.fours[c] = 0; cs.pend2[c] = cs.pend4[c] = 0; }
 #pragma unroll
             for (int j = 0; j < (PB_K1_KHI + 1) * 4; j++) s_hi[j * PB_K1_COLS + tid] = 0;
-            nleaf = 0;
-            continue;
+            cs.nleaf = 0;
         }
-        uint64_t cv = 0, c0 = 0, c1 = 0;
-        if (node != PB_OP_NULL) {
-            mbar_wait(full0 + boff, phase);                              // TMA bytes have landed
-            const uint64_t* src = reinterpret_cast<const uint64_t*>(my_ring + soff);
-            cv = src[0]; c0 = src[PB_K1_COLS]; c1 = src[2 * PB_K1_COLS];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + boff);                   // stage is free again
-            soff += K1_STAGE_BYTES; boff += 8;
-            if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
-            if (edge_block) cv &= edge_mask;                             // caller's padding bits of the last word never count
-            if (op & PB_OP_TEST) {
-                const uint64_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
-                if (mrca) emit_events(mrca, c0, c1, site_base, node | (op & PB_OP_LEAF), s_queue, &s_count, p);
-            }
-            if (op & PB_OP_SETCUR) { pv = cv; p0 = c0; p1 = c1; }
-        }
-        if (op & PB_OP_LEAF) {
-            const uint64_t x[4] = {cv & ~c0 & ~c1, cv & c0 & ~c1, cv & ~c0 & c1, cv & c0 & c1};
-            const int ph = nleaf & 7;                                    // block-uniform
-            nleaf++;
-#pragma unroll
-            for (int c = 0; c < 4; c++) { pend2[c] |= ones[c] & x[c]; ones[c] ^= x[c]; }
-            if (ph & 1) {
-#pragma unroll
-                for (int c = 0; c < 4; c++) { pend4[c] |= twos[c] & pend2[c]; twos[c] ^= pend2[c]; pend2[c] = 0; }
-                if (ph & 2) {
-                    if (!(ph & 4)) {
-#pragma unroll
-                        for (int c = 0; c < 4; c++) { s_p8[c * PB_K1_COLS] = fours[c] & pend4[c]; fours[c] ^= pend4[c]; pend4[c] = 0; }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            uint64_t carry = s_p8[c * PB_K1_COLS] | (fours[c] & pend4[c]);
-                            fours[c] ^= pend4[c]; pend4[c] = 0;
-#pragma unroll
-                            for (int j = 0; j < PB_K1_KHI; j++) {
-                                uint64_t* hp = s_hi + (j * 4 + c) * PB_K1_COLS + tid;
-                                const uint64_t h = *hp;
-                                *hp = h ^ carry;
-                                carry &= h;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        if (((i - op0) & 63) == 63) drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
+        if (((i - r0) & 31) == 31) drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
     }
     drain_queue(s_queue, &s_count, &s_base, tid, 1, p.raw, p.raw_cursor, p.raw_cap);
 }

@@ -156,36 +156,46 @@ static int build_chunks(pb_ctx* ctx) {
     n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, 65535));
     ctx->n_chunks = (int32_t)n_chunks;
 
-    std::vector<uint32_t> ops;
-    ops.reserve((size_t)n_lops * 5 / 4 + 64 * n_chunks);
+    std::vector<uint32_t> recs;   // 4 words per record
+    recs.reserve((size_t)n_lops * 3 + 64 * n_chunks);
     std::vector<int32_t> chunk_op(n_chunks + 1, 0);
     int32_t n_flush = 0;
     for (int64_t c = 0; c < n_chunks; c++) {
         const int64_t l0 = n_lops * c / n_chunks, l1 = n_lops * (c + 1) / n_chunks;
         int32_t cur = -1;       // node whose row the kernel holds as "current parent"
         int32_t seg_leaves = 0;
+        uint32_t slot[2] = {PB_OP_NULL, PB_OP_NULL};
+        int filled = 0;
+        auto close = [&](uint32_t flush_id) {
+            recs.push_back(slot[0]); recs.push_back(slot[1]); recs.push_back(flush_id); recs.push_back(0u);
+            slot[0] = slot[1] = PB_OP_NULL; filled = 0;
+        };
+        auto push = [&](uint32_t op) {
+            slot[filled++] = op;
+            if (filled == 2) close(PB_REC_NOFLUSH);
+        };
         auto flush = [&]() {
-            while (seg_leaves % 8) { ops.push_back(PB_OP_LEAF | PB_OP_NULL); seg_leaves++; }
-            ops.push_back(PB_OP_FLUSH | (uint32_t)n_flush++);
+            while (seg_leaves % 8) { push(PB_OP_LEAF | PB_OP_NULL); seg_leaves++; }
+            close((uint32_t)n_flush++);   // closes the open record (possibly empty) with the flush attached
             seg_leaves = 0;
         };
         for (int64_t i = l0; i < l1; i++) {
             const int32_t child = ctx->lop_child[i], par = ctx->lop_parent[i];
             const bool test = par != ctx->root;     // edges hanging off the root are never tested (HC.java:1674)
-            if (test && cur != par) { ops.push_back(PB_OP_SETCUR | (uint32_t)par); cur = par; }
+            if (test && cur != par) { push(PB_OP_SETCUR | (uint32_t)par); cur = par; }
             if (ctx->is_leaf[child]) {
                 if (seg_leaves == PB_K1_SEG_LEAVES) flush();
-                ops.push_back(PB_OP_LEAF | (test ? PB_OP_TEST : 0u) | (uint32_t)child);
+                push(PB_OP_LEAF | (test ? PB_OP_TEST : 0u) | (uint32_t)child);
                 seg_leaves++;
             } else {
-                ops.push_back(PB_OP_SETCUR | (test ? PB_OP_TEST : 0u) | (uint32_t)child);
+                push(PB_OP_SETCUR | (test ? PB_OP_TEST : 0u) | (uint32_t)child);
                 cur = child;
             }
         }
         flush();   // every chunk ends with a flush (possibly of an all-zero census)
-        while (ops.size() % 4) ops.push_back(PB_OP_NULL);
-        chunk_op[c + 1] = (int32_t)ops.size();
+        chunk_op[c + 1] = (int32_t)(recs.size() / 4);
     }
+    const std::vector<uint32_t>& ops = recs;
     ctx->n_flush = n_flush;
     ctx->n_ops = (int64_t)ops.size();
     int rc;

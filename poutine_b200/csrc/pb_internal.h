@@ -10,7 +10,8 @@
 #include "../../include/poutine_b200.h"
 
 // ---- K1 edge program -----------------------------------------------------------------------------
-// One 32-bit op per tree row visit, in DFS preorder (pb_api.cu build_program):
+// One 32-bit op per tree row visit, in DFS preorder (pb_api.cu build_chunks); the kernel consumes them as
+// 16-byte records {op A, op B, flush id or PB_REC_NOFLUSH, 0}: two rows per ring stage, census flush after them.
 //   bits 0..28 node index (PB_OP_NULL = no row), bit 29 TEST (MRCA test against the current parent row),
 //   bit 30 SETCUR (this row becomes the current parent row), bit 31 LEAF (leaf census).
 //   TEST|SETCUR|LEAF together = FLUSH: write the census partial number <node field> and clear it.
@@ -20,6 +21,7 @@
 #define PB_OP_SETCUR 0x40000000u
 #define PB_OP_LEAF 0x80000000u
 #define PB_OP_FLUSH 0xE0000000u
+#define PB_REC_NOFLUSH 0xFFFFFFFFu
 
 // raw MRCA event: lo = site (context-local), hi = node | base<<29 | is_leaf<<31
 typedef unsigned long long raw_event_t;
@@ -37,13 +39,13 @@ typedef unsigned long long raw_event_t;
 
 // census: 4 per-base leaf counters, bit-sliced: slices 0..2 (ones/twos/fours) in registers,
 // PB_K1_KHI high slices in shared memory; a census segment holds at most PB_K1_SEG_LEAVES leaves
-#define PB_K1_KHI 6
+#define PB_K1_KHI 5
 #define PB_K1_KS (3 + PB_K1_KHI)
-#define PB_K1_SEG_LEAVES 504
+#define PB_K1_SEG_LEAVES 248
 #define PB_K1_KT 24         // slices of the reduced census (leaf counts < 2^24)
 #define PB_K1_COLS 128      // 64-site word columns per block = consumer threads
 #define PB_K1_THREADS 160   // 4 consumer warps + 1 TMA producer warp
-#define PB_K1_STAGES 6      // row ring (one 3 KB TMA box per stage: 3 planes x 128 words)
+#define PB_K1_STAGES 4      // ring of row PAIRS (two 3 KB TMA boxes per stage: 3 planes x 128 words each)
 #define PB_K1_QCAP 768      // per-block event queue (6 KB)
 
 // allele flags
@@ -72,7 +74,7 @@ struct pb_ctx {
     std::vector<uint8_t> is_leaf;
     std::vector<int32_t> lop_child, lop_parent;  // logical edge list in DFS preorder (host)
     uint32_t* d_ops = nullptr;      // K1 program
-    int32_t* d_chunk_op = nullptr;  // n_chunks+1 op boundaries (multiples of 4)
+    int32_t* d_chunk_op = nullptr;  // n_chunks+1 record boundaries
     int32_t n_chunks = 0, n_flush = 0;
     int64_t n_ops = 0;
     int32_t* d_node_sample = nullptr;  // N: sample index of a leaf with a pheno row, else -1
