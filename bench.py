@@ -238,7 +238,7 @@ def run_b200(args):
         t0 = time.perf_counter()
         hc.put_planes(*host_planes)                      # H2D of this step's inputs (pinned host memory)
         t1 = time.perf_counter()
-        ev, cc = hc.count_all_homoplasy_events()         # D2H: per-site Homoplasy_Events records
+        ev, cc = hc.count_all_homoplasy_events(compact=False)   # D2H: per-site Homoplasy_Events records (page-locked buffer)
         t2 = time.perf_counter()
         st, mt = hc.assoc()                              # D2H: per-informative-site statistics + sorted maxT
         t3 = time.perf_counter()

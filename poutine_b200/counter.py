@@ -73,11 +73,26 @@ class HomoplasyCounter:
         self.n_nodes = 0
         self.n_samples = 0
         self.n_informative = 0
+        self._pinned = {}   # name -> (array, handle): page-locked result buffers, reused across calls
 
     def close(self):
         if self._h is not None:
             _lib.lib().pb_destroy(self._h)
             self._h = None
+        for _, p in getattr(self, "_pinned", {}).values():
+            _lib.pinned_free(p)
+        self._pinned = {}
+
+    def _result_buffer(self, name, n, dtype):
+        """page-locked (cudaHostAlloc) result buffer of >= n records; D2H into pageable memory is several
+        times slower.  The returned array is a VIEW that the next call of the same entry point overwrites."""
+        cur = self._pinned.get(name)
+        if cur is None or len(cur[0]) < n:
+            if cur is not None:
+                _lib.pinned_free(cur[1])
+            cap = max(int(n), 1)
+            self._pinned[name] = _lib.pinned_empty((cap,), dtype)
+        return self._pinned[name][0][:n]
 
     def __del__(self):
         try:
@@ -129,11 +144,13 @@ class HomoplasyCounter:
         self.set_planes(B0, B1, V, chars.shape[1])
 
     # ---- the two reference entry points ----------------------------------------------------------
-    def count_all_homoplasy_events(self, fetch_sites=True):
+    def count_all_homoplasy_events(self, fetch_sites=True, compact=True):
         """-> (all_events, class_counts).  all_events = structured array over the BIALLELIC sites in
-        site order (the reference's ArrayList<Homoplasy_Events>), fields as Homoplasy_Events."""
+        site order (the reference's ArrayList<Homoplasy_Events>), fields as Homoplasy_Events.
+        compact=False returns the C ABI's own output instead: one record per site (site_class tells which
+        are biallelic), as a view of a page-locked buffer that the next call overwrites."""
         cc = PbClassCounts()
-        sites = np.empty(self.n_sites, dtype=SITE_DTYPE) if fetch_sites else None
+        sites = self._result_buffer("sites", self.n_sites, SITE_DTYPE) if fetch_sites else None
         self._check(_lib.lib().pb_run_events(self._h, ptr(sites), C.byref(cc)))
         counts = dict(no_allele=cc.n_no_allele, mono=cc.n_mono, bi=cc.n_bi, tri=cc.n_tri, quad=cc.n_quad,
                       raw_events=cc.n_raw_events)
@@ -141,6 +158,8 @@ class HomoplasyCounter:
         self.sites = sites
         if not fetch_sites:
             return None, counts
+        if not compact:
+            return sites, counts
         return sites[sites["site_class"] == 2], counts
 
     def assoc(self, replay_perms=None, fetch=True, want_maxT=True):
@@ -149,8 +168,8 @@ class HomoplasyCounter:
         L = _lib.lib()
         tm = self.timings()
         cap = max(int(tm["n_informative"]), 1)
-        stats = np.empty(cap, dtype=STAT_DTYPE) if fetch else None
-        maxT = np.empty(self.m, dtype=np.float64) if (fetch and want_maxT) else None
+        stats = self._result_buffer("stats", cap, STAT_DTYPE) if fetch else None
+        maxT = self._result_buffer("maxT", self.m, np.float64) if (fetch and want_maxT) else None
         n_inf = C.c_int64(0)
         perms = None
         if replay_perms is not None:

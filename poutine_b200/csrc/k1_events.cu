@@ -21,6 +21,7 @@
 //   * the leaf census (how many leaves carry A/C/G/T per site) is dense: bit-sliced vertical counters,
 //     Harley-Seal carry-save levels 1/2/4 in registers, slices 8.. in shared memory.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "pb_internal.h"
 
@@ -520,7 +521,8 @@ int pbk_events(pb_ctx* ctx) {
     p.ops = ctx->d_ops; p.chunk_op = ctx->d_chunk_op;
     p.census = ctx->d_census;
     p.raw = ctx->d_raw; p.raw_cursor = ctx->d_raw_cursor; p.raw_cap = (unsigned long long)ctx->raw_cap;
-    const size_t smem = (size_t)K1_SMEM_TOTAL;
+    size_t smem = (size_t)K1_SMEM_TOTAL;
+    if (const char* e = getenv("PB_K1_SMEM_PAD_KB")) smem += (size_t)atoi(e) * 1024;   // experiment knob: lowers blocks/SM
     static bool attr_set = false;
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(k1_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

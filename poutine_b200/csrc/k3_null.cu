@@ -443,6 +443,71 @@ static int ensure(pb_ctx* ctx, void** ptr, int64_t* cap, int64_t need_bytes) {
     return PB_OK;
 }
 
+// replicate tiling of the label matrices + their buffers
+struct K3Plan { int64_t tile, Rw32, Rw; bool has_miss; };
+
+static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
+    const int64_t m = ctx->cfg.n_replicates;
+    pl->has_miss = ctx->n_miss > 0;
+    // tile size: label matrices of one tile <= 512 MB by default (measured: K3b is insensitive to L2 residency,
+    // K3a wants as many replicates per launch as possible)
+    int64_t budget = 512ll << 20;
+    if (const char* e = getenv("PB_K3_TILE_MB")) budget = atoll(e) << 20;
+    int64_t tile = (budget * 8) / ((int64_t)ctx->P * (pl->has_miss ? 2 : 1));
+    tile = (tile / 2048) * 2048;
+    if (tile < 2048) tile = 2048;
+    const int64_t m_pad = ((m + 255) / 256) * 256;
+    if (tile > m_pad) tile = m_pad;
+    pl->tile = tile;
+    pl->Rw32 = ((tile + 255) / 256) * 8;  // uint32 pitch
+    pl->Rw = pl->Rw32 / 2;
+    int rc;
+    const int64_t need = (int64_t)ctx->P * pl->Rw * 8;
+    void* pc = ctx->d_Xcase;
+    if ((rc = ensure(ctx, &pc, &ctx->X_cap, need))) { ctx->d_Xcase = nullptr; return rc; }
+    ctx->d_Xcase = (uint64_t*)pc;
+    if (pl->has_miss) {
+        void* pmx = ctx->d_Xmiss;
+        if ((rc = ensure(ctx, &pmx, &ctx->Xm_cap, need))) { ctx->d_Xmiss = nullptr; return rc; }
+        ctx->d_Xmiss = (uint64_t*)pmx;
+    }
+    return PB_OK;
+}
+
+static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t nr, cudaStream_t st) {
+    const unsigned gblocks = (unsigned)((nr + GEN_THREADS - 1) / GEN_THREADS);
+    if (pl.has_miss)
+        k3_gen_kernel<0, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr,
+                                                               (uint32_t*)ctx->d_Xcase, (uint32_t*)ctx->d_Xmiss, pl.Rw32);
+    else
+        k3_gen_kernel<0, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr,
+                                                                (uint32_t*)ctx->d_Xcase, nullptr, pl.Rw32);
+    ctx->tm.n_launches += 1;
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// Called by pb_run_events right after the K1 sweep is enqueued: the label matrix of the first replicate tile
+// depends only on the phenotype table and the seed, so it is generated on a second stream while the (small,
+// latency-bound) K1 tail, K2 and the p-table kernels run; pb_run_assoc picks it up through an event.
+int pbk_pregen_labels(pb_ctx* ctx) {
+    ctx->pregen_valid = false;
+    if (ctx->cfg.mode != PB_MODE_PHILOX || ctx->P == 0 || ctx->n_case + ctx->n_ctrl == 0) return PB_OK;
+    if (getenv("PB_NO_PREGEN")) return PB_OK;
+    K3Plan pl;
+    int rc;
+    if ((rc = k3_plan(ctx, &pl))) return rc;
+    const int64_t m = ctx->cfg.n_replicates;
+    const int64_t nr = m < pl.tile ? m : pl.tile;
+    PB_CUDA(cudaEventRecord(ctx->ev_k1_done, ctx->stream));
+    PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_k1_done, 0));
+    if ((rc = k3_launch_philox(ctx, pl, 0, nr, ctx->stream2))) return rc;
+    PB_CUDA(cudaEventRecord(ctx->ev_gen_done, ctx->stream2));
+    ctx->pregen_valid = true;
+    ctx->pregen_tile = pl.tile;
+    return PB_OK;
+}
+
 int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     const int64_t m = ctx->cfg.n_replicates;
     const int64_t n_slots = 2 * ctx->S_inf;
@@ -472,28 +537,11 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     PB_CUDA(cudaMemsetAsync(ctx->d_r, 0, (size_t)n_slots * 4, st));
     ctx->tm.n_launches += 1;
 
-    const bool has_miss = ctx->n_miss > 0;
-    // tile size: label matrices of one tile <= 512 MB by default (measured: K3b is insensitive to L2 residency,
-    // K3a wants as many replicates per launch as possible)
-    int64_t l2_budget = 512ll << 20;
-    if (const char* e = getenv("PB_K3_TILE_MB")) l2_budget = atoll(e) << 20;
-    int64_t tile = (l2_budget * 8) / ((int64_t)ctx->P * (has_miss ? 2 : 1));
-    tile = (tile / 2048) * 2048;
-    if (tile < 2048) tile = 2048;
-    const int64_t m_pad = ((m + 255) / 256) * 256;
-    if (tile > m_pad) tile = m_pad;
-    const int64_t Rw32 = ((tile + 255) / 256) * 8;  // uint32 pitch
-    const int64_t Rw = Rw32 / 2;
+    K3Plan pl;
+    if ((rc = k3_plan(ctx, &pl))) return rc;
+    const bool has_miss = pl.has_miss;
+    const int64_t tile = pl.tile, Rw32 = pl.Rw32, Rw = pl.Rw;
     {
-        const int64_t need = (int64_t)ctx->P * Rw * 8;
-        void* pc = ctx->d_Xcase;
-        if ((rc = ensure(ctx, &pc, &ctx->X_cap, need))) { ctx->d_Xcase = nullptr; return rc; }
-        ctx->d_Xcase = (uint64_t*)pc;
-        if (has_miss) {
-            void* pmx = ctx->d_Xmiss;
-            if ((rc = ensure(ctx, &pmx, &ctx->Xm_cap, need))) { ctx->d_Xmiss = nullptr; return rc; }
-            ctx->d_Xmiss = (uint64_t*)pmx;
-        }
         if (!ctx->d_colpop || ctx->colpop_cap < ctx->P) {
             if (ctx->d_colpop) cudaFree(ctx->d_colpop);
             ctx->d_colpop = nullptr;
@@ -523,15 +571,13 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             else
                 k3_gen_kernel<1, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
                                                                         ctx->d_perms, (uint32_t*)ctx->d_Xcase, nullptr, Rw32);
+            ctx->tm.n_launches += 1;
+        } else if (base == 0 && ctx->pregen_valid && ctx->pregen_tile == tile) {
+            PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_gen_done, 0));   // tile 0 was generated alongside the K1 tail
         } else {
-            if (has_miss)
-                k3_gen_kernel<0, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
-                                                                       nullptr, (uint32_t*)ctx->d_Xcase, (uint32_t*)ctx->d_Xmiss, Rw32);
-            else
-                k3_gen_kernel<0, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
-                                                                        nullptr, (uint32_t*)ctx->d_Xcase, nullptr, Rw32);
+            if ((rc = k3_launch_philox(ctx, pl, base, nr, st))) return rc;
         }
-        ctx->tm.n_launches += 1;
+        ctx->pregen_valid = false;
         PB_CUDA(cudaEventRecord(ctx->ev[6], st));
 
         K3Params p;

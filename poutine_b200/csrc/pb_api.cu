@@ -58,7 +58,10 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
     };
     if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_k1_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_gen_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_raw_cursor, 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_class_counts, 16 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_fb_count, 4)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -71,7 +74,11 @@ extern "C" void pb_destroy(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     pbn_destroy(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     free_all(ctx);
+    if (ctx->ev_k1_done) cudaEventDestroy(ctx->ev_k1_done);
+    if (ctx->ev_gen_done) cudaEventDestroy(ctx->ev_gen_done);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -238,6 +245,8 @@ extern "C" int pb_set_tree(pb_ctx* ctx, int32_t n_nodes, const int32_t* parent, 
     ctx->parent.assign(parent, parent + n_nodes);
     ctx->is_leaf.assign(is_leaf, is_leaf + n_nodes);
     ctx->events_done = ctx->assoc_done = false;
+    if (ctx->stream2) PB_CUDA(cudaStreamSynchronize(ctx->stream2));
+    ctx->pregen_valid = false;
     ctx->P = 0; ctx->sample_node.clear(); ctx->label.clear();
     int rc;
     if ((rc = build_schedule(ctx))) return rc;
@@ -264,6 +273,8 @@ extern "C" int pb_set_labels(pb_ctx* ctx, int32_t n_samples, const int32_t* samp
         if (label[j] == PB_LABEL_CASE) nc++; else if (label[j] == PB_LABEL_CONTROL) nt++; else if (label[j] == PB_LABEL_MISSING) nm++;
         else FAIL(ctx, PB_ERR_INVALID, "pb_set_labels: label code must be 0, 1 or 2");
     }
+    if (ctx->stream2) PB_CUDA(cudaStreamSynchronize(ctx->stream2));   // a pre-generated label matrix is stale now
+    ctx->pregen_valid = false;
     ctx->P = n_samples; ctx->n_case = nc; ctx->n_ctrl = nt; ctx->n_miss = nm;
     ctx->sample_node.assign(sample_node, sample_node + n_samples);
     ctx->label.assign(label, label + n_samples);
@@ -351,6 +362,7 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
     PB_CUDA(cudaEventRecord(ctx->ev[12], ctx->stream));
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = pbk_events(ctx))) return rc;
+        if (attempt == 0 && (rc = pbk_pregen_labels(ctx))) return rc;
         unsigned long long cur = 0;
         PB_CUDA(cudaMemcpyAsync(&cur, ctx->d_raw_cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -65,6 +65,9 @@ struct pb_ctx {
     pb_config cfg{};
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // label-matrix pre-generation (K3a) alongside the K1 tail
+    cudaEvent_t ev_k1_done = nullptr, ev_gen_done = nullptr;
+    bool pregen_valid = false; int64_t pregen_tile = 0;
     std::string err;
     int sm_count = 148;
 
@@ -158,6 +161,7 @@ struct pb_ctx {
 int pbk_events(pb_ctx* ctx);                                   // k1_events.cu
 int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts); // k1_events.cu
 int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms);      // k3_null.cu (+ k4)
+int pbk_pregen_labels(pb_ctx* ctx);                            // k3_null.cu
 int pbk_ptable(pb_ctx* ctx);                                   // k4_pvalues.cu
 int pbk_thresholds(pb_ctx* ctx);                               // k4_pvalues.cu
 int pbk_pvalues(pb_ctx* ctx);                                  // k4_pvalues.cu
