@@ -4,8 +4,14 @@
 // Replaces: observed binomialTest calls (HC.java:3047-3057), the "n_k" p-value cache
 // (HC.java:4226-4236), calc_pointwise_estimate_binom (HC.java:4812-4838) and
 // calc_familywise_estimates_binom_combined_nulldists (HC.java:4558-4654).
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "binom_device.cuh"
 #include "pb_internal.h"
+
+namespace cg = cooperative_groups;
 
 // ---- f[n][k] = binomialTest(n, k, p, GREATER_THAN), triangular layout n*(n+1)/2 + k -------------
 __global__ void k4_ptable_kernel(double* __restrict__ tab, int32_t n_max, double p) {
@@ -130,40 +136,65 @@ __global__ void k4_classify_kernel(const AlleleMeta* __restrict__ alleles, int64
 }
 
 // ---- bitonic sort of maxT (m doubles in [0,1]; padded with +inf to a power of two) -----------------
-__global__ void k4_sort_init_kernel(const unsigned long long* __restrict__ maxT, int64_t m, int64_t n_pad, double* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_pad) out[i] = i < m ? __longlong_as_double((long long)maxT[i]) : __longlong_as_double(0x7FF0000000000000ll);
-}
-__global__ void k4_bitonic_step_kernel(double* __restrict__ a, int64_t n_pad, int64_t j, int64_t k) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pad) return;
-    const int64_t l = i ^ j;
-    if (l > i) {
-        const double x = a[i], y = a[l];
-        const bool up = (i & k) == 0;
-        if ((x > y) == up) { a[i] = y; a[l] = x; }
-    }
-}
-// all steps with j < 1024 of one k-phase, inside shared memory (2048 elements per block)
 #define BSORT_TILE 2048
-__global__ void __launch_bounds__(1024) k4_bitonic_smem_kernel(double* __restrict__ a, int64_t k, int64_t j_start) {
+// whole bitonic network in ONE cooperative launch: tile-local stages in shared memory, tile-crossing stages
+// in global memory with a grid barrier in between (replaces ~40 dependent launches at m = 1e5)
+__global__ void __launch_bounds__(1024) k4_sort_coop_kernel(const unsigned long long* __restrict__ maxT, int64_t m, int64_t n_pad,
+                                                            double* __restrict__ a) {
+    cg::grid_group grid = cg::this_grid();
     __shared__ double sh[BSORT_TILE];
-    const int64_t base = (int64_t)blockIdx.x * BSORT_TILE;
-    sh[threadIdx.x] = a[base + threadIdx.x];
-    sh[threadIdx.x + 1024] = a[base + threadIdx.x + 1024];
-    __syncthreads();
-    for (int64_t j = j_start; j > 0; j >>= 1) {
-        // each thread handles one compare-exchange pair
-        const int t = threadIdx.x;
-        const int lo = (int)(((t / j) * 2 * j) + (t % j));
-        const int hi = lo + (int)j;
-        const double x = sh[lo], y = sh[hi];
-        const bool up = ((base + lo) & k) == 0;
-        if ((x > y) == up) { sh[lo] = y; sh[hi] = x; }
+    const int t = threadIdx.x;
+    const int64_t n_tiles = n_pad / BSORT_TILE;
+    const double INF = __longlong_as_double(0x7FF0000000000000ll);
+    // local sort of every tile (all k <= BSORT_TILE), fused with the load / +inf padding
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * BSORT_TILE;
+        const int64_t i0 = base + t, i1 = base + t + 1024;
+        sh[t] = i0 < m ? __longlong_as_double((long long)maxT[i0]) : INF;
+        sh[t + 1024] = i1 < m ? __longlong_as_double((long long)maxT[i1]) : INF;
+        __syncthreads();
+        for (int k = 2; k <= BSORT_TILE; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const int lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+                const double x = sh[lo], y = sh[hi];
+                const bool up = ((base + lo) & k) == 0;
+                if ((x > y) == up) { sh[lo] = y; sh[hi] = x; }
+                __syncthreads();
+            }
+        a[i0] = sh[t];
+        a[i1] = sh[t + 1024];
         __syncthreads();
     }
-    a[base + threadIdx.x] = sh[threadIdx.x];
-    a[base + threadIdx.x + 1024] = sh[threadIdx.x + 1024];
+    grid.sync();
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + t, gthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = 2 * BSORT_TILE; k <= n_pad; k <<= 1) {
+        for (int64_t j = k >> 1; j >= BSORT_TILE; j >>= 1) {
+            for (int64_t idx = gtid; idx < n_pad / 2; idx += gthreads) {
+                const int64_t i = ((idx / j) * 2 * j) + (idx % j), l = i + j;
+                const double x = a[i], y = a[l];
+                const bool up = (i & k) == 0;
+                if ((x > y) == up) { a[i] = y; a[l] = x; }
+            }
+            grid.sync();
+        }
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t base = tile * BSORT_TILE;
+            sh[t] = a[base + t];
+            sh[t + 1024] = a[base + t + 1024];
+            __syncthreads();
+            const bool up = (base & k) == 0;   // k > BSORT_TILE: the direction is constant inside a tile
+            for (int j = BSORT_TILE / 2; j > 0; j >>= 1) {
+                const int lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+                const double x = sh[lo], y = sh[hi];
+                if ((x > y) == up) { sh[lo] = y; sh[hi] = x; }
+                __syncthreads();
+            }
+            a[base + t] = sh[t];
+            a[base + t + 1024] = sh[t + 1024];
+            __syncthreads();
+        }
+        grid.sync();
+    }
 }
 
 // ---- final per-site statistics -----------------------------------------------------------------------
@@ -291,15 +322,15 @@ int pbk_pvalues(pb_ctx* ctx) {
         ctx->d_maxT_sorted = (double*)ps; ctx->sorted_cap = cap / 8;
     }
     const int T = 256;
-    k4_sort_init_kernel<<<(unsigned)((n_pad + T - 1) / T), T, 0, st>>>(ctx->d_maxT, m, n_pad, ctx->d_maxT_sorted);
-    ctx->tm.n_launches += 1;
-    for (int64_t k = 2; k <= n_pad; k <<= 1) {
-        int64_t j = k >> 1;
-        for (; j >= BSORT_TILE / 2 * 2; j >>= 1) {  // strides that cross a 2048-element tile: global steps
-            k4_bitonic_step_kernel<<<(unsigned)((n_pad + T - 1) / T), T, 0, st>>>(ctx->d_maxT_sorted, n_pad, j, k);
-            ctx->tm.n_launches += 1;
-        }
-        k4_bitonic_smem_kernel<<<(unsigned)(n_pad / BSORT_TILE), 1024, 0, st>>>(ctx->d_maxT_sorted, k, j);
+    {
+        static int max_blocks_per_sm = -1;
+        if (max_blocks_per_sm < 0) PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, k4_sort_coop_kernel, 1024, 0));
+        int64_t grid = std::min<int64_t>(n_pad / BSORT_TILE, (int64_t)std::max(max_blocks_per_sm, 1) * ctx->sm_count);
+        const unsigned long long* a_maxT = ctx->d_maxT;
+        int64_t a_m = m, a_npad = n_pad;
+        double* a_out = ctx->d_maxT_sorted;
+        void* args[] = {(void*)&a_maxT, (void*)&a_m, (void*)&a_npad, (void*)&a_out};
+        PB_CUDA(cudaLaunchCooperativeKernel((const void*)k4_sort_coop_kernel, dim3((unsigned)grid), dim3(1024), args, 0, st));
         ctx->tm.n_launches += 1;
     }
     {

@@ -360,9 +360,11 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
     ctx->tm = pb_timings{};
     int rc;
     PB_CUDA(cudaEventRecord(ctx->ev[12], ctx->stream));
+    const bool pregen_early = getenv("PB_PREGEN_EARLY") != nullptr;
+    if (pregen_early && (rc = pbk_pregen_labels(ctx))) return rc;
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = pbk_events(ctx))) return rc;
-        if (attempt == 0 && (rc = pbk_pregen_labels(ctx))) return rc;
+        if (!pregen_early && attempt == 0 && (rc = pbk_pregen_labels(ctx))) return rc;
         unsigned long long cur = 0;
         PB_CUDA(cudaMemcpyAsync(&cur, ctx->d_raw_cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(cudaStreamSynchronize(ctx->stream));
