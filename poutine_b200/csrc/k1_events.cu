@@ -57,13 +57,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "K1_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra K1_WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // %2: suspend-time hint, the thread sleeps instead of spinning
+        "@!p bra K1_WAIT_%=;\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 // one 3-D tiled TMA load: box (128 words, 1 node, 3 planes) at (col0, node, 0) -> 3 KB in shared memory
 __device__ __forceinline__ void tma_load_row(uint32_t dst, const CUtensorMap* tmap, int32_t col0, int32_t node, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst), "l"(tmap), "r"(col0), "r"(node), "r"(0), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+// keeps a shared-window address in a register (stops the compiler from re-deriving it from the CTA id every use)
+__device__ __forceinline__ uint32_t pin_u32(uint32_t x) {
+    uint32_t y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
 }
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PB_K1_COLS) : "memory"); }
 
@@ -170,8 +181,8 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
     const int32_t col0 = (int32_t)blockIdx.x * PB_K1_COLS;
     const int r0 = p.chunk_op[chunk], r1 = p.chunk_op[chunk + 1];
     const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(p.ops);
-    const uint32_t ring0 = smem_u32(smem);
-    const uint32_t full0 = ring0 + K1_SMEM_RING + K1_SMEM_HI + K1_SMEM_QUEUE, empty0 = full0 + 8 * PB_K1_STAGES;
+    const uint32_t ring0 = pin_u32(smem_u32(smem));
+    const uint32_t full0 = pin_u32(ring0 + K1_SMEM_RING + K1_SMEM_HI + K1_SMEM_QUEUE), empty0 = full0 + 8 * PB_K1_STAGES;
 
     if (tid == 0) {
         s_count = 0;
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
     const int64_t w = (int64_t)col0 + tid;
     const bool edge_block = (int64_t)col0 + PB_K1_COLS >= p.W;          // block-uniform: holds word W-1 (TMA zero-fills beyond W)
     const uint32_t site_base = (uint32_t)(w * 64);
-    const unsigned char* my_ring = smem + tid * 8;
+    const uint32_t my_ring = pin_u32(ring0 + tid * 8);
 
     // leaf census, bit-sliced with deferred carries: level L holds a counter slice and the OR of the carries the
     // level below produced since its last update (two consecutive half-add carries are mutually exclusive:
@@ -226,17 +237,23 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
     for (int i = r0; i < r1; i++) {
         const uint4 rec = __ldg(recs + i);
         const bool ra = (rec.x & PB_OP_NODE_MASK) != PB_OP_NULL, rb = (rec.y & PB_OP_NODE_MASK) != PB_OP_NULL;
-        uint64_t av = 0, a0 = 0, a1 = 0, bv = 0, b0 = 0, b1 = 0;
+        uint64_t av, a0, a1, bv, b0, b1;
         if (ra | rb) {
             mbar_wait(full0 + boff, phase);                              // TMA bytes have landed
-            const uint64_t* src = reinterpret_cast<const uint64_t*>(my_ring + soff);
-            if (ra) { av = src[0]; a0 = src[PB_K1_COLS]; a1 = src[2 * PB_K1_COLS]; }
-            if (rb) { bv = src[3 * PB_K1_COLS]; b0 = src[4 * PB_K1_COLS]; b1 = src[5 * PB_K1_COLS]; }
+            const uint32_t src = my_ring + soff;
+            av = lds_u64(src); a0 = lds_u64(src + PB_K1_COLS * 8); a1 = lds_u64(src + 2 * PB_K1_COLS * 8);
+            bv = lds_u64(src + 3 * PB_K1_COLS * 8); b0 = lds_u64(src + 4 * PB_K1_COLS * 8); b1 = lds_u64(src + 5 * PB_K1_COLS * 8);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + boff);                   // stage is free again
             soff += K1_STAGE_BYTES; boff += 8;
             if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
             if (edge_block) { av &= edge_mask; bv &= edge_mask; }        // caller's padding bits of the last word never count
+            if (!(ra & rb)) {                                            // rare: a padding slot holds stale ring bytes
+                if (!ra) { av = 0; a0 = 0; a1 = 0; }
+                if (!rb) { bv = 0; b0 = 0; b1 = 0; }
+            }
+        } else {
+            av = a0 = a1 = bv = b0 = b1 = 0;
         }
         k1_row(rec.x, av, a0, a1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, s_queue, &s_count, p);
         k1_row(rec.y, bv, b0, b1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, s_queue, &s_count, p);
