@@ -444,16 +444,18 @@ static int ensure(pb_ctx* ctx, void** ptr, int64_t* cap, int64_t need_bytes) {
 }
 
 // replicate tiling of the label matrices + their buffers
-struct K3Plan { int64_t tile, Rw32, Rw; bool has_miss; };
+struct K3Plan { int64_t tile, Rw32, Rw; bool has_miss; int nbuf; int64_t buf_words; };
 
 static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
     const int64_t m = ctx->cfg.n_replicates;
     pl->has_miss = ctx->n_miss > 0;
-    // tile size: label matrices of one tile <= 512 MB by default (measured: K3b is insensitive to L2 residency,
-    // K3a wants as many replicates per launch as possible)
-    int64_t budget = 512ll << 20;
+    // tile size: K3b streams label-matrix rows from L2 (13 TB/s measured at C2), so a tile's matrices should stay
+    // L2-resident (126 MB L2): everything in one tile when that is <= 100 MB, else tiles of ~64 MB
+    const int64_t bytes_per_rep = ((int64_t)ctx->P * (pl->has_miss ? 2 : 1) + 7) / 8;
+    int64_t budget = (m * bytes_per_rep <= (100ll << 20)) ? (100ll << 20) : (64ll << 20);
     if (const char* e = getenv("PB_K3_TILE_MB")) budget = atoll(e) << 20;
-    int64_t tile = (budget * 8) / ((int64_t)ctx->P * (pl->has_miss ? 2 : 1));
+    if (const char* e = getenv("PB_K3_TILE_KB")) budget = atoll(e) << 10;   // test hook: forces many small tiles
+    int64_t tile = budget / bytes_per_rep;
     tile = (tile / 2048) * 2048;
     if (tile < 2048) tile = 2048;
     const int64_t m_pad = ((m + 255) / 256) * 256;
@@ -462,7 +464,10 @@ static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
     pl->Rw32 = ((tile + 255) / 256) * 8;  // uint32 pitch
     pl->Rw = pl->Rw32 / 2;
     int rc;
-    const int64_t need = (int64_t)ctx->P * pl->Rw * 8;
+    // two matrix buffers when the null is tiled: tile t+1 is generated on the second stream while tile t is counted
+    pl->nbuf = (m > tile && ctx->cfg.mode == PB_MODE_PHILOX && !getenv("PB_NO_PREGEN")) ? 2 : 1;
+    pl->buf_words = (int64_t)ctx->P * pl->Rw;
+    const int64_t need = pl->buf_words * 8 * pl->nbuf;
     void* pc = ctx->d_Xcase;
     if ((rc = ensure(ctx, &pc, &ctx->X_cap, need))) { ctx->d_Xcase = nullptr; return rc; }
     ctx->d_Xcase = (uint64_t*)pc;
@@ -474,14 +479,15 @@ static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
     return PB_OK;
 }
 
-static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t nr, cudaStream_t st) {
+static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t nr, cudaStream_t st, int buf) {
     const unsigned gblocks = (unsigned)((nr + GEN_THREADS - 1) / GEN_THREADS);
     if (pl.has_miss)
         k3_gen_kernel<0, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr,
-                                                               (uint32_t*)ctx->d_Xcase, (uint32_t*)ctx->d_Xmiss, pl.Rw32);
+                                                               (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words),
+                                                               (uint32_t*)(ctx->d_Xmiss + buf * pl.buf_words), pl.Rw32);
     else
         k3_gen_kernel<0, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr,
-                                                                (uint32_t*)ctx->d_Xcase, nullptr, pl.Rw32);
+                                                                (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words), nullptr, pl.Rw32);
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -501,7 +507,7 @@ int pbk_pregen_labels(pb_ctx* ctx) {
     const int64_t nr = m < pl.tile ? m : pl.tile;
     PB_CUDA(cudaEventRecord(ctx->ev_k1_done, ctx->stream));
     PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_k1_done, 0));
-    if ((rc = k3_launch_philox(ctx, pl, 0, nr, ctx->stream2))) return rc;
+    if ((rc = k3_launch_philox(ctx, pl, 0, nr, ctx->stream2, 0))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev_gen_done, ctx->stream2));
     ctx->pregen_valid = true;
     ctx->pregen_tile = pl.tile;
@@ -557,6 +563,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     for (int64_t base = 0; base < m; base += tile) {
         const int64_t nr = (m - base < tile) ? (m - base) : tile;
         const unsigned gblocks = (unsigned)((nr + GEN_THREADS - 1) / GEN_THREADS);
+        const int buf = (pl.nbuf == 2) ? (int)((base / tile) & 1) : 0;
         PB_CUDA(cudaEventRecord(ctx->ev[5], st));
         if (ctx->cfg.mode == PB_MODE_REPLAY) {
             const int64_t bytes = nr * (int64_t)ctx->P * 4;
@@ -574,15 +581,24 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             ctx->tm.n_launches += 1;
         } else if (base == 0 && ctx->pregen_valid && ctx->pregen_tile == tile) {
             PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_gen_done, 0));   // tile 0 was generated alongside the K1 tail
+        } else if (base > 0 && pl.nbuf == 2) {
+            PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_gen_b[buf], 0)); // generated on the second stream during the previous tile's count
         } else {
-            if ((rc = k3_launch_philox(ctx, pl, base, nr, st))) return rc;
+            if ((rc = k3_launch_philox(ctx, pl, base, nr, st, buf))) return rc;
+        }
+        if (pl.nbuf == 2 && base + tile < m) {
+            // next tile into the other buffer (its last reader, the count of tile t-1, has completed: the host
+            // synchronised on it below), concurrently with this tile's count
+            const int64_t nb = base + tile, nnr = (m - nb < tile) ? (m - nb) : tile;
+            if ((rc = k3_launch_philox(ctx, pl, nb, nnr, ctx->stream2, buf ^ 1))) return rc;
+            PB_CUDA(cudaEventRecord(ctx->ev_gen_b[buf ^ 1], ctx->stream2));
         }
         ctx->pregen_valid = false;
         PB_CUDA(cudaEventRecord(ctx->ev[6], st));
 
         K3Params p;
         p.alleles = ctx->d_alleles; p.n_slots = n_slots; p.csr = ctx->d_csr; p.pobs = ctx->d_pobs; p.ptable = ctx->d_ptable;
-        p.ktau = ctx->d_ktau; p.tau = ctx->d_tau; p.Xc = ctx->d_Xcase; p.Xm = has_miss ? ctx->d_Xmiss : nullptr; p.Rw = Rw;
+        p.ktau = ctx->d_ktau; p.tau = ctx->d_tau; p.Xc = ctx->d_Xcase + buf * pl.buf_words; p.Xm = has_miss ? ctx->d_Xmiss + buf * pl.buf_words : nullptr; p.Rw = Rw;
         p.rep_base = base; p.n_reps = nr; p.r = ctx->d_r; p.maxT = ctx->d_maxT;
         p.slots_per_chunk = 0;
         const int64_t nA = ctx->n_work[0], nB = ctx->n_work[1], nC = ctx->n_work[2];
@@ -590,7 +606,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
         int64_t bps = 16;
         if (const char* e = getenv("PB_K3_BLOCKS_PER_SM")) bps = atoll(e);
         if (nA > 0) {
-            k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(ctx->d_Xcase, Rw, words, ctx->d_colpop);
+            k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(p.Xc, Rw, words, ctx->d_colpop);
             k3_trivial_kernel<<<(unsigned)((nA + T - 1) / T), T, 0, st>>>(p, ctx->d_work, nA, ctx->d_colpop);
             ctx->tm.n_launches += 2;
         }

@@ -62,6 +62,7 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_k1_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_gen_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    for (auto& ev : ctx->ev_gen_b) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_raw_cursor, 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_class_counts, 16 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_fb_count, 4)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -78,6 +79,7 @@ extern "C" void pb_destroy(pb_ctx* ctx) {
     free_all(ctx);
     if (ctx->ev_k1_done) cudaEventDestroy(ctx->ev_k1_done);
     if (ctx->ev_gen_done) cudaEventDestroy(ctx->ev_gen_done);
+    for (auto& ev : ctx->ev_gen_b) if (ev) cudaEventDestroy(ev);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

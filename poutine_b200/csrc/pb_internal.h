@@ -66,7 +66,7 @@ struct pb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // label-matrix pre-generation (K3a) alongside the K1 tail
-    cudaEvent_t ev_k1_done = nullptr, ev_gen_done = nullptr;
+    cudaEvent_t ev_k1_done = nullptr, ev_gen_done = nullptr, ev_gen_b[2] = {nullptr, nullptr};
     bool pregen_valid = false; int64_t pregen_tile = 0;
     std::string err;
     int sm_count = 148;

@@ -212,6 +212,29 @@ def test_assoc_philox_bit_exact(oracle_mod, na_frac):
     np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), mt_u.view(np.uint64))
 
 
+@pytest.mark.parametrize("na_frac,replay", [(0.0, False), (0.03, False), (0.0, True)])
+def test_assoc_multi_tile(oracle_mod, monkeypatch, na_frac, replay):
+    """replicates split into several tiles (double-buffered label matrices generated on the second stream)"""
+    monkeypatch.setenv("PB_K3_TILE_KB", "16")
+    m = 7000                                          # 2048-replicate tiles -> 4 tiles, the last one partial
+    tree, o, hc, sn, lab = _assoc_case(oracle_mod, 150, 500, m, 91, na_frac, 0.0, seed=77, replay=replay)
+    if replay:
+        perms = oracle_mod.java_shuffle_perms(3, m, len(lab))
+        st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=perms, n_threads=4)
+        g_st, g_mt = hc.assoc(replay_perms=perms)
+    else:
+        st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=None, seed=77, n_threads=4)
+        g_st, g_mt = hc.assoc()
+    assert_stats_equal(g_st, st)
+    np.testing.assert_array_equal(g_mt.view(np.uint64), mt_s.view(np.uint64))
+    np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), mt_u.view(np.uint64))
+    # a second pass on the same context (pre-generated tile 0 from pb_run_events) gives the same answer
+    g_st, g_mt = g_st.copy(), g_mt.copy()             # results are views of reused page-locked buffers
+    hc.count_all_homoplasy_events()
+    g_st2, g_mt2 = hc.assoc(replay_perms=perms) if replay else hc.assoc()
+    assert g_st2.tobytes() == g_st.tobytes() and g_mt2.tobytes() == g_mt.tobytes()
+
+
 def test_assoc_nasty_inputs_replay(oracle_mod):
     m = 300
     tree, o, hc, sn, lab = _assoc_case(oracle_mod, 90, 700, m, 51, 0.05, 0.05, nasty=True, replay=True)
