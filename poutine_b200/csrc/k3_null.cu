@@ -177,7 +177,9 @@ __device__ __forceinline__ int extract(const uint64_t (&c)[NB], int b) {
 // The allele's sample rows are streamed (coalesced 256 B per row per step, L2-resident matrix),
 // r is accumulated in registers and written once — no atomics on r.
 template <int NB>
-__device__ __forceinline__ void sweep_allele(const K3Params& p, const AlleleMeta& m, int64_t slot, int lane, double tau) {
+__device__ __forceinline__ void sweep_allele(const K3Params& p, const AlleleMeta& m, int64_t slot, int lane, double tau, int w0 = -1,
+                                             int wstride = 32) {
+    // default: one warp owns the allele (lane = first word, stride 32, plain add); otherwise a thread block shares it
     constexpr int NREG = (NB <= 3) ? ((1 << NB) - 1) : 1;   // small lists live in registers
     const int n = m.n;
     const int32_t* __restrict__ ev = p.csr + m.off;
@@ -196,7 +198,7 @@ __device__ __forceinline__ void sweep_allele(const K3Params& p, const AlleleMeta
     const int tail = (int)(p.n_reps & 63);
     unsigned int rcount = 0;
 #pragma unroll 2
-    for (int64_t w = lane; w < words; w += 32) {
+    for (int64_t w = (w0 < 0 ? lane : w0); w < words; w += wstride) {
         const uint64_t valid = (w == words - 1 && tail) ? ((1ull << tail) - 1) : ~0ull;
         uint64_t c[NB], u[NB];
 #pragma unroll
@@ -257,7 +259,10 @@ __device__ __forceinline__ void sweep_allele(const K3Params& p, const AlleleMeta
         }
     }
     rcount = __reduce_add_sync(0xffffffffu, rcount);
-    if (lane == 0 && rcount) p.r[slot] += rcount;   // this warp is the slot's only writer in this launch
+    if (lane == 0 && rcount) {
+        if (w0 < 0) p.r[slot] += rcount;   // this warp is the slot's only writer in this launch
+        else atomicAdd(p.r + slot, rcount);
+    }
 }
 
 // ---- tight sweeps for the common case ---------------------------------------------------------------
@@ -311,6 +316,52 @@ __device__ __forceinline__ unsigned int sweep_upto7(const K3Params& p, const All
     return rc;
 }
 
+// missing labels in the pheno file, n <= 7: a replicate sees n_r = n - j labelled leaves (j = its missing draws
+// among the allele's samples) and counts when k_r >= k*_j.  Bit-sliced k (cases) and j (missing), one pass per j.
+template <int NB>
+__device__ __forceinline__ unsigned int sweep_miss(const K3Params& p, const AlleleMeta& m, int lane, int words) {
+    constexpr int NMAX = (1 << NB) - 1;
+    const int n = m.n;
+    const uint32_t kpack = m.kpack;
+    const uint64_t* __restrict__ rc_[NMAX];
+    const uint64_t* __restrict__ rm_[NMAX];
+#pragma unroll
+    for (int e = 0; e < NMAX; e++) {
+        const int64_t o = (int64_t)((e < n) ? __ldg(p.csr + m.off + e) : 0) * p.Rw + lane;
+        rc_[e] = p.Xc + o; rm_[e] = p.Xm + o;
+    }
+    const int tail = (int)(p.n_reps & 63);
+    unsigned int rc = 0;
+#pragma unroll 2
+    for (int w = lane, off = 0; w < words; w += 32, off += 32) {
+        uint64_t c[NB], u[NB];
+#pragma unroll
+        for (int j = 0; j < NB; j++) { c[j] = 0; u[j] = 0; }
+#pragma unroll
+        for (int e = 0; e < NMAX; e++) {
+            if (e < n) {
+                uint64_t x = __ldg(rc_[e] + off), y = __ldg(rm_[e] + off);
+#pragma unroll
+                for (int j = 0; j < NB; j++) { const uint64_t t = c[j] & x; c[j] ^= x; x = t; }
+#pragma unroll
+                for (int j = 0; j < NB; j++) { const uint64_t t = u[j] & y; u[j] ^= y; y = t; }
+            }
+        }
+        uint64_t acc = 0;
+        for (int j = 0; j <= n; j++) {                       // warp-uniform
+            const int kj = (int)((kpack >> (4 * j)) & 15u);  // k* for n_r = n - j
+            uint64_t eq = ~0ull;                             // (missing count == j)
+#pragma unroll
+            for (int b = 0; b < NB; b++) eq &= ((j >> b) & 1) ? u[b] : ~u[b];
+            const uint64_t ge = (kj <= 0) ? ~0ull : (kj > n - j ? 0ull : ge_const<NB>(c, kj));
+            acc |= eq & ge;
+        }
+        if (w == words - 1 && tail) acc &= (1ull << tail) - 1;   // padding replicates of the last word
+        rc += (unsigned int)__popcll(acc);
+    }
+    return rc;
+}
+
 #define K3_THREADS 256
 // work list B: alleles with 2 <= n < 8 (plus every small allele that needs the general path)
 __global__ void __launch_bounds__(K3_THREADS, 4) k3_count_small_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
@@ -323,8 +374,12 @@ __global__ void __launch_bounds__(K3_THREADS, 4) k3_count_small_kernel(const K3P
         const int64_t slot = list[i];
         const AlleleMeta m = p.alleles[slot];
         const int n = m.n, ks = m.kstar;
-        const bool tight = (m.flags & PB_AF_FAST) && p.Xm == nullptr && p.ktau[n] > n;
-        if (tight) {
+        const bool tight = (m.flags & PB_AF_TIGHT) != 0;
+        if (tight && p.Xm != nullptr) {
+            unsigned int rc = n < 2 ? sweep_miss<1>(p, m, lane, words) : n < 4 ? sweep_miss<2>(p, m, lane, words) : sweep_miss<3>(p, m, lane, words);
+            rc = __reduce_add_sync(0xffffffffu, rc);
+            if (lane == 0 && rc) p.r[slot] += rc;
+        } else if (tight) {
             unsigned int rc;
             if (ks <= 0) rc = (lane == 0) ? (unsigned int)p.n_reps : 0u;   // every replicate counts
             else if (ks > n) rc = 0;
@@ -343,43 +398,63 @@ __global__ void __launch_bounds__(K3_THREADS, 4) k3_count_small_kernel(const K3P
     }
 }
 
-// work list C: the long-list tail (n >= 8)
+// work list C: the long-list tail (n >= 8) and whatever needs the general path there.  These are few and long:
+// a whole thread block shares one allele (thread = word, stride 256) so that no single warp becomes the long pole.
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_count_large_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
     const int lane = threadIdx.x & 31;
-    const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
     const double tau = *p.tau;
-    for (int64_t i = gwarp; i < n_list; i += nwarps) {
+    for (int64_t i = blockIdx.x; i < n_list; i += gridDim.x) {
         const int64_t slot = list[i];
         const AlleleMeta m = p.alleles[slot];
         const int n = m.n;
-        if (n < 16) sweep_allele<4>(p, m, slot, lane, tau);
-        else if (n < 64) sweep_allele<6>(p, m, slot, lane, tau);
-        else if (n < 256) sweep_allele<8>(p, m, slot, lane, tau);
-        else if (n < 4096) sweep_allele<12>(p, m, slot, lane, tau);
-        else sweep_allele<17>(p, m, slot, lane, tau);
+        if (n < 16) sweep_allele<4>(p, m, slot, lane, tau, threadIdx.x, K3_THREADS);
+        else if (n < 64) sweep_allele<6>(p, m, slot, lane, tau, threadIdx.x, K3_THREADS);
+        else if (n < 256) sweep_allele<8>(p, m, slot, lane, tau, threadIdx.x, K3_THREADS);
+        else if (n < 4096) sweep_allele<12>(p, m, slot, lane, tau, threadIdx.x, K3_THREADS);
+        else sweep_allele<17>(p, m, slot, lane, tau, threadIdx.x, K3_THREADS);
     }
 }
 
 // work list A: n <= 1 alleles of the tight class need no sweep at all — the per-sample column popcount is shared
-__global__ void k3_colpop_kernel(const uint64_t* __restrict__ Xc, int64_t Rw, int64_t words, uint32_t* __restrict__ colpop) {
-    __shared__ unsigned int sh[4];
-    const uint64_t* row = Xc + (int64_t)blockIdx.x * Rw;
-    unsigned int c = 0;
-    for (int64_t w = threadIdx.x; w < words; w += blockDim.x) c += (unsigned int)__popcll(row[w]);
+__global__ void k3_colpop_kernel(const uint64_t* __restrict__ Xc, const uint64_t* __restrict__ Xm, int64_t Rw, int64_t words, int32_t P,
+                                 uint32_t* __restrict__ colpop /* [2][P]: cases, missing */) {
+    __shared__ unsigned int sh[2][4];
+    const uint64_t* rc = Xc + (int64_t)blockIdx.x * Rw;
+    const uint64_t* rm = Xm ? Xm + (int64_t)blockIdx.x * Rw : nullptr;
+    unsigned int c = 0, u = 0;
+    for (int64_t w = threadIdx.x; w < words; w += blockDim.x) {
+        c += (unsigned int)__popcll(rc[w]);
+        if (rm) u += (unsigned int)__popcll(rm[w]);
+    }
     c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    u = __reduce_add_sync(0xffffffffu, u);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = c; sh[1][threadIdx.x >> 5] = u; }
     __syncthreads();
-    if (threadIdx.x == 0) colpop[blockIdx.x] = sh[0] + sh[1] + sh[2] + sh[3];
+    if (threadIdx.x == 0) {
+        colpop[blockIdx.x] = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+        colpop[P + blockIdx.x] = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+    }
 }
-__global__ void k3_trivial_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list, const uint32_t* __restrict__ colpop) {
+__global__ void k3_trivial_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list, const uint32_t* __restrict__ colpop,
+                                  int32_t P) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_list) return;
     const int64_t slot = list[i];
     const AlleleMeta m = p.alleles[slot];
     unsigned int rc = 0;
-    if (m.kstar <= 0) rc = (unsigned int)p.n_reps;
-    else if (m.n == 1 && m.kstar == 1) rc = colpop[p.csr[m.off]];
+    if (p.Xm == nullptr) {
+        if (m.kstar <= 0) rc = (unsigned int)p.n_reps;
+        else if (m.n == 1 && m.kstar == 1) rc = colpop[p.csr[m.off]];
+    } else {
+        // missing labels (n <= 1): k*_0 for a labelled draw (n_r = n), k*_1 for a missing one (n_r = 0)
+        const int k0 = (int)(m.kpack & 15u), k1 = (int)((m.kpack >> 4) & 15u);
+        if (m.n == 0) rc = k0 <= 0 ? (unsigned int)p.n_reps : 0u;
+        else {
+            const int32_t s = p.csr[m.off];
+            const unsigned int pc = colpop[s], pm = colpop[P + s], pt = (unsigned int)p.n_reps - pc - pm;
+            rc = (k1 <= 0 ? pm : 0u) + (k0 <= 1 ? pc : 0u) + (k0 <= 0 ? pt : 0u);
+        }
+    }
     if (rc) p.r[slot] += rc;
 }
 
@@ -551,7 +626,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
         if (!ctx->d_colpop || ctx->colpop_cap < ctx->P) {
             if (ctx->d_colpop) cudaFree(ctx->d_colpop);
             ctx->d_colpop = nullptr;
-            PB_CUDA(cudaMalloc(&ctx->d_colpop, (size_t)ctx->P * 4));
+            PB_CUDA(cudaMalloc(&ctx->d_colpop, (size_t)ctx->P * 2 * 4));
             ctx->colpop_cap = ctx->P;
         }
         void* pl = ctx->d_fb_reps;
@@ -606,8 +681,8 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
         int64_t bps = 16;
         if (const char* e = getenv("PB_K3_BLOCKS_PER_SM")) bps = atoll(e);
         if (nA > 0) {
-            k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(p.Xc, Rw, words, ctx->d_colpop);
-            k3_trivial_kernel<<<(unsigned)((nA + T - 1) / T), T, 0, st>>>(p, ctx->d_work, nA, ctx->d_colpop);
+            k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(p.Xc, p.Xm, Rw, words, ctx->P, ctx->d_colpop);
+            k3_trivial_kernel<<<(unsigned)((nA + T - 1) / T), T, 0, st>>>(p, ctx->d_work, nA, ctx->d_colpop, ctx->P);
             ctx->tm.n_launches += 2;
         }
         if (nB > 0) {
@@ -616,7 +691,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             ctx->tm.n_launches += 1;
         }
         if (nC > 0) {
-            int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * 4, (nC + (K3_THREADS / 32) - 1) / (K3_THREADS / 32));
+            int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * 4, nC);
             k3_count_large_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + 2 * n_slots, nC);
             ctx->tm.n_launches += 1;
         }

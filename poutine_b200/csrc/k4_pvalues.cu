@@ -29,7 +29,7 @@ __global__ void k4_ptable_kernel(double* __restrict__ tab, int32_t n_max, double
 // ---- observed p-value, k* and the n-histogram -------------------------------------------------------
 #define OBS_SH 256
 __global__ void k4_observed_kernel(AlleleMeta* __restrict__ alleles, int64_t n_slots, const double* __restrict__ tab,
-                                   double* __restrict__ pobs, unsigned int* __restrict__ n_hist, int force_general,
+                                   double* __restrict__ pobs, unsigned int* __restrict__ n_hist, int force_general, int has_miss,
                                    unsigned long long* __restrict__ n_fast) {
     // block-local histogram of the common small n (global atomics only for the tail and once per block)
     __shared__ unsigned int s_hist[OBS_SH], s_fast;
@@ -55,8 +55,26 @@ __global__ void k4_observed_kernel(AlleleMeta* __restrict__ alleles, int64_t n_s
                 if (le && kstar > m.n) kstar = k;
                 if (!le && kstar <= m.n) upset = false;
             }
-            uint32_t fl = m.flags & ~PB_AF_FAST;
+            // missing labels: a replicate sees n_r = n - j labelled leaves; k*_j per j, packed (short lists only)
+            uint32_t kpack = 0;
+            bool upset_all = has_miss && m.n <= 7;
+            if (upset_all) {
+                    for (int j = 0; j <= m.n; j++) {
+                        const int nr = m.n - j;
+                        const double* rj = tab + (int64_t)nr * (nr + 1) / 2;
+                        int kj = nr + 1;
+                        for (int k = 0; k <= nr; k++) {
+                            const bool le = rj[k] <= po;
+                            if (le && kj > nr) kj = k;
+                            if (!le && kj <= nr) upset_all = false;
+                        }
+                        kpack |= (uint32_t)kj << (4 * j);
+                    }
+            }
+            alleles[a].kpack = kpack;
+            uint32_t fl = m.flags & ~(PB_AF_FAST | PB_AF_MISS_OK);
             if (upset && !force_general) { fl |= PB_AF_FAST; atomicAdd(&s_fast, 1u); }
+            if (upset_all && !force_general) fl |= PB_AF_MISS_OK;
             alleles[a].flags = fl;
             alleles[a].kstar = kstar;
         }
@@ -111,15 +129,23 @@ __global__ void k4_ktau_kernel(const double* __restrict__ tab, int32_t n_max, co
 }
 
 // ---- work lists for K3b: A = no sweep needed, B = short lists (n < 8), C = long lists -----------------
-__global__ void k4_classify_kernel(const AlleleMeta* __restrict__ alleles, int64_t n_slots, const int32_t* __restrict__ ktau, int has_miss,
+__global__ void k4_classify_kernel(AlleleMeta* __restrict__ alleles, int64_t n_slots, const int32_t* __restrict__ ktau, int has_miss,
                                    int32_t* __restrict__ lists, unsigned int* __restrict__ counts) {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int cls = -1;
     if (a < n_slots) {
         const AlleleMeta m = alleles[a];
         if (m.flags & PB_AF_IN_USE) {
-            const bool tight = (m.flags & PB_AF_FAST) && !has_miss && ktau[m.n] > m.n;
-            cls = (tight && (m.n <= 1 || m.kstar <= 0 || m.kstar > m.n)) ? 0 : (m.n < 8 ? 1 : 2);
+            // no maxT candidate possible: f(n',k) > tau for every k, for every n' a replicate can see
+            bool cand_free = ktau[m.n] > m.n;
+            if (has_miss) {
+                cand_free = m.n <= 7;
+                for (int n2 = 0; n2 <= m.n && cand_free; n2++) cand_free = ktau[n2] > n2;
+            }
+            const bool tight = ((m.flags & (has_miss ? PB_AF_MISS_OK : PB_AF_FAST)) != 0) && cand_free;
+            alleles[a].flags = (m.flags & ~PB_AF_TIGHT) | (tight ? PB_AF_TIGHT : 0u);
+            const bool no_sweep = tight && (has_miss ? m.n <= 1 : (m.n <= 1 || m.kstar <= 0 || m.kstar > m.n));
+            cls = no_sweep ? 0 : (m.n < 8 ? 1 : 2);
         }
     }
     const unsigned int lane = threadIdx.x & 31u;
@@ -286,7 +312,7 @@ int pbk_thresholds(pb_ctx* ctx) {
     const int T = 256;
     const int force_general = (ctx->cfg.flags & PB_FLAG_FORCE_GENERAL_NULL) ? 1 : 0;
     k4_observed_kernel<<<(unsigned)((n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ptable, ctx->d_pobs, d_hist,
-                                                                      force_general, d_nfast);
+                                                                      force_general, ctx->n_miss > 0 ? 1 : 0, d_nfast);
     k4_tau_expect_kernel<<<TAU_LEVELS, 256, 0, st>>>(ctx->d_ptable, d_hist, n_max, d_expect);
     k4_tau_pick_kernel<<<1, 1, 0, st>>>(d_expect, 16.0, ctx->cfg.maxt_tau, ctx->d_tau);
     k4_ktau_kernel<<<(unsigned)((n1 + T - 1) / T), T, 0, st>>>(ctx->d_ptable, n_max, ctx->d_tau, ctx->d_ktau);

@@ -50,7 +50,9 @@ typedef unsigned long long raw_event_t;
 
 // allele flags
 #define PB_AF_IN_USE 1u
-#define PB_AF_FAST 2u   // {k : f(n,k) <= p_obs} is an up-set and no missing labels: threshold path
+#define PB_AF_FAST 2u   // {k : f(n,k) <= p_obs} is an up-set: threshold path for replicates that see all n labels
+#define PB_AF_MISS_OK 8u // n <= 7 and every row f(n-j, .), j = 0..n, is an up-set w.r.t. p_obs: kpack is valid
+#define PB_AF_TIGHT 4u  // FAST and no replicate of this allele can be a maxT candidate: sweep without per-bit work
 
 struct AlleleMeta {      // one per allele slot (2 per informative site), 32 bytes
     int64_t off;         // CSR offset of its sample list
@@ -58,7 +60,7 @@ struct AlleleMeta {      // one per allele slot (2 per informative site), 32 byt
     uint32_t flags;
     int32_t kstar;       // min k with f(n,k) <= p_obs (fast path)
     int32_t obs_case, obs_ctrl;
-    int32_t pad;
+    uint32_t kpack;      // missing labels in the pheno file, n <= 7: k*_j for n_r = n - j, 4 bits each (j = 0..n)
 };
 
 struct pb_ctx {
@@ -134,7 +136,7 @@ struct pb_ctx {
     pb_stat_out* d_stats = nullptr; int64_t stats_cap = 0;
     int32_t* d_work = nullptr; int64_t work_cap = 0;   // 3 work lists of slot ids (classes A/B/C), n_slots each
     int64_t n_work[3] = {0, 0, 0};
-    uint32_t* d_colpop = nullptr; int64_t colpop_cap = 0;  // [P] per-sample case popcount of the current tile
+    uint32_t* d_colpop = nullptr; int64_t colpop_cap = 0;  // [2][P] per-sample case / missing-label popcounts of the current tile
     int32_t* d_fb_reps = nullptr;  // fallback replicate list
     unsigned int* d_fb_count = nullptr;
     bool assoc_done = false;
