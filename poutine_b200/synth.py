@@ -155,6 +155,22 @@ def random_tree(n_leaves: int, seed: int, polytomy: float = 0.2, root_leaf_child
     return _finish_tree(newp, rng)
 
 
+def caterpillar_tree(n_leaves: int, seed: int) -> Tree:
+    """Maximally unbalanced (ladder) topology: depth = number of leaves.  Stresses the iterative DFS of the
+    K1 schedule and the reference's O(L * depth) walks."""
+    rng = np.random.default_rng(seed)
+    parent = [-1]
+    spine = 0
+    for i in range(n_leaves - 1):
+        parent.append(spine)            # leaf hanging off the spine
+        if i < n_leaves - 2:
+            parent.append(spine)        # next spine node
+            spine = len(parent) - 1
+        else:
+            parent.append(spine)        # last two leaves share the deepest spine node
+    return _finish_tree(parent, rng)
+
+
 def topo_order(parent: np.ndarray) -> np.ndarray:
     """Nodes ordered so that every parent precedes its children."""
     n = len(parent)

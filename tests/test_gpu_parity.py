@@ -141,6 +141,30 @@ def test_events_many_chunks_and_site_offset(oracle_mod, monkeypatch):
         assert_events_equal(ev, cc, or_ev, or_cc)
 
 
+def test_events_caterpillar_tree(oracle_mod):
+    """ladder topology (depth = #leaves): every internal node is re-visited as the current parent"""
+    tree = synth.caterpillar_tree(400, 5)
+    S = 300
+    chars = synth.simulate_chars(tree, S, 6, nasty=True)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(chars)
+    hc, ev, cc = run_gpu_events(tree, chars=chars, num_replicates=10)
+    assert_events_equal(ev, cc, or_ev, or_cc)
+
+
+def test_events_census_segments(oracle_mod, monkeypatch):
+    """one chunk holding > 248 leaves: the census is flushed in several segments and re-summed"""
+    monkeypatch.setenv("PB_K1_CHUNKS", "1")
+    tree = synth.yule_tree(1100, 13)
+    S = 130
+    B0, B1, V = synth.simulate_planes(tree, S, 14, leaf_gap=True, multiallelic_frac=0.1)
+    chars = synth.planes_to_chars(B0, B1, V, 0, S)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(chars)
+    hc, ev, cc = run_gpu_events(tree, planes=(B0, B1, V), n_sites=S, num_replicates=10)
+    assert_events_equal(ev, cc, or_ev, or_cc)
+
+
 def test_events_dense_overflowing_queue(oracle_mod):
     """every edge an event at every site: shared queue overflow path + event-buffer regrow"""
     tree = synth.yule_tree(300, 21)
@@ -233,6 +257,32 @@ def test_assoc_multi_tile(oracle_mod, monkeypatch, na_frac, replay):
     hc.count_all_homoplasy_events()
     g_st2, g_mt2 = hc.assoc(replay_perms=perms) if replay else hc.assoc()
     assert g_st2.tobytes() == g_st.tobytes() and g_mt2.tobytes() == g_mt.tobytes()
+
+
+@pytest.mark.parametrize("na_frac", [0.0, 0.05])
+def test_assoc_long_event_lists(oracle_mod, na_frac):
+    """heavily homoplasic sites: alleles with n from 1 to > 64 extant events (every list-length class of K3b)"""
+    m = 400
+    tree = synth.yule_tree(700, 101)
+    S = 128
+    chars = synth.planes_to_chars(*synth.simulate_planes(tree, S, 102, mean_extra_mut=700.0), 0, S)
+    chars2 = synth.planes_to_chars(*synth.simulate_planes(tree, S, 103, mean_extra_mut=12.0), 0, S)
+    chars = np.ascontiguousarray(np.concatenate([chars, chars2], axis=1))
+    sn, lab = synth.simulate_phenotypes(tree, 104, na_frac=na_frac)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, _ = o.count_all_homoplasy_events(chars)
+    assert max(or_ev["a1_extant"].max(), or_ev["a2_extant"].max()) > 64
+    hc = pb.HomoplasyCounter(num_replicates=m, seed=5)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_seg_sites(chars)
+    ev, cc = hc.count_all_homoplasy_events()
+    for f in ("a1_count", "a2_count", "a1_extant", "a2_extant"):
+        np.testing.assert_array_equal(ev[f], or_ev[f], err_msg=f)
+    st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=None, seed=5, n_threads=4)
+    g_st, g_mt = hc.assoc()
+    assert_stats_equal(g_st, st)
+    np.testing.assert_array_equal(g_mt.view(np.uint64), mt_s.view(np.uint64))
 
 
 def test_assoc_nasty_inputs_replay(oracle_mod):
