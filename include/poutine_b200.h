@@ -169,6 +169,18 @@ int pb_comm_init(pb_ctx* ctx, const void* id128, int32_t rank, int32_t world);
  * Fasta_Record -> plane step of the host (HC.java:1252-1266). */
 int pb_pack_chars(const char* seq, int64_t n_nodes, int64_t n_sites, int64_t seq_pitch,
                   uint64_t* B0, uint64_t* B1, uint64_t* V, int64_t pitch_words);
+/* FASTA -> planes at speed (host side of HC.java:1241-1306; record semantics of compiled/Fasta_Manager.class next()):
+ * the file is mmap'ed and indexed once; pb_fasta_pack_tile packs the column tile [site_begin, site_begin+n_sites_tile)
+ * (site_begin % 64 == 0) of every record into row node_of_record[i] (-1 = skip) of tile-local planes, multi-threaded,
+ * so a host can pack tile t+1 while pb_put_planes uploads tile t.  Header text is returned trimmed, NOT NUL-terminated. */
+typedef struct pb_fasta pb_fasta;
+int pb_fasta_open(const char* path, pb_fasta** out);
+void pb_fasta_close(pb_fasta* f);
+int64_t pb_fasta_num_records(pb_fasta* f);
+int pb_fasta_record(pb_fasta* f, int64_t i, const char** name, int64_t* name_len, int64_t* seq_len);
+int pb_fasta_pack_tile(pb_fasta* f, const int32_t* node_of_record, int64_t site_begin, int64_t n_sites_tile,
+                       uint64_t* B0, uint64_t* B1, uint64_t* V, int64_t pitch_words, int32_t n_threads);
+const char* pb_fasta_last_error(void);
 /* Pinned host allocations for streaming uploads. */
 int pb_host_alloc(void** out, uint64_t bytes);
 int pb_host_free(void* p);

@@ -53,7 +53,8 @@ class PbTimings(C.Structure):
 EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_set_tree", "pb_set_labels", "pb_set_sites", "pb_put_planes",
            "pb_run_events", "pb_run_assoc", "pb_get_sites", "pb_get_raw_events", "pb_get_event_csr",
            "pb_get_maxT_unsorted", "pb_get_ptable", "pb_get_timings", "pb_stopwatch_mark", "pb_stopwatch_ms", "pb_comm_unique_id", "pb_comm_init",
-           "pb_pack_chars", "pb_host_alloc", "pb_host_free", "pb_version"]
+           "pb_pack_chars", "pb_host_alloc", "pb_host_free", "pb_version",
+           "pb_fasta_open", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_record", "pb_fasta_pack_tile", "pb_fasta_last_error"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -97,10 +98,16 @@ def lib():
         L.pb_comm_unique_id.argtypes = [vp]
         L.pb_comm_init.argtypes = [vp, vp, i32, i32]
         L.pb_pack_chars.argtypes = [vp, i64, i64, i64, vp, vp, vp, i64]
+        L.pb_fasta_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.pb_fasta_close.argtypes = [vp]; L.pb_fasta_close.restype = None
+        L.pb_fasta_num_records.argtypes = [vp]; L.pb_fasta_num_records.restype = i64
+        L.pb_fasta_record.argtypes = [vp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
+        L.pb_fasta_pack_tile.argtypes = [vp, vp, i64, i64, vp, vp, vp, i64, i32]
+        L.pb_fasta_last_error.argtypes = []; L.pb_fasta_last_error.restype = C.c_char_p
         L.pb_host_alloc.argtypes = [C.POINTER(vp), u64]
         L.pb_host_free.argtypes = [vp]
         for n in EXPORTS:
-            if n not in ("pb_destroy", "pb_last_error"):
+            if n not in ("pb_destroy", "pb_last_error", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_last_error"):
                 getattr(L, n).restype = C.c_int
         _LIB = L
     return _LIB

@@ -1,0 +1,234 @@
+// Host packer at speed: ancestral_sequences.fasta -> node-major bit planes, by column tile,
+// so that packing of tile t+1 overlaps the upload (pb_put_planes) and K1 of tile t.
+//
+// Record semantics follow the reference's reader (compiled/Fasta_Manager.class next(), used by build_seg_sites,
+// HC.java:1241-1306): a header line starts with '>', node name = header.substring(1).trim(); the sequence is the
+// concatenation of the following lines up to the next header or EOF, lines split the way BufferedReader.readLine
+// does ("\n", "\r\n" or "\r"), nothing else trimmed.  Characters are classified as in pb_pack_chars:
+// upper-case A/C/G/T are alleles, everything else is missing (HC.java:1600, 1845).
+//
+// The file is mmap'ed; records are indexed once (parallel-friendly, single pass); each record remembers its
+// first-line width so that site -> file offset is O(1) for regular FASTA (fixed line width or one line per
+// record); irregular records fall back to a per-record line table.
+#include <fcntl.h>
+#include <stdint.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/poutine_b200.h"
+
+struct FastaRecord {
+    int64_t name_off, name_len;   // trimmed header text
+    int64_t seq_off;              // file offset of the first sequence char
+    int64_t seq_len;              // chars after concatenating lines
+    int64_t line_w;               // chars per full line (regular layout), 0 = irregular -> `lines`
+    int64_t line_stride;          // bytes from one line start to the next (line_w + eol bytes)
+    std::vector<int64_t> lines;   // irregular only: (file offset, cumulative chars before) pairs
+};
+
+struct pb_fasta {
+    int fd = -1;
+    const char* data = nullptr;
+    int64_t size = 0;
+    std::vector<FastaRecord> recs;
+    std::string err;
+};
+
+static thread_local std::string g_fasta_err;
+
+static inline bool is_eol(char c) { return c == '\n' || c == '\r'; }
+
+static void index_records(pb_fasta* f) {
+    const char* d = f->data;
+    const int64_t n = f->size;
+    int64_t pos = 0;
+    // skip anything before the first header (Fasta_Manager expects the file to start with '>')
+    while (pos < n && d[pos] != '>') {
+        while (pos < n && !is_eol(d[pos])) pos++;
+        while (pos < n && is_eol(d[pos])) pos++;
+    }
+    while (pos < n) {
+        FastaRecord r{};
+        // header line
+        int64_t h0 = pos + 1, h1 = h0;
+        while (h1 < n && !is_eol(d[h1])) h1++;
+        int64_t a = h0, b = h1;
+        while (a < b && (unsigned char)d[a] <= ' ') a++;          // String.trim(): chars <= U+0020
+        while (b > a && (unsigned char)d[b - 1] <= ' ') b--;
+        r.name_off = a; r.name_len = b - a;
+        pos = h1;
+        if (pos < n && d[pos] == '\r') pos++;
+        if (pos < n && d[pos] == '\n') pos++;
+        r.seq_off = pos;
+        // sequence lines: (file offset, chars before) per readLine() line
+        int64_t total = 0;
+        std::vector<int64_t> lines;
+        while (pos < n && d[pos] != '>') {
+            const int64_t l0 = pos;
+            const char* nl = (const char*)memchr(d + pos, '\n', (size_t)(n - pos));
+            const int64_t l1 = nl ? (nl - d) : n;     // physical line end (exclusive of '\n')
+            int64_t e = l1;
+            if (e > l0 && d[e - 1] == '\r') e--;      // "\r\n"
+            int64_t s = l0;
+            for (;;) {                                 // a bare '\r' also ends a readLine() line
+                const char* cr = (const char*)memchr(d + s, '\r', (size_t)(e - s));
+                const int64_t se = cr ? (cr - d) : e;
+                lines.push_back(s); lines.push_back(total);
+                total += se - s;
+                if (!cr) break;
+                s = se + 1;
+            }
+            pos = nl ? l1 + 1 : n;
+        }
+        r.seq_len = total;
+        const int64_t n_lines = (int64_t)lines.size() / 2;
+        bool regular = n_lines > 0;
+        if (n_lines == 1) {
+            r.line_w = total > 0 ? total : 1; r.line_stride = r.line_w + 1;
+        } else if (n_lines > 1) {
+            const int64_t w0 = lines[3] - lines[1], st0 = lines[2] - lines[0];
+            for (int64_t i = 1; i < n_lines && regular; i++) {
+                const int64_t wi = ((i + 1 < n_lines) ? lines[2 * i + 3] : total) - lines[2 * i + 1];
+                if (lines[2 * i] - lines[2 * i - 2] != st0) regular = false;
+                if (i + 1 < n_lines ? wi != w0 : wi > w0) regular = false;
+            }
+            if (regular && w0 > 0) { r.line_w = w0; r.line_stride = st0; }
+            else { r.line_w = 0; r.lines = std::move(lines); }
+        } else {
+            r.line_w = 1; r.line_stride = 2;           // empty record
+        }
+        f->recs.push_back(std::move(r));
+    }
+}
+
+extern "C" const char* pb_fasta_last_error(void) { return g_fasta_err.c_str(); }
+
+extern "C" int pb_fasta_open(const char* path, pb_fasta** out) {
+    if (!path || !out) { g_fasta_err = "pb_fasta_open: null argument"; return PB_ERR_INVALID; }
+    *out = nullptr;
+    pb_fasta* f = new pb_fasta();
+    f->fd = open(path, O_RDONLY);
+    if (f->fd < 0) { g_fasta_err = std::string("pb_fasta_open: cannot open ") + path; delete f; return PB_ERR_INVALID; }
+    struct stat st;
+    if (fstat(f->fd, &st) != 0) { g_fasta_err = "pb_fasta_open: fstat failed"; close(f->fd); delete f; return PB_ERR_INVALID; }
+    f->size = (int64_t)st.st_size;
+    if (f->size > 0) {
+        void* p = mmap(nullptr, (size_t)f->size, PROT_READ, MAP_PRIVATE, f->fd, 0);
+        if (p == MAP_FAILED) { g_fasta_err = "pb_fasta_open: mmap failed"; close(f->fd); delete f; return PB_ERR_OOM; }
+        f->data = (const char*)p;
+        madvise(p, (size_t)f->size, MADV_WILLNEED);
+    }
+    index_records(f);
+    *out = f;
+    return PB_OK;
+}
+
+extern "C" void pb_fasta_close(pb_fasta* f) {
+    if (!f) return;
+    if (f->data) munmap((void*)f->data, (size_t)f->size);
+    if (f->fd >= 0) close(f->fd);
+    delete f;
+}
+
+extern "C" int64_t pb_fasta_num_records(pb_fasta* f) { return f ? (int64_t)f->recs.size() : -1; }
+
+extern "C" int pb_fasta_record(pb_fasta* f, int64_t i, const char** name, int64_t* name_len, int64_t* seq_len) {
+    if (!f || i < 0 || i >= (int64_t)f->recs.size()) return PB_ERR_INVALID;
+    const FastaRecord& r = f->recs[(size_t)i];
+    if (name) *name = f->data + r.name_off;
+    if (name_len) *name_len = r.name_len;
+    if (seq_len) *seq_len = r.seq_len;
+    return PB_OK;
+}
+
+// copy sites [s0, s1) of record r into buf (concatenated-line coordinates)
+static void gather_chars(const pb_fasta* f, const FastaRecord& r, int64_t s0, int64_t s1, unsigned char* buf) {
+    const char* d = f->data;
+    if (r.line_w > 0) {
+        int64_t s = s0;
+        while (s < s1) {
+            const int64_t line = s / r.line_w, col = s % r.line_w;
+            const int64_t take = std::min(r.line_w - col, s1 - s);
+            memcpy(buf + (s - s0), d + r.seq_off + line * r.line_stride + col, (size_t)take);
+            s += take;
+        }
+    } else {
+        // irregular: binary search the line table (pairs: offset, cumulative chars)
+        const int64_t nl = (int64_t)r.lines.size() / 2;
+        int64_t lo = 0, hi = nl - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (r.lines[2 * mid + 1] <= s0) lo = mid; else hi = mid - 1;
+        }
+        int64_t s = s0, li = lo;
+        while (s < s1 && li < nl) {
+            const int64_t cum = r.lines[2 * li + 1];
+            const int64_t next_cum = (li + 1 < nl) ? r.lines[2 * li + 3] : r.seq_len;
+            const int64_t col = s - cum, avail = next_cum - s;
+            const int64_t take = std::min(avail, s1 - s);
+            if (take > 0) memcpy(buf + (s - s0), d + r.lines[2 * li] + col, (size_t)take);
+            s += take;
+            li++;
+        }
+    }
+}
+
+static void pack_records(const pb_fasta* f, const int32_t* node_of_record, int64_t r0, int64_t r1, int64_t site_begin, int64_t n_sites_tile,
+                         uint64_t* B0, uint64_t* B1, uint64_t* V, int64_t pitch_words) {
+    uint8_t code[256];
+    memset(code, 0, sizeof(code));
+    code[(unsigned char)'A'] = 4 | 0; code[(unsigned char)'C'] = 4 | 1; code[(unsigned char)'G'] = 4 | 2; code[(unsigned char)'T'] = 4 | 3;
+    const int64_t W = (n_sites_tile + 63) / 64;
+    std::vector<unsigned char> buf((size_t)W * 64);
+    for (int64_t i = r0; i < r1; i++) {
+        const int32_t v = node_of_record[i];
+        if (v < 0) continue;
+        const FastaRecord& r = f->recs[(size_t)i];
+        const int64_t s0 = std::min(site_begin, r.seq_len), s1 = std::min(site_begin + n_sites_tile, r.seq_len);
+        memset(buf.data(), 0, buf.size());           // short records: the rest is "missing"
+        if (s1 > s0) gather_chars(f, r, s0, s1, buf.data());
+        uint64_t* b0 = B0 + (int64_t)v * pitch_words;
+        uint64_t* b1 = B1 + (int64_t)v * pitch_words;
+        uint64_t* vv = V + (int64_t)v * pitch_words;
+        for (int64_t w = 0; w < W; w++) {
+            const unsigned char* c = buf.data() + w * 64;
+            uint64_t x0 = 0, x1 = 0, xv = 0;
+            for (int j = 0; j < 64; j++) {
+                const uint64_t k = code[c[j]];
+                x0 |= (k & 1) << j;
+                x1 |= ((k >> 1) & 1) << j;
+                xv |= ((k >> 2) & 1) << j;
+            }
+            b0[w] = x0; b1[w] = x1; vv[w] = xv;
+        }
+    }
+}
+
+// Pack the column tile [site_begin, site_begin + n_sites_tile) (site_begin % 64 == 0) of every record into row
+// node_of_record[i] of the tile-local planes (row pitch pitch_words >= ceil(n_sites_tile / 64)).  Records mapped
+// to -1 are skipped; rows of nodes without a record are left untouched (the caller zero-fills).
+extern "C" int pb_fasta_pack_tile(pb_fasta* f, const int32_t* node_of_record, int64_t site_begin, int64_t n_sites_tile, uint64_t* B0,
+                                  uint64_t* B1, uint64_t* V, int64_t pitch_words, int32_t n_threads) {
+    if (!f || !node_of_record || !B0 || !B1 || !V || site_begin < 0 || (site_begin & 63) || n_sites_tile < 1 ||
+        pitch_words < (n_sites_tile + 63) / 64) {
+        g_fasta_err = "pb_fasta_pack_tile: invalid arguments";
+        return PB_ERR_INVALID;
+    }
+    const int64_t nrec = (int64_t)f->recs.size();
+    int64_t nt = n_threads > 0 ? n_threads : (int64_t)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > nrec) nt = nrec > 0 ? nrec : 1;
+    if (nt == 1) { pack_records(f, node_of_record, 0, nrec, site_begin, n_sites_tile, B0, B1, V, pitch_words); return PB_OK; }
+    std::vector<std::thread> th;
+    for (int64_t t = 0; t < nt; t++)
+        th.emplace_back(pack_records, f, node_of_record, nrec * t / nt, nrec * (t + 1) / nt, site_begin, n_sites_tile, B0, B1, V, pitch_words);
+    for (auto& t : th) t.join();
+    return PB_OK;
+}

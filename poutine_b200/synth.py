@@ -407,3 +407,45 @@ def make_config(name: str, n_sites: int | None = None, site_shard: tuple[int, in
                              third_allele_internal_frac=cfg.get("third_allele_internal_frac", 0.0))
     cfg["n_sites"] = S
     return tree, planes, sample_node, label, cfg
+
+
+def write_inputs(dirname: str, tree: Tree, chars: np.ndarray, sample_node, label, line_width: int = 0, eol: str = "\n",
+                 nexus: bool = False, seed: int = 0):
+    """The four files of `poutine.sh -u -f -t -p -m` (README of the reference): ancestral FASTA of ALL nodes (segregating
+    sites only), tree with internal labels (Newick, or treetime-style annotated nexus), 2-column pheno TSV, PLINK map.
+    -> dict of paths + physical positions."""
+    import os
+    rng = np.random.default_rng(seed)
+    os.makedirs(dirname, exist_ok=True)
+    N, S = chars.shape
+    paths = {k: os.path.join(dirname, v) for k, v in dict(fasta="ancestral_sequences.fasta", tree="ancestral_tree.newick",
+                                                           pheno="pheno.tsv", map="sites.map").items()}
+    order = rng.permutation(N)                        # record order is arbitrary in the reference (HashMap by name)
+    with open(paths["fasta"], "w", newline="") as f:
+        for v in order:
+            f.write(">" + tree.names[v] + eol)
+            seq = chars[v].tobytes().decode("latin-1")
+            if line_width > 0:
+                for i in range(0, S, line_width):
+                    f.write(seq[i:i + line_width] + eol)
+            else:
+                f.write(seq + eol)
+    nwk = tree.to_newick()
+    if nexus:
+        paths["tree"] = os.path.join(dirname, "annotated_tree.nexus")
+        import re
+        annotated = re.sub(r"(:[0-9.eE+-]+)", r'[&mutations="A1C"]\1', nwk, count=5)
+        with open(paths["tree"], "w") as f:
+            f.write("#NEXUS\nBegin Taxa;\n Dimensions NTax=%d;\nEnd;\nBegin Trees;\n Tree tree1=[&U]%s\nEnd;\n" % (tree.n_leaves, annotated))
+    else:
+        with open(paths["tree"], "w") as f:
+            f.write(nwk + "\n")
+    with open(paths["pheno"], "w") as f:
+        for v, l in zip(sample_node, label):
+            f.write("%s\t%s\n" % (tree.names[int(v)], "1" if l == 1 else "0" if l == 0 else "NA"))
+    pos = np.sort(rng.choice(np.arange(1, 50 * S + 2), size=S, replace=False)).astype(np.int64)
+    with open(paths["map"], "w") as f:
+        for i, p_ in enumerate(pos):
+            f.write("1\tsnp%d\t0\t%d\n" % (i + 1, p_))
+    paths["physical_pos"] = pos
+    return paths

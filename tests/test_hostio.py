@@ -1,0 +1,179 @@
+"""Host-side loaders / packer / writer: semantics of the reference's own readers, no GPU needed.
+The end-to-end files-in/files-out run is in the gpu section at the bottom."""
+import os
+
+import numpy as np
+import pytest
+
+import poutine_b200 as pb
+from poutine_b200 import hostio, synth
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    pb.build()
+
+
+# ---- Newick (coevolution.jar state machine) ----------------------------------------------------------------
+def _by_name(tree):
+    return {tree.names[v]: (tree.names[tree.parent[v]] if tree.parent[v] >= 0 else None) for v in range(tree.n_nodes)}
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_newick_roundtrip(seed):
+    t = synth.random_tree(40 + 10 * seed, seed, polytomy=0.3)
+    u = hostio.parse_newick(t.to_newick())
+    assert _by_name(u) == _by_name(t)
+    # leaves come out in left-to-right DFS order, as NewickTree.buildCaches lists them
+    assert [u.names[v] for v in u.leaf_nodes] == [t.names[v] for v in t.leaf_nodes]
+    assert u.parent[u.root] == -1 and u.names[u.root] == t.names[t.root]
+
+
+def test_newick_reader_quirks():
+    t = hostio.parse_newick(" ( A:0.1 ,\n B :2e-3)R ; trailing garbage")   # whitespace splits tokens; parsing stops at ';'
+    assert t.names == ["R", "A", "B"] and list(t.parent) == [-1, 0, 0]
+    assert t.branch_len[1] == pytest.approx(0.1, rel=1e-6) and t.branch_len[2] == pytest.approx(2e-3, rel=1e-6)
+    t = hostio.parse_newick("(A,,(B,C));")                # empty child between commas = unnamed node
+    assert t.names == [None, "A", None, None, "B", "C"]
+    for bad in ("(A,B", "(A,B));", "(A:x,B);", "((A,B);", "(A,B)"):   # the last one: "Unexpected end of data."
+        with pytest.raises(hostio.DataFormatError):
+            hostio.parse_newick(bad)
+
+
+def test_nexus_to_newick(tmp_path):
+    t = synth.yule_tree(12, 3)
+    chars = synth.simulate_chars(t, 5, 1, nasty=False)
+    sn, lab = synth.simulate_phenotypes(t, 2)
+    paths = synth.write_inputs(str(tmp_path), t, chars, sn, lab, nexus=True)
+    nwk = hostio.nexus_to_newick(paths["tree"])
+    assert nwk.startswith("(") and "[" not in nwk and "]" not in nwk
+    assert _by_name(hostio.parse_newick(nwk)) == _by_name(t)
+
+
+# ---- pheno / map ---------------------------------------------------------------------------------------------
+def test_pheno_and_map_readers(tmp_path):
+    p = tmp_path / "ph.tsv"
+    p.write_text("s1\t1\ns2\t0\ns3\tNA\ns1\t0\n")          # repeated id: HashMap.put keeps the last
+    ph = hostio.read_phenos(str(p))
+    assert ph == {"s1": "0", "s2": "0", "s3": "NA"}
+    m = tmp_path / "a.map"
+    m.write_text("1\tx\t0\t100\n1\ty\t250\n")               # last column, any number of columns
+    assert list(hostio.read_map(str(m))) == [100, 250]
+
+
+# ---- FASTA packer ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("line_width,eol", [(0, "\n"), (60, "\n"), (7, "\r\n"), (64, "\n"), (1, "\n")])
+def test_fasta_pack_matches_char_packer(tmp_path, line_width, eol):
+    t = synth.yule_tree(30, 5)
+    S = 64 * 5 + 13
+    chars = synth.simulate_chars(t, S, 6, nasty=True)
+    sn, lab = synth.simulate_phenotypes(t, 7)
+    paths = synth.write_inputs(str(tmp_path), t, chars, sn, lab, line_width=line_width, eol=eol, seed=3)
+    fa = hostio.FastaFile(paths["fasta"])
+    assert sorted(fa.names) == sorted(t.names) and np.all(fa.lengths == S)
+    node_of = {n: v for v, n in enumerate(t.names)}
+    nor = np.array([node_of[n] for n in fa.names], dtype=np.int32)
+    R0, R1, RV = pb.pack_chars(chars)
+    W = (S + 63) // 64
+    # whole alignment in one tile, then in 2-word tiles written into a wider buffer (pitch != tile width)
+    B0, B1, V = (np.zeros((t.n_nodes, W), dtype=np.uint64) for _ in range(3))
+    fa.pack_tile(nor, 0, S, B0, B1, V, 3)
+    for a, b in ((B0, R0), (B1, R1), (V, RV)):
+        np.testing.assert_array_equal(a, b)
+    T0, T1, TV = (np.zeros((t.n_nodes, W), dtype=np.uint64) for _ in range(3))
+    for w0 in range(0, W, 2):
+        nw = min(2, W - w0)
+        ns = min(S - 64 * w0, 64 * nw)
+        fa.pack_tile(nor, 64 * w0, ns, T0[:, w0:w0 + nw], T1[:, w0:w0 + nw], TV[:, w0:w0 + nw], 1)
+    for a, b in ((T0, R0), (T1, R1), (TV, RV)):
+        np.testing.assert_array_equal(a, b)
+    fa.close()
+
+
+def test_fasta_reader_semantics(tmp_path):
+    p = tmp_path / "x.fa"
+    # header trimmed (String.trim), ragged line widths, bare CR as a line break, record without trailing newline
+    p.write_bytes(b">  n1 extra words \nACG\nT\nAC\n>n2\rAC\rGTAC\n>n3\nacgtN-AC")
+    fa = hostio.FastaFile(str(p))
+    assert fa.names == ["n1 extra words", "n2", "n3"]
+    assert list(fa.lengths) == [6, 6, 8]
+    B0, B1, V = (np.zeros((3, 1), dtype=np.uint64) for _ in range(3))
+    fa.pack_tile(np.array([2, 0, 1], dtype=np.int32), 0, 8, B0, B1, V, 1)
+    back = synth.planes_to_chars(B0, B1, V, 0, 8)
+    assert back[2].tobytes() == b"ACGTACNN"        # n1: "ACGTAC", the tail is missing
+    assert back[0].tobytes() == b"ACGTACNN"        # n2
+    assert back[1].tobytes() == b"NNNNNNAC"        # n3: lower case / N / '-' are missing (HC.java:1600)
+    fa.close()
+
+
+# ---- writer -----------------------------------------------------------------------------------------------------
+def test_java_double_to_string():
+    j = hostio.java_double_str
+    cases = {1.0: "1.0", 0.5: "0.5", 0.001: "0.001", 0.00099: "9.9E-4", 1e7: "1.0E7", 9999999.0: "9999999.0", 1e-5: "1.0E-5",
+             9.99990000099999e-06: "9.99990000099999E-6", 1.0 / 3: "0.3333333333333333", 2.0 ** -53: "1.1102230246251565E-16",
+             float("nan"): "NaN", 0.0: "0.0", 12345678.0: "1.2345678E7", 3.0 / 100001: "2.999970000299997E-5"}
+    for x, s in cases.items():
+        assert j(x) == s, (x, j(x), s)
+
+
+def test_write_outputs_format_and_sorts(tmp_path):
+    from poutine_b200._lib import SITE_DTYPE, STAT_DTYPE
+    sites = np.zeros(6, dtype=SITE_DTYPE)
+    sites["segsite_id"] = np.arange(1, 7)
+    sites["site_class"] = 2
+    sites["allele1"], sites["allele2"] = ord("A"), ord("G")
+    sites["a1_count"], sites["a2_count"], sites["a1_extant"], sites["a2_extant"] = 0, 3, 0, 2
+    st = np.zeros(4, dtype=STAT_DTYPE)
+    st["site_index"] = [0, 2, 3, 5]
+    st["segsite_id"] = [1, 3, 4, 6]
+    nan = float("nan")
+    st["r_a1"], st["r_maxT_a1"] = [-1, 5, -1, 7], [-1, 50, -1, 50]
+    st["pointwise_a1"], st["obs_p_a1"] = [nan, 0.06, nan, 0.08], [nan, 0.01, nan, 0.02]
+    st["familywise_a1"] = [nan, 0.5, nan, 0.5]                      # a tie: order must follow the a2-sorted array (stable)
+    st["r_a2"], st["r_maxT_a2"] = [3, 0, 9, 1], [30, 0, 90, 10]
+    st["pointwise_a2"], st["obs_p_a2"] = [0.04, 1e-5, 0.1, 0.02], [0.001, 1e-7, 0.05, 0.004]
+    st["familywise_a2"] = [0.3, 9.99990000099999e-06, 0.9, 0.1]
+    st["obs_counts"] = [[0, 0, 2, 0], [1, 1, 2, 1], [0, 0, 1, 1], [2, 0, 3, 0]]
+    out = str(tmp_path / "res.out")
+    hostio.write_outputs(out, sites, st, np.arange(6) * 10 + 5)
+    lines = open(out).read().splitlines()
+    assert lines[0] == hostio.EVENT_COLS + "\t" + hostio.STAT_COLS
+    assert lines[1] == "1\t5\tA\tG\t0\t3\t0\t2\t[0, 0, 2, 0]\t-1\t3\tNaN\t0.04\tNaN\t0.001\t-1\t30\tNaN\t0.3"
+    assert lines[2].endswith("\t5\t0\t0.06\t1.0E-5\t0.01\t1.0E-7\t50\t0\t0.5\t9.99990000099999E-6")
+    a2 = [l.split("\t")[0] for l in open(out + ".sorted_by_a2_maxT").read().splitlines()[1:]]
+    assert a2 == ["3", "6", "1", "4"]
+    a1 = [l.split("\t")[0] for l in open(out + ".sorted_by_a1_maxT").read().splitlines()[1:]]
+    assert a1 == ["3", "6"]                                        # NaN rows dropped; tie keeps the a2 order
+
+
+# ---- files in, files out (GPU) ----------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("nexus,line_width", [(False, 0), (True, 70)])
+def test_run_homoplasy_counter_matches_oracle(tmp_path, oracle_mod, nexus, line_width):
+    t = synth.yule_tree(200, 11)
+    S = 64 * 40 + 9
+    chars = synth.planes_to_chars(*synth.simulate_planes(t, S, 12, leaf_gap=True, multiallelic_frac=0.05), 0, S)
+    sn, lab = synth.simulate_phenotypes(t, 13, na_frac=0.03, no_row_frac=0.02)
+    paths = synth.write_inputs(str(tmp_path), t, chars, sn, lab, line_width=line_width, nexus=nexus, seed=5)
+    out = str(tmp_path / "run.out")
+    m = 800
+    res = hostio.run_homoplasy_counter(paths["fasta"], paths["tree"], paths["pheno"], paths["map"], out, num_replicates=m, seed=21,
+                                       tile_sites=640)
+    # the oracle on the same inputs (node numbering of the parsed tree differs; results are per site)
+    o = oracle_mod.Oracle(t.parent, t.leaf_nodes)
+    ev, cc = o.count_all_homoplasy_events(chars, paths["physical_pos"].astype(np.int32))
+    st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=None, seed=21, n_threads=4)
+    assert res["counts"]["bi"] == cc["bi"] and res["n_informative"] == len(st)
+    from poutine_b200._lib import SITE_DTYPE, STAT_DTYPE
+    sites = np.zeros(S, dtype=SITE_DTYPE)
+    for f in ("segsite_id", "allele1", "allele2", "a1_count", "a2_count", "a1_extant", "a2_extant"):
+        sites[f][ev["segsite_id"] - 1] = ev[f]
+    gst = np.zeros(len(st), dtype=STAT_DTYPE)
+    for f in STAT_DTYPE.names:
+        if f != "site_index":
+            gst[f] = st[f]
+    gst["site_index"] = st["segsite_id"] - 1
+    ref_out = str(tmp_path / "oracle.out")
+    hostio.write_outputs(ref_out, sites, gst, paths["physical_pos"])
+    for suffix in ("", ".sorted_by_a2_maxT", ".sorted_by_a1_maxT"):
+        assert open(out + suffix).read() == open(ref_out + suffix).read(), suffix
