@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/poutine_b200.h"
+#include "pack_simd.h"
 
 struct FastaRecord {
     int64_t name_off, name_len;   // trimmed header text
@@ -182,9 +183,7 @@ static void gather_chars(const pb_fasta* f, const FastaRecord& r, int64_t s0, in
 
 static void pack_records(const pb_fasta* f, const int32_t* node_of_record, int64_t r0, int64_t r1, int64_t site_begin, int64_t n_sites_tile,
                          uint64_t* B0, uint64_t* B1, uint64_t* V, int64_t pitch_words) {
-    uint8_t code[256];
-    memset(code, 0, sizeof(code));
-    code[(unsigned char)'A'] = 4 | 0; code[(unsigned char)'C'] = 4 | 1; code[(unsigned char)'G'] = 4 | 2; code[(unsigned char)'T'] = 4 | 3;
+    const pb_pack64_fn pack64 = pb_pack64_select();
     const int64_t W = (n_sites_tile + 63) / 64;
     std::vector<unsigned char> buf((size_t)W * 64);
     for (int64_t i = r0; i < r1; i++) {
@@ -197,17 +196,7 @@ static void pack_records(const pb_fasta* f, const int32_t* node_of_record, int64
         uint64_t* b0 = B0 + (int64_t)v * pitch_words;
         uint64_t* b1 = B1 + (int64_t)v * pitch_words;
         uint64_t* vv = V + (int64_t)v * pitch_words;
-        for (int64_t w = 0; w < W; w++) {
-            const unsigned char* c = buf.data() + w * 64;
-            uint64_t x0 = 0, x1 = 0, xv = 0;
-            for (int j = 0; j < 64; j++) {
-                const uint64_t k = code[c[j]];
-                x0 |= (k & 1) << j;
-                x1 |= ((k >> 1) & 1) << j;
-                xv |= ((k >> 2) & 1) << j;
-            }
-            b0[w] = x0; b1[w] = x1; vv[w] = xv;
-        }
+        for (int64_t w = 0; w < W; w++) pack64(buf.data() + w * 64, b0 + w, b1 + w, vv + w);
     }
 }
 

@@ -12,13 +12,11 @@
 #include <vector>
 
 #include "../../include/poutine_b200.h"
+#include "pack_simd.h"
 
 static void pack_rows(const char* seq, int64_t v0, int64_t v1, int64_t n_sites, int64_t seq_pitch, uint64_t* B0, uint64_t* B1,
                       uint64_t* V, int64_t pitch_words) {
-    // code table: bit0 = B0, bit1 = B1, bit2 = valid
-    uint8_t code[256];
-    memset(code, 0, sizeof(code));
-    code[(unsigned char)'A'] = 4 | 0; code[(unsigned char)'C'] = 4 | 1; code[(unsigned char)'G'] = 4 | 2; code[(unsigned char)'T'] = 4 | 3;
+    const pb_pack64_fn pack64 = pb_pack64_select();
     const int64_t W = (n_sites + 63) / 64;
     for (int64_t v = v0; v < v1; v++) {
         const unsigned char* row = (const unsigned char*)seq + v * seq_pitch;
@@ -27,15 +25,11 @@ static void pack_rows(const char* seq, int64_t v0, int64_t v1, int64_t n_sites, 
         uint64_t* vv = V + v * pitch_words;
         for (int64_t w = 0; w < W; w++) {
             const int64_t s0 = w * 64;
-            const int n = (int)((n_sites - s0 < 64) ? (n_sites - s0) : 64);
-            uint64_t x0 = 0, x1 = 0, xv = 0;
-            for (int j = 0; j < n; j++) {
-                const uint64_t c = code[row[s0 + j]];
-                x0 |= (c & 1) << j;
-                x1 |= ((c >> 1) & 1) << j;
-                xv |= ((c >> 2) & 1) << j;
-            }
-            b0[w] = x0; b1[w] = x1; vv[w] = xv;
+            if (n_sites - s0 >= 64) { pack64(row + s0, b0 + w, b1 + w, vv + w); continue; }
+            unsigned char tail[64];
+            memset(tail, 0, sizeof(tail));                 // padding sites are "missing": V = 0
+            memcpy(tail, row + s0, (size_t)(n_sites - s0));
+            pack64(tail, b0 + w, b1 + w, vv + w);
         }
         for (int64_t w = W; w < pitch_words; w++) { b0[w] = 0; b1[w] = 0; vv[w] = 0; }
     }
