@@ -519,7 +519,7 @@ static int ensure(pb_ctx* ctx, void** ptr, int64_t* cap, int64_t need_bytes) {
 }
 
 // replicate tiling of the label matrices + their buffers
-struct K3Plan { int64_t tile, Rw32, Rw; bool has_miss; int nbuf; int64_t buf_words; };
+struct K3Plan { int64_t tile, ctile, Rw32, Rw; bool has_miss; int nbuf; int64_t buf_words; };  // tile = generation tile, ctile = count tile
 
 static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
     const int64_t m = ctx->cfg.n_replicates;
@@ -530,10 +530,19 @@ static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
     int64_t budget = (m * bytes_per_rep <= (100ll << 20)) ? (100ll << 20) : (64ll << 20);
     if (const char* e = getenv("PB_K3_TILE_MB")) budget = atoll(e) << 20;
     if (const char* e = getenv("PB_K3_TILE_KB")) budget = atoll(e) << 10;   // test hook: forces many small tiles
-    int64_t tile = budget / bytes_per_rep;
-    tile = (tile / 2048) * 2048;
-    if (tile < 2048) tile = 2048;
+    int64_t ctile = budget / bytes_per_rep;
+    ctile = (ctile / 2048) * 2048;
+    if (ctile < 2048) ctile = 2048;
     const int64_t m_pad = ((m + 255) / 256) * 256;
+    if (ctile > m_pad) ctile = m_pad;
+    pl->ctile = ctile;
+    // generation tile: K3a is one thread per replicate with P sequential draws, so it wants as many replicates per
+    // launch as memory allows (<= 2 GB per matrix by default), a whole number of count tiles
+    int64_t gen_budget = 2048ll << 20;
+    if (const char* e = getenv("PB_K3_GEN_MB")) gen_budget = atoll(e) << 20;
+    if (const char* e = getenv("PB_K3_GEN_KB")) gen_budget = atoll(e) << 10;   // test hook
+    int64_t tile = (gen_budget / bytes_per_rep / ctile) * ctile;
+    if (tile < ctile) tile = ctile;
     if (tile > m_pad) tile = m_pad;
     pl->tile = tile;
     pl->Rw32 = ((tile + 255) / 256) * 8;  // uint32 pitch
@@ -671,51 +680,58 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
         ctx->pregen_valid = false;
         PB_CUDA(cudaEventRecord(ctx->ev[6], st));
 
-        K3Params p;
-        p.alleles = ctx->d_alleles; p.n_slots = n_slots; p.csr = ctx->d_csr; p.pobs = ctx->d_pobs; p.ptable = ctx->d_ptable;
-        p.ktau = ctx->d_ktau; p.tau = ctx->d_tau; p.Xc = ctx->d_Xcase + buf * pl.buf_words; p.Xm = has_miss ? ctx->d_Xmiss + buf * pl.buf_words : nullptr; p.Rw = Rw;
-        p.rep_base = base; p.n_reps = nr; p.r = ctx->d_r; p.maxT = ctx->d_maxT;
-        p.slots_per_chunk = 0;
-        const int64_t nA = ctx->n_work[0], nB = ctx->n_work[1], nC = ctx->n_work[2];
-        const int64_t words = (nr + 63) / 64;
-        int64_t bps = 16;
-        if (const char* e = getenv("PB_K3_BLOCKS_PER_SM")) bps = atoll(e);
-        if (nA > 0) {
-            k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(p.Xc, p.Xm, Rw, words, ctx->P, ctx->d_colpop);
-            k3_trivial_kernel<<<(unsigned)((nA + T - 1) / T), T, 0, st>>>(p, ctx->d_work, nA, ctx->d_colpop, ctx->P);
-            ctx->tm.n_launches += 2;
-        }
-        if (nB > 0) {
-            int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * bps, (nB + (K3_THREADS / 32) - 1) / (K3_THREADS / 32));
-            k3_count_small_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, nB);
+        // count in L2-sized column tiles of the generated matrix
+        for (int64_t cb = 0; cb < nr; cb += pl.ctile) {
+            const int64_t cnr = (nr - cb < pl.ctile) ? (nr - cb) : pl.ctile;
+            K3Params p;
+            p.alleles = ctx->d_alleles; p.n_slots = n_slots; p.csr = ctx->d_csr; p.pobs = ctx->d_pobs; p.ptable = ctx->d_ptable;
+            p.ktau = ctx->d_ktau; p.tau = ctx->d_tau;
+            p.Xc = ctx->d_Xcase + buf * pl.buf_words + cb / 64;
+            p.Xm = has_miss ? ctx->d_Xmiss + buf * pl.buf_words + cb / 64 : nullptr;
+            p.Rw = Rw;
+            p.rep_base = base + cb; p.n_reps = cnr; p.r = ctx->d_r; p.maxT = ctx->d_maxT;
+            p.slots_per_chunk = 0;
+            const int64_t nA = ctx->n_work[0], nB = ctx->n_work[1], nC = ctx->n_work[2];
+            const int64_t words = (cnr + 63) / 64;
+            int64_t bps = 16;
+            if (const char* e = getenv("PB_K3_BLOCKS_PER_SM")) bps = atoll(e);
+            if (nA > 0) {
+                k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(p.Xc, p.Xm, Rw, words, ctx->P, ctx->d_colpop);
+                k3_trivial_kernel<<<(unsigned)((nA + T - 1) / T), T, 0, st>>>(p, ctx->d_work, nA, ctx->d_colpop, ctx->P);
+                ctx->tm.n_launches += 2;
+            }
+            if (nB > 0) {
+                int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * bps, (nB + (K3_THREADS / 32) - 1) / (K3_THREADS / 32));
+                k3_count_small_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, nB);
+                ctx->tm.n_launches += 1;
+            }
+            if (nC > 0) {
+                int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * 4, nC);
+                k3_count_large_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + 2 * n_slots, nC);
+                ctx->tm.n_launches += 1;
+            }
+            // fallback for uncertified replicates
+            PB_CUDA(cudaMemsetAsync(ctx->d_fb_count, 0, 4, st));
+            k3_collect_fallback_kernel<<<(unsigned)((cnr + T - 1) / T), T, 0, st>>>(ctx->d_maxT, p.rep_base, cnr, ctx->d_tau, ctx->d_fb_reps,
+                                                                                 ctx->d_fb_count);
             ctx->tm.n_launches += 1;
-        }
-        if (nC > 0) {
-            int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * 4, nC);
-            k3_count_large_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + 2 * n_slots, nC);
-            ctx->tm.n_launches += 1;
+            unsigned int n_fb = 0;
+            PB_CUDA(cudaMemcpyAsync(&n_fb, ctx->d_fb_count, 4, cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaStreamSynchronize(st));
+            if (n_fb) {
+                k3_fallback_kernel<<<n_fb, 256, 0, st>>>(p, ctx->d_fb_reps);
+                ctx->tm.n_launches += 1;
+                ctx->tm.n_maxt_fallback_reps += n_fb;
+            }
         }
         PB_CUDA(cudaEventRecord(ctx->ev[7], st));
-
-        // fallback for uncertified replicates
-        PB_CUDA(cudaMemsetAsync(ctx->d_fb_count, 0, 4, st));
-        k3_collect_fallback_kernel<<<(unsigned)((nr + T - 1) / T), T, 0, st>>>(ctx->d_maxT, base, nr, ctx->d_tau, ctx->d_fb_reps, ctx->d_fb_count);
-        ctx->tm.n_launches += 1;
-        unsigned int n_fb = 0;
-        PB_CUDA(cudaMemcpyAsync(&n_fb, ctx->d_fb_count, 4, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaStreamSynchronize(st));
-        if (n_fb) {
-            k3_fallback_kernel<<<n_fb, 256, 0, st>>>(p, ctx->d_fb_reps);
-            ctx->tm.n_launches += 1;
-            ctx->tm.n_maxt_fallback_reps += n_fb;
-        }
         PB_CUDA(cudaEventRecord(ctx->ev[8], st));
         PB_CUDA(cudaStreamSynchronize(st));
         PB_CUDA(cudaGetLastError());
         float t;
         cudaEventElapsedTime(&t, ctx->ev[5], ctx->ev[6]); ms_gen += t;
         cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]); ms_cnt += t;
-        cudaEventElapsedTime(&t, ctx->ev[7], ctx->ev[8]); ms_fb += t;
+        cudaEventElapsedTime(&t, ctx->ev[7], ctx->ev[8]); ms_fb += t;   // (the fallback pass now runs inside the count tiles)
     }
     ctx->tm.ms_null_gen = ms_gen; ctx->tm.ms_null_count = ms_cnt; ctx->tm.ms_null_fallback = ms_fb;
 

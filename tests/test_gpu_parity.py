@@ -236,10 +236,13 @@ def test_assoc_philox_bit_exact(oracle_mod, na_frac):
     np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), mt_u.view(np.uint64))
 
 
-@pytest.mark.parametrize("na_frac,replay", [(0.0, False), (0.03, False), (0.0, True)])
-def test_assoc_multi_tile(oracle_mod, monkeypatch, na_frac, replay):
-    """replicates split into several tiles (double-buffered label matrices generated on the second stream)"""
+@pytest.mark.parametrize("na_frac,replay,gen_kb", [(0.0, False, None), (0.03, False, "128"), (0.0, True, "128"), (0.0, False, "16")])
+def test_assoc_multi_tile(oracle_mod, monkeypatch, na_frac, replay, gen_kb):
+    """replicates split into several generation tiles (double-buffered on the second stream), each counted in
+    several L2-sized column tiles"""
     monkeypatch.setenv("PB_K3_TILE_KB", "16")
+    if gen_kb:
+        monkeypatch.setenv("PB_K3_GEN_KB", gen_kb)
     m = 7000                                          # 2048-replicate tiles -> 4 tiles, the last one partial
     tree, o, hc, sn, lab = _assoc_case(oracle_mod, 150, 500, m, 91, na_frac, 0.0, seed=77, replay=replay)
     if replay:
