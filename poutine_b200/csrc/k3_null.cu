@@ -363,24 +363,22 @@ __device__ __forceinline__ unsigned int sweep_miss(const K3Params& p, const Alle
 }
 
 #define K3_THREADS 256
-// work list B: alleles with 2 <= n < 8 (plus every small allele that needs the general path)
-__global__ void __launch_bounds__(K3_THREADS, 4) k3_count_small_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
+// work list 1: short lists (n < 8) on the tight path.  Few registers -> many resident warps: the sweep is bound by the
+// latency of the label-matrix loads.  MISS = the pheno file has missing labels.
+template <bool MISS>
+__global__ void __launch_bounds__(K3_THREADS, MISS ? 4 : 5) k3_count_tight_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
-    const double tau = *p.tau;
     const int words = (int)((p.n_reps + 63) >> 6);
     for (int64_t i = gwarp; i < n_list; i += nwarps) {
         const int64_t slot = list[i];
         const AlleleMeta m = p.alleles[slot];
         const int n = m.n, ks = m.kstar;
-        const bool tight = (m.flags & PB_AF_TIGHT) != 0;
-        if (tight && p.Xm != nullptr) {
-            unsigned int rc = n < 2 ? sweep_miss<1>(p, m, lane, words) : n < 4 ? sweep_miss<2>(p, m, lane, words) : sweep_miss<3>(p, m, lane, words);
-            rc = __reduce_add_sync(0xffffffffu, rc);
-            if (lane == 0 && rc) p.r[slot] += rc;
-        } else if (tight) {
-            unsigned int rc;
+        unsigned int rc;
+        if (MISS) {
+            rc = n < 2 ? sweep_miss<1>(p, m, lane, words) : n < 4 ? sweep_miss<2>(p, m, lane, words) : sweep_miss<3>(p, m, lane, words);
+        } else {
             if (ks <= 0) rc = (lane == 0) ? (unsigned int)p.n_reps : 0u;   // every replicate counts
             else if (ks > n) rc = 0;
             else if (n == 1) rc = sweep_fixed<1, 1>(p, m, lane, words);
@@ -388,13 +386,25 @@ __global__ void __launch_bounds__(K3_THREADS, 4) k3_count_small_kernel(const K3P
             else if (n == 3) rc = ks == 1 ? sweep_fixed<3, 1>(p, m, lane, words) : ks == 2 ? sweep_fixed<3, 2>(p, m, lane, words)
                                                                                            : sweep_fixed<3, 3>(p, m, lane, words);
             else rc = sweep_upto7(p, m, lane, words);
-            rc = __reduce_add_sync(0xffffffffu, rc);
-            if (lane == 0 && rc) p.r[slot] += rc;
-        } else {
-            if (n < 2) sweep_allele<1>(p, m, slot, lane, tau);
-            else if (n < 4) sweep_allele<2>(p, m, slot, lane, tau);
-            else sweep_allele<3>(p, m, slot, lane, tau);
         }
+        rc = __reduce_add_sync(0xffffffffu, rc);
+        if (lane == 0 && rc) p.r[slot] += rc;
+    }
+}
+
+// work list 3: short lists that need the general path (non-monotone table rows, possible maxT candidates, test hooks)
+__global__ void __launch_bounds__(K3_THREADS, 2) k3_count_small_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
+    const double tau = *p.tau;
+    for (int64_t i = gwarp; i < n_list; i += nwarps) {
+        const int64_t slot = list[i];
+        const AlleleMeta m = p.alleles[slot];
+        const int n = m.n;
+        if (n < 2) sweep_allele<1>(p, m, slot, lane, tau);
+        else if (n < 4) sweep_allele<2>(p, m, slot, lane, tau);
+        else sweep_allele<3>(p, m, slot, lane, tau);
     }
 }
 
@@ -691,9 +701,9 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             p.Rw = Rw;
             p.rep_base = base + cb; p.n_reps = cnr; p.r = ctx->d_r; p.maxT = ctx->d_maxT;
             p.slots_per_chunk = 0;
-            const int64_t nA = ctx->n_work[0], nB = ctx->n_work[1], nC = ctx->n_work[2];
+            const int64_t nA = ctx->n_work[0], nB = ctx->n_work[1], nC = ctx->n_work[2], nG = ctx->n_work[3];
             const int64_t words = (cnr + 63) / 64;
-            int64_t bps = 16;
+            int64_t bps = 32;
             if (const char* e = getenv("PB_K3_BLOCKS_PER_SM")) bps = atoll(e);
             if (nA > 0) {
                 k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(p.Xc, p.Xm, Rw, words, ctx->P, ctx->d_colpop);
@@ -702,7 +712,13 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             }
             if (nB > 0) {
                 int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * bps, (nB + (K3_THREADS / 32) - 1) / (K3_THREADS / 32));
-                k3_count_small_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, nB);
+                if (has_miss) k3_count_tight_kernel<true><<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, nB);
+                else k3_count_tight_kernel<false><<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, nB);
+                ctx->tm.n_launches += 1;
+            }
+            if (nG > 0) {
+                int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * 8, (nG + (K3_THREADS / 32) - 1) / (K3_THREADS / 32));
+                k3_count_small_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + 3 * n_slots, nG);
                 ctx->tm.n_launches += 1;
             }
             if (nC > 0) {

@@ -128,7 +128,8 @@ __global__ void k4_ktau_kernel(const double* __restrict__ tab, int32_t n_max, co
     ktau[n] = kt;
 }
 
-// ---- work lists for K3b: A = no sweep needed, B = short lists (n < 8), C = long lists -----------------
+// ---- work lists for K3b: 0 = no sweep needed, 1 = short lists (n < 8) on the tight path, 2 = long lists (n >= 8),
+//      3 = short lists that need the general path -----------------------------------------------------------
 __global__ void k4_classify_kernel(AlleleMeta* __restrict__ alleles, int64_t n_slots, const int32_t* __restrict__ ktau, int has_miss,
                                    int32_t* __restrict__ lists, unsigned int* __restrict__ counts) {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,12 +146,12 @@ __global__ void k4_classify_kernel(AlleleMeta* __restrict__ alleles, int64_t n_s
             const bool tight = ((m.flags & (has_miss ? PB_AF_MISS_OK : PB_AF_FAST)) != 0) && cand_free;
             alleles[a].flags = (m.flags & ~PB_AF_TIGHT) | (tight ? PB_AF_TIGHT : 0u);
             const bool no_sweep = tight && (has_miss ? m.n <= 1 : (m.n <= 1 || m.kstar <= 0 || m.kstar > m.n));
-            cls = no_sweep ? 0 : (m.n < 8 ? 1 : 2);
+            cls = no_sweep ? 0 : (m.n >= 8 ? 2 : (tight ? 1 : 3));
         }
     }
     const unsigned int lane = threadIdx.x & 31u;
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
+    for (int c = 0; c < 4; c++) {
         const unsigned int mask = __ballot_sync(0xffffffffu, cls == c);
         if (!mask) continue;
         const int leader = __ffs(mask) - 1;
@@ -320,7 +321,7 @@ int pbk_thresholds(pb_ctx* ctx) {
         if (ctx->d_work) cudaFree(ctx->d_work);
         ctx->d_work = nullptr;
         ctx->work_cap = n_slots + n_slots / 8 + 1024;
-        PB_CUDA(cudaMalloc(&ctx->d_work, (size_t)ctx->work_cap * 3 * 4));
+        PB_CUDA(cudaMalloc(&ctx->d_work, (size_t)ctx->work_cap * 4 * 4));
     }
     if (n_slots > 0)
         k4_classify_kernel<<<(unsigned)((n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ktau, ctx->n_miss > 0 ? 1 : 0,
@@ -331,7 +332,7 @@ int pbk_thresholds(pb_ctx* ctx) {
     PB_CUDA(cudaMemcpyAsync(&h, d_nfast, sizeof(h), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
     ctx->tm.n_fast_alleles = (int64_t)h.nf;
-    for (int c = 0; c < 3; c++) ctx->n_work[c] = (int64_t)h.lc[c];
+    for (int c = 0; c < 4; c++) ctx->n_work[c] = (int64_t)h.lc[c];
     return PB_OK;
 }
 

@@ -134,8 +134,8 @@ struct pb_ctx {
     int64_t X_cap = 0, Xm_cap = 0, fb_cap = 0;
     uint32_t* d_perms = nullptr; int64_t perms_cap = 0;
     pb_stat_out* d_stats = nullptr; int64_t stats_cap = 0;
-    int32_t* d_work = nullptr; int64_t work_cap = 0;   // 3 work lists of slot ids (classes A/B/C), n_slots each
-    int64_t n_work[3] = {0, 0, 0};
+    int32_t* d_work = nullptr; int64_t work_cap = 0;   // 4 work lists of slot ids (k4_classify_kernel), n_slots each
+    int64_t n_work[4] = {0, 0, 0, 0};
     uint32_t* d_colpop = nullptr; int64_t colpop_cap = 0;  // [2][P] per-sample case / missing-label popcounts of the current tile
     int32_t* d_fb_reps = nullptr;  // fallback replicate list
     unsigned int* d_fb_count = nullptr;
