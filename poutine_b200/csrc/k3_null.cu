@@ -599,8 +599,15 @@ int pbk_pregen_labels(pb_ctx* ctx) {
     if ((rc = k3_plan(ctx, &pl))) return rc;
     const int64_t m = ctx->cfg.n_replicates;
     const int64_t nr = m < pl.tile ? m : pl.tile;
-    PB_CUDA(cudaEventRecord(ctx->ev_k1_done, ctx->stream));
-    PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_k1_done, 0));
+    // default: the generator starts when K1 has finished.  PB_PREGEN_EARLY (experiment): it is ordered behind the previous
+    // step only (ev[0] is recorded just before the K1 launch), so the low-priority stream may pick up SM slots while
+    // K1's last wave drains.
+    if (getenv("PB_PREGEN_EARLY")) {
+        PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev[0], 0));
+    } else {
+        PB_CUDA(cudaEventRecord(ctx->ev_k1_done, ctx->stream));
+        PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_k1_done, 0));
+    }
     if ((rc = k3_launch_philox(ctx, pl, 0, nr, ctx->stream2, 0))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev_gen_done, ctx->stream2));
     ctx->pregen_valid = true;

@@ -57,8 +57,13 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
         return PB_ERR_CUDA;
     };
     if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("cudaSetDevice", e);
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    {
+        // the main stream outranks the label-generation stream: when both have blocks pending, the path's own kernels go first
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    }
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_k1_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_gen_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -362,11 +367,9 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
     ctx->tm = pb_timings{};
     int rc;
     PB_CUDA(cudaEventRecord(ctx->ev[12], ctx->stream));
-    const bool pregen_early = getenv("PB_PREGEN_EARLY") != nullptr;
-    if (pregen_early && (rc = pbk_pregen_labels(ctx))) return rc;
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = pbk_events(ctx))) return rc;
-        if (!pregen_early && attempt == 0 && (rc = pbk_pregen_labels(ctx))) return rc;
+        if (attempt == 0 && (rc = pbk_pregen_labels(ctx))) return rc;
         unsigned long long cur = 0;
         PB_CUDA(cudaMemcpyAsync(&cur, ctx->d_raw_cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(cudaStreamSynchronize(ctx->stream));
