@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpoutine_b200.so")
+LIB_PATH = os.environ.get("PB_LIB") or os.path.join(_HERE, "libpoutine_b200.so")   # PB_LIB: experiment builds
 _LIB = None
 
 PB_MODE_PHILOX, PB_MODE_REPLAY = 0, 1

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
             for (int j = 0; j < (PB_K1_KHI + 1) * 4; j++) s_hi[j * PB_K1_COLS + tid] = 0;
             cs.nleaf = 0;
         }
-        if (((i - r0) & 31) == 31) drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
+        if (((i - r0) & (PB_K1_DRAIN_EVERY - 1)) == PB_K1_DRAIN_EVERY - 1) drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
     }
     drain_queue(s_queue, &s_count, &s_base, tid, 1, p.raw, p.raw_cursor, p.raw_cap);
 }

@@ -11,16 +11,21 @@
 // B200 design: replicates are bit-parallel.
 //   K3a  builds the label bit-matrix X[sample][replicate] (64 replicates per word), either from
 //        counter-based Philox4x32-10 streams (one thread = one replicate, sequential draw without
-//        replacement, warp ballot -> words) or from explicit replay permutations.
-//   K3b  one warp = 32 words (2048 replicates) x a chunk of alleles.  Per allele the n sample rows are
-//        gathered (coalesced 256 B per row, L2-resident) and summed with bit-sliced vertical
-//        counters; "p_r <= p_obs" is a bit-sliced compare k_r >= k* (valid because f(n,.) is checked
-//        to be an up-set on the host of the table), popcounted and warp-reduced (REDUX) into one
-//        atomic per allele per 2048 replicates.  maxT uses a candidate threshold tau: only replicates
-//        whose p-value can be <= tau are extracted to scalars and atomically min-ed; replicates left
-//        without a candidate are recomputed exactly by a fallback kernel.
-//        Replicates in which one of the allele's leaves drew a *missing* label (n_r < n) and alleles
-//        whose table row is not monotone take the exact scalar path bit by bit.
+//        replacement, warp ballot -> words) or from explicit replay permutations.  In Philox mode the
+//        first generation tile is launched by pb_run_events on a second stream (overlaps the K1 tail).
+//   K3b  alleles are classified once (k4_classify_kernel) into work lists:
+//          0  nothing to sweep: r follows from per-sample column popcounts (n <= 1) or is 0 / n_reps;
+//          1  short lists (n < 8) on the tight path: one warp sweeps one allele over all replicate words of the
+//             tile, rows streamed coalesced from the (L2-resident) matrix, "k_r >= k*" evaluated bit-sliced,
+//             r accumulated in registers and written once — no atomics;
+//          2  long lists (n >= 8): a whole block per allele, general bit-sliced path;
+//          3  short lists that need the general path (possible maxT candidates, non-monotone table rows).
+//        "p_r <= p_obs" as a threshold k_r >= k* is valid because f(n,.) is checked per allele to be an
+//        up-set w.r.t. p_obs (k4_observed_kernel); with missing labels in the pheno file the check covers every
+//        n_r = n - j a replicate can see, with one threshold per j (AlleleMeta.kpack).  Otherwise, and for
+//        maxT, replicate bits are extracted to scalars and looked up in f exactly as the reference does.
+//        maxT uses a candidate threshold tau: only p-values <= tau are min-ed atomically; replicates left
+//        without a certified minimum are recomputed exactly by k3_fallback_kernel.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -139,7 +144,6 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
 struct K3Params {
     const AlleleMeta* __restrict__ alleles;
     int64_t n_slots;
-    int32_t slots_per_chunk;
     const int32_t* __restrict__ csr;
     const double* __restrict__ pobs;      // [n_slots]
     const double* __restrict__ ptable;    // triangular
@@ -707,7 +711,6 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             p.Xm = has_miss ? ctx->d_Xmiss + buf * pl.buf_words + cb / 64 : nullptr;
             p.Rw = Rw;
             p.rep_base = base + cb; p.n_reps = cnr; p.r = ctx->d_r; p.maxT = ctx->d_maxT;
-            p.slots_per_chunk = 0;
             const int64_t nA = ctx->n_work[0], nB = ctx->n_work[1], nC = ctx->n_work[2], nG = ctx->n_work[3];
             const int64_t words = (cnr + 63) / 64;
             int64_t bps = 32;

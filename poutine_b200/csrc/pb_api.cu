@@ -211,7 +211,6 @@ static int build_chunks(pb_ctx* ctx) {
     }
     const std::vector<uint32_t>& ops = recs;
     ctx->n_flush = n_flush;
-    ctx->n_ops = (int64_t)ops.size();
     int rc;
     if ((rc = upload(ctx, &ctx->d_ops, ops))) return rc;
     if ((rc = upload(ctx, &ctx->d_chunk_op, chunk_op))) return rc;

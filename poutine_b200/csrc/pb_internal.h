@@ -47,6 +47,9 @@ typedef unsigned long long raw_event_t;
 #define PB_K1_THREADS 160   // 4 consumer warps + 1 TMA producer warp
 #define PB_K1_STAGES 4      // ring of row PAIRS (two 3 KB TMA boxes per stage: 3 planes x 128 words each)
 #define PB_K1_QCAP 768      // per-block event queue (6 KB)
+#ifndef PB_K1_DRAIN_EVERY
+#define PB_K1_DRAIN_EVERY 128 // records between queue-drain checks (a consumer-wide barrier each)
+#endif
 
 // allele flags
 #define PB_AF_IN_USE 1u
@@ -81,7 +84,6 @@ struct pb_ctx {
     uint32_t* d_ops = nullptr;      // K1 program
     int32_t* d_chunk_op = nullptr;  // n_chunks+1 record boundaries
     int32_t n_chunks = 0, n_flush = 0;
-    int64_t n_ops = 0;
     int32_t* d_node_sample = nullptr;  // N: sample index of a leaf with a pheno row, else -1
 
     // labels
