@@ -36,11 +36,13 @@ struct K1Params {
     unsigned long long raw_cap;
 };
 
-__device__ __forceinline__ void csa(uint64_t& h, uint64_t& l, uint64_t a, uint64_t b, uint64_t c) {
-    const uint64_t u = a ^ b;
-    h = (a & b) | (u & c);
-    l = u ^ c;
-}
+#if PB_K1_LANE_BITS == 64
+typedef uint64_t lane_t;
+__device__ __forceinline__ int lane_ffs(lane_t x) { return __ffsll((long long)x); }
+#else
+typedef uint32_t lane_t;
+__device__ __forceinline__ int lane_ffs(lane_t x) { return __ffs((int)x); }
+#endif
 
 // ---- mbarrier / TMA primitives (inline PTX; barrier and ring addresses are 32-bit shared-window offsets) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,9 +67,13 @@ __device__ __forceinline__ void tma_load_row(uint32_t dst, const CUtensorMap* tm
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst), "l"(tmap), "r"(col0), "r"(node), "r"(0), "r"(bar) : "memory");
 }
-__device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
-    uint64_t v;
+__device__ __forceinline__ lane_t lds_lane(uint32_t addr) {
+    lane_t v;
+#if PB_K1_LANE_BITS == 64
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+#else
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+#endif
     return v;
 }
 // keeps a shared-window address in a register (stops the compiler from re-deriving it from the CTA id every use)
@@ -76,14 +82,14 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t x) {
     asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
-__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PB_K1_COLS) : "memory"); }
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PB_K1_CONSUMERS) : "memory"); }
 
-__device__ __forceinline__ void emit_events(uint64_t mrca, uint64_t b0, uint64_t b1, uint32_t site_base, uint32_t node_tag,
+__device__ __forceinline__ void emit_events(lane_t mrca, lane_t b0, lane_t b1, uint32_t site_base, uint32_t node_tag,
                                             raw_event_t* s_queue, unsigned int* s_count, const K1Params& p) {
     while (mrca) {
-        const int b = __ffsll((long long)mrca) - 1;
+        const int b = lane_ffs(mrca) - 1;
         mrca &= mrca - 1;
-        const uint32_t base = (uint32_t)((b0 >> b) & 1ull) | ((uint32_t)((b1 >> b) & 1ull) << 1);
+        const uint32_t base = (uint32_t)((b0 >> b) & 1u) | ((uint32_t)((b1 >> b) & 1u) << 1);
         const raw_event_t rec = (raw_event_t)(site_base + (uint32_t)b) | ((raw_event_t)(node_tag | (base << 29)) << 32);
         const unsigned int slot = atomicAdd(s_count, 1u);
         if (slot < PB_K1_QCAP) {
@@ -104,7 +110,7 @@ __device__ __noinline__ void drain_queue(raw_event_t* s_queue, unsigned int* s_c
         if (tid == 0) *s_base = atomicAdd(raw_cursor, (unsigned long long)n);
         consumer_bar_sync();
         const unsigned long long base = *s_base;
-        for (unsigned int i = tid; i < n; i += PB_K1_COLS) {
+        for (unsigned int i = tid; i < n; i += PB_K1_CONSUMERS) {
             const unsigned long long pos = base + i;
             if (pos < raw_cap) raw[pos] = s_queue[i];
         }
@@ -124,21 +130,21 @@ __device__ __noinline__ void drain_queue(raw_event_t* s_queue, unsigned int* s_c
 
 // consumer-thread state of the leaf census (see k1_events_kernel)
 struct Census {
-    uint64_t ones[4], twos[4], fours[4], pend2[4], pend4[4];
+    lane_t ones[4], twos[4], fours[4], pend2[4], pend4[4];
     int nleaf;
 };
 
 // one tree row: MRCA test against the current parent row, optional parent update, optional leaf census
-__device__ __forceinline__ void k1_row(uint32_t op, uint64_t cv, uint64_t c0, uint64_t c1, uint64_t& pv, uint64_t& p0, uint64_t& p1,
-                                       Census& cs, uint64_t* s_hi, uint64_t* s_p8, int tid, uint32_t site_base, raw_event_t* s_queue,
+__device__ __forceinline__ void k1_row(uint32_t op, lane_t cv, lane_t c0, lane_t c1, lane_t& pv, lane_t& p0, lane_t& p1,
+                                       Census& cs, lane_t* s_hi, lane_t* s_p8, int tid, uint32_t site_base, raw_event_t* s_queue,
                                        unsigned int* s_count, const K1Params& p) {
     if (op & PB_OP_TEST) {
-        const uint64_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
+        const lane_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
         if (mrca) emit_events(mrca, c0, c1, site_base, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), s_queue, s_count, p);
     }
     if (op & PB_OP_SETCUR) { pv = cv; p0 = c0; p1 = c1; }
     if (op & PB_OP_LEAF) {
-        const uint64_t x[4] = {cv & ~c0 & ~c1, cv & c0 & ~c1, cv & ~c0 & c1, cv & c0 & c1};
+        const lane_t x[4] = {cv & ~c0 & ~c1, cv & c0 & ~c1, cv & ~c0 & c1, cv & c0 & c1};
         const int ph = cs.nleaf & 7;                                 // block-uniform
         cs.nleaf++;
 #pragma unroll
@@ -149,16 +155,16 @@ __device__ __forceinline__ void k1_row(uint32_t op, uint64_t cv, uint64_t c0, ui
             if (ph & 2) {
                 if (!(ph & 4)) {
 #pragma unroll
-                    for (int c = 0; c < 4; c++) { s_p8[c * PB_K1_COLS] = cs.fours[c] & cs.pend4[c]; cs.fours[c] ^= cs.pend4[c]; cs.pend4[c] = 0; }
+                    for (int c = 0; c < 4; c++) { s_p8[c * PB_K1_CONSUMERS] = cs.fours[c] & cs.pend4[c]; cs.fours[c] ^= cs.pend4[c]; cs.pend4[c] = 0; }
                 } else {
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
-                        uint64_t carry = s_p8[c * PB_K1_COLS] | (cs.fours[c] & cs.pend4[c]);
+                        lane_t carry = s_p8[c * PB_K1_CONSUMERS] | (cs.fours[c] & cs.pend4[c]);
                         cs.fours[c] ^= cs.pend4[c]; cs.pend4[c] = 0;
 #pragma unroll
                         for (int j = 0; j < PB_K1_KHI; j++) {
-                            uint64_t* hp = s_hi + (j * 4 + c) * PB_K1_COLS + tid;
-                            const uint64_t h = *hp;
+                            lane_t* hp = s_hi + (j * 4 + c) * PB_K1_CONSUMERS + tid;
+                            const lane_t h = *hp;
                             *hp = h ^ carry;
                             carry &= h;
                         }
@@ -171,7 +177,7 @@ __device__ __forceinline__ void k1_row(uint32_t op, uint64_t cv, uint64_t c0, ui
 
 __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* s_hi = reinterpret_cast<uint64_t*>(smem + K1_SMEM_RING);                    // [slice][base][col]
+    lane_t* s_hi = reinterpret_cast<lane_t*>(smem + K1_SMEM_RING);                        // [slice][base][consumer]
     raw_event_t* s_queue = reinterpret_cast<raw_event_t*>(smem + K1_SMEM_RING + K1_SMEM_HI);
     __shared__ unsigned int s_count;
     __shared__ unsigned long long s_base;
@@ -186,17 +192,17 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
 
     if (tid == 0) {
         s_count = 0;
-        for (int s = 0; s < PB_K1_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, PB_K1_COLS / 32); }
+        for (int s = 0; s < PB_K1_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, PB_K1_CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (tid < PB_K1_COLS)
-        for (int i = 0; i < (PB_K1_KHI + 1) * 4; i++) s_hi[i * PB_K1_COLS + tid] = 0;
+    if (tid < PB_K1_CONSUMERS)
+        for (int i = 0; i < (PB_K1_KHI + 1) * 4; i++) s_hi[i * PB_K1_CONSUMERS + tid] = 0;
     __syncthreads();
 
-    if (tid >= PB_K1_COLS) {
+    if (tid >= PB_K1_CONSUMERS) {
         // ================= producer warp: one lane feeds the ring with TMA =================
-        if (tid == PB_K1_COLS) {
+        if (tid == PB_K1_CONSUMERS) {
             uint32_t soff = 0, boff = 0, phase = 0;
             for (int i = r0; i < r1; i++) {
                 const uint4 rec = __ldg(recs + i);
@@ -216,10 +222,12 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
 
     // ================= consumer warps =================
     const int lane = tid & 31;
-    const int64_t w = (int64_t)col0 + tid;
+    constexpr int SUBS = 64 / PB_K1_LANE_BITS;                          // consumer threads per word column
+    const int sub = tid % SUBS;                                         // which part of the 64-site word this thread owns
+    const int64_t w = (int64_t)col0 + tid / SUBS;
     const bool edge_block = (int64_t)col0 + PB_K1_COLS >= p.W;          // block-uniform: holds word W-1 (TMA zero-fills beyond W)
-    const uint32_t site_base = (uint32_t)(w * 64);
-    const uint32_t my_ring = pin_u32(ring0 + tid * 8);
+    const uint32_t site_base = (uint32_t)(w * 64 + sub * PB_K1_LANE_BITS);
+    const uint32_t my_ring = pin_u32(ring0 + tid * (PB_K1_LANE_BITS / 8));
 
     // leaf census, bit-sliced with deferred carries: level L holds a counter slice and the OR of the carries the
     // level below produced since its last update (two consecutive half-add carries are mutually exclusive:
@@ -228,21 +236,21 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
 #pragma unroll
     for (int c = 0; c < 4; c++) { cs.ones[c] = cs.twos[c] = cs.fours[c] = 0; cs.pend2[c] = cs.pend4[c] = 0; }
     cs.nleaf = 0;
-    uint64_t* s_p8 = s_hi + (PB_K1_KHI * 4) * PB_K1_COLS + tid;       // pending carries into slice 8
-    uint64_t pv = 0, p0 = 0, p1 = 0;   // current parent row
+    lane_t* s_p8 = s_hi + (PB_K1_KHI * 4) * PB_K1_CONSUMERS + tid;    // pending carries into slice 8
+    lane_t pv = 0, p0 = 0, p1 = 0;   // current parent row
     uint32_t soff = 0, boff = 0, phase = 0;
-    const uint64_t edge_mask = (edge_block && w == p.W - 1) ? p.last_mask : ~0ull;
+    const lane_t edge_mask = (edge_block && w == p.W - 1) ? (lane_t)(p.last_mask >> (sub * PB_K1_LANE_BITS)) : (lane_t)~(lane_t)0;
 
 #pragma unroll 1
     for (int i = r0; i < r1; i++) {
         const uint4 rec = __ldg(recs + i);
         const bool ra = (rec.x & PB_OP_NODE_MASK) != PB_OP_NULL, rb = (rec.y & PB_OP_NODE_MASK) != PB_OP_NULL;
-        uint64_t av, a0, a1, bv, b0, b1;
+        lane_t av, a0, a1, bv, b0, b1;
         if (ra | rb) {
             mbar_wait(full0 + boff, phase);                              // TMA bytes have landed
             const uint32_t src = my_ring + soff;
-            av = lds_u64(src); a0 = lds_u64(src + PB_K1_COLS * 8); a1 = lds_u64(src + 2 * PB_K1_COLS * 8);
-            bv = lds_u64(src + 3 * PB_K1_COLS * 8); b0 = lds_u64(src + 4 * PB_K1_COLS * 8); b1 = lds_u64(src + 5 * PB_K1_COLS * 8);
+            av = lds_lane(src); a0 = lds_lane(src + PB_K1_COLS * 8); a1 = lds_lane(src + 2 * PB_K1_COLS * 8);
+            bv = lds_lane(src + 3 * PB_K1_COLS * 8); b0 = lds_lane(src + 4 * PB_K1_COLS * 8); b1 = lds_lane(src + 5 * PB_K1_COLS * 8);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + boff);                   // stage is free again
             soff += K1_STAGE_BYTES; boff += 8;
@@ -260,20 +268,22 @@ __global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __gri
         if (rec.z != PB_REC_NOFLUSH) {
             // census partial rec.z: [flush][base][slice][W]   (segments are padded to 8 leaves: nothing is pending)
             if (w < p.W) {
-                uint64_t* out = p.census + ((int64_t)rec.z * 4 * PB_K1_KS) * p.W + w;
+                // census words are uint64 [flush][base][slice][W]; a 32-bit lane writes its half (little-endian)
+                lane_t* out = reinterpret_cast<lane_t*>(p.census) + (((int64_t)rec.z * 4 * PB_K1_KS) * p.W + w) * SUBS + sub;
+                const int64_t sl = p.W * SUBS;                           // lanes per slice
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    out[((int64_t)c * PB_K1_KS + 0) * p.W] = cs.ones[c];
-                    out[((int64_t)c * PB_K1_KS + 1) * p.W] = cs.twos[c];
-                    out[((int64_t)c * PB_K1_KS + 2) * p.W] = cs.fours[c];
+                    out[((int64_t)c * PB_K1_KS + 0) * sl] = cs.ones[c];
+                    out[((int64_t)c * PB_K1_KS + 1) * sl] = cs.twos[c];
+                    out[((int64_t)c * PB_K1_KS + 2) * sl] = cs.fours[c];
 #pragma unroll
-                    for (int j = 0; j < PB_K1_KHI; j++) out[((int64_t)c * PB_K1_KS + 3 + j) * p.W] = s_hi[(j * 4 + c) * PB_K1_COLS + tid];
+                    for (int j = 0; j < PB_K1_KHI; j++) out[((int64_t)c * PB_K1_KS + 3 + j) * sl] = s_hi[(j * 4 + c) * PB_K1_CONSUMERS + tid];
                 }
             }
 #pragma unroll
             for (int c = 0; c < 4; c++) { cs.ones[c] = cs.twos[c] = cs.fours[c] = 0; cs.pend2[c] = cs.pend4[c] = 0; }
 #pragma unroll
-            for (int j = 0; j < (PB_K1_KHI + 1) * 4; j++) s_hi[j * PB_K1_COLS + tid] = 0;
+            for (int j = 0; j < (PB_K1_KHI + 1) * 4; j++) s_hi[j * PB_K1_CONSUMERS + tid] = 0;
             cs.nleaf = 0;
         }
         if (((i - r0) & (PB_K1_DRAIN_EVERY - 1)) == PB_K1_DRAIN_EVERY - 1) drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
