@@ -366,6 +366,40 @@ __device__ __forceinline__ unsigned int sweep_miss(const K3Params& p, const Alle
     return rc;
 }
 
+// n <= 7, every label present, maxT candidates possible for k >= kt (1 <= kt <= n): the tight sweep plus a scalar
+// look-up + atomic min for the (rare) candidate replicates.  k* may be anything (<= 0: all count, > n: none).
+__device__ __forceinline__ unsigned int sweep_upto7_cand(const K3Params& p, const AlleleMeta& m, int lane, int words, int kt, double tau) {
+    const int n = m.n, kstar = m.kstar;
+    const uint64_t* __restrict__ rp[7];
+#pragma unroll
+    for (int e = 0; e < 7; e++) rp[e] = p.Xc + (int64_t)((e < n) ? __ldg(p.csr + m.off + e) : 0) * p.Rw + lane;
+    const double* __restrict__ row_n = p.ptable + (int64_t)n * (n + 1) / 2;
+    const int tail = (int)(p.n_reps & 63);
+    unsigned int rc = 0;
+    for (int w = lane, off = 0; w < words; w += 32, off += 32) {
+        uint64_t c[3] = {0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 7; e++) {
+            if (e < n) {
+                uint64_t x = __ldg(rp[e] + off);
+#pragma unroll
+                for (int j = 0; j < 3; j++) { const uint64_t t = c[j] & x; c[j] ^= x; x = t; }
+            }
+        }
+        uint64_t ge = (kstar <= 0) ? ~0ull : (kstar > n ? 0ull : ge_const<3>(c, kstar));
+        if (w == words - 1 && tail) ge &= (1ull << tail) - 1;        // k* <= 0 would count the padding replicates
+        rc += (unsigned int)__popcll(ge);
+        uint64_t cand = ge_const<3>(c, kt);                           // kt >= 1: padding bits (k = 0) are never candidates
+        while (cand) {
+            const int b = __ffsll((long long)cand) - 1;
+            cand &= cand - 1;
+            const double pv = row_n[extract<3>(c, b)];
+            if (pv <= tau) atomicMin(p.maxT + (p.rep_base + (int64_t)w * 64 + b), (unsigned long long)__double_as_longlong(pv));
+        }
+    }
+    return rc;
+}
+
 #define K3_THREADS 256
 // work list 1: short lists (n < 8) on the tight path.  Few registers -> many resident warps: the sweep is bound by the
 // latency of the label-matrix loads.  MISS = the pheno file has missing labels.
@@ -396,7 +430,8 @@ __global__ void __launch_bounds__(K3_THREADS, MISS ? 4 : 5) k3_count_tight_kerne
     }
 }
 
-// work list 3: short lists that need the general path (non-monotone table rows, possible maxT candidates, test hooks)
+// work list 3: short lists with possible maxT candidates (tight sweep + scalar candidate look-ups) or that need the
+// general path (non-monotone table rows, missing labels with candidates, test hooks)
 __global__ void __launch_bounds__(K3_THREADS, 2) k3_count_small_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
@@ -406,7 +441,12 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_count_small_kernel(const K3P
         const int64_t slot = list[i];
         const AlleleMeta m = p.alleles[slot];
         const int n = m.n;
-        if (n < 2) sweep_allele<1>(p, m, slot, lane, tau);
+        if (m.flags & PB_AF_TIGHT_CAND) {
+            unsigned int rc = sweep_upto7_cand(p, m, lane, (int)((p.n_reps + 63) >> 6), p.ktau[n], tau);
+            rc = __reduce_add_sync(0xffffffffu, rc);
+            if (lane == 0 && rc) p.r[slot] += rc;
+        }
+        else if (n < 2) sweep_allele<1>(p, m, slot, lane, tau);
         else if (n < 4) sweep_allele<2>(p, m, slot, lane, tau);
         else sweep_allele<3>(p, m, slot, lane, tau);
     }

@@ -144,7 +144,9 @@ __global__ void k4_classify_kernel(AlleleMeta* __restrict__ alleles, int64_t n_s
                 for (int n2 = 0; n2 <= m.n && cand_free; n2++) cand_free = ktau[n2] > n2;
             }
             const bool tight = ((m.flags & (has_miss ? PB_AF_MISS_OK : PB_AF_FAST)) != 0) && cand_free;
-            alleles[a].flags = (m.flags & ~PB_AF_TIGHT) | (tight ? PB_AF_TIGHT : 0u);
+            // short list, every label present, candidates possible but only for k >= ktau[n] >= 1 (so never for padding bits)
+            const bool tight_cand = !tight && !has_miss && (m.flags & PB_AF_FAST) && m.n < 8 && ktau[m.n] >= 1;
+            alleles[a].flags = (m.flags & ~(PB_AF_TIGHT | PB_AF_TIGHT_CAND)) | (tight ? PB_AF_TIGHT : 0u) | (tight_cand ? PB_AF_TIGHT_CAND : 0u);
             const bool no_sweep = tight && (has_miss ? m.n <= 1 : (m.n <= 1 || m.kstar <= 0 || m.kstar > m.n));
             cls = no_sweep ? 0 : (m.n >= 8 ? 2 : (tight ? 1 : 3));
         }

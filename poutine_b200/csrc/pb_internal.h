@@ -59,6 +59,7 @@ typedef unsigned long long raw_event_t;
 #define PB_AF_IN_USE 1u
 #define PB_AF_FAST 2u   // {k : f(n,k) <= p_obs} is an up-set: threshold path for replicates that see all n labels
 #define PB_AF_MISS_OK 8u // n <= 7 and every row f(n-j, .), j = 0..n, is an up-set w.r.t. p_obs: kpack is valid
+#define PB_AF_TIGHT_CAND 16u // like TIGHT (no missing labels, n < 8) but some k can be a maxT candidate: 1 <= ktau[n] <= n
 #define PB_AF_TIGHT 4u  // FAST and no replicate of this allele can be a maxT candidate: sweep without per-bit work
 
 struct AlleleMeta {      // one per allele slot (2 per informative site), 32 bytes
