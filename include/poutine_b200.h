@@ -62,7 +62,7 @@ typedef struct {
 
 enum {
     PB_FLAG_FORCE_GENERAL_NULL = 1u,  /* disable the all-labelled bit-sliced fast path (test hook) */
-    PB_FLAG_KEEP_RAW_EVENTS = 2u      /* keep the raw MRCA event list for pb_get_raw_events */
+    PB_FLAG_KEEP_RAW_EVENTS = 2u      /* reserved: the raw MRCA event list is always kept until the next pb_run_events */
 };
 
 /* One record per site of this context, field-for-field Homoplasy_Events (HC.java:5531-5550);
@@ -101,9 +101,10 @@ typedef struct {
     float ms_events_total;    /* K1 + count + finalize + compaction */
     float ms_tally;           /* K2 */
     float ms_ptable;          /* p-value table + thresholds */
-    float ms_null_gen;        /* K3a label bit-matrix generation */
+    float ms_null_gen;        /* K3a label bit-matrix generation as seen by the main stream (~0 when the tile was
+                                 pre-generated on the second stream during pb_run_events) */
     float ms_null_count;      /* K3b replicate counting */
-    float ms_null_fallback;   /* maxT fallback pass (normally 0) */
+    float ms_null_fallback;   /* (the maxT fallback pass now runs inside the count tiles: included in ms_null_count) */
     float ms_allreduce;       /* NCCL all-reduce(min) of maxT */
     float ms_pvalues;         /* K4: sort maxT + pointwise/familywise */
     float ms_assoc_total;
