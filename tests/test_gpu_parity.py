@@ -364,6 +364,58 @@ def test_ptable_golden_values_on_device(oracle_mod, golden_dir):
     np.testing.assert_array_equal(tab[:cnt].view(np.uint64), gold[:cnt].view(np.uint64))
 
 
+def test_degenerate_trees(oracle_mod):
+    """star tree (every leaf hangs off the root: no edge is ever tested), a 3-node tree, one site"""
+    for parent in ([-1] + [0] * 9, [-1, 0, 0]):
+        parent = np.array(parent, dtype=np.int32)
+        N = len(parent)
+        is_leaf = np.ones(N, dtype=np.uint8)
+        is_leaf[0] = 0
+        leaves = np.arange(1, N, dtype=np.int32)
+        rng = np.random.default_rng(N)
+        for S in (1, 70):
+            chars = np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, size=(N, S))]
+            o = oracle_mod.Oracle(parent, leaves)
+            or_ev, or_cc = o.count_all_homoplasy_events(chars)
+            hc, ev, cc = run_gpu_events((parent, is_leaf), chars=chars, num_replicates=10)
+            assert_events_equal(ev, cc, or_ev, or_cc)
+            assert cc["raw_events"] == 0
+            hc.set_phenos(leaves, (np.arange(N - 1) % 2).astype(np.uint8))
+            hc.count_all_homoplasy_events()
+            with pytest.raises(pb.NoInformativeSites):       # nothing can be homoplasic on a star
+                hc.assoc()
+
+
+@pytest.mark.parametrize("labels", ["all_cases", "all_controls", "one_sample"])
+def test_assoc_degenerate_phenotypes(oracle_mod, labels):
+    """p_success = 1, 0, or a single phenotyped sample: the commons-math chain goes through log(0) / n = 0 rows;
+    whatever it yields (NaN included), device and oracle must agree bit for bit and nothing may hang"""
+    m = 200
+    tree = synth.yule_tree(80, 7)
+    chars = synth.planes_to_chars(*synth.simulate_planes(tree, 400, 8, mean_extra_mut=4.0), 0, 400)
+    if labels == "one_sample":
+        sn, lab = tree.leaf_nodes[:1].copy(), np.array([1], dtype=np.uint8)
+    else:
+        sn = tree.leaf_nodes.copy()
+        lab = np.full(len(sn), 1 if labels == "all_cases" else 0, dtype=np.uint8)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    o.count_all_homoplasy_events(chars)
+    st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=None, seed=3, n_threads=2)
+    hc = pb.HomoplasyCounter(num_replicates=m, seed=3)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_seg_sites(chars)
+    hc.count_all_homoplasy_events()
+    g_st, g_mt = hc.assoc()
+    assert len(g_st) == len(st)
+    for f in ("obs_counts", "a1_in_use", "a2_in_use"):
+        np.testing.assert_array_equal(g_st[f], st[f], err_msg=f)
+    for f in ("obs_p_a1", "obs_p_a2"):
+        np.testing.assert_array_equal(g_st[f].view(np.uint64), st[f].view(np.uint64), err_msg=f)
+    for f in ("r_a1", "r_a2", "r_maxT_a1", "r_maxT_a2"):
+        np.testing.assert_array_equal(g_st[f], st[f], err_msg=f)
+
+
 def test_no_informative_sites_error(oracle_mod):
     tree = synth.yule_tree(50, 3)
     chars = synth.simulate_chars(tree, 40, 4, nasty=False)
