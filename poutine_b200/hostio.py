@@ -15,6 +15,7 @@ All numerics still run in libpoutine_b200.so on the GPU; nothing here computes a
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 import threading
 from decimal import Decimal
@@ -230,6 +231,7 @@ STAT_COLS = ("r_a1\tr_a2\tpointwise_pvalue_a1\tpointwise_pvalue_a2\tobs_binom_pv
              "familywise_pvalue_a1\tfamilywise_pvalue_a2")
 
 
+@functools.lru_cache(maxsize=1 << 20)     # p-values repeat massively: (r+1)/(m+1) and table entries
 def java_double_str(x: float) -> str:
     """java.lang.Double.toString: shortest digits that round-trip (JDK 19+; earlier JDKs print one digit more in
     rare cases), plain decimal for 1e-3 <= |x| < 1e7, otherwise d.dddE[-]n; always at least one fraction digit."""
