@@ -231,8 +231,12 @@ STAT_COLS = ("r_a1\tr_a2\tpointwise_pvalue_a1\tpointwise_pvalue_a2\tobs_binom_pv
              "familywise_pvalue_a1\tfamilywise_pvalue_a2")
 
 
-@functools.lru_cache(maxsize=1 << 20)     # p-values repeat massively: (r+1)/(m+1) and table entries
 def java_double_str(x: float) -> str:
+    return "NaN" if x != x else _java_double_str(x)     # NaN is not a usable cache key (nan != nan)
+
+
+@functools.lru_cache(maxsize=1 << 20)     # p-values repeat massively: (r+1)/(m+1) and table entries
+def _java_double_str(x: float) -> str:
     """java.lang.Double.toString: shortest digits that round-trip (JDK 19+; earlier JDKs print one digit more in
     rare cases), plain decimal for 1e-3 <= |x| < 1e7, otherwise d.dddE[-]n; always at least one fraction digit."""
     if x != x:
