@@ -249,7 +249,11 @@ def run_b200(args):
         tm = step_resident()
 
     # ---- timed: inputs resident in HBM ---------------------------------------------------------------
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    try:
+        gpu_id = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)   # immune to CUDA_VISIBLE_DEVICES remapping
+    except Exception:
+        gpu_id = str(local_rank)
+    sampler = ClockSampler(gpu_id) if rank == 0 else None
     k1_ms, launches, parts = [], 0, {}
     barrier()
     t0 = time.perf_counter()

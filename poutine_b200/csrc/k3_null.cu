@@ -112,7 +112,10 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
                             }
                         }
                         const uint32_t u = (uint32_t)(prod >> 32);
-                        if (u < rem_case) { lab = 1; rem_case--; }
+                        if (!MISS) {                      // no missing labels: whatever is not a case is a control
+                            lab = u < rem_case ? 1u : 0u;
+                            rem_case -= lab;
+                        } else if (u < rem_case) { lab = 1; rem_case--; }
                         else if (u < rem_case + rem_ctrl) { lab = 0; rem_ctrl--; }
                         else lab = 2;
                     } else {
