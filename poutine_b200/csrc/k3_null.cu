@@ -68,6 +68,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 #define GEN_THREADS 256
 #define GEN_ROWS 128
+#ifndef GEN_ILP
+#define GEN_ILP 4          // Philox blocks computed together (GEN_ROWS must be a multiple of 4 * GEN_ILP)
+#endif
 
 // mode 0: Philox (sampling spec in DESIGN.md §K3a; restated by oracle/oracle.cpp or_philox_labels)
 // mode 1: replay (sample j gets label[perms[rep*P + j]])
@@ -88,17 +91,22 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
 
     for (int i0 = 0; i0 < P; i0 += GEN_ROWS) {          // GEN_ROWS is a multiple of 4
         const int rows = min(GEN_ROWS, P - i0);
-        for (int ii = 0; ii < rows; ii += 4) {
-            uint32_t w[4] = {0, 0, 0, 0};
-            if (MODE == 0) philox4x32_10((uint32_t)((i0 + ii) >> 2), r0, r1, 0u, k0, k1, w);
+        for (int ii = 0; ii < rows; ii += 4 * GEN_ILP) {
+            // GEN_ILP independent Philox blocks per pass: their 10-round dependent chains interleave in the pipeline
+            uint32_t w[GEN_ILP][4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int i = i0 + ii + j;
-                if (i < P) {                              // block-uniform
+            for (int q4 = 0; q4 < GEN_ILP; q4++) {
+                w[q4][0] = w[q4][1] = w[q4][2] = w[q4][3] = 0;
+                if (MODE == 0) philox4x32_10((uint32_t)((i0 + ii) >> 2) + q4, r0, r1, 0u, k0, k1, w[q4]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4 * GEN_ILP; jj++) {
+                const int i = i0 + ii + jj;
+                if (ii + jj < rows) {                     // block-uniform (rows, GEN_ROWS are multiples of nothing in particular)
                     uint32_t lab;
                     if (MODE == 0) {
                         const uint32_t range = (uint32_t)(P - i);
-                        uint64_t prod = (uint64_t)w[j] * range;
+                        uint64_t prod = (uint64_t)w[jj >> 2][jj & 3] * range;
                         uint32_t lo = (uint32_t)prod;
                         if (lo < range) {  // Lemire: exact rejection, taken with probability < range / 2^32
                             const uint32_t t = (0u - range) % range;
@@ -122,10 +130,10 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
                         lab = active ? label[prow[i]] : 0;
                     }
                     const uint32_t bc = __ballot_sync(0xffffffffu, active && lab == 1);
-                    if (lane == 0) sc[ii + j][warp] = bc;
+                    if (lane == 0) sc[ii + jj][warp] = bc;
                     if (MISS) {
                         const uint32_t bm = __ballot_sync(0xffffffffu, active && lab == 2);
-                        if (lane == 0) sm[ii + j][warp] = bm;
+                        if (lane == 0) sm[ii + jj][warp] = bm;
                     }
                 }
             }
