@@ -87,9 +87,47 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
     const uint64_t rep = (uint64_t)(rep_base + rep_local);
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), r0 = (uint32_t)rep, r1 = (uint32_t)(rep >> 32);
     uint32_t rem_case = (uint32_t)n_case, rem_ctrl = (uint32_t)n_ctrl, q = 0;
+    if (MODE == 0 && !MISS && !active) rem_case = 0;     // padding replicates of the last block never draw a case: bits stay 0
     const uint32_t* prow = (MODE == 1 && active) ? perms + rep_local * (int64_t)P : nullptr;
+    uint32_t range = (uint32_t)P;                         // samples not yet labelled (Philox mode)
 
-    for (int i0 = 0; i0 < P; i0 += GEN_ROWS) {          // GEN_ROWS is a multiple of 4
+    // one sample: Lemire draw in [0, range) with exact rejection, label, ballot -> one 32-replicate word per warp
+    auto draw = [&](uint32_t x, int i, int row) {
+        uint32_t lab;
+        if (MODE == 0) {
+            uint64_t prod = (uint64_t)x * range;
+            uint32_t lo = (uint32_t)prod;
+            if (lo < range) {  // taken with probability < range / 2^32
+                const uint32_t t = (0u - range) % range;
+                while (lo < t) {
+                    uint32_t rw[4];
+                    philox4x32_10(q >> 2, r0, r1, 1u, k0, k1, rw);
+                    const uint32_t y = (q & 2) ? ((q & 1) ? rw[3] : rw[2]) : ((q & 1) ? rw[1] : rw[0]);
+                    q++;
+                    prod = (uint64_t)y * range;
+                    lo = (uint32_t)prod;
+                }
+            }
+            range--;
+            const uint32_t u = (uint32_t)(prod >> 32);
+            if (!MISS) {                      // no missing labels: whatever is not a case is a control
+                lab = u < rem_case ? 1u : 0u;
+                rem_case -= lab;
+            } else if (u < rem_case) { lab = 1; rem_case--; }
+            else if (u < rem_case + rem_ctrl) { lab = 0; rem_ctrl--; }
+            else lab = 2;
+        } else {
+            lab = active ? label[prow[i]] : 0;
+        }
+        const uint32_t bc = (MODE == 0 && !MISS) ? __ballot_sync(0xffffffffu, lab != 0) : __ballot_sync(0xffffffffu, active && lab == 1);
+        if (lane == 0) sc[row][warp] = bc;
+        if (MISS) {
+            const uint32_t bm = __ballot_sync(0xffffffffu, active && lab == 2);
+            if (lane == 0) sm[row][warp] = bm;
+        }
+    };
+
+    for (int i0 = 0; i0 < P; i0 += GEN_ROWS) {          // GEN_ROWS is a multiple of 4 * GEN_ILP
         const int rows = min(GEN_ROWS, P - i0);
         for (int ii = 0; ii < rows; ii += 4 * GEN_ILP) {
             // GEN_ILP independent Philox blocks per pass: their 10-round dependent chains interleave in the pipeline
@@ -99,43 +137,13 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
                 w[q4][0] = w[q4][1] = w[q4][2] = w[q4][3] = 0;
                 if (MODE == 0) philox4x32_10((uint32_t)((i0 + ii) >> 2) + q4, r0, r1, 0u, k0, k1, w[q4]);
             }
+            if (ii + 4 * GEN_ILP <= rows) {               // full group: no per-sample bounds checks (block-uniform)
 #pragma unroll
-            for (int jj = 0; jj < 4 * GEN_ILP; jj++) {
-                const int i = i0 + ii + jj;
-                if (ii + jj < rows) {                     // block-uniform (rows, GEN_ROWS are multiples of nothing in particular)
-                    uint32_t lab;
-                    if (MODE == 0) {
-                        const uint32_t range = (uint32_t)(P - i);
-                        uint64_t prod = (uint64_t)w[jj >> 2][jj & 3] * range;
-                        uint32_t lo = (uint32_t)prod;
-                        if (lo < range) {  // Lemire: exact rejection, taken with probability < range / 2^32
-                            const uint32_t t = (0u - range) % range;
-                            while (lo < t) {
-                                uint32_t rw[4];
-                                philox4x32_10(q >> 2, r0, r1, 1u, k0, k1, rw);
-                                const uint32_t x = (q & 2) ? ((q & 1) ? rw[3] : rw[2]) : ((q & 1) ? rw[1] : rw[0]);
-                                q++;
-                                prod = (uint64_t)x * range;
-                                lo = (uint32_t)prod;
-                            }
-                        }
-                        const uint32_t u = (uint32_t)(prod >> 32);
-                        if (!MISS) {                      // no missing labels: whatever is not a case is a control
-                            lab = u < rem_case ? 1u : 0u;
-                            rem_case -= lab;
-                        } else if (u < rem_case) { lab = 1; rem_case--; }
-                        else if (u < rem_case + rem_ctrl) { lab = 0; rem_ctrl--; }
-                        else lab = 2;
-                    } else {
-                        lab = active ? label[prow[i]] : 0;
-                    }
-                    const uint32_t bc = __ballot_sync(0xffffffffu, active && lab == 1);
-                    if (lane == 0) sc[ii + jj][warp] = bc;
-                    if (MISS) {
-                        const uint32_t bm = __ballot_sync(0xffffffffu, active && lab == 2);
-                        if (lane == 0) sm[ii + jj][warp] = bm;
-                    }
-                }
+                for (int jj = 0; jj < 4 * GEN_ILP; jj++) draw(w[jj >> 2][jj & 3], i0 + ii + jj, ii + jj);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 4 * GEN_ILP; jj++)
+                    if (ii + jj < rows) draw(w[jj >> 2][jj & 3], i0 + ii + jj, ii + jj);
             }
         }
         __syncthreads();
