@@ -175,7 +175,7 @@ __device__ __forceinline__ void k1_row(uint32_t op, lane_t cv, lane_t c0, lane_t
     }
 }
 
-__global__ void __launch_bounds__(PB_K1_THREADS, 4) k1_events_kernel(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
+__global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_kernel(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     lane_t* s_hi = reinterpret_cast<lane_t*>(smem + K1_SMEM_RING);                        // [slice][base][consumer]
     raw_event_t* s_queue = reinterpret_cast<raw_event_t*>(smem + K1_SMEM_RING + K1_SMEM_HI);

@@ -153,7 +153,7 @@ static int build_chunks(pb_ctx* ctx) {
     const int64_t n_lops = (int64_t)ctx->lop_child.size();
     const int64_t blocks_x = (ctx->W + PB_K1_COLS - 1) / PB_K1_COLS;
     // grid.y: ~4 waves of 4 resident blocks per SM, picking the chunk count whose last wave is fullest
-    int64_t slots = (int64_t)ctx->sm_count * 4;
+    int64_t slots = (int64_t)ctx->sm_count * PB_K1_BLOCKS_PER_SM;
     if (const char* e = getenv("PB_K1_TARGET_BLOCKS")) slots = atoll(e);
     int64_t n_chunks = 1;
     {

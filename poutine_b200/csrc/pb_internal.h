@@ -43,14 +43,17 @@ typedef unsigned long long raw_event_t;
 #define PB_K1_KS (3 + PB_K1_KHI)
 #define PB_K1_SEG_LEAVES 248
 #define PB_K1_KT 24         // slices of the reduced census (leaf counts < 2^24)
-#define PB_K1_COLS 128      // 64-site word columns per block
+#ifndef PB_K1_COLS
+#define PB_K1_COLS 128      // 64-site word columns per block (128 -> 4 resident blocks per SM, 256 -> 2)
+#endif
+#define PB_K1_BLOCKS_PER_SM (512 / PB_K1_COLS)
 #ifndef PB_K1_LANE_BITS
 #define PB_K1_LANE_BITS 64   // sites per consumer thread: 64 (one word column) or 32 (half a column: twice the warps, half the state)
 #endif
 #define PB_K1_CONSUMERS (PB_K1_COLS * 64 / PB_K1_LANE_BITS)
 #define PB_K1_THREADS (PB_K1_CONSUMERS + 32)   // consumer warps + 1 TMA producer warp
 #define PB_K1_STAGES 4      // ring of row PAIRS (two 3 KB TMA boxes per stage: 3 planes x 128 words each)
-#define PB_K1_QCAP 768      // per-block event queue (6 KB)
+#define PB_K1_QCAP (6 * PB_K1_COLS)   // per-block event queue (6 KB per 128 columns)
 #ifndef PB_K1_DRAIN_EVERY
 #define PB_K1_DRAIN_EVERY 128 // records between queue-drain checks (a consumer-wide barrier each)
 #endif
