@@ -66,7 +66,10 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-#define GEN_THREADS 256
+#ifndef GEN_THREADS
+#define GEN_THREADS 256       // replicates per block (a multiple of 32; Rw32 assumes tiles padded to 256 replicates)
+#endif
+#define GEN_WORDS (GEN_THREADS / 32)
 #define GEN_ROWS 128
 #ifndef GEN_ILP
 #define GEN_ILP 4          // Philox blocks computed together (GEN_ROWS must be a multiple of 4 * GEN_ILP)
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
                                                              int32_t n_ctrl, const uint8_t* __restrict__ label,
                                                              const uint32_t* __restrict__ perms, uint32_t* __restrict__ Xc32,
                                                              uint32_t* __restrict__ Xm32, int64_t Rw32) {
-    __shared__ uint32_t sc[GEN_ROWS][8], sm[MISS ? GEN_ROWS : 1][8];
+    __shared__ uint32_t sc[GEN_ROWS][GEN_WORDS], sm[MISS ? GEN_ROWS : 1][GEN_WORDS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rep_local = (int64_t)blockIdx.x * GEN_THREADS + tid;
     const bool active = rep_local < n_reps;
@@ -147,9 +150,9 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
             }
         }
         __syncthreads();
-        for (int t = tid; t < rows * 8; t += GEN_THREADS) {
-            const int row = t >> 3, wd = t & 7;
-            const int64_t o = (int64_t)(i0 + row) * Rw32 + (int64_t)blockIdx.x * 8 + wd;
+        for (int t = tid; t < rows * GEN_WORDS; t += GEN_THREADS) {
+            const int row = t / GEN_WORDS, wd = t % GEN_WORDS;
+            const int64_t o = (int64_t)(i0 + row) * Rw32 + (int64_t)blockIdx.x * GEN_WORDS + wd;
             Xc32[o] = sc[row][wd];
             if (MISS) Xm32[o] = sm[row][wd];
         }
