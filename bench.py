@@ -208,11 +208,13 @@ def run_b200(args):
     # pinned staging copies: the e2e leg uploads from these every step
     pinned = []
     host_planes = []
+    Wp = (W + 15) & ~15                                   # the library's device row pitch: lets pb_put_planes do flat copies
     for a in (B0, B1, V):
-        h, p = _lib.pinned_empty((N, W), np.uint64)
-        h[...] = a
+        h, p = _lib.pinned_empty((N, Wp), np.uint64)
+        h[:, :W] = a
+        h[:, W:] = 0
         pinned.append(p)
-        host_planes.append(h)
+        host_planes.append(h[:, :W])
     cpu_chars = synth.planes_to_chars(B0, B1, V, 0, min(CPU_SAMPLE_SITES, S)) if rank == 0 and world == 1 else None
     del B0, B1, V
     t_gen = time.perf_counter() - t_gen
@@ -285,7 +287,7 @@ def run_b200(args):
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
     clocks = sampler.stop() if sampler else None      # sampled over both timed regions (resident + end to end)
-    h2d = 3 * N * W * 8
+    h2d = 3 * N * Wp * 8                                  # what pb_put_planes copies (rows padded to the device pitch)
     d2h = S * _lib.SITE_DTYPE.itemsize + len(st) * _lib.STAT_DTYPE.itemsize + m * 8
     e2e_value = total_sites * args.steps / (e2e_ms / 1e3)
     n_draws = sum_over_ranks(tm["n_alleles_in_use"]) * m

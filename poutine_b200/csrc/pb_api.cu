@@ -352,9 +352,15 @@ extern "C" int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, i
     ctx->events_done = ctx->assoc_done = false;
     const uint64_t* src[3] = {B0, B1, V};
     uint64_t* dst[3] = {ctx->d_B0, ctx->d_B1, ctx->d_V};
-    for (int i = 0; i < 3; i++)
-        PB_CUDA(cudaMemcpy2DAsync(dst[i] + word_begin, (size_t)ctx->Wp * 8, src[i], (size_t)src_pitch_words * 8, (size_t)n_words * 8,
-                                  (size_t)ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    if (word_begin == 0 && n_words == ctx->W && src_pitch_words == ctx->Wp) {
+        // the caller's rows already have the device pitch (W rounded up to 16 words): one flat copy per plane
+        for (int i = 0; i < 3; i++)
+            PB_CUDA(cudaMemcpyAsync(dst[i], src[i], (size_t)ctx->N * ctx->Wp * 8, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        for (int i = 0; i < 3; i++)
+            PB_CUDA(cudaMemcpy2DAsync(dst[i] + word_begin, (size_t)ctx->Wp * 8, src[i], (size_t)src_pitch_words * 8, (size_t)n_words * 8,
+                                      (size_t)ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    }
     PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers are caller-owned: do not retain them past return
     return PB_OK;
 }
