@@ -118,6 +118,19 @@ def test_events_tiled_upload_and_pitch(oracle_mod):
     hc2.set_planes(B0, B1, V, S, tile_words=5)   # slices of a wider array: pitch != n_words
     ev2, cc2 = hc2.count_all_homoplasy_events()
     assert ev1.tobytes() == ev2.tobytes() and cc1 == cc2
+    # host rows already padded to the device pitch (W rounded up to 16 words): pb_put_planes takes the flat-copy path
+    W = (S + 63) // 64
+    Wp = (W + 15) & ~15
+    padded = []
+    for a in (B0, B1, V):
+        h = np.full((tree.n_nodes, Wp), np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)   # garbage in the padding words
+        h[:, :W] = a
+        padded.append(h[:, :W])
+    hc3 = pb.HomoplasyCounter(num_replicates=10)
+    hc3.set_tree(tree.parent, tree.is_leaf)
+    hc3.set_planes(*padded, S)
+    ev3, cc3 = hc3.count_all_homoplasy_events()
+    assert ev1.tobytes() == ev3.tobytes() and cc1 == cc3
     chars = synth.planes_to_chars(B0, B1, V, 0, S)
     o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
     or_ev, or_cc = o.count_all_homoplasy_events(chars)
