@@ -151,17 +151,24 @@ __global__ void k4_classify_kernel(AlleleMeta* __restrict__ alleles, int64_t n_s
             cls = no_sweep ? 0 : (m.n >= 8 ? 2 : (tight ? 1 : 3));
         }
     }
-    const unsigned int lane = threadIdx.x & 31u;
+    // list append: one global atomic per class per BLOCK (per-warp ballots -> block prefix in shared memory)
+    __shared__ unsigned int s_wcount[8][4], s_base[4];
+    const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned int my_rank = 0;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const unsigned int mask = __ballot_sync(0xffffffffu, cls == c);
-        if (!mask) continue;
-        const int leader = __ffs(mask) - 1;
-        unsigned int base = 0;
-        if ((int)lane == leader) base = atomicAdd(counts + c, (unsigned int)__popc(mask));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (cls == c) lists[(int64_t)c * n_slots + base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)a;
+        if (lane == 0) s_wcount[warp][c] = (unsigned int)__popc(mask);
+        if (cls == c) my_rank = (unsigned int)__popc(mask & ((1u << lane) - 1u));
     }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned int tot = 0;
+        for (int w = 0; w < 8; w++) { const unsigned int t = s_wcount[w][threadIdx.x]; s_wcount[w][threadIdx.x] = tot; tot += t; }
+        s_base[threadIdx.x] = tot ? atomicAdd(counts + threadIdx.x, tot) : 0u;
+    }
+    __syncthreads();
+    if (cls >= 0) lists[(int64_t)cls * n_slots + s_base[cls] + s_wcount[warp][cls] + my_rank] = (int32_t)a;
 }
 
 // ---- bitonic sort of maxT (m doubles in [0,1]; padded with +inf to a power of two) -----------------
