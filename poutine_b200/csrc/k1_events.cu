@@ -23,6 +23,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "pb_internal.h"
 
 struct K1Params {
@@ -292,10 +294,11 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
 }
 
 // ---- per-site event counters -------------------------------------------------------------------
-__global__ void k1_count_events_kernel(const raw_event_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ node_sample,
-                                       uint32_t* __restrict__ cnt) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// the raw list's length lives on the device (K1's cursor, clamped to the buffer): no host round trip before the tail
+__global__ void k1_count_events_kernel(const raw_event_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
+                                       const int32_t* __restrict__ node_sample, uint32_t* __restrict__ cnt) {
+    const int64_t n = min((int64_t)*cursor, raw_cap);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const raw_event_t e = raw[i];
     const uint32_t site = (uint32_t)e, hi = (uint32_t)(e >> 32);
     const uint32_t base = (hi >> 29) & 3u, node = hi & PB_EV_NODE_MASK;
@@ -304,6 +307,7 @@ __global__ void k1_count_events_kernel(const raw_event_t* __restrict__ raw, int6
     if (hi & 0x80000000u) {
         atomicAdd(c + 4 + base, 1u);
         if (node_sample[node] >= 0) atomicAdd(c + 8 + base, 1u);
+    }
     }
 }
 
@@ -515,29 +519,31 @@ __global__ void k1_scatter_sites_kernel(int64_t S, const uint8_t* __restrict__ f
     }
 }
 
-__global__ void k1_scatter_events_kernel(const raw_event_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ node_sample,
-                                         const uint8_t* __restrict__ flags, const uint64_t* __restrict__ scan,
-                                         const uint64_t* __restrict__ scan_in, const pb_site_out* __restrict__ sites,
-                                         const AlleleMeta* __restrict__ alleles, uint32_t* __restrict__ cursor, int32_t* __restrict__ csr) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const raw_event_t e = raw[i];
-    const uint32_t hi = (uint32_t)(e >> 32);
-    if (!(hi & 0x80000000u)) return;                 // extant (leaf) events only (EXTANT_NODES_ONLY, HC.java:173)
-    const int32_t smp = node_sample[hi & PB_EV_NODE_MASK];
-    if (smp < 0) return;                              // leaf without a pheno row: never tallied (HC.java:3743)
-    const uint32_t site = (uint32_t)e;
-    if (!(scan_in[site] >> 38)) return;
-    const uint8_t fl = flags[site];
-    const uint32_t base = (hi >> 29) & 3u;
-    const int a = (base == ((fl >> PB_SF_A1_CODE_SHIFT) & 3u)) ? 0 : 1;
-    if (!(fl & (a == 0 ? PB_SF_A1_USE : PB_SF_A2_USE))) return;
-    // bucket emptied by the <2 rule?  (in_use with min_hcount 0 keeps n = 0)
-    const pb_site_out so = sites[site];
-    if ((a == 0 ? so.a1_count : so.a2_count) < 2) return;
-    const int64_t slot = 2 * (int64_t)(scan[site] >> 38) + a;
-    const uint32_t k = atomicAdd(cursor + slot, 1u);
-    csr[alleles[slot].off + k] = smp;
+__global__ void k1_scatter_events_kernel(const raw_event_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
+                                         const int32_t* __restrict__ node_sample, const uint8_t* __restrict__ flags,
+                                         const uint64_t* __restrict__ scan, const uint64_t* __restrict__ scan_in,
+                                         const pb_site_out* __restrict__ sites, const AlleleMeta* __restrict__ alleles,
+                                         uint32_t* __restrict__ csr_cursor, int32_t* __restrict__ csr) {
+    const int64_t n = min((int64_t)*cursor, raw_cap);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const raw_event_t e = raw[i];
+        const uint32_t hi = (uint32_t)(e >> 32);
+        if (!(hi & 0x80000000u)) continue;               // extant (leaf) events only (EXTANT_NODES_ONLY, HC.java:173)
+        const int32_t smp = node_sample[hi & PB_EV_NODE_MASK];
+        if (smp < 0) continue;                            // leaf without a pheno row: never tallied (HC.java:3743)
+        const uint32_t site = (uint32_t)e;
+        if (!(scan_in[site] >> 38)) continue;
+        const uint8_t fl = flags[site];
+        const uint32_t base = (hi >> 29) & 3u;
+        const int a = (base == ((fl >> PB_SF_A1_CODE_SHIFT) & 3u)) ? 0 : 1;
+        if (!(fl & (a == 0 ? PB_SF_A1_USE : PB_SF_A2_USE))) continue;
+        // bucket emptied by the <2 rule?  (in_use with min_hcount 0 keeps n = 0)
+        const pb_site_out so = sites[site];
+        if ((a == 0 ? so.a1_count : so.a2_count) < 2) continue;
+        const int64_t slot = 2 * (int64_t)(scan[site] >> 38) + a;
+        const uint32_t k = atomicAdd(csr_cursor + slot, 1u);
+        csr[alleles[slot].off + k] = smp;
+    }
 }
 
 // =================================================================================================
@@ -565,73 +571,65 @@ int pbk_events(pb_ctx* ctx) {
     return PB_OK;
 }
 
-int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts) {
+// Everything after the K1 sweep, enqueued without a host round trip: the raw list length, S_inf and E stay on the
+// device, the compaction outputs are sized for the worst case (every site informative, every raw event extant).
+// One readback at the end: class counters, n_max, #alleles in use, scan totals, K1's cursor.
+int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out) {
     const int64_t S = ctx->S;
     const int T = 256;
-    PB_CUDA(cudaMemsetAsync(ctx->d_cnt, 0, (size_t)S * PB_CNT_STRIDE * 4, ctx->stream));
-    PB_CUDA(cudaMemsetAsync(ctx->d_class_counts, 0, 16 * 8, ctx->stream));
-    if (ctx->n_raw > 0) {
-        k1_count_events_kernel<<<(unsigned)((ctx->n_raw + T - 1) / T), T, 0, ctx->stream>>>(ctx->d_raw, ctx->n_raw, ctx->d_node_sample, ctx->d_cnt);
-        ctx->tm.n_launches += 1;
+    cudaStream_t st = ctx->stream;
+    if (S > ctx->inf_cap) {
+        cudaFree(ctx->d_inf_site); cudaFree(ctx->d_alleles); cudaFree(ctx->d_csr_cursor); cudaFree(ctx->d_pobs); cudaFree(ctx->d_r);
+        ctx->d_inf_site = nullptr; ctx->d_alleles = nullptr; ctx->d_csr_cursor = nullptr; ctx->d_pobs = nullptr; ctx->d_r = nullptr;
+        PB_CUDA(cudaMalloc(&ctx->d_inf_site, (size_t)S * 4));
+        PB_CUDA(cudaMalloc(&ctx->d_alleles, (size_t)S * 2 * sizeof(AlleleMeta)));
+        PB_CUDA(cudaMalloc(&ctx->d_csr_cursor, (size_t)S * 2 * 4));
+        PB_CUDA(cudaMalloc(&ctx->d_pobs, (size_t)S * 2 * 8));
+        PB_CUDA(cudaMalloc(&ctx->d_r, (size_t)S * 2 * 4));
+        ctx->inf_cap = S;
     }
-    k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), 4), 128, 0, ctx->stream>>>(ctx->d_census, ctx->n_flush, ctx->W,
-                                                                                              ctx->d_census_total);
+    if (ctx->raw_cap > ctx->csr_cap) {
+        cudaFree(ctx->d_csr); ctx->d_csr = nullptr;
+        PB_CUDA(cudaMalloc(&ctx->d_csr, (size_t)ctx->raw_cap * 4));
+        ctx->csr_cap = ctx->raw_cap;
+    }
+    const unsigned ev_blocks = (unsigned)std::min<int64_t>((ctx->raw_cap + T - 1) / T, (int64_t)ctx->sm_count * 16);
+    PB_CUDA(cudaMemsetAsync(ctx->d_cnt, 0, (size_t)S * PB_CNT_STRIDE * 4, st));
+    PB_CUDA(cudaMemsetAsync(ctx->d_class_counts, 0, 16 * 8, st));
+    PB_CUDA(cudaMemsetAsync(ctx->d_csr_cursor, 0, (size_t)S * 2 * 4, st));
+    k1_count_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_cnt);
+    k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), 4), 128, 0, st>>>(ctx->d_census, ctx->n_flush, ctx->W, ctx->d_census_total);
     int kt_used = 1;
     while ((1ll << kt_used) <= (int64_t)ctx->L) kt_used++;
-    k1_finalize_kernel<<<(unsigned)((S + T - 1) / T), T, 0, ctx->stream>>>(
+    k1_finalize_kernel<<<(unsigned)((S + T - 1) / T), T, 0, st>>>(
         ctx->d_census_total, kt_used, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->d_cnt, ctx->cfg.min_hcount,
         ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan /* reused as scan input */, ctx->d_class_counts);
-    ctx->tm.n_launches += 2;
+    ctx->tm.n_launches += 3;
     PB_CUDA(cudaGetLastError());
     // scan: d_site_scan (input) -> d_site_scan_out.  We keep input in the first half of a 2*S buffer.
     uint64_t* scan_in = ctx->d_site_scan;
     uint64_t* scan_out = ctx->d_site_scan + S;
     int rc = pbk_exclusive_scan_u64(ctx, scan_in, scan_out, S, (uint64_t*)(ctx->d_class_counts + 7));
     if (rc) return rc;
+    k1_scatter_sites_kernel<<<(unsigned)((S + T - 1) / T), T, 0, st>>>(S, ctx->d_site_flags, scan_out, scan_in, ctx->d_cnt, ctx->d_sites,
+                                                                      ctx->d_inf_site, ctx->d_alleles, ctx->d_class_counts);
+    k1_scatter_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
+                                                     scan_out, scan_in, ctx->d_sites, ctx->d_alleles, ctx->d_csr_cursor, ctx->d_csr);
+    ctx->tm.n_launches += 2;
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaMemcpyAsync(ctx->d_class_counts + 8, ctx->d_raw_cursor, 8, cudaMemcpyDeviceToDevice, st));
     unsigned long long h[16];
-    PB_CUDA(cudaMemcpyAsync(h, ctx->d_class_counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(cudaMemcpyAsync(h, ctx->d_class_counts, sizeof(h), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    PB_CUDA(cudaGetLastError());
+    *cursor_out = h[8];
     ctx->S_inf = (int64_t)(h[7] >> 38);
     ctx->E = (int64_t)(h[7] & ((1ull << 38) - 1));
+    ctx->n_max = (int32_t)h[5];
+    ctx->A_inuse = (int64_t)h[6];
     if (counts) {
         counts->n_no_allele = (int64_t)h[0]; counts->n_mono = (int64_t)h[1]; counts->n_bi = (int64_t)h[2];
-        counts->n_tri = (int64_t)h[3]; counts->n_quad = (int64_t)h[4]; counts->n_raw_events = ctx->n_raw;
-    }
-    // (re)allocate compaction outputs
-    if (ctx->S_inf > ctx->inf_cap) {
-        cudaFree(ctx->d_inf_site); cudaFree(ctx->d_alleles); cudaFree(ctx->d_csr_cursor); cudaFree(ctx->d_pobs); cudaFree(ctx->d_r);
-        ctx->d_inf_site = nullptr; ctx->d_alleles = nullptr; ctx->d_csr_cursor = nullptr; ctx->d_pobs = nullptr; ctx->d_r = nullptr;
-        const int64_t cap = ctx->S_inf + ctx->S_inf / 8 + 1024;
-        PB_CUDA(cudaMalloc(&ctx->d_inf_site, (size_t)cap * 4));
-        PB_CUDA(cudaMalloc(&ctx->d_alleles, (size_t)cap * 2 * sizeof(AlleleMeta)));
-        PB_CUDA(cudaMalloc(&ctx->d_csr_cursor, (size_t)cap * 2 * 4));
-        PB_CUDA(cudaMalloc(&ctx->d_pobs, (size_t)cap * 2 * 8));
-        PB_CUDA(cudaMalloc(&ctx->d_r, (size_t)cap * 2 * 4));
-        ctx->inf_cap = cap;
-    }
-    if (ctx->E > ctx->csr_cap) {
-        cudaFree(ctx->d_csr); ctx->d_csr = nullptr;
-        const int64_t cap = ctx->E + ctx->E / 8 + 1024;
-        PB_CUDA(cudaMalloc(&ctx->d_csr, (size_t)cap * 4));
-        ctx->csr_cap = cap;
-    }
-    ctx->n_max = 0; ctx->A_inuse = 0;
-    if (ctx->S_inf > 0) {
-        PB_CUDA(cudaMemsetAsync(ctx->d_csr_cursor, 0, (size_t)ctx->S_inf * 2 * 4, ctx->stream));
-        k1_scatter_sites_kernel<<<(unsigned)((S + T - 1) / T), T, 0, ctx->stream>>>(S, ctx->d_site_flags, scan_out, scan_in, ctx->d_cnt,
-                                                                                   ctx->d_sites, ctx->d_inf_site, ctx->d_alleles, ctx->d_class_counts);
-        ctx->tm.n_launches += 1;
-        if (ctx->n_raw > 0) {
-            k1_scatter_events_kernel<<<(unsigned)((ctx->n_raw + T - 1) / T), T, 0, ctx->stream>>>(
-                ctx->d_raw, ctx->n_raw, ctx->d_node_sample, ctx->d_site_flags, scan_out, scan_in, ctx->d_sites, ctx->d_alleles,
-                ctx->d_csr_cursor, ctx->d_csr);
-            ctx->tm.n_launches += 1;
-        }
-        PB_CUDA(cudaGetLastError());
-        PB_CUDA(cudaMemcpyAsync(h, ctx->d_class_counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->n_max = (int32_t)h[5];
-        ctx->A_inuse = (int64_t)h[6];
+        counts->n_tri = (int64_t)h[3]; counts->n_quad = (int64_t)h[4]; counts->n_raw_events = (int64_t)h[8];
     }
     return PB_OK;
 }

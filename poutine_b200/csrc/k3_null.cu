@@ -426,7 +426,8 @@ __device__ __forceinline__ unsigned int sweep_upto7_cand(const K3Params& p, cons
 // work list 1: short lists (n < 8) on the tight path.  Few registers -> many resident warps: the sweep is bound by the
 // latency of the label-matrix loads.  MISS = the pheno file has missing labels.
 template <bool MISS>
-__global__ void __launch_bounds__(K3_THREADS, MISS ? 4 : 5) k3_count_tight_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
+__global__ void __launch_bounds__(K3_THREADS, MISS ? 4 : 5) k3_count_tight_kernel(const K3Params p, const int32_t* __restrict__ list, const unsigned int* __restrict__ n_list_dev) {
+    const int64_t n_list = *n_list_dev;   // list lengths stay on the device (k4_classify_kernel): no host round trip
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
@@ -454,7 +455,8 @@ __global__ void __launch_bounds__(K3_THREADS, MISS ? 4 : 5) k3_count_tight_kerne
 
 // work list 3: short lists with possible maxT candidates (tight sweep + scalar candidate look-ups) or that need the
 // general path (non-monotone table rows, missing labels with candidates, test hooks)
-__global__ void __launch_bounds__(K3_THREADS, 2) k3_count_small_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
+__global__ void __launch_bounds__(K3_THREADS, 2) k3_count_small_kernel(const K3Params p, const int32_t* __restrict__ list, const unsigned int* __restrict__ n_list_dev) {
+    const int64_t n_list = *n_list_dev;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
@@ -476,7 +478,8 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_count_small_kernel(const K3P
 
 // work list C: the long-list tail (n >= 8) and whatever needs the general path there.  These are few and long:
 // a whole thread block shares one allele (thread = word, stride 256) so that no single warp becomes the long pole.
-__global__ void __launch_bounds__(K3_THREADS, 1) k3_count_large_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list) {
+__global__ void __launch_bounds__(K3_THREADS, 1) k3_count_large_kernel(const K3Params p, const int32_t* __restrict__ list, const unsigned int* __restrict__ n_list_dev) {
+    const int64_t n_list = *n_list_dev;
     const int lane = threadIdx.x & 31;
     const double tau = *p.tau;
     for (int64_t i = blockIdx.x; i < n_list; i += gridDim.x) {
@@ -511,10 +514,10 @@ __global__ void k3_colpop_kernel(const uint64_t* __restrict__ Xc, const uint64_t
         colpop[P + blockIdx.x] = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
     }
 }
-__global__ void k3_trivial_kernel(const K3Params p, const int32_t* __restrict__ list, int64_t n_list, const uint32_t* __restrict__ colpop,
-                                  int32_t P) {
+__global__ void k3_trivial_kernel(const K3Params p, const int32_t* __restrict__ list, const unsigned int* __restrict__ n_list_dev,
+                                  const uint32_t* __restrict__ colpop, int32_t P) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_list) return;
+    if (i >= (int64_t)*n_list_dev) return;
     const int64_t slot = list[i];
     const AlleleMeta m = p.alleles[slot];
     unsigned int rc = 0;
@@ -545,9 +548,13 @@ __global__ void k3_collect_fallback_kernel(const unsigned long long* __restrict_
     if (!(v <= *tau)) list[atomicAdd(count, 1u)] = (int32_t)i;
 }
 
-__global__ void __launch_bounds__(256) k3_fallback_kernel(const K3Params p, const int32_t* __restrict__ list) {
+__global__ void __launch_bounds__(256) k3_fallback_kernel(const K3Params p, const int32_t* __restrict__ list, const unsigned int* __restrict__ count,
+                                                          unsigned long long* __restrict__ total) {
     __shared__ double smin[256];
-    const int64_t rl = list[blockIdx.x];
+    const unsigned int n = *count;                      // device-side list length: the kernel is always launched
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(total, (unsigned long long)n);
+    for (unsigned int li = blockIdx.x; li < n; li += gridDim.x) {
+    const int64_t rl = list[li];
     const int64_t word = rl >> 6;
     const int b = (int)(rl & 63);
     double best = __longlong_as_double(0x7FF0000000000000ll);
@@ -571,6 +578,8 @@ __global__ void __launch_bounds__(256) k3_fallback_kernel(const K3Params p, cons
         __syncthreads();
     }
     if (threadIdx.x == 0) p.maxT[p.rep_base + rl] = (unsigned long long)__double_as_longlong(smin[0]);
+    __syncthreads();
+    }
 }
 
 __global__ void fill_u64_kernel(unsigned long long* p, int64_t n, unsigned long long v) {
@@ -592,6 +601,12 @@ static int ensure(pb_ctx* ctx, void** ptr, int64_t* cap, int64_t need_bytes) {
     }
     *cap = bytes;
     return PB_OK;
+}
+
+__global__ void k3_headstart_kernel(unsigned int ns) {
+    const unsigned long long t0 = clock64();
+    // ~2 cycles per ns at 1.9 GHz; __nanosleep keeps the SM slot idle instead of spinning hot
+    while (clock64() - t0 < 2ull * ns) __nanosleep(1000);
 }
 
 // replicate tiling of the label matrices + their buffers
@@ -673,9 +688,23 @@ int pbk_pregen_labels(pb_ctx* ctx) {
     } else {
         PB_CUDA(cudaEventRecord(ctx->ev_k1_done, ctx->stream));
         PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_k1_done, 0));
+        PB_CUDA(cudaEventRecord(ctx->ev_gen_started, ctx->stream2));
     }
     if ((rc = k3_launch_philox(ctx, pl, 0, nr, ctx->stream2, 0))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev_gen_done, ctx->stream2));
+    // The generator is ONE wave of long-running blocks: it finishes ~0.65 ms after its LAST block starts, and the main
+    // stream's tail kernels (queued right behind K1) would otherwise win the race for the SM slots K1 frees.  Hold the
+    // main stream for a few microseconds behind the K1 dependency so that the generator's blocks become resident first;
+    // the short tail kernels then fill in around them.  (Measured at C2: 2.76 ms per step without the head start, 2.44 ms with 3-12 us; PB_GEN_HEADSTART_US tunes it.)
+    {
+        int us = 8;
+        if (const char* e = getenv("PB_GEN_HEADSTART_US")) us = atoi(e);
+        if (us > 0 && !getenv("PB_PREGEN_EARLY")) {
+            PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_gen_started, 0));
+            k3_headstart_kernel<<<1, 1, 0, ctx->stream>>>((unsigned)us * 1000u);
+            ctx->tm.n_launches += 1;
+        }
+    }
     ctx->pregen_valid = true;
     ctx->pregen_tile = pl.tile;
     return PB_OK;
@@ -690,7 +719,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
 
     // ---- K2 observed tallies
     PB_CUDA(cudaEventRecord(ctx->ev[2], st));
-    k2_tally_kernel<<<(unsigned)((n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_csr, ctx->d_label);
+    k2_tally_kernel<<<(unsigned)std::max<int64_t>(1, (n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_csr, ctx->d_label);
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaEventRecord(ctx->ev[3], st));
 
@@ -725,13 +754,22 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
         if ((rc = ensure(ctx, &pl, &ctx->fb_cap, (tile + 256) * 4))) { ctx->d_fb_reps = nullptr; return rc; }
         ctx->d_fb_reps = (int32_t*)pl;
     }
-    float ms_gen = 0, ms_cnt = 0, ms_fb = 0;
+    // No host round trip inside the loop: list lengths, the fallback list and its length stay on the device; buffer
+    // reuse between the two streams is ordered with events.  (Replay mode uploads each tile's permutations.)
     ctx->tm.n_maxt_fallback_reps = 0;
+    const unsigned int* lc = ctx->d_lcount;
+    int64_t bps = 32;
+    if (const char* e = getenv("PB_K3_BLOCKS_PER_SM")) bps = atoll(e);
+    const int64_t warps_per_block = K3_THREADS / 32;
+    const unsigned tight_blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * bps, (n_slots + warps_per_block - 1) / warps_per_block));
+    const unsigned small_blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 8, (n_slots + warps_per_block - 1) / warps_per_block));
+    const unsigned large_blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 4, n_slots));
+    PB_CUDA(cudaEventRecord(ctx->ev[5], st));
+    bool first_gen_timed = false;
     for (int64_t base = 0; base < m; base += tile) {
         const int64_t nr = (m - base < tile) ? (m - base) : tile;
         const unsigned gblocks = (unsigned)((nr + GEN_THREADS - 1) / GEN_THREADS);
         const int buf = (pl.nbuf == 2) ? (int)((base / tile) & 1) : 0;
-        PB_CUDA(cudaEventRecord(ctx->ev[5], st));
         if (ctx->cfg.mode == PB_MODE_REPLAY) {
             const int64_t bytes = nr * (int64_t)ctx->P * 4;
             int64_t cap = ctx->perms_cap;
@@ -746,6 +784,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
                 k3_gen_kernel<1, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
                                                                         ctx->d_perms, (uint32_t*)ctx->d_Xcase, nullptr, Rw32);
             ctx->tm.n_launches += 1;
+            // replay_perms is caller-owned pageable memory: the copy above is staged synchronously by the runtime
         } else if (base == 0 && ctx->pregen_valid && ctx->pregen_tile == tile) {
             PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_gen_done, 0));   // tile 0 was generated alongside the K1 tail
         } else if (base > 0 && pl.nbuf == 2) {
@@ -754,14 +793,15 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             if ((rc = k3_launch_philox(ctx, pl, base, nr, st, buf))) return rc;
         }
         if (pl.nbuf == 2 && base + tile < m) {
-            // next tile into the other buffer (its last reader, the count of tile t-1, has completed: the host
-            // synchronised on it below), concurrently with this tile's count
+            // next tile into the other buffer, on the second stream, concurrently with this tile's count; the buffer's
+            // last reader was the count of the previous tile
             const int64_t nb = base + tile, nnr = (m - nb < tile) ? (m - nb) : tile;
+            if (base > 0) PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_cnt_b[buf ^ 1], 0));
             if ((rc = k3_launch_philox(ctx, pl, nb, nnr, ctx->stream2, buf ^ 1))) return rc;
             PB_CUDA(cudaEventRecord(ctx->ev_gen_b[buf ^ 1], ctx->stream2));
         }
         ctx->pregen_valid = false;
-        PB_CUDA(cudaEventRecord(ctx->ev[6], st));
+        if (!first_gen_timed) { PB_CUDA(cudaEventRecord(ctx->ev[6], st)); first_gen_timed = true; }
 
         // count in L2-sized column tiles of the generated matrix
         for (int64_t cb = 0; cb < nr; cb += pl.ctile) {
@@ -773,55 +813,25 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             p.Xm = has_miss ? ctx->d_Xmiss + buf * pl.buf_words + cb / 64 : nullptr;
             p.Rw = Rw;
             p.rep_base = base + cb; p.n_reps = cnr; p.r = ctx->d_r; p.maxT = ctx->d_maxT;
-            const int64_t nA = ctx->n_work[0], nB = ctx->n_work[1], nC = ctx->n_work[2], nG = ctx->n_work[3];
             const int64_t words = (cnr + 63) / 64;
-            int64_t bps = 32;
-            if (const char* e = getenv("PB_K3_BLOCKS_PER_SM")) bps = atoll(e);
-            if (nA > 0) {
-                k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(p.Xc, p.Xm, Rw, words, ctx->P, ctx->d_colpop);
-                k3_trivial_kernel<<<(unsigned)((nA + T - 1) / T), T, 0, st>>>(p, ctx->d_work, nA, ctx->d_colpop, ctx->P);
-                ctx->tm.n_launches += 2;
-            }
-            if (nB > 0) {
-                int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * bps, (nB + (K3_THREADS / 32) - 1) / (K3_THREADS / 32));
-                if (has_miss) k3_count_tight_kernel<true><<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, nB);
-                else k3_count_tight_kernel<false><<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, nB);
-                ctx->tm.n_launches += 1;
-            }
-            if (nG > 0) {
-                int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * 8, (nG + (K3_THREADS / 32) - 1) / (K3_THREADS / 32));
-                k3_count_small_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + 3 * n_slots, nG);
-                ctx->tm.n_launches += 1;
-            }
-            if (nC > 0) {
-                int64_t blocks = std::min<int64_t>((int64_t)ctx->sm_count * 4, nC);
-                k3_count_large_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), K3_THREADS, 0, st>>>(p, ctx->d_work + 2 * n_slots, nC);
-                ctx->tm.n_launches += 1;
-            }
-            // fallback for uncertified replicates
+            k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(p.Xc, p.Xm, Rw, words, ctx->P, ctx->d_colpop);
+            k3_trivial_kernel<<<(unsigned)std::max<int64_t>(1, (n_slots + T - 1) / T), T, 0, st>>>(p, ctx->d_work, lc + 0, ctx->d_colpop, ctx->P);
+            if (has_miss) k3_count_tight_kernel<true><<<tight_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, lc + 1);
+            else k3_count_tight_kernel<false><<<tight_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, lc + 1);
+            k3_count_small_kernel<<<small_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + 3 * n_slots, lc + 3);
+            k3_count_large_kernel<<<large_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + 2 * n_slots, lc + 2);
+            // replicates whose minimum was not certified by a candidate are recomputed exactly
             PB_CUDA(cudaMemsetAsync(ctx->d_fb_count, 0, 4, st));
             k3_collect_fallback_kernel<<<(unsigned)((cnr + T - 1) / T), T, 0, st>>>(ctx->d_maxT, p.rep_base, cnr, ctx->d_tau, ctx->d_fb_reps,
                                                                                  ctx->d_fb_count);
-            ctx->tm.n_launches += 1;
-            unsigned int n_fb = 0;
-            PB_CUDA(cudaMemcpyAsync(&n_fb, ctx->d_fb_count, 4, cudaMemcpyDeviceToHost, st));
-            PB_CUDA(cudaStreamSynchronize(st));
-            if (n_fb) {
-                k3_fallback_kernel<<<n_fb, 256, 0, st>>>(p, ctx->d_fb_reps);
-                ctx->tm.n_launches += 1;
-                ctx->tm.n_maxt_fallback_reps += n_fb;
-            }
+            k3_fallback_kernel<<<(unsigned)std::min<int64_t>(cnr, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(p, ctx->d_fb_reps, ctx->d_fb_count,
+                                                                                                           ctx->d_fb_total);
+            ctx->tm.n_launches += 7;
         }
-        PB_CUDA(cudaEventRecord(ctx->ev[7], st));
-        PB_CUDA(cudaEventRecord(ctx->ev[8], st));
-        PB_CUDA(cudaStreamSynchronize(st));
+        if (pl.nbuf == 2) PB_CUDA(cudaEventRecord(ctx->ev_cnt_b[buf], st));
         PB_CUDA(cudaGetLastError());
-        float t;
-        cudaEventElapsedTime(&t, ctx->ev[5], ctx->ev[6]); ms_gen += t;
-        cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]); ms_cnt += t;
-        cudaEventElapsedTime(&t, ctx->ev[7], ctx->ev[8]); ms_fb += t;   // (the fallback pass now runs inside the count tiles)
     }
-    ctx->tm.ms_null_gen = ms_gen; ctx->tm.ms_null_count = ms_cnt; ctx->tm.ms_null_fallback = ms_fb;
+    PB_CUDA(cudaEventRecord(ctx->ev[7], st));
 
     // ---- the one collective: all-reduce(min) of maxT over site shards
     PB_CUDA(cudaEventRecord(ctx->ev[9], st));
@@ -833,12 +843,21 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     // ---- K4
     if ((rc = pbk_pvalues(ctx))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev[11], st));
+    struct { unsigned long long nf; unsigned int lc[4]; unsigned long long fb; } hb;   // layout of the scratch block in pbk_thresholds
+    PB_CUDA(cudaMemcpyAsync(&hb, ctx->d_nfast, sizeof(hb), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
+    PB_CUDA(cudaGetLastError());
     float t;
     cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]); ctx->tm.ms_tally = t;
     cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4]); ctx->tm.ms_ptable = t;
+    cudaEventElapsedTime(&t, ctx->ev[5], ctx->ev[6]); ctx->tm.ms_null_gen = t;      // first tile, as seen by the main stream
+    cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]); ctx->tm.ms_null_count = t;    // everything after it (counts, fallback, later tiles)
+    ctx->tm.ms_null_fallback = 0;
     cudaEventElapsedTime(&t, ctx->ev[9], ctx->ev[10]); ctx->tm.ms_allreduce = t;
     cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[11]); ctx->tm.ms_pvalues = t;
     cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[11]); ctx->tm.ms_assoc_total = t;
+    ctx->tm.n_fast_alleles = (int64_t)hb.nf;
+    for (int c = 0; c < 4; c++) ctx->n_work[c] = (int64_t)hb.lc[c];
+    ctx->tm.n_maxt_fallback_reps = (int64_t)hb.fb;
     return PB_OK;
 }

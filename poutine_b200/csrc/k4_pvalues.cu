@@ -307,21 +307,25 @@ int pbk_thresholds(pb_ctx* ctx) {
     const int32_t n_max = ctx->n_max;
     cudaStream_t st = ctx->stream;
     int rc;
-    // one scratch allocation: [expect 64 f64][tau f64][n_fast u64][list counts 4 x u32][ktau i32 x (n_max+1)][hist u32 x (n_max+1)]
+    // one scratch allocation: [expect 64 f64][tau f64][n_fast u64][list counts 4 x u32][fallback total u64]
+    //                         [ktau i32 x (n_max+1)][hist u32 x (n_max+1)]
     const int64_t n1 = (int64_t)n_max + 1;
-    const int64_t need = TAU_LEVELS * 8 + 8 + 8 + 16 + n1 * 4 + n1 * 4;
+    const int64_t need = TAU_LEVELS * 8 + 8 + 8 + 16 + 8 + n1 * 4 + n1 * 4;
     if ((rc = ensure_bytes(ctx, &ctx->d_thr, &ctx->thr_cap, need))) return rc;
     char* base = (char*)ctx->d_thr;
     double* d_expect = (double*)base;
     ctx->d_tau = (double*)(base + TAU_LEVELS * 8);
     unsigned long long* d_nfast = (unsigned long long*)(base + TAU_LEVELS * 8 + 8);
     unsigned int* d_lcount = (unsigned int*)(base + TAU_LEVELS * 8 + 16);
-    ctx->d_ktau = (int32_t*)(base + TAU_LEVELS * 8 + 32);
-    unsigned int* d_hist = (unsigned int*)(base + TAU_LEVELS * 8 + 32 + n1 * 4);
+    ctx->d_nfast = d_nfast;                 // {n_fast u64, list counts 4 x u32, fallback total u64}: read back once, at the end of pbk_assoc
+    ctx->d_lcount = d_lcount;
+    ctx->d_fb_total = (unsigned long long*)(base + TAU_LEVELS * 8 + 32);
+    ctx->d_ktau = (int32_t*)(base + TAU_LEVELS * 8 + 40);
+    unsigned int* d_hist = (unsigned int*)(base + TAU_LEVELS * 8 + 40 + n1 * 4);
     PB_CUDA(cudaMemsetAsync(ctx->d_thr, 0, (size_t)need, st));
     const int T = 256;
     const int force_general = (ctx->cfg.flags & PB_FLAG_FORCE_GENERAL_NULL) ? 1 : 0;
-    k4_observed_kernel<<<(unsigned)((n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ptable, ctx->d_pobs, d_hist,
+    k4_observed_kernel<<<(unsigned)std::max<int64_t>(1, (n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ptable, ctx->d_pobs, d_hist,
                                                                       force_general, ctx->n_miss > 0 ? 1 : 0, d_nfast);
     k4_tau_expect_kernel<<<TAU_LEVELS, 256, 0, st>>>(ctx->d_ptable, d_hist, n_max, d_expect);
     k4_tau_pick_kernel<<<1, 1, 0, st>>>(d_expect, 16.0, ctx->cfg.maxt_tau, ctx->d_tau);
@@ -332,16 +336,10 @@ int pbk_thresholds(pb_ctx* ctx) {
         ctx->work_cap = n_slots + n_slots / 8 + 1024;
         PB_CUDA(cudaMalloc(&ctx->d_work, (size_t)ctx->work_cap * 4 * 4));
     }
-    if (n_slots > 0)
-        k4_classify_kernel<<<(unsigned)((n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ktau, ctx->n_miss > 0 ? 1 : 0,
+    k4_classify_kernel<<<(unsigned)std::max<int64_t>(1, (n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ktau, ctx->n_miss > 0 ? 1 : 0,
                                                                           ctx->d_work, d_lcount);
     ctx->tm.n_launches += 5;
     PB_CUDA(cudaGetLastError());
-    struct { unsigned long long nf; unsigned int lc[4]; } h;
-    PB_CUDA(cudaMemcpyAsync(&h, d_nfast, sizeof(h), cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaStreamSynchronize(st));
-    ctx->tm.n_fast_alleles = (int64_t)h.nf;
-    for (int c = 0; c < 4; c++) ctx->n_work[c] = (int64_t)h.lc[c];
     return PB_OK;
 }
 
@@ -375,7 +373,7 @@ int pbk_pvalues(pb_ctx* ctx) {
         if ((rc = ensure_bytes(ctx, &ps, &cap, ctx->S_inf * (int64_t)sizeof(pb_stat_out)))) { ctx->d_stats = nullptr; ctx->stats_cap = 0; return rc; }
         ctx->d_stats = (pb_stat_out*)ps; ctx->stats_cap = cap / (int64_t)sizeof(pb_stat_out);
     }
-    k4_stats_kernel<<<(unsigned)((ctx->S_inf + T - 1) / T), T, 0, st>>>(ctx->d_inf_site, ctx->S_inf, ctx->d_alleles, ctx->d_pobs, ctx->d_r,
+    k4_stats_kernel<<<(unsigned)std::max<int64_t>(1, (ctx->S_inf + T - 1) / T), T, 0, st>>>(ctx->d_inf_site, ctx->S_inf, ctx->d_alleles, ctx->d_pobs, ctx->d_r,
                                                                       ctx->d_maxT_sorted, m, ctx->cfg.site_offset, ctx->d_stats);
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());

@@ -58,16 +58,20 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
     };
     if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("cudaSetDevice", e);
     {
-        // the main stream outranks the label-generation stream: when both have blocks pending, the path's own kernels go first
+        // the label generator is the long pole between K1 and the replicate counts (it is released by an event when K1
+        // has finished): its blocks go first, the short tail kernels of the main stream fill in around them
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
-        if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if (getenv("PB_GEN_LOW_PRIORITY")) std::swap(prio_lo, prio_hi);   // experiment knob
+        if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
     }
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_k1_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_gen_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_gen_started, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     for (auto& ev : ctx->ev_gen_b) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    for (auto& ev : ctx->ev_cnt_b) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_raw_cursor, 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_class_counts, 16 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_fb_count, 4)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -84,7 +88,9 @@ extern "C" void pb_destroy(pb_ctx* ctx) {
     free_all(ctx);
     if (ctx->ev_k1_done) cudaEventDestroy(ctx->ev_k1_done);
     if (ctx->ev_gen_done) cudaEventDestroy(ctx->ev_gen_done);
+    if (ctx->ev_gen_started) cudaEventDestroy(ctx->ev_gen_started);
     for (auto& ev : ctx->ev_gen_b) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_cnt_b) if (ev) cudaEventDestroy(ev);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -376,18 +382,15 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
         if ((rc = pbk_events(ctx))) return rc;
         if (attempt == 0 && (rc = pbk_pregen_labels(ctx))) return rc;
         unsigned long long cur = 0;
-        PB_CUDA(cudaMemcpyAsync(&cur, ctx->d_raw_cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(cudaStreamSynchronize(ctx->stream));
-        PB_CUDA(cudaGetLastError());
+        if ((rc = pbk_finalize_events(ctx, counts, &cur))) return rc;   // the whole tail, one host round trip at its end
         if ((int64_t)cur <= ctx->raw_cap) { ctx->n_raw = (int64_t)cur; break; }
-        // event list larger than the buffer (dense / adversarial input): grow to the exact need and redo
+        // event list larger than the buffer (dense / adversarial input): grow to the exact need and redo the pass
         cudaFree(ctx->d_raw); ctx->d_raw = nullptr;
         ctx->raw_cap = (int64_t)cur + (int64_t)cur / 16 + 1024;
         cudaError_t e = cudaMalloc(&ctx->d_raw, (size_t)ctx->raw_cap * sizeof(raw_event_t));
         if (e != cudaSuccess) { ctx->err = "pb_run_events: cannot allocate the event list"; ctx->raw_cap = 0; return PB_ERR_OOM; }
         if (attempt == 2) FAIL(ctx, PB_ERR_CUDA, "pb_run_events: event list kept overflowing");
     }
-    if ((rc = pbk_finalize_events(ctx, counts))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev[13], ctx->stream));
     if (per_site) PB_CUDA(cudaMemcpyAsync(per_site, ctx->d_sites, (size_t)ctx->S * sizeof(pb_site_out), cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -79,7 +79,7 @@ struct pb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // label-matrix pre-generation (K3a) alongside the K1 tail
-    cudaEvent_t ev_k1_done = nullptr, ev_gen_done = nullptr, ev_gen_b[2] = {nullptr, nullptr};
+    cudaEvent_t ev_k1_done = nullptr, ev_gen_started = nullptr, ev_gen_done = nullptr, ev_gen_b[2] = {nullptr, nullptr}, ev_cnt_b[2] = {nullptr, nullptr};
     bool pregen_valid = false; int64_t pregen_tile = 0;
     std::string err;
     int sm_count = 148;
@@ -134,6 +134,9 @@ struct pb_ctx {
     double* d_ptable = nullptr;  int64_t ptable_cap = 0;  int32_t ptable_nmax = -1;
     void* d_thr = nullptr; int64_t thr_cap = 0;  // threshold scratch (expect, tau, ktau, n-histogram)
     int32_t* d_ktau = nullptr;   // [n_max+1]   (inside d_thr)
+    unsigned long long* d_nfast = nullptr;     // (inside d_thr) followed by the 4 list counts and the fallback total
+    unsigned int* d_lcount = nullptr;          // (inside d_thr) lengths of the 4 K3b work lists
+    unsigned long long* d_fb_total = nullptr;  // (inside d_thr) replicates recomputed by the maxT fallback
     double* d_tau = nullptr;     // 1           (inside d_thr)
     double* d_pobs = nullptr;    // [2*S_inf]
     uint32_t* d_r = nullptr;     // [2*S_inf]
@@ -171,7 +174,7 @@ struct pb_ctx {
 
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------
 int pbk_events(pb_ctx* ctx);                                   // k1_events.cu
-int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts); // k1_events.cu
+int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out); // k1_events.cu
 int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms);      // k3_null.cu (+ k4)
 int pbk_pregen_labels(pb_ctx* ctx);                            // k3_null.cu
 int pbk_ptable(pb_ctx* ctx);                                   // k4_pvalues.cu

@@ -9,7 +9,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, S, m, q):
+def _mono_tail(B0, B1, V, S, world):
+    """make rank 1's shard monomorphic ('A' everywhere): it has no informative site but still joins the all-reduce"""
+    from poutine_b200 import shard
+    s0, s1 = shard.site_range(S, 1, world)
+    B0[:, s0 // 64:] = 0
+    B1[:, s0 // 64:] = 0
+
+
+def _worker(rank, world, port, S, m, q, empty_rank1=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
@@ -20,6 +28,8 @@ def _worker(rank, world, port, S, m, q):
     B0, B1, V = synth.simulate_planes(tree, S, 6, leaf_gap=True)
     sn, lab = synth.simulate_phenotypes(tree, 7, na_frac=0.02)
     s0, s1 = shard.site_range(S, rank, world)
+    if empty_rank1:
+        _mono_tail(B0, B1, V, S, world)
     hc = pb.HomoplasyCounter(num_replicates=m, device=rank, seed=4242, site_offset=s0)
     hc.set_tree(tree.parent, tree.is_leaf)
     hc.set_phenos(sn, lab)
@@ -35,7 +45,8 @@ def _worker(rank, world, port, S, m, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_sharded_equals_single_gpu():
+@pytest.mark.parametrize("empty_rank1", [False, True])
+def test_two_gpu_sharded_equals_single_gpu(empty_rank1):
     import torch.multiprocessing as mp
     import poutine_b200 as pb
     from poutine_b200 import _lib, synth
@@ -44,7 +55,7 @@ def test_two_gpu_sharded_equals_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, S, m, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, S, m, q, empty_rank1)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
@@ -54,6 +65,8 @@ def test_two_gpu_sharded_equals_single_gpu():
     tree = synth.yule_tree(300, 5)
     B0, B1, V = synth.simulate_planes(tree, S, 6, leaf_gap=True)
     sn, lab = synth.simulate_phenotypes(tree, 7, na_frac=0.02)
+    if empty_rank1:
+        _mono_tail(B0, B1, V, S, world)
     hc = pb.HomoplasyCounter(num_replicates=m, seed=4242)
     hc.set_tree(tree.parent, tree.is_leaf)
     hc.set_phenos(sn, lab)
@@ -61,10 +74,9 @@ def test_two_gpu_sharded_equals_single_gpu():
     hc.count_all_homoplasy_events()
     st, mt = hc.assoc()
     parts = [np.frombuffer(r[1], dtype=_lib.STAT_DTYPE).copy() for r in res]
-    off = 0
-    for r, p in zip(res, parts):
-        p["site_index"] += off                      # shard-local -> global
-        off = p["site_index"].max() // 64 * 64 + 64 if len(p) else off
+    from poutine_b200 import shard
+    for rk, p in enumerate(parts):
+        p["site_index"] += shard.site_range(S, rk, world)[0]     # shard-local -> global
     got = np.concatenate(parts)
     for f in ("segsite_id", "obs_counts", "r_a1", "r_a2", "r_maxT_a1", "r_maxT_a2", "a1_in_use", "a2_in_use"):
         np.testing.assert_array_equal(got[f], st[f], err_msg=f)
