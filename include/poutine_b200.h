@@ -134,11 +134,14 @@ int pb_set_sites(pb_ctx* ctx, int64_t n_sites);
 /* Node-major bit planes of `seg_sites` (HC.java:1241-1306): 2-bit base code A0 C1 G2 T3 in
  * (B1,B0), V = genotype is an upper-case ACGT.  Bit j of word w = site 64*w+j.  Uploads the
  * column tile [word_begin, word_begin+n_words) of all nodes; row v of each source starts at
- * src + v*src_pitch_words.  Streamable: call once per tile. */
+ * src + v*src_pitch_words.  Streamable: call once per tile.  A whole-alignment upload whose src_pitch_words equals
+ * the device pitch (W rounded up to a multiple of 16 words) is done as one flat copy per plane. */
 int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
                   const uint64_t* B0, const uint64_t* B1, const uint64_t* V);
 
-/* count_all_homoplasy_events (HC.java:1402).  per_site (n_sites records) and counts may be NULL. */
+/* count_all_homoplasy_events (HC.java:1402).  per_site (n_sites records) and counts may be NULL.
+ * If pb_set_labels was called before (Philox mode), the label matrix of the first replicate tile is generated on a
+ * second stream behind the event kernel, so that pb_run_assoc finds it ready: set labels first, then run events. */
 int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts);
 
 /* assoc (HC.java:2029 -> 3013-3186): observed tallies, permutation null, point-wise and
