@@ -123,7 +123,7 @@ __device__ __noinline__ void drain_queue(raw_event_t* s_queue, unsigned int* s_c
 }
 
 #define K1_ROW_BYTES (3 * PB_K1_COLS * 8)
-#define K1_STAGE_BYTES (2 * K1_ROW_BYTES)
+#define K1_STAGE_BYTES (2 * PB_K1_RPS * K1_ROW_BYTES)
 #define K1_SMEM_RING (PB_K1_STAGES * K1_STAGE_BYTES)
 #define K1_SMEM_HI ((PB_K1_KHI + 1) * 4 * PB_K1_COLS * 8)   // high slices + the pending carries into slice 8
 #define K1_SMEM_QUEUE (PB_K1_QCAP * 8)
@@ -206,15 +206,20 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
         // ================= producer warp: one lane feeds the ring with TMA =================
         if (tid == PB_K1_CONSUMERS) {
             uint32_t soff = 0, boff = 0, phase = 0;
-            for (int i = r0; i < r1; i++) {
-                const uint4 rec = __ldg(recs + i);
-                const uint32_t na = rec.x & PB_OP_NODE_MASK, nb = rec.y & PB_OP_NODE_MASK;
-                const uint32_t nreal = (na != PB_OP_NULL ? 1u : 0u) + (nb != PB_OP_NULL ? 1u : 0u);
+            for (int i = r0; i < r1; i += PB_K1_RPS) {
+                uint32_t node[2 * PB_K1_RPS], nreal = 0;
+#pragma unroll
+                for (int k = 0; k < PB_K1_RPS; k++) {
+                    const uint4 rec = __ldg(recs + i + k);
+                    node[2 * k] = rec.x & PB_OP_NODE_MASK; node[2 * k + 1] = rec.y & PB_OP_NODE_MASK;
+                    nreal += (node[2 * k] != PB_OP_NULL ? 1u : 0u) + (node[2 * k + 1] != PB_OP_NULL ? 1u : 0u);
+                }
                 if (nreal == 0) continue;
                 mbar_wait(empty0 + boff, phase ^ 1);                     // consumers have drained this stage
                 mbar_arrive_expect_tx(full0 + boff, nreal * K1_ROW_BYTES);
-                if (na != PB_OP_NULL) tma_load_row(ring0 + soff, &tmap, col0, (int32_t)na, full0 + boff);
-                if (nb != PB_OP_NULL) tma_load_row(ring0 + soff + K1_ROW_BYTES, &tmap, col0, (int32_t)nb, full0 + boff);
+#pragma unroll
+                for (int k = 0; k < 2 * PB_K1_RPS; k++)
+                    if (node[k] != PB_OP_NULL) tma_load_row(ring0 + soff + k * K1_ROW_BYTES, &tmap, col0, (int32_t)node[k], full0 + boff);
                 soff += K1_STAGE_BYTES; boff += 8;
                 if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
             }
@@ -244,51 +249,62 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
     const lane_t edge_mask = (edge_block && w == p.W - 1) ? (lane_t)(p.last_mask >> (sub * PB_K1_LANE_BITS)) : (lane_t)~(lane_t)0;
 
 #pragma unroll 1
-    for (int i = r0; i < r1; i++) {
-        const uint4 rec = __ldg(recs + i);
-        const bool ra = (rec.x & PB_OP_NODE_MASK) != PB_OP_NULL, rb = (rec.y & PB_OP_NODE_MASK) != PB_OP_NULL;
-        lane_t av, a0, a1, bv, b0, b1;
-        if (ra | rb) {
-            mbar_wait(full0 + boff, phase);                              // TMA bytes have landed
-            const uint32_t src = my_ring + soff;
-            av = lds_lane(src); a0 = lds_lane(src + PB_K1_COLS * 8); a1 = lds_lane(src + 2 * PB_K1_COLS * 8);
-            bv = lds_lane(src + 3 * PB_K1_COLS * 8); b0 = lds_lane(src + 4 * PB_K1_COLS * 8); b1 = lds_lane(src + 5 * PB_K1_COLS * 8);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + boff);                   // stage is free again
-            soff += K1_STAGE_BYTES; boff += 8;
-            if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
-            if (edge_block) { av &= edge_mask; bv &= edge_mask; }        // caller's padding bits of the last word never count
-            if (!(ra & rb)) {                                            // rare: a padding slot holds stale ring bytes
-                if (!ra) { av = 0; a0 = 0; a1 = 0; }
-                if (!rb) { bv = 0; b0 = 0; b1 = 0; }
-            }
-        } else {
-            av = a0 = a1 = bv = b0 = b1 = 0;
+    for (int i = r0; i < r1; i += PB_K1_RPS) {
+        uint4 rec[PB_K1_RPS];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < PB_K1_RPS; k++) {
+            rec[k] = __ldg(recs + i + k);
+            any |= ((rec[k].x & rec[k].y & PB_OP_NODE_MASK) != PB_OP_NULL);      // some slot of this stage holds a row
         }
-        k1_row(rec.x, av, a0, a1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, s_queue, &s_count, p);
-        k1_row(rec.y, bv, b0, b1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, s_queue, &s_count, p);
-        if (rec.z != PB_REC_NOFLUSH) {
-            // census partial rec.z: [flush][base][slice][W]   (segments are padded to 8 leaves: nothing is pending)
-            if (w < p.W) {
-                // census words are uint64 [flush][base][slice][W]; a 32-bit lane writes its half (little-endian)
-                lane_t* out = reinterpret_cast<lane_t*>(p.census) + (((int64_t)rec.z * 4 * PB_K1_KS) * p.W + w) * SUBS + sub;
-                const int64_t sl = p.W * SUBS;                           // lanes per slice
+        if (any) mbar_wait(full0 + boff, phase);                         // the stage's TMA bytes have landed
+        const uint32_t src = my_ring + soff;
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    out[((int64_t)c * PB_K1_KS + 0) * sl] = cs.ones[c];
-                    out[((int64_t)c * PB_K1_KS + 1) * sl] = cs.twos[c];
-                    out[((int64_t)c * PB_K1_KS + 2) * sl] = cs.fours[c];
-#pragma unroll
-                    for (int j = 0; j < PB_K1_KHI; j++) out[((int64_t)c * PB_K1_KS + 3 + j) * sl] = s_hi[(j * 4 + c) * PB_K1_CONSUMERS + tid];
+        for (int k = 0; k < PB_K1_RPS; k++) {
+            const bool ra = (rec[k].x & PB_OP_NODE_MASK) != PB_OP_NULL, rb = (rec[k].y & PB_OP_NODE_MASK) != PB_OP_NULL;
+            lane_t av = 0, a0 = 0, a1 = 0, bv = 0, b0 = 0, b1 = 0;
+            if (ra | rb) {
+                const uint32_t s2 = src + k * 2 * K1_ROW_BYTES;
+                av = lds_lane(s2); a0 = lds_lane(s2 + PB_K1_COLS * 8); a1 = lds_lane(s2 + 2 * PB_K1_COLS * 8);
+                bv = lds_lane(s2 + 3 * PB_K1_COLS * 8); b0 = lds_lane(s2 + 4 * PB_K1_COLS * 8); b1 = lds_lane(s2 + 5 * PB_K1_COLS * 8);
+                if (edge_block) { av &= edge_mask; bv &= edge_mask; }    // caller's padding bits of the last word never count
+                if (!(ra & rb)) {                                        // rare: a padding slot holds stale ring bytes
+                    if (!ra) { av = 0; a0 = 0; a1 = 0; }
+                    if (!rb) { bv = 0; b0 = 0; b1 = 0; }
                 }
             }
+            if (k == PB_K1_RPS - 1 && any) {                             // every row of the stage is in registers: free it
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + boff);
+                soff += K1_STAGE_BYTES; boff += 8;
+                if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
+            }
+            k1_row(rec[k].x, av, a0, a1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, s_queue, &s_count, p);
+            k1_row(rec[k].y, bv, b0, b1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, s_queue, &s_count, p);
+            if (rec[k].z != PB_REC_NOFLUSH) {
+                // census partial rec.z: [flush][base][slice][W]   (segments are padded to 8 leaves: nothing is pending)
+                if (w < p.W) {
+                    // census words are uint64 [flush][base][slice][W]; a 32-bit lane writes its half (little-endian)
+                    lane_t* out = reinterpret_cast<lane_t*>(p.census) + (((int64_t)rec[k].z * 4 * PB_K1_KS) * p.W + w) * SUBS + sub;
+                    const int64_t sl = p.W * SUBS;                       // lanes per slice
 #pragma unroll
-            for (int c = 0; c < 4; c++) { cs.ones[c] = cs.twos[c] = cs.fours[c] = 0; cs.pend2[c] = cs.pend4[c] = 0; }
+                    for (int c = 0; c < 4; c++) {
+                        out[((int64_t)c * PB_K1_KS + 0) * sl] = cs.ones[c];
+                        out[((int64_t)c * PB_K1_KS + 1) * sl] = cs.twos[c];
+                        out[((int64_t)c * PB_K1_KS + 2) * sl] = cs.fours[c];
 #pragma unroll
-            for (int j = 0; j < (PB_K1_KHI + 1) * 4; j++) s_hi[j * PB_K1_CONSUMERS + tid] = 0;
-            cs.nleaf = 0;
+                        for (int j = 0; j < PB_K1_KHI; j++) out[((int64_t)c * PB_K1_KS + 3 + j) * sl] = s_hi[(j * 4 + c) * PB_K1_CONSUMERS + tid];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) { cs.ones[c] = cs.twos[c] = cs.fours[c] = 0; cs.pend2[c] = cs.pend4[c] = 0; }
+#pragma unroll
+                for (int j = 0; j < (PB_K1_KHI + 1) * 4; j++) s_hi[j * PB_K1_CONSUMERS + tid] = 0;
+                cs.nleaf = 0;
+            }
         }
-        if (((i - r0) & (PB_K1_DRAIN_EVERY - 1)) == PB_K1_DRAIN_EVERY - 1) drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
+        if ((((i - r0) / PB_K1_RPS) & (PB_K1_DRAIN_EVERY / PB_K1_RPS - 1)) == PB_K1_DRAIN_EVERY / PB_K1_RPS - 1)
+            drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
     }
     drain_queue(s_queue, &s_count, &s_base, tid, 1, p.raw, p.raw_cursor, p.raw_cap);
 }

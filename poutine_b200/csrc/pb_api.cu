@@ -213,6 +213,7 @@ static int build_chunks(pb_ctx* ctx) {
             }
         }
         flush();   // every chunk ends with a flush (possibly of an all-zero census)
+        while ((recs.size() / 4) % PB_K1_RPS) close(PB_REC_NOFLUSH);   // whole ring stages (empty records cost nothing)
         chunk_op[c + 1] = (int32_t)(recs.size() / 4);
     }
     const std::vector<uint32_t>& ops = recs;

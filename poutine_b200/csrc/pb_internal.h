@@ -52,7 +52,10 @@ typedef unsigned long long raw_event_t;
 #endif
 #define PB_K1_CONSUMERS (PB_K1_COLS * 64 / PB_K1_LANE_BITS)
 #define PB_K1_THREADS (PB_K1_CONSUMERS + 32)   // consumer warps + 1 TMA producer warp
-#define PB_K1_STAGES 4      // ring of row PAIRS (two 3 KB TMA boxes per stage: 3 planes x 128 words each)
+#ifndef PB_K1_RPS
+#define PB_K1_RPS 2         // 16-byte records (row pairs) per ring stage: one full/empty handshake per 2*RPS rows
+#endif
+#define PB_K1_STAGES (4 / PB_K1_RPS)   // ring = 8 rows (24 KB per 128 columns): 3 KB TMA boxes, 2*RPS of them per stage
 #define PB_K1_QCAP (6 * PB_K1_COLS)   // per-block event queue (6 KB per 128 columns)
 #ifndef PB_K1_DRAIN_EVERY
 #define PB_K1_DRAIN_EVERY 128 // records between queue-drain checks (a consumer-wide barrier each)
