@@ -29,7 +29,6 @@
 
 struct K1Params {
     int64_t W;
-    uint64_t last_mask;                    // valid site bits of word W-1
     const uint32_t* __restrict__ ops;
     const int32_t* __restrict__ chunk_op;
     uint64_t* __restrict__ census;         // [flush][4][KS][W]
@@ -207,19 +206,18 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
         if (tid == PB_K1_CONSUMERS) {
             uint32_t soff = 0, boff = 0, phase = 0;
             for (int i = r0; i < r1; i += PB_K1_RPS) {
-                uint32_t node[2 * PB_K1_RPS], nreal = 0;
+                // padding slots carry node = PB_OP_NULL, a coordinate beyond the tensor's node extent: TMA zero-fills the box
+                // without touching memory and still counts its bytes, so every stage is four loads and a constant tx count
+                uint32_t node[2 * PB_K1_RPS];
 #pragma unroll
                 for (int k = 0; k < PB_K1_RPS; k++) {
                     const uint4 rec = __ldg(recs + i + k);
                     node[2 * k] = rec.x & PB_OP_NODE_MASK; node[2 * k + 1] = rec.y & PB_OP_NODE_MASK;
-                    nreal += (node[2 * k] != PB_OP_NULL ? 1u : 0u) + (node[2 * k + 1] != PB_OP_NULL ? 1u : 0u);
                 }
-                if (nreal == 0) continue;
                 mbar_wait(empty0 + boff, phase ^ 1);                     // consumers have drained this stage
-                mbar_arrive_expect_tx(full0 + boff, nreal * K1_ROW_BYTES);
+                mbar_arrive_expect_tx(full0 + boff, K1_STAGE_BYTES);
 #pragma unroll
-                for (int k = 0; k < 2 * PB_K1_RPS; k++)
-                    if (node[k] != PB_OP_NULL) tma_load_row(ring0 + soff + k * K1_ROW_BYTES, &tmap, col0, (int32_t)node[k], full0 + boff);
+                for (int k = 0; k < 2 * PB_K1_RPS; k++) tma_load_row(ring0 + soff + k * K1_ROW_BYTES, &tmap, col0, (int32_t)node[k], full0 + boff);
                 soff += K1_STAGE_BYTES; boff += 8;
                 if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
             }
@@ -232,7 +230,6 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
     constexpr int SUBS = 64 / PB_K1_LANE_BITS;                          // consumer threads per word column
     const int sub = tid % SUBS;                                         // which part of the 64-site word this thread owns
     const int64_t w = (int64_t)col0 + tid / SUBS;
-    const bool edge_block = (int64_t)col0 + PB_K1_COLS >= p.W;          // block-uniform: holds word W-1 (TMA zero-fills beyond W)
     const uint32_t site_base = (uint32_t)(w * 64 + sub * PB_K1_LANE_BITS);
     const uint32_t my_ring = pin_u32(ring0 + tid * (PB_K1_LANE_BITS / 8));
 
@@ -246,34 +243,22 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
     lane_t* s_p8 = s_hi + (PB_K1_KHI * 4) * PB_K1_CONSUMERS + tid;    // pending carries into slice 8
     lane_t pv = 0, p0 = 0, p1 = 0;   // current parent row
     uint32_t soff = 0, boff = 0, phase = 0;
-    const lane_t edge_mask = (edge_block && w == p.W - 1) ? (lane_t)(p.last_mask >> (sub * PB_K1_LANE_BITS)) : (lane_t)~(lane_t)0;
 
+    // Rows arrive clean: padding slots are zero-filled by TMA (no allele, no event), columns beyond W likewise, and the
+    // caller's padding bits of word W-1 were cleared from the V plane at upload (pb_put_planes -> pbk_mask_last_word).
 #pragma unroll 1
     for (int i = r0; i < r1; i += PB_K1_RPS) {
         uint4 rec[PB_K1_RPS];
-        bool any = false;
 #pragma unroll
-        for (int k = 0; k < PB_K1_RPS; k++) {
-            rec[k] = __ldg(recs + i + k);
-            any |= ((rec[k].x & rec[k].y & PB_OP_NODE_MASK) != PB_OP_NULL);      // some slot of this stage holds a row
-        }
-        if (any) mbar_wait(full0 + boff, phase);                         // the stage's TMA bytes have landed
+        for (int k = 0; k < PB_K1_RPS; k++) rec[k] = __ldg(recs + i + k);
+        mbar_wait(full0 + boff, phase);                                  // the stage's TMA bytes have landed
         const uint32_t src = my_ring + soff;
 #pragma unroll
         for (int k = 0; k < PB_K1_RPS; k++) {
-            const bool ra = (rec[k].x & PB_OP_NODE_MASK) != PB_OP_NULL, rb = (rec[k].y & PB_OP_NODE_MASK) != PB_OP_NULL;
-            lane_t av = 0, a0 = 0, a1 = 0, bv = 0, b0 = 0, b1 = 0;
-            if (ra | rb) {
-                const uint32_t s2 = src + k * 2 * K1_ROW_BYTES;
-                av = lds_lane(s2); a0 = lds_lane(s2 + PB_K1_COLS * 8); a1 = lds_lane(s2 + 2 * PB_K1_COLS * 8);
-                bv = lds_lane(s2 + 3 * PB_K1_COLS * 8); b0 = lds_lane(s2 + 4 * PB_K1_COLS * 8); b1 = lds_lane(s2 + 5 * PB_K1_COLS * 8);
-                if (edge_block) { av &= edge_mask; bv &= edge_mask; }    // caller's padding bits of the last word never count
-                if (!(ra & rb)) {                                        // rare: a padding slot holds stale ring bytes
-                    if (!ra) { av = 0; a0 = 0; a1 = 0; }
-                    if (!rb) { bv = 0; b0 = 0; b1 = 0; }
-                }
-            }
-            if (k == PB_K1_RPS - 1 && any) {                             // every row of the stage is in registers: free it
+            const uint32_t s2 = src + k * 2 * K1_ROW_BYTES;
+            const lane_t av = lds_lane(s2), a0 = lds_lane(s2 + PB_K1_COLS * 8), a1 = lds_lane(s2 + 2 * PB_K1_COLS * 8);
+            const lane_t bv = lds_lane(s2 + 3 * PB_K1_COLS * 8), b0 = lds_lane(s2 + 4 * PB_K1_COLS * 8), b1 = lds_lane(s2 + 5 * PB_K1_COLS * 8);
+            if (k == PB_K1_RPS - 1) {                                    // every row of the stage is in registers: free it
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty0 + boff);
                 soff += K1_STAGE_BYTES; boff += 8;
@@ -563,10 +548,24 @@ __global__ void k1_scatter_events_kernel(const raw_event_t* __restrict__ raw, co
 }
 
 // =================================================================================================
+// The caller's padding bits of the last site word (S % 64 != 0) must never count as sites: they are cleared from the
+// V plane once, when the tile holding word W-1 is uploaded, instead of being masked per row inside K1.
+__global__ void k1_mask_last_word_kernel(uint64_t* __restrict__ V, int32_t N, int64_t Wp, int64_t w_last, uint64_t mask) {
+    const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < N) V[(int64_t)v * Wp + w_last] &= mask;
+}
+
+int pbk_mask_last_word(pb_ctx* ctx) {
+    if (!(ctx->S & 63) || ctx->N == 0) return PB_OK;
+    const uint64_t mask = (1ull << (ctx->S & 63)) - 1;
+    k1_mask_last_word_kernel<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_V, ctx->N, ctx->Wp, ctx->W - 1, mask);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
 int pbk_events(pb_ctx* ctx) {
     K1Params p;
     p.W = ctx->W;
-    p.last_mask = (ctx->S & 63) ? ((1ull << (ctx->S & 63)) - 1) : ~0ull;
     p.ops = ctx->d_ops; p.chunk_op = ctx->d_chunk_op;
     p.census = ctx->d_census;
     p.raw = ctx->d_raw; p.raw_cursor = ctx->d_raw_cursor; p.raw_cap = (unsigned long long)ctx->raw_cap;

@@ -368,6 +368,7 @@ extern "C" int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, i
             PB_CUDA(cudaMemcpy2DAsync(dst[i] + word_begin, (size_t)ctx->Wp * 8, src[i], (size_t)src_pitch_words * 8, (size_t)n_words * 8,
                                       (size_t)ctx->N, cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (word_begin + n_words == ctx->W) { int rc = pbk_mask_last_word(ctx); if (rc) return rc; }
     PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers are caller-owned: do not retain them past return
     return PB_OK;
 }

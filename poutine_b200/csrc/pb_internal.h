@@ -177,6 +177,7 @@ struct pb_ctx {
 
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------
 int pbk_events(pb_ctx* ctx);                                   // k1_events.cu
+int pbk_mask_last_word(pb_ctx* ctx);                           // k1_events.cu (clears the padding bits of site word W-1 in V)
 int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out); // k1_events.cu
 int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms);      // k3_null.cu (+ k4)
 int pbk_pregen_labels(pb_ctx* ctx);                            // k3_null.cu
