@@ -85,19 +85,22 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t x) {
 }
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PB_K1_CONSUMERS) : "memory"); }
 
+// Queue push with plain shared-memory instructions: one ATOMS per event (a warp row rarely holds more than one or two
+// events, so the compiler's warp-aggregated atomicAdd sequence costs more than it saves) and a 32-bit shared-window store.
 __device__ __forceinline__ void emit_events(lane_t mrca, lane_t b0, lane_t b1, uint32_t site_base, uint32_t node_tag,
-                                            raw_event_t* s_queue, unsigned int* s_count, const K1Params& p) {
+                                            uint32_t queue_addr, uint32_t count_addr, const K1Params& p) {
     while (mrca) {
         const int b = lane_ffs(mrca) - 1;
         mrca &= mrca - 1;
         const uint32_t base = (uint32_t)((b0 >> b) & 1u) | ((uint32_t)((b1 >> b) & 1u) << 1);
-        const raw_event_t rec = (raw_event_t)(site_base + (uint32_t)b) | ((raw_event_t)(node_tag | (base << 29)) << 32);
-        const unsigned int slot = atomicAdd(s_count, 1u);
+        const uint32_t lo = site_base + (uint32_t)b, hi = node_tag | (base << 29);
+        uint32_t slot;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(count_addr) : "memory");
         if (slot < PB_K1_QCAP) {
-            s_queue[slot] = rec;
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(queue_addr + slot * 8), "r"(lo), "r"(hi) : "memory");
         } else {  // queue full: slow path straight to global (correct for arbitrarily dense inputs)
             const unsigned long long pos = atomicAdd(p.raw_cursor, 1ull);
-            if (pos < p.raw_cap) p.raw[pos] = rec;
+            if (pos < p.raw_cap) p.raw[pos] = (raw_event_t)lo | ((raw_event_t)hi << 32);
         }
     }
 }
@@ -137,11 +140,11 @@ struct Census {
 
 // one tree row: MRCA test against the current parent row, optional parent update, optional leaf census
 __device__ __forceinline__ void k1_row(uint32_t op, lane_t cv, lane_t c0, lane_t c1, lane_t& pv, lane_t& p0, lane_t& p1,
-                                       Census& cs, lane_t* s_hi, lane_t* s_p8, int tid, uint32_t site_base, raw_event_t* s_queue,
-                                       unsigned int* s_count, const K1Params& p) {
+                                       Census& cs, lane_t* s_hi, lane_t* s_p8, int tid, uint32_t site_base, uint32_t queue_addr,
+                                       uint32_t count_addr, const K1Params& p) {
     if (op & PB_OP_TEST) {
         const lane_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
-        if (mrca) emit_events(mrca, c0, c1, site_base, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), s_queue, s_count, p);
+        if (mrca) emit_events(mrca, c0, c1, site_base, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
     }
     if (op & PB_OP_SETCUR) { pv = cv; p0 = c0; p1 = c1; }
     if (op & PB_OP_LEAF) {
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
     const int64_t w = (int64_t)col0 + tid / SUBS;
     const uint32_t site_base = (uint32_t)(w * 64 + sub * PB_K1_LANE_BITS);
     const uint32_t my_ring = pin_u32(ring0 + tid * (PB_K1_LANE_BITS / 8));
+    const uint32_t queue_addr = pin_u32(ring0 + K1_SMEM_RING + K1_SMEM_HI), count_addr = pin_u32(smem_u32(&s_count));
 
     // leaf census, bit-sliced with deferred carries: level L holds a counter slice and the OR of the carries the
     // level below produced since its last update (two consecutive half-add carries are mutually exclusive:
@@ -264,8 +268,8 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
                 soff += K1_STAGE_BYTES; boff += 8;
                 if (boff == 8 * PB_K1_STAGES) { soff = 0; boff = 0; phase ^= 1; }
             }
-            k1_row(rec[k].x, av, a0, a1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, s_queue, &s_count, p);
-            k1_row(rec[k].y, bv, b0, b1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, s_queue, &s_count, p);
+            k1_row(rec[k].x, av, a0, a1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, queue_addr, count_addr, p);
+            k1_row(rec[k].y, bv, b0, b1, pv, p0, p1, cs, s_hi, s_p8, tid, site_base, queue_addr, count_addr, p);
             if (rec[k].z != PB_REC_NOFLUSH) {
                 // census partial rec.z: [flush][base][slice][W]   (segments are padded to 8 leaves: nothing is pending)
                 if (w < p.W) {
