@@ -148,11 +148,17 @@ __device__ __forceinline__ void k1_row(uint32_t op, lane_t cv, lane_t c0, lane_t
     }
     if (op & PB_OP_SETCUR) { pv = cv; p0 = c0; p1 = c1; }
     if (op & PB_OP_LEAF) {
-        const lane_t x[4] = {cv & ~c0 & ~c1, cv & c0 & ~c1, cv & ~c0 & c1, cv & c0 & c1};
+        // the four counters are n(V), n(V&B0), n(V&B1), n(V&B0&B1) (k1_finalize_kernel turns them into per-base counts):
+        // new = old ^ (V & B) and carry = old & ~new are one 3-input LOP3 each, no materialised one-hot masks
         const int ph = cs.nleaf & 7;                                 // block-uniform
         cs.nleaf++;
-#pragma unroll
-        for (int c = 0; c < 4; c++) { cs.pend2[c] |= cs.ones[c] & x[c]; cs.ones[c] ^= x[c]; }
+        {
+            const lane_t o0 = cs.ones[0], o1 = cs.ones[1], o2 = cs.ones[2], o3 = cs.ones[3], t3 = cv & c0 & c1;
+            cs.ones[0] = o0 ^ cv;        cs.pend2[0] |= o0 & ~cs.ones[0];
+            cs.ones[1] = o1 ^ (cv & c0); cs.pend2[1] |= o1 & ~cs.ones[1];
+            cs.ones[2] = o2 ^ (cv & c1); cs.pend2[2] |= o2 & ~cs.ones[2];
+            cs.ones[3] = o3 ^ t3;        cs.pend2[3] |= o3 & t3;
+        }
         if (ph & 1) {
 #pragma unroll
             for (int c = 0; c < 4; c++) { cs.pend4[c] |= cs.twos[c] & cs.pend2[c]; cs.twos[c] ^= cs.pend2[c]; cs.pend2[c] = 0; }
@@ -360,11 +366,12 @@ __global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, int kt_us
     if (s < S) {
         const int64_t w = s >> 6;
         const int b = (int)(s & 63);
-        uint32_t leafcnt[4] = {0, 0, 0, 0};  // by 2-bit code: A C G T
+        uint32_t q[4] = {0, 0, 0, 0};        // K1's counters: leaves with V, V&B0, V&B1, V&B0&B1
 #pragma unroll
         for (int c = 0; c < 4; c++)
             for (int j = 0; j < kt_used; j++)
-                leafcnt[c] |= (uint32_t)((total[((int64_t)c * PB_K1_KT + j) * W + w] >> b) & 1ull) << j;
+                q[c] |= (uint32_t)((total[((int64_t)c * PB_K1_KT + j) * W + w] >> b) & 1ull) << j;
+        const uint32_t leafcnt[4] = {q[0] - q[1] - q[2] + q[3], q[1] - q[3], q[2] - q[3], q[3]};  // by 2-bit code: A C G T
         // HashMap<Character,..> iteration order A, C, T, G  (buckets 'A'&15=1, 'C'&15=3, 'T'&15=4, 'G'&15=7)
         const int order[4] = {0, 1, 3, 2};
         int n_alleles = 0, first = -1, second = -1;
