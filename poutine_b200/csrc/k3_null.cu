@@ -204,8 +204,9 @@ __device__ __forceinline__ int extract(const uint64_t (&c)[NB], int b) {
 // r is accumulated in registers and written once — no atomics on r.
 template <int NB>
 __device__ __forceinline__ void sweep_allele(const K3Params& p, const AlleleMeta& m, int64_t slot, int lane, double tau, int w0 = -1,
-                                             int wstride = 32) {
-    // default: one warp owns the allele (lane = first word, stride 32, plain add); otherwise a thread block shares it
+                                             int wstride = 32, int64_t wend = -1) {
+    // default: one warp owns the allele (lane = first word, stride 32, plain add); otherwise several warps share it
+    // (a thread block striding over all words, or warps owning word segments [w0 - lane, wend)) and r is added atomically
     constexpr int NREG = (NB <= 3) ? ((1 << NB) - 1) : 1;   // small lists live in registers
     const int n = m.n;
     const int32_t* __restrict__ ev = p.csr + m.off;
@@ -221,10 +222,11 @@ __device__ __forceinline__ void sweep_allele(const K3Params& p, const AlleleMeta
     const int kt = p.ktau[n];
     const double* __restrict__ row_n = p.ptable + (int64_t)n * (n + 1) / 2;
     const int64_t words = (p.n_reps + 63) >> 6;
+    const int64_t wstop = (wend < 0 || wend > words) ? words : wend;
     const int tail = (int)(p.n_reps & 63);
     unsigned int rcount = 0;
 #pragma unroll 2
-    for (int64_t w = (w0 < 0 ? lane : w0); w < words; w += wstride) {
+    for (int64_t w = (w0 < 0 ? lane : w0); w < wstop; w += wstride) {
         const uint64_t valid = (w == words - 1 && tail) ? ((1ull << tail) - 1) : ~0ull;
         uint64_t c[NB], u[NB];
 #pragma unroll
@@ -397,7 +399,8 @@ __device__ __forceinline__ unsigned int sweep_miss(const K3Params& p, const Alle
 
 // n <= 7, every label present, maxT candidates possible for k >= kt (1 <= kt <= n): the tight sweep plus a scalar
 // look-up + atomic min for the (rare) candidate replicates.  k* may be anything (<= 0: all count, > n: none).
-__device__ __forceinline__ unsigned int sweep_upto7_cand(const K3Params& p, const AlleleMeta& m, int lane, int words, int kt, double tau) {
+__device__ __forceinline__ unsigned int sweep_upto7_cand(const K3Params& p, const AlleleMeta& m, int lane, int words, int kt, double tau,
+                                                         int wbeg, int wend) {
     const int n = m.n, kstar = m.kstar;
     const uint64_t* __restrict__ rp[7];
 #pragma unroll
@@ -405,7 +408,7 @@ __device__ __forceinline__ unsigned int sweep_upto7_cand(const K3Params& p, cons
     const double* __restrict__ row_n = p.ptable + (int64_t)n * (n + 1) / 2;
     const int tail = (int)(p.n_reps & 63);
     unsigned int rc = 0;
-    for (int w = lane, off = 0; w < words; w += 32, off += 32) {
+    for (int w = wbeg + lane, off = wbeg; w < wend; w += 32, off += 32) {   // wbeg is a multiple of 32, wend <= words
         uint64_t c[3] = {0, 0, 0};
 #pragma unroll
         for (int e = 0; e < 7; e++) {
@@ -462,24 +465,50 @@ __global__ void __launch_bounds__(K3_THREADS, MISS ? 4 : K3_TIGHT_BLOCKS) k3_cou
 
 // work list 3: short lists with possible maxT candidates (tight sweep + scalar candidate look-ups) or that need the
 // general path (non-monotone table rows, missing labels with candidates, test hooks)
-__global__ void __launch_bounds__(K3_THREADS, 2) k3_count_small_kernel(const K3Params p, const int32_t* __restrict__ list, const unsigned int* __restrict__ n_list_dev) {
-    const int64_t n_list = *n_list_dev;
+// These alleles are few (thousands at C2) and each sweep is long, so one task = one allele x one segment of the
+// replicate words: K3_SMALL_SEGS warps share an allele and add their partial r atomically.
+#define K3_SMALL_SEGS 8
+// (a) candidate short lists on the tight path.  Kept apart from the general path below so that it stays at 64 registers and
+// its blocks fit on an SM next to the tight sweep's (it runs on the side stream, concurrently with k3_count_tight_kernel).
+__global__ void __launch_bounds__(K3_THREADS, 4) k3_count_cand_kernel(const K3Params p, const int32_t* __restrict__ list, const unsigned int* __restrict__ n_list_dev) {
+    const int64_t n_tasks = (int64_t)*n_list_dev * K3_SMALL_SEGS;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
     const double tau = *p.tau;
-    for (int64_t i = gwarp; i < n_list; i += nwarps) {
-        const int64_t slot = list[i];
+    const int words = (int)((p.n_reps + 63) >> 6);
+    const int seg = ((words + K3_SMALL_SEGS - 1) / K3_SMALL_SEGS + 31) & ~31;   // whole warp steps
+    for (int64_t t = gwarp; t < n_tasks; t += nwarps) {
+        const int wbeg = (int)(t % K3_SMALL_SEGS) * seg, wend = min(words, wbeg + seg);
+        if (wbeg >= words) continue;
+        const int64_t slot = list[t / K3_SMALL_SEGS];
+        const AlleleMeta m = p.alleles[slot];
+        if (!(m.flags & PB_AF_TIGHT_CAND)) continue;
+        unsigned int rc = sweep_upto7_cand(p, m, lane, words, p.ktau[m.n], tau, wbeg, wend);
+        rc = __reduce_add_sync(0xffffffffu, rc);
+        if (lane == 0 && rc) atomicAdd(p.r + slot, rc);
+    }
+}
+
+// (b) whatever needs the general path
+__global__ void __launch_bounds__(K3_THREADS, 2) k3_count_small_kernel(const K3Params p, const int32_t* __restrict__ list, const unsigned int* __restrict__ n_list_dev) {
+    const int64_t n_tasks = (int64_t)*n_list_dev * K3_SMALL_SEGS;
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
+    const double tau = *p.tau;
+    const int words = (int)((p.n_reps + 63) >> 6);
+    const int seg = ((words + K3_SMALL_SEGS - 1) / K3_SMALL_SEGS + 31) & ~31;
+    for (int64_t t = gwarp; t < n_tasks; t += nwarps) {
+        const int wbeg = (int)(t % K3_SMALL_SEGS) * seg, wend = min(words, wbeg + seg);
+        if (wbeg >= words) continue;
+        const int64_t slot = list[t / K3_SMALL_SEGS];
         const AlleleMeta m = p.alleles[slot];
         const int n = m.n;
-        if (m.flags & PB_AF_TIGHT_CAND) {
-            unsigned int rc = sweep_upto7_cand(p, m, lane, (int)((p.n_reps + 63) >> 6), p.ktau[n], tau);
-            rc = __reduce_add_sync(0xffffffffu, rc);
-            if (lane == 0 && rc) p.r[slot] += rc;
-        }
-        else if (n < 2) sweep_allele<1>(p, m, slot, lane, tau);
-        else if (n < 4) sweep_allele<2>(p, m, slot, lane, tau);
-        else sweep_allele<3>(p, m, slot, lane, tau);
+        if (m.flags & PB_AF_TIGHT_CAND) continue;
+        if (n < 2) sweep_allele<1>(p, m, slot, lane, tau, wbeg + lane, 32, wend);
+        else if (n < 4) sweep_allele<2>(p, m, slot, lane, tau, wbeg + lane, 32, wend);
+        else sweep_allele<3>(p, m, slot, lane, tau, wbeg + lane, 32, wend);
     }
 }
 
@@ -821,19 +850,30 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             p.Rw = Rw;
             p.rep_base = base + cb; p.n_reps = cnr; p.r = ctx->d_r; p.maxT = ctx->d_maxT;
             const int64_t words = (cnr + 63) / 64;
+            // the few heavy sweeps (candidate short lists, long lists) go to a side stream: they are instruction-bound and
+            // fill the issue slots the load-latency-bound tight sweep leaves idle; the lists are disjoint, maxT is atomicMin
+            const bool side = !getenv("PB_K3_NO_SIDE_STREAM");
+            cudaStream_t ss = side ? ctx->stream3 : st;
+            if (side) {
+                PB_CUDA(cudaEventRecord(ctx->ev_side_fork, st));
+                PB_CUDA(cudaStreamWaitEvent(ss, ctx->ev_side_fork, 0));
+            }
+            k3_count_cand_kernel<<<small_blocks, K3_THREADS, 0, ss>>>(p, ctx->d_work + 3 * n_slots, lc + 3);
+            k3_count_small_kernel<<<small_blocks, K3_THREADS, 0, ss>>>(p, ctx->d_work + 3 * n_slots, lc + 3);
+            k3_count_large_kernel<<<large_blocks, K3_THREADS, 0, ss>>>(p, ctx->d_work + 2 * n_slots, lc + 2);
+            if (side) PB_CUDA(cudaEventRecord(ctx->ev_side_join, ss));
             k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(p.Xc, p.Xm, Rw, words, ctx->P, ctx->d_colpop);
             k3_trivial_kernel<<<(unsigned)std::max<int64_t>(1, (n_slots + T - 1) / T), T, 0, st>>>(p, ctx->d_work, lc + 0, ctx->d_colpop, ctx->P);
             if (has_miss) k3_count_tight_kernel<true><<<tight_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, lc + 1);
             else k3_count_tight_kernel<false><<<tight_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, lc + 1);
-            k3_count_small_kernel<<<small_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + 3 * n_slots, lc + 3);
-            k3_count_large_kernel<<<large_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + 2 * n_slots, lc + 2);
+            if (side) PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_side_join, 0));
             // replicates whose minimum was not certified by a candidate are recomputed exactly
             PB_CUDA(cudaMemsetAsync(ctx->d_fb_count, 0, 4, st));
             k3_collect_fallback_kernel<<<(unsigned)((cnr + T - 1) / T), T, 0, st>>>(ctx->d_maxT, p.rep_base, cnr, ctx->d_tau, ctx->d_fb_reps,
                                                                                  ctx->d_fb_count);
             k3_fallback_kernel<<<(unsigned)std::min<int64_t>(cnr, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(p, ctx->d_fb_reps, ctx->d_fb_count,
                                                                                                            ctx->d_fb_total);
-            ctx->tm.n_launches += 7;
+            ctx->tm.n_launches += 8;
         }
         if (pl.nbuf == 2) PB_CUDA(cudaEventRecord(ctx->ev_cnt_b[buf], st));
         PB_CUDA(cudaGetLastError());
@@ -866,5 +906,8 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     ctx->tm.n_fast_alleles = (int64_t)hb.nf;
     for (int c = 0; c < 4; c++) ctx->n_work[c] = (int64_t)hb.lc[c];
     ctx->tm.n_maxt_fallback_reps = (int64_t)hb.fb;
+    if (getenv("PB_VERBOSE"))
+        fprintf(stderr, "[poutine_b200] work lists: trivial %u, tight %u, long %u, general %u; fallback replicates %llu\n", hb.lc[0], hb.lc[1], hb.lc[2],
+                hb.lc[3], hb.fb);
     return PB_OK;
 }

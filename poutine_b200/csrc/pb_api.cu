@@ -65,7 +65,10 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
         if (getenv("PB_GEN_LOW_PRIORITY")) std::swap(prio_lo, prio_hi);   // experiment knob
         if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("cudaStreamCreate", e);
         if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
     }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_side_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_side_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_k1_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_gen_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -85,7 +88,11 @@ extern "C" void pb_destroy(pb_ctx* ctx) {
     pbn_destroy(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
     free_all(ctx);
+    if (ctx->ev_side_fork) cudaEventDestroy(ctx->ev_side_fork);
+    if (ctx->ev_side_join) cudaEventDestroy(ctx->ev_side_join);
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     if (ctx->ev_k1_done) cudaEventDestroy(ctx->ev_k1_done);
     if (ctx->ev_gen_done) cudaEventDestroy(ctx->ev_gen_done);
     if (ctx->ev_gen_started) cudaEventDestroy(ctx->ev_gen_started);

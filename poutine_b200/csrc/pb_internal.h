@@ -82,6 +82,8 @@ struct pb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // label-matrix pre-generation (K3a) alongside the K1 tail
+    cudaStream_t stream3 = nullptr;          // K3b side stream: the few heavy short-list/long-list sweeps run next to the tight sweep
+    cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
     cudaEvent_t ev_k1_done = nullptr, ev_gen_started = nullptr, ev_gen_done = nullptr, ev_gen_b[2] = {nullptr, nullptr}, ev_cnt_b[2] = {nullptr, nullptr};
     bool pregen_valid = false; int64_t pregen_tile = 0;
     std::string err;
