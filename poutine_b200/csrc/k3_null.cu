@@ -861,9 +861,9 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             k3_count_cand_kernel<<<small_blocks, K3_THREADS, 0, ss>>>(p, ctx->d_work + 3 * n_slots, lc + 3);
             k3_count_small_kernel<<<small_blocks, K3_THREADS, 0, ss>>>(p, ctx->d_work + 3 * n_slots, lc + 3);
             k3_count_large_kernel<<<large_blocks, K3_THREADS, 0, ss>>>(p, ctx->d_work + 2 * n_slots, lc + 2);
+            k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, ss>>>(p.Xc, p.Xm, Rw, words, ctx->P, ctx->d_colpop);
+            k3_trivial_kernel<<<(unsigned)std::max<int64_t>(1, (n_slots + T - 1) / T), T, 0, ss>>>(p, ctx->d_work, lc + 0, ctx->d_colpop, ctx->P);
             if (side) PB_CUDA(cudaEventRecord(ctx->ev_side_join, ss));
-            k3_colpop_kernel<<<(unsigned)ctx->P, 128, 0, st>>>(p.Xc, p.Xm, Rw, words, ctx->P, ctx->d_colpop);
-            k3_trivial_kernel<<<(unsigned)std::max<int64_t>(1, (n_slots + T - 1) / T), T, 0, st>>>(p, ctx->d_work, lc + 0, ctx->d_colpop, ctx->P);
             if (has_miss) k3_count_tight_kernel<true><<<tight_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, lc + 1);
             else k3_count_tight_kernel<false><<<tight_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, lc + 1);
             if (side) PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_side_join, 0));
