@@ -590,7 +590,9 @@ int pbk_events(pb_ctx* ctx) {
     dim3 grid((unsigned)((ctx->W + PB_K1_COLS - 1) / PB_K1_COLS), (unsigned)ctx->n_chunks);
     PB_CUDA(cudaMemsetAsync(ctx->d_raw_cursor, 0, 8, ctx->stream));
     PB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    pb_trace_mark(ctx, "start");
     k1_events_kernel<<<grid, PB_K1_THREADS, smem, ctx->stream>>>(ctx->tmap, p);
+    pb_trace_mark(ctx, "k1");
     PB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
@@ -600,10 +602,10 @@ int pbk_events(pb_ctx* ctx) {
 // Everything after the K1 sweep, enqueued without a host round trip: the raw list length, S_inf and E stay on the
 // device, the compaction outputs are sized for the worst case (every site informative, every raw event extant).
 // One readback at the end: class counters, n_max, #alleles in use, scan totals, K1's cursor.
-int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out) {
+// Buffers of the tail (worst-case sizes) and the zero-fill of its counters.  The 56 MB of memsets at C2 do not depend on
+// K1, so they go to the second stream BEFORE the sweep is enqueued and run underneath it; the tail waits on ev_zero_done.
+int pbk_prepare_tail(pb_ctx* ctx) {
     const int64_t S = ctx->S;
-    const int T = 256;
-    cudaStream_t st = ctx->stream;
     if (S > ctx->inf_cap) {
         cudaFree(ctx->d_inf_site); cudaFree(ctx->d_alleles); cudaFree(ctx->d_csr_cursor); cudaFree(ctx->d_pobs); cudaFree(ctx->d_r);
         ctx->d_inf_site = nullptr; ctx->d_alleles = nullptr; ctx->d_csr_cursor = nullptr; ctx->d_pobs = nullptr; ctx->d_r = nullptr;
@@ -619,17 +621,30 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
         PB_CUDA(cudaMalloc(&ctx->d_csr, (size_t)ctx->raw_cap * 4));
         ctx->csr_cap = ctx->raw_cap;
     }
+    PB_CUDA(cudaMemsetAsync(ctx->d_cnt, 0, (size_t)S * PB_CNT_STRIDE * 4, ctx->stream2));
+    PB_CUDA(cudaMemsetAsync(ctx->d_csr_cursor, 0, (size_t)S * 2 * 4, ctx->stream2));
+    PB_CUDA(cudaEventRecord(ctx->ev_zero_done, ctx->stream2));
+    return PB_OK;
+}
+
+int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out) {
+    const int64_t S = ctx->S;
+    const int T = 256;
+    cudaStream_t st = ctx->stream;
     const unsigned ev_blocks = (unsigned)std::min<int64_t>((ctx->raw_cap + T - 1) / T, (int64_t)ctx->sm_count * 16);
-    PB_CUDA(cudaMemsetAsync(ctx->d_cnt, 0, (size_t)S * PB_CNT_STRIDE * 4, st));
+    PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_zero_done, 0));   // d_cnt, d_csr_cursor zeroed underneath K1 (pbk_prepare_tail)
     PB_CUDA(cudaMemsetAsync(ctx->d_class_counts, 0, 16 * 8, st));
-    PB_CUDA(cudaMemsetAsync(ctx->d_csr_cursor, 0, (size_t)S * 2 * 4, st));
+    pb_trace_mark(ctx, "headstart+memsets");
     k1_count_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_cnt);
+    pb_trace_mark(ctx, "count_events");
     k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), 4), 128, 0, st>>>(ctx->d_census, ctx->n_flush, ctx->W, ctx->d_census_total);
+    pb_trace_mark(ctx, "census_reduce");
     int kt_used = 1;
     while ((1ll << kt_used) <= (int64_t)ctx->L) kt_used++;
     k1_finalize_kernel<<<(unsigned)((S + T - 1) / T), T, 0, st>>>(
         ctx->d_census_total, kt_used, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->d_cnt, ctx->cfg.min_hcount,
         ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan /* reused as scan input */, ctx->d_class_counts);
+    pb_trace_mark(ctx, "finalize");
     ctx->tm.n_launches += 3;
     PB_CUDA(cudaGetLastError());
     // scan: d_site_scan (input) -> d_site_scan_out.  We keep input in the first half of a 2*S buffer.
@@ -637,10 +652,13 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     uint64_t* scan_out = ctx->d_site_scan + S;
     int rc = pbk_exclusive_scan_u64(ctx, scan_in, scan_out, S, (uint64_t*)(ctx->d_class_counts + 7));
     if (rc) return rc;
+    pb_trace_mark(ctx, "scan");
     k1_scatter_sites_kernel<<<(unsigned)((S + T - 1) / T), T, 0, st>>>(S, ctx->d_site_flags, scan_out, scan_in, ctx->d_cnt, ctx->d_sites,
                                                                       ctx->d_inf_site, ctx->d_alleles, ctx->d_class_counts);
+    pb_trace_mark(ctx, "scatter_sites");
     k1_scatter_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
                                                      scan_out, scan_in, ctx->d_sites, ctx->d_alleles, ctx->d_csr_cursor, ctx->d_csr);
+    pb_trace_mark(ctx, "scatter_events");
     ctx->tm.n_launches += 2;
     PB_CUDA(cudaGetLastError());
     PB_CUDA(cudaMemcpyAsync(ctx->d_class_counts + 8, ctx->d_raw_cursor, 8, cudaMemcpyDeviceToDevice, st));
@@ -648,6 +666,7 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     PB_CUDA(cudaMemcpyAsync(h, ctx->d_class_counts, sizeof(h), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
     PB_CUDA(cudaGetLastError());
+    pb_trace_dump(ctx, "events");
     *cursor_out = h[8];
     ctx->S_inf = (int64_t)(h[7] >> 38);
     ctx->E = (int64_t)(h[7] & ((1ull << 38) - 1));

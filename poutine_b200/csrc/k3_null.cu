@@ -82,7 +82,7 @@ template <int MODE, bool MISS>
 __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
                                                              int32_t n_ctrl, const uint8_t* __restrict__ label,
                                                              const uint32_t* __restrict__ perms, uint32_t* __restrict__ Xc32,
-                                                             uint32_t* __restrict__ Xm32, int64_t Rw32) {
+                                                             uint32_t* __restrict__ Xm32, int64_t Rw32, int force_replay = 0) {
     __shared__ uint32_t sc[GEN_ROWS][GEN_WORDS], sm[MISS ? GEN_ROWS : 1][GEN_WORDS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rep_local = (int64_t)blockIdx.x * GEN_THREADS + tid;
@@ -140,7 +140,35 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
                 w[q4][0] = w[q4][1] = w[q4][2] = w[q4][3] = 0;
                 if (MODE == 0) philox4x32_10((uint32_t)((i0 + ii) >> 2) + q4, r0, r1, 0u, k0, k1, w[q4]);
             }
-            if (ii + 4 * GEN_ILP <= rows) {               // full group: no per-sample bounds checks (block-uniform)
+            if (MODE == 0 && !MISS && ii + 4 * GEN_ILP <= rows) {
+                // Full group, binary labels: the draws run without their per-draw rejection test.  A Lemire retry is needed only
+                // if some low product word is below its range (probability < range / 2^32 per draw): the group keeps the minimum
+                // low word, one vote per group checks it against the group's largest range, and the rare hit replays the whole
+                // group through the exact path from the saved state (same words are overwritten).  7 instead of 14 instructions
+                // per draw around the Philox rounds.
+                const uint32_t rem0 = rem_case, range0 = range;
+                uint32_t mn = 0xffffffffu;
+#pragma unroll
+                for (int jj = 0; jj < 4 * GEN_ILP; jj++) {
+                    const uint64_t prod = (uint64_t)w[jj >> 2][jj & 3] * range;
+                    mn = min(mn, (uint32_t)prod);
+                    range--;
+                    uint32_t bc;
+                    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %0;\n\t@q add.u32 %0, %0, -1;\n\tvote.sync.ballot.b32 %1, q, 0xffffffff;\n\t}"
+                                 : "+r"(rem_case), "=r"(bc) : "r"((uint32_t)(prod >> 32)));
+                    sc[ii + jj][warp] = bc;               // every lane stores the same word: no lane test, one broadcast store
+                }
+                if (__any_sync(0xffffffffu, mn < range0) || force_replay) {   // force_replay: test hook (PB_GEN_FORCE_REPLAY)
+                    rem_case = rem0; range = range0;
+#pragma unroll 1
+                    for (int q4 = 0; q4 < GEN_ILP; q4++) {      // cold path: the Philox words are recomputed, not kept addressable
+                        uint32_t ww[4];
+                        philox4x32_10((uint32_t)((i0 + ii) >> 2) + q4, r0, r1, 0u, k0, k1, ww);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) draw(ww[j], i0 + ii + 4 * q4 + j, ii + 4 * q4 + j);
+                    }
+                }
+            } else if (ii + 4 * GEN_ILP <= rows) {        // full group: no per-sample bounds checks (block-uniform)
 #pragma unroll
                 for (int jj = 0; jj < 4 * GEN_ILP; jj++) draw(w[jj >> 2][jj & 3], i0 + ii + jj, ii + jj);
             } else {
@@ -692,13 +720,14 @@ static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
 
 static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t nr, cudaStream_t st, int buf) {
     const unsigned gblocks = (unsigned)((nr + GEN_THREADS - 1) / GEN_THREADS);
+    const int force_replay = getenv("PB_GEN_FORCE_REPLAY") ? 1 : 0;   // every group also goes through the exact Lemire path
     if (pl.has_miss)
         k3_gen_kernel<0, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr,
                                                                (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words),
                                                                (uint32_t*)(ctx->d_Xmiss + buf * pl.buf_words), pl.Rw32);
     else
         k3_gen_kernel<0, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr,
-                                                                (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words), nullptr, pl.Rw32);
+                                                                (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words), nullptr, pl.Rw32, force_replay);
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -755,14 +784,17 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
 
     // ---- K2 observed tallies
     PB_CUDA(cudaEventRecord(ctx->ev[2], st));
+    pb_trace_mark(ctx, "start");
     k2_tally_kernel<<<(unsigned)std::max<int64_t>(1, (n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_csr, ctx->d_label);
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaEventRecord(ctx->ev[3], st));
+    pb_trace_mark(ctx, "tally");
 
     // ---- p-table, observed p-values, thresholds
     if ((rc = pbk_ptable(ctx))) return rc;
     if ((rc = pbk_thresholds(ctx))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev[4], st));
+    pb_trace_mark(ctx, "ptable+thresholds");
 
     // ---- null distribution, tiled over replicates
     {
@@ -838,6 +870,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
         }
         ctx->pregen_valid = false;
         if (!first_gen_timed) { PB_CUDA(cudaEventRecord(ctx->ev[6], st)); first_gen_timed = true; }
+        pb_trace_mark(ctx, "fill+wait_gen");
 
         // count in L2-sized column tiles of the generated matrix
         for (int64_t cb = 0; cb < nr; cb += pl.ctile) {
@@ -866,6 +899,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             if (side) PB_CUDA(cudaEventRecord(ctx->ev_side_join, ss));
             if (has_miss) k3_count_tight_kernel<true><<<tight_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, lc + 1);
             else k3_count_tight_kernel<false><<<tight_blocks, K3_THREADS, 0, st>>>(p, ctx->d_work + n_slots, lc + 1);
+            pb_trace_mark(ctx, "tight");
             if (side) PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_side_join, 0));
             // replicates whose minimum was not certified by a candidate are recomputed exactly
             PB_CUDA(cudaMemsetAsync(ctx->d_fb_count, 0, 4, st));
@@ -873,6 +907,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
                                                                                  ctx->d_fb_count);
             k3_fallback_kernel<<<(unsigned)std::min<int64_t>(cnr, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(p, ctx->d_fb_reps, ctx->d_fb_count,
                                                                                                            ctx->d_fb_total);
+            pb_trace_mark(ctx, "join+fallback");
             ctx->tm.n_launches += 8;
         }
         if (pl.nbuf == 2) PB_CUDA(cudaEventRecord(ctx->ev_cnt_b[buf], st));
@@ -890,6 +925,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     // ---- K4
     if ((rc = pbk_pvalues(ctx))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev[11], st));
+    pb_trace_mark(ctx, "allreduce+pvalues");
     struct { unsigned long long nf; unsigned int lc[4]; unsigned long long fb; } hb;   // layout of the scratch block in pbk_thresholds
     PB_CUDA(cudaMemcpyAsync(&hb, ctx->d_nfast, sizeof(hb), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
@@ -903,6 +939,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     cudaEventElapsedTime(&t, ctx->ev[9], ctx->ev[10]); ctx->tm.ms_allreduce = t;
     cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[11]); ctx->tm.ms_pvalues = t;
     cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[11]); ctx->tm.ms_assoc_total = t;
+    pb_trace_dump(ctx, "assoc");
     ctx->tm.n_fast_alleles = (int64_t)hb.nf;
     for (int c = 0; c < 4; c++) ctx->n_work[c] = (int64_t)hb.lc[c];
     ctx->tm.n_maxt_fallback_reps = (int64_t)hb.fb;

@@ -69,6 +69,7 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
     }
     if ((e = cudaEventCreateWithFlags(&ctx->ev_side_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_side_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_zero_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_k1_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_gen_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -78,6 +79,7 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
     if ((e = cudaMalloc(&ctx->d_raw_cursor, 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_class_counts, 16 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_fb_count, 4)) != cudaSuccess) return fail("cudaMalloc", e);
+    ctx->trace_on = getenv("PB_TRACE") != nullptr;
     *out = ctx;
     return PB_OK;
 }
@@ -90,8 +92,10 @@ extern "C" void pb_destroy(pb_ctx* ctx) {
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
     free_all(ctx);
+    for (auto& t : ctx->trace) cudaEventDestroy(t.second);
     if (ctx->ev_side_fork) cudaEventDestroy(ctx->ev_side_fork);
     if (ctx->ev_side_join) cudaEventDestroy(ctx->ev_side_join);
+    if (ctx->ev_zero_done) cudaEventDestroy(ctx->ev_zero_done);
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     if (ctx->ev_k1_done) cudaEventDestroy(ctx->ev_k1_done);
     if (ctx->ev_gen_done) cudaEventDestroy(ctx->ev_gen_done);
@@ -388,6 +392,7 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
     int rc;
     PB_CUDA(cudaEventRecord(ctx->ev[12], ctx->stream));
     for (int attempt = 0; attempt < 3; attempt++) {
+        if ((rc = pbk_prepare_tail(ctx))) return rc;
         if ((rc = pbk_events(ctx))) return rc;
         if (attempt == 0 && (rc = pbk_pregen_labels(ctx))) return rc;
         unsigned long long cur = 0;

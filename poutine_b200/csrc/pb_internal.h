@@ -3,8 +3,10 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/poutine_b200.h"
@@ -83,7 +85,7 @@ struct pb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // label-matrix pre-generation (K3a) alongside the K1 tail
     cudaStream_t stream3 = nullptr;          // K3b side stream: the few heavy short-list/long-list sweeps run next to the tight sweep
-    cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
+    cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr, ev_zero_done = nullptr;
     cudaEvent_t ev_k1_done = nullptr, ev_gen_started = nullptr, ev_gen_done = nullptr, ev_gen_b[2] = {nullptr, nullptr}, ev_cnt_b[2] = {nullptr, nullptr};
     bool pregen_valid = false; int64_t pregen_tile = 0;
     std::string err;
@@ -166,6 +168,10 @@ struct pb_ctx {
     // timing
     pb_timings tm{};
     cudaEvent_t ev[16]{};
+    // PB_TRACE=1: an event after every main-stream kernel of the tail / assoc, printed by pb_trace_dump (debug aid)
+    bool trace_on = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> trace;
+    size_t trace_used = 0;
 };
 
 #define PB_CUDA(call)                                                                             \
@@ -180,6 +186,7 @@ struct pb_ctx {
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------
 int pbk_events(pb_ctx* ctx);                                   // k1_events.cu
 int pbk_mask_last_word(pb_ctx* ctx);                           // k1_events.cu (clears the padding bits of site word W-1 in V)
+int pbk_prepare_tail(pb_ctx* ctx);                             // k1_events.cu (tail buffers + zero-fill on stream2, before K1)
 int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out); // k1_events.cu
 int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms);      // k3_null.cu (+ k4)
 int pbk_pregen_labels(pb_ctx* ctx);                            // k3_null.cu
@@ -193,3 +200,23 @@ int pbn_unique_id(void* id128, std::string& err);
 int pbn_init(pb_ctx* ctx, const void* id128, int rank, int world);
 int pbn_allreduce_min_f64(pb_ctx* ctx, double* buf, int64_t n);
 void pbn_destroy(pb_ctx* ctx);
+
+// debug timeline (PB_TRACE=1): mark = event on the main stream; dump after a synchronize
+static inline void pb_trace_mark(pb_ctx* ctx, const char* label) {
+    if (!ctx->trace_on) return;
+    if (ctx->trace_used == ctx->trace.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->trace.push_back({label, e}); }
+    ctx->trace[ctx->trace_used].first = label;
+    cudaEventRecord(ctx->trace[ctx->trace_used].second, ctx->stream);
+    ctx->trace_used++;
+}
+static inline void pb_trace_dump(pb_ctx* ctx, const char* what) {
+    if (!ctx->trace_on || ctx->trace_used < 2) { ctx->trace_used = 0; return; }
+    fprintf(stderr, "[poutine_b200 trace] %s:", what);
+    for (size_t i = 1; i < ctx->trace_used; i++) {
+        float t = 0; cudaEventElapsedTime(&t, ctx->trace[i - 1].second, ctx->trace[i].second);
+        fprintf(stderr, " %s %.1f", ctx->trace[i].first, t * 1000.f);
+    }
+    float tt = 0; cudaEventElapsedTime(&tt, ctx->trace[0].second, ctx->trace[ctx->trace_used - 1].second);
+    fprintf(stderr, " | total %.1f us\n", tt * 1000.f);
+    ctx->trace_used = 0;
+}

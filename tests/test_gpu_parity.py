@@ -249,6 +249,22 @@ def test_assoc_philox_bit_exact(oracle_mod, na_frac):
     np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), mt_u.view(np.uint64))
 
 
+def test_assoc_philox_replayed_groups(oracle_mod, monkeypatch):
+    """the label generator's fast groups skip the per-draw Lemire rejection test and replay a group through the
+    exact path when a retry may be needed; forcing the replay for every group must not change a bit"""
+    m = 1100
+    tree, o, hc, sn, lab = _assoc_case(oracle_mod, 180, 700, m, 43, 0.0, 0.0, seed=0xABCDEF0123)
+    st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=None, seed=0xABCDEF0123, n_threads=4)
+    g_st, g_mt = hc.assoc()
+    assert_stats_equal(g_st, st)
+    np.testing.assert_array_equal(g_mt.view(np.uint64), mt_s.view(np.uint64))
+    g_st, g_mt = g_st.copy(), g_mt.copy()
+    monkeypatch.setenv("PB_GEN_FORCE_REPLAY", "1")
+    hc.count_all_homoplasy_events()
+    g_st2, g_mt2 = hc.assoc()
+    assert g_st2.tobytes() == g_st.tobytes() and g_mt2.tobytes() == g_mt.tobytes()
+
+
 @pytest.mark.parametrize("na_frac,replay,gen_kb", [(0.0, False, None), (0.03, False, "128"), (0.0, True, "128"), (0.0, False, "16")])
 def test_assoc_multi_tile(oracle_mod, monkeypatch, na_frac, replay, gen_kb):
     """replicates split into several generation tiles (double-buffered on the second stream), each counted in

@@ -25,9 +25,12 @@ for l in dis[start + 1:]:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         insts.append((cur, m.group(2)))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + (sys.argv[5] if len(sys.argv) > 5 else kern)], capture_output=True, text=True).stdout
 r = list(csv.reader(io.StringIO(out)))
 h, rows = r[1], r[2:]
+nxt = [i for i, x in enumerate(rows) if x and x[0] == 'Kernel Name']   # several launches matched: keep the first
+if nxt:
+    rows = rows[:nxt[0]]
 ix = {n: i for i, n in enumerate(h)}
 assert len(rows) == len(insts), (len(rows), len(insts))
 by = collections.defaultdict(lambda: [0, 0, 0])
