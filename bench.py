@@ -217,6 +217,14 @@ def run_b200(args):
         host_planes.append(h[:, :W])
     cpu_chars = synth.planes_to_chars(B0, B1, V, 0, min(CPU_SAMPLE_SITES, S)) if rank == 0 and world == 1 else None
     del B0, B1, V
+    # compact form of the same input (one plane + per-column site masks) when every site has at most two bases:
+    # prepared once on the host, like the planes themselves; the e2e leg then uploads a third of the bytes
+    hX, pX = _lib.pinned_empty((N, Wp), np.uint64)
+    hX[:, W:] = 0
+    pinned.append(pX)
+    t_c = time.perf_counter()
+    compact = None if args.full_planes_only else pb.compact_planes(*host_planes, S, X=hX)
+    t_compact = time.perf_counter() - t_c
     t_gen = time.perf_counter() - t_gen
 
     hc = pb.HomoplasyCounter(num_replicates=m, min_hcount=1, device=local_rank, seed=20260, site_offset=rank * (W * 64))
@@ -236,9 +244,12 @@ def run_b200(args):
 
     e2e_parts = {"put_planes": 0.0, "events": 0.0, "assoc": 0.0}
 
-    def step_e2e():
+    def step_e2e(use_compact=True):
         t0 = time.perf_counter()
-        hc.put_planes(*host_planes)                      # H2D of this step's inputs (pinned host memory)
+        if use_compact and compact is not None:          # H2D of this step's inputs (pinned host memory) + device expansion
+            hc.put_planes_biallelic(compact[0], None if compact[2] else host_planes[2], compact[1])
+        else:
+            hc.put_planes(*host_planes)
         t1 = time.perf_counter()
         ev, cc = hc.count_all_homoplasy_events(compact=False)   # D2H: per-site Homoplasy_Events records (page-locked buffer)
         t2 = time.perf_counter()
@@ -286,8 +297,23 @@ def run_b200(args):
         tm_e, ev, st, mt = step_e2e()
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
-    clocks = sampler.stop() if sampler else None      # sampled over both timed regions (resident + end to end)
-    h2d = 3 * N * Wp * 8                                  # what pb_put_planes copies (rows padded to the device pitch)
+    e2e_breakdown = {k: v / args.steps for k, v in e2e_parts.items()}
+    h2d_full = 3 * N * Wp * 8                             # what pb_put_planes copies (rows padded to the device pitch)
+    h2d = h2d_full
+    e2e_full = None
+    if compact is not None:
+        # the same end-to-end step with the plain three-plane upload, reported next to the headline
+        h2d = (1 if compact[2] else 2) * N * Wp * 8 + W * 32
+        step_e2e(False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e(False)
+        barrier()
+        full_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        e2e_full = {"value": total_sites * args.steps / (full_ms / 1e3), "unit": "sites/s", "ms_per_step": full_ms / args.steps,
+                    "h2d_bytes_per_step": h2d_full, "upload": "pb_put_planes (three planes)"}
+    clocks = sampler.stop() if sampler else None      # sampled over all timed regions (resident + end to end)
     d2h = S * _lib.SITE_DTYPE.itemsize + len(st) * _lib.STAT_DTYPE.itemsize + m * 8
     e2e_value = total_sites * args.steps / (e2e_ms / 1e3)
     n_draws = sum_over_ranks(tm["n_alleles_in_use"]) * m
@@ -324,7 +350,11 @@ def run_b200(args):
                 "config": bench_config(args, cfg, S, m, tree, world),
                 "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps,
-                        "breakdown_ms": {k: v / args.steps for k, v in e2e_parts.items()}, "timer": "host wall clock around synchronous C-ABI calls, max over ranks"},
+                        "breakdown_ms": e2e_breakdown, "timer": "host wall clock around synchronous C-ABI calls, max over ranks",
+                        "upload": ("pb_put_planes_biallelic (X plane%s + site masks, expanded on the device; host-side compaction "
+                                   "%.2f s once, outside the timed region like the FASTA packing)" % ("" if compact[2] else " + V plane", t_compact))
+                                  if compact is not None else "pb_put_planes (three planes)",
+                        "full_planes": e2e_full},
                 "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "replicate_draws_per_sec": n_draws * args.steps / (dev_ms / 1e3),
@@ -354,6 +384,7 @@ def main():
     ap.add_argument("--sites", type=int, default=0, help="override sites per GPU (scaled-down runs)")
     ap.add_argument("--replicates", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-planes-only", action="store_true", help="e2e leg uploads three planes even when the input is biallelic")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)

@@ -139,6 +139,17 @@ int pb_set_sites(pb_ctx* ctx, int64_t n_sites);
 int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
                   const uint64_t* B0, const uint64_t* B1, const uint64_t* V);
 
+/* Compact upload of a column tile in which every site carries at most TWO distinct bases over all nodes (the usual
+ * biallelic SNP alignment): one plane instead of three crosses PCIe, the library expands it on the device into the same
+ * B0/B1/V rows pb_put_planes would have written (identical results; under V = 0 the B bits are don't-care).
+ *   X        bit = the node's genotype is the site's second base (0 = its first base, or not a valid base)
+ *   V        as in pb_put_planes, or NULL when every genotype of the tile is an upper-case ACGT
+ *   colmask  n_words x 4 words {A0, A1, D0, D1}: per site the 2-bit code of the first base (A1:A0) and first XOR second
+ *            base (D1:D0); the device computes B0 = A0 ^ (X & D0), B1 = A1 ^ (X & D1)
+ * pb_compact_planes (host helper below) derives X / colmask from full planes and says whether the tile qualifies. */
+int pb_put_planes_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
+                            const uint64_t* X, const uint64_t* V, const uint64_t* colmask);
+
 /* count_all_homoplasy_events (HC.java:1402).  per_site (n_sites records) and counts may be NULL.
  * If pb_set_labels was called before (Philox mode), the label matrix of the first replicate tile is generated on a
  * second stream behind the event kernel, so that pb_run_assoc finds it ready: set labels first, then run events. */
@@ -173,6 +184,13 @@ int pb_comm_init(pb_ctx* ctx, const void* id128, int32_t rank, int32_t world);
  * Fasta_Record -> plane step of the host (HC.java:1252-1266). */
 int pb_pack_chars(const char* seq, int64_t n_nodes, int64_t n_sites, int64_t seq_pitch,
                   uint64_t* B0, uint64_t* B1, uint64_t* V, int64_t pitch_words);
+/* Tries to compact a tile of full planes (n_sites = sites of the TILE, rows at pitch_words) for pb_put_planes_biallelic.
+ * Returns 1 and fills X (rows at x_pitch_words), colmask (4 words per word column) and *all_valid (1: V may be passed as
+ * NULL) when every site of the tile has at most two distinct valid bases over all nodes; returns 0 (outputs undefined)
+ * when some site has three or more: upload that tile with pb_put_planes.  n_threads 0 = all host threads. */
+int pb_compact_planes(const uint64_t* B0, const uint64_t* B1, const uint64_t* V, int64_t n_nodes, int64_t n_sites,
+                      int64_t pitch_words, uint64_t* X, int64_t x_pitch_words, uint64_t* colmask, int32_t* all_valid,
+                      int32_t n_threads);
 /* FASTA -> planes at speed (host side of HC.java:1241-1306; record semantics of compiled/Fasta_Manager.class next()):
  * the file is mmap'ed and indexed once; pb_fasta_pack_tile packs the column tile [site_begin, site_begin+n_sites_tile)
  * (site_begin % 64 == 0) of every record into row node_of_record[i] (-1 = skip) of tile-local planes, multi-threaded,

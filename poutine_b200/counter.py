@@ -44,6 +44,26 @@ def pack_chars(seq: np.ndarray, pitch_words: int | None = None):
     return B0, B1, V
 
 
+def compact_planes(B0, B1, V, n_sites, X=None, n_threads=0):
+    """Full planes of a column tile -> (X, colmask, all_valid) for put_planes_biallelic, or None when some site of the
+    tile carries three or more distinct bases over all nodes (host helper pb_compact_planes, csrc/packer.cpp)."""
+    for a in (B0, B1, V):
+        assert a.dtype == np.uint64 and a.ndim == 2 and a.strides[1] == 8
+    assert B0.shape == B1.shape == V.shape and B0.strides == B1.strides == V.strides
+    N, W = B0.shape[0], (n_sites + 63) // 64
+    assert B0.shape[1] >= W
+    if X is None:
+        X = np.empty((N, W), dtype=np.uint64)
+    assert X.dtype == np.uint64 and X.shape[0] == N and X.shape[1] >= W and X.strides[1] == 8
+    colmask = np.empty((W, 4), dtype=np.uint64)
+    av = C.c_int32(0)
+    rc = _lib.lib().pb_compact_planes(ptr(B0), ptr(B1), ptr(V), N, int(n_sites), B0.strides[0] // 8, ptr(X), X.strides[0] // 8,
+                                      ptr(colmask), C.byref(av), int(n_threads))
+    if rc < 0:
+        raise PoutineError(rc, "pb_compact_planes: invalid arguments")
+    return (X[:, :W], colmask, bool(av.value)) if rc == 1 else None
+
+
 class HomoplasyCounter:
     """One GPU context.  Usage mirrors Homoplasy_Counter.call() (HC.java:296-314):
 
@@ -131,13 +151,34 @@ class HomoplasyCounter:
         assert B0.strides == B1.strides == V.strides
         self._check(_lib.lib().pb_put_planes(self._h, int(word_begin), B0.shape[1], B0.strides[0] // 8, ptr(B0), ptr(B1), ptr(V)))
 
-    def set_planes(self, B0, B1, V, n_sites, tile_words=None):
+    def put_planes_biallelic(self, X, V, colmask, word_begin=0):
+        """Compact upload of a column tile whose sites carry at most two bases (see compact_planes): X, optionally V
+        (None = every genotype valid) and the per-word-column site masks; expanded on the device."""
+        assert X.dtype == np.uint64 and X.ndim == 2 and X.shape[0] == self.n_nodes and X.strides[1] == 8
+        if V is not None:
+            assert V.dtype == np.uint64 and V.shape == X.shape
+            if V.strides != X.strides:       # the C ABI takes one row pitch for both planes
+                v2 = np.empty((X.shape[0], X.strides[0] // 8), dtype=np.uint64)[:, :X.shape[1]]
+                v2[...] = V
+                V = v2
+        colmask = np.ascontiguousarray(colmask, dtype=np.uint64)
+        assert colmask.shape == (X.shape[1], 4)
+        self._check(_lib.lib().pb_put_planes_biallelic(self._h, int(word_begin), X.shape[1], X.strides[0] // 8, ptr(X), ptr(V),
+                                                       ptr(colmask)))
+
+    def set_planes(self, B0, B1, V, n_sites, tile_words=None, compact=False):
+        """compact=True: every tile that qualifies goes up as one plane (put_planes_biallelic), the others as three."""
         self.set_sites(n_sites)
         W = (n_sites + 63) // 64
         tw = tile_words or W
         for w0 in range(0, W, tw):
             w1 = min(W, w0 + tw)
-            self.put_planes(B0[:, w0:w1], B1[:, w0:w1], V[:, w0:w1], w0)
+            b0, b1, v = B0[:, w0:w1], B1[:, w0:w1], V[:, w0:w1]
+            c = compact_planes(b0, b1, v, min(n_sites, w1 * 64) - w0 * 64) if compact else None
+            if c is not None:
+                self.put_planes_biallelic(c[0], None if c[2] else v, c[1], w0)
+            else:
+                self.put_planes(b0, b1, v, w0)
 
     def set_seg_sites(self, chars):
         B0, B1, V = pack_chars(chars)

@@ -574,6 +574,37 @@ int pbk_mask_last_word(pb_ctx* ctx) {
     return PB_OK;
 }
 
+// ---- compact (biallelic) upload: expand X in place --------------------------------------------------------
+// pb_put_planes_biallelic copied the tile's X plane into the B0 rows: B0 = A0 ^ (X & D0), B1 = A1 ^ (X & D1), and, when
+// the caller sent no V plane, V = all sites valid (padding bits of site word W-1 excluded).  One thread owns one word
+// column (its four masks stay in registers) and walks a slice of the rows: 8 B read + 16/24 B written per node word.
+__global__ void k1_expand_biallelic_kernel(uint64_t* __restrict__ B0, uint64_t* __restrict__ B1, uint64_t* __restrict__ V, int32_t N,
+                                           int64_t Wp, int64_t w0, int64_t nw, const uint64_t* __restrict__ colmask, int fill_v,
+                                           int64_t w_last, uint64_t last_mask) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nw) return;
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(colmask + 4 * c), d = *reinterpret_cast<const ulonglong2*>(colmask + 4 * c + 2);
+    const int64_t w = w0 + c;
+    const uint64_t full = w == w_last ? last_mask : ~0ull;
+    for (int32_t v = blockIdx.y; v < N; v += gridDim.y) {
+        const int64_t o = (int64_t)v * Wp + w;
+        const uint64_t x = B0[o];
+        B0[o] = a.x ^ (x & d.x);
+        B1[o] = a.y ^ (x & d.y);
+        if (fill_v) V[o] = full;
+    }
+}
+
+int pbk_expand_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, const uint64_t* d_colmask, bool fill_v) {
+    const uint64_t last_mask = (ctx->S & 63) ? (1ull << (ctx->S & 63)) - 1 : ~0ull;
+    const unsigned gx = (unsigned)((n_words + 127) / 128);
+    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->N, ((int64_t)ctx->sm_count * 16 + gx - 1) / gx));
+    k1_expand_biallelic_kernel<<<dim3(gx, gy), 128, 0, ctx->stream>>>(ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->N, ctx->Wp, word_begin, n_words,
+                                                                     d_colmask, fill_v ? 1 : 0, ctx->W - 1, last_mask);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
 int pbk_events(pb_ctx* ctx) {
     K1Params p;
     p.W = ctx->W;

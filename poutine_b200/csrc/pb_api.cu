@@ -19,7 +19,7 @@ static void free_all(pb_ctx* c) {
     void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_node_sample, c->d_label, c->d_planes,
                     c->d_census, c->d_census_total, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
                     c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT,
-                    c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop};
+                    c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop, c->d_colmask};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -380,6 +380,37 @@ extern "C" int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, i
                                       (size_t)ctx->N, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (word_begin + n_words == ctx->W) { int rc = pbk_mask_last_word(ctx); if (rc) return rc; }
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers are caller-owned: do not retain them past return
+    return PB_OK;
+}
+
+extern "C" int pb_put_planes_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* X,
+                                       const uint64_t* V, const uint64_t* colmask) {
+    CHECK_CTX(ctx);
+    if (!ctx->d_B0) FAIL(ctx, PB_ERR_INVALID, "pb_put_planes_biallelic: call pb_set_sites first");
+    if (!X || !colmask || word_begin < 0 || n_words < 1 || word_begin + n_words > ctx->W || src_pitch_words < n_words)
+        FAIL(ctx, PB_ERR_INVALID, "pb_put_planes_biallelic: tile out of range");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    ctx->events_done = ctx->assoc_done = false;
+    if (n_words > ctx->colmask_cap) {
+        if (ctx->d_colmask) { cudaFree(ctx->d_colmask); ctx->d_colmask = nullptr; ctx->colmask_cap = 0; }
+        PB_CUDA(cudaMalloc(&ctx->d_colmask, (size_t)n_words * 32));
+        ctx->colmask_cap = n_words;
+    }
+    PB_CUDA(cudaMemcpyAsync(ctx->d_colmask, colmask, (size_t)n_words * 32, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t* src[2] = {X, V};
+    uint64_t* dst[2] = {ctx->d_B0, ctx->d_V};       // X lands in the B0 rows and is expanded in place
+    for (int i = 0; i < 2; i++) {
+        if (!src[i]) continue;
+        if (word_begin == 0 && n_words == ctx->W && src_pitch_words == ctx->Wp)
+            PB_CUDA(cudaMemcpyAsync(dst[i], src[i], (size_t)ctx->N * ctx->Wp * 8, cudaMemcpyHostToDevice, ctx->stream));
+        else
+            PB_CUDA(cudaMemcpy2DAsync(dst[i] + word_begin, (size_t)ctx->Wp * 8, src[i], (size_t)src_pitch_words * 8, (size_t)n_words * 8,
+                                      (size_t)ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int rc = pbk_expand_biallelic(ctx, word_begin, n_words, ctx->d_colmask, V == nullptr);
+    if (rc) return rc;
+    if (V && word_begin + n_words == ctx->W) { rc = pbk_mask_last_word(ctx); if (rc) return rc; }
     PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers are caller-owned: do not retain them past return
     return PB_OK;
 }

@@ -112,6 +112,7 @@ struct pb_ctx {
     uint64_t* d_planes = nullptr;   // one allocation [3][N][Wp]: plane 0 = V, 1 = B0, 2 = B1
     uint64_t *d_B0 = nullptr, *d_B1 = nullptr, *d_V = nullptr;   // views into d_planes
     CUtensorMap tmap{};             // 3-D TMA descriptor over d_planes: box = 128 words x 1 node x 3 planes
+    uint64_t* d_colmask = nullptr; int64_t colmask_cap = 0;   // [n_words][4] site masks of a compact (biallelic) tile upload
 
     // K1 outputs
     uint64_t* d_census = nullptr;      // [n_flush][4][KS][W]
@@ -186,6 +187,7 @@ struct pb_ctx {
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------
 int pbk_events(pb_ctx* ctx);                                   // k1_events.cu
 int pbk_mask_last_word(pb_ctx* ctx);                           // k1_events.cu (clears the padding bits of site word W-1 in V)
+int pbk_expand_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, const uint64_t* d_colmask, bool fill_v);  // k1_events.cu
 int pbk_prepare_tail(pb_ctx* ctx);                             // k1_events.cu (tail buffers + zero-fill on stream2, before K1)
 int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out); // k1_events.cu
 int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms);      // k3_null.cu (+ k4)

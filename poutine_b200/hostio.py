@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import ptr
-from .counter import HomoplasyCounter
+from .counter import HomoplasyCounter, compact_planes
 from .synth import Tree
 
 DELIMS = "(),:;"
@@ -310,7 +310,7 @@ def write_outputs(out_path: str, sites, stats, physical_pos):
 # call() with --use-precomputed-anc-recon
 # -------------------------------------------------------------------------------------------------
 def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_replicates=100000, min_hcount=1, seed=0, device=0,
-                          tile_sites=1 << 17, pack_threads=0):
+                          tile_sites=1 << 17, pack_threads=0, compact_upload=True):
     """Files in, files out: same inputs as `poutine.sh -u -f -t -p -m`, same three result files.
     `tree_file` is a Newick file with internal node labels, or treetime's annotated_tree.nexus."""
     with open(tree_file) as f:
@@ -348,19 +348,24 @@ def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_
     # stream the alignment: pack tile t+1 on a worker thread (the C packer releases the GIL) while tile t uploads
     tile_sites = max(64, (tile_sites // 64) * 64)
     tw = tile_sites // 64
+    # A tile whose sites all carry at most two bases (the usual SNP alignment) is compacted on the worker thread too and
+    # goes up as one plane (+ V when some call is not a base) instead of three: buffer slot 3 holds X.
     bufs = []
     for _ in range(2):
-        arrs = [_lib.pinned_empty((tree.n_nodes, tw), np.uint64) for _ in range(3)]
+        arrs = [_lib.pinned_empty((tree.n_nodes, tw), np.uint64) for _ in range(4)]
         bufs.append(arrs)
     starts = list(range(0, S, tile_sites))
+    compacted = [None, None]
 
     def pack(k):
         s0 = starts[k]
         ns = min(tile_sites, S - s0)
-        B0, B1, V = (a[0] for a in bufs[k & 1])
+        B0, B1, V, X = (a[0] for a in bufs[k & 1])
         fa.pack_tile(node_of_record, s0, ns, B0, B1, V, pack_threads)
+        compacted[k & 1] = compact_planes(B0, B1, V, ns, X=X, n_threads=pack_threads) if compact_upload else None
 
     worker = None
+    n_compact_tiles = 0
     if starts:
         pack(0)
     for k, s0 in enumerate(starts):
@@ -369,15 +374,21 @@ def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_
             worker.start()
         ns = min(tile_sites, S - s0)
         nw = (ns + 63) // 64
-        B0, B1, V = (a[0][:, :nw] for a in bufs[k & 1])
-        hc.put_planes(B0, B1, V, s0 // 64)
+        B0, B1, V = (a[0][:, :nw] for a in bufs[k & 1][:3])
+        c = compacted[k & 1]
+        if c is not None:
+            hc.put_planes_biallelic(c[0], None if c[2] else V, c[1], s0 // 64)
+            n_compact_tiles += 1
+        else:
+            hc.put_planes(B0, B1, V, s0 // 64)
         if worker is not None:
             worker.join()
             worker = None
     all_events, counts = hc.count_all_homoplasy_events(compact=False)
     stats, maxT = hc.assoc()
     write_outputs(out_path, all_events, stats, physical_pos)
-    result = dict(counts=counts, n_informative=len(stats), n_sites=S, n_nodes=tree.n_nodes, n_samples=len(label))
+    result = dict(counts=counts, n_informative=len(stats), n_sites=S, n_nodes=tree.n_nodes, n_samples=len(label),
+                  n_tiles=len(starts), n_compact_tiles=n_compact_tiles)
     fa.close()
     hc.close()
     for arrs in bufs:

@@ -138,6 +138,64 @@ def test_events_tiled_upload_and_pitch(oracle_mod):
     assert cc1["tri"] + cc1["quad"] > 0
 
 
+@pytest.mark.parametrize("gaps,S", [(False, 64 * 41 + 11), (True, 64 * 41 + 11), (False, 64 * 32)])
+def test_events_compact_biallelic_upload(oracle_mod, gaps, S):
+    """pb_put_planes_biallelic (one plane over PCIe, expanded on the device) == pb_put_planes == oracle; tiles that do
+    not qualify (a third base somewhere in the tile) go up as full planes in the same run; end-to-end through assoc."""
+    tree = synth.yule_tree(150, 8)
+    B0, B1, V = synth.simulate_planes(tree, S, 3, leaf_gap=gaps)
+    if gaps:   # arbitrary B bits under V = 0, as a packer fed lower-case / N calls would leave them
+        rng = np.random.default_rng(5)
+        B0 = B0 ^ (rng.integers(0, 2**63, size=B0.shape, dtype=np.uint64) & ~V)
+        B1 = B1 ^ (rng.integers(0, 2**63, size=B1.shape, dtype=np.uint64) & ~V)
+    chars = synth.planes_to_chars(B0, B1, V, 0, S)
+    site = 64 * 12 + 5                                              # one site of tile 2 (tile_words = 6) gets a third base
+    third = [b for b in b"ACGT" if b not in set(chars[:, site].tolist())][0]
+    chars[tree.leaf_nodes[3], site] = third
+    B0, B1, V = pb.pack_chars(chars)
+    sn, lab = synth.simulate_phenotypes(tree, 4)
+    res = []
+    for compact in (False, True):
+        hc = pb.HomoplasyCounter(num_replicates=256, seed=3)
+        hc.set_tree(tree.parent, tree.is_leaf)
+        hc.set_phenos(sn, lab)
+        hc.set_planes(B0, B1, V, S, tile_words=6, compact=compact)
+        ev, cc = hc.count_all_homoplasy_events()
+        st, mt = hc.assoc()
+        res.append((ev.tobytes(), cc, st.tobytes(), mt.tobytes()))
+        if compact:
+            o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+            or_ev, or_cc = o.count_all_homoplasy_events(chars)
+            assert_events_equal(ev, cc, or_ev, or_cc)
+        hc.close()
+    assert res[0] == res[1]
+    W = (S + 63) // 64
+    n_compact = sum(pb.compact_planes(B0[:, w:w + 6], B1[:, w:w + 6], V[:, w:w + 6], min(S, (w + 6) * 64) - w * 64) is not None
+                    for w in range(0, W, 6))
+    assert n_compact == (W + 5) // 6 - 1                            # exactly the doctored tile was refused
+    # whole-alignment compact upload with device-pitch rows (flat-copy path)
+    chars[tree.leaf_nodes[3], site] = chars[tree.root, site]
+    B0, B1, V = pb.pack_chars(chars)
+    Wp = (W + 15) & ~15
+    Xp = np.full((tree.n_nodes, Wp), np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+    X, colmask, all_valid = pb.compact_planes(B0, B1, V, S, X=Xp)
+    assert all_valid == (not gaps)
+    Vp = None
+    if gaps:
+        Vp = np.zeros((tree.n_nodes, Wp), dtype=np.uint64)
+        Vp[:, :W] = V
+        Vp = Vp[:, :W]
+    hc = pb.HomoplasyCounter(num_replicates=16)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_sites(S)
+    hc.put_planes_biallelic(X, Vp, colmask)
+    ev, cc = hc.count_all_homoplasy_events()
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(chars)
+    assert_events_equal(ev, cc, or_ev, or_cc)
+    hc.close()
+
+
 def test_events_many_chunks_and_site_offset(oracle_mod, monkeypatch):
     """force the edge schedule into many chunks (census partials are summed across chunks)"""
     tree = synth.yule_tree(700, 11)

@@ -50,6 +50,51 @@ def test_nexus_to_newick(tmp_path):
     assert _by_name(hostio.parse_newick(nwk)) == _by_name(t)
 
 
+# ---- biallelic compaction (host helper of the compact upload) ---------------------------------------------
+def _expand(X, colmask):
+    A0, A1, D0, D1 = (colmask[:, i][None, :] for i in range(4))
+    return A0 ^ (X & D0), A1 ^ (X & D1)
+
+
+@pytest.mark.parametrize("n_sites,gaps", [(64 * 70 + 13, False), (64 * 3, True), (50, True), (64 * 130 + 1, False)])
+def test_compact_planes_roundtrip(n_sites, gaps):
+    t = synth.yule_tree(60, 5)
+    B0, B1, V = synth.simulate_planes(t, n_sites, 9, leaf_gap=gaps)
+    rng = np.random.default_rng(1)
+    if gaps:   # garbage under V = 0 must not matter (lower-case / N calls carry arbitrary B bits)
+        B0 = B0 ^ (rng.integers(0, 2**63, size=B0.shape, dtype=np.uint64) & ~V)
+        B1 = B1 ^ (rng.integers(0, 2**63, size=B1.shape, dtype=np.uint64) & ~V)
+    c = pb.compact_planes(B0, B1, V, n_sites)
+    assert c is not None
+    X, colmask, all_valid = c
+    assert all_valid == (not gaps)
+    e0, e1 = _expand(X, colmask)
+    np.testing.assert_array_equal(e0 & V, B0 & V)
+    np.testing.assert_array_equal(e1 & V, B1 & V)
+    np.testing.assert_array_equal(X & ~V, np.zeros_like(X))            # X is canonical: 0 where the genotype is not a base
+    # multi-threaded and single-threaded runs agree
+    c1 = pb.compact_planes(B0, B1, V, n_sites, n_threads=1)
+    np.testing.assert_array_equal(c1[0], X)
+    np.testing.assert_array_equal(c1[1], colmask)
+
+
+def test_compact_planes_rejects_third_base():
+    t = synth.yule_tree(40, 2)
+    n_sites = 64 * 5 + 9
+    B0, B1, V = synth.simulate_planes(t, n_sites, 4)
+    assert pb.compact_planes(B0, B1, V, n_sites) is not None
+    chars = synth.planes_to_chars(B0, B1, V, 0, n_sites)
+    col = chars[:, 200]
+    third = [b for b in b"ACGT" if b not in set(col.tolist())][0]
+    chars[17, 200] = third                                           # one internal or leaf node carries a third base
+    b0, b1, v = pb.pack_chars(chars)
+    assert pb.compact_planes(b0, b1, v, n_sites) is None
+    chars[17, 200] = ord("n")                                        # ... an invalid call instead is fine, with V uploaded
+    b0, b1, v = pb.pack_chars(chars)
+    c = pb.compact_planes(b0, b1, v, n_sites)
+    assert c is not None and c[2] is False
+
+
 # ---- pheno / map ---------------------------------------------------------------------------------------------
 def test_pheno_and_map_readers(tmp_path):
     p = tmp_path / "ph.tsv"
@@ -148,11 +193,12 @@ def test_write_outputs_format_and_sorts(tmp_path):
 
 # ---- files in, files out (GPU) ----------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("nexus,line_width", [(False, 0), (True, 70)])
-def test_run_homoplasy_counter_matches_oracle(tmp_path, oracle_mod, nexus, line_width):
+@pytest.mark.parametrize("nexus,line_width,multi", [(False, 0, 0.05), (True, 70, 0.05), (False, 60, 0.002)])
+def test_run_homoplasy_counter_matches_oracle(tmp_path, oracle_mod, nexus, line_width, multi):
     t = synth.yule_tree(200, 11)
     S = 64 * 40 + 9
-    chars = synth.planes_to_chars(*synth.simulate_planes(t, S, 12, leaf_gap=True, multiallelic_frac=0.05), 0, S)
+    # multi = 0.002: a handful of multi-allelic sites, so most upload tiles are compact (one plane) and a few are full
+    chars = synth.planes_to_chars(*synth.simulate_planes(t, S, 12, leaf_gap=True, multiallelic_frac=multi), 0, S)
     sn, lab = synth.simulate_phenotypes(t, 13, na_frac=0.03, no_row_frac=0.02)
     paths = synth.write_inputs(str(tmp_path), t, chars, sn, lab, line_width=line_width, nexus=nexus, seed=5)
     out = str(tmp_path / "run.out")
@@ -164,6 +210,8 @@ def test_run_homoplasy_counter_matches_oracle(tmp_path, oracle_mod, nexus, line_
     ev, cc = o.count_all_homoplasy_events(chars, paths["physical_pos"].astype(np.int32))
     st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=None, seed=21, n_threads=4)
     assert res["counts"]["bi"] == cc["bi"] and res["n_informative"] == len(st)
+    if multi < 0.01:
+        assert 0 < res["n_compact_tiles"] < res["n_tiles"]
     from poutine_b200._lib import SITE_DTYPE, STAT_DTYPE
     sites = np.zeros(S, dtype=SITE_DTYPE)
     for f in ("segsite_id", "allele1", "allele2", "a1_count", "a2_count", "a1_extant", "a2_extant"):
