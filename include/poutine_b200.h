@@ -162,6 +162,17 @@ int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts);
 int pb_run_assoc(pb_ctx* ctx, const uint32_t* replay_perms, pb_stat_out* per_inf_site, int64_t cap,
                  int64_t* n_inf, double* maxT_sorted);
 
+/* Two per-site statistics outside the reference's LIVE path, on request after pb_run_assoc (either pointer may be NULL).
+ * PARITY UNPINNED: the reference has no runnable counterpart; checked against exact rational arithmetic (1e-12 relative).
+ *   exact_pointwise[2*i + a]  the m -> infinity limit of allele a's point-wise estimate r/m (HC.java:4812-4838) for
+ *                             informative site i: the exact probability, under a uniform permutation of the pheno
+ *                             labels (HC.java:4890-4923), that a replicate's f(n_r, k_r) <= p_obs (HC.java:4239);
+ *                             NaN when the allele is not in use.  
+ *   fisher_p[i]               two-sided Fisher's exact p-value of {a1case, a1ctrl; a2case, a2ctrl} (= obs_counts), R's
+ *                             fisher.test definition; the reference's dead fishers_exact path (HC.java:5008-5093) pipes
+ *                             the same table to an R script that is not in its repository. */
+int pb_run_extras(pb_ctx* ctx, double* exact_pointwise /* 2*n_inf */, double* fisher_p /* n_inf */);
+
 /* Introspection used by the parity tests. */
 int pb_get_sites(pb_ctx* ctx, pb_site_out* per_site);
 int pb_get_raw_events(pb_ctx* ctx, int64_t cap, int32_t* site, int32_t* node, int64_t* n);

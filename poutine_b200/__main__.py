@@ -26,6 +26,8 @@ def main(argv=None):
     ap.add_argument("-X", "--force-overwrite", action="store_true")
     ap.add_argument("--seed", type=int, default=None, help="Philox seed (default: from the clock, like the reference's unseeded RNG)")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--extras", action="store_true", help="also write <out>.extras: exact point-wise null + two-sided Fisher "
+                                                          "(not reference outputs; the three reference files are unchanged)")
     a = ap.parse_args(argv)
     if not a.use_precomputed_anc_recon:
         ap.error("only --use-precomputed-anc-recon (-u) mode is supported: ancestral reconstruction stays with the Java host / treetime")
@@ -40,7 +42,7 @@ def main(argv=None):
     t0 = time.time()
     try:
         res = hostio.run_homoplasy_counter(a.fasta, a.tree, a.phenos, a.map, out, num_replicates=a.replicates, min_hcount=a.min_hcount,
-                                           seed=seed, device=a.device, pack_threads=a.threads)
+                                           seed=seed, device=a.device, pack_threads=a.threads, extras=a.extras)
     except NoInformativeSites:
         print("min_hcount = %d is set too high and has filtered out all segregating sites" % a.min_hcount)     # HC.java:3866-3869
         return 255

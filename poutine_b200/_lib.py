@@ -52,7 +52,7 @@ class PbTimings(C.Structure):
 
 EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_set_tree", "pb_set_labels", "pb_set_sites", "pb_put_planes",
            "pb_put_planes_biallelic", "pb_compact_planes",
-           "pb_run_events", "pb_run_assoc", "pb_get_sites", "pb_get_raw_events", "pb_get_event_csr",
+           "pb_run_events", "pb_run_assoc", "pb_run_extras", "pb_get_sites", "pb_get_raw_events", "pb_get_event_csr",
            "pb_get_maxT_unsorted", "pb_get_ptable", "pb_get_timings", "pb_stopwatch_mark", "pb_stopwatch_ms", "pb_comm_unique_id", "pb_comm_init",
            "pb_pack_chars", "pb_host_alloc", "pb_host_free", "pb_version",
            "pb_fasta_open", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_record", "pb_fasta_pack_tile", "pb_fasta_last_error"]
@@ -90,6 +90,7 @@ def lib():
         L.pb_compact_planes.argtypes = [vp, vp, vp, i64, i64, i64, vp, i64, vp, C.POINTER(i32), i32]
         L.pb_run_events.argtypes = [vp, vp, C.POINTER(PbClassCounts)]
         L.pb_run_assoc.argtypes = [vp, vp, vp, i64, C.POINTER(i64), vp]
+        L.pb_run_extras.argtypes = [vp, vp, vp]
         L.pb_get_sites.argtypes = [vp, vp]
         L.pb_get_raw_events.argtypes = [vp, i64, vp, vp, C.POINTER(i64)]
         L.pb_get_event_csr.argtypes = [vp, vp, vp, i64]

@@ -220,6 +220,16 @@ class HomoplasyCounter:
         self.n_informative = n_inf.value
         return (stats[:n_inf.value] if fetch else None), maxT
 
+    def extras(self):
+        """-> (exact_pointwise float64[n_inf, 2], fisher_p float64[n_inf]) after assoc().  Outside the reference's live
+        path (parity unpinned): the exact m -> infinity limit of the point-wise estimate under the label-permutation
+        null, and R-style two-sided Fisher's exact p of the obs_counts table (dead code in the reference)."""
+        n = self.n_informative
+        ep = np.empty((n, 2), dtype=np.float64)
+        fp = np.empty(n, dtype=np.float64)
+        self._check(_lib.lib().pb_run_extras(self._h, ptr(ep), ptr(fp)))
+        return ep, fp
+
     # ---- introspection ------------------------------------------------------------------------------
     def timings(self):
         t = PbTimings()

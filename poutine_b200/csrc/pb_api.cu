@@ -19,7 +19,7 @@ static void free_all(pb_ctx* c) {
     void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_node_sample, c->d_label, c->d_planes,
                     c->d_census, c->d_census_total, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
                     c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT,
-                    c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop, c->d_colmask};
+                    c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop, c->d_colmask, c->d_extras};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -471,6 +471,13 @@ extern "C" int pb_run_assoc(pb_ctx* ctx, const uint32_t* replay_perms, pb_stat_o
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->assoc_done = true;
     return PB_OK;
+}
+
+extern "C" int pb_run_extras(pb_ctx* ctx, double* exact_pointwise, double* fisher_p) {
+    CHECK_CTX(ctx);
+    if (!ctx->assoc_done) FAIL(ctx, PB_ERR_INVALID, "pb_run_extras: call pb_run_assoc first");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    return pbk_extras(ctx, exact_pointwise, fisher_p);
 }
 
 // ---- introspection -------------------------------------------------------------------------------------

@@ -160,6 +160,7 @@ struct pb_ctx {
     uint32_t* d_colpop = nullptr; int64_t colpop_cap = 0;  // [2][P] per-sample case / missing-label popcounts of the current tile
     int32_t* d_fb_reps = nullptr;  // fallback replicate list
     unsigned int* d_fb_count = nullptr;
+    double* d_extras = nullptr; int64_t extras_cap = 0;   // [3*S_inf] exact point-wise (2 per site) + Fisher (k5_extras.cu)
     bool assoc_done = false;
 
     // nccl
@@ -195,6 +196,7 @@ int pbk_pregen_labels(pb_ctx* ctx);                            // k3_null.cu
 int pbk_ptable(pb_ctx* ctx);                                   // k4_pvalues.cu
 int pbk_thresholds(pb_ctx* ctx);                               // k4_pvalues.cu
 int pbk_pvalues(pb_ctx* ctx);                                  // k4_pvalues.cu
+int pbk_extras(pb_ctx* ctx, double* h_exact_pointwise, double* h_fisher);   // k5_extras.cu
 int pbk_exclusive_scan_u64(pb_ctx* ctx, const uint64_t* in, uint64_t* out, int64_t n, uint64_t* d_total);  // k1_events.cu
 
 // nccl_dyn.cpp

@@ -310,7 +310,7 @@ def write_outputs(out_path: str, sites, stats, physical_pos):
 # call() with --use-precomputed-anc-recon
 # -------------------------------------------------------------------------------------------------
 def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_replicates=100000, min_hcount=1, seed=0, device=0,
-                          tile_sites=1 << 17, pack_threads=0, compact_upload=True):
+                          tile_sites=1 << 17, pack_threads=0, compact_upload=True, extras=False):
     """Files in, files out: same inputs as `poutine.sh -u -f -t -p -m`, same three result files.
     `tree_file` is a Newick file with internal node labels, or treetime's annotated_tree.nexus."""
     with open(tree_file) as f:
@@ -387,6 +387,14 @@ def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_
     all_events, counts = hc.count_all_homoplasy_events(compact=False)
     stats, maxT = hc.assoc()
     write_outputs(out_path, all_events, stats, physical_pos)
+    if extras:
+        # not a reference file: the exact point-wise null and two-sided Fisher per informative site (HomoplasyCounter.extras)
+        ep, fp = hc.extras()
+        with open(out_path + ".extras", "w") as f:
+            f.write("segsite_ID\tpos\texact_pointwise_a1\texact_pointwise_a2\tfisher_two_sided\n")
+            for i in range(len(stats)):
+                f.write("%d\t%d\t%s\t%s\t%s\n" % (stats["segsite_id"][i], physical_pos[stats["site_index"][i]],
+                                                  java_double_str(float(ep[i, 0])), java_double_str(float(ep[i, 1])), java_double_str(float(fp[i]))))
     result = dict(counts=counts, n_informative=len(stats), n_sites=S, n_nodes=tree.n_nodes, n_samples=len(label),
                   n_tiles=len(starts), n_compact_tiles=n_compact_tiles)
     fa.close()

@@ -56,3 +56,32 @@ def assert_stats_equal(gpu, ref, p_rtol=0.0):
             np.testing.assert_array_equal(a[ok].view(np.uint64), b[ok].view(np.uint64), err_msg=f + " (bit-exact)")
         else:
             np.testing.assert_allclose(a[ok], b[ok], rtol=p_rtol, atol=0, err_msg=f)
+
+
+# ---- exact rational statements of the two "extras" (pb_run_extras; parity unpinned: no reference code can run) ----
+def exact_pointwise_null(P, n_case, n_miss, n, p_obs, f):
+    """P(f(n - j, k) <= p_obs) under a uniform permutation of the P labels (n_case cases, n_miss missing) over the P
+    samples, for an allele with n sampled leaves: j of them draw a missing label, k a case.  f(n, k) -> float."""
+    from fractions import Fraction
+    from math import comb
+    n_ctrl = P - n_case - n_miss
+    acc = 0
+    for j in range(0, min(n, n_miss) + 1):
+        nr = n - j
+        for k in range(0, min(nr, n_case) + 1):
+            ways = comb(n_miss, j) * comb(n_case, k) * comb(n_ctrl, nr - k)
+            if ways and f(nr, k) <= p_obs:
+                acc += ways
+    return Fraction(acc, comb(P, n))
+
+
+def fisher_two_sided(a, b, c, d):
+    """R's fisher.test p-value for [[a, b], [c, d]]: sum of hypergeometric table probabilities <= P(obs) * (1 + 1e-7)."""
+    from fractions import Fraction
+    from math import comb
+    m, n, k = a + b, c + d, a + c
+    lo, hi = max(0, k - n), min(k, m)
+    ways = {x: comb(m, x) * comb(n, k - x) for x in range(lo, hi + 1)}
+    tot = sum(ways.values())
+    acc = sum(w for w in ways.values() if w * 10**7 <= ways[a] * (10**7 + 1))
+    return Fraction(acc, tot)

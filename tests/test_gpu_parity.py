@@ -503,6 +503,49 @@ def test_assoc_degenerate_phenotypes(oracle_mod, labels):
         np.testing.assert_array_equal(g_st[f], st[f], err_msg=f)
 
 
+@pytest.mark.parametrize("na_frac,min_hcount", [(0.0, 1), (0.05, 1), (0.03, 0)])
+def test_extras_exact_pointwise_and_fisher(oracle_mod, na_frac, min_hcount):
+    """pb_run_extras (parity unpinned — no reference code can run): the exact label-permutation null of the point-wise
+    statistic and R-style two-sided Fisher, against exact rational arithmetic, relative tolerance 1e-12; and the
+    Monte-Carlo r/m of the live path inside a 6-sigma binomial band around the exact value."""
+    from tests.helpers import exact_pointwise_null, fisher_two_sided
+    tree = synth.yule_tree(260, 31)
+    S, m = 1500, 6000
+    B0, B1, V = synth.simulate_planes(tree, S, 32, leaf_gap=True)
+    sn, lab = synth.simulate_phenotypes(tree, 33, na_frac=na_frac, no_row_frac=0.02)
+    hc = pb.HomoplasyCounter(num_replicates=m, seed=5, min_hcount=min_hcount)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_planes(B0, B1, V, S)
+    hc.count_all_homoplasy_events()
+    st, _ = hc.assoc()
+    ep, fp = hc.extras()
+    off, idx = hc.event_csr()
+    nmax, tab = hc.ptable()
+    f = lambda n, k: tab[n * (n + 1) // 2 + k]
+    P, n_case, n_miss = len(lab), int((lab == 1).sum()), int((lab == 2).sum())
+    assert (n_miss > 0) == (na_frac > 0)
+    checked = 0
+    for i in range(len(st)):
+        oc = [int(x) for x in st["obs_counts"][i]]
+        want = float(fisher_two_sided(*oc))
+        assert abs(fp[i] - want) <= 1e-12 * want, (i, oc, fp[i], want)
+        for a, name in enumerate(("a1", "a2")):
+            if not st[name + "_in_use"][i]:
+                assert np.isnan(ep[i, a])
+                continue
+            n = int(off[2 * i + a + 1] - off[2 * i + a])
+            p_obs = st["obs_p_" + name][i]
+            want = float(exact_pointwise_null(P, n_case, n_miss, n, p_obs, f))
+            assert abs(ep[i, a] - want) <= 1e-12 * max(want, 1e-300), (i, a, n, ep[i, a], want)
+            mc = st["r_" + name][i] / m
+            sd = np.sqrt(max(want * (1 - want), 1e-12) / m)
+            assert abs(mc - want) < 6 * sd + 2.0 / m, (i, a, mc, want)
+            checked += 1
+    assert checked > 200
+    hc.close()
+
+
 def test_no_informative_sites_error(oracle_mod):
     tree = synth.yule_tree(50, 3)
     chars = synth.simulate_chars(tree, 40, 4, nasty=False)

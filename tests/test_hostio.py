@@ -225,3 +225,34 @@ def test_run_homoplasy_counter_matches_oracle(tmp_path, oracle_mod, nexus, line_
     hostio.write_outputs(ref_out, sites, gst, paths["physical_pos"])
     for suffix in ("", ".sorted_by_a2_maxT", ".sorted_by_a1_maxT"):
         assert open(out + suffix).read() == open(ref_out + suffix).read(), suffix
+
+
+@pytest.mark.gpu
+def test_cli_precomputed_mode_with_extras(tmp_path, capsys):
+    """`python -m poutine_b200 -u -f -t -p -m -r -d -o -X --seed --extras`: the reference's flags for the precomputed
+    reconstruction mode; same three files as run_homoplasy_counter, plus the .extras table; refuses to overwrite without -X."""
+    from poutine_b200.__main__ import main
+    t = synth.yule_tree(120, 3)
+    S = 64 * 9 + 5
+    chars = synth.planes_to_chars(*synth.simulate_planes(t, S, 4), 0, S)
+    sn, lab = synth.simulate_phenotypes(t, 5)
+    paths = synth.write_inputs(str(tmp_path), t, chars, sn, lab, nexus=True, seed=2)
+    argv = ["-u", "-f", paths["fasta"], "-t", paths["tree"], "-p", paths["pheno"], "-m", paths["map"], "-r", "300",
+            "-d", str(tmp_path / "o"), "-o", "run.out", "--seed", "9", "--extras"]
+    assert main(argv) == 0
+    assert "homoplasically informative sites" in capsys.readouterr().out
+    out = str(tmp_path / "o" / "run.out")
+    ref = str(tmp_path / "direct.out")
+    res = hostio.run_homoplasy_counter(paths["fasta"], paths["tree"], paths["pheno"], paths["map"], ref, num_replicates=300, seed=9)
+    for suffix in ("", ".sorted_by_a2_maxT", ".sorted_by_a1_maxT"):
+        assert open(out + suffix).read() == open(ref + suffix).read(), suffix
+    rows = open(out + ".extras").read().splitlines()
+    assert rows[0].split("\t") == ["segsite_ID", "pos", "exact_pointwise_a1", "exact_pointwise_a2", "fisher_two_sided"]
+    assert len(rows) == 1 + res["n_informative"]
+    vals = [r.split("\t") for r in rows[1:]]
+    assert all(0.0 < float(v[4]) <= 1.0 for v in vals)
+    assert all(v[2] == "NaN" or 0.0 <= float(v[2]) <= 1.0 for v in vals)
+    assert main(argv) == 1                                            # exists, no -X
+    assert main(argv + ["-X"]) == 0
+    with pytest.raises(SystemExit):                                   # without -u: argparse error, as only that mode is offered
+        main(argv[1:])
