@@ -158,7 +158,9 @@ def bench_config(args, cfg, S, m, tree, world):
             "baseline_config": "configs[1]" if args.config == "C2" else args.config,
             "sites_per_gpu": S, "sites_total": S * world, "leaves": tree.n_leaves, "nodes": tree.n_nodes, "replicates": m,
             "parallelism": "site-sharded x%d, all-reduce(min) of maxT[m]" % world if world > 1 else "single GPU",
-            "l2_policy": "inputs larger than L2 (bit planes %.2f GB per GPU vs 126 MB L2)" % (3 * tree.n_nodes * ((S + 63) // 64) * 8 / 1e9)}
+            "l2_policy": "inputs larger than L2 (bit planes per GPU: %.2f GB as one plane when every site is biallelic and every genotype "
+                         "valid, %.2f GB as three planes otherwise; L2 is 126 MB)"
+                         % (tree.n_nodes * ((S + 63) // 64) * 8 / 1e9, 3 * tree.n_nodes * ((S + 63) // 64) * 8 / 1e9)}
 
 
 def run_b200(args):
@@ -235,7 +237,14 @@ def run_b200(args):
         ids = [pb.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         hc.comm_init(ids[0], rank, world)
-    hc.put_planes(*host_planes)
+
+    def upload(use_compact=True):
+        if use_compact and compact is not None:          # one plane (+ V if some genotype is not a base) + per-column site masks
+            hc.put_planes_biallelic(compact[0], None if compact[2] else host_planes[2], compact[1])
+        else:
+            hc.put_planes(*host_planes)
+
+    upload()          # biallelic input with every genotype valid stays ONE plane in HBM (k1x_events_kernel), else three
 
     def step_resident():
         hc.count_all_homoplasy_events(fetch_sites=False)
@@ -246,10 +255,7 @@ def run_b200(args):
 
     def step_e2e(use_compact=True):
         t0 = time.perf_counter()
-        if use_compact and compact is not None:          # H2D of this step's inputs (pinned host memory) + device expansion
-            hc.put_planes_biallelic(compact[0], None if compact[2] else host_planes[2], compact[1])
-        else:
-            hc.put_planes(*host_planes)
+        upload(use_compact)                              # H2D of this step's inputs (pinned host memory)
         t1 = time.perf_counter()
         ev, cc = hc.count_all_homoplasy_events(compact=False)   # D2H: per-site Homoplasy_Events records (page-locked buffer)
         t2 = time.perf_counter()
@@ -267,23 +273,46 @@ def run_b200(args):
     except Exception:
         gpu_id = str(local_rank)
     sampler = ClockSampler(gpu_id) if rank == 0 else None
-    k1_ms, launches, parts = [], 0, {}
-    barrier()
-    t0 = time.perf_counter()
-    hc.stopwatch_start()
-    for _ in range(args.steps):
-        tm = step_resident()
-        k1_ms.append(tm["ms_events_kernel"])
-        launches += int(tm["n_launches"])
-        for k in ("ms_events_kernel", "ms_events_total", "ms_tally", "ms_ptable", "ms_null_gen", "ms_null_count",
-                  "ms_null_fallback", "ms_allreduce", "ms_pvalues", "ms_assoc_total"):
-            parts[k] = parts.get(k, 0.0) + tm[k] / args.steps
-    dev_ms = hc.stopwatch_stop_ms()
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    dev_ms = max_over_ranks(dev_ms)
-    wall_ms = max_over_ranks(wall_ms)
     total_sites = S * world
+    peak, peak_src = measured_hbm_peak()
+
+    def timed_resident():
+        """K timed steps with the planes resident in HBM -> (device ms, wall ms, launches, per-part ms, roofline of the sweep kernel)"""
+        k1_ms, launches, parts = [], 0, {}
+        barrier()
+        t0 = time.perf_counter()
+        hc.stopwatch_start()
+        for _ in range(args.steps):
+            tm = step_resident()
+            k1_ms.append(tm["ms_events_kernel"])
+            launches += int(tm["n_launches"])
+            for k in ("ms_events_kernel", "ms_events_total", "ms_tally", "ms_ptable", "ms_null_gen", "ms_null_count",
+                      "ms_null_fallback", "ms_allreduce", "ms_pvalues", "ms_assoc_total"):
+                parts[k] = parts.get(k, 0.0) + tm[k] / args.steps
+        dev_ms = hc.stopwatch_stop_ms()
+        barrier()
+        wall_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        dev_ms = max_over_ranks(dev_ms)
+        # roofline of the HBM-bound counting sweep: algorithmic bytes (DESIGN.md section 3) / mean launch time, both live
+        kernel = "k1x_events_kernel" if tm["plane_mode"] == _lib.PB_PLANES_X else "k1_events_kernel"
+        k1_avg = float(np.mean(k1_ms))
+        alg_bytes = int(tm["k1_algorithmic_bytes"])
+        achieved = alg_bytes / (k1_avg / 1e3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+                tj = json.load(f).get(kernel, {})
+                if tj.get("sites") == S and tj.get("nodes") == N:
+                    traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roofline = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k1_avg, "peak_source": peak_src,
+                    "frac_of_nominal_8TBps": achieved / 8000.0,
+                    "planes_in_hbm": 1 if kernel == "k1x_events_kernel" else 3}
+        return dev_ms, wall_ms, launches, parts, roofline, tm
+
+    dev_ms, wall_ms, launches, parts, roofline, tm = timed_resident()
     value = total_sites * args.steps / (dev_ms / 1e3)
 
     # ---- timed: end to end through the public API with host buffers ------------------------------------
@@ -301,6 +330,7 @@ def run_b200(args):
     h2d_full = 3 * N * Wp * 8                             # what pb_put_planes copies (rows padded to the device pitch)
     h2d = h2d_full
     e2e_full = None
+    three_planes = None
     if compact is not None:
         # the same end-to-end step with the plain three-plane upload, reported next to the headline
         h2d = (1 if compact[2] else 2) * N * Wp * 8 + W * 32
@@ -313,27 +343,18 @@ def run_b200(args):
         full_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
         e2e_full = {"value": total_sites * args.steps / (full_ms / 1e3), "unit": "sites/s", "ms_per_step": full_ms / args.steps,
                     "h2d_bytes_per_step": h2d_full, "upload": "pb_put_planes (three planes)"}
+        # the context now holds three planes (the general storage: gaps, multi-allelic sites): the same resident measurement
+        for _ in range(args.warmup):
+            step_resident()
+        f_dev, f_wall, f_launches, f_parts, f_roof, _ = timed_resident()
+        launches += f_launches
+        three_planes = {"value": total_sites * args.steps / (f_dev / 1e3), "unit": "sites/s", "ms_per_step": f_dev / args.steps,
+                        "roofline": f_roof, "breakdown_ms": f_parts, "e2e": e2e_full,
+                        "note": "same workload held as three full planes (what gap-carrying or multi-allelic input uses)"}
     clocks = sampler.stop() if sampler else None      # sampled over all timed regions (resident + end to end)
     d2h = S * _lib.SITE_DTYPE.itemsize + len(st) * _lib.STAT_DTYPE.itemsize + m * 8
     e2e_value = total_sites * args.steps / (e2e_ms / 1e3)
     n_draws = sum_over_ranks(tm["n_alleles_in_use"]) * m
-
-    # ---- roofline of the HBM-bound counting kernel (K1) -----------------------------------------------
-    peak, peak_src = measured_hbm_peak()
-    k1_avg = float(np.mean(k1_ms))
-    alg_bytes = int(tm["k1_algorithmic_bytes"])
-    achieved = alg_bytes / (k1_avg / 1e3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
-            tj = json.load(f)
-            if tj.get("sites") == S and tj.get("nodes") == N:
-                traffic = tj["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    roofline = {"kernel": "k1_events_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k1_avg, "peak_source": peak_src,
-                "frac_of_nominal_8TBps": achieved / 8000.0}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -351,10 +372,12 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps,
                         "breakdown_ms": e2e_breakdown, "timer": "host wall clock around synchronous C-ABI calls, max over ranks",
-                        "upload": ("pb_put_planes_biallelic (X plane%s + site masks, expanded on the device; host-side compaction "
-                                   "%.2f s once, outside the timed region like the FASTA packing)" % ("" if compact[2] else " + V plane", t_compact))
+                        "upload": ("pb_put_planes_biallelic (%s; host-side compaction %.2f s once, outside the timed region like "
+                                   "the FASTA packing)" % ("X plane + site masks, kept as one plane in HBM" if compact[2] else
+                                                           "X + V planes + site masks, expanded to three planes on the device", t_compact))
                                   if compact is not None else "pb_put_planes (three planes)",
-                        "full_planes": e2e_full},
+                        },
+                "three_planes": three_planes,
                 "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "replicate_draws_per_sec": n_draws * args.steps / (dev_ms / 1e3),

@@ -62,7 +62,8 @@ typedef struct {
 
 enum {
     PB_FLAG_FORCE_GENERAL_NULL = 1u,  /* disable the all-labelled bit-sliced fast path (test hook) */
-    PB_FLAG_KEEP_RAW_EVENTS = 2u      /* reserved: the raw MRCA event list is always kept until the next pb_run_events */
+    PB_FLAG_KEEP_RAW_EVENTS = 2u,     /* reserved: the raw MRCA event list is always kept until the next pb_run_events */
+    PB_FLAG_FULL_PLANES = 4u          /* always hold three planes in HBM, even when every uploaded tile is compact */
 };
 
 /* One record per site of this context, field-for-field Homoplasy_Events (HC.java:5531-5550);
@@ -109,10 +110,12 @@ typedef struct {
     float ms_pvalues;         /* K4: sort maxT + pointwise/familywise */
     float ms_assoc_total;
     int64_t n_launches;       /* kernels launched by the last events+assoc pair */
-    int64_t k1_algorithmic_bytes;  /* 3*N*W*8 plane bytes + 32 B/site + 8 B/raw event */
+    int64_t k1_algorithmic_bytes;  /* planes*N*W*8 plane bytes (planes = 3, or 1 in compact mode) + 32 B/site + 8 B/raw event */
     int64_t n_informative, n_alleles_in_use, n_extant_events;  /* S_inf, A, E of SURVEY §8 */
     int64_t n_fast_alleles;   /* alleles handled by the bit-sliced threshold path */
     int64_t n_maxt_fallback_reps;
+    int64_t plane_mode;       /* how the alignment was held in HBM for the last pb_run_events: 1 = one plane X + site masks
+                                 (every tile compact, all genotypes valid; k1x_events_kernel), 2 = three planes (k1_events_kernel) */
 } pb_timings;
 
 int pb_create(const pb_config* cfg, pb_ctx** out);

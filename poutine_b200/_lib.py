@@ -17,7 +17,8 @@ LIB_PATH = os.environ.get("PB_LIB") or os.path.join(_HERE, "libpoutine_b200.so")
 _LIB = None
 
 PB_MODE_PHILOX, PB_MODE_REPLAY = 0, 1
-PB_FLAG_FORCE_GENERAL_NULL, PB_FLAG_KEEP_RAW_EVENTS = 1, 2
+PB_FLAG_FORCE_GENERAL_NULL, PB_FLAG_KEEP_RAW_EVENTS, PB_FLAG_FULL_PLANES = 1, 2, 4
+PB_PLANES_X, PB_PLANES_FULL = 1, 2
 PB_ERR_NO_INFORMATIVE = -3
 
 SITE_DTYPE = np.dtype([("segsite_id", "<i4"), ("site_class", "<i4"), ("allele1", "<i4"), ("allele2", "<i4"),
@@ -44,7 +45,7 @@ class PbTimings(C.Structure):
                                          "ms_null_count", "ms_null_fallback", "ms_allreduce", "ms_pvalues",
                                          "ms_assoc_total")] + \
                [(n, C.c_int64) for n in ("n_launches", "k1_algorithmic_bytes", "n_informative", "n_alleles_in_use",
-                                         "n_extant_events", "n_fast_alleles", "n_maxt_fallback_reps")]
+                                         "n_extant_events", "n_fast_alleles", "n_maxt_fallback_reps", "plane_mode")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -76,13 +76,14 @@ class HomoplasyCounter:
     """
 
     def __init__(self, num_replicates=100000, min_hcount=1, device=0, seed=0, replay=False, site_offset=0,
-                 maxt_tau=0.0, force_general_null=False):
+                 maxt_tau=0.0, force_general_null=False, full_planes=False):
         self._h = None
         L = _lib.lib()
         cfg = PbConfig(device=device, mode=_lib.PB_MODE_REPLAY if replay else _lib.PB_MODE_PHILOX,
                        n_replicates=int(num_replicates), min_hcount=int(min_hcount), seed=int(seed),
                        site_offset=int(site_offset), maxt_tau=float(maxt_tau),
-                       flags=_lib.PB_FLAG_FORCE_GENERAL_NULL if force_general_null else 0)
+                       flags=(_lib.PB_FLAG_FORCE_GENERAL_NULL if force_general_null else 0) |
+                             (_lib.PB_FLAG_FULL_PLANES if full_planes else 0))
         h = C.c_void_p()
         rc = L.pb_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -304,6 +304,175 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
     drain_queue(s_queue, &s_count, &s_base, tid, 1, p.raw, p.raw_cursor, p.raw_cap);
 }
 
+// =================================================================================================
+// K1X — the same sweep over ONE plane.  When every site carries at most two bases and every genotype is valid
+// (pb_put_planes_biallelic with V = NULL for every tile), a node's genotype is one bit: X = "carries the site's second
+// base".  The MRCA test of an edge is then X_child ^ X_parent, the leaf census one counter (how many leaves carry the
+// second base), and a row is 1 KB per block instead of 3 KB: a third of the HBM bytes, about a third of the instructions.
+// Same edge program, same ring protocol (four 1 KB TMA boxes per stage, PB_KX_STAGES stages), same event queue; the
+// 2-bit base code of an event is rebuilt from the column's site masks (A0, A1, D0, D1 in registers) only when an
+// event is emitted.  The census counter lives entirely in registers (slices 1..128: segments hold <= 248 leaves).
+#define PB_KX_STAGES 4
+#define PB_KX_BLOCKS_PER_SM 6
+#define KX_ROW_BYTES (PB_K1_COLS * 8)
+#define KX_STAGE_BYTES (2 * PB_K1_RPS * KX_ROW_BYTES)
+#define KX_SMEM_RING (PB_KX_STAGES * KX_STAGE_BYTES)
+#define KX_SMEM_BARS (2 * PB_KX_STAGES * 8)
+#define KX_SMEM_TOTAL (KX_SMEM_RING + K1_SMEM_QUEUE + KX_SMEM_BARS)
+
+struct KXParams {
+    int64_t W;
+    const uint32_t* __restrict__ ops;
+    const int32_t* __restrict__ chunk_op;
+    const uint64_t* __restrict__ xmask;    // [W][4]
+    uint64_t* __restrict__ census;         // [flush][KS][W]: leaves carrying the second base
+    raw_event_t* __restrict__ raw;
+    unsigned long long* raw_cursor;
+    unsigned long long raw_cap;
+};
+
+__device__ __forceinline__ void tma_load_row_2d(uint32_t dst, const CUtensorMap* tmap, int32_t col0, int32_t node, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(col0), "r"(node), "r"(bar) : "memory");
+}
+
+struct CensusX {
+    uint64_t s[PB_K1_KS];     // slices 1, 2, 4, 8, ... 128
+    uint64_t pend2, pend4, pend8;
+    int nleaf;
+};
+
+__device__ __forceinline__ void k1x_row(uint32_t op, uint64_t x, uint64_t& px, CensusX& cs, uint64_t a0, uint64_t a1, uint64_t d0, uint64_t d1,
+                                        uint32_t site_base, uint32_t queue_addr, uint32_t count_addr, const K1Params& p) {
+    if (op & PB_OP_TEST) {
+        const uint64_t mrca = x ^ px;
+        if (mrca) emit_events(mrca, a0 ^ (x & d0), a1 ^ (x & d1), site_base, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
+    }
+    if (op & PB_OP_SETCUR) px = x;
+    if (op & PB_OP_LEAF) {
+        // deferred-carry bit-sliced counter, as in k1_row, for the single quantity "leaves with X = 1"
+        const int ph = cs.nleaf & 7;                                 // block-uniform
+        cs.nleaf++;
+        const uint64_t o = cs.s[0];
+        cs.s[0] = o ^ x; cs.pend2 |= o & x;
+        if (ph & 1) {
+            cs.pend4 |= cs.s[1] & cs.pend2; cs.s[1] ^= cs.pend2; cs.pend2 = 0;
+            if (ph & 2) {
+                if (!(ph & 4)) {
+                    cs.pend8 = cs.s[2] & cs.pend4; cs.s[2] ^= cs.pend4; cs.pend4 = 0;
+                } else {
+                    uint64_t carry = cs.pend8 | (cs.s[2] & cs.pend4);
+                    cs.s[2] ^= cs.pend4; cs.pend4 = 0; cs.pend8 = 0;
+#pragma unroll
+                    for (int j = 3; j < PB_K1_KS; j++) { const uint64_t h = cs.s[j]; cs.s[j] = h ^ carry; carry &= h; }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events_kernel(const __grid_constant__ CUtensorMap tmap, const KXParams q) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned int s_count;
+    __shared__ unsigned long long s_base;
+    raw_event_t* s_queue = reinterpret_cast<raw_event_t*>(smem + KX_SMEM_RING);
+
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.y;
+    const int32_t col0 = (int32_t)blockIdx.x * PB_K1_COLS;
+    const int r0 = q.chunk_op[chunk], r1 = q.chunk_op[chunk + 1];
+    const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(q.ops);
+    const uint32_t ring0 = pin_u32(smem_u32(smem));
+    const uint32_t full0 = pin_u32(ring0 + KX_SMEM_RING + K1_SMEM_QUEUE), empty0 = full0 + 8 * PB_KX_STAGES;
+
+    if (tid == 0) {
+        s_count = 0;
+        for (int s = 0; s < PB_KX_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, PB_K1_COLS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= PB_K1_COLS) {
+        // producer warp: one lane, four 1 KB boxes per stage (padding slots are out-of-bounds boxes: zero-filled)
+        if (tid == PB_K1_COLS) {
+            uint32_t soff = 0, boff = 0, phase = 0;
+            for (int i = r0; i < r1; i += PB_K1_RPS) {
+                uint32_t node[2 * PB_K1_RPS];
+#pragma unroll
+                for (int k = 0; k < PB_K1_RPS; k++) {
+                    const uint4 rec = __ldg(recs + i + k);
+                    node[2 * k] = rec.x & PB_OP_NODE_MASK; node[2 * k + 1] = rec.y & PB_OP_NODE_MASK;
+                }
+                mbar_wait(empty0 + boff, phase ^ 1);
+                mbar_arrive_expect_tx(full0 + boff, KX_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 2 * PB_K1_RPS; k++) tma_load_row_2d(ring0 + soff + k * KX_ROW_BYTES, &tmap, col0, (int32_t)node[k], full0 + boff);
+                soff += KX_STAGE_BYTES; boff += 8;
+                if (boff == 8 * PB_KX_STAGES) { soff = 0; boff = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // consumer warps: one thread = one 64-site word column
+    const int lane = tid & 31;
+    const int64_t w = (int64_t)col0 + tid;
+    const uint32_t site_base = (uint32_t)(w * 64);
+    const uint32_t my_ring = pin_u32(ring0 + tid * 8);
+    const uint32_t queue_addr = pin_u32(ring0 + KX_SMEM_RING), count_addr = pin_u32(smem_u32(&s_count));
+    uint64_t a0 = 0, a1 = 0, d0 = 0, d1 = 0;
+    if (w < q.W) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(q.xmask + 4 * w), d = *reinterpret_cast<const ulonglong2*>(q.xmask + 4 * w + 2);
+        a0 = a.x; a1 = a.y; d0 = d.x; d1 = d.y;
+    }
+    K1Params ep;                 // emit_events / drain_queue only use the raw list fields
+    ep.raw = q.raw; ep.raw_cursor = q.raw_cursor; ep.raw_cap = q.raw_cap;
+
+    CensusX cs;
+#pragma unroll
+    for (int j = 0; j < PB_K1_KS; j++) cs.s[j] = 0;
+    cs.pend2 = cs.pend4 = cs.pend8 = 0;
+    cs.nleaf = 0;
+    uint64_t px = 0;
+    uint32_t soff = 0, boff = 0, phase = 0;
+
+#pragma unroll 1
+    for (int i = r0; i < r1; i += PB_K1_RPS) {
+        uint4 rec[PB_K1_RPS];
+#pragma unroll
+        for (int k = 0; k < PB_K1_RPS; k++) rec[k] = __ldg(recs + i + k);
+        mbar_wait(full0 + boff, phase);
+        const uint32_t src = my_ring + soff;
+        uint64_t x[2 * PB_K1_RPS];
+#pragma unroll
+        for (int k = 0; k < 2 * PB_K1_RPS; k++) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(x[k]) : "r"(src + k * KX_ROW_BYTES));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + boff);                     // the stage's rows are in registers: free it
+        soff += KX_STAGE_BYTES; boff += 8;
+        if (boff == 8 * PB_KX_STAGES) { soff = 0; boff = 0; phase ^= 1; }
+#pragma unroll
+        for (int k = 0; k < PB_K1_RPS; k++) {
+            k1x_row(rec[k].x, x[2 * k], px, cs, a0, a1, d0, d1, site_base, queue_addr, count_addr, ep);
+            k1x_row(rec[k].y, x[2 * k + 1], px, cs, a0, a1, d0, d1, site_base, queue_addr, count_addr, ep);
+            if (rec[k].z != PB_REC_NOFLUSH) {
+                if (w < q.W) {
+                    uint64_t* out = q.census + ((int64_t)rec[k].z * PB_K1_KS) * q.W + w;
+#pragma unroll
+                    for (int j = 0; j < PB_K1_KS; j++) out[(int64_t)j * q.W] = cs.s[j];
+                }
+#pragma unroll
+                for (int j = 0; j < PB_K1_KS; j++) cs.s[j] = 0;
+                cs.pend2 = cs.pend4 = cs.pend8 = 0;
+                cs.nleaf = 0;
+            }
+        }
+        if ((((i - r0) / PB_K1_RPS) & (PB_K1_DRAIN_EVERY / PB_K1_RPS - 1)) == PB_K1_DRAIN_EVERY / PB_K1_RPS - 1)
+            drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, q.raw, q.raw_cursor, q.raw_cap);
+    }
+    drain_queue(s_queue, &s_count, &s_base, tid, 1, q.raw, q.raw_cursor, q.raw_cap);
+}
+
 // ---- per-site event counters -------------------------------------------------------------------
 // the raw list's length lives on the device (K1's cursor, clamped to the buffer): no host round trip before the tail
 __global__ void k1_count_events_kernel(const raw_event_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
@@ -326,13 +495,13 @@ __global__ void k1_count_events_kernel(const raw_event_t* __restrict__ raw, cons
 // thread = (word column, base); total[base][PB_K1_KT][W]
 __global__ void k1_census_reduce_kernel(const uint64_t* __restrict__ census, int n_flush, int64_t W, uint64_t* __restrict__ total) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = blockIdx.y;
+    const int c = blockIdx.y, n_counters = gridDim.y;   // 4 (k1_events_kernel) or 1 (k1x_events_kernel)
     if (w >= W) return;
     uint64_t acc[PB_K1_KT];
 #pragma unroll
     for (int j = 0; j < PB_K1_KT; j++) acc[j] = 0;
     for (int f = 0; f < n_flush; f++) {
-        const uint64_t* in = census + (((int64_t)f * 4 + c) * PB_K1_KS) * W + w;
+        const uint64_t* in = census + (((int64_t)f * n_counters + c) * PB_K1_KS) * W + w;
         uint64_t carry = 0;
 #pragma unroll
         for (int j = 0; j < PB_K1_KS; j++) {
@@ -354,9 +523,12 @@ __global__ void k1_census_reduce_kernel(const uint64_t* __restrict__ census, int
 }
 
 // ---- per-site finalisation: census -> class / major-minor; counters -> Homoplasy_Events -----------
+// XMODE: the alignment is held as one plane.  B0 = X, B1 = the site masks [W][4], V = the valid-site words [W]; the
+// census holds one counter (leaves carrying the second base) and n_leaves the tree's leaf count.
+template <bool XMODE>
 __global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, int kt_used, int64_t W, int64_t S,
                                    const uint64_t* __restrict__ B0, const uint64_t* __restrict__ B1, const uint64_t* __restrict__ V,
-                                   int64_t Wp, int32_t root, const uint32_t* __restrict__ cnt, int32_t min_hcount, int64_t site_offset,
+                                   int64_t Wp, int32_t root, int32_t n_leaves, const uint32_t* __restrict__ cnt, int32_t min_hcount, int64_t site_offset,
                                    pb_site_out* __restrict__ sites, uint8_t* __restrict__ flags, uint64_t* __restrict__ scan_in,
                                    unsigned long long* __restrict__ class_counts) {
     __shared__ unsigned int s_cls[5];
@@ -366,12 +538,25 @@ __global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, int kt_us
     if (s < S) {
         const int64_t w = s >> 6;
         const int b = (int)(s & 63);
-        uint32_t q[4] = {0, 0, 0, 0};        // K1's counters: leaves with V, V&B0, V&B1, V&B0&B1
+        uint32_t leafcnt[4] = {0, 0, 0, 0};  // by 2-bit code: A C G T
+        int xa = 0, xd = 0;                  // XMODE: code of the site's first base, first XOR second
+        bool xvalid = true;
+        if (XMODE) {
+            uint32_t nx = 0;
+            for (int j = 0; j < kt_used; j++) nx |= (uint32_t)((total[(int64_t)j * W + w] >> b) & 1ull) << j;
+            const uint64_t* m = B1 + 4 * w;
+            xa = (int)((m[0] >> b) & 1ull) | ((int)((m[1] >> b) & 1ull) << 1);
+            xd = (int)((m[2] >> b) & 1ull) | ((int)((m[3] >> b) & 1ull) << 1);
+            xvalid = (V[w] >> b) & 1ull;     // the column was uploaded (nothing uploaded = no valid genotype, as in full mode)
+            if (xvalid) { leafcnt[xa] = (uint32_t)n_leaves - nx; leafcnt[xa ^ xd] += nx; }   // xd == 0 implies nx == 0
+        } else {
+            uint32_t q[4] = {0, 0, 0, 0};    // K1's counters: leaves with V, V&B0, V&B1, V&B0&B1
 #pragma unroll
-        for (int c = 0; c < 4; c++)
-            for (int j = 0; j < kt_used; j++)
-                q[c] |= (uint32_t)((total[((int64_t)c * PB_K1_KT + j) * W + w] >> b) & 1ull) << j;
-        const uint32_t leafcnt[4] = {q[0] - q[1] - q[2] + q[3], q[1] - q[3], q[2] - q[3], q[3]};  // by 2-bit code: A C G T
+            for (int c = 0; c < 4; c++)
+                for (int j = 0; j < kt_used; j++)
+                    q[c] |= (uint32_t)((total[((int64_t)c * PB_K1_KT + j) * W + w] >> b) & 1ull) << j;
+            leafcnt[0] = q[0] - q[1] - q[2] + q[3]; leafcnt[1] = q[1] - q[3]; leafcnt[2] = q[2] - q[3]; leafcnt[3] = q[3];
+        }
         // HashMap<Character,..> iteration order A, C, T, G  (buckets 'A'&15=1, 'C'&15=3, 'T'&15=4, 'G'&15=7)
         const int order[4] = {0, 1, 3, 2};
         int n_alleles = 0, first = -1, second = -1;
@@ -395,8 +580,9 @@ __global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, int kt_us
             const char L4[4] = {'A', 'C', 'G', 'T'};
             const uint32_t* c = cnt + s * PB_CNT_STRIDE;
             const int64_t ro = (int64_t)root * Wp + w;
-            const bool rvalid = (V[ro] >> b) & 1ull;
-            const int rcode = (int)((B0[ro] >> b) & 1ull) | ((int)((B1[ro] >> b) & 1ull) << 1);
+            const bool rvalid = XMODE ? xvalid : (bool)((V[ro] >> b) & 1ull);
+            const int rcode = XMODE ? (xa ^ (((B0[ro] >> b) & 1ull) ? xd : 0))
+                                    : ((int)((B0[ro] >> b) & 1ull) | ((int)((B1[ro] >> b) & 1ull) << 1));
             const bool root_a1 = rvalid && rcode == a1;   // add_MRCA(root): a1 iff geno(root)==allele1 (HC.java:1689, 1861)
             uint32_t m_all = c[0] + c[1] + c[2] + c[3], x_all = c[4] + c[5] + c[6] + c[7], xs_all = c[8] + c[9] + c[10] + c[11];
             uint32_t a1c = c[a1] + (root_a1 ? 1u : 0u);
@@ -605,7 +791,69 @@ int pbk_expand_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, const
     return PB_OK;
 }
 
+// X-mode helpers: padding bits of site word W-1 never count (X and the valid-site word), and the promotion to three planes
+__global__ void k1x_mask_valid_kernel(uint64_t* __restrict__ xvalid, int64_t w_last, uint64_t mask) { xvalid[w_last] &= mask; }
+
+int pbk_mask_last_word_x(pb_ctx* ctx) {
+    if (!(ctx->S & 63) || ctx->N == 0) return PB_OK;
+    const uint64_t mask = (1ull << (ctx->S & 63)) - 1;
+    k1_mask_last_word_kernel<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_X, ctx->N, ctx->Wp, ctx->W - 1, mask);
+    k1x_mask_valid_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_xvalid, ctx->W - 1, mask);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+__global__ void k1x_promote_kernel(const uint64_t* __restrict__ X, const uint64_t* __restrict__ xmask, const uint64_t* __restrict__ xvalid,
+                                   uint64_t* __restrict__ B0, uint64_t* __restrict__ B1, uint64_t* __restrict__ V, int32_t N, int64_t Wp, int64_t W) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(xmask + 4 * w), d = *reinterpret_cast<const ulonglong2*>(xmask + 4 * w + 2);
+    const uint64_t valid = xvalid[w];
+    for (int32_t v = blockIdx.y; v < N; v += gridDim.y) {
+        const int64_t o = (int64_t)v * Wp + w;
+        const uint64_t x = X[o];
+        B0[o] = a.x ^ (x & d.x);
+        B1[o] = a.y ^ (x & d.y);
+        V[o] = valid;
+    }
+}
+
+int pbk_promote_planes(pb_ctx* ctx) {
+    const unsigned gx = (unsigned)((ctx->W + 127) / 128);
+    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->N, ((int64_t)ctx->sm_count * 16 + gx - 1) / gx));
+    k1x_promote_kernel<<<dim3(gx, gy), 128, 0, ctx->stream>>>(ctx->d_X, ctx->d_xmask, ctx->d_xvalid, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->N,
+                                                             ctx->Wp, ctx->W);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+static int pbk_events_x(pb_ctx* ctx) {
+    KXParams q;
+    q.W = ctx->W;
+    q.ops = ctx->d_ops; q.chunk_op = ctx->d_chunk_op;
+    q.xmask = ctx->d_xmask;
+    q.census = ctx->d_census;
+    q.raw = ctx->d_raw; q.raw_cursor = ctx->d_raw_cursor; q.raw_cap = (unsigned long long)ctx->raw_cap;
+    const size_t smem = (size_t)KX_SMEM_TOTAL;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(k1x_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((ctx->W + PB_K1_COLS - 1) / PB_K1_COLS), (unsigned)ctx->n_chunks);
+    PB_CUDA(cudaMemsetAsync(ctx->d_raw_cursor, 0, 8, ctx->stream));
+    PB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    pb_trace_mark(ctx, "start");
+    k1x_events_kernel<<<grid, PB_K1_THREADS, smem, ctx->stream>>>(ctx->tmap_x, q);
+    pb_trace_mark(ctx, "k1x");
+    PB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->tm.n_launches += 1;
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
 int pbk_events(pb_ctx* ctx) {
+    if (ctx->plane_mode == PB_PLANES_X) return pbk_events_x(ctx);
     K1Params p;
     p.W = ctx->W;
     p.ops = ctx->d_ops; p.chunk_op = ctx->d_chunk_op;
@@ -668,13 +916,19 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     pb_trace_mark(ctx, "headstart+memsets");
     k1_count_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_cnt);
     pb_trace_mark(ctx, "count_events");
-    k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), 4), 128, 0, st>>>(ctx->d_census, ctx->n_flush, ctx->W, ctx->d_census_total);
+    const bool xmode = ctx->plane_mode == PB_PLANES_X;
+    k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), xmode ? 1 : 4), 128, 0, st>>>(ctx->d_census, ctx->n_flush, ctx->W, ctx->d_census_total);
     pb_trace_mark(ctx, "census_reduce");
     int kt_used = 1;
     while ((1ll << kt_used) <= (int64_t)ctx->L) kt_used++;
-    k1_finalize_kernel<<<(unsigned)((S + T - 1) / T), T, 0, st>>>(
-        ctx->d_census_total, kt_used, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->d_cnt, ctx->cfg.min_hcount,
-        ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan /* reused as scan input */, ctx->d_class_counts);
+    if (xmode)
+        k1_finalize_kernel<true><<<(unsigned)((S + T - 1) / T), T, 0, st>>>(
+            ctx->d_census_total, kt_used, ctx->W, S, ctx->d_X, ctx->d_xmask, ctx->d_xvalid, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt,
+            ctx->cfg.min_hcount, ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan, ctx->d_class_counts);
+    else
+        k1_finalize_kernel<false><<<(unsigned)((S + T - 1) / T), T, 0, st>>>(
+            ctx->d_census_total, kt_used, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt, ctx->cfg.min_hcount,
+            ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan /* reused as scan input */, ctx->d_class_counts);
     pb_trace_mark(ctx, "finalize");
     ctx->tm.n_launches += 3;
     PB_CUDA(cudaGetLastError());

@@ -19,7 +19,7 @@ static void free_all(pb_ctx* c) {
     void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_node_sample, c->d_label, c->d_planes,
                     c->d_census, c->d_census_total, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
                     c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT,
-                    c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop, c->d_colmask, c->d_extras};
+                    c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop, c->d_colmask, c->d_extras, c->d_X, c->d_xmask, c->d_xvalid};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -308,48 +308,106 @@ extern "C" int pb_set_labels(pb_ctx* ctx, int32_t n_samples, const int32_t* samp
     return build_node_sample(ctx);
 }
 
-extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
-    CHECK_CTX(ctx);
-    if (ctx->N == 0) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: call pb_set_tree first");
-    if (n_sites < 1 || n_sites >= (1ll << 32)) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: n_sites out of range");
-    PB_CUDA(cudaSetDevice(ctx->device));
-    ctx->events_done = ctx->assoc_done = false;
-    if (n_sites == ctx->S && ctx->d_planes) return PB_OK;
-    if (ctx->d_planes) { cudaFree(ctx->d_planes); ctx->d_planes = nullptr; }
-    ctx->d_B0 = ctx->d_B1 = ctx->d_V = nullptr;
-    for (void** p : {(void**)&ctx->d_cnt, (void**)&ctx->d_sites, (void**)&ctx->d_site_flags, (void**)&ctx->d_site_scan, (void**)&ctx->d_raw})
+typedef CUresult (*pb_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int tensor_map(pb_ctx* ctx, CUtensorMap* out, void* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstride, const cuuint32_t* box) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(ctx, PB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint32_t estride[3] = {1, 1, 1};
+    CUresult cr = ((pb_encode_fn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, base, gdim, gstride, box, estride,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) FAIL(ctx, PB_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)cr) + ")");
+    return PB_OK;
+}
+
+static void free_planes(pb_ctx* ctx) {
+    for (void** p : {(void**)&ctx->d_planes, (void**)&ctx->d_X, (void**)&ctx->d_xmask, (void**)&ctx->d_xvalid})
         if (*p) { cudaFree(*p); *p = nullptr; }
-    ctx->S = n_sites;
-    ctx->W = (n_sites + 63) / 64;
-    ctx->Wp = (ctx->W + 15) & ~15ll;  // rows padded to 128 B
+    ctx->d_B0 = ctx->d_B1 = ctx->d_V = nullptr;
+    ctx->plane_mode = PB_PLANES_NONE;
+}
+
+// the three full planes (zero-filled: a column nobody uploads has no valid genotype) and their 3-D TMA descriptor
+static int alloc_full_planes(pb_ctx* ctx) {
     const size_t plane = (size_t)ctx->N * ctx->Wp * 8;
     cudaError_t e = cudaMalloc(&ctx->d_planes, 3 * plane);
     if (e != cudaSuccess) {
-        ctx->err = std::string("pb_set_sites: cudaMalloc of 3 x ") + std::to_string(plane) + " B planes: " + cudaGetErrorString(e);
-        ctx->S = 0;
+        ctx->err = std::string("cudaMalloc of 3 x ") + std::to_string(plane) + " B planes: " + cudaGetErrorString(e);
+        ctx->d_planes = nullptr;
         return PB_ERR_OOM;
     }
     ctx->d_V = ctx->d_planes;
     ctx->d_B0 = ctx->d_planes + (size_t)ctx->N * ctx->Wp;
     ctx->d_B1 = ctx->d_planes + 2 * (size_t)ctx->N * ctx->Wp;
     PB_CUDA(cudaMemsetAsync(ctx->d_planes, 0, 3 * plane, ctx->stream));
+    // dims (word column, node, plane); one box = the 3 KB a block needs of one tree row
+    const cuuint64_t gdim[3] = {(cuuint64_t)ctx->W, (cuuint64_t)ctx->N, 3};
+    const cuuint64_t gstride[2] = {(cuuint64_t)ctx->Wp * 8, (cuuint64_t)plane};
+    const cuuint32_t box[3] = {PB_K1_COLS, 1, 3};
+    return tensor_map(ctx, &ctx->tmap, ctx->d_planes, 3, gdim, gstride, box);
+}
+
+// Moves the context to the requested storage mode.  NONE -> X or FULL allocates; X -> FULL promotes (expands what was
+// uploaded so far); FULL stays FULL (a compact tile is then expanded on arrival).
+static int ensure_plane_mode(pb_ctx* ctx, int want) {
+    if (ctx->plane_mode == want || ctx->plane_mode == PB_PLANES_FULL) return PB_OK;
+    int rc;
+    if (want == PB_PLANES_X) {
+        const size_t plane = (size_t)ctx->N * ctx->Wp * 8;
+        cudaError_t e = cudaMalloc(&ctx->d_X, plane);
+        if (e != cudaSuccess) { ctx->d_X = nullptr; ctx->err = std::string("cudaMalloc of the X plane: ") + cudaGetErrorString(e); return PB_ERR_OOM; }
+        PB_CUDA(cudaMalloc(&ctx->d_xmask, (size_t)ctx->W * 32));
+        PB_CUDA(cudaMalloc(&ctx->d_xvalid, (size_t)ctx->W * 8));
+        PB_CUDA(cudaMemsetAsync(ctx->d_X, 0, plane, ctx->stream));
+        PB_CUDA(cudaMemsetAsync(ctx->d_xmask, 0, (size_t)ctx->W * 32, ctx->stream));
+        PB_CUDA(cudaMemsetAsync(ctx->d_xvalid, 0, (size_t)ctx->W * 8, ctx->stream));
+        const cuuint64_t gdim[2] = {(cuuint64_t)ctx->W, (cuuint64_t)ctx->N};
+        const cuuint64_t gstride[1] = {(cuuint64_t)ctx->Wp * 8};
+        const cuuint32_t box[2] = {PB_K1_COLS, 1};
+        if ((rc = tensor_map(ctx, &ctx->tmap_x, ctx->d_X, 2, gdim, gstride, box))) return rc;
+        ctx->plane_mode = PB_PLANES_X;
+        return PB_OK;
+    }
+    if ((rc = alloc_full_planes(ctx))) return rc;
+    if (ctx->plane_mode == PB_PLANES_X) {
+        if ((rc = pbk_promote_planes(ctx))) return rc;
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_X); cudaFree(ctx->d_xmask); cudaFree(ctx->d_xvalid);
+        ctx->d_X = ctx->d_xmask = ctx->d_xvalid = nullptr;
+    }
+    ctx->plane_mode = PB_PLANES_FULL;
+    return PB_OK;
+}
+
+extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
+    CHECK_CTX(ctx);
+    if (ctx->N == 0) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: call pb_set_tree first");
+    if (n_sites < 1 || n_sites >= (1ll << 32)) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: n_sites out of range");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    ctx->events_done = ctx->assoc_done = false;
+    if (n_sites == ctx->S && ctx->plane_mode != PB_PLANES_NONE) return PB_OK;   // same shape: the uploaded planes stay
+    free_planes(ctx);
+    for (void** p : {(void**)&ctx->d_cnt, (void**)&ctx->d_sites, (void**)&ctx->d_site_flags, (void**)&ctx->d_site_scan, (void**)&ctx->d_raw})
+        if (*p) { cudaFree(*p); *p = nullptr; }
+    ctx->S = n_sites;
+    ctx->W = (n_sites + 63) / 64;
+    ctx->Wp = (ctx->W + 15) & ~15ll;  // rows padded to 128 B
+    // The planes themselves are allocated by the first upload: one plane (X) while every tile is biallelic with all
+    // genotypes valid, three otherwise.  Make sure the worst case fits now, so that an oversized alignment fails here.
     {
-        // TMA descriptor: dims (word column, node, plane); one box = the 3 KB a block needs of one tree row
-        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        PB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(ctx, PB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-        const cuuint64_t gdim[3] = {(cuuint64_t)ctx->W, (cuuint64_t)ctx->N, 3};
-        const cuuint64_t gstride[2] = {(cuuint64_t)ctx->Wp * 8, (cuuint64_t)plane};
-        const cuuint32_t box[3] = {PB_K1_COLS, 1, 3};
-        const cuuint32_t estride[3] = {1, 1, 1};
-        CUresult cr = ((encode_fn)fn)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, ctx->d_planes, gdim, gstride, box, estride,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) FAIL(ctx, PB_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)cr) + ")");
+        size_t free_b = 0, total_b = 0;
+        PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t plane = (size_t)ctx->N * ctx->Wp * 8;
+        if (plane > free_b) {
+            ctx->err = "pb_set_sites: a plane of " + std::to_string(plane) + " B does not fit the device (" + std::to_string(free_b) + " B free)";
+            ctx->S = 0;
+            return PB_ERR_OOM;
+        }
     }
     PB_CUDA(cudaMalloc(&ctx->d_cnt, (size_t)n_sites * PB_CNT_STRIDE * 4));
     PB_CUDA(cudaMalloc(&ctx->d_sites, (size_t)n_sites * sizeof(pb_site_out)));
@@ -363,11 +421,12 @@ extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
 extern "C" int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* B0,
                              const uint64_t* B1, const uint64_t* V) {
     CHECK_CTX(ctx);
-    if (!ctx->d_B0) FAIL(ctx, PB_ERR_INVALID, "pb_put_planes: call pb_set_sites first");
+    if (ctx->S == 0) FAIL(ctx, PB_ERR_INVALID, "pb_put_planes: call pb_set_sites first");
     if (!B0 || !B1 || !V || word_begin < 0 || n_words < 1 || word_begin + n_words > ctx->W || src_pitch_words < n_words)
         FAIL(ctx, PB_ERR_INVALID, "pb_put_planes: tile out of range");
     PB_CUDA(cudaSetDevice(ctx->device));
     ctx->events_done = ctx->assoc_done = false;
+    { int rc = ensure_plane_mode(ctx, PB_PLANES_FULL); if (rc) return rc; }
     const uint64_t* src[3] = {B0, B1, V};
     uint64_t* dst[3] = {ctx->d_B0, ctx->d_B1, ctx->d_V};
     if (word_begin == 0 && n_words == ctx->W && src_pitch_words == ctx->Wp) {
@@ -387,38 +446,49 @@ extern "C" int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, i
 extern "C" int pb_put_planes_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* X,
                                        const uint64_t* V, const uint64_t* colmask) {
     CHECK_CTX(ctx);
-    if (!ctx->d_B0) FAIL(ctx, PB_ERR_INVALID, "pb_put_planes_biallelic: call pb_set_sites first");
+    if (ctx->S == 0) FAIL(ctx, PB_ERR_INVALID, "pb_put_planes_biallelic: call pb_set_sites first");
     if (!X || !colmask || word_begin < 0 || n_words < 1 || word_begin + n_words > ctx->W || src_pitch_words < n_words)
         FAIL(ctx, PB_ERR_INVALID, "pb_put_planes_biallelic: tile out of range");
     PB_CUDA(cudaSetDevice(ctx->device));
     ctx->events_done = ctx->assoc_done = false;
+    int rc;
+    const bool flat = word_begin == 0 && n_words == ctx->W && src_pitch_words == ctx->Wp;
+    auto copy_rows = [&](uint64_t* dst, const uint64_t* src) -> cudaError_t {
+        if (flat) return cudaMemcpyAsync(dst, src, (size_t)ctx->N * ctx->Wp * 8, cudaMemcpyHostToDevice, ctx->stream);
+        return cudaMemcpy2DAsync(dst + word_begin, (size_t)ctx->Wp * 8, src, (size_t)src_pitch_words * 8, (size_t)n_words * 8, (size_t)ctx->N,
+                                 cudaMemcpyHostToDevice, ctx->stream);
+    };
+    // every genotype valid and no full-plane tile so far: the alignment stays one plane in HBM (k1x_events_kernel)
+    const bool keep_x = !V && ctx->plane_mode != PB_PLANES_FULL && !(ctx->cfg.flags & PB_FLAG_FULL_PLANES);
+    if (keep_x) {
+        if ((rc = ensure_plane_mode(ctx, PB_PLANES_X))) return rc;
+        PB_CUDA(cudaMemcpyAsync(ctx->d_xmask + 4 * word_begin, colmask, (size_t)n_words * 32, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(cudaMemsetAsync(ctx->d_xvalid + word_begin, 0xFF, (size_t)n_words * 8, ctx->stream));
+        PB_CUDA(copy_rows(ctx->d_X, X));
+        if (word_begin + n_words == ctx->W && (rc = pbk_mask_last_word_x(ctx))) return rc;
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers are caller-owned: do not retain them past return
+        return PB_OK;
+    }
+    if ((rc = ensure_plane_mode(ctx, PB_PLANES_FULL))) return rc;
     if (n_words > ctx->colmask_cap) {
         if (ctx->d_colmask) { cudaFree(ctx->d_colmask); ctx->d_colmask = nullptr; ctx->colmask_cap = 0; }
         PB_CUDA(cudaMalloc(&ctx->d_colmask, (size_t)n_words * 32));
         ctx->colmask_cap = n_words;
     }
     PB_CUDA(cudaMemcpyAsync(ctx->d_colmask, colmask, (size_t)n_words * 32, cudaMemcpyHostToDevice, ctx->stream));
-    const uint64_t* src[2] = {X, V};
-    uint64_t* dst[2] = {ctx->d_B0, ctx->d_V};       // X lands in the B0 rows and is expanded in place
-    for (int i = 0; i < 2; i++) {
-        if (!src[i]) continue;
-        if (word_begin == 0 && n_words == ctx->W && src_pitch_words == ctx->Wp)
-            PB_CUDA(cudaMemcpyAsync(dst[i], src[i], (size_t)ctx->N * ctx->Wp * 8, cudaMemcpyHostToDevice, ctx->stream));
-        else
-            PB_CUDA(cudaMemcpy2DAsync(dst[i] + word_begin, (size_t)ctx->Wp * 8, src[i], (size_t)src_pitch_words * 8, (size_t)n_words * 8,
-                                      (size_t)ctx->N, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    int rc = pbk_expand_biallelic(ctx, word_begin, n_words, ctx->d_colmask, V == nullptr);
-    if (rc) return rc;
+    PB_CUDA(copy_rows(ctx->d_B0, X));               // X lands in the B0 rows and is expanded in place
+    if (V) PB_CUDA(copy_rows(ctx->d_V, V));
+    if ((rc = pbk_expand_biallelic(ctx, word_begin, n_words, ctx->d_colmask, V == nullptr))) return rc;
     if (V && word_begin + n_words == ctx->W) { rc = pbk_mask_last_word(ctx); if (rc) return rc; }
-    PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers are caller-owned: do not retain them past return
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
     return PB_OK;
 }
 
 extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts) {
     CHECK_CTX(ctx);
-    if (!ctx->d_B0 || ctx->N == 0) FAIL(ctx, PB_ERR_INVALID, "pb_run_events: tree and planes must be set");
+    if (ctx->S == 0 || ctx->N == 0) FAIL(ctx, PB_ERR_INVALID, "pb_run_events: tree and planes must be set");
     PB_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->plane_mode == PB_PLANES_NONE) { int rc0 = ensure_plane_mode(ctx, PB_PLANES_FULL); if (rc0) return rc0; }   // nothing uploaded: no valid genotype anywhere
     ctx->tm = pb_timings{};
     int rc;
     PB_CUDA(cudaEventRecord(ctx->ev[12], ctx->stream));
@@ -442,7 +512,8 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
     float t;
     cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]); ctx->tm.ms_events_kernel = t;
     cudaEventElapsedTime(&t, ctx->ev[12], ctx->ev[13]); ctx->tm.ms_events_total = t;
-    ctx->tm.k1_algorithmic_bytes = 3ll * ctx->N * ctx->W * 8 + 32ll * ctx->S + 8ll * ctx->n_raw;
+    ctx->tm.plane_mode = ctx->plane_mode;
+    ctx->tm.k1_algorithmic_bytes = (ctx->plane_mode == PB_PLANES_X ? 1ll : 3ll) * ctx->N * ctx->W * 8 + 32ll * ctx->S + 8ll * ctx->n_raw;
     ctx->tm.n_informative = ctx->S_inf; ctx->tm.n_alleles_in_use = ctx->A_inuse; ctx->tm.n_extant_events = ctx->E;
     ctx->events_done = true;
     ctx->assoc_done = false;

@@ -25,6 +25,8 @@
 #define PB_OP_FLUSH 0xE0000000u
 #define PB_REC_NOFLUSH 0xFFFFFFFFu
 
+enum { PB_PLANES_NONE = 0, PB_PLANES_X = 1, PB_PLANES_FULL = 2 };
+
 // raw MRCA event: lo = site (context-local), hi = node | base<<29 | is_leaf<<31
 typedef unsigned long long raw_event_t;
 #define PB_EV_NODE_MASK 0x1FFFFFFFu
@@ -113,6 +115,14 @@ struct pb_ctx {
     uint64_t *d_B0 = nullptr, *d_B1 = nullptr, *d_V = nullptr;   // views into d_planes
     CUtensorMap tmap{};             // 3-D TMA descriptor over d_planes: box = 128 words x 1 node x 3 planes
     uint64_t* d_colmask = nullptr; int64_t colmask_cap = 0;   // [n_words][4] site masks of a compact (biallelic) tile upload
+    // Plane storage mode.  PB_PLANES_X: every tile uploaded so far was biallelic with all genotypes valid, so the alignment is
+    // held as ONE plane X[N][Wp] + per-column site masks, and events run k1x_events_kernel over a third of the bytes.  The
+    // first tile that does not qualify promotes the context to the three full planes (pbk_promote_planes).
+    int plane_mode = 0;             // PB_PLANES_*
+    uint64_t* d_X = nullptr;        // [N][Wp]
+    uint64_t* d_xmask = nullptr;    // [W][4] {A0, A1, D0, D1} of every uploaded column (zero where nothing was uploaded)
+    uint64_t* d_xvalid = nullptr;   // [W] sites that exist in an uploaded column (padding bits of word W-1 excluded)
+    CUtensorMap tmap_x{};           // 2-D TMA descriptor over d_X: box = 128 words x 1 node
 
     // K1 outputs
     uint64_t* d_census = nullptr;      // [n_flush][4][KS][W]
@@ -188,6 +198,8 @@ struct pb_ctx {
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------
 int pbk_events(pb_ctx* ctx);                                   // k1_events.cu
 int pbk_mask_last_word(pb_ctx* ctx);                           // k1_events.cu (clears the padding bits of site word W-1 in V)
+int pbk_promote_planes(pb_ctx* ctx);                           // k1_events.cu: X + masks -> the three full planes (already allocated)
+int pbk_mask_last_word_x(pb_ctx* ctx);                         // k1_events.cu
 int pbk_expand_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, const uint64_t* d_colmask, bool fill_v);  // k1_events.cu
 int pbk_prepare_tail(pb_ctx* ctx);                             // k1_events.cu (tail buffers + zero-fill on stream2, before K1)
 int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out); // k1_events.cu

@@ -161,6 +161,7 @@ def test_events_compact_biallelic_upload(oracle_mod, gaps, S):
         hc.set_phenos(sn, lab)
         hc.set_planes(B0, B1, V, S, tile_words=6, compact=compact)
         ev, cc = hc.count_all_homoplasy_events()
+        assert hc.timings()["plane_mode"] == 2     # tile 2 is not compact: three planes (promoted from X when gaps is False)
         st, mt = hc.assoc()
         res.append((ev.tobytes(), cc, st.tobytes(), mt.tobytes()))
         if compact:
@@ -190,9 +191,79 @@ def test_events_compact_biallelic_upload(oracle_mod, gaps, S):
     hc.set_sites(S)
     hc.put_planes_biallelic(X, Vp, colmask)
     ev, cc = hc.count_all_homoplasy_events()
+    assert hc.timings()["plane_mode"] == (2 if gaps else 1)
     o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
     or_ev, or_cc = o.count_all_homoplasy_events(chars)
     assert_events_equal(ev, cc, or_ev, or_cc)
+    hc.close()
+
+
+@pytest.mark.parametrize("n_leaves,S,chunks", [(150, 64 * 41 + 11, None), (700, 500, "1"), (700, 500, "21"), (1300, 64 * 300, None)])
+def test_events_one_plane_mode(oracle_mod, monkeypatch, n_leaves, S, chunks):
+    """Every tile compact with all genotypes valid: the alignment stays ONE plane in HBM and k1x_events_kernel runs.
+    Events, raw MRCA list, CSR and the whole assoc output are identical to the three-plane path and to the oracle."""
+    if chunks:
+        monkeypatch.setenv("PB_K1_CHUNKS", chunks)
+    tree = synth.yule_tree(n_leaves, 8) if n_leaves != 700 else synth.random_tree(700, 4, polytomy=0.3)
+    B0, B1, V = synth.simulate_planes(tree, S, 3)
+    sn, lab = synth.simulate_phenotypes(tree, 4, na_frac=0.02, no_row_frac=0.02)
+    res = []
+    for full in (False, True):
+        hc = pb.HomoplasyCounter(num_replicates=256, seed=3, full_planes=full, site_offset=640)
+        hc.set_tree(tree.parent, tree.is_leaf)
+        hc.set_phenos(sn, lab)
+        hc.set_planes(B0, B1, V, S, tile_words=7, compact=True)
+        ev, cc = hc.count_all_homoplasy_events()
+        assert hc.timings()["plane_mode"] == (2 if full else 1)
+        rs, rn = hc.raw_events()
+        order = np.lexsort((rn, rs))
+        off, idx = hc.event_csr()
+        csr = [sorted(idx[off[i]:off[i + 1]].tolist()) for i in range(len(off) - 1)]
+        st, mt = hc.assoc()
+        res.append((ev.tobytes(), cc, rs[order].tobytes(), rn[order].tobytes(), csr, st.tobytes(), mt.tobytes()))
+        if not full:
+            o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+            or_ev, or_cc = o.count_all_homoplasy_events(synth.planes_to_chars(B0, B1, V, 0, S))
+            e2 = ev.copy()
+            e2["segsite_id"] -= 640
+            assert_events_equal(e2, cc, or_ev, or_cc)
+        hc.close()
+    assert res[0] == res[1]
+
+
+def test_one_plane_mode_partial_upload_and_reuse(oracle_mod):
+    """Columns nobody uploaded hold no valid genotype in either storage mode; a context re-used for a second alignment of
+    the same shape keeps working; a full-plane tile arriving late promotes the context without losing earlier tiles."""
+    tree = synth.yule_tree(90, 2)
+    S = 64 * 20 + 3
+    B0, B1, V = synth.simulate_planes(tree, S, 5)
+    out = []
+    for full in (False, True):
+        hc = pb.HomoplasyCounter(num_replicates=16, full_planes=full)
+        hc.set_tree(tree.parent, tree.is_leaf)
+        hc.set_sites(S)
+        c = pb.compact_planes(B0[:, 4:15], B1[:, 4:15], V[:, 4:15], 64 * 11)
+        hc.put_planes_biallelic(c[0], None, c[1], 4)                # only words 4..14
+        ev, cc = hc.count_all_homoplasy_events()
+        assert cc["no_allele"] == S - 64 * 11
+        out.append((ev.tobytes(), cc))
+        hc.set_planes(B0, B1, V, S, compact=True)                   # same shape again, now everything
+        ev2, cc2 = hc.count_all_homoplasy_events()
+        out.append((ev2.tobytes(), cc2))
+        hc.close()
+    assert out[0] == out[2] and out[1] == out[3]
+    # late promotion: tiles 0..1 compact (X mode), then a three-plane tile
+    hc = pb.HomoplasyCounter(num_replicates=16)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_sites(S)
+    W = (S + 63) // 64
+    for w0 in (0, 7):
+        c = pb.compact_planes(B0[:, w0:w0 + 7], B1[:, w0:w0 + 7], V[:, w0:w0 + 7], 64 * 7)
+        hc.put_planes_biallelic(c[0], None, c[1], w0)
+    hc.put_planes(B0[:, 14:W], B1[:, 14:W], V[:, 14:W], 14)
+    ev3, cc3 = hc.count_all_homoplasy_events()
+    assert hc.timings()["plane_mode"] == 2
+    assert (ev3.tobytes(), cc3) == out[1]
     hc.close()
 
 
