@@ -312,19 +312,23 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
 // Same edge program, same ring protocol (four 1 KB TMA boxes per stage, PB_KX_STAGES stages), same event queue; the
 // 2-bit base code of an event is rebuilt from the column's site masks (A0, A1, D0, D1 in registers) only when an
 // event is emitted.  The census counter lives entirely in registers (slices 1..128: segments hold <= 248 leaves).
+#ifndef PB_KX_STAGES
 #define PB_KX_STAGES 4
+#endif
+#ifndef PB_KX_BLOCKS_PER_SM
 #define PB_KX_BLOCKS_PER_SM 6
+#endif
 #define KX_ROW_BYTES (PB_K1_COLS * 8)
 #define KX_STAGE_BYTES (2 * PB_K1_RPS * KX_ROW_BYTES)
 #define KX_SMEM_RING (PB_KX_STAGES * KX_STAGE_BYTES)
 #define KX_SMEM_BARS (2 * PB_KX_STAGES * 8)
-#define KX_SMEM_TOTAL (KX_SMEM_RING + K1_SMEM_QUEUE + KX_SMEM_BARS)
+#define KX_SMEM_HI ((PB_K1_KHI + 1) * PB_K1_COLS * 8)          // high census slices + the pending carries into slice 8
+#define KX_SMEM_TOTAL (KX_SMEM_RING + KX_SMEM_HI + K1_SMEM_QUEUE + KX_SMEM_BARS)
 
 struct KXParams {
     int64_t W;
     const uint32_t* __restrict__ ops;
     const int32_t* __restrict__ chunk_op;
-    const uint64_t* __restrict__ xmask;    // [W][4]
     uint64_t* __restrict__ census;         // [flush][KS][W]: leaves carrying the second base
     raw_event_t* __restrict__ raw;
     unsigned long long* raw_cursor;
@@ -337,16 +341,17 @@ __device__ __forceinline__ void tma_load_row_2d(uint32_t dst, const CUtensorMap*
 }
 
 struct CensusX {
-    uint64_t s[PB_K1_KS];     // slices 1, 2, 4, 8, ... 128
-    uint64_t pend2, pend4, pend8;
+    uint64_t s[3];            // slices 1, 2, 4 (slices 8.. and the pending carries into 8 live in shared memory, as in k1_row:
+    uint64_t pend2, pend4;    //  a register-resident counter makes the compiler shuffle the whole state at every flush check)
     int nleaf;
 };
 
-__device__ __forceinline__ void k1x_row(uint32_t op, uint64_t x, uint64_t& px, CensusX& cs, uint64_t a0, uint64_t a1, uint64_t d0, uint64_t d1,
+__device__ __forceinline__ void k1x_row(uint32_t op, uint64_t x, uint64_t& px, CensusX& cs, uint64_t* s_hi, int tid,
                                         uint32_t site_base, uint32_t queue_addr, uint32_t count_addr, const K1Params& p) {
     if (op & PB_OP_TEST) {
         const uint64_t mrca = x ^ px;
-        if (mrca) emit_events(mrca, a0 ^ (x & d0), a1 ^ (x & d1), site_base, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
+        // the event carries the child's X bit in its base field; the tail kernels turn it into the 2-bit base code
+        if (mrca) emit_events(mrca, x, 0, site_base, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
     }
     if (op & PB_OP_SETCUR) px = x;
     if (op & PB_OP_LEAF) {
@@ -358,13 +363,14 @@ __device__ __forceinline__ void k1x_row(uint32_t op, uint64_t x, uint64_t& px, C
         if (ph & 1) {
             cs.pend4 |= cs.s[1] & cs.pend2; cs.s[1] ^= cs.pend2; cs.pend2 = 0;
             if (ph & 2) {
+                uint64_t* s_p8 = s_hi + PB_K1_KHI * PB_K1_COLS + tid;
                 if (!(ph & 4)) {
-                    cs.pend8 = cs.s[2] & cs.pend4; cs.s[2] ^= cs.pend4; cs.pend4 = 0;
+                    *s_p8 = cs.s[2] & cs.pend4; cs.s[2] ^= cs.pend4; cs.pend4 = 0;
                 } else {
-                    uint64_t carry = cs.pend8 | (cs.s[2] & cs.pend4);
-                    cs.s[2] ^= cs.pend4; cs.pend4 = 0; cs.pend8 = 0;
+                    uint64_t carry = *s_p8 | (cs.s[2] & cs.pend4);
+                    cs.s[2] ^= cs.pend4; cs.pend4 = 0;
 #pragma unroll
-                    for (int j = 3; j < PB_K1_KS; j++) { const uint64_t h = cs.s[j]; cs.s[j] = h ^ carry; carry &= h; }
+                    for (int j = 0; j < PB_K1_KHI; j++) { uint64_t* hp = s_hi + j * PB_K1_COLS + tid; const uint64_t h = *hp; *hp = h ^ carry; carry &= h; }
                 }
             }
         }
@@ -375,7 +381,8 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned int s_count;
     __shared__ unsigned long long s_base;
-    raw_event_t* s_queue = reinterpret_cast<raw_event_t*>(smem + KX_SMEM_RING);
+    uint64_t* s_hi = reinterpret_cast<uint64_t*>(smem + KX_SMEM_RING);                     // [slice][consumer]
+    raw_event_t* s_queue = reinterpret_cast<raw_event_t*>(smem + KX_SMEM_RING + KX_SMEM_HI);
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y;
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
     const int r0 = q.chunk_op[chunk], r1 = q.chunk_op[chunk + 1];
     const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(q.ops);
     const uint32_t ring0 = pin_u32(smem_u32(smem));
-    const uint32_t full0 = pin_u32(ring0 + KX_SMEM_RING + K1_SMEM_QUEUE), empty0 = full0 + 8 * PB_KX_STAGES;
+    const uint32_t full0 = pin_u32(ring0 + KX_SMEM_RING + KX_SMEM_HI + K1_SMEM_QUEUE), empty0 = full0 + 8 * PB_KX_STAGES;
 
     if (tid == 0) {
         s_count = 0;
@@ -391,6 +398,8 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (tid < PB_K1_COLS)
+        for (int i = 0; i < PB_K1_KHI + 1; i++) s_hi[i * PB_K1_COLS + tid] = 0;
     __syncthreads();
 
     if (tid >= PB_K1_COLS) {
@@ -420,19 +429,13 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
     const int64_t w = (int64_t)col0 + tid;
     const uint32_t site_base = (uint32_t)(w * 64);
     const uint32_t my_ring = pin_u32(ring0 + tid * 8);
-    const uint32_t queue_addr = pin_u32(ring0 + KX_SMEM_RING), count_addr = pin_u32(smem_u32(&s_count));
-    uint64_t a0 = 0, a1 = 0, d0 = 0, d1 = 0;
-    if (w < q.W) {
-        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(q.xmask + 4 * w), d = *reinterpret_cast<const ulonglong2*>(q.xmask + 4 * w + 2);
-        a0 = a.x; a1 = a.y; d0 = d.x; d1 = d.y;
-    }
+    const uint32_t queue_addr = pin_u32(ring0 + KX_SMEM_RING + KX_SMEM_HI), count_addr = pin_u32(smem_u32(&s_count));
     K1Params ep;                 // emit_events / drain_queue only use the raw list fields
     ep.raw = q.raw; ep.raw_cursor = q.raw_cursor; ep.raw_cap = q.raw_cap;
 
     CensusX cs;
-#pragma unroll
-    for (int j = 0; j < PB_K1_KS; j++) cs.s[j] = 0;
-    cs.pend2 = cs.pend4 = cs.pend8 = 0;
+    cs.s[0] = cs.s[1] = cs.s[2] = 0;
+    cs.pend2 = cs.pend4 = 0;
     cs.nleaf = 0;
     uint64_t px = 0;
     uint32_t soff = 0, boff = 0, phase = 0;
@@ -453,17 +456,20 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
         if (boff == 8 * PB_KX_STAGES) { soff = 0; boff = 0; phase ^= 1; }
 #pragma unroll
         for (int k = 0; k < PB_K1_RPS; k++) {
-            k1x_row(rec[k].x, x[2 * k], px, cs, a0, a1, d0, d1, site_base, queue_addr, count_addr, ep);
-            k1x_row(rec[k].y, x[2 * k + 1], px, cs, a0, a1, d0, d1, site_base, queue_addr, count_addr, ep);
+            k1x_row(rec[k].x, x[2 * k], px, cs, s_hi, tid, site_base, queue_addr, count_addr, ep);
+            k1x_row(rec[k].y, x[2 * k + 1], px, cs, s_hi, tid, site_base, queue_addr, count_addr, ep);
             if (rec[k].z != PB_REC_NOFLUSH) {
                 if (w < q.W) {
                     uint64_t* out = q.census + ((int64_t)rec[k].z * PB_K1_KS) * q.W + w;
 #pragma unroll
-                    for (int j = 0; j < PB_K1_KS; j++) out[(int64_t)j * q.W] = cs.s[j];
-                }
+                    for (int j = 0; j < 3; j++) out[(int64_t)j * q.W] = cs.s[j];
 #pragma unroll
-                for (int j = 0; j < PB_K1_KS; j++) cs.s[j] = 0;
-                cs.pend2 = cs.pend4 = cs.pend8 = 0;
+                    for (int j = 0; j < PB_K1_KHI; j++) out[(int64_t)(3 + j) * q.W] = s_hi[j * PB_K1_COLS + tid];
+                }
+                cs.s[0] = cs.s[1] = cs.s[2] = 0;
+                cs.pend2 = cs.pend4 = 0;
+#pragma unroll
+                for (int j = 0; j < PB_K1_KHI + 1; j++) s_hi[j * PB_K1_COLS + tid] = 0;
                 cs.nleaf = 0;
             }
         }
@@ -475,13 +481,24 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
 
 // ---- per-site event counters -------------------------------------------------------------------
 // the raw list's length lives on the device (K1's cursor, clamped to the buffer): no host round trip before the tail
+// one-plane mode: an event's base field holds the child's X bit; the 2-bit code is the site's first base, XOR (first ^ second) if X
+__device__ __forceinline__ uint32_t event_base(uint32_t hi, uint32_t site, const uint64_t* __restrict__ xmask) {
+    const uint32_t f = (hi >> 29) & 3u;
+    if (!xmask) return f;
+    const uint64_t* m = xmask + 4 * (int64_t)(site >> 6);
+    const int b = (int)(site & 63);
+    const uint32_t a = (uint32_t)((m[0] >> b) & 1ull) | ((uint32_t)((m[1] >> b) & 1ull) << 1);
+    const uint32_t d = (uint32_t)((m[2] >> b) & 1ull) | ((uint32_t)((m[3] >> b) & 1ull) << 1);
+    return a ^ (f ? d : 0u);
+}
+
 __global__ void k1_count_events_kernel(const raw_event_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
-                                       const int32_t* __restrict__ node_sample, uint32_t* __restrict__ cnt) {
+                                       const int32_t* __restrict__ node_sample, const uint64_t* __restrict__ xmask, uint32_t* __restrict__ cnt) {
     const int64_t n = min((int64_t)*cursor, raw_cap);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const raw_event_t e = raw[i];
     const uint32_t site = (uint32_t)e, hi = (uint32_t)(e >> 32);
-    const uint32_t base = (hi >> 29) & 3u, node = hi & PB_EV_NODE_MASK;
+    const uint32_t base = event_base(hi, site, xmask), node = hi & PB_EV_NODE_MASK;
     uint32_t* c = cnt + (int64_t)site * PB_CNT_STRIDE;
     atomicAdd(c + base, 1u);
     if (hi & 0x80000000u) {
@@ -721,7 +738,7 @@ __global__ void k1_scatter_events_kernel(const raw_event_t* __restrict__ raw, co
                                          const int32_t* __restrict__ node_sample, const uint8_t* __restrict__ flags,
                                          const uint64_t* __restrict__ scan, const uint64_t* __restrict__ scan_in,
                                          const pb_site_out* __restrict__ sites, const AlleleMeta* __restrict__ alleles,
-                                         uint32_t* __restrict__ csr_cursor, int32_t* __restrict__ csr) {
+                                         const uint64_t* __restrict__ xmask, uint32_t* __restrict__ csr_cursor, int32_t* __restrict__ csr) {
     const int64_t n = min((int64_t)*cursor, raw_cap);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const raw_event_t e = raw[i];
@@ -732,7 +749,7 @@ __global__ void k1_scatter_events_kernel(const raw_event_t* __restrict__ raw, co
         const uint32_t site = (uint32_t)e;
         if (!(scan_in[site] >> 38)) continue;
         const uint8_t fl = flags[site];
-        const uint32_t base = (hi >> 29) & 3u;
+        const uint32_t base = event_base(hi, site, xmask);
         const int a = (base == ((fl >> PB_SF_A1_CODE_SHIFT) & 3u)) ? 0 : 1;
         if (!(fl & (a == 0 ? PB_SF_A1_USE : PB_SF_A2_USE))) continue;
         // bucket emptied by the <2 rule?  (in_use with min_hcount 0 keeps n = 0)
@@ -831,7 +848,6 @@ static int pbk_events_x(pb_ctx* ctx) {
     KXParams q;
     q.W = ctx->W;
     q.ops = ctx->d_ops; q.chunk_op = ctx->d_chunk_op;
-    q.xmask = ctx->d_xmask;
     q.census = ctx->d_census;
     q.raw = ctx->d_raw; q.raw_cursor = ctx->d_raw_cursor; q.raw_cap = (unsigned long long)ctx->raw_cap;
     const size_t smem = (size_t)KX_SMEM_TOTAL;
@@ -914,9 +930,10 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_zero_done, 0));   // d_cnt, d_csr_cursor zeroed underneath K1 (pbk_prepare_tail)
     PB_CUDA(cudaMemsetAsync(ctx->d_class_counts, 0, 16 * 8, st));
     pb_trace_mark(ctx, "headstart+memsets");
-    k1_count_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_cnt);
-    pb_trace_mark(ctx, "count_events");
     const bool xmode = ctx->plane_mode == PB_PLANES_X;
+    const uint64_t* xmask = xmode ? ctx->d_xmask : nullptr;
+    k1_count_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, xmask, ctx->d_cnt);
+    pb_trace_mark(ctx, "count_events");
     k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), xmode ? 1 : 4), 128, 0, st>>>(ctx->d_census, ctx->n_flush, ctx->W, ctx->d_census_total);
     pb_trace_mark(ctx, "census_reduce");
     int kt_used = 1;
@@ -942,7 +959,7 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
                                                                       ctx->d_inf_site, ctx->d_alleles, ctx->d_class_counts);
     pb_trace_mark(ctx, "scatter_sites");
     k1_scatter_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
-                                                     scan_out, scan_in, ctx->d_sites, ctx->d_alleles, ctx->d_csr_cursor, ctx->d_csr);
+                                                     scan_out, scan_in, ctx->d_sites, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr);
     pb_trace_mark(ctx, "scatter_events");
     ctx->tm.n_launches += 2;
     PB_CUDA(cudaGetLastError());
