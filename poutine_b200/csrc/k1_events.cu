@@ -308,21 +308,27 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
 // K1X — the same sweep over ONE plane.  When every site carries at most two bases and every genotype is valid
 // (pb_put_planes_biallelic with V = NULL for every tile), a node's genotype is one bit: X = "carries the site's second
 // base".  The MRCA test of an edge is then X_child ^ X_parent, the leaf census one counter (how many leaves carry the
-// second base), and a row is 1 KB per block instead of 3 KB: a third of the HBM bytes, about a third of the instructions.
-// Same edge program, same ring protocol (four 1 KB TMA boxes per stage, PB_KX_STAGES stages), same event queue; the
-// 2-bit base code of an event is rebuilt from the column's site masks (A0, A1, D0, D1 in registers) only when an
-// event is emitted.  The census counter lives entirely in registers (slices 1..128: segments hold <= 248 leaves).
+// second base), and a tree row is a third of the bytes.  With so little work per word the per-row control flow (op
+// decode, ring handshake, census phases) dominates, so a consumer thread owns PB_KX_WPT adjacent word columns (one
+// 16-byte shared-memory load per row) and a block PB_KX_COLS = 128 * PB_KX_WPT columns; its own edge program
+// (pb_ctx::progx) is cut for that grid.  Same ring protocol (2*RPS TMA boxes per stage, PB_KX_STAGES stages), same
+// event queue; an event carries the child's X bit in its base field and the tail kernels rebuild the 2-bit base code
+// from the column's site masks (event_base).  Census: slices 1/2/4 in registers, 8.. in shared memory, as in k1_row.
+#ifndef PB_KX_WPT
+#define PB_KX_WPT 2
+#endif
 #ifndef PB_KX_STAGES
-#define PB_KX_STAGES 4
+#define PB_KX_STAGES (4 / PB_KX_WPT)
 #endif
 #ifndef PB_KX_BLOCKS_PER_SM
-#define PB_KX_BLOCKS_PER_SM 6
+#define PB_KX_BLOCKS_PER_SM 5
 #endif
-#define KX_ROW_BYTES (PB_K1_COLS * 8)
+#define PB_KX_COLS (PB_K1_COLS * PB_KX_WPT)
+#define KX_ROW_BYTES (PB_KX_COLS * 8)
 #define KX_STAGE_BYTES (2 * PB_K1_RPS * KX_ROW_BYTES)
 #define KX_SMEM_RING (PB_KX_STAGES * KX_STAGE_BYTES)
 #define KX_SMEM_BARS (2 * PB_KX_STAGES * 8)
-#define KX_SMEM_HI ((PB_K1_KHI + 1) * PB_K1_COLS * 8)          // high census slices + the pending carries into slice 8
+#define KX_SMEM_HI ((PB_K1_KHI + 1) * PB_KX_COLS * 8)          // high census slices + the pending carries into slice 8
 #define KX_SMEM_TOTAL (KX_SMEM_RING + KX_SMEM_HI + K1_SMEM_QUEUE + KX_SMEM_BARS)
 
 struct KXParams {
@@ -341,36 +347,60 @@ __device__ __forceinline__ void tma_load_row_2d(uint32_t dst, const CUtensorMap*
 }
 
 struct CensusX {
-    uint64_t s[3];            // slices 1, 2, 4 (slices 8.. and the pending carries into 8 live in shared memory, as in k1_row:
-    uint64_t pend2, pend4;    //  a register-resident counter makes the compiler shuffle the whole state at every flush check)
+    uint64_t s[3][PB_KX_WPT];       // slices 1, 2, 4 (slices 8.. and the pending carries into 8 live in shared memory: a fully
+    uint64_t pend2[PB_KX_WPT], pend4[PB_KX_WPT];   // register-resident counter makes the compiler shuffle the state at every flush check)
     int nleaf;
 };
 
-__device__ __forceinline__ void k1x_row(uint32_t op, uint64_t x, uint64_t& px, CensusX& cs, uint64_t* s_hi, int tid,
+struct XRow { uint64_t w[PB_KX_WPT]; };
+
+__device__ __forceinline__ XRow lds_xrow(uint32_t addr) {
+    XRow r;
+#if PB_KX_WPT == 2
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(r.w[0]), "=l"(r.w[1]) : "r"(addr));
+#else
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(r.w[0]) : "r"(addr));
+#endif
+    return r;
+}
+
+__device__ __forceinline__ void k1x_row(uint32_t op, const XRow& x, XRow& px, CensusX& cs, uint64_t* s_hi, int tid,
                                         uint32_t site_base, uint32_t queue_addr, uint32_t count_addr, const K1Params& p) {
     if (op & PB_OP_TEST) {
-        const uint64_t mrca = x ^ px;
-        // the event carries the child's X bit in its base field; the tail kernels turn it into the 2-bit base code
-        if (mrca) emit_events(mrca, x, 0, site_base, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
+#pragma unroll
+        for (int j = 0; j < PB_KX_WPT; j++) {
+            const uint64_t mrca = x.w[j] ^ px.w[j];
+            if (mrca) emit_events(mrca, x.w[j], 0, site_base + 64u * j, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
+        }
     }
     if (op & PB_OP_SETCUR) px = x;
     if (op & PB_OP_LEAF) {
         // deferred-carry bit-sliced counter, as in k1_row, for the single quantity "leaves with X = 1"
         const int ph = cs.nleaf & 7;                                 // block-uniform
         cs.nleaf++;
-        const uint64_t o = cs.s[0];
-        cs.s[0] = o ^ x; cs.pend2 |= o & x;
-        if (ph & 1) {
-            cs.pend4 |= cs.s[1] & cs.pend2; cs.s[1] ^= cs.pend2; cs.pend2 = 0;
-            if (ph & 2) {
-                uint64_t* s_p8 = s_hi + PB_K1_KHI * PB_K1_COLS + tid;
-                if (!(ph & 4)) {
-                    *s_p8 = cs.s[2] & cs.pend4; cs.s[2] ^= cs.pend4; cs.pend4 = 0;
-                } else {
-                    uint64_t carry = *s_p8 | (cs.s[2] & cs.pend4);
-                    cs.s[2] ^= cs.pend4; cs.pend4 = 0;
 #pragma unroll
-                    for (int j = 0; j < PB_K1_KHI; j++) { uint64_t* hp = s_hi + j * PB_K1_COLS + tid; const uint64_t h = *hp; *hp = h ^ carry; carry &= h; }
+        for (int j = 0; j < PB_KX_WPT; j++) { const uint64_t o = cs.s[0][j]; cs.s[0][j] = o ^ x.w[j]; cs.pend2[j] |= o & x.w[j]; }
+        if (ph & 1) {
+#pragma unroll
+            for (int j = 0; j < PB_KX_WPT; j++) { cs.pend4[j] |= cs.s[1][j] & cs.pend2[j]; cs.s[1][j] ^= cs.pend2[j]; cs.pend2[j] = 0; }
+            if (ph & 2) {
+                uint64_t* s_p8 = s_hi + PB_K1_KHI * PB_KX_COLS + tid * PB_KX_WPT;
+                if (!(ph & 4)) {
+#pragma unroll
+                    for (int j = 0; j < PB_KX_WPT; j++) { s_p8[j] = cs.s[2][j] & cs.pend4[j]; cs.s[2][j] ^= cs.pend4[j]; cs.pend4[j] = 0; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PB_KX_WPT; j++) {
+                        uint64_t carry = s_p8[j] | (cs.s[2][j] & cs.pend4[j]);
+                        cs.s[2][j] ^= cs.pend4[j]; cs.pend4[j] = 0;
+#pragma unroll
+                        for (int k = 0; k < PB_K1_KHI; k++) {
+                            uint64_t* hp = s_hi + k * PB_KX_COLS + tid * PB_KX_WPT + j;
+                            const uint64_t h = *hp;
+                            *hp = h ^ carry;
+                            carry &= h;
+                        }
+                    }
                 }
             }
         }
@@ -381,12 +411,12 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned int s_count;
     __shared__ unsigned long long s_base;
-    uint64_t* s_hi = reinterpret_cast<uint64_t*>(smem + KX_SMEM_RING);                     // [slice][consumer]
+    uint64_t* s_hi = reinterpret_cast<uint64_t*>(smem + KX_SMEM_RING);                     // [slice][word column of the block]
     raw_event_t* s_queue = reinterpret_cast<raw_event_t*>(smem + KX_SMEM_RING + KX_SMEM_HI);
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y;
-    const int32_t col0 = (int32_t)blockIdx.x * PB_K1_COLS;
+    const int32_t col0 = (int32_t)blockIdx.x * PB_KX_COLS;
     const int r0 = q.chunk_op[chunk], r1 = q.chunk_op[chunk + 1];
     const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(q.ops);
     const uint32_t ring0 = pin_u32(smem_u32(smem));
@@ -399,11 +429,11 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (tid < PB_K1_COLS)
-        for (int i = 0; i < PB_K1_KHI + 1; i++) s_hi[i * PB_K1_COLS + tid] = 0;
+        for (int i = 0; i < (PB_K1_KHI + 1) * PB_KX_WPT; i++) s_hi[i * PB_K1_COLS + tid] = 0;
     __syncthreads();
 
     if (tid >= PB_K1_COLS) {
-        // producer warp: one lane, four 1 KB boxes per stage (padding slots are out-of-bounds boxes: zero-filled)
+        // producer warp: one lane, 2*RPS row boxes per stage (padding slots are out-of-bounds boxes: zero-filled)
         if (tid == PB_K1_COLS) {
             uint32_t soff = 0, boff = 0, phase = 0;
             for (int i = r0; i < r1; i += PB_K1_RPS) {
@@ -424,20 +454,22 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
         return;
     }
 
-    // consumer warps: one thread = one 64-site word column
+    // consumer warps: one thread = PB_KX_WPT adjacent 64-site word columns
     const int lane = tid & 31;
-    const int64_t w = (int64_t)col0 + tid;
+    const int64_t w = (int64_t)col0 + tid * PB_KX_WPT;
     const uint32_t site_base = (uint32_t)(w * 64);
-    const uint32_t my_ring = pin_u32(ring0 + tid * 8);
+    const uint32_t my_ring = pin_u32(ring0 + tid * (8 * PB_KX_WPT));
     const uint32_t queue_addr = pin_u32(ring0 + KX_SMEM_RING + KX_SMEM_HI), count_addr = pin_u32(smem_u32(&s_count));
-    K1Params ep;                 // emit_events / drain_queue only use the raw list fields
+    K1Params ep;                 // emit_events only uses the raw list fields
     ep.raw = q.raw; ep.raw_cursor = q.raw_cursor; ep.raw_cap = q.raw_cap;
 
     CensusX cs;
-    cs.s[0] = cs.s[1] = cs.s[2] = 0;
-    cs.pend2 = cs.pend4 = 0;
+#pragma unroll
+    for (int j = 0; j < PB_KX_WPT; j++) { cs.s[0][j] = cs.s[1][j] = cs.s[2][j] = 0; cs.pend2[j] = cs.pend4[j] = 0; }
     cs.nleaf = 0;
-    uint64_t px = 0;
+    XRow px;
+#pragma unroll
+    for (int j = 0; j < PB_KX_WPT; j++) px.w[j] = 0;
     uint32_t soff = 0, boff = 0, phase = 0;
 
 #pragma unroll 1
@@ -447,9 +479,9 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
         for (int k = 0; k < PB_K1_RPS; k++) rec[k] = __ldg(recs + i + k);
         mbar_wait(full0 + boff, phase);
         const uint32_t src = my_ring + soff;
-        uint64_t x[2 * PB_K1_RPS];
+        XRow x[2 * PB_K1_RPS];
 #pragma unroll
-        for (int k = 0; k < 2 * PB_K1_RPS; k++) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(x[k]) : "r"(src + k * KX_ROW_BYTES));
+        for (int k = 0; k < 2 * PB_K1_RPS; k++) x[k] = lds_xrow(src + k * KX_ROW_BYTES);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + boff);                     // the stage's rows are in registers: free it
         soff += KX_STAGE_BYTES; boff += 8;
@@ -459,17 +491,20 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
             k1x_row(rec[k].x, x[2 * k], px, cs, s_hi, tid, site_base, queue_addr, count_addr, ep);
             k1x_row(rec[k].y, x[2 * k + 1], px, cs, s_hi, tid, site_base, queue_addr, count_addr, ep);
             if (rec[k].z != PB_REC_NOFLUSH) {
-                if (w < q.W) {
-                    uint64_t* out = q.census + ((int64_t)rec[k].z * PB_K1_KS) * q.W + w;
 #pragma unroll
-                    for (int j = 0; j < 3; j++) out[(int64_t)j * q.W] = cs.s[j];
+                for (int j = 0; j < PB_KX_WPT; j++) {
+                    if (w + j < q.W) {
+                        uint64_t* out = q.census + ((int64_t)rec[k].z * PB_K1_KS) * q.W + w + j;
 #pragma unroll
-                    for (int j = 0; j < PB_K1_KHI; j++) out[(int64_t)(3 + j) * q.W] = s_hi[j * PB_K1_COLS + tid];
+                        for (int t = 0; t < 3; t++) out[(int64_t)t * q.W] = cs.s[t][j];
+#pragma unroll
+                        for (int t = 0; t < PB_K1_KHI; t++) out[(int64_t)(3 + t) * q.W] = s_hi[t * PB_KX_COLS + tid * PB_KX_WPT + j];
+                    }
+                    cs.s[0][j] = cs.s[1][j] = cs.s[2][j] = 0;
+                    cs.pend2[j] = cs.pend4[j] = 0;
+#pragma unroll
+                    for (int t = 0; t < PB_K1_KHI + 1; t++) s_hi[t * PB_KX_COLS + tid * PB_KX_WPT + j] = 0;
                 }
-                cs.s[0] = cs.s[1] = cs.s[2] = 0;
-                cs.pend2 = cs.pend4 = 0;
-#pragma unroll
-                for (int j = 0; j < PB_K1_KHI + 1; j++) s_hi[j * PB_K1_COLS + tid] = 0;
                 cs.nleaf = 0;
             }
         }
@@ -478,6 +513,9 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
     }
     drain_queue(s_queue, &s_count, &s_base, tid, 1, q.raw, q.raw_cursor, q.raw_cap);
 }
+
+int pbk_kx_cols() { return PB_KX_COLS; }
+int pbk_kx_blocks_per_sm() { return PB_KX_BLOCKS_PER_SM; }
 
 // ---- per-site event counters -------------------------------------------------------------------
 // the raw list's length lives on the device (K1's cursor, clamped to the buffer): no host round trip before the tail
@@ -847,7 +885,7 @@ int pbk_promote_planes(pb_ctx* ctx) {
 static int pbk_events_x(pb_ctx* ctx) {
     KXParams q;
     q.W = ctx->W;
-    q.ops = ctx->d_ops; q.chunk_op = ctx->d_chunk_op;
+    q.ops = ctx->d_ops_x; q.chunk_op = ctx->d_chunk_op_x;
     q.census = ctx->d_census;
     q.raw = ctx->d_raw; q.raw_cursor = ctx->d_raw_cursor; q.raw_cap = (unsigned long long)ctx->raw_cap;
     const size_t smem = (size_t)KX_SMEM_TOTAL;
@@ -856,7 +894,7 @@ static int pbk_events_x(pb_ctx* ctx) {
         PB_CUDA(cudaFuncSetAttribute(k1x_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    dim3 grid((unsigned)((ctx->W + PB_K1_COLS - 1) / PB_K1_COLS), (unsigned)ctx->n_chunks);
+    dim3 grid((unsigned)((ctx->W + PB_KX_COLS - 1) / PB_KX_COLS), (unsigned)ctx->n_chunks_x);
     PB_CUDA(cudaMemsetAsync(ctx->d_raw_cursor, 0, 8, ctx->stream));
     PB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     pb_trace_mark(ctx, "start");
@@ -934,7 +972,8 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     const uint64_t* xmask = xmode ? ctx->d_xmask : nullptr;
     k1_count_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, xmask, ctx->d_cnt);
     pb_trace_mark(ctx, "count_events");
-    k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), xmode ? 1 : 4), 128, 0, st>>>(ctx->d_census, ctx->n_flush, ctx->W, ctx->d_census_total);
+    k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), xmode ? 1 : 4), 128, 0, st>>>(ctx->d_census, xmode ? ctx->n_flush_x : ctx->n_flush,
+                                                                                                 ctx->W, ctx->d_census_total);
     pb_trace_mark(ctx, "census_reduce");
     int kt_used = 1;
     while ((1ll << kt_used) <= (int64_t)ctx->L) kt_used++;

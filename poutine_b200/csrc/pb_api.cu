@@ -16,7 +16,7 @@ extern "C" int pb_version(void) { return 100; }
 extern "C" const char* pb_last_error(pb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 static void free_all(pb_ctx* c) {
-    void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_node_sample, c->d_label, c->d_planes,
+    void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_ops_x, c->d_chunk_op_x, c->d_node_sample, c->d_label, c->d_planes,
                     c->d_census, c->d_census_total, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
                     c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT,
                     c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop, c->d_colmask, c->d_extras, c->d_X, c->d_xmask, c->d_xvalid};
@@ -165,12 +165,12 @@ static int build_schedule(pb_ctx* ctx) {
 // stream: SETCUR reloads where the tracked parent row is not the edge's parent, census segments closed
 // by FLUSH ops (leaf count padded to a multiple of 8 with null leaves: the carry-save tree works in
 // groups of 8), chunks padded to a multiple of 4 ops.
-static int build_chunks(pb_ctx* ctx) {
-    if (ctx->N == 0 || ctx->W == 0) return PB_OK;
+static int build_program(pb_ctx* ctx, int64_t cols_per_block, int64_t blocks_per_sm, uint32_t** d_ops, int32_t** d_chunk_op,
+                         int32_t* n_chunks_out, int32_t* n_flush_out) {
     const int64_t n_lops = (int64_t)ctx->lop_child.size();
-    const int64_t blocks_x = (ctx->W + PB_K1_COLS - 1) / PB_K1_COLS;
+    const int64_t blocks_x = (ctx->W + cols_per_block - 1) / cols_per_block;
     // grid.y: ~4 waves of 4 resident blocks per SM, picking the chunk count whose last wave is fullest
-    int64_t slots = (int64_t)ctx->sm_count * PB_K1_BLOCKS_PER_SM;
+    int64_t slots = (int64_t)ctx->sm_count * blocks_per_sm;
     if (const char* e = getenv("PB_K1_TARGET_BLOCKS")) slots = atoll(e);
     int64_t n_chunks = 1;
     {
@@ -185,7 +185,7 @@ static int build_chunks(pb_ctx* ctx) {
     if (const char* e = getenv("PB_K1_CHUNKS")) n_chunks = atoll(e);
     n_chunks = std::min<int64_t>(n_chunks, std::max<int64_t>(1, n_lops / 32));
     n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, 65535));
-    ctx->n_chunks = (int32_t)n_chunks;
+    *n_chunks_out = (int32_t)n_chunks;
 
     std::vector<uint32_t> recs;   // 4 words per record
     recs.reserve((size_t)n_lops * 3 + 64 * n_chunks);
@@ -228,16 +228,25 @@ static int build_chunks(pb_ctx* ctx) {
         chunk_op[c + 1] = (int32_t)(recs.size() / 4);
     }
     const std::vector<uint32_t>& ops = recs;
-    ctx->n_flush = n_flush;
+    *n_flush_out = n_flush;
     int rc;
-    if ((rc = upload(ctx, &ctx->d_ops, ops))) return rc;
-    if ((rc = upload(ctx, &ctx->d_chunk_op, chunk_op))) return rc;
+    if ((rc = upload(ctx, d_ops, ops))) return rc;
+    return upload(ctx, d_chunk_op, chunk_op);
+}
+
+// two programs over the same edge list: one per sweep kernel (their grids differ), one census buffer for both
+static int build_chunks(pb_ctx* ctx) {
+    if (ctx->N == 0 || ctx->W == 0) return PB_OK;
+    int rc;
+    if ((rc = build_program(ctx, PB_K1_COLS, PB_K1_BLOCKS_PER_SM, &ctx->d_ops, &ctx->d_chunk_op, &ctx->n_chunks, &ctx->n_flush))) return rc;
+    if ((rc = build_program(ctx, pbk_kx_cols(), pbk_kx_blocks_per_sm(), &ctx->d_ops_x, &ctx->d_chunk_op_x, &ctx->n_chunks_x, &ctx->n_flush_x))) return rc;
     if (ctx->d_census) { cudaFree(ctx->d_census); ctx->d_census = nullptr; }
-    PB_CUDA(cudaMalloc(&ctx->d_census, (size_t)n_flush * 4 * PB_K1_KS * ctx->W * 8));
+    PB_CUDA(cudaMalloc(&ctx->d_census, (size_t)std::max<int64_t>(4ll * ctx->n_flush, ctx->n_flush_x) * PB_K1_KS * ctx->W * 8));
     if (ctx->d_census_total) { cudaFree(ctx->d_census_total); ctx->d_census_total = nullptr; }
     PB_CUDA(cudaMalloc(&ctx->d_census_total, (size_t)4 * PB_K1_KT * ctx->W * 8));
     return PB_OK;
 }
+
 
 static int build_node_sample(pb_ctx* ctx) {
     if (ctx->N == 0) return PB_OK;
@@ -368,7 +377,7 @@ static int ensure_plane_mode(pb_ctx* ctx, int want) {
         PB_CUDA(cudaMemsetAsync(ctx->d_xvalid, 0, (size_t)ctx->W * 8, ctx->stream));
         const cuuint64_t gdim[2] = {(cuuint64_t)ctx->W, (cuuint64_t)ctx->N};
         const cuuint64_t gstride[1] = {(cuuint64_t)ctx->Wp * 8};
-        const cuuint32_t box[2] = {PB_K1_COLS, 1};
+        const cuuint32_t box[2] = {(cuuint32_t)pbk_kx_cols(), 1};
         if ((rc = tensor_map(ctx, &ctx->tmap_x, ctx->d_X, 2, gdim, gstride, box))) return rc;
         ctx->plane_mode = PB_PLANES_X;
         return PB_OK;

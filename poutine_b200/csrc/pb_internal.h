@@ -101,6 +101,9 @@ struct pb_ctx {
     uint32_t* d_ops = nullptr;      // K1 program
     int32_t* d_chunk_op = nullptr;  // n_chunks+1 record boundaries
     int32_t n_chunks = 0, n_flush = 0;
+    uint32_t* d_ops_x = nullptr;    // the same edge list cut for k1x_events_kernel's grid (wider blocks, other residency)
+    int32_t* d_chunk_op_x = nullptr;
+    int32_t n_chunks_x = 0, n_flush_x = 0;
     int32_t* d_node_sample = nullptr;  // N: sample index of a leaf with a pheno row, else -1
 
     // labels
@@ -198,6 +201,8 @@ struct pb_ctx {
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------
 int pbk_events(pb_ctx* ctx);                                   // k1_events.cu
 int pbk_mask_last_word(pb_ctx* ctx);                           // k1_events.cu (clears the padding bits of site word W-1 in V)
+int pbk_kx_cols();                                             // k1_events.cu: word columns per k1x block
+int pbk_kx_blocks_per_sm();
 int pbk_promote_planes(pb_ctx* ctx);                           // k1_events.cu: X + masks -> the three full planes (already allocated)
 int pbk_mask_last_word_x(pb_ctx* ctx);                         // k1_events.cu
 int pbk_expand_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, const uint64_t* d_colmask, bool fill_v);  // k1_events.cu
