@@ -323,6 +323,9 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
 #ifndef PB_KX_BLOCKS_PER_SM
 #define PB_KX_BLOCKS_PER_SM 5
 #endif
+#ifndef PB_KX_DRAIN_EVERY
+#define PB_KX_DRAIN_EVERY (PB_K1_DRAIN_EVERY / PB_KX_WPT)   // a block sees PB_KX_WPT times the events per row
+#endif
 #define PB_KX_COLS (PB_K1_COLS * PB_KX_WPT)
 #define KX_ROW_BYTES (PB_KX_COLS * 8)
 #define KX_STAGE_BYTES (2 * PB_K1_RPS * KX_ROW_BYTES)
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
                 cs.nleaf = 0;
             }
         }
-        if ((((i - r0) / PB_K1_RPS) & (PB_K1_DRAIN_EVERY / PB_K1_RPS - 1)) == PB_K1_DRAIN_EVERY / PB_K1_RPS - 1)
+        if ((((i - r0) / PB_K1_RPS) & (PB_KX_DRAIN_EVERY / PB_K1_RPS - 1)) == PB_KX_DRAIN_EVERY / PB_K1_RPS - 1)
             drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, q.raw, q.raw_cursor, q.raw_cap);
     }
     drain_queue(s_queue, &s_count, &s_base, tid, 1, q.raw, q.raw_cursor, q.raw_cap);
