@@ -32,7 +32,7 @@ struct K1Params {
     const uint32_t* __restrict__ ops;
     const int32_t* __restrict__ chunk_op;
     uint64_t* __restrict__ census;         // [flush][4][KS][W]
-    raw_event_t* __restrict__ raw;
+    raw_rec_t* __restrict__ raw;
     unsigned long long* raw_cursor;
     unsigned long long raw_cap;
 };
@@ -85,42 +85,44 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t x) {
 }
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PB_K1_CONSUMERS) : "memory"); }
 
-// Queue push with plain shared-memory instructions: one ATOMS per event (a warp row rarely holds more than one or two
-// events, so the compiler's warp-aggregated atomicAdd sequence costs more than it saves) and a 32-bit shared-window store.
+// Queue push: one shared-memory atomic and two 16-byte stores per (row, word) that holds any event; the bits are peeled by
+// the tail kernels (k1_count_events_kernel, k1_scatter_events_kernel).
+template <int QCAP>
 __device__ __forceinline__ void emit_events(lane_t mrca, lane_t b0, lane_t b1, uint32_t site_base, uint32_t node_tag,
                                             uint32_t queue_addr, uint32_t count_addr, const K1Params& p) {
-    while (mrca) {
-        const int b = lane_ffs(mrca) - 1;
-        mrca &= mrca - 1;
-        const uint32_t base = (uint32_t)((b0 >> b) & 1u) | ((uint32_t)((b1 >> b) & 1u) << 1);
-        const uint32_t lo = site_base + (uint32_t)b, hi = node_tag | (base << 29);
-        uint32_t slot;
-        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(count_addr) : "memory");
-        if (slot < PB_K1_QCAP) {
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(queue_addr + slot * 8), "r"(lo), "r"(hi) : "memory");
-        } else {  // queue full: slow path straight to global (correct for arbitrarily dense inputs)
-            const unsigned long long pos = atomicAdd(p.raw_cursor, 1ull);
-            if (pos < p.raw_cap) p.raw[pos] = (raw_event_t)lo | ((raw_event_t)hi << 32);
-        }
+    static_assert(sizeof(lane_t) == 8, "raw records hold whole 64-site words");
+    uint32_t slot;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(count_addr) : "memory");
+    const uint32_t wcol = site_base >> 6;
+    if (slot < QCAP) {
+        const uint32_t a = queue_addr + slot * 32;
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(wcol), "r"(node_tag) : "memory");
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(a + 8), "l"(mrca) : "memory");
+        asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(a + 16), "l"(b0), "l"(b1) : "memory");
+    } else {  // queue full: slow path straight to global (correct for arbitrarily dense inputs)
+        const unsigned long long pos = atomicAdd(p.raw_cursor, 1ull);
+        if (pos < p.raw_cap) { raw_rec_t r; r.wcol = wcol; r.tag = node_tag; r.mrca = mrca; r.b0 = b0; r.b1 = b1; p.raw[pos] = r; }
     }
 }
 
-// consumers only: move the block's queued events to the global list (one global atomic)
-__device__ __noinline__ void drain_queue(raw_event_t* s_queue, unsigned int* s_count, unsigned long long* s_base, int tid,
-                                         unsigned int threshold, raw_event_t* raw, unsigned long long* raw_cursor, unsigned long long raw_cap) {
-    consumer_bar_sync();
-    const unsigned int n = min(*s_count, (unsigned int)PB_K1_QCAP);
+// consumers only: move the block's queued records to the global list (one global atomic)
+template <int QCAP, int CONSUMERS>
+__device__ __noinline__ void drain_queue(const uint4* s_queue, unsigned int* s_count, unsigned long long* s_base, int tid,
+                                         unsigned int threshold, raw_rec_t* raw, unsigned long long* raw_cursor, unsigned long long raw_cap) {
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
+    const unsigned int n = min(*s_count, (unsigned int)QCAP);
     if (n >= threshold && n > 0) {   // block-uniform
         if (tid == 0) *s_base = atomicAdd(raw_cursor, (unsigned long long)n);
-        consumer_bar_sync();
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
         const unsigned long long base = *s_base;
-        for (unsigned int i = tid; i < n; i += PB_K1_CONSUMERS) {
-            const unsigned long long pos = base + i;
-            if (pos < raw_cap) raw[pos] = s_queue[i];
+        uint4* out = reinterpret_cast<uint4*>(raw);
+        for (unsigned int i = tid; i < 2 * n; i += CONSUMERS) {       // 16-byte halves: coalesced
+            const unsigned long long pos = base + (i >> 1);
+            if (pos < raw_cap) out[2 * base + i] = s_queue[i];
         }
-        consumer_bar_sync();
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
         if (tid == 0) *s_count = 0;
-        consumer_bar_sync();
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
     }
 }
 
@@ -128,7 +130,7 @@ __device__ __noinline__ void drain_queue(raw_event_t* s_queue, unsigned int* s_c
 #define K1_STAGE_BYTES (2 * PB_K1_RPS * K1_ROW_BYTES)
 #define K1_SMEM_RING (PB_K1_STAGES * K1_STAGE_BYTES)
 #define K1_SMEM_HI ((PB_K1_KHI + 1) * 4 * PB_K1_COLS * 8)   // high slices + the pending carries into slice 8
-#define K1_SMEM_QUEUE (PB_K1_QCAP * 8)
+#define K1_SMEM_QUEUE (PB_K1_QCAP * 32)
 #define K1_SMEM_BARS (2 * PB_K1_STAGES * 8)
 #define K1_SMEM_TOTAL (K1_SMEM_RING + K1_SMEM_HI + K1_SMEM_QUEUE + K1_SMEM_BARS)
 
@@ -144,7 +146,7 @@ __device__ __forceinline__ void k1_row(uint32_t op, lane_t cv, lane_t c0, lane_t
                                        uint32_t count_addr, const K1Params& p) {
     if (op & PB_OP_TEST) {
         const lane_t mrca = cv & (~pv | (c0 ^ p0) | (c1 ^ p1));
-        if (mrca) emit_events(mrca, c0, c1, site_base, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
+        if (mrca) emit_events<PB_K1_QCAP>(mrca, c0, c1, site_base, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
     }
     if (op & PB_OP_SETCUR) { pv = cv; p0 = c0; p1 = c1; }
     if (op & PB_OP_LEAF) {
@@ -188,7 +190,7 @@ __device__ __forceinline__ void k1_row(uint32_t op, lane_t cv, lane_t c0, lane_t
 __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_kernel(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     lane_t* s_hi = reinterpret_cast<lane_t*>(smem + K1_SMEM_RING);                        // [slice][base][consumer]
-    raw_event_t* s_queue = reinterpret_cast<raw_event_t*>(smem + K1_SMEM_RING + K1_SMEM_HI);
+    const uint4* s_queue = reinterpret_cast<const uint4*>(smem + K1_SMEM_RING + K1_SMEM_HI);
     __shared__ unsigned int s_count;
     __shared__ unsigned long long s_base;
 
@@ -299,9 +301,9 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
             }
         }
         if ((((i - r0) / PB_K1_RPS) & (PB_K1_DRAIN_EVERY / PB_K1_RPS - 1)) == PB_K1_DRAIN_EVERY / PB_K1_RPS - 1)
-            drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
+            drain_queue<PB_K1_QCAP, PB_K1_CONSUMERS>(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
     }
-    drain_queue(s_queue, &s_count, &s_base, tid, 1, p.raw, p.raw_cursor, p.raw_cap);
+    drain_queue<PB_K1_QCAP, PB_K1_CONSUMERS>(s_queue, &s_count, &s_base, tid, 1, p.raw, p.raw_cursor, p.raw_cap);
 }
 
 // =================================================================================================
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
 #define PB_KX_BLOCKS_PER_SM 5
 #endif
 #ifndef PB_KX_DRAIN_EVERY
-#define PB_KX_DRAIN_EVERY (PB_K1_DRAIN_EVERY / PB_KX_WPT)   // a block sees PB_KX_WPT times the events per row
+#define PB_KX_DRAIN_EVERY PB_K1_DRAIN_EVERY
 #endif
 #define PB_KX_COLS (PB_K1_COLS * PB_KX_WPT)
 #define KX_ROW_BYTES (PB_KX_COLS * 8)
@@ -332,14 +334,16 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
 #define KX_SMEM_RING (PB_KX_STAGES * KX_STAGE_BYTES)
 #define KX_SMEM_BARS (2 * PB_KX_STAGES * 8)
 #define KX_SMEM_HI ((PB_K1_KHI + 1) * PB_KX_COLS * 8)          // high census slices + the pending carries into slice 8
-#define KX_SMEM_TOTAL (KX_SMEM_RING + KX_SMEM_HI + K1_SMEM_QUEUE + KX_SMEM_BARS)
+#define PB_KX_QCAP (PB_K1_QCAP * PB_KX_WPT + 128)              // raw-record queue: a block sees PB_KX_WPT times the events per row
+#define KX_SMEM_QUEUE (PB_KX_QCAP * 32)
+#define KX_SMEM_TOTAL (KX_SMEM_RING + KX_SMEM_HI + KX_SMEM_QUEUE + KX_SMEM_BARS)
 
 struct KXParams {
     int64_t W;
     const uint32_t* __restrict__ ops;
     const int32_t* __restrict__ chunk_op;
     uint64_t* __restrict__ census;         // [flush][KS][W]: leaves carrying the second base
-    raw_event_t* __restrict__ raw;
+    raw_rec_t* __restrict__ raw;
     unsigned long long* raw_cursor;
     unsigned long long raw_cap;
 };
@@ -373,7 +377,7 @@ __device__ __forceinline__ void k1x_row(uint32_t op, const XRow& x, XRow& px, Ce
 #pragma unroll
         for (int j = 0; j < PB_KX_WPT; j++) {
             const uint64_t mrca = x.w[j] ^ px.w[j];
-            if (mrca) emit_events(mrca, x.w[j], 0, site_base + 64u * j, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
+            if (mrca) emit_events<PB_KX_QCAP>(mrca, x.w[j], 0, site_base + 64u * j, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
         }
     }
     if (op & PB_OP_SETCUR) px = x;
@@ -415,7 +419,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
     __shared__ unsigned int s_count;
     __shared__ unsigned long long s_base;
     uint64_t* s_hi = reinterpret_cast<uint64_t*>(smem + KX_SMEM_RING);                     // [slice][word column of the block]
-    raw_event_t* s_queue = reinterpret_cast<raw_event_t*>(smem + KX_SMEM_RING + KX_SMEM_HI);
+    const uint4* s_queue = reinterpret_cast<const uint4*>(smem + KX_SMEM_RING + KX_SMEM_HI);
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y;
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
     const int r0 = q.chunk_op[chunk], r1 = q.chunk_op[chunk + 1];
     const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(q.ops);
     const uint32_t ring0 = pin_u32(smem_u32(smem));
-    const uint32_t full0 = pin_u32(ring0 + KX_SMEM_RING + KX_SMEM_HI + K1_SMEM_QUEUE), empty0 = full0 + 8 * PB_KX_STAGES;
+    const uint32_t full0 = pin_u32(ring0 + KX_SMEM_RING + KX_SMEM_HI + KX_SMEM_QUEUE), empty0 = full0 + 8 * PB_KX_STAGES;
 
     if (tid == 0) {
         s_count = 0;
@@ -512,9 +516,9 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
             }
         }
         if ((((i - r0) / PB_K1_RPS) & (PB_KX_DRAIN_EVERY / PB_K1_RPS - 1)) == PB_KX_DRAIN_EVERY / PB_K1_RPS - 1)
-            drain_queue(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, q.raw, q.raw_cursor, q.raw_cap);
+            drain_queue<PB_KX_QCAP, PB_K1_COLS>(s_queue, &s_count, &s_base, tid, PB_KX_QCAP / 2, q.raw, q.raw_cursor, q.raw_cap);
     }
-    drain_queue(s_queue, &s_count, &s_base, tid, 1, q.raw, q.raw_cursor, q.raw_cap);
+    drain_queue<PB_KX_QCAP, PB_K1_COLS>(s_queue, &s_count, &s_base, tid, 1, q.raw, q.raw_cursor, q.raw_cap);
 }
 
 int pbk_kx_cols() { return PB_KX_COLS; }
@@ -522,31 +526,50 @@ int pbk_kx_blocks_per_sm() { return PB_KX_BLOCKS_PER_SM; }
 
 // ---- per-site event counters -------------------------------------------------------------------
 // the raw list's length lives on the device (K1's cursor, clamped to the buffer): no host round trip before the tail
-// one-plane mode: an event's base field holds the child's X bit; the 2-bit code is the site's first base, XOR (first ^ second) if X
-__device__ __forceinline__ uint32_t event_base(uint32_t hi, uint32_t site, const uint64_t* __restrict__ xmask) {
-    const uint32_t f = (hi >> 29) & 3u;
+// The tail kernels peel the records: one thread per record, one iteration per set bit (usually one).
+// one-plane mode (xmask != nullptr): b0 holds the child's X bits; the 2-bit code is the site's first base, XOR (first ^ second) if X
+__device__ __forceinline__ uint32_t event_base(const raw_rec_t& r, int b, const uint64_t* __restrict__ xmask) {
+    const uint32_t f = (uint32_t)((r.b0 >> b) & 1ull) | ((uint32_t)((r.b1 >> b) & 1ull) << 1);
     if (!xmask) return f;
-    const uint64_t* m = xmask + 4 * (int64_t)(site >> 6);
-    const int b = (int)(site & 63);
+    const uint64_t* m = xmask + 4 * (int64_t)r.wcol;
     const uint32_t a = (uint32_t)((m[0] >> b) & 1ull) | ((uint32_t)((m[1] >> b) & 1ull) << 1);
     const uint32_t d = (uint32_t)((m[2] >> b) & 1ull) | ((uint32_t)((m[3] >> b) & 1ull) << 1);
     return a ^ (f ? d : 0u);
 }
 
-__global__ void k1_count_events_kernel(const raw_event_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
-                                       const int32_t* __restrict__ node_sample, const uint64_t* __restrict__ xmask, uint32_t* __restrict__ cnt) {
+// ---- per-site event counters -------------------------------------------------------------------
+// the record list's length lives on the device (the sweep's cursor, clamped to the buffer): no host round trip before the tail
+__global__ void k1_count_events_kernel(const raw_rec_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
+                                       const int32_t* __restrict__ node_sample, const uint64_t* __restrict__ xmask, uint32_t* __restrict__ cnt,
+                                       unsigned long long* __restrict__ n_events) {
     const int64_t n = min((int64_t)*cursor, raw_cap);
+    unsigned int nev = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const raw_event_t e = raw[i];
-    const uint32_t site = (uint32_t)e, hi = (uint32_t)(e >> 32);
-    const uint32_t base = event_base(hi, site, xmask), node = hi & PB_EV_NODE_MASK;
-    uint32_t* c = cnt + (int64_t)site * PB_CNT_STRIDE;
-    atomicAdd(c + base, 1u);
-    if (hi & 0x80000000u) {
-        atomicAdd(c + 4 + base, 1u);
-        if (node_sample[node] >= 0) atomicAdd(c + 8 + base, 1u);
+        const raw_rec_t r = raw[i];
+        const bool leaf = r.tag & 0x80000000u;
+        const bool sampled = leaf && node_sample[r.tag & PB_EV_NODE_MASK] >= 0;
+        uint64_t m = r.mrca;
+        nev += (unsigned int)__popcll(m);
+        while (m) {
+            const int b = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const uint32_t base = event_base(r, b, xmask);
+            uint32_t* c = cnt + ((int64_t)r.wcol * 64 + b) * PB_CNT_STRIDE;
+            atomicAdd(c + base, 1u);
+            if (leaf) {
+                atomicAdd(c + 4 + base, 1u);
+                if (sampled) atomicAdd(c + 8 + base, 1u);
+            }
+        }
     }
-    }
+    // one global atomic per block (all blocks hit the same word)
+    __shared__ unsigned int s_nev;
+    if (threadIdx.x == 0) s_nev = 0;
+    __syncthreads();
+    nev = __reduce_add_sync(0xffffffffu, nev);
+    if ((threadIdx.x & 31) == 0 && nev) atomicAdd(&s_nev, nev);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_nev) atomicAdd(n_events, (unsigned long long)s_nev);
 }
 
 // ---- census reduction: sum the bit-sliced partials of all flushes -----------------------------------
@@ -775,30 +798,36 @@ __global__ void k1_scatter_sites_kernel(int64_t S, const uint8_t* __restrict__ f
     }
 }
 
-__global__ void k1_scatter_events_kernel(const raw_event_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
+__global__ void k1_scatter_events_kernel(const raw_rec_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
                                          const int32_t* __restrict__ node_sample, const uint8_t* __restrict__ flags,
                                          const uint64_t* __restrict__ scan, const uint64_t* __restrict__ scan_in,
                                          const pb_site_out* __restrict__ sites, const AlleleMeta* __restrict__ alleles,
-                                         const uint64_t* __restrict__ xmask, uint32_t* __restrict__ csr_cursor, int32_t* __restrict__ csr) {
+                                         const uint64_t* __restrict__ xmask, uint32_t* __restrict__ csr_cursor, int32_t* __restrict__ csr,
+                                         int64_t csr_cap) {
     const int64_t n = min((int64_t)*cursor, raw_cap);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const raw_event_t e = raw[i];
-        const uint32_t hi = (uint32_t)(e >> 32);
-        if (!(hi & 0x80000000u)) continue;               // extant (leaf) events only (EXTANT_NODES_ONLY, HC.java:173)
-        const int32_t smp = node_sample[hi & PB_EV_NODE_MASK];
+        const raw_rec_t r = raw[i];
+        if (!(r.tag & 0x80000000u)) continue;            // extant (leaf) events only (EXTANT_NODES_ONLY, HC.java:173)
+        const int32_t smp = node_sample[r.tag & PB_EV_NODE_MASK];
         if (smp < 0) continue;                            // leaf without a pheno row: never tallied (HC.java:3743)
-        const uint32_t site = (uint32_t)e;
-        if (!(scan_in[site] >> 38)) continue;
-        const uint8_t fl = flags[site];
-        const uint32_t base = event_base(hi, site, xmask);
-        const int a = (base == ((fl >> PB_SF_A1_CODE_SHIFT) & 3u)) ? 0 : 1;
-        if (!(fl & (a == 0 ? PB_SF_A1_USE : PB_SF_A2_USE))) continue;
-        // bucket emptied by the <2 rule?  (in_use with min_hcount 0 keeps n = 0)
-        const pb_site_out so = sites[site];
-        if ((a == 0 ? so.a1_count : so.a2_count) < 2) continue;
-        const int64_t slot = 2 * (int64_t)(scan[site] >> 38) + a;
-        const uint32_t k = atomicAdd(csr_cursor + slot, 1u);
-        csr[alleles[slot].off + k] = smp;
+        uint64_t m = r.mrca;
+        while (m) {
+            const int b = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const uint32_t site = r.wcol * 64u + (uint32_t)b;
+            if (!(scan_in[site] >> 38)) continue;
+            const uint8_t fl = flags[site];
+            const uint32_t base = event_base(r, b, xmask);
+            const int a = (base == ((fl >> PB_SF_A1_CODE_SHIFT) & 3u)) ? 0 : 1;
+            if (!(fl & (a == 0 ? PB_SF_A1_USE : PB_SF_A2_USE))) continue;
+            // bucket emptied by the <2 rule?  (in_use with min_hcount 0 keeps n = 0)
+            const pb_site_out so = sites[site];
+            if ((a == 0 ? so.a1_count : so.a2_count) < 2) continue;
+            const int64_t slot = 2 * (int64_t)(scan[site] >> 38) + a;
+            const uint32_t k = atomicAdd(csr_cursor + slot, 1u);
+            const int64_t o = alleles[slot].off + k;
+            if (o < csr_cap) csr[o] = smp;               // (E beyond the buffer: pb_run_events grows it and repeats the pass)
+        }
     }
 }
 
@@ -952,10 +981,10 @@ int pbk_prepare_tail(pb_ctx* ctx) {
         PB_CUDA(cudaMalloc(&ctx->d_r, (size_t)S * 2 * 4));
         ctx->inf_cap = S;
     }
-    if (ctx->raw_cap > ctx->csr_cap) {
+    if (std::max(ctx->raw_cap, ctx->csr_want) > ctx->csr_cap) {
         cudaFree(ctx->d_csr); ctx->d_csr = nullptr;
-        PB_CUDA(cudaMalloc(&ctx->d_csr, (size_t)ctx->raw_cap * 4));
-        ctx->csr_cap = ctx->raw_cap;
+        ctx->csr_cap = std::max(ctx->raw_cap, ctx->csr_want);
+        PB_CUDA(cudaMalloc(&ctx->d_csr, (size_t)ctx->csr_cap * 4));
     }
     PB_CUDA(cudaMemsetAsync(ctx->d_cnt, 0, (size_t)S * PB_CNT_STRIDE * 4, ctx->stream2));
     PB_CUDA(cudaMemsetAsync(ctx->d_csr_cursor, 0, (size_t)S * 2 * 4, ctx->stream2));
@@ -973,7 +1002,8 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     pb_trace_mark(ctx, "headstart+memsets");
     const bool xmode = ctx->plane_mode == PB_PLANES_X;
     const uint64_t* xmask = xmode ? ctx->d_xmask : nullptr;
-    k1_count_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, xmask, ctx->d_cnt);
+    k1_count_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, xmask, ctx->d_cnt,
+                                                    ctx->d_class_counts + 9);
     pb_trace_mark(ctx, "count_events");
     k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), xmode ? 1 : 4), 128, 0, st>>>(ctx->d_census, xmode ? ctx->n_flush_x : ctx->n_flush,
                                                                                                  ctx->W, ctx->d_census_total);
@@ -1001,7 +1031,7 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
                                                                       ctx->d_inf_site, ctx->d_alleles, ctx->d_class_counts);
     pb_trace_mark(ctx, "scatter_sites");
     k1_scatter_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
-                                                     scan_out, scan_in, ctx->d_sites, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr);
+                                                     scan_out, scan_in, ctx->d_sites, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr, ctx->csr_cap);
     pb_trace_mark(ctx, "scatter_events");
     ctx->tm.n_launches += 2;
     PB_CUDA(cudaGetLastError());
@@ -1012,13 +1042,14 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     PB_CUDA(cudaGetLastError());
     pb_trace_dump(ctx, "events");
     *cursor_out = h[8];
+    ctx->n_raw = (int64_t)h[9];                       // events = set bits over all records (exact only when nothing overflowed)
     ctx->S_inf = (int64_t)(h[7] >> 38);
     ctx->E = (int64_t)(h[7] & ((1ull << 38) - 1));
     ctx->n_max = (int32_t)h[5];
     ctx->A_inuse = (int64_t)h[6];
     if (counts) {
         counts->n_no_allele = (int64_t)h[0]; counts->n_mono = (int64_t)h[1]; counts->n_bi = (int64_t)h[2];
-        counts->n_tri = (int64_t)h[3]; counts->n_quad = (int64_t)h[4]; counts->n_raw_events = (int64_t)h[8];
+        counts->n_tri = (int64_t)h[3]; counts->n_quad = (int64_t)h[4]; counts->n_raw_events = (int64_t)h[9];
     }
     return PB_OK;
 }

@@ -423,7 +423,7 @@ extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
     PB_CUDA(cudaMalloc(&ctx->d_site_flags, (size_t)n_sites));
     PB_CUDA(cudaMalloc(&ctx->d_site_scan, (size_t)n_sites * 2 * 8));
     ctx->raw_cap = std::max<int64_t>(4 * n_sites, 1 << 20);
-    PB_CUDA(cudaMalloc(&ctx->d_raw, (size_t)ctx->raw_cap * sizeof(raw_event_t)));
+    PB_CUDA(cudaMalloc(&ctx->d_raw, (size_t)ctx->raw_cap * sizeof(raw_rec_t)));
     return build_chunks(ctx);
 }
 
@@ -507,12 +507,16 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
         if (attempt == 0 && (rc = pbk_pregen_labels(ctx))) return rc;
         unsigned long long cur = 0;
         if ((rc = pbk_finalize_events(ctx, counts, &cur))) return rc;   // the whole tail, one host round trip at its end
-        if ((int64_t)cur <= ctx->raw_cap) { ctx->n_raw = (int64_t)cur; break; }
-        // event list larger than the buffer (dense / adversarial input): grow to the exact need and redo the pass
-        cudaFree(ctx->d_raw); ctx->d_raw = nullptr;
-        ctx->raw_cap = (int64_t)cur + (int64_t)cur / 16 + 1024;
-        cudaError_t e = cudaMalloc(&ctx->d_raw, (size_t)ctx->raw_cap * sizeof(raw_event_t));
-        if (e != cudaSuccess) { ctx->err = "pb_run_events: cannot allocate the event list"; ctx->raw_cap = 0; return PB_ERR_OOM; }
+        if ((int64_t)cur <= ctx->raw_cap && ctx->E <= ctx->csr_cap) { ctx->n_rec = (int64_t)cur; break; }
+        // record list (or the CSR of extant events: a record can hold up to 64) larger than its buffer — dense / adversarial
+        // input: grow to the exact need and redo the pass
+        if ((int64_t)cur > ctx->raw_cap) {
+            cudaFree(ctx->d_raw); ctx->d_raw = nullptr;
+            ctx->raw_cap = (int64_t)cur + (int64_t)cur / 16 + 1024;
+            cudaError_t e = cudaMalloc(&ctx->d_raw, (size_t)ctx->raw_cap * sizeof(raw_rec_t));
+            if (e != cudaSuccess) { ctx->err = "pb_run_events: cannot allocate the event list"; ctx->raw_cap = 0; return PB_ERR_OOM; }
+        }
+        if (ctx->E > ctx->csr_cap) ctx->csr_want = ctx->E + ctx->E / 16 + 1024;
         if (attempt == 2) FAIL(ctx, PB_ERR_CUDA, "pb_run_events: event list kept overflowing");
     }
     PB_CUDA(cudaEventRecord(ctx->ev[13], ctx->stream));
@@ -576,9 +580,16 @@ extern "C" int pb_get_raw_events(pb_ctx* ctx, int64_t cap, int32_t* site, int32_
     if (n) *n = ctx->n_raw;
     if (!site || !node) return PB_OK;
     if (cap < ctx->n_raw) FAIL(ctx, PB_ERR_INVALID, "pb_get_raw_events: buffer too small");
-    std::vector<raw_event_t> h((size_t)ctx->n_raw);
-    if (ctx->n_raw) PB_CUDA(cudaMemcpy(h.data(), ctx->d_raw, (size_t)ctx->n_raw * 8, cudaMemcpyDeviceToHost));
-    for (int64_t i = 0; i < ctx->n_raw; i++) { site[i] = (int32_t)(uint32_t)h[i]; node[i] = (int32_t)((uint32_t)(h[i] >> 32) & PB_EV_NODE_MASK); }
+    std::vector<raw_rec_t> h((size_t)ctx->n_rec);
+    if (ctx->n_rec) PB_CUDA(cudaMemcpy(h.data(), ctx->d_raw, (size_t)ctx->n_rec * sizeof(raw_rec_t), cudaMemcpyDeviceToHost));
+    int64_t k = 0;
+    for (const raw_rec_t& r : h)
+        for (uint64_t m = r.mrca; m; m &= m - 1) {
+            if (k >= cap) FAIL(ctx, PB_ERR_INVALID, "pb_get_raw_events: buffer too small");
+            site[k] = (int32_t)(r.wcol * 64u + (uint32_t)__builtin_ctzll(m));
+            node[k] = (int32_t)(r.tag & PB_EV_NODE_MASK);
+            k++;
+        }
     return PB_OK;
 }
 

@@ -27,8 +27,14 @@
 
 enum { PB_PLANES_NONE = 0, PB_PLANES_X = 1, PB_PLANES_FULL = 2 };
 
-// raw MRCA event: lo = site (context-local), hi = node | base<<29 | is_leaf<<31
-typedef unsigned long long raw_event_t;
+// raw MRCA record: ALL events of one (tree row, 64-site word): the sweep kernels store the masks as they are and the
+// tail kernels peel the bits (a per-event record cost the sweep ~36 warp-instructions per event, at one active lane)
+struct __align__(16) raw_rec_t {
+    uint32_t wcol;        // site word (context-local): sites 64*wcol ..
+    uint32_t tag;         // node | is_leaf << 31
+    uint64_t mrca;        // sites of the word where this node is an MRCA
+    uint64_t b0, b1;      // the node's base-code planes of the word (one-plane mode: b0 = X, b1 = 0)
+};
 #define PB_EV_NODE_MASK 0x1FFFFFFFu
 
 // per-site event counters filled by k1_count_events: [0..3] all MRCAs by own base code,
@@ -60,9 +66,9 @@ typedef unsigned long long raw_event_t;
 #define PB_K1_RPS 2         // 16-byte records (row pairs) per ring stage: one full/empty handshake per 2*RPS rows
 #endif
 #define PB_K1_STAGES (4 / PB_K1_RPS)   // ring = 8 rows (24 KB per 128 columns): 3 KB TMA boxes, 2*RPS of them per stage
-#define PB_K1_QCAP (6 * PB_K1_COLS)   // per-block event queue (6 KB per 128 columns)
+#define PB_K1_QCAP 192   // per-block queue of raw records (6 KB)
 #ifndef PB_K1_DRAIN_EVERY
-#define PB_K1_DRAIN_EVERY 128 // records between queue-drain checks (a consumer-wide barrier each)
+#define PB_K1_DRAIN_EVERY 16  // op records (2 rows each) between queue-drain checks (a consumer-wide barrier each)
 #endif
 
 // allele flags
@@ -130,8 +136,8 @@ struct pb_ctx {
     // K1 outputs
     uint64_t* d_census = nullptr;      // [n_flush][4][KS][W]
     uint64_t* d_census_total = nullptr;  // [4][KT][W]
-    raw_event_t* d_raw = nullptr;
-    int64_t raw_cap = 0;
+    raw_rec_t* d_raw = nullptr;
+    int64_t raw_cap = 0, n_rec = 0;   // capacity / length of the record list (n_raw = events = set bits over all records)
     unsigned long long* d_raw_cursor = nullptr;
     int64_t n_raw = 0;
     uint32_t* d_cnt = nullptr;         // [S][PB_CNT_STRIDE]
@@ -148,7 +154,7 @@ struct pb_ctx {
     AlleleMeta* d_alleles = nullptr;   // [2*S_inf]
     int32_t* d_csr = nullptr;          // [E]
     uint32_t* d_csr_cursor = nullptr;  // [2*S_inf]
-    int64_t inf_cap = 0, csr_cap = 0;
+    int64_t inf_cap = 0, csr_cap = 0, csr_want = 0;   // csr_want: E overflowed the CSR buffer, grow to this on the next pass
 
     // assoc
     double p_success = 0;
