@@ -54,9 +54,12 @@ __global__ void k2_tally_kernel(AlleleMeta* __restrict__ alleles, int64_t n_slot
 // ---------------------------------------------------------------------------------------------------
 // K3a: label bit-matrix
 // ---------------------------------------------------------------------------------------------------
+#ifndef PB_PHILOX_ROUNDS
+#define PB_PHILOX_ROUNDS 10   // experiment knob only (7 rounds: generator 0.52 -> 0.43 ms at C2, not adopted; the oracle restates 10)
+#endif
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < PB_PHILOX_ROUNDS; r++) {
         const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
         const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
         const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
