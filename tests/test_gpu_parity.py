@@ -321,6 +321,39 @@ def test_events_dense_overflowing_queue(oracle_mod):
     assert cc["raw_events"] > 4 * S
 
 
+def test_events_dense_regrow_record_list_and_csr(oracle_mod):
+    """more than 2^20 raw records (every node differs from its parent in half of the sites of every word) and more extant
+    events than the CSR buffer was sized for: pb_run_events grows both and repeats the pass; one-plane and three-plane mode"""
+    tree = synth.yule_tree(600, 22)
+    S = 64 * 900
+    rng = np.random.default_rng(4)
+    N = tree.n_nodes
+    chars = np.frombuffer(b"GT", dtype=np.uint8)[rng.integers(0, 2, size=(N, S), dtype=np.uint8)]
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(chars, n_threads=8)
+    sn, lab = synth.simulate_phenotypes(tree, 5)
+    B0, B1, V = pb.pack_chars(chars)
+    out = []
+    for full in (False, True):
+        hc = pb.HomoplasyCounter(num_replicates=4, seed=1, full_planes=full)
+        hc.set_tree(tree.parent, tree.is_leaf)
+        hc.set_phenos(sn, lab)
+        hc.set_planes(B0, B1, V, S, compact=True)
+        ev, cc = hc.count_all_homoplasy_events()
+        assert hc.timings()["plane_mode"] == (2 if full else 1)
+        assert_events_equal(ev, cc, or_ev, or_cc)
+        assert cc["raw_events"] > 30_000_000
+        tm = hc.timings()
+        assert tm["n_extant_events"] > (1 << 20)                       # beyond the initial CSR capacity
+        off, idx = hc.event_csr()
+        assert off[-1] == tm["n_extant_events"] and idx.min() >= 0 and idx.max() < len(lab)
+        st, _ = hc.assoc()
+        np.testing.assert_array_equal(st["obs_counts"].sum(axis=1), ev["a1_extant"] + ev["a2_extant"])   # all leaves have a 0/1 label
+        out.append((ev.tobytes(), st["obs_counts"].tobytes(), st["r_a1"].tobytes(), st["r_a2"].tobytes()))
+        hc.close()
+    assert out[0] == out[1]
+
+
 # -------------------------------------------------------------------------------------------------
 # K2/K3/K4: association
 # -------------------------------------------------------------------------------------------------
