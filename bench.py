@@ -179,6 +179,7 @@ def run_b200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

@@ -9,15 +9,15 @@
 // plus the root itself; v goes to bucket a1 iff geno(v) == allele1, else a2; a bucket with
 // fewer than 2 members is emptied.  The test is edge-local, so K1 streams every plane row ONCE:
 //   * a block owns 128 word columns (8,192 sites) and one chunk of the host-built DFS edge program;
-//   * a producer warp (one elected lane) moves each row segment (3 planes x 1 KB) into an 8-stage
-//     shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx); the four
+//   * a producer warp (one elected lane) moves each row segment (3 planes x 1 KB, one 3-D TMA box) into a shared-memory
+//     ring of 8 rows (2 stages of four boxes, cp.async.bulk.tensor + mbarrier complete_tx); the four
 //     consumer warps wait on the stage's full barrier, pull their 64-bit words into registers and
 //     release the stage at once (empty barrier) — memory-level parallelism comes from the ring,
 //     not from registers;
 //   * the DFS order keeps the parent row in registers: MRCA mask of an edge =
 //     Vc & (~Vp | (B0c^B0p) | (B1c^B1p)) (3 LOP3 per 32-bit half);
-//   * events are sparse (~2.5 per site per tree): set bits are peeled with ffs into a per-block
-//     shared queue, drained with one global atomic per drain;
+//   * events are sparse (~2.5 per site per tree): a (row, word) that holds any goes, masks as they are, into a
+//     per-block shared queue of 32-byte records drained with one global atomic per drain; the tail kernels peel the bits;
 //   * the leaf census (how many leaves carry A/C/G/T per site) is dense: bit-sliced vertical counters,
 //     Harley-Seal carry-save levels 1/2/4 in registers, slices 8.. in shared memory.
 #include <stdio.h>
@@ -37,13 +37,9 @@ struct K1Params {
     unsigned long long raw_cap;
 };
 
-#if PB_K1_LANE_BITS == 64
+static_assert(PB_K1_LANE_BITS == 64, "a consumer thread owns one whole 64-site word column (raw records hold whole words); "
+                                     "32-bit lanes were measured slower in round 1 and are no longer supported");
 typedef uint64_t lane_t;
-__device__ __forceinline__ int lane_ffs(lane_t x) { return __ffsll((long long)x); }
-#else
-typedef uint32_t lane_t;
-__device__ __forceinline__ int lane_ffs(lane_t x) { return __ffs((int)x); }
-#endif
 
 // ---- mbarrier / TMA primitives (inline PTX; barrier and ring addresses are 32-bit shared-window offsets) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,7 +79,6 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t x) {
     asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
-__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PB_K1_CONSUMERS) : "memory"); }
 
 // Queue push: one shared-memory atomic and two 16-byte stores per (row, word) that holds any event; the bits are peeled by
 // the tail kernels (k1_count_events_kernel, k1_scatter_events_kernel).

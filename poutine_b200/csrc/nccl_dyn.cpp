@@ -13,7 +13,7 @@
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64 = 8 };
+enum { ncclUint64 = 5, ncclFloat64 = 8 };
 enum { ncclMin = 3 };
 
 struct NcclApi {
@@ -79,7 +79,9 @@ int pbn_allreduce_min_f64(pb_ctx* ctx, double* buf, int64_t n) {
     if (ctx->world <= 1) return PB_OK;
     NcclApi* a = nccl_api(ctx->err);
     if (!a || !ctx->nccl_comm) { ctx->err = "all-reduce requested but pb_comm_init was not called"; return PB_ERR_NCCL; }
-    ncclResult_t r = a->AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclMin, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    // p-values are non-negative doubles: their bit patterns order like unsigned integers (the kernels already atomicMin them that
+    // way), and an integer min is eligible for NCCL's in-switch (NVLS) reduction, which a double min is not
+    ncclResult_t r = a->AllReduce(buf, buf, (size_t)n, ncclUint64, ncclMin, (ncclComm_t)ctx->nccl_comm, ctx->stream);
     if (r != 0) { ctx->err = std::string("ncclAllReduce: ") + (a->GetErrorString ? a->GetErrorString(r) : "error"); return PB_ERR_NCCL; }
     return PB_OK;
 }

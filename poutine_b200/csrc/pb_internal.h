@@ -58,7 +58,7 @@ struct __align__(16) raw_rec_t {
 #endif
 #define PB_K1_BLOCKS_PER_SM (512 / PB_K1_COLS)
 #ifndef PB_K1_LANE_BITS
-#define PB_K1_LANE_BITS 64   // sites per consumer thread: 64 (one word column) or 32 (half a column: twice the warps, half the state)
+#define PB_K1_LANE_BITS 64   // sites per consumer thread: one word column (must be 64)
 #endif
 #define PB_K1_CONSUMERS (PB_K1_COLS * 64 / PB_K1_LANE_BITS)
 #define PB_K1_THREADS (PB_K1_CONSUMERS + 32)   // consumer warps + 1 TMA producer warp
