@@ -265,6 +265,32 @@ def test_one_plane_mode_partial_upload_and_reuse(oracle_mod):
     assert hc.timings()["plane_mode"] == 2
     assert (ev3.tobytes(), cc3) == out[1]
     hc.close()
+    # ... and a late COMPACT tile that carries a V plane (invalid calls, still at most two bases) promotes as well
+    V2 = V.copy()
+    V2[tree.leaf_nodes[::7], 14:W] &= np.uint64(0xF0F0F0F0F0F0F0F0)
+    res = []
+    for compact in (True, False):
+        hc = pb.HomoplasyCounter(num_replicates=16)
+        hc.set_tree(tree.parent, tree.is_leaf)
+        hc.set_sites(S)
+        if compact:
+            for w0 in (0, 7):
+                c = pb.compact_planes(B0[:, w0:w0 + 7], B1[:, w0:w0 + 7], V2[:, w0:w0 + 7], 64 * 7)
+                assert c[2]
+                hc.put_planes_biallelic(c[0], None, c[1], w0)
+            c = pb.compact_planes(B0[:, 14:W], B1[:, 14:W], V2[:, 14:W], S - 64 * 14)
+            assert c is not None and not c[2]
+            hc.put_planes_biallelic(c[0], V2[:, 14:W], c[1], 14)
+        else:
+            hc.put_planes(B0, B1, V2)
+        ev4, cc4 = hc.count_all_homoplasy_events()
+        assert hc.timings()["plane_mode"] == 2
+        res.append((ev4.tobytes(), cc4))
+        hc.close()
+    assert res[0] == res[1]
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(synth.planes_to_chars(B0, B1, V2, 0, S))
+    assert_events_equal(np.frombuffer(res[0][0], dtype=ev3.dtype), res[0][1], or_ev, or_cc)
 
 
 def test_events_many_chunks_and_site_offset(oracle_mod, monkeypatch):
