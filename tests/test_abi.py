@@ -98,3 +98,84 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
                 assert "liboracle" not in txt, f
                 assert not re.search(r'#include\s+"[^"]*oracle/', txt), f
+
+
+# ---- the C ABI from plain C -------------------------------------------------------------------------------
+def _build_host_min(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "host_min")
+    libdir = os.path.join(ROOT, "poutine_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "host_min.c"), "-o", exe, "-L" + libdir, "-lpoutine_b200",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def _host_min_inputs():
+    """the input examples/host_min.c builds, restated"""
+    parent = np.array([-1, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7], dtype=np.int32)
+    N, S = 17, 70
+    is_leaf = np.ones(N, dtype=np.uint8)
+    is_leaf[parent[parent >= 0]] = 0
+    chars = np.zeros((N, S), dtype=np.uint8)
+    for s in range(S):
+        a, b = (ord("C"), ord("T")) if s & 1 else (ord("A"), ord("G"))
+        chars[:, s] = a
+        for v in range(N):
+            if is_leaf[v] and ((v * 7 + s * 3) % 5 == 0 or (v + s) % 11 == 0):
+                chars[v, s] = b
+        if s % 9 == 4:
+            chars[[4, 10, 11], s] = b
+    chars[16, 5] = chars[16, 66] = ord("N")
+    sample_node = np.flatnonzero(is_leaf).astype(np.int32)
+    label = np.array([2 if v == 12 else (v & 1) for v in sample_node], dtype=np.uint8)
+    return parent, is_leaf, chars, sample_node, label
+
+
+def test_header_is_c99_and_plain_c_host_builds(lib, tmp_path):
+    """include/poutine_b200.h is valid C99 under -Wall -Wextra -Werror, a plain-C host links against the library, and
+    without a GPU it fails loudly at pb_create (no CPU fallback)."""
+    import subprocess
+    import torch
+    exe = _build_host_min(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run itself is covered by the gpu test below")
+    r = subprocess.run([exe, "50"], capture_output=True, text=True)
+    assert r.returncode == 1 and "pb_create failed" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_host_matches_python_mirror(lib, tmp_path):
+    """examples/host_min.c (C ABI, no Python in the process) prints the same events, statistics and extras as the ctypes
+    mirror computes for the same input."""
+    import subprocess
+    exe = _build_host_min(tmp_path)
+    m, seed = 500, 7
+    r = subprocess.run([exe, str(m), str(seed)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.splitlines()
+    parent, is_leaf, chars, sn, lab = _host_min_inputs()
+    hc = pb.HomoplasyCounter(num_replicates=m, seed=seed)
+    hc.set_tree(parent, is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_seg_sites(chars)
+    ev, cc = hc.count_all_homoplasy_events()
+    st, mt = hc.assoc()
+    ep, fp = hc.extras()
+    assert out[0] == "upload compact=1 all_valid=0"
+    assert out[1] == "classes mono=%d bi=%d tri=%d quad=%d none=%d raw_events=%d" % (cc["mono"], cc["bi"], cc["tri"], cc["quad"],
+                                                                                     cc["no_allele"], cc["raw_events"])
+    site_lines = [l for l in out if l.startswith("site ")]
+    assert site_lines == ["site %d %s %s %d %d %d %d" % (e["segsite_id"], chr(e["allele1"]), chr(e["allele2"]), e["a1_count"], e["a2_count"],
+                                                         e["a1_extant"], e["a2_extant"]) for e in ev]
+    stat_lines = [l for l in out if l.startswith("stat ")]
+    assert len(stat_lines) == len(st) and len(st) > 5
+    for l, t, e2, f in zip(stat_lines, st, ep, fp):
+        want = ("stat %d [%d, %d, %d, %d] r=%d,%d rmaxT=%d,%d obs_p=%.17g,%.17g pointwise=%.17g,%.17g exact=%.17g,%.17g fisher=%.17g"
+                % (t["segsite_id"], *t["obs_counts"], t["r_a1"], t["r_a2"], t["r_maxT_a1"], t["r_maxT_a2"], t["obs_p_a1"], t["obs_p_a2"],
+                   t["pointwise_a1"], t["pointwise_a2"], e2[0], e2[1], f))
+        assert l.replace("-nan", "nan") == want.replace("-nan", "nan"), (l, want)
+    assert out[-2] == "maxT[0]=%.17g maxT[m-1]=%.17g" % (mt[0], mt[-1])
+    assert out[-1].startswith("plane_mode=2 ")      # the 'N' calls need the V plane: three planes in HBM
+    hc.close()
