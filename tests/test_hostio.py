@@ -78,6 +78,44 @@ def test_compact_planes_roundtrip(n_sites, gaps):
     np.testing.assert_array_equal(c1[1], colmask)
 
 
+def test_compact_planes_property_random_alignments():
+    """random small alignments over a nasty alphabet: compaction succeeds exactly when no site has three distinct valid
+    bases over all nodes; X / colmask then reproduce the planes under V; all_valid exactly when every call is a base"""
+    rng = np.random.default_rng(42)
+    valid = np.frombuffer(b"ACGT", np.uint8)
+    n_ok = n_bad = 0
+    for trial in range(300):
+        N = int(rng.integers(1, 9))
+        S = int(rng.integers(1, 200))
+        k = int(rng.integers(1, 4))                                   # bases available per site: 1..3
+        junk = rng.random() < 0.5
+        chars = np.empty((N, S), dtype=np.uint8)
+        for s_ in range(S):
+            pool = rng.choice(valid, size=min(k, 1 + int(rng.integers(0, 3))), replace=False)
+            col = rng.choice(pool, size=N)
+            if junk:
+                bad = rng.random(N) < 0.2
+                col = np.where(bad, rng.choice(np.frombuffer(b"Nn-acgtRY", np.uint8), size=N), col)
+            chars[:, s_] = col
+        B0, B1, V = pb.pack_chars(chars)
+        isv = np.isin(chars, valid)
+        n_distinct = np.array([len(set(chars[isv[:, s_], s_].tolist())) for s_ in range(S)])
+        c = pb.compact_planes(B0, B1, V, S, n_threads=int(rng.integers(0, 3)))
+        if n_distinct.max(initial=0) >= 3:
+            assert c is None
+            n_bad += 1
+            continue
+        n_ok += 1
+        assert c is not None
+        X, colmask, all_valid = c
+        assert all_valid == bool(isv.all())
+        e0, e1 = _expand(X, colmask)
+        np.testing.assert_array_equal(e0 & V, B0 & V)
+        np.testing.assert_array_equal(e1 & V, B1 & V)
+        assert not np.any(X & ~V)
+    assert n_ok > 50 and n_bad > 50
+
+
 def test_compact_planes_rejects_third_base():
     t = synth.yule_tree(40, 2)
     n_sites = 64 * 5 + 9
