@@ -100,10 +100,10 @@ __device__ __forceinline__ void emit_events(lane_t mrca, lane_t b0, lane_t b1, u
     }
 }
 
-// consumers only: move the block's queued records to the global list (one global atomic)
-template <int QCAP, int CONSUMERS>
+// consumers only: move the block's queued records (U 16-byte units each) to the global list (one global atomic)
+template <int QCAP, int CONSUMERS, int U>
 __device__ __noinline__ void drain_queue(const uint4* s_queue, unsigned int* s_count, unsigned long long* s_base, int tid,
-                                         unsigned int threshold, raw_rec_t* raw, unsigned long long* raw_cursor, unsigned long long raw_cap) {
+                                         unsigned int threshold, void* raw, unsigned long long* raw_cursor, unsigned long long raw_cap) {
     asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
     const unsigned int n = min(*s_count, (unsigned int)QCAP);
     if (n >= threshold && n > 0) {   // block-uniform
@@ -111,9 +111,9 @@ __device__ __noinline__ void drain_queue(const uint4* s_queue, unsigned int* s_c
         asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
         const unsigned long long base = *s_base;
         uint4* out = reinterpret_cast<uint4*>(raw);
-        for (unsigned int i = tid; i < 2 * n; i += CONSUMERS) {       // 16-byte halves: coalesced
-            const unsigned long long pos = base + (i >> 1);
-            if (pos < raw_cap) out[2 * base + i] = s_queue[i];
+        for (unsigned int i = tid; i < U * n; i += CONSUMERS) {       // 16-byte units: coalesced
+            const unsigned long long pos = base + i / U;
+            if (pos < raw_cap) out[U * base + i] = s_queue[i];
         }
         asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
         if (tid == 0) *s_count = 0;
@@ -296,21 +296,27 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
             }
         }
         if ((((i - r0) / PB_K1_RPS) & (PB_K1_DRAIN_EVERY / PB_K1_RPS - 1)) == PB_K1_DRAIN_EVERY / PB_K1_RPS - 1)
-            drain_queue<PB_K1_QCAP, PB_K1_CONSUMERS>(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
+            drain_queue<PB_K1_QCAP, PB_K1_CONSUMERS, 2>(s_queue, &s_count, &s_base, tid, PB_K1_QCAP / 2, p.raw, p.raw_cursor, p.raw_cap);
     }
-    drain_queue<PB_K1_QCAP, PB_K1_CONSUMERS>(s_queue, &s_count, &s_base, tid, 1, p.raw, p.raw_cursor, p.raw_cap);
+    drain_queue<PB_K1_QCAP, PB_K1_CONSUMERS, 2>(s_queue, &s_count, &s_base, tid, 1, p.raw, p.raw_cursor, p.raw_cap);
 }
 
 // =================================================================================================
-// K1X — the same sweep over ONE plane.  When every site carries at most two bases and every genotype is valid
+// K1X — the sweep over ONE plane.  When every site carries at most two bases and every genotype is valid
 // (pb_put_planes_biallelic with V = NULL for every tile), a node's genotype is one bit: X = "carries the site's second
-// base".  The MRCA test of an edge is then X_child ^ X_parent, the leaf census one counter (how many leaves carry the
-// second base), and a tree row is a third of the bytes.  With so little work per word the per-row control flow (op
-// decode, ring handshake, census phases) dominates, so a consumer thread owns PB_KX_WPT adjacent word columns (one
-// 16-byte shared-memory load per row) and a block PB_KX_COLS = 128 * PB_KX_WPT columns; its own edge program
-// (pb_ctx::progx) is cut for that grid.  Same ring protocol (2*RPS TMA boxes per stage, PB_KX_STAGES stages), same
-// event queue; an event carries the child's X bit in its base field and the tail kernels rebuild the 2-bit base code
-// from the column's site masks (event_base).  Census: slices 1/2/4 in registers, 8.. in shared memory, as in k1_row.
+// base", a tree row is a third of the bytes and the MRCA test of an edge is X_child ^ X_parent.  With so little work per
+// word the per-row control flow (op decode, ring handshake) dominates, so
+//   * a consumer thread owns PB_KX_WPT adjacent word columns (one 16-byte shared-memory load per row) and a block
+//     PB_KX_COLS = 128 * PB_KX_WPT columns; its own lowering of the edge list (pb_ctx::d_ops_x) is cut for that grid;
+//   * there is NO leaf census in the sweep.  X(leaf) = X(root) + the sum of X(c) - X(p) over the edges of its root path, so
+//       #leaves carrying the second base = L * X(root) + sum over edges with X(c) != X(p) of (X(c) ? +1 : -1) * leaves_below(c):
+//     a sum over the sparse records the sweep emits anyway (k1_count_events_kernel adds it up, one atomic per event).  For that
+//     the edges hanging off the root are tested too; their records are marked NOMRCA (the reference never makes a child of the
+//     root an MRCA, HC.java:1674) and feed the census only.  The dense bit-sliced counter this replaces was a fifth of the
+//     sweep's instructions and 20 of its registers;
+//   * a record is 16 bytes {word column, node | X | flags, site mask} (xrec_t): one shared atomic + ONE 16-byte store; a word
+//     whose edge flips sites in both directions gives two records.
+// Same ring protocol as K1 (2*RPS TMA boxes per stage, PB_KX_STAGES stages, here 2-D boxes), same queue drain.
 #ifndef PB_KX_WPT
 #define PB_KX_WPT 2
 #endif
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
 #define PB_KX_STAGES (4 / PB_KX_WPT)
 #endif
 #ifndef PB_KX_BLOCKS_PER_SM
-#define PB_KX_BLOCKS_PER_SM 5
+#define PB_KX_BLOCKS_PER_SM 7
 #endif
 #ifndef PB_KX_DRAIN_EVERY
 #define PB_KX_DRAIN_EVERY PB_K1_DRAIN_EVERY
@@ -328,17 +334,14 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
 #define KX_STAGE_BYTES (2 * PB_K1_RPS * KX_ROW_BYTES)
 #define KX_SMEM_RING (PB_KX_STAGES * KX_STAGE_BYTES)
 #define KX_SMEM_BARS (2 * PB_KX_STAGES * 8)
-#define KX_SMEM_HI ((PB_K1_KHI + 1) * PB_KX_COLS * 8)          // high census slices + the pending carries into slice 8
-#define PB_KX_QCAP (PB_K1_QCAP * PB_KX_WPT + 128)              // raw-record queue: a block sees PB_KX_WPT times the events per row
-#define KX_SMEM_QUEUE (PB_KX_QCAP * 32)
-#define KX_SMEM_TOTAL (KX_SMEM_RING + KX_SMEM_HI + KX_SMEM_QUEUE + KX_SMEM_BARS)
+#define PB_KX_QCAP (PB_K1_QCAP * PB_KX_WPT + 128)              // record queue: a block sees PB_KX_WPT times the events per row
+#define KX_SMEM_QUEUE (PB_KX_QCAP * 16)
+#define KX_SMEM_TOTAL (KX_SMEM_RING + KX_SMEM_QUEUE + KX_SMEM_BARS)
 
 struct KXParams {
-    int64_t W;
     const uint32_t* __restrict__ ops;
     const int32_t* __restrict__ chunk_op;
-    uint64_t* __restrict__ census;         // [flush][KS][W]: leaves carrying the second base
-    raw_rec_t* __restrict__ raw;
+    xrec_t* __restrict__ raw;
     unsigned long long* raw_cursor;
     unsigned long long raw_cap;
 };
@@ -347,12 +350,6 @@ __device__ __forceinline__ void tma_load_row_2d(uint32_t dst, const CUtensorMap*
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(tmap), "r"(col0), "r"(node), "r"(bar) : "memory");
 }
-
-struct CensusX {
-    uint64_t s[3][PB_KX_WPT];       // slices 1, 2, 4 (slices 8.. and the pending carries into 8 live in shared memory: a fully
-    uint64_t pend2[PB_KX_WPT], pend4[PB_KX_WPT];   // register-resident counter makes the compiler shuffle the state at every flush check)
-    int nleaf;
-};
 
 struct XRow { uint64_t w[PB_KX_WPT]; };
 
@@ -366,55 +363,54 @@ __device__ __forceinline__ XRow lds_xrow(uint32_t addr) {
     return r;
 }
 
-__device__ __forceinline__ void k1x_row(uint32_t op, const XRow& x, XRow& px, CensusX& cs, uint64_t* s_hi, int tid,
-                                        uint32_t site_base, uint32_t queue_addr, uint32_t count_addr, const K1Params& p) {
+// queue full: slow path straight to global (correct for arbitrarily dense inputs); out of line, it is rare
+__device__ __noinline__ void emit_xrec_overflow(uint64_t mask, uint32_t wcol, uint32_t tag, xrec_t* raw, unsigned long long* raw_cursor,
+                                                unsigned long long raw_cap) {
+    const unsigned long long pos = atomicAdd(raw_cursor, 1ull);
+    if (pos < raw_cap) { xrec_t r; r.wcol = wcol; r.tag = tag; r.mask = mask; raw[pos] = r; }
+}
+
+// queue push of one xrec_t: one shared-memory atomic and one 16-byte store
+#ifdef PB_KX_EMIT_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void emit_xrec(uint64_t mask, uint32_t wcol, uint32_t tag, uint32_t queue_addr, uint32_t count_addr, const KXParams& q) {
+    uint32_t slot;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(count_addr) : "memory");
+    if (slot < PB_KX_QCAP) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(queue_addr + slot * 16), "r"(wcol), "r"(tag), "r"((uint32_t)mask),
+                     "r"((uint32_t)(mask >> 32)) : "memory");
+    } else {
+        emit_xrec_overflow(mask, wcol, tag, q.raw, q.raw_cursor, q.raw_cap);
+    }
+}
+
+// one tree row: X_child ^ X_parent against the current parent row, optional parent update
+__device__ __forceinline__ void k1x_row(uint32_t op, const XRow& x, XRow& px, uint32_t wcol0, uint32_t queue_addr, uint32_t count_addr,
+                                        const KXParams& q) {
     if (op & PB_OP_TEST) {
+        // xrec_t tag: node | NOMRCA (op bit 28 -> tag bit 30) | LEAF (bit 31 in both); bit 28 = the child's X
+        const uint32_t tag = (op & PB_OPX_NODE_MASK) | (op & PB_OP_LEAF) | ((op & PB_OPX_NOMRCA) << 2);
 #pragma unroll
         for (int j = 0; j < PB_KX_WPT; j++) {
-            const uint64_t mrca = x.w[j] ^ px.w[j];
-            if (mrca) emit_events<PB_KX_QCAP>(mrca, x.w[j], 0, site_base + 64u * j, (op & PB_OP_NODE_MASK) | (op & PB_OP_LEAF), queue_addr, count_addr, p);
-        }
-    }
-    if (op & PB_OP_SETCUR) px = x;
-    if (op & PB_OP_LEAF) {
-        // deferred-carry bit-sliced counter, as in k1_row, for the single quantity "leaves with X = 1"
-        const int ph = cs.nleaf & 7;                                 // block-uniform
-        cs.nleaf++;
-#pragma unroll
-        for (int j = 0; j < PB_KX_WPT; j++) { const uint64_t o = cs.s[0][j]; cs.s[0][j] = o ^ x.w[j]; cs.pend2[j] |= o & x.w[j]; }
-        if (ph & 1) {
-#pragma unroll
-            for (int j = 0; j < PB_KX_WPT; j++) { cs.pend4[j] |= cs.s[1][j] & cs.pend2[j]; cs.s[1][j] ^= cs.pend2[j]; cs.pend2[j] = 0; }
-            if (ph & 2) {
-                uint64_t* s_p8 = s_hi + PB_K1_KHI * PB_KX_COLS + tid * PB_KX_WPT;
-                if (!(ph & 4)) {
-#pragma unroll
-                    for (int j = 0; j < PB_KX_WPT; j++) { s_p8[j] = cs.s[2][j] & cs.pend4[j]; cs.s[2][j] ^= cs.pend4[j]; cs.pend4[j] = 0; }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < PB_KX_WPT; j++) {
-                        uint64_t carry = s_p8[j] | (cs.s[2][j] & cs.pend4[j]);
-                        cs.s[2][j] ^= cs.pend4[j]; cs.pend4[j] = 0;
-#pragma unroll
-                        for (int k = 0; k < PB_K1_KHI; k++) {
-                            uint64_t* hp = s_hi + k * PB_KX_COLS + tid * PB_KX_WPT + j;
-                            const uint64_t h = *hp;
-                            *hp = h ^ carry;
-                            carry &= h;
-                        }
-                    }
-                }
+            const uint64_t diff = x.w[j] ^ px.w[j];
+            if (diff) {
+                const uint64_t up = diff & x.w[j];                 // sites where the child gained the second base
+                if (up) emit_xrec(up, wcol0 + j, tag | PB_XT_XBIT, queue_addr, count_addr, q);
+                if (diff != up) emit_xrec(diff ^ up, wcol0 + j, tag, queue_addr, count_addr, q);
             }
         }
     }
+    if (op & PB_OP_SETCUR) px = x;
 }
 
 __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events_kernel(const __grid_constant__ CUtensorMap tmap, const KXParams q) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned int s_count;
     __shared__ unsigned long long s_base;
-    uint64_t* s_hi = reinterpret_cast<uint64_t*>(smem + KX_SMEM_RING);                     // [slice][word column of the block]
-    const uint4* s_queue = reinterpret_cast<const uint4*>(smem + KX_SMEM_RING + KX_SMEM_HI);
+    const uint4* s_queue = reinterpret_cast<const uint4*>(smem + KX_SMEM_RING);
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y;
@@ -422,7 +418,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
     const int r0 = q.chunk_op[chunk], r1 = q.chunk_op[chunk + 1];
     const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(q.ops);
     const uint32_t ring0 = pin_u32(smem_u32(smem));
-    const uint32_t full0 = pin_u32(ring0 + KX_SMEM_RING + KX_SMEM_HI + KX_SMEM_QUEUE), empty0 = full0 + 8 * PB_KX_STAGES;
+    const uint32_t full0 = pin_u32(ring0 + KX_SMEM_RING + KX_SMEM_QUEUE), empty0 = full0 + 8 * PB_KX_STAGES;
 
     if (tid == 0) {
         s_count = 0;
@@ -430,8 +426,6 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (tid < PB_K1_COLS)
-        for (int i = 0; i < (PB_K1_KHI + 1) * PB_KX_WPT; i++) s_hi[i * PB_K1_COLS + tid] = 0;
     __syncthreads();
 
     if (tid >= PB_K1_COLS) {
@@ -443,7 +437,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
 #pragma unroll
                 for (int k = 0; k < PB_K1_RPS; k++) {
                     const uint4 rec = __ldg(recs + i + k);
-                    node[2 * k] = rec.x & PB_OP_NODE_MASK; node[2 * k + 1] = rec.y & PB_OP_NODE_MASK;
+                    node[2 * k] = rec.x & PB_OPX_NODE_MASK; node[2 * k + 1] = rec.y & PB_OPX_NODE_MASK;
                 }
                 mbar_wait(empty0 + boff, phase ^ 1);
                 mbar_arrive_expect_tx(full0 + boff, KX_STAGE_BYTES);
@@ -458,17 +452,10 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
 
     // consumer warps: one thread = PB_KX_WPT adjacent 64-site word columns
     const int lane = tid & 31;
-    const int64_t w = (int64_t)col0 + tid * PB_KX_WPT;
-    const uint32_t site_base = (uint32_t)(w * 64);
+    const uint32_t wcol0 = (uint32_t)col0 + (uint32_t)tid * PB_KX_WPT;
     const uint32_t my_ring = pin_u32(ring0 + tid * (8 * PB_KX_WPT));
-    const uint32_t queue_addr = pin_u32(ring0 + KX_SMEM_RING + KX_SMEM_HI), count_addr = pin_u32(smem_u32(&s_count));
-    K1Params ep;                 // emit_events only uses the raw list fields
-    ep.raw = q.raw; ep.raw_cursor = q.raw_cursor; ep.raw_cap = q.raw_cap;
+    const uint32_t queue_addr = pin_u32(ring0 + KX_SMEM_RING), count_addr = pin_u32(smem_u32(&s_count));
 
-    CensusX cs;
-#pragma unroll
-    for (int j = 0; j < PB_KX_WPT; j++) { cs.s[0][j] = cs.s[1][j] = cs.s[2][j] = 0; cs.pend2[j] = cs.pend4[j] = 0; }
-    cs.nleaf = 0;
     XRow px;
 #pragma unroll
     for (int j = 0; j < PB_KX_WPT; j++) px.w[j] = 0;
@@ -490,68 +477,79 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
         if (boff == 8 * PB_KX_STAGES) { soff = 0; boff = 0; phase ^= 1; }
 #pragma unroll
         for (int k = 0; k < PB_K1_RPS; k++) {
-            k1x_row(rec[k].x, x[2 * k], px, cs, s_hi, tid, site_base, queue_addr, count_addr, ep);
-            k1x_row(rec[k].y, x[2 * k + 1], px, cs, s_hi, tid, site_base, queue_addr, count_addr, ep);
-            if (rec[k].z != PB_REC_NOFLUSH) {
-#pragma unroll
-                for (int j = 0; j < PB_KX_WPT; j++) {
-                    if (w + j < q.W) {
-                        uint64_t* out = q.census + ((int64_t)rec[k].z * PB_K1_KS) * q.W + w + j;
-#pragma unroll
-                        for (int t = 0; t < 3; t++) out[(int64_t)t * q.W] = cs.s[t][j];
-#pragma unroll
-                        for (int t = 0; t < PB_K1_KHI; t++) out[(int64_t)(3 + t) * q.W] = s_hi[t * PB_KX_COLS + tid * PB_KX_WPT + j];
-                    }
-                    cs.s[0][j] = cs.s[1][j] = cs.s[2][j] = 0;
-                    cs.pend2[j] = cs.pend4[j] = 0;
-#pragma unroll
-                    for (int t = 0; t < PB_K1_KHI + 1; t++) s_hi[t * PB_KX_COLS + tid * PB_KX_WPT + j] = 0;
-                }
-                cs.nleaf = 0;
-            }
+            k1x_row(rec[k].x, x[2 * k], px, wcol0, queue_addr, count_addr, q);
+            k1x_row(rec[k].y, x[2 * k + 1], px, wcol0, queue_addr, count_addr, q);
         }
         if ((((i - r0) / PB_K1_RPS) & (PB_KX_DRAIN_EVERY / PB_K1_RPS - 1)) == PB_KX_DRAIN_EVERY / PB_K1_RPS - 1)
-            drain_queue<PB_KX_QCAP, PB_K1_COLS>(s_queue, &s_count, &s_base, tid, PB_KX_QCAP / 2, q.raw, q.raw_cursor, q.raw_cap);
+            drain_queue<PB_KX_QCAP, PB_K1_COLS, 1>(s_queue, &s_count, &s_base, tid, PB_KX_QCAP / 2, q.raw, q.raw_cursor, q.raw_cap);
     }
-    drain_queue<PB_KX_QCAP, PB_K1_COLS>(s_queue, &s_count, &s_base, tid, 1, q.raw, q.raw_cursor, q.raw_cap);
+    drain_queue<PB_KX_QCAP, PB_K1_COLS, 1>(s_queue, &s_count, &s_base, tid, 1, q.raw, q.raw_cursor, q.raw_cap);
 }
 
 int pbk_kx_cols() { return PB_KX_COLS; }
 int pbk_kx_blocks_per_sm() { return PB_KX_BLOCKS_PER_SM; }
 
 // ---- per-site event counters -------------------------------------------------------------------
-// the raw list's length lives on the device (K1's cursor, clamped to the buffer): no host round trip before the tail
-// The tail kernels peel the records: one thread per record, one iteration per set bit (usually one).
-// one-plane mode (xmask != nullptr): b0 holds the child's X bits; the 2-bit code is the site's first base, XOR (first ^ second) if X
-__device__ __forceinline__ uint32_t event_base(const raw_rec_t& r, int b, const uint64_t* __restrict__ xmask) {
-    const uint32_t f = (uint32_t)((r.b0 >> b) & 1ull) | ((uint32_t)((r.b1 >> b) & 1ull) << 1);
-    if (!xmask) return f;
-    const uint64_t* m = xmask + 4 * (int64_t)r.wcol;
-    const uint32_t a = (uint32_t)((m[0] >> b) & 1ull) | ((uint32_t)((m[1] >> b) & 1ull) << 1);
-    const uint32_t d = (uint32_t)((m[2] >> b) & 1ull) | ((uint32_t)((m[3] >> b) & 1ull) << 1);
-    return a ^ (f ? d : 0u);
+// The tail kernels peel the records: one thread per record, one iteration per set bit (usually one).  Both record
+// layouts (raw_rec_t of the three-plane sweep, xrec_t of the one-plane sweep) are read into one view.
+struct ev_rec_t {
+    uint32_t wcol, node;
+    bool leaf, nomrca;    // nomrca: one-plane record of an edge hanging off the root (census only)
+    uint32_t xbit;        // one-plane mode: the child's X at every site of the mask
+    uint64_t mask, b0, b1;
+};
+
+template <bool XMODE>
+__device__ __forceinline__ ev_rec_t load_rec(const raw_rec_t* __restrict__ raw, int64_t i) {
+    ev_rec_t e;
+    if (XMODE) {
+        const xrec_t r = reinterpret_cast<const xrec_t*>(raw)[i];
+        e.wcol = r.wcol; e.node = r.tag & PB_XT_NODE_MASK; e.leaf = (r.tag & PB_XT_LEAF) != 0; e.nomrca = (r.tag & PB_XT_NOMRCA) != 0;
+        e.xbit = (r.tag & PB_XT_XBIT) ? 1u : 0u; e.mask = r.mask; e.b0 = e.b1 = 0;
+    } else {
+        const raw_rec_t r = raw[i];
+        e.wcol = r.wcol; e.node = r.tag & PB_EV_NODE_MASK; e.leaf = (r.tag & 0x80000000u) != 0; e.nomrca = false;
+        e.xbit = 0; e.mask = r.mrca; e.b0 = r.b0; e.b1 = r.b1;
+    }
+    return e;
 }
 
-// ---- per-site event counters -------------------------------------------------------------------
-// the record list's length lives on the device (the sweep's cursor, clamped to the buffer): no host round trip before the tail
+// 2-bit base code of the record's node at site bit b; one-plane mode: the site's first base, XOR (first ^ second) if X
+template <bool XMODE>
+__device__ __forceinline__ uint32_t event_base(const ev_rec_t& e, int b, const uint64_t* __restrict__ xmask) {
+    if (!XMODE) return (uint32_t)((e.b0 >> b) & 1ull) | ((uint32_t)((e.b1 >> b) & 1ull) << 1);
+    const uint64_t* m = xmask + 4 * (int64_t)e.wcol;
+    const uint32_t a = (uint32_t)((m[0] >> b) & 1ull) | ((uint32_t)((m[1] >> b) & 1ull) << 1);
+    const uint32_t d = (uint32_t)((m[2] >> b) & 1ull) | ((uint32_t)((m[3] >> b) & 1ull) << 1);
+    return a ^ (e.xbit ? d : 0u);
+}
+
+// the record list's length lives on the device (the sweep's cursor, clamped to the buffer): no host round trip before the tail.
+// One-plane mode also accumulates the census sum (see xrec_t): xcensus[site] += (X_child ? +1 : -1) * leaves_below(child).
+template <bool XMODE>
 __global__ void k1_count_events_kernel(const raw_rec_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
-                                       const int32_t* __restrict__ node_sample, const uint64_t* __restrict__ xmask, uint32_t* __restrict__ cnt,
+                                       const int32_t* __restrict__ node_sample, const int32_t* __restrict__ leaves_below,
+                                       const uint64_t* __restrict__ xmask, uint32_t* __restrict__ cnt, int32_t* __restrict__ xcensus,
                                        unsigned long long* __restrict__ n_events) {
     const int64_t n = min((int64_t)*cursor, raw_cap);
     unsigned int nev = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const raw_rec_t r = raw[i];
-        const bool leaf = r.tag & 0x80000000u;
-        const bool sampled = leaf && node_sample[r.tag & PB_EV_NODE_MASK] >= 0;
-        uint64_t m = r.mrca;
-        nev += (unsigned int)__popcll(m);
+        const ev_rec_t r = load_rec<XMODE>(raw, i);
+        const bool sampled = r.leaf && node_sample[r.node] >= 0;
+        int32_t delta = 0;
+        if (XMODE) { const int32_t lb = leaves_below[r.node]; delta = r.xbit ? lb : -lb; }
+        uint64_t m = r.mask;
+        if (!r.nomrca) nev += (unsigned int)__popcll(m);
         while (m) {
             const int b = __ffsll((long long)m) - 1;
             m &= m - 1;
-            const uint32_t base = event_base(r, b, xmask);
-            uint32_t* c = cnt + ((int64_t)r.wcol * 64 + b) * PB_CNT_STRIDE;
+            const int64_t site = (int64_t)r.wcol * 64 + b;
+            if (XMODE) atomicAdd(xcensus + site, delta);
+            if (r.nomrca) continue;
+            const uint32_t base = event_base<XMODE>(r, b, xmask);
+            uint32_t* c = cnt + site * PB_CNT_STRIDE;
             atomicAdd(c + base, 1u);
-            if (leaf) {
+            if (r.leaf) {
                 atomicAdd(c + 4 + base, 1u);
                 if (sampled) atomicAdd(c + 8 + base, 1u);
             }
@@ -600,9 +598,10 @@ __global__ void k1_census_reduce_kernel(const uint64_t* __restrict__ census, int
 
 // ---- per-site finalisation: census -> class / major-minor; counters -> Homoplasy_Events -----------
 // XMODE: the alignment is held as one plane.  B0 = X, B1 = the site masks [W][4], V = the valid-site words [W]; the
-// census holds one counter (leaves carrying the second base) and n_leaves the tree's leaf count.
+// census is xcensus[S], the signed sum k1_count_events_kernel took over the records (see xrec_t): leaves carrying the
+// second base = n_leaves * X(root) + xcensus.
 template <bool XMODE>
-__global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, int kt_used, int64_t W, int64_t S,
+__global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, const int32_t* __restrict__ xcensus, int kt_used, int64_t W, int64_t S,
                                    const uint64_t* __restrict__ B0, const uint64_t* __restrict__ B1, const uint64_t* __restrict__ V,
                                    int64_t Wp, int32_t root, int32_t n_leaves, const uint32_t* __restrict__ cnt, int32_t min_hcount, int64_t site_offset,
                                    pb_site_out* __restrict__ sites, uint8_t* __restrict__ flags, uint64_t* __restrict__ scan_in,
@@ -618,8 +617,7 @@ __global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, int kt_us
         int xa = 0, xd = 0;                  // XMODE: code of the site's first base, first XOR second
         bool xvalid = true;
         if (XMODE) {
-            uint32_t nx = 0;
-            for (int j = 0; j < kt_used; j++) nx |= (uint32_t)((total[(int64_t)j * W + w] >> b) & 1ull) << j;
+            const uint32_t nx = (uint32_t)((((B0[(int64_t)root * Wp + w] >> b) & 1ull) ? n_leaves : 0) + xcensus[s]);
             const uint64_t* m = B1 + 4 * w;
             xa = (int)((m[0] >> b) & 1ull) | ((int)((m[1] >> b) & 1ull) << 1);
             xd = (int)((m[2] >> b) & 1ull) | ((int)((m[3] >> b) & 1ull) << 1);
@@ -793,6 +791,7 @@ __global__ void k1_scatter_sites_kernel(int64_t S, const uint8_t* __restrict__ f
     }
 }
 
+template <bool XMODE>
 __global__ void k1_scatter_events_kernel(const raw_rec_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
                                          const int32_t* __restrict__ node_sample, const uint8_t* __restrict__ flags,
                                          const uint64_t* __restrict__ scan, const uint64_t* __restrict__ scan_in,
@@ -801,18 +800,18 @@ __global__ void k1_scatter_events_kernel(const raw_rec_t* __restrict__ raw, cons
                                          int64_t csr_cap) {
     const int64_t n = min((int64_t)*cursor, raw_cap);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const raw_rec_t r = raw[i];
-        if (!(r.tag & 0x80000000u)) continue;            // extant (leaf) events only (EXTANT_NODES_ONLY, HC.java:173)
-        const int32_t smp = node_sample[r.tag & PB_EV_NODE_MASK];
+        const ev_rec_t r = load_rec<XMODE>(raw, i);
+        if (!r.leaf || r.nomrca) continue;                // extant (leaf) events only (EXTANT_NODES_ONLY, HC.java:173)
+        const int32_t smp = node_sample[r.node];
         if (smp < 0) continue;                            // leaf without a pheno row: never tallied (HC.java:3743)
-        uint64_t m = r.mrca;
+        uint64_t m = r.mask;
         while (m) {
             const int b = __ffsll((long long)m) - 1;
             m &= m - 1;
             const uint32_t site = r.wcol * 64u + (uint32_t)b;
             if (!(scan_in[site] >> 38)) continue;
             const uint8_t fl = flags[site];
-            const uint32_t base = event_base(r, b, xmask);
+            const uint32_t base = event_base<XMODE>(r, b, xmask);
             const int a = (base == ((fl >> PB_SF_A1_CODE_SHIFT) & 3u)) ? 0 : 1;
             if (!(fl & (a == 0 ? PB_SF_A1_USE : PB_SF_A2_USE))) continue;
             // bucket emptied by the <2 rule?  (in_use with min_hcount 0 keeps n = 0)
@@ -911,10 +910,8 @@ int pbk_promote_planes(pb_ctx* ctx) {
 
 static int pbk_events_x(pb_ctx* ctx) {
     KXParams q;
-    q.W = ctx->W;
     q.ops = ctx->d_ops_x; q.chunk_op = ctx->d_chunk_op_x;
-    q.census = ctx->d_census;
-    q.raw = ctx->d_raw; q.raw_cursor = ctx->d_raw_cursor; q.raw_cap = (unsigned long long)ctx->raw_cap;
+    q.raw = reinterpret_cast<xrec_t*>(ctx->d_raw); q.raw_cursor = ctx->d_raw_cursor; q.raw_cap = (unsigned long long)ctx->raw_cap;
     const size_t smem = (size_t)KX_SMEM_TOTAL;
     static bool attr_set = false;
     if (!attr_set) {
@@ -981,7 +978,7 @@ int pbk_prepare_tail(pb_ctx* ctx) {
         ctx->csr_cap = std::max(ctx->raw_cap, ctx->csr_want);
         PB_CUDA(cudaMalloc(&ctx->d_csr, (size_t)ctx->csr_cap * 4));
     }
-    PB_CUDA(cudaMemsetAsync(ctx->d_cnt, 0, (size_t)S * PB_CNT_STRIDE * 4, ctx->stream2));
+    PB_CUDA(cudaMemsetAsync(ctx->d_cnt, 0, (size_t)S * PB_CNT_ALLOC_STRIDE * 4, ctx->stream2));   // counters + the one-plane census sum
     PB_CUDA(cudaMemsetAsync(ctx->d_csr_cursor, 0, (size_t)S * 2 * 4, ctx->stream2));
     PB_CUDA(cudaEventRecord(ctx->ev_zero_done, ctx->stream2));
     return PB_OK;
@@ -997,24 +994,30 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     pb_trace_mark(ctx, "headstart+memsets");
     const bool xmode = ctx->plane_mode == PB_PLANES_X;
     const uint64_t* xmask = xmode ? ctx->d_xmask : nullptr;
-    k1_count_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, xmask, ctx->d_cnt,
-                                                    ctx->d_class_counts + 9);
-    pb_trace_mark(ctx, "count_events");
-    k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), xmode ? 1 : 4), 128, 0, st>>>(ctx->d_census, xmode ? ctx->n_flush_x : ctx->n_flush,
-                                                                                                 ctx->W, ctx->d_census_total);
-    pb_trace_mark(ctx, "census_reduce");
+    int32_t* xcensus = reinterpret_cast<int32_t*>(ctx->d_cnt + S * PB_CNT_STRIDE);
     int kt_used = 1;
     while ((1ll << kt_used) <= (int64_t)ctx->L) kt_used++;
-    if (xmode)
+    if (xmode) {
+        // one-plane mode: the leaf census is a by-product of the record pass (no dense counters, nothing to reduce)
+        k1_count_events_kernel<true><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_leaves_below,
+                                                              xmask, ctx->d_cnt, xcensus, ctx->d_class_counts + 9);
+        pb_trace_mark(ctx, "count_events");
         k1_finalize_kernel<true><<<(unsigned)((S + T - 1) / T), T, 0, st>>>(
-            ctx->d_census_total, kt_used, ctx->W, S, ctx->d_X, ctx->d_xmask, ctx->d_xvalid, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt,
+            nullptr, xcensus, kt_used, ctx->W, S, ctx->d_X, ctx->d_xmask, ctx->d_xvalid, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt,
             ctx->cfg.min_hcount, ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan, ctx->d_class_counts);
-    else
+        ctx->tm.n_launches += 2;
+    } else {
+        k1_count_events_kernel<false><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, nullptr, nullptr,
+                                                               ctx->d_cnt, nullptr, ctx->d_class_counts + 9);
+        pb_trace_mark(ctx, "count_events");
+        k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), 4), 128, 0, st>>>(ctx->d_census, ctx->n_flush, ctx->W, ctx->d_census_total);
+        pb_trace_mark(ctx, "census_reduce");
         k1_finalize_kernel<false><<<(unsigned)((S + T - 1) / T), T, 0, st>>>(
-            ctx->d_census_total, kt_used, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt, ctx->cfg.min_hcount,
+            ctx->d_census_total, nullptr, kt_used, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt, ctx->cfg.min_hcount,
             ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan /* reused as scan input */, ctx->d_class_counts);
+        ctx->tm.n_launches += 3;
+    }
     pb_trace_mark(ctx, "finalize");
-    ctx->tm.n_launches += 3;
     PB_CUDA(cudaGetLastError());
     // scan: d_site_scan (input) -> d_site_scan_out.  We keep input in the first half of a 2*S buffer.
     uint64_t* scan_in = ctx->d_site_scan;
@@ -1025,8 +1028,12 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     k1_scatter_sites_kernel<<<(unsigned)((S + T - 1) / T), T, 0, st>>>(S, ctx->d_site_flags, scan_out, scan_in, ctx->d_cnt, ctx->d_sites,
                                                                       ctx->d_inf_site, ctx->d_alleles, ctx->d_class_counts);
     pb_trace_mark(ctx, "scatter_sites");
-    k1_scatter_events_kernel<<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
-                                                     scan_out, scan_in, ctx->d_sites, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr, ctx->csr_cap);
+    if (xmode)
+        k1_scatter_events_kernel<true><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
+                                                               scan_out, scan_in, ctx->d_sites, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr, ctx->csr_cap);
+    else
+        k1_scatter_events_kernel<false><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
+                                                                scan_out, scan_in, ctx->d_sites, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr, ctx->csr_cap);
     pb_trace_mark(ctx, "scatter_events");
     ctx->tm.n_launches += 2;
     PB_CUDA(cudaGetLastError());

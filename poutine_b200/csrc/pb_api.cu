@@ -16,7 +16,7 @@ extern "C" int pb_version(void) { return 100; }
 extern "C" const char* pb_last_error(pb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 static void free_all(pb_ctx* c) {
-    void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_ops_x, c->d_chunk_op_x, c->d_node_sample, c->d_label, c->d_planes,
+    void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_ops_x, c->d_chunk_op_x, c->d_node_sample, c->d_leaves_below, c->d_label, c->d_planes,
                     c->d_census, c->d_census_total, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
                     c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT,
                     c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop, c->d_colmask, c->d_extras, c->d_X, c->d_xmask, c->d_xvalid};
@@ -140,6 +140,13 @@ static int build_schedule(pb_ctx* ctx) {
     if ((int32_t)order.size() != N) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: parent[] does not describe one tree (cycle or several roots)");
     std::vector<int32_t> sz(N, 1);
     for (int32_t i = N - 1; i > 0; i--) sz[ctx->parent[order[i]]] += sz[order[i]];
+    {   // leaves in each subtree: the weights of the one-plane mode's census sum (xrec_t, pb_internal.h)
+        std::vector<int32_t> lb(N, 0);
+        for (int32_t v = 0; v < N; v++) lb[v] = ctx->is_leaf[v] ? 1 : 0;
+        for (int32_t i = N - 1; i > 0; i--) lb[ctx->parent[order[i]]] += lb[order[i]];
+        int rc = upload(ctx, &ctx->d_leaves_below, lb);
+        if (rc) return rc;
+    }
     for (int32_t u = 0; u < N; u++)
         std::sort(kids.begin() + first[u], kids.begin() + first[u + 1], [&](int32_t a, int32_t b) {
             if (sz[a] != sz[b]) return sz[a] < sz[b];   // leaves (size 1) first, then ascending subtree size
@@ -165,7 +172,9 @@ static int build_schedule(pb_ctx* ctx) {
 // stream: SETCUR reloads where the tracked parent row is not the edge's parent, census segments closed
 // by FLUSH ops (leaf count padded to a multiple of 8 with null leaves: the carry-save tree works in
 // groups of 8), chunks padded to a multiple of 4 ops.
-static int build_program(pb_ctx* ctx, int64_t cols_per_block, int64_t blocks_per_sm, uint32_t** d_ops, int32_t** d_chunk_op,
+// xprog: the lowering k1x_events_kernel runs (one-plane mode) — no census, so no LEAF padding and no flushes; every edge
+// is tested, those hanging off the root as PB_OPX_NOMRCA (their records feed the census sum only); 28-bit node field.
+static int build_program(pb_ctx* ctx, bool xprog, int64_t cols_per_block, int64_t blocks_per_sm, uint32_t** d_ops, int32_t** d_chunk_op,
                          int32_t* n_chunks_out, int32_t* n_flush_out) {
     const int64_t n_lops = (int64_t)ctx->lop_child.size();
     const int64_t blocks_x = (ctx->W + cols_per_block - 1) / cols_per_block;
@@ -195,11 +204,12 @@ static int build_program(pb_ctx* ctx, int64_t cols_per_block, int64_t blocks_per
         const int64_t l0 = n_lops * c / n_chunks, l1 = n_lops * (c + 1) / n_chunks;
         int32_t cur = -1;       // node whose row the kernel holds as "current parent"
         int32_t seg_leaves = 0;
-        uint32_t slot[2] = {PB_OP_NULL, PB_OP_NULL};
+        const uint32_t null_op = xprog ? PB_OPX_NULL : PB_OP_NULL;
+        uint32_t slot[2] = {null_op, null_op};
         int filled = 0;
         auto close = [&](uint32_t flush_id) {
             recs.push_back(slot[0]); recs.push_back(slot[1]); recs.push_back(flush_id); recs.push_back(0u);
-            slot[0] = slot[1] = PB_OP_NULL; filled = 0;
+            slot[0] = slot[1] = null_op; filled = 0;
         };
         auto push = [&](uint32_t op) {
             slot[filled++] = op;
@@ -210,7 +220,14 @@ static int build_program(pb_ctx* ctx, int64_t cols_per_block, int64_t blocks_per
             close((uint32_t)n_flush++);   // closes the open record (possibly empty) with the flush attached
             seg_leaves = 0;
         };
-        for (int64_t i = l0; i < l1; i++) {
+        for (int64_t i = l0; xprog && i < l1; i++) {
+            const int32_t child = ctx->lop_child[i], par = ctx->lop_parent[i];
+            const uint32_t fl = PB_OP_TEST | (par == ctx->root ? PB_OPX_NOMRCA : 0u);   // HC.java:1674: never an MRCA, but part of the census sum
+            if (cur != par) { push(PB_OP_SETCUR | (uint32_t)par); cur = par; }
+            if (ctx->is_leaf[child]) push(PB_OP_LEAF | fl | (uint32_t)child);
+            else { push(PB_OP_SETCUR | fl | (uint32_t)child); cur = child; }
+        }
+        for (int64_t i = l0; !xprog && i < l1; i++) {
             const int32_t child = ctx->lop_child[i], par = ctx->lop_parent[i];
             const bool test = par != ctx->root;     // edges hanging off the root are never tested (HC.java:1674)
             if (test && cur != par) { push(PB_OP_SETCUR | (uint32_t)par); cur = par; }
@@ -223,7 +240,8 @@ static int build_program(pb_ctx* ctx, int64_t cols_per_block, int64_t blocks_per
                 cur = child;
             }
         }
-        flush();   // every chunk ends with a flush (possibly of an all-zero census)
+        if (!xprog) flush();   // every chunk ends with a flush (possibly of an all-zero census)
+        else if (filled) close(PB_REC_NOFLUSH);
         while ((recs.size() / 4) % PB_K1_RPS) close(PB_REC_NOFLUSH);   // whole ring stages (empty records cost nothing)
         chunk_op[c + 1] = (int32_t)(recs.size() / 4);
     }
@@ -238,10 +256,10 @@ static int build_program(pb_ctx* ctx, int64_t cols_per_block, int64_t blocks_per
 static int build_chunks(pb_ctx* ctx) {
     if (ctx->N == 0 || ctx->W == 0) return PB_OK;
     int rc;
-    if ((rc = build_program(ctx, PB_K1_COLS, PB_K1_BLOCKS_PER_SM, &ctx->d_ops, &ctx->d_chunk_op, &ctx->n_chunks, &ctx->n_flush))) return rc;
-    if ((rc = build_program(ctx, pbk_kx_cols(), pbk_kx_blocks_per_sm(), &ctx->d_ops_x, &ctx->d_chunk_op_x, &ctx->n_chunks_x, &ctx->n_flush_x))) return rc;
+    if ((rc = build_program(ctx, false, PB_K1_COLS, PB_K1_BLOCKS_PER_SM, &ctx->d_ops, &ctx->d_chunk_op, &ctx->n_chunks, &ctx->n_flush))) return rc;
+    if ((rc = build_program(ctx, true, pbk_kx_cols(), pbk_kx_blocks_per_sm(), &ctx->d_ops_x, &ctx->d_chunk_op_x, &ctx->n_chunks_x, &ctx->n_flush_x))) return rc;
     if (ctx->d_census) { cudaFree(ctx->d_census); ctx->d_census = nullptr; }
-    PB_CUDA(cudaMalloc(&ctx->d_census, (size_t)std::max<int64_t>(4ll * ctx->n_flush, ctx->n_flush_x) * PB_K1_KS * ctx->W * 8));
+    PB_CUDA(cudaMalloc(&ctx->d_census, (size_t)4 * ctx->n_flush * PB_K1_KS * ctx->W * 8));
     if (ctx->d_census_total) { cudaFree(ctx->d_census_total); ctx->d_census_total = nullptr; }
     PB_CUDA(cudaMalloc(&ctx->d_census_total, (size_t)4 * PB_K1_KT * ctx->W * 8));
     return PB_OK;
@@ -258,7 +276,7 @@ static int build_node_sample(pb_ctx* ctx) {
 extern "C" int pb_set_tree(pb_ctx* ctx, int32_t n_nodes, const int32_t* parent, const uint8_t* is_leaf) {
     CHECK_CTX(ctx);
     if (n_nodes < 2 || !parent || !is_leaf) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: need >= 2 nodes, parent[] and is_leaf[]");
-    if (n_nodes >= (int32_t)PB_EV_NODE_MASK) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: too many nodes (limit 2^29-2)");
+    if (n_nodes >= (int32_t)PB_OPX_NODE_MASK) FAIL(ctx, PB_ERR_INVALID, "pb_set_tree: too many nodes (limit 2^28-2)");
     PB_CUDA(cudaSetDevice(ctx->device));
     int32_t root = -1, L = 0;
     std::vector<int32_t> nchild(n_nodes, 0);
@@ -418,7 +436,7 @@ extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
             return PB_ERR_OOM;
         }
     }
-    PB_CUDA(cudaMalloc(&ctx->d_cnt, (size_t)n_sites * PB_CNT_STRIDE * 4));
+    PB_CUDA(cudaMalloc(&ctx->d_cnt, (size_t)n_sites * PB_CNT_ALLOC_STRIDE * 4));
     PB_CUDA(cudaMalloc(&ctx->d_sites, (size_t)n_sites * sizeof(pb_site_out)));
     PB_CUDA(cudaMalloc(&ctx->d_site_flags, (size_t)n_sites));
     PB_CUDA(cudaMalloc(&ctx->d_site_scan, (size_t)n_sites * 2 * 8));
@@ -580,9 +598,23 @@ extern "C" int pb_get_raw_events(pb_ctx* ctx, int64_t cap, int32_t* site, int32_
     if (n) *n = ctx->n_raw;
     if (!site || !node) return PB_OK;
     if (cap < ctx->n_raw) FAIL(ctx, PB_ERR_INVALID, "pb_get_raw_events: buffer too small");
+    int64_t k = 0;
+    if (ctx->plane_mode == PB_PLANES_X) {   // 16-byte records; those of the root's own edges are not MRCAs
+        std::vector<xrec_t> hx((size_t)ctx->n_rec);
+        if (ctx->n_rec) PB_CUDA(cudaMemcpy(hx.data(), ctx->d_raw, (size_t)ctx->n_rec * sizeof(xrec_t), cudaMemcpyDeviceToHost));
+        for (const xrec_t& r : hx) {
+            if (r.tag & PB_XT_NOMRCA) continue;
+            for (uint64_t m = r.mask; m; m &= m - 1) {
+                if (k >= cap) FAIL(ctx, PB_ERR_INVALID, "pb_get_raw_events: buffer too small");
+                site[k] = (int32_t)(r.wcol * 64u + (uint32_t)__builtin_ctzll(m));
+                node[k] = (int32_t)(r.tag & PB_XT_NODE_MASK);
+                k++;
+            }
+        }
+        return PB_OK;
+    }
     std::vector<raw_rec_t> h((size_t)ctx->n_rec);
     if (ctx->n_rec) PB_CUDA(cudaMemcpy(h.data(), ctx->d_raw, (size_t)ctx->n_rec * sizeof(raw_rec_t), cudaMemcpyDeviceToHost));
-    int64_t k = 0;
     for (const raw_rec_t& r : h)
         for (uint64_t m = r.mrca; m; m &= m - 1) {
             if (k >= cap) FAIL(ctx, PB_ERR_INVALID, "pb_get_raw_events: buffer too small");

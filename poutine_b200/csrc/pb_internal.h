@@ -25,6 +25,13 @@
 #define PB_OP_FLUSH 0xE0000000u
 #define PB_REC_NOFLUSH 0xFFFFFFFFu
 
+// The one-plane sweep (k1x_events_kernel) runs its own lowering of the same edge list: no census flags (the leaf census
+// comes out of the events, see xrec_t), every edge tested — the edges hanging off the root too, marked NOMRCA because
+// the reference never makes their child an MRCA (HC.java:1674) — and a 28-bit node field.
+#define PB_OPX_NODE_MASK 0x0FFFFFFFu
+#define PB_OPX_NULL 0x0FFFFFFFu
+#define PB_OPX_NOMRCA 0x10000000u
+
 enum { PB_PLANES_NONE = 0, PB_PLANES_X = 1, PB_PLANES_FULL = 2 };
 
 // raw MRCA record: ALL events of one (tree row, 64-site word): the sweep kernels store the masks as they are and the
@@ -37,9 +44,27 @@ struct __align__(16) raw_rec_t {
 };
 #define PB_EV_NODE_MASK 0x1FFFFFFFu
 
+// One-plane mode: 16-byte records.  All sites of one (tree row, 64-site word) where X_child != X_parent AND the child
+// carries X = x (two records when the word holds edges of both directions: rare).  The X bit is all the tail needs to
+// rebuild the child's base code from the column's site masks — and to rebuild the LEAF CENSUS without ever counting leaf
+// rows: X(leaf) = X(root) + sum over the edges (p -> c) of its root path of X(c) - X(p), hence
+//   #leaves carrying the second base = L * X(root) + sum over edges with X(c) != X(p) of (X(c) ? +1 : -1) * leaves_below(c),
+// a sum over exactly the (sparse) records, including those of the root's own edges (NOMRCA: census only).
+struct __align__(16) xrec_t {
+    uint32_t wcol;        // site word (context-local)
+    uint32_t tag;         // node (28 bits) | X << 28 | NOMRCA << 30 | is_leaf << 31
+    uint64_t mask;        // sites of the word with X_child != X_parent and X_child == X
+};
+#define PB_XT_NODE_MASK 0x0FFFFFFFu
+#define PB_XT_XBIT 0x10000000u
+#define PB_XT_NOMRCA 0x40000000u
+#define PB_XT_LEAF 0x80000000u
+
 // per-site event counters filled by k1_count_events: [0..3] all MRCAs by own base code,
 // [4..7] leaf MRCAs, [8..11] leaf MRCAs that have a pheno row
 #define PB_CNT_STRIDE 12
+// the allocation holds one more int32 per site behind the [S][12] counters: the one-plane mode's signed census sum
+#define PB_CNT_ALLOC_STRIDE 13
 
 // site flags byte written by k1_finalize
 #define PB_SF_BI 1u
@@ -111,6 +136,7 @@ struct pb_ctx {
     int32_t* d_chunk_op_x = nullptr;
     int32_t n_chunks_x = 0, n_flush_x = 0;
     int32_t* d_node_sample = nullptr;  // N: sample index of a leaf with a pheno row, else -1
+    int32_t* d_leaves_below = nullptr; // N: leaves in the node's subtree (1 for a leaf): weights of the one-plane census sum
 
     // labels
     int32_t P = 0, n_case = 0, n_ctrl = 0, n_miss = 0;
@@ -134,10 +160,10 @@ struct pb_ctx {
     CUtensorMap tmap_x{};           // 2-D TMA descriptor over d_X: box = 128 words x 1 node
 
     // K1 outputs
-    uint64_t* d_census = nullptr;      // [n_flush][4][KS][W]
+    uint64_t* d_census = nullptr;      // [n_flush][4][KS][W]   (three-plane mode only)
     uint64_t* d_census_total = nullptr;  // [4][KT][W]
-    raw_rec_t* d_raw = nullptr;
-    int64_t raw_cap = 0, n_rec = 0;   // capacity / length of the record list (n_raw = events = set bits over all records)
+    raw_rec_t* d_raw = nullptr;        // raw_cap records of 32 bytes; the one-plane mode writes xrec_t (16 bytes) into the same buffer
+    int64_t raw_cap = 0, n_rec = 0;   // capacity / length of the record list (n_raw = MRCA events = set bits over all MRCA records)
     unsigned long long* d_raw_cursor = nullptr;
     int64_t n_raw = 0;
     uint32_t* d_cnt = nullptr;         // [S][PB_CNT_STRIDE]
