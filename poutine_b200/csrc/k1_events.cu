@@ -379,7 +379,7 @@ __device__ __forceinline__
 void emit_xrec(uint64_t mask, uint32_t wcol, uint32_t tag, uint32_t queue_addr, uint32_t count_addr, const KXParams& q) {
     uint32_t slot;
     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(count_addr) : "memory");
-    if (slot < PB_KX_QCAP) {
+    if (__builtin_expect(slot < PB_KX_QCAP, 1)) {
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(queue_addr + slot * 16), "r"(wcol), "r"(tag), "r"((uint32_t)mask),
                      "r"((uint32_t)(mask >> 32)) : "memory");
     } else {
@@ -390,9 +390,8 @@ void emit_xrec(uint64_t mask, uint32_t wcol, uint32_t tag, uint32_t queue_addr, 
 // one tree row: X_child ^ X_parent against the current parent row, optional parent update
 __device__ __forceinline__ void k1x_row(uint32_t op, const XRow& x, XRow& px, uint32_t wcol0, uint32_t queue_addr, uint32_t count_addr,
                                         const KXParams& q) {
-    if (op & PB_OP_TEST) {
-        // xrec_t tag: node | NOMRCA (op bit 28 -> tag bit 30) | LEAF (bit 31 in both); bit 28 = the child's X
-        const uint32_t tag = (op & PB_OPX_NODE_MASK) | (op & PB_OP_LEAF) | ((op & PB_OPX_NOMRCA) << 2);
+    if (op & PB_OPX_TEST) {
+        const uint32_t tag = op & PB_OPX_TAG_MASK;                 // node | NOMRCA | LEAF sit where xrec_t wants them; bit 28 = the child's X
 #pragma unroll
         for (int j = 0; j < PB_KX_WPT; j++) {
             const uint64_t diff = x.w[j] ^ px.w[j];
@@ -403,7 +402,7 @@ __device__ __forceinline__ void k1x_row(uint32_t op, const XRow& x, XRow& px, ui
             }
         }
     }
-    if (op & PB_OP_SETCUR) px = x;
+    if (op & PB_OPX_SETCUR) px = x;
 }
 
 __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events_kernel(const __grid_constant__ CUtensorMap tmap, const KXParams q) {

@@ -748,10 +748,15 @@ int pbk_pregen_labels(pb_ctx* ctx) {
     if ((rc = k3_plan(ctx, &pl))) return rc;
     const int64_t m = ctx->cfg.n_replicates;
     const int64_t nr = m < pl.tile ? m : pl.tile;
-    // default: the generator starts when K1 has finished.  PB_PREGEN_EARLY (experiment): it is ordered behind the previous
+    // default: the generator starts when K1 has finished.  Experiments: PB_PREGEN_EARLY — it is ordered behind the previous
     // step only (ev[0] is recorded just before the K1 launch), so the low-priority stream may pick up SM slots while
-    // K1's last wave drains.
-    if (getenv("PB_PREGEN_EARLY")) {
+    // K1's last wave drains; PB_PREGEN_FIRST — pb_run_events calls this BEFORE it enqueues the sweep (ordered behind
+    // ev[12], the start of the call), so the generator's blocks are resident first and the sweep fills the rest of each SM.
+    const bool early = getenv("PB_PREGEN_EARLY") != nullptr, first = getenv("PB_PREGEN_FIRST") != nullptr;
+    if (first) {
+        PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev[12], 0));
+        PB_CUDA(cudaEventRecord(ctx->ev_gen_started, ctx->stream2));
+    } else if (early) {
         PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev[0], 0));
     } else {
         PB_CUDA(cudaEventRecord(ctx->ev_k1_done, ctx->stream));
@@ -767,7 +772,7 @@ int pbk_pregen_labels(pb_ctx* ctx) {
     {
         int us = 8;
         if (const char* e = getenv("PB_GEN_HEADSTART_US")) us = atoi(e);
-        if (us > 0 && !getenv("PB_PREGEN_EARLY")) {
+        if (us > 0 && !early) {
             PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_gen_started, 0));
             k3_headstart_kernel<<<1, 1, 0, ctx->stream>>>((unsigned)us * 1000u);
             ctx->tm.n_launches += 1;

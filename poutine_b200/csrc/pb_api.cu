@@ -222,10 +222,10 @@ static int build_program(pb_ctx* ctx, bool xprog, int64_t cols_per_block, int64_
         };
         for (int64_t i = l0; xprog && i < l1; i++) {
             const int32_t child = ctx->lop_child[i], par = ctx->lop_parent[i];
-            const uint32_t fl = PB_OP_TEST | (par == ctx->root ? PB_OPX_NOMRCA : 0u);   // HC.java:1674: never an MRCA, but part of the census sum
-            if (cur != par) { push(PB_OP_SETCUR | (uint32_t)par); cur = par; }
-            if (ctx->is_leaf[child]) push(PB_OP_LEAF | fl | (uint32_t)child);
-            else { push(PB_OP_SETCUR | fl | (uint32_t)child); cur = child; }
+            const uint32_t fl = PB_OPX_TEST | (par == ctx->root ? PB_OPX_NOMRCA : 0u);   // HC.java:1674: never an MRCA, but part of the census sum
+            if (cur != par) { push(PB_OPX_SETCUR | (uint32_t)par); cur = par; }
+            if (ctx->is_leaf[child]) push(PB_OPX_LEAF | fl | (uint32_t)child);
+            else { push(PB_OPX_SETCUR | fl | (uint32_t)child); cur = child; }
         }
         for (int64_t i = l0; !xprog && i < l1; i++) {
             const int32_t child = ctx->lop_child[i], par = ctx->lop_parent[i];
@@ -521,8 +521,10 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
     PB_CUDA(cudaEventRecord(ctx->ev[12], ctx->stream));
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = pbk_prepare_tail(ctx))) return rc;
+        const bool gen_first = getenv("PB_PREGEN_FIRST") != nullptr;   // experiment: label generator resident before the sweep
+        if (attempt == 0 && gen_first && (rc = pbk_pregen_labels(ctx))) return rc;
         if ((rc = pbk_events(ctx))) return rc;
-        if (attempt == 0 && (rc = pbk_pregen_labels(ctx))) return rc;
+        if (attempt == 0 && !gen_first && (rc = pbk_pregen_labels(ctx))) return rc;
         unsigned long long cur = 0;
         if ((rc = pbk_finalize_events(ctx, counts, &cur))) return rc;   // the whole tail, one host round trip at its end
         if ((int64_t)cur <= ctx->raw_cap && ctx->E <= ctx->csr_cap) { ctx->n_rec = (int64_t)cur; break; }

@@ -27,10 +27,15 @@
 
 // The one-plane sweep (k1x_events_kernel) runs its own lowering of the same edge list: no census flags (the leaf census
 // comes out of the events, see xrec_t), every edge tested — the edges hanging off the root too, marked NOMRCA because
-// the reference never makes their child an MRCA (HC.java:1674) — and a 28-bit node field.
+// the reference never makes their child an MRCA (HC.java:1674) — and a 28-bit node field.  The flag bits are laid out so
+// that a record's tag is ONE AND of the op: node (0..27), SETCUR (28; the tag's X bit), TEST (29), NOMRCA (30), LEAF (31).
 #define PB_OPX_NODE_MASK 0x0FFFFFFFu
 #define PB_OPX_NULL 0x0FFFFFFFu
-#define PB_OPX_NOMRCA 0x10000000u
+#define PB_OPX_SETCUR 0x10000000u
+#define PB_OPX_TEST 0x20000000u
+#define PB_OPX_NOMRCA 0x40000000u
+#define PB_OPX_LEAF 0x80000000u
+#define PB_OPX_TAG_MASK (PB_OPX_NODE_MASK | PB_OPX_NOMRCA | PB_OPX_LEAF)
 
 enum { PB_PLANES_NONE = 0, PB_PLANES_X = 1, PB_PLANES_FULL = 2 };
 
@@ -59,6 +64,8 @@ struct __align__(16) xrec_t {
 #define PB_XT_XBIT 0x10000000u
 #define PB_XT_NOMRCA 0x40000000u
 #define PB_XT_LEAF 0x80000000u
+static_assert(PB_XT_NODE_MASK == PB_OPX_NODE_MASK && PB_XT_NOMRCA == PB_OPX_NOMRCA && PB_XT_LEAF == PB_OPX_LEAF &&
+              (PB_OPX_TAG_MASK & PB_XT_XBIT) == 0, "an xrec_t tag is the X op ANDed with PB_OPX_TAG_MASK");
 
 // per-site event counters filled by k1_count_events: [0..3] all MRCAs by own base code,
 // [4..7] leaf MRCAs, [8..11] leaf MRCAs that have a pheno row

@@ -231,6 +231,66 @@ def test_events_one_plane_mode(oracle_mod, monkeypatch, n_leaves, S, chunks):
     assert res[0] == res[1]
 
 
+@pytest.mark.parametrize("seed,density", [(0, "dense"), (1, "dense"), (2, "sparse"), (3, "sparse"), (4, "dense")])
+def test_one_plane_mode_census_from_records(oracle_mod, seed, density):
+    """k1x_events_kernel keeps no leaf counters: the census is L * X(root) + the signed sum, over the records, of
+    leaves_below(child).  Topologies that stress it: leaves hanging off the root (their records are census-only and must
+    never become MRCAs or extant events), polytomies, shuffled node ids; dense columns put flips of both directions into
+    one (row, word) cell (two records) and make X(root) = 1 at half of the sites.  Oracle parity + identity with the
+    three-plane path for events, raw MRCA list, CSR and the assoc output."""
+    tree = synth.random_tree(40 + 37 * seed, 900 + seed, polytomy=0.3, root_leaf_children=1 + seed % 3)
+    S = [64 * 3 + 5, 64 * 9, 700, 64 * 17 + 63, 129][seed]
+    rng = np.random.default_rng(50 + seed)
+    N = tree.n_nodes
+    if density == "dense":
+        X = rng.integers(0, 2, size=(N, S)).astype(np.uint8)
+    else:                                     # a few flipped subtrees per site, plus single flipped leaves
+        X = np.zeros((N, S), dtype=np.uint8)
+        X[:, rng.random(S) < 0.5] = 1         # root state
+        flip = rng.random((N, S)) < 2.5 / N
+        par = np.asarray(tree.parent)
+        kids = {}
+        for v in range(N):
+            if par[v] >= 0:
+                kids.setdefault(int(par[v]), []).append(v)
+        todo = [int(tree.root)]                # X(v) = X(parent) ^ flip(v), parents before children
+        while todo:
+            u = todo.pop()
+            for c in kids.get(u, []):
+                X[c] = X[u] ^ flip[c]
+                todo.append(c)
+    first = rng.integers(0, 4, size=S)
+    second = (first + 1 + rng.integers(0, 3, size=S)) % 4
+    pair = np.frombuffer(b"ACGT", dtype=np.uint8)[np.stack([first, second])]
+    chars = np.where(X == 1, pair[1][None, :], pair[0][None, :]).astype(np.uint8)
+    B0, B1, V = pb.pack_chars(chars)
+    sn, lab = synth.simulate_phenotypes(tree, 60 + seed, na_frac=0.03, no_row_frac=0.05)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(chars)
+    res = []
+    for full in (False, True):
+        hc = pb.HomoplasyCounter(num_replicates=128, seed=9, full_planes=full, min_hcount=seed % 2)
+        hc.set_tree(tree.parent, tree.is_leaf)
+        hc.set_phenos(sn, lab)
+        hc.set_planes(B0, B1, V, S, tile_words=5, compact=True)
+        ev, cc = hc.count_all_homoplasy_events()
+        assert hc.timings()["plane_mode"] == (2 if full else 1)
+        assert_events_equal(ev, cc, or_ev, or_cc)
+        rs, rn = hc.raw_events()
+        assert not np.any(np.asarray(tree.parent)[rn] == tree.root), "a child of the root is never an MRCA (HC.java:1674)"
+        order = np.lexsort((rn, rs))
+        off, idx = hc.event_csr()
+        csr = [sorted(idx[off[i]:off[i + 1]].tolist()) for i in range(len(off) - 1)]
+        try:
+            st, mt = hc.assoc()
+            tail = (st.tobytes(), mt.tobytes())
+        except pb.NoInformativeSites:
+            tail = None
+        res.append((ev.tobytes(), cc, rs[order].tobytes(), rn[order].tobytes(), csr, tail))
+        hc.close()
+    assert res[0] == res[1]
+
+
 def test_one_plane_mode_partial_upload_and_reuse(oracle_mod):
     """Columns nobody uploaded hold no valid genotype in either storage mode; a context re-used for a second alignment of
     the same shape keeps working; a full-plane tile arriving late promotes the context without losing earlier tiles."""
