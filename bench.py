@@ -253,6 +253,7 @@ def run_b200(args):
         return hc.timings()
 
     e2e_parts = {"put_planes": 0.0, "events": 0.0, "assoc": 0.0}
+    e2e_steps = []                                       # wall ms of every end-to-end step on this rank (an outlier shows here)
 
     def step_e2e(use_compact=True):
         t0 = time.perf_counter()
@@ -263,6 +264,7 @@ def run_b200(args):
         st, mt = hc.assoc()                              # D2H: per-informative-site statistics + sorted maxT
         t3 = time.perf_counter()
         e2e_parts["put_planes"] += 1e3 * (t1 - t0); e2e_parts["events"] += 1e3 * (t2 - t1); e2e_parts["assoc"] += 1e3 * (t3 - t2)
+        e2e_steps.append(round(1e3 * (t3 - t0), 3))
         return hc.timings(), ev, st, mt
 
     for _ in range(args.warmup):
@@ -317,17 +319,19 @@ def run_b200(args):
     value = total_sites * args.steps / (dev_ms / 1e3)
 
     # ---- timed: end to end through the public API with host buffers ------------------------------------
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(min(args.warmup, 3)):
         step_e2e()
     barrier()
     for k in e2e_parts:
         e2e_parts[k] = 0.0
+    del e2e_steps[:]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         tm_e, ev, st, mt = step_e2e()
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
     e2e_breakdown = {k: v / args.steps for k, v in e2e_parts.items()}
+    e2e_step_ms = list(e2e_steps)
     h2d_full = 3 * N * Wp * 8                             # what pb_put_planes copies (rows padded to the device pitch)
     h2d = h2d_full
     e2e_full = None
@@ -372,7 +376,7 @@ def run_b200(args):
                 "config": bench_config(args, cfg, S, m, tree, world),
                 "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps,
-                        "breakdown_ms": e2e_breakdown, "timer": "host wall clock around synchronous C-ABI calls, max over ranks",
+                        "breakdown_ms": e2e_breakdown, "ms_steps_rank0": e2e_step_ms, "timer": "host wall clock around synchronous C-ABI calls, max over ranks",
                         "upload": ("pb_put_planes_biallelic (%s; host-side compaction %.2f s once, outside the timed region like "
                                    "the FASTA packing)" % ("X plane + site masks, kept as one plane in HBM" if compact[2] else
                                                            "X + V planes + site masks, expanded to three planes on the device", t_compact))

@@ -124,7 +124,8 @@ void pb_destroy(pb_ctx* ctx);
 const char* pb_last_error(pb_ctx* ctx);
 
 /* NewickTree flattened by the host: parent index per node (root = -1), leaf flags.
- * Any node order; the host keeps the name table.  Replaces the tree argument of HC.java:1402. */
+ * Any node order; the host keeps the name table.  Replaces the tree argument of HC.java:1402.
+ * Limits: 2 <= n_nodes <= 2^28 - 2, fewer than 2^24 leaves. */
 int pb_set_tree(pb_ctx* ctx, int32_t n_nodes, const int32_t* parent, const uint8_t* is_leaf);
 
 /* `phenos` (HC.java:1972-2019) flattened: one entry per pheno-file row in file order:
