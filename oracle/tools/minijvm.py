@@ -8,8 +8,8 @@ reaches (`BinomialTest.binomialTest` -> `BinomialDistribution.cumulativeProbabil
 `Beta.regularizedBeta` -> `ContinuedFraction.evaluate`, `Gamma.*`, `FastMath.exp/log/log1p`)
 directly from the jar and emits golden vectors (see `gen_binom_golden.py`).
 
-It is NOT a general JVM: no threads, no exceptions tables, no invokedynamic, no JDK class
-library beyond a few `java.lang.Double/Math` natives.  Objects of classes outside the jar
+It is NOT a general JVM: no threads, no exceptions tables, no invokedynamic (refjvm.py adds the
+two bootstrap kinds javac emits), no JDK class library beyond a few `java.lang.Double/Math` natives.  Objects of classes outside the jar
 are opaque.  Python `float` is IEEE-754 binary64, Java's `double` arithmetic (strict, no
 FMA contraction) maps 1:1 onto it.
 
@@ -355,6 +355,9 @@ class MiniJVM:
             raise NotImplementedError(f"abstract/native {cname}.{name}{desc}")
         return self.run(m, args)
 
+    def invokedynamic(self, cf, cp_index, st):
+        raise NotImplementedError("invokedynamic")   # refjvm.RefJVM implements LambdaMetafactory / StringConcatFactory sites
+
     # ------------------------------------------------------------------ interpreter loop
     def run(self, m: Method, args):
         code = m.code
@@ -680,7 +683,7 @@ class MiniJVM:
                     push(r)
                 pc += 5 if op == 0xB9 else 3
             elif op == 0xBA:
-                raise NotImplementedError("invokedynamic")
+                self.invokedynamic(cf, u2(pc + 1), st); pc += 5   # hook: pops the call site's arguments, pushes its result
             elif op == 0xBB:
                 cname = cf.utf(cp[u2(pc + 1)][1])
                 if self.has_class(cname):

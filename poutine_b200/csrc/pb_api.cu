@@ -220,15 +220,16 @@ static int build_program(pb_ctx* ctx, bool xprog, int64_t cols_per_block, int64_
             close((uint32_t)n_flush++);   // closes the open record (possibly empty) with the flush attached
             seg_leaves = 0;
         };
-        for (int64_t i = l0; xprog && i < l1; i++) {
+        for (int64_t i = l0; i < l1; i++) {
             const int32_t child = ctx->lop_child[i], par = ctx->lop_parent[i];
-            const uint32_t fl = PB_OPX_TEST | (par == ctx->root ? PB_OPX_NOMRCA : 0u);   // HC.java:1674: never an MRCA, but part of the census sum
-            if (cur != par) { push(PB_OPX_SETCUR | (uint32_t)par); cur = par; }
-            if (ctx->is_leaf[child]) push(PB_OPX_LEAF | fl | (uint32_t)child);
-            else { push(PB_OPX_SETCUR | fl | (uint32_t)child); cur = child; }
-        }
-        for (int64_t i = l0; !xprog && i < l1; i++) {
-            const int32_t child = ctx->lop_child[i], par = ctx->lop_parent[i];
+            if (xprog) {
+                // every edge tested; an edge hanging off the root never makes an MRCA (HC.java:1674) but is part of the census sum
+                const uint32_t fl = PB_OPX_TEST | (par == ctx->root ? PB_OPX_NOMRCA : 0u);
+                if (cur != par) { push(PB_OPX_SETCUR | (uint32_t)par); cur = par; }
+                if (ctx->is_leaf[child]) push(PB_OPX_LEAF | fl | (uint32_t)child);
+                else { push(PB_OPX_SETCUR | fl | (uint32_t)child); cur = child; }
+                continue;
+            }
             const bool test = par != ctx->root;     // edges hanging off the root are never tested (HC.java:1674)
             if (test && cur != par) { push(PB_OP_SETCUR | (uint32_t)par); cur = par; }
             if (ctx->is_leaf[child]) {
@@ -252,16 +253,22 @@ static int build_program(pb_ctx* ctx, bool xprog, int64_t cols_per_block, int64_
     return upload(ctx, d_chunk_op, chunk_op);
 }
 
-// two programs over the same edge list: one per sweep kernel (their grids differ), one census buffer for both
+// two lowerings of the same edge list: one per sweep kernel (their grids and op sets differ)
 static int build_chunks(pb_ctx* ctx) {
     if (ctx->N == 0 || ctx->W == 0) return PB_OK;
     int rc;
     if ((rc = build_program(ctx, false, PB_K1_COLS, PB_K1_BLOCKS_PER_SM, &ctx->d_ops, &ctx->d_chunk_op, &ctx->n_chunks, &ctx->n_flush))) return rc;
     if ((rc = build_program(ctx, true, pbk_kx_cols(), pbk_kx_blocks_per_sm(), &ctx->d_ops_x, &ctx->d_chunk_op_x, &ctx->n_chunks_x, &ctx->n_flush_x))) return rc;
+    // the census partials belong to the three-plane sweep only: allocated at its first run (ensure_census)
     if (ctx->d_census) { cudaFree(ctx->d_census); ctx->d_census = nullptr; }
-    PB_CUDA(cudaMalloc(&ctx->d_census, (size_t)4 * ctx->n_flush * PB_K1_KS * ctx->W * 8));
     if (ctx->d_census_total) { cudaFree(ctx->d_census_total); ctx->d_census_total = nullptr; }
-    PB_CUDA(cudaMalloc(&ctx->d_census_total, (size_t)4 * PB_K1_KT * ctx->W * 8));
+    return PB_OK;
+}
+
+static int ensure_census(pb_ctx* ctx) {
+    if (ctx->d_census && ctx->d_census_total) return PB_OK;
+    if (!ctx->d_census) PB_CUDA(cudaMalloc(&ctx->d_census, (size_t)4 * ctx->n_flush * PB_K1_KS * ctx->W * 8));
+    if (!ctx->d_census_total) PB_CUDA(cudaMalloc(&ctx->d_census_total, (size_t)4 * PB_K1_KT * ctx->W * 8));
     return PB_OK;
 }
 
@@ -518,6 +525,7 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
     if (ctx->plane_mode == PB_PLANES_NONE) { int rc0 = ensure_plane_mode(ctx, PB_PLANES_FULL); if (rc0) return rc0; }   // nothing uploaded: no valid genotype anywhere
     ctx->tm = pb_timings{};
     int rc;
+    if (ctx->plane_mode == PB_PLANES_FULL && (rc = ensure_census(ctx))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev[12], ctx->stream));
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = pbk_prepare_tail(ctx))) return rc;

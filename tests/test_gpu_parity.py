@@ -73,6 +73,46 @@ def test_hand_fixture_events(oracle_mod, golden_dir):
     assert (cc["mono"], cc["bi"], cc["tri"], cc["quad"], cc["no_allele"]) == (want["mono"], want["bi"], want["tri"], want["quad"], want["other"])
 
 
+def test_events_match_reference_bytecode(golden_dir):
+    """CUDA path against tests/golden/events_refbytecode.json — outputs of the reference's own compiled
+    count_all_homoplasy_events (Homoplasy_Counter.class run by oracle/tools/refjvm.py): Homoplasy_Events fields, class
+    counters and, where neither bucket was cleared, the exact MRCA node sets.  The all-valid biallelic case runs in both
+    storage modes (k1x_events_kernel and k1_events_kernel)."""
+    from tests.test_oracle_events import refbytecode_cases
+    for c, chars in refbytecode_cases(golden_dir):
+        parent = np.asarray(c["parent"], dtype=np.int32)
+        is_leaf = np.zeros(len(parent), dtype=np.uint8)
+        is_leaf[c["leaf_nodes"]] = 1
+        names = np.asarray(c["names"])
+        root = int(np.where(parent < 0)[0][0])
+        S = chars.shape[1]
+        modes = [dict(compact=False)] if c["name"] != "biallelic_all_valid" else [dict(compact=True), dict(compact=True, full_planes=True)]
+        for mode in modes:
+            hc = pb.HomoplasyCounter(num_replicates=10, full_planes=mode.get("full_planes", False))
+            hc.set_tree(parent, is_leaf)
+            hc.set_planes(*pb.pack_chars(chars), S, compact=mode["compact"])
+            ev, cc = hc.count_all_homoplasy_events()
+            if c["name"] == "biallelic_all_valid":
+                assert hc.timings()["plane_mode"] == (2 if mode.get("full_planes") else 1)
+            want_cc = c["class_counts"]
+            assert (cc["bi"], cc["mono"], cc["tri"], cc["quad"], cc["no_allele"]) == tuple(want_cc[k] for k in ("bi", "mono", "tri", "quad", "other"))
+            assert len(ev) == len(c["events"])
+            site, node = hc.raw_events()
+            sets = {}
+            for s_, v in zip(site.tolist(), node.tolist()):
+                sets.setdefault(s_ + 1, set()).add(v)
+            for e, r in zip(ev, c["events"]):
+                got = [int(e["segsite_id"]), chr(e["allele1"]), chr(e["allele2"]), int(e["a1_count"]), int(e["a2_count"]),
+                       int(e["a1_extant"]), int(e["a2_extant"])]
+                assert got == [r[k] for k in ("segsite_id", "allele1", "allele2", "a1_count", "a2_count", "a1_extant", "a2_extant")], (c["name"], r["segsite_id"])
+                want = set(r["a1_mrcas"]) | set(r["a2_mrcas"])
+                have = set(names[sorted(sets.get(r["segsite_id"], set()))].tolist())
+                assert want - {names[root]} <= have, (c["name"], r["segsite_id"])
+                if r["a1_count"] >= 2 and r["a2_count"] >= 2:
+                    assert want - {names[root]} == have, (c["name"], r["segsite_id"])
+            hc.close()
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_events_nasty_random_trees(oracle_mod, seed):
     """polytomies, leaves on the root, shuffled node ids; gaps, lowercase, third alleles, ties, N at root"""

@@ -27,6 +27,37 @@ def test_hand_derived_fixture(oracle_mod, golden_dir):
     assert cc == fx["class_counts"]
 
 
+def refbytecode_cases(golden_dir):
+    """tests/golden/events_refbytecode.json: what the reference's own compiled count_all_homoplasy_events produced
+    (executed from Homoplasy_Counter.class by oracle/tools/refjvm.py, see gen_events_refbytecode_golden.py)."""
+    with open(os.path.join(golden_dir, "events_refbytecode.json")) as f:
+        fx = json.load(f)
+    for c in fx["cases"]:
+        chars = np.array([[ord(ch) for ch in row] for row in c["rows"]], dtype=np.uint8)
+        yield c, chars
+
+
+def test_oracle_matches_reference_bytecode(oracle_mod, golden_dir):
+    """THE pin of rows a1-a5: every Homoplasy_Events field, both MRCA node sets and the class counters the reference logs,
+    for 5 seeded alignments on nasty topologies, as computed by the reference's bytecode."""
+    n_sites = 0
+    for c, chars in refbytecode_cases(golden_dir):
+        o = oracle_mod.Oracle(c["parent"], c["leaf_nodes"])
+        ev, cc = o.count_all_homoplasy_events(chars, np.asarray(c["physical_pos"], dtype=np.int32))
+        assert cc == c["class_counts"], c["name"]
+        assert len(ev) == len(c["events"]), c["name"]
+        names = np.asarray(c["names"])
+        for i, (e, r) in enumerate(zip(ev, c["events"])):
+            got = [int(e["segsite_id"]), int(e["physical_pos"]), chr(e["allele1"]), chr(e["allele2"]), int(e["a1_count"]),
+                   int(e["a2_count"]), int(e["a1_extant"]), int(e["a2_extant"])]
+            want = [r[k] for k in ("segsite_id", "physical_pos", "allele1", "allele2", "a1_count", "a2_count", "a1_extant", "a2_extant")]
+            assert got == want, (c["name"], i)
+            assert sorted(names[o.mrca(i, 0)].tolist()) == r["a1_mrcas"], (c["name"], i)
+            assert sorted(names[o.mrca(i, 1)].tolist()) == r["a2_mrcas"], (c["name"], i)
+        n_sites += len(ev)
+    assert n_sites > 400
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_literal_walk_equals_closed_form(oracle_mod, seed):
     tree = synth.random_tree(12 + 5 * seed, 100 + seed, polytomy=0.3, root_leaf_children=seed % 3)
