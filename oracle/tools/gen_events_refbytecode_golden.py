@@ -1,4 +1,5 @@
-"""Generate tests/golden/events_refbytecode.json: outputs of the REFERENCE'S OWN BYTECODE for entry point 1.
+"""Generate tests/golden/events_refbytecode.json and tests/golden/assoc_refbytecode.json: outputs of the REFERENCE'S OWN
+BYTECODE for both entry points of the hot path.
 
 `count_all_homoplasy_events(tree, seg_sites, physical_poss)` (HC.java:1402) is executed from
 /root/reference/compiled/Homoplasy_Counter.class (+ coevolution.jar's NewickTree classes) by the bytecode interpreter
@@ -9,7 +10,17 @@ nodes, ties in the allele census, tri- and quad-allelic and all-missing sites, p
 (HC.java:5531-5550) and both MRCA node-name sets; per case the class counters the reference wrote to its log
 (HC.java:1477-1480).  The script refuses to write the fixture unless the C++ oracle reproduces all of it.
 
-This is what pins the oracle (and through it the CUDA path) for rows a1-a5 of SURVEY.md section 8.
+Entry point 2, `assoc(all_events, phenos)` (HC.java:2029 -> 2096), runs on the very Homoplasy_Events objects entry point 1
+left in the interpreter: subset_by_min_hcount (HC.java:3783), then the live resampling driver (HC.java:3013) with
+commons-math 3.6.1's BinomialTest executed from ITS jar, m Replicate.run() calls (HC.java:3229), the point-wise and the
+family-wise estimates.  Collections.shuffle draws from a seeded java.util.Random and the replicates run serially (the two
+things the JDK leaves open, see refjvm.ReferenceEvents.assoc); every shuffle is recorded as a permutation of the
+pheno-file rows, which is what the oracle's and the GPU's replay mode consume.  assoc_refbytecode.json keeps, per
+informative site, obs_counts and every Binomial_Test_Stat field (HC.java:5876-5887, doubles as IEEE-754 bit patterns),
+the unsorted and sorted maxT arrays and the permutations.  Again the fixture is only written if the oracle reproduces
+all of it bit for bit.
+
+This is what pins the oracle (and through it the CUDA path) for rows a1-a11 of SURVEY.md section 8.
 
 run (in the authoring container, needs /root/reference):  python oracle/tools/gen_events_refbytecode_golden.py
 """
@@ -31,12 +42,22 @@ from poutine_b200 import synth  # noqa: E402
 
 CASES = [
     # name, tree kwargs, sites, char kwargs
-    dict(name="nasty_small", leaves=14, tseed=701, polytomy=0.3, root_leaf_children=2, S=160, cseed=801, nasty=True),
-    dict(name="nasty_mid", leaves=60, tseed=702, polytomy=0.25, root_leaf_children=1, S=130, cseed=802, nasty=True),
-    dict(name="nasty_polytomies", leaves=45, tseed=703, polytomy=0.6, root_leaf_children=3, S=110, cseed=803, nasty=True),
-    dict(name="binary_no_root_leaves", leaves=80, tseed=704, polytomy=0.0, root_leaf_children=0, S=100, cseed=804, nasty=True),
-    dict(name="biallelic_all_valid", leaves=70, tseed=705, polytomy=0.2, root_leaf_children=2, S=140, cseed=805, nasty=False),
+    dict(name="nasty_small", leaves=14, tseed=701, polytomy=0.3, root_leaf_children=2, S=160, cseed=801, nasty=True,
+         m=120, min_hcount=1, na_frac=0.1, no_row_frac=0.1),
+    dict(name="nasty_mid", leaves=60, tseed=702, polytomy=0.25, root_leaf_children=1, S=130, cseed=802, nasty=True,
+         m=100, min_hcount=1, na_frac=0.05, no_row_frac=0.03),
+    dict(name="nasty_polytomies", leaves=45, tseed=703, polytomy=0.6, root_leaf_children=3, S=110, cseed=803, nasty=True,
+         m=100, min_hcount=0, na_frac=0.0, no_row_frac=0.05),
+    dict(name="binary_no_root_leaves", leaves=80, tseed=704, polytomy=0.0, root_leaf_children=0, S=100, cseed=804, nasty=True,
+         m=80, min_hcount=2, na_frac=0.04, no_row_frac=0.0),
+    dict(name="biallelic_all_valid", leaves=70, tseed=705, polytomy=0.2, root_leaf_children=2, S=140, cseed=805, nasty=False,
+         m=100, min_hcount=1, na_frac=0.0, no_row_frac=0.0),
 ]
+
+
+def bits(x):
+    return "%016x" % int(np.float64(x).view(np.uint64))
+
 
 
 def names_of(tree):
@@ -78,18 +99,64 @@ def run_case(c):
         assert sorted(name_arr[o.mrca(i, 1)].tolist()) == r["a2_mrcas"], (c["name"], i, "a2 set")
     print("%-24s N=%3d S=%3d biallelic %3d  %.1f s, %d bytecodes: oracle == reference bytecode" %
           (c["name"], tree.n_nodes, S, len(ev), dt, ref.vm.n_bytecodes))
-    return {"name": c["name"], "names": names, "parent": parent, "leaf_nodes": [int(v) for v in tree.leaf_nodes],
-            "physical_pos": pos, "rows": ["".join(map(chr, row)) for row in chars.tolist()],
-            "class_counts": {"bi": counts["bi-allelic"], "mono": counts["monomorphic"], "tri": counts["tri-allelic"],
-                             "quad": counts["quad-allelic"], "other": S - sum(counts.values())},
-            "log": log, "events": ev}
+    ev_case = {"name": c["name"], "names": names, "parent": parent, "leaf_nodes": [int(v) for v in tree.leaf_nodes],
+               "physical_pos": pos, "rows": ["".join(map(chr, row)) for row in chars.tolist()],
+               "class_counts": {"bi": counts["bi-allelic"], "mono": counts["monomorphic"], "tri": counts["tri-allelic"],
+                                "quad": counts["quad-allelic"], "other": S - sum(counts.values())},
+               "log": log, "events": ev}
+
+    # ---- entry point 2 on the same interpreter state
+    m, mh = c["m"], c["min_hcount"]
+    sample_node, label = synth.simulate_phenotypes(tree, c["tseed"] + 50, na_frac=c["na_frac"], no_row_frac=c["no_row_frac"])
+    label_str = [{0: "0", 1: "1"}.get(int(x), "NA") for x in label]
+    t0 = time.time()
+    n0 = ref.vm.n_bytecodes
+    ra = ref.assoc([names[int(v)] for v in sample_node], label_str, m, mh, shuffle_seed=9000 + c["tseed"])
+    dt = time.time() - t0
+    perms = np.asarray(ra["perms"], dtype=np.uint32)
+    for r in range(m):
+        assert sorted(perms[r].tolist()) == list(range(len(label)))
+    st, mt_s, mt_u = o.assoc(sample_node, label, m, mh, perms=perms)
+    assert bits(o.p_success) == bits(ra["p_success"])
+    assert len(st) == len(ra["sites"]), (len(st), len(ra["sites"]))
+    assert [bits(x) for x in mt_u] == [bits(x) for x in ra["maxT_unsorted"]], "per-replicate min p (maxT) differs"
+    assert [bits(x) for x in mt_s] == [bits(x) for x in ra["maxT_sorted"]]
+    rows = []
+    for srow, r in zip(st, ra["sites"]):
+        assert int(srow["segsite_id"]) == r["segsite_id"] and int(srow["a1_in_use"]) == r["a1_in_use"] and int(srow["a2_in_use"]) == r["a2_in_use"]
+        assert srow["obs_counts"].tolist() == r["obs_counts"], (c["name"], r["segsite_id"], srow["obs_counts"], r["obs_counts"])
+        for k in ("r_a1", "r_a2", "r_maxT_a1", "r_maxT_a2"):
+            assert int(srow[k]) == r[k], (c["name"], r["segsite_id"], k, int(srow[k]), r[k])
+        row = {k: r[k] for k in ("segsite_id", "a1_in_use", "a2_in_use", "obs_counts", "r_a1", "r_a2", "r_maxT_a1", "r_maxT_a2")}
+        for ko, kr in (("obs_p_a1", "obs_binom_pvalue_a1"), ("obs_p_a2", "obs_binom_pvalue_a2"), ("pointwise_a1", "pointwise_pvalue_a1"),
+                       ("pointwise_a2", "pointwise_pvalue_a2"), ("familywise_a1", "familywise_pvalue_a1"), ("familywise_a2", "familywise_pvalue_a2")):
+            a, b = float(srow[ko]), r[kr]
+            assert (a != a and b != b) or bits(a) == bits(b), (c["name"], r["segsite_id"], ko, a, b)
+            row[ko] = bits(b)
+        rows.append(row)
+    print("%-24s assoc: P=%3d m=%3d min_hcount=%d informative %3d  %.1f s, %d bytecodes: oracle == reference bytecode (bit for bit)" %
+          ("", len(label), m, mh, len(rows), dt, ref.vm.n_bytecodes - n0))
+    as_case = {"name": c["name"], "m": m, "min_hcount": mh, "shuffle_seed": 9000 + c["tseed"],
+               "sample_node": [int(v) for v in sample_node], "label": [int(x) for x in label], "p_success": bits(ra["p_success"]),
+               "perms": perms.tolist(), "sites": rows, "maxT_unsorted": [bits(x) for x in ra["maxT_unsorted"]],
+               "maxT_sorted": [bits(x) for x in ra["maxT_sorted"]]}
+    return ev_case, as_case
 
 
 if __name__ == "__main__":
+    both = [run_case(c) for c in CASES]
     out = {"source": "count_all_homoplasy_events executed from /root/reference/compiled/Homoplasy_Counter.class + coevolution.jar by "
                      "oracle/tools/refjvm.py (bytecode interpreter; JDK collections emulated with HashMap's iteration order)",
-           "cases": [run_case(c) for c in CASES]}
+           "cases": [b[0] for b in both]}
     path = os.path.join(ROOT, "tests", "golden", "events_refbytecode.json")
+    with open(path, "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print(path, os.path.getsize(path), "bytes")
+    out = {"source": "subset_by_min_hcount + resample_all_mutations_binom_test_combined_nulldists_memoization_concurrent executed from "
+                     "/root/reference/compiled/*.class + commons-math3-3.6.1.jar by oracle/tools/refjvm.py on the events of "
+                     "events_refbytecode.json (same case names); replicates serial, Collections.shuffle seeded; doubles as hex bit patterns",
+           "cases": [b[1] for b in both]}
+    path = os.path.join(ROOT, "tests", "golden", "assoc_refbytecode.json")
     with open(path, "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print(path, os.path.getsize(path), "bytes")

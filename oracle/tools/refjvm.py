@@ -24,7 +24,7 @@ import os
 import struct
 import zipfile
 
-from minijvm import ClassFile, JArray, JObject, JLong, JFloat, MiniJVM, parse_desc, _i32
+from minijvm import NATIVES, ClassFile, JArray, JObject, JLong, JFloat, MiniJVM, parse_desc, _i32, _i64
 
 REF = "/root/reference/compiled"
 NODE = "org/gersteinlab/coevolution/core/data/NewickTreeNode"
@@ -181,6 +181,70 @@ class JCollectorGroupingBy:
         self.fn = fn
 
 
+class JDouble:
+    """java.lang.Double (boxed: one stack slot, unlike the primitive, which the interpreter keeps as a python float)"""
+    __slots__ = ("v",)
+
+    def __init__(self, v):
+        self.v = float(v)
+
+
+class JBoxedLong:
+    """java.lang.Long (boxed)"""
+    __slots__ = ("v",)
+
+    def __init__(self, v):
+        self.v = int(v)
+
+
+class JStringBuilder:
+    def __init__(self):
+        self.parts = []
+
+
+class JDoubleStream:
+    def __init__(self, items):
+        self.items = items
+
+
+class JOptionalDouble:
+    def __init__(self, v):
+        self.v = v
+
+
+class JLatch:
+    def __init__(self, n):
+        self.n = n
+
+
+class JOpaque:
+    """a JDK object the path only passes around (ZonedDateTime, Duration, ExecutorService, Runtime)"""
+    def __init__(self, what):
+        self.what = what
+
+
+class JavaRandom:
+    """java.util.Random (the documented LCG) — stands in for the unseeded static Random inside Collections.shuffle(List)"""
+    def __init__(self, seed):
+        self.seed = (seed ^ 0x5DEECE66D) & ((1 << 48) - 1)
+
+    def next(self, bits):
+        self.seed = (self.seed * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+        return _i32(self.seed >> (48 - bits))
+
+    def next_int(self, bound):
+        r = self.next(31)
+        m = bound - 1
+        if (bound & m) == 0:
+            return _i32((bound * r) >> 31)
+        u = r
+        while True:
+            r = u % bound
+            if _i32(u - r + m) >= 0:
+                return r
+            u = self.next(31)
+
+
 class JWriter:
     """BufferedWriter / PrintStream sink: keeps what was written"""
     def __init__(self):
@@ -201,6 +265,8 @@ def jstr(v, desc_char=None):
         return v
     if isinstance(v, JChar):
         return chr(v.v)
+    if isinstance(v, JBoxedLong):
+        return str(v.v)
     if desc_char == "C":
         return chr(v)
     if desc_char == "Z":
@@ -271,8 +337,15 @@ def parse_indy(cf: ClassFile):
 # ----------------------------------------------------------------------------- the VM
 class RefJVM(MiniJVM):
     def __init__(self):
-        self.jar = zipfile.ZipFile(os.path.join(REF, "coevolution.jar"))
-        self.jar_names = set(self.jar.namelist())
+        self.jars = [zipfile.ZipFile(os.path.join(REF, j)) for j in ("coevolution.jar", "commons-math3-3.6.1.jar")]
+        self.jar_of = {}
+        for z in self.jars:
+            for nm in z.namelist():
+                if nm.endswith(".class"):
+                    self.jar_of.setdefault(nm, z)
+        self.shuffle_rng = None          # JavaRandom: the source of Collections.shuffle(List); set by the driver
+        self.shuffles = []               # every shuffle's result as (before, after) python lists
+        self.sorted_arrays = []          # (copy before, the JArray) of every Arrays.parallelSort(double[])
         self.classes = {}
         self.initialized = set()
         self.n_bytecodes = 0
@@ -281,16 +354,27 @@ class RefJVM(MiniJVM):
 
     # -- class loading: loose .class files of the reference + coevolution.jar
     def has_class(self, name):
-        return os.path.exists(os.path.join(REF, name + ".class")) or (name + ".class") in self.jar_names
+        return os.path.exists(os.path.join(REF, name + ".class")) or (name + ".class") in self.jar_of
 
     def load(self, name):
         c = self.classes.get(name)
         if c is None:
             p = os.path.join(REF, name + ".class")
-            data = open(p, "rb").read() if os.path.exists(p) else self.jar.read(name + ".class")
+            data = open(p, "rb").read() if os.path.exists(p) else self.jar_of[name + ".class"].read(name + ".class")
             c = ClassFile(data)
             self.classes[name] = c
-        self.initialized.add(name)      # no <clinit> of these classes is needed on this path (picocli statics stay untouched)
+        if name not in self.initialized:
+            self.initialized.add(name)
+            if c.super_name and self.has_class(c.super_name):
+                self.load(c.super_name)
+            if name == "Homoplasy_Counter":
+                # its <clinit> only sets $assertionsDisabled = !Homoplasy_Counter.class.desiredAssertionStatus(): a JVM started
+                # without -ea (poutine.sh does not pass it) runs with assertions disabled
+                c.static_fields["$assertionsDisabled"] = 1
+            else:
+                m = c.methods.get(("<clinit>", "()V"))
+                if m is not None:
+                    self.run(m, [])
         return c
 
     # -- invokedynamic
@@ -337,6 +421,12 @@ class RefJVM(MiniJVM):
 
     # -- method dispatch: reference bytecode first, JDK emulation for everything else
     def invoke(self, kind, cname, name, desc, args):
+        if name == "get_thread_pool_status" and cname == "Homoplasy_Counter":
+            return "[thread pool emulated: replicates run serially in submission order]"   # console decoration only (HC.java:3188-3227)
+        if args and isinstance(args[0], JArray) and name == "clone":
+            return JArray(list(args[0].data), args[0].kind)
+        if name == "ordinal" and desc == "()I" and args and isinstance(args[0], JObject) and "$ordinal" in args[0].fields:
+            return args[0].fields["$ordinal"]
         if kind in ("virtual", "interface", "special") and args and isinstance(args[0], JObject) and self.has_class(args[0].cls) \
                 and "$impl" not in args[0].fields:
             start = args[0].cls if kind != "special" else cname
@@ -356,10 +446,25 @@ class RefJVM(MiniJVM):
         return self.jdk(kind, cname, name, desc, args)
 
     def jdk(self, kind, cname, name, desc, args):
+        nat = NATIVES.get((cname, name, desc))           # java.lang.Double / Math statics of the numeric chain
+        if nat is not None:
+            return nat(args)
         # ---- constructors: the `new` opcode made an empty JObject shell; give it its emulation object
         if name == "<init>":
             o = args[0]
             if cname == "java/lang/Object":
+                return None
+            if cname == "java/lang/Enum":                # Enum(String name, int ordinal)
+                o.fields["$name"], o.fields["$ordinal"] = args[1], args[2]
+                return None
+            if cname == "java/util/concurrent/ConcurrentHashMap" and desc == "()V":
+                o.fields["$impl"] = JHashMap()           # no order-sensitive use: get / containsKey / put with String keys
+                return None
+            if cname == "java/util/concurrent/CountDownLatch":
+                o.fields["$impl"] = JLatch(args[1])
+                return None
+            if cname == "java/lang/StringBuilder" and desc == "()V":
+                o.fields["$impl"] = JStringBuilder()
                 return None
             if cname in ("java/util/HashMap", "java/util/LinkedHashMap"):
                 if cname != "java/util/HashMap":
@@ -394,6 +499,37 @@ class RefJVM(MiniJVM):
                 return JChar(args[0])
             if cname == "java/lang/Integer" and name == "valueOf":
                 return int(args[0])
+            if cname == "java/lang/Double" and name == "valueOf" and desc == "(D)Ljava/lang/Double;":
+                return JDouble(args[0])
+            if cname == "java/lang/Long" and name == "valueOf" and desc == "(J)Ljava/lang/Long;":
+                return JBoxedLong(args[0])
+            if cname == "java/lang/Runtime" and name == "getRuntime":
+                return JOpaque("runtime")
+            if cname == "java/util/concurrent/Executors" and name == "newFixedThreadPool":
+                return JOpaque("executor")
+            if cname == "java/time/ZonedDateTime" and name == "now":
+                return JOpaque("zoned-date-time")
+            if cname == "java/time/Duration" and name == "between":
+                return JOpaque("duration")
+            if cname == "java/lang/Math" and name == "toIntExact":
+                if not -(1 << 31) <= int(args[0]) < (1 << 31):
+                    raise RuntimeError("Math.toIntExact overflow")
+                return int(args[0])
+            if cname == "java/util/Arrays" and name == "parallelSort" and desc == "([D)V":
+                self.sorted_arrays.append((list(args[0].data), args[0]))
+                args[0].data.sort()                      # p-values in [0, 1]: no NaN / -0.0 ordering subtleties
+                return None
+            if cname == "java/util/Arrays" and name == "stream" and desc == "([D)Ljava/util/stream/DoubleStream;":
+                return JDoubleStream(list(args[0].data))
+            if cname == "java/util/Collections" and name == "shuffle" and desc == "(Ljava/util/List;)V":
+                lst = _impl(args[0])
+                before = list(lst.d)
+                rnd = self.shuffle_rng
+                for i in range(len(lst.d), 1, -1):       # JDK: for (int i = size; i > 1; i--) swap(list, i - 1, rnd.nextInt(i));
+                    j = rnd.next_int(i)
+                    lst.d[i - 1], lst.d[j] = lst.d[j], lst.d[i - 1]
+                self.shuffles.append((before, list(lst.d)))
+                return None
             if cname == "java/util/stream/Collectors" and name == "groupingBy" and len(args) == 1:
                 return JCollectorGroupingBy(args[0])
             if cname == "java/lang/String" and name == "format":
@@ -412,6 +548,58 @@ class RefJVM(MiniJVM):
                 self.console.text.append(a[0] if a else "")
                 return None
             raise NotImplementedError(("null receiver", cname, name, desc))
+        if isinstance(recv, JOpaque):
+            if recv.what == "runtime" and name == "availableProcessors":
+                return 1
+            if recv.what == "executor":
+                if name == "submit":                     # the Runnable runs here and now: serial, in submission order
+                    self.invoke("interface", "java/lang/Runnable", "run", "()V", [a[0]])
+                    return None
+                if name in ("shutdown",):
+                    return None
+                if name == "toString":
+                    return "[emulated executor]"
+            if recv.what == "duration":
+                if name == "toHours":
+                    return JLong(0)
+                if name in ("toMinutesPart", "toSecondsPart"):
+                    return 0
+            if name == "toString":
+                return "[" + recv.what + "]"
+        if isinstance(recv, JLatch):
+            if name == "countDown":
+                recv.n = max(0, recv.n - 1)
+                return None
+            if name == "await":
+                if recv.n != 0:
+                    raise RuntimeError("CountDownLatch.await with %d replicates outstanding" % recv.n)
+                return None
+            if name == "getCount":
+                return JLong(recv.n)
+            if name == "toString":
+                return "[latch %d]" % recv.n
+        if isinstance(recv, JStringBuilder):
+            if name == "append":
+                t = _arg_types(desc)[0]
+                recv.parts.append(jstr(a[0], t))
+                return args[0]
+            if name == "toString":
+                return "".join(recv.parts)
+        if isinstance(recv, JDouble):
+            if name == "doubleValue":
+                return recv.v
+        if isinstance(recv, JDoubleStream):
+            if name == "filter":
+                return JDoubleStream([x for x in recv.items if self.call_lambda(a[0], [x])])
+            if name == "count":
+                return JLong(len(recv.items))
+            if name == "min":
+                return JOptionalDouble(min(recv.items) if recv.items else None)
+        if isinstance(recv, JOptionalDouble):
+            if name == "getAsDouble":
+                if recv.v is None:
+                    raise RuntimeError("NoSuchElementException: a replicate with no allele in use")
+                return recv.v
         if isinstance(recv, JChar):
             if name == "charValue":
                 return recv.v
@@ -479,6 +667,10 @@ class RefJVM(MiniJVM):
                 return JIterator(recv.d)
             if name == "stream":
                 return JStream(list(recv.d))
+            if name == "addAll":
+                add = self._iterate(a[0])
+                recv.d.extend(add)
+                return int(bool(add))
             if name == "forEach":
                 for x in list(recv.d):
                     self.call_lambda(a[0], [x])
@@ -498,6 +690,8 @@ class RefJVM(MiniJVM):
         if isinstance(recv, JStream):
             if name == "filter":
                 return JStream([x for x in recv.items if self.call_lambda(a[0], [x])])
+            if name == "mapToDouble":
+                return JDoubleStream([self.call_lambda(a[0], [x]) for x in recv.items])
             if name == "collect" and isinstance(a[0], JCollectorGroupingBy):
                 # Collectors.groupingBy(f) = groupingBy(f, HashMap::new, toList()): a java.util.HashMap of ArrayLists,
                 # filled in encounter order
@@ -569,6 +763,9 @@ def _java_format(fmt, args):
                 out.append("%")
             elif c in "ds":
                 out.append(jstr(args[ai])); ai += 1
+            elif fmt[i + 1:i + 4] == "02d":
+                out.append("%02d" % int(args[ai].v if isinstance(args[ai], JBoxedLong) else args[ai])); ai += 1
+                i += 2
             else:
                 raise NotImplementedError("format %" + c)
             i += 2
@@ -628,6 +825,7 @@ class ReferenceEvents:
         m = vm.find_method("Homoplasy_Counter", "count_all_homoplasy_events",
                            "(L" + TREE + ";Ljava/util/HashMap;[I)Ljava/util/ArrayList;")
         res = vm.run(m, [hc, tree, seg, pos])
+        self.hc, self.all_events, self.log = hc, res, log
         out = []
         for he in _impl(res).d:
             f = he.fields
@@ -638,3 +836,67 @@ class ReferenceEvents:
                         "a1_extant": f.get("a1_count_extant_only", 0), "a2_extant": f.get("a2_count_extant_only", 0),
                         "a1_mrcas": a1, "a2_mrcas": a2})
         return out, "".join(log.text), "".join(vm.console.text)
+
+
+    # ---- entry point 2: assoc(all_events, phenos) -> HC.java:2029 -> 2096 -> subset_by_min_hcount + the live resampling driver
+    def assoc(self, sample_names, labels, m, min_hcount, shuffle_seed):
+        """Runs, from the reference's bytecode and on the Homoplasy_Events objects the run() above left in the VM:
+        subset_by_min_hcount (HC.java:3783) and resample_all_mutations_binom_test_combined_nulldists_memoization_concurrent
+        (HC.java:3013: observed counts and binomial p-values — commons-math 3.6.1's own bytecode —, m Replicate.run() calls,
+        point-wise and family-wise estimates).  Two things are supplied from outside, because the JDK leaves them open:
+        the thread pool runs the replicates one after the other in submission order (the reference's `r++` races make
+        the serial result the only defined one), and Collections.shuffle(List) draws from a java.util.Random seeded with
+        `shuffle_seed` instead of an unseeded one.  Every shuffle is recorded, so the same label arrangements can be
+        replayed through the oracle and the GPU.
+        labels: the pheno-file strings ("1", "0", anything else = missing), one per sample, in file order.
+        -> dict(p_success, sites=[...], maxT_unsorted, maxT_sorted, perms (m x P indices into `labels`), log)"""
+        vm, hc = self.vm, self.hc
+        phenos = vm.new("java/util/HashMap")
+        for nm, lab in zip(sample_names, labels):
+            vm.call(phenos, "put", "(Ljava/lang/Object;Ljava/lang/Object;)Ljava/lang/Object;", nm, lab)
+        # what read_phenos (HC.java:1999-2007) leaves behind
+        hc.fields["tot_num_sample_cases"] = sum(1 for x in labels if x == "1")
+        hc.fields["tot_num_sample_controls"] = sum(1 for x in labels if x == "0")
+        # instance initialisers of Homoplasy_Counter (HC.java:167-181): the live configuration
+        hc.fields["EXTANT_NODES_ONLY"] = 1
+        hc.fields["m"] = int(m)
+        alt = "org/apache/commons/math3/stat/inference/AlternativeHypothesis"
+        vm.load(alt)
+        hc.fields["TAIL_TYPE"] = vm.find_static_holder(alt, "GREATER_THAN").static_fields["GREATER_THAN"]
+        vm.load("Homoplasy_Counter$AlgoParams").static_fields["min_hcount"] = int(min_hcount)
+        vm.load("Homoplasy_Counter$RuntimeSettings").static_fields["num_threads"] = 1
+        vm.shuffle_rng = JavaRandom(shuffle_seed)
+        vm.shuffles, vm.sorted_arrays = [], []
+        sub = vm.call(hc, "subset_by_min_hcount", "(Ljava/util/ArrayList;I)Ljava/util/ArrayList;", self.all_events, int(min_hcount))
+        stats = vm.call(hc, "resample_all_mutations_binom_test_combined_nulldists_memoization_concurrent",
+                        "(Ljava/util/ArrayList;Ljava/util/HashMap;)[LHomoplasy_Counter$Binomial_Test_Stat;", sub, phenos)
+        p_success = vm.call(hc, "calc_background_p_success", "()D")
+        sites = []
+        for he, st in zip(_impl(sub).d, stats.data):
+            f, g = he.fields, st.fields
+            row = {"segsite_id": f["segsite_ID"], "a1_in_use": int(f.get("a1_in_use", 0)), "a2_in_use": int(f.get("a2_in_use", 0)),
+                   "obs_counts": [int(x) for x in f["obs_counts"].data]}
+            for k in ("r_a1", "r_a2", "r_maxT_a1", "r_maxT_a2"):
+                row[k] = int(g.get(k, 0))
+            for k in ("obs_binom_pvalue_a1", "obs_binom_pvalue_a2", "pointwise_pvalue_a1", "pointwise_pvalue_a2", "familywise_pvalue_a1",
+                      "familywise_pvalue_a2"):
+                row[k] = float(g[k])
+            sites.append(row)
+        assert len(vm.sorted_arrays) == 1 and len(vm.shuffles) == m
+        unsorted, arr = vm.sorted_arrays[0]
+        # the label arrangement of every replicate as a permutation of the pheno-file rows.  permute_phenos (HC.java:4890)
+        # lists the samples in phenos.entrySet() order, shuffles the label list and pairs them up again by position.
+        order = [c[0] for c in _impl(phenos).ordered()]          # sample names in HashMap iteration order
+        row_of = {nm: j for j, nm in enumerate(sample_names)}
+        perms = []
+        for before, after in vm.shuffles:
+            assert before == [labels[row_of[nm]] for nm in order]
+            pools = {}
+            for j, lab in enumerate(labels):                     # pheno-file rows carrying each label string, in file order
+                pools.setdefault(lab, []).append(j)
+            perm = [0] * len(labels)
+            for nm, lab in zip(order, after):                    # sample nm ends up with label string `lab`
+                perm[row_of[nm]] = pools[lab].pop(0)
+            perms.append(perm)
+        return {"p_success": p_success, "sites": sites, "maxT_unsorted": unsorted, "maxT_sorted": list(arr.data), "perms": perms,
+                "log": "".join(self.log.text)}

@@ -113,6 +113,30 @@ def test_events_match_reference_bytecode(golden_dir):
             hc.close()
 
 
+def test_assoc_matches_reference_bytecode(golden_dir):
+    """CUDA path in replay mode against tests/golden/assoc_refbytecode.json — what the reference's own compiled resampling
+    driver produced (commons-math's BinomialTest from its jar included) with the recorded shuffles: obs_counts, r counts,
+    per-replicate min p, sorted maxT, point-wise and family-wise estimates; every double bit for bit."""
+    from tests.test_oracle_events import assoc_refbytecode_cases, assert_stats_equal_refbytecode
+    for c, chars, a in assoc_refbytecode_cases(golden_dir):
+        parent = np.asarray(c["parent"], dtype=np.int32)
+        is_leaf = np.zeros(len(parent), dtype=np.uint8)
+        is_leaf[c["leaf_nodes"]] = 1
+        for compact in ((False, True) if c["name"] == "biallelic_all_valid" else (False,)):
+            hc = pb.HomoplasyCounter(num_replicates=a["m"], min_hcount=a["min_hcount"], replay=True)
+            hc.set_tree(parent, is_leaf)
+            hc.set_phenos(np.asarray(a["sample_node"], dtype=np.int32), np.asarray(a["label"], dtype=np.uint8))
+            hc.set_planes(*pb.pack_chars(chars), chars.shape[1], compact=compact)
+            hc.count_all_homoplasy_events()
+            st, mt = hc.assoc(replay_perms=np.asarray(a["perms"], dtype=np.uint32))
+            p_success = hc.timings().get("p_success")
+            if p_success is None:
+                n1, n0 = sum(1 for x in a["label"] if x == 1), sum(1 for x in a["label"] if x == 0)
+                p_success = np.float64(n1) / np.float64(n1 + n0)
+            assert_stats_equal_refbytecode(st, mt, hc.maxT_unsorted(), p_success, a)
+            hc.close()
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_events_nasty_random_trees(oracle_mod, seed):
     """polytomies, leaves on the root, shuffled node ids; gaps, lowercase, third alleles, ties, N at root"""

@@ -58,6 +58,53 @@ def test_oracle_matches_reference_bytecode(oracle_mod, golden_dir):
     assert n_sites > 400
 
 
+def _f64(hexbits):
+    return np.array([int(hexbits, 16)], dtype=np.uint64).view(np.float64)[0]
+
+
+def assert_stats_equal_refbytecode(st, mt_sorted, mt_unsorted, p_success, a):
+    """st / maxT arrays (oracle or GPU) against one case of tests/golden/assoc_refbytecode.json, doubles bit for bit"""
+    bits = lambda x: "%016x" % int(np.float64(x).view(np.uint64))
+    assert bits(p_success) == a["p_success"]
+    assert len(st) == len(a["sites"])
+    assert [bits(x) for x in mt_sorted] == a["maxT_sorted"]
+    if mt_unsorted is not None:
+        assert [bits(x) for x in mt_unsorted] == a["maxT_unsorted"]
+    for row, r in zip(st, a["sites"]):
+        tag = (a["name"], r["segsite_id"])
+        assert int(row["segsite_id"]) == r["segsite_id"], tag
+        assert (int(row["a1_in_use"]), int(row["a2_in_use"])) == (r["a1_in_use"], r["a2_in_use"]), tag
+        assert row["obs_counts"].tolist() == r["obs_counts"], tag
+        for k in ("r_a1", "r_a2", "r_maxT_a1", "r_maxT_a2"):
+            assert int(row[k]) == r[k], tag + (k,)
+        for k in ("obs_p_a1", "obs_p_a2", "pointwise_a1", "pointwise_a2", "familywise_a1", "familywise_a2"):
+            want = _f64(r[k])
+            assert (np.isnan(row[k]) and np.isnan(want)) or bits(row[k]) == r[k], tag + (k, float(row[k]), float(want))
+
+
+def assoc_refbytecode_cases(golden_dir):
+    """(events case, chars, assoc case) triples: assoc_refbytecode.json holds what the reference's compiled
+    subset_by_min_hcount + resampling driver (+ commons-math's own bytecode) produced on the events of the same-named case."""
+    with open(os.path.join(golden_dir, "assoc_refbytecode.json")) as f:
+        fa = {c["name"]: c for c in json.load(f)["cases"]}
+    for c, chars in refbytecode_cases(golden_dir):
+        yield c, chars, fa[c["name"]]
+
+
+def test_oracle_assoc_matches_reference_bytecode(oracle_mod, golden_dir):
+    """THE pin of rows a6-a11: observed tallies, binomial p-values, r counts, per-replicate min p, point-wise and
+    family-wise estimates of the reference's own bytecode, replayed through the oracle with the recorded shuffles."""
+    n = 0
+    for c, chars, a in assoc_refbytecode_cases(golden_dir):
+        o = oracle_mod.Oracle(c["parent"], c["leaf_nodes"])
+        o.count_all_homoplasy_events(chars, np.asarray(c["physical_pos"], dtype=np.int32))
+        st, mt_s, mt_u = o.assoc(np.asarray(a["sample_node"]), np.asarray(a["label"], dtype=np.uint8), a["m"], a["min_hcount"],
+                                 perms=np.asarray(a["perms"], dtype=np.uint32))
+        assert_stats_equal_refbytecode(st, mt_s, mt_u, o.p_success, a)
+        n += len(st)
+    assert n > 400
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_literal_walk_equals_closed_form(oracle_mod, seed):
     tree = synth.random_tree(12 + 5 * seed, 100 + seed, polytomy=0.3, root_leaf_children=seed % 3)
