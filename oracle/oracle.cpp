@@ -8,10 +8,18 @@
 // PARITY PIN STATUS
 //   * binomial p-values: PINNED — checked bit-for-bit against the commons-math3 3.6.1 bytecode
 //     executed by oracle/tools/minijvm.py (tests/golden/binom_golden.json).
-//   * event detection / tallies / permutation statistics: "parity unpinned" by the reference
-//     (it ships no tests, fixtures or golden outputs, and no JVM exists here to run it); this
-//     file is a literal restatement of the Java control flow, cross-checked against an
-//     independent closed form in tests/.
+//   * event detection (rows a1-a5 of SURVEY.md section 8): PINNED — the reference's own compiled
+//     count_all_homoplasy_events (compiled/Homoplasy_Counter.class + coevolution.jar) is executed by
+//     oracle/tools/refjvm.py (bytecode interpreter + JDK-collection emulation, HashMap iteration order
+//     included); tests/golden/events_refbytecode.json holds its outputs for 5 alignments on nasty
+//     topologies (every Homoplasy_Events field, both MRCA sets, the logged class counters) and this
+//     file reproduces all of them (tests/test_oracle_events.py).
+//   * observed tallies, binomial statistics, replicate counting, maxT, point-wise and family-wise
+//     estimates (rows a6-a11): PINNED the same way — subset_by_min_hcount and the live resampling
+//     driver run from the reference's bytecode, BinomialTest from commons-math's jar, with
+//     Collections.shuffle seeded and the replicates serial; tests/golden/assoc_refbytecode.json records
+//     the shuffles and the results, and this file reproduces every integer and every double bit for
+//     bit in replay mode.
 //
 // Deviations from a literal transcription (none change results):
 //   * nodes are integers, not name strings (HashMap<String,..> keyed by unique node names

@@ -5,8 +5,9 @@
     HC.java:1647-1698 / 1837-1888 / 1954-1962 and written below as literals; the script refuses
     to write the fixture unless the oracle reproduces every one of them.
 (2) c1_slice.npz — a C1-shaped slice (1,300 leaves x 2,000 sites, 2 % NA labels, replay mode with
-    Java-LCG permutations): inputs + the oracle's outputs.  "Parity unpinned" by the reference
-    (it ships no fixtures); this pins the GPU path to the oracle and the oracle to itself over time.
+    Java-LCG permutations): inputs + the oracle's outputs.  A regression fixture at a size the bytecode interpreter
+    cannot reach: it pins the GPU path to the oracle and the oracle to itself over time; the oracle itself is pinned to the
+    reference's bytecode by gen_events_refbytecode_golden.py.
 
 run:  python oracle/tools/gen_events_golden.py
 """
