@@ -148,15 +148,21 @@ def nexus_to_newick(path: str) -> str:
             break
     else:
         raise DataFormatError("no 'Begin Trees;' line in " + path)    # the reference dies with an NPE here
+    if i + 1 >= len(lines):
+        raise DataFormatError("no tree line after 'Begin Trees;' in " + path)
     s = lines[i + 1]
     k = s.find("(")
-    s = s[k:] if k >= 0 else s       # StringBuilder.delete(0, -1) throws in the reference; keep the line
+    if k < 0:                        # StringBuilder.delete(0, -1) throws in the reference
+        raise DataFormatError("the tree line of %s holds no '('" % path)
+    s = s[k:]
     while True:
         a = s.find("[")
         if a < 0:
             break
         b = s.find("]")
-        s = s[:a] + s[b + 1:] if b >= a else s[:a]
+        if b < a:      # StringBuilder.delete(start, end + 1) with end + 1 < start throws in the reference
+            raise DataFormatError("unbalanced '[' ... ']' annotation in the tree line of " + path)
+        s = s[:a] + s[b + 1:]
     return s
 
 
@@ -232,7 +238,11 @@ STAT_COLS = ("r_a1\tr_a2\tpointwise_pvalue_a1\tpointwise_pvalue_a2\tobs_binom_pv
 
 
 def java_double_str(x: float) -> str:
-    return "NaN" if x != x else _java_double_str(x)     # NaN is not a usable cache key (nan != nan)
+    if x != x:                                          # NaN is not a usable cache key (nan != nan) ...
+        return "NaN"
+    if x == 0:                                          # ... and -0.0 / 0.0 are the same key
+        return "-0.0" if math.copysign(1.0, x) < 0 else "0.0"
+    return _java_double_str(x)
 
 
 @functools.lru_cache(maxsize=1 << 20)     # p-values repeat massively: (r+1)/(m+1) and table entries
@@ -250,6 +260,13 @@ def _java_double_str(x: float) -> str:
     digits = "".join(map(str, dg)).lstrip("0")
     e10 = len(digits) - 1 + ex                            # decimal exponent of the first digit
     digits = digits.rstrip("0") or "0"
+    if len(digits) == 1:
+        # at least two digits are rendered and the two-digit decimal closest to x is chosen: differs from "shortest digit
+        # + 0" only for subnormals with a few bits (Double.MIN_VALUE prints as 4.9E-324)
+        two = "%.1e" % abs(x)
+        if float(two) == abs(x):
+            digits = (two[0] + two[2]).rstrip("0") or "0"
+            e10 = int(two.split("e")[1])
     if 1e-3 <= abs(x) < 1e7:
         if e10 >= 0:
             ipart = digits[:e10 + 1].ljust(e10 + 1, "0")
