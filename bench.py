@@ -143,7 +143,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 bit planes / int32 counts / f64 p-values", "data": "synthetic",
-            "config": bench_config(args, cfg, S, m, tree, 1),
+            # the b200 arm's config at this N (the workload named is the same; `sample` says what the CPU actually ran)
+            "config": bench_config(args, cfg, S, m, tree, max(int(args.gpus), 1)),
             "cpu_baseline": {"value": value, "unit": "sites/s", "cores": threads, "kind": "port", "sample": sample,
                              "seconds_events": l4 / args.steps, "seconds_assoc": l5 / args.steps},
             "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -37,8 +37,9 @@ struct Args {
     int32_t min_hcount = 1, threads = 0, device = 0;
     bool precomputed = false, overwrite = false, extras = false, have_seed = false;
     uint64_t seed = 0;
-    int64_t tile_sites = 1 << 17;
+    int64_t tile_sites = 1 << 15;
     bool compact_upload = true;
+    bool timing = false;       // --timing: phase wall clocks on stderr
 };
 
 [[noreturn]] void usage(const char* why) {
@@ -46,7 +47,7 @@ struct Args {
     std::fprintf(stderr,
                  "usage: poutine_b200_host -u -f <ancestral fasta> -t <ancestral newick | annotated_tree.nexus> -p <phenos> -m <map>\n"
                  "       [-r <# replicates>=100000] [-c <min_hcount>=1] [-T <# packer threads>] [-d <out dir>] [-o <out file>] [-X]\n"
-                 "       [--seed <n>] [--device <ordinal>] [--extras] [--tile-sites <n>] [--no-compact-upload]\n");
+                 "       [--seed <n>] [--device <ordinal>] [--extras] [--tile-sites <n>=32768] [--no-compact-upload] [--timing]\n");
     std::exit(2);
 }
 
@@ -89,7 +90,18 @@ struct RunResult {
     int64_t n_informative = 0, n_sites = 0, n_tiles = 0, n_compact_tiles = 0;
 };
 
+struct PhaseClock {
+    bool on;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        auto now = std::chrono::steady_clock::now();
+        if (on) std::fprintf(stderr, "[timing] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
+    PhaseClock clk{a.timing};
     const std::string text = read_file(a.tree);
     size_t k = 0;
     while (k < text.size() && std::isspace((unsigned char)text[k])) k++;
@@ -132,6 +144,7 @@ RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
         label.push_back(ph.labels[i] == "1" ? PB_LABEL_CASE : ph.labels[i] == "0" ? PB_LABEL_CONTROL : PB_LABEL_MISSING);
     }
 
+    clk.lap("loaders + fasta index");
     Options o;
     o.num_replicates = a.replicates;
     o.min_hcount = a.min_hcount;
@@ -141,10 +154,11 @@ RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
     hc.set_tree(tree.parent, tree.is_leaf);
     hc.set_phenos(sample_node, label);
     hc.set_sites(S);
+    clk.lap("context, tree, phenos, planes");
 
     // stream the alignment: tile t+1 is packed (and compacted, when all of its sites carry at most two bases) on a worker
     // thread while tile t uploads from the other page-locked buffer set
-    const int64_t tile_sites = std::max<int64_t>(64, a.tile_sites / 64 * 64);
+    const int64_t tile_sites = std::max<int64_t>(64, std::min(a.tile_sites, S + 63) / 64 * 64);
     const int64_t tw = tile_sites / 64;
     struct Buf {
         PinnedArray<uint64_t> B0, B1, V, X;
@@ -161,6 +175,7 @@ RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
         b.colmask.resize((size_t)(4 * tw));
     }
     const int64_t n_tiles = (S + tile_sites - 1) / tile_sites;
+    clk.lap("page-locked tile buffers");
     auto pack = [&](int64_t t) {
         Buf& b = bufs[t & 1];
         const int64_t s0 = t * tile_sites, ns = std::min(tile_sites, S - s0);
@@ -200,10 +215,14 @@ RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
         }
         if (worker.joinable()) worker.join();
     }
+    clk.lap("pack + upload (pipelined)");
     const pb_site_out* all_events = hc.count_all_homoplasy_events(&res.counts);     // HC.java:299
+    clk.lap("count_all_homoplasy_events");
     AssocResult as = hc.assoc();                                                    // HC.java:314
+    clk.lap("assoc");
     res.n_informative = (int64_t)as.stats.size();
     write_outputs(out_path, all_events, as.stats, physical_pos);
+    clk.lap("write_outputs");
     if (a.extras) {      // not a reference file: exact point-wise null + two-sided Fisher per informative site
         std::vector<double> ep, fp;
         hc.extras(ep, fp);
@@ -300,6 +319,7 @@ int main(int argc, char** argv) {
             else if (f == "--extras") a.extras = true;
             else if (f == "--tile-sites") a.tile_sites = std::atoll(val());
             else if (f == "--no-compact-upload") a.compact_upload = false;
+            else if (f == "--timing") a.timing = true;
             else if (f == "-h" || f == "--help") usage(nullptr);
             else usage(("unknown option " + f).c_str());
         }

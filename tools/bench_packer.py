@@ -66,6 +66,20 @@ try:
 except Exception as e:  # no GPU here
     out["files_in_files_out_s"] = None
     out["error"] = str(e)[:200]
+# the same run through the native host binary (process start and CUDA context creation included), files byte-compared
+exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "poutine_b200", "poutine_b200_host")
+if out["files_in_files_out_s"] is not None and os.path.exists(exe):
+    import subprocess
+    t0 = time.perf_counter()
+    r = subprocess.run([exe, "-u", "-f", fasta, "-t", os.path.join(d, "t.nwk"), "-p", os.path.join(d, "p.tsv"), "-m", os.path.join(d, "m.map"),
+                        "-r", "100000", "--seed", "1", "-d", d, "-o", "native.out", "-X"], capture_output=True, text=True)
+    out["native_host_files_in_files_out_s"] = time.perf_counter() - t0
+    out["native_host_rc"] = r.returncode
+    out["native_host_stdout_tail"] = r.stdout.strip().splitlines()[-1:] if r.returncode == 0 else r.stderr[-300:]
+    if r.returncode == 0:
+        out["native_files_equal_python_files"] = all(
+            open(os.path.join(d, "native.out") + sfx, "rb").read() == open(os.path.join(d, "run.out") + sfx, "rb").read()
+            for sfx in ("", ".sorted_by_a2_maxT", ".sorted_by_a1_maxT"))
 print(json.dumps(out))
 for fn in os.listdir(d):
     os.unlink(os.path.join(d, fn))
