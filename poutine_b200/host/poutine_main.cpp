@@ -37,7 +37,7 @@ struct Args {
     int32_t min_hcount = 1, threads = 0, device = 0;
     bool precomputed = false, overwrite = false, extras = false, have_seed = false;
     uint64_t seed = 0;
-    int64_t tile_sites = 1 << 15;
+    int64_t tile_sites = 1 << 14;   // profiles/r1_native_host_sweep.json: page-locked buffer set-up vs per-tile overhead
     bool compact_upload = true;
     bool timing = false;       // --timing: phase wall clocks on stderr
 };
@@ -47,7 +47,7 @@ struct Args {
     std::fprintf(stderr,
                  "usage: poutine_b200_host -u -f <ancestral fasta> -t <ancestral newick | annotated_tree.nexus> -p <phenos> -m <map>\n"
                  "       [-r <# replicates>=100000] [-c <min_hcount>=1] [-T <# packer threads>] [-d <out dir>] [-o <out file>] [-X]\n"
-                 "       [--seed <n>] [--device <ordinal>] [--extras] [--tile-sites <n>=32768] [--no-compact-upload] [--timing]\n");
+                 "       [--seed <n>] [--device <ordinal>] [--extras] [--tile-sites <n>=16384] [--no-compact-upload] [--timing]\n");
     std::exit(2);
 }
 

@@ -327,7 +327,7 @@ def write_outputs(out_path: str, sites, stats, physical_pos):
 # call() with --use-precomputed-anc-recon
 # -------------------------------------------------------------------------------------------------
 def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_replicates=100000, min_hcount=1, seed=0, device=0,
-                          tile_sites=1 << 17, pack_threads=0, compact_upload=True, extras=False):
+                          tile_sites=1 << 14, pack_threads=0, compact_upload=True, extras=False):
     """Files in, files out: same inputs as `poutine.sh -u -f -t -p -m`, same three result files.
     `tree_file` is a Newick file with internal node labels, or treetime's annotated_tree.nexus."""
     with open(tree_file) as f:
@@ -363,7 +363,8 @@ def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_
     hc.set_phenos(sample_node, label)
     hc.set_sites(S)
     # stream the alignment: pack tile t+1 on a worker thread (the C packer releases the GIL) while tile t uploads
-    tile_sites = max(64, (tile_sites // 64) * 64)
+    # 16384-site tiles: page-locked buffer set-up against per-tile overhead (profiles/r1_native_host_sweep.json)
+    tile_sites = max(64, (min(tile_sites, S + 63) // 64) * 64)
     tw = tile_sites // 64
     # A tile whose sites all carry at most two bases (the usual SNP alignment) is compacted on the worker thread too and
     # goes up as one plane (+ V when some call is not a base) instead of three: buffer slot 3 holds X.
