@@ -2,7 +2,7 @@
 // libpoutine_b200.so:
 //
 //     poutine_b200_host -u -f anc.fasta -t anc.newick|annotated_tree.nexus -p pheno.tsv -m sites.map [-r m] [-c min_hcount]
-//                       [-T threads] [-d out_dir] [-o out] [-X] [--seed s] [--devices d0[,d1,...]] [--extras]
+//                       [-T threads] [-d out_dir] [-o out] [-X] [--seed s] [--device d] [--extras]
 //
 // = Homoplasy_Counter.call() (HC.java:230-319) with the picocli flags of HC.java:59-154: loaders (hostio.cpp), the mmap'ed
 // FASTA packer streamed tile by tile into pb_put_planes / pb_put_planes_biallelic, the two hot entry points through
@@ -11,12 +11,8 @@
 //
 // The "--x-..." sub-commands print what the loaders / formatter produce; tests/test_host_cpp.py compares them with the
 // Python host (poutine_b200/hostio.py) — no GPU involved.
-#include <algorithm>
 #include <chrono>
 #include <cinttypes>
-#include <condition_variable>
-#include <memory>
-#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -38,8 +34,7 @@ namespace {
 struct Args {
     std::string fasta, phenos, tree, map, out_dir, out;
     int64_t replicates = 100000;
-    int32_t min_hcount = 1, threads = 0;
-    std::vector<int32_t> devices{0};     // --device d | --devices d0,d1,... : one site shard per GPU
+    int32_t min_hcount = 1, threads = 0, device = 0;
     bool precomputed = false, overwrite = false, extras = false, have_seed = false;
     uint64_t seed = 0;
     int64_t tile_sites = 1 << 14;   // profiles/r1_native_host_sweep.json: page-locked buffer set-up vs per-tile overhead
@@ -52,7 +47,7 @@ struct Args {
     std::fprintf(stderr,
                  "usage: poutine_b200_host -u -f <ancestral fasta> -t <ancestral newick | annotated_tree.nexus> -p <phenos> -m <map>\n"
                  "       [-r <# replicates>=100000] [-c <min_hcount>=1] [-T <# packer threads>] [-d <out dir>] [-o <out file>] [-X]\n"
-                 "       [--seed <n>] [--devices <ordinal>[,<ordinal>...]] [--extras] [--tile-sites <n>=16384] [--no-compact-upload] [--timing]\n");
+                 "       [--seed <n>] [--device <ordinal>] [--extras] [--tile-sites <n>=16384] [--no-compact-upload] [--timing]\n");
     std::exit(2);
 }
 
@@ -93,7 +88,6 @@ struct FastaFile {     // build_seg_sites (HC.java:1241-1306) source: indexed on
 struct RunResult {
     pb_class_counts counts{};
     int64_t n_informative = 0, n_sites = 0, n_tiles = 0, n_compact_tiles = 0;
-    int n_gpus = 1;
 };
 
 struct PhaseClock {
@@ -151,175 +145,92 @@ RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
     }
 
     clk.lap("loaders + fasta index");
+    Options o;
+    o.num_replicates = a.replicates;
+    o.min_hcount = a.min_hcount;
+    o.device = a.device;
+    o.seed = a.seed;
+    HomoplasyCounter hc(o);
+    hc.set_tree(tree.parent, tree.is_leaf);
+    hc.set_phenos(sample_node, label);
+    hc.set_sites(S);
+    clk.lap("context, tree, phenos, planes");
 
-    // Site shards: contiguous 64-site-word ranges, one context and one host thread per GPU; every rank draws
-    // the same permutations (same seed), the one exchange is the all-reduce(min) of maxT[m] inside assoc().
-    const int64_t W = (S + 63) / 64;
-    const int G = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)a.devices.size(), W));
-    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
-    const int pack_threads = a.threads > 0 ? std::max(1, a.threads / G) : std::max(1, hw / G);
-    char nccl_id[128] = {0};
-    if (G > 1 && pb_comm_unique_id(nccl_id) != 0) throw PoutineError(PB_ERR_NCCL, pb_last_error(nullptr));
-
-    struct Shard {
-        int64_t s0 = 0, s1 = 0, n_tiles = 0, n_compact_tiles = 0;
-        pb_class_counts counts{};
-        std::vector<pb_site_out> sites;
-        AssocResult assoc;
-        std::vector<double> exact_pointwise, fisher_p;
+    // stream the alignment: tile t+1 is packed (and compacted, when all of its sites carry at most two bases) on a worker
+    // thread while tile t uploads from the other page-locked buffer set
+    const int64_t tile_sites = std::max<int64_t>(64, std::min(a.tile_sites, S + 63) / 64 * 64);
+    const int64_t tw = tile_sites / 64;
+    struct Buf {
+        PinnedArray<uint64_t> B0, B1, V, X;
+        std::vector<uint64_t> colmask;
+        int compact = 0;
+        int32_t all_valid = 0;
         std::string error;
-        bool no_informative = false;
-    };
-    std::vector<Shard> shards((size_t)G);
-    std::vector<pb_site_out> all_events((size_t)S);       // the reference's all_events, one record per site, site order
-    // rendezvous before the first collective: a rank whose input handling failed must not leave the others waiting in NCCL
-    std::mutex mu;
-    std::condition_variable cv;
-    int arrived = 0, failed = 0;
-
-    auto run_shard = [&](int g) {
-        Shard& sh = shards[(size_t)g];
-        sh.s0 = 64 * (W * g / G);
-        sh.s1 = std::min(S, 64 * (W * (g + 1) / G));
-        const int64_t Sg = sh.s1 - sh.s0;
-        std::unique_ptr<HomoplasyCounter> hc;
-        bool ready = false;
-        try {
-            Options o;
-            o.num_replicates = a.replicates;
-            o.min_hcount = a.min_hcount;
-            o.device = a.devices[(size_t)g];
-            o.seed = a.seed;
-            o.site_offset = sh.s0;
-            hc.reset(new HomoplasyCounter(o));
-            hc->set_tree(tree.parent, tree.is_leaf);
-            hc->set_phenos(sample_node, label);
-            hc->set_sites(Sg);
-            if (g == 0) clk.lap("context, tree, phenos, planes");
-
-            // stream the shard's columns: tile t+1 is packed (and compacted, when all of its sites carry at most two bases)
-            // on a worker thread while tile t uploads from the other page-locked buffer set
-            const int64_t tile_sites = std::max<int64_t>(64, std::min(a.tile_sites, Sg + 63) / 64 * 64);
-            const int64_t tw = tile_sites / 64;
-            struct Buf {
-                PinnedArray<uint64_t> B0, B1, V, X;
-                std::vector<uint64_t> colmask;
-                int compact = 0;
-                int32_t all_valid = 0;
-                std::string error;
-            } bufs[2];
-            for (Buf& b : bufs) {
-                b.B0.reset((size_t)(N * tw));
-                b.B1.reset((size_t)(N * tw));
-                b.V.reset((size_t)(N * tw));
-                b.X.reset((size_t)(N * tw));
-                b.colmask.resize((size_t)(4 * tw));
-            }
-            sh.n_tiles = (Sg + tile_sites - 1) / tile_sites;
-            if (g == 0) clk.lap("page-locked tile buffers");
-            auto pack = [&](int64_t t) {
-                Buf& b = bufs[t & 1];
-                const int64_t t0 = t * tile_sites, ns = std::min(tile_sites, Sg - t0);
-                b.error.clear();
-                if (pb_fasta_pack_tile(fa.h, node_of_record.data(), sh.s0 + t0, ns, b.B0.data(), b.B1.data(), b.V.data(), tw, pack_threads) != 0) {
-                    b.error = pb_fasta_last_error();
-                    return;
-                }
-                b.compact = 0;
-                if (a.compact_upload) {
-                    int rc = pb_compact_planes(b.B0.data(), b.B1.data(), b.V.data(), N, ns, tw, b.X.data(), tw, b.colmask.data(), &b.all_valid,
-                                               pack_threads);
-                    if (rc < 0) b.error = "pb_compact_planes: invalid arguments";
-                    b.compact = rc == 1;
-                }
-            };
-            if (sh.n_tiles) pack(0);
-            for (int64_t t = 0; t < sh.n_tiles; t++) {
-                std::thread worker;
-                if (t + 1 < sh.n_tiles) worker = std::thread(pack, t + 1);
-                Buf& b = bufs[t & 1];
-                const int64_t t0 = t * tile_sites, ns = std::min(tile_sites, Sg - t0), nw = (ns + 63) / 64;
-                try {
-                    if (!b.error.empty()) throw DataFormatError(b.error);
-                    if (b.compact) {
-                        hc->put_planes_biallelic(t0 / 64, nw, tw, b.X.data(), b.all_valid ? nullptr : b.V.data(), b.colmask.data());
-                        sh.n_compact_tiles++;
-                    } else {
-                        hc->put_planes(t0 / 64, nw, tw, b.B0.data(), b.B1.data(), b.V.data());
-                    }
-                } catch (...) {
-                    if (worker.joinable()) worker.join();
-                    throw;
-                }
-                if (worker.joinable()) worker.join();
-            }
-            if (g == 0) clk.lap("pack + upload (pipelined)");
-            ready = true;
-        } catch (const std::exception& e) {
-            sh.error = e.what();
-        }
-        {
-            std::unique_lock<std::mutex> lk(mu);
-            arrived++;
-            if (!ready) failed++;
-            cv.notify_all();
-            cv.wait(lk, [&] { return arrived == G; });
-            if (failed) return;
-        }
-        try {
-            if (G > 1) hc->comm_init(nccl_id, g, G);
-            const pb_site_out* ev = hc->count_all_homoplasy_events(&sh.counts);     // HC.java:299
-            std::copy(ev, ev + Sg, all_events.begin() + sh.s0);
-            if (g == 0) clk.lap("count_all_homoplasy_events");
-            sh.assoc = hc->assoc(nullptr, false);                                    // HC.java:314
-            for (pb_stat_out& t : sh.assoc.stats) t.site_index += (int32_t)sh.s0;    // shard-local -> global
-            if (g == 0) clk.lap("assoc");
-            if (a.extras) hc->extras(sh.exact_pointwise, sh.fisher_p);
-        } catch (const NoInformativeSites& e) {
-            sh.no_informative = true;
-            sh.error = e.what();
-        } catch (const std::exception& e) {
-            sh.error = e.what();
-        }
-    };
-    if (G == 1) {
-        run_shard(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int g = 0; g < G; g++) th.emplace_back(run_shard, g);
-        for (std::thread& t : th) t.join();
+    } bufs[2];
+    for (Buf& b : bufs) {
+        b.B0.reset((size_t)(N * tw));
+        b.B1.reset((size_t)(N * tw));
+        b.V.reset((size_t)(N * tw));
+        b.X.reset((size_t)(N * tw));
+        b.colmask.resize((size_t)(4 * tw));
     }
+    const int64_t n_tiles = (S + tile_sites - 1) / tile_sites;
+    clk.lap("page-locked tile buffers");
+    auto pack = [&](int64_t t) {
+        Buf& b = bufs[t & 1];
+        const int64_t s0 = t * tile_sites, ns = std::min(tile_sites, S - s0);
+        b.error.clear();
+        if (pb_fasta_pack_tile(fa.h, node_of_record.data(), s0, ns, b.B0.data(), b.B1.data(), b.V.data(), tw, a.threads) != 0) {
+            b.error = pb_fasta_last_error();
+            return;
+        }
+        b.compact = 0;
+        if (a.compact_upload) {
+            int rc = pb_compact_planes(b.B0.data(), b.B1.data(), b.V.data(), N, ns, tw, b.X.data(), tw, b.colmask.data(), &b.all_valid,
+                                       a.threads);
+            if (rc < 0) b.error = "pb_compact_planes: invalid arguments";
+            b.compact = rc == 1;
+        }
+    };
     RunResult res;
     res.n_sites = S;
-    res.n_gpus = G;
-    std::vector<pb_stat_out> stats;
-    std::vector<double> ep, fp;
-    for (const Shard& sh : shards) {
-        if (sh.no_informative) throw NoInformativeSites(PB_ERR_NO_INFORMATIVE, sh.error);
-        if (!sh.error.empty()) throw std::runtime_error(sh.error);
-        res.n_tiles += sh.n_tiles;
-        res.n_compact_tiles += sh.n_compact_tiles;
-        res.counts.n_no_allele += sh.counts.n_no_allele;
-        res.counts.n_mono += sh.counts.n_mono;
-        res.counts.n_bi += sh.counts.n_bi;
-        res.counts.n_tri += sh.counts.n_tri;
-        res.counts.n_quad += sh.counts.n_quad;
-        res.counts.n_raw_events += sh.counts.n_raw_events;
-        stats.insert(stats.end(), sh.assoc.stats.begin(), sh.assoc.stats.end());
-        ep.insert(ep.end(), sh.exact_pointwise.begin(), sh.exact_pointwise.end());
-        fp.insert(fp.end(), sh.fisher_p.begin(), sh.fisher_p.end());
+    res.n_tiles = n_tiles;
+    if (n_tiles) pack(0);
+    for (int64_t t = 0; t < n_tiles; t++) {
+        std::thread worker;
+        if (t + 1 < n_tiles) worker = std::thread(pack, t + 1);
+        Buf& b = bufs[t & 1];
+        const int64_t s0 = t * tile_sites, ns = std::min(tile_sites, S - s0), nw = (ns + 63) / 64;
+        try {
+            if (!b.error.empty()) throw DataFormatError(b.error);
+            if (b.compact) {
+                hc.put_planes_biallelic(s0 / 64, nw, tw, b.X.data(), b.all_valid ? nullptr : b.V.data(), b.colmask.data());
+                res.n_compact_tiles++;
+            } else {
+                hc.put_planes(s0 / 64, nw, tw, b.B0.data(), b.B1.data(), b.V.data());
+            }
+        } catch (...) {
+            if (worker.joinable()) worker.join();
+            throw;
+        }
+        if (worker.joinable()) worker.join();
     }
-    res.n_informative = (int64_t)stats.size();
-    if (stats.empty())      // sharded contexts leave this check to the host: no rank alone sees all sites (HC.java:3866-3869)
-        throw NoInformativeSites(PB_ERR_NO_INFORMATIVE, "min_hcount is set too high and has filtered out all segregating sites");
-    write_outputs(out_path, all_events.data(), stats, physical_pos);
+    clk.lap("pack + upload (pipelined)");
+    const pb_site_out* all_events = hc.count_all_homoplasy_events(&res.counts);     // HC.java:299
+    clk.lap("count_all_homoplasy_events");
+    AssocResult as = hc.assoc();                                                    // HC.java:314
+    clk.lap("assoc");
+    res.n_informative = (int64_t)as.stats.size();
+    write_outputs(out_path, all_events, as.stats, physical_pos);
     clk.lap("write_outputs");
     if (a.extras) {      // not a reference file: exact point-wise null + two-sided Fisher per informative site
+        std::vector<double> ep, fp;
+        hc.extras(ep, fp);
         FILE* f = std::fopen((out_path + ".extras").c_str(), "wb");
         if (!f) throw DataFormatError("cannot write " + out_path + ".extras");
         std::fputs("segsite_ID\tpos\texact_pointwise_a1\texact_pointwise_a2\tfisher_two_sided\n", f);
-        for (size_t i = 0; i < stats.size(); i++)
-            std::fprintf(f, "%d\t%d\t%s\t%s\t%s\n", stats[i].segsite_id, physical_pos[(size_t)stats[i].site_index],
+        for (size_t i = 0; i < as.stats.size(); i++)
+            std::fprintf(f, "%d\t%d\t%s\t%s\t%s\n", as.stats[i].segsite_id, physical_pos[(size_t)as.stats[i].site_index],
                          java_double_str(ep[2 * i]).c_str(), java_double_str(ep[2 * i + 1]).c_str(), java_double_str(fp[i]).c_str());
         std::fclose(f);
     }
@@ -404,18 +315,7 @@ int main(int argc, char** argv) {
             else if (f == "-o" || f == "--out") a.out = val();
             else if (f == "-X" || f == "--force-overwrite") a.overwrite = true;
             else if (f == "--seed") { a.seed = std::strtoull(val(), nullptr, 10); a.have_seed = true; }
-            else if (f == "--device" || f == "--devices") {
-                a.devices.clear();
-                for (const char* p = val(); *p;) {
-                    char* end = nullptr;
-                    long d = std::strtol(p, &end, 10);
-                    if (end == p || d < 0) usage("--devices expects a comma-separated list of CUDA ordinals");
-                    a.devices.push_back((int32_t)d);
-                    p = *end == ',' ? end + 1 : end;
-                    if (*end && *end != ',') usage("--devices expects a comma-separated list of CUDA ordinals");
-                }
-                if (a.devices.empty()) usage("--devices expects a comma-separated list of CUDA ordinals");
-            }
+            else if (f == "--device") a.device = std::atoi(val());
             else if (f == "--extras") a.extras = true;
             else if (f == "--tile-sites") a.tile_sites = std::atoll(val());
             else if (f == "--no-compact-upload") a.compact_upload = false;
