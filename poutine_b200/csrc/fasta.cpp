@@ -46,14 +46,17 @@ static thread_local std::string g_fasta_err;
 
 static inline bool is_eol(char c) { return c == '\n' || c == '\r'; }
 
-static void index_records(pb_fasta* f) {
+// false: the file does not start with a header line — where Fasta_Manager.next() prints "First line of Fasta file muust be a
+// header line." (or, for an empty first line, "the header line should never be an empty string") and calls System.exit(-1).
+// Every later record can only begin at a '>' line, so the first line is the one place this can happen.
+static bool index_records(pb_fasta* f) {
     const char* d = f->data;
     const int64_t n = f->size;
-    int64_t pos = 0;
-    // skip anything before the first header (Fasta_Manager expects the file to start with '>')
-    while (pos < n && d[pos] != '>') {
-        while (pos < n && !is_eol(d[pos])) pos++;
-        while (pos < n && is_eol(d[pos])) pos++;
+    int64_t pos = 0, next_nl = -1;
+    if (n > 0 && d[0] != '>') {
+        f->err = is_eol(d[0]) ? "pb_fasta_open: the first line is empty, the header line should never be an empty string"
+                              : "pb_fasta_open: first line of the FASTA file must be a header line ('>')";
+        return false;
     }
     while (pos < n) {
         FastaRecord r{};
@@ -71,10 +74,15 @@ static void index_records(pb_fasta* f) {
         // sequence lines: (file offset, chars before) per readLine() line
         int64_t total = 0;
         std::vector<int64_t> lines;
+        bool header_after_cr = false;
         while (pos < n && d[pos] != '>') {
             const int64_t l0 = pos;
-            const char* nl = (const char*)memchr(d + pos, '\n', (size_t)(n - pos));
-            const int64_t l1 = nl ? (nl - d) : n;     // physical line end (exclusive of '\n')
+            if (next_nl < pos) {                       // cached: a file with bare-'\r' line ends has few (or no) '\n'
+                const char* q = (const char*)memchr(d + pos, '\n', (size_t)(n - pos));
+                next_nl = q ? (q - d) : n;
+            }
+            const bool nl = next_nl < n;
+            const int64_t l1 = next_nl;               // physical line end (exclusive of '\n')
             int64_t e = l1;
             if (e > l0 && d[e - 1] == '\r') e--;      // "\r\n"
             int64_t s = l0;
@@ -85,7 +93,9 @@ static void index_records(pb_fasta* f) {
                 total += se - s;
                 if (!cr) break;
                 s = se + 1;
+                if (s < e && d[s] == '>') { header_after_cr = true; break; }   // the bare '\r' ended the line before a header line
             }
+            if (header_after_cr) { pos = s; break; }
             pos = nl ? l1 + 1 : n;
         }
         r.seq_len = total;
@@ -107,6 +117,7 @@ static void index_records(pb_fasta* f) {
         }
         f->recs.push_back(std::move(r));
     }
+    return true;
 }
 
 extern "C" const char* pb_fasta_last_error(void) { return g_fasta_err.c_str(); }
@@ -126,7 +137,11 @@ extern "C" int pb_fasta_open(const char* path, pb_fasta** out) {
         f->data = (const char*)p;
         madvise(p, (size_t)f->size, MADV_WILLNEED);
     }
-    index_records(f);
+    if (!index_records(f)) {
+        g_fasta_err = f->err;
+        pb_fasta_close(f);
+        return PB_ERR_INVALID;
+    }
     *out = f;
     return PB_OK;
 }

@@ -82,21 +82,30 @@ struct Tokenizer {
     }
 };
 
+// NewickTreeReader.reportFormatError's message
 [[noreturn]] void newick_error(char state, const std::string& tok) {
-    throw DataFormatError(std::string("Newick format error in state ") + state + " at token '" + tok + "'");
+    const char* name = state == 'S' ? "NODE_START" : state == 'I' ? "ID" : state == 'C' ? "COLON" : state == 'D' ? "DIST"
+                     : state == 'E' ? "NODE_END" : "SEMI_COLON";
+    throw DataFormatError("Unexpected token [" + tok + "] encountered in the " + name + " state.");
 }
 
-// Float.parseFloat: decimal / hex floating literal with an optional f|F|d|D suffix, whole token consumed
-float parse_java_float(const std::string& tok, char state) {
+// Float.parseFloat on a token (no blanks inside): optional sign, decimal digits / '.' / exponent, optional f|F|d|D suffix;
+// "NaN" / "Infinity".  Anything else is the reference's NumberFormatException (which build_tree, HC.java:1155, does not
+// catch: the run dies with that exception).
+float parse_java_float(const std::string& tok) {
     std::string t = tok;
-    if (t.size() > 1 && (t.back() == 'f' || t.back() == 'F' || t.back() == 'd' || t.back() == 'D') &&
-        !(t.size() > 2 && (t[1] == 'x' || t[1] == 'X')))
-        t.pop_back();
-    if (t.empty()) newick_error(state, tok);
-    char* end = nullptr;
-    double v = std::strtod(t.c_str(), &end);
-    if (end != t.c_str() + t.size()) newick_error(state, tok);
-    return (float)v;
+    if (t.size() > 1 && (t.back() == 'f' || t.back() == 'F' || t.back() == 'd' || t.back() == 'D')) t.pop_back();
+    bool ok = !t.empty() && t != "+" && t != "-";
+    for (char c : t) ok = ok && ((c >= '0' && c <= '9') || c == '.' || c == 'e' || c == 'E' || c == '+' || c == '-');
+    const size_t sign = !t.empty() && (t[0] == '+' || t[0] == '-') ? 1 : 0;
+    if (t.compare(sign, std::string::npos, "NaN") == 0) return std::nanf("");
+    if (t.compare(sign, std::string::npos, "Infinity") == 0) return t[0] == '-' ? -HUGE_VALF : HUGE_VALF;
+    if (ok) {
+        char* end = nullptr;
+        double v = std::strtod(t.c_str(), &end);
+        if (end == t.c_str() + t.size()) return (float)v;
+    }
+    throw DataFormatError("For input string: \"" + tok + "\"");
 }
 
 }  // namespace
@@ -107,7 +116,7 @@ Tree parse_newick(const std::string& text) {
         tr.parent.push_back(par);
         tr.names.emplace_back();
         tr.has_name.push_back(0);
-        tr.dist_to_parent.push_back(0.0f);
+        tr.dist_to_parent.push_back(std::nanf(""));     // NewickTreeNode.<init>: Float.NaN until a ':dist' is read
         return (int32_t)tr.parent.size() - 1;
     };
     auto set_id = [&](int32_t v, const std::string& id) {
@@ -168,7 +177,7 @@ Tree parse_newick(const std::string& text) {
             break;
         case 'C':
             if (delim) newick_error(state, tok);
-            tr.dist_to_parent[cur] = parse_java_float(tok, state);
+            tr.dist_to_parent[cur] = parse_java_float(tok);
             state = 'D';
             break;
         }

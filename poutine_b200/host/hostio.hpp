@@ -30,7 +30,7 @@ struct Tree {
     std::vector<int32_t> parent;        // -1 for the root (node 0: the outermost bracket pair)
     std::vector<uint8_t> is_leaf;
     std::vector<int32_t> leaf_nodes;    // NewickTree.buildCaches: left-to-right DFS order
-    std::vector<float> dist_to_parent;  // parsed like the reference does, never used by POUTINE
+    std::vector<float> dist_to_parent;  // parsed like the reference does (NaN when absent), never used by POUTINE
     std::vector<std::string> names;     // node ids; has_name[v] == 0 for an unnamed node
     std::vector<uint8_t> has_name;
     int64_t n_nodes() const { return (int64_t)parent.size(); }

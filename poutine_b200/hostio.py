@@ -37,6 +37,20 @@ class DataFormatError(ValueError):
 # -------------------------------------------------------------------------------------------------
 # Newick (bytecode-faithful restatement of NewickTreeTokenizer.nextToken / NewickTreeReader.readTree)
 # -------------------------------------------------------------------------------------------------
+_STATE_NAMES = {"S": "NODE_START", "I": "ID", "C": "COLON", "D": "DIST", "E": "NODE_END", "F": "SEMI_COLON"}
+
+
+def _java_is_whitespace(ch: str) -> bool:
+    """java.lang.Character.isWhitespace: \\t \\n VT FF \\r FS GS RS US and the Unicode space / line / paragraph separators
+    except the no-break spaces (str.isspace() differs: it accepts U+00A0 and U+0085)"""
+    if ch in "\t\n\x0b\x0c\r\x1c\x1d\x1e\x1f ":
+        return True
+    if ord(ch) < 0x80:
+        return False
+    import unicodedata
+    return unicodedata.category(ch) in ("Zs", "Zl", "Zp") and ch not in "\u00a0\u2007\u202f"
+
+
 def _tokens(text: str):
     buf = []
     for ch in text:
@@ -45,7 +59,7 @@ def _tokens(text: str):
                 yield "".join(buf)
                 buf = []
             yield ch
-        elif ch.isspace():                      # Character.isWhitespace: ends a token, never part of one
+        elif _java_is_whitespace(ch):           # Character.isWhitespace: ends a token, never part of one
             if buf:
                 yield "".join(buf)
                 buf = []
@@ -53,6 +67,22 @@ def _tokens(text: str):
             buf.append(ch)
     if buf:
         yield "".join(buf)
+
+
+def _java_parse_float(tok: str) -> float:
+    """Float.parseFloat on a token (no blanks inside): optional sign, decimal digits / '.' / exponent, optional f|F|d|D
+    suffix; "NaN" / "Infinity"; anything else is the reference's NumberFormatException (which build_tree, HC.java:1155, does
+    not catch: the run dies with that exception)."""
+    body = tok[:-1] if len(tok) > 1 and tok[-1] in "fFdD" else tok
+    ok = body not in ("", "+", "-") and all(c in "0123456789.eE+-" for c in body)
+    if body.lstrip("+-") in ("NaN", "Infinity") and len(body) - len(body.lstrip("+-")) <= 1:
+        body, ok = body.replace("Infinity", "inf").replace("NaN", "nan"), True
+    if ok:
+        try:
+            return float(np.float32(float(body)))
+        except ValueError:
+            pass
+    raise DataFormatError('For input string: "%s"' % tok)
 
 
 def parse_newick(text: str) -> Tree:
@@ -64,11 +94,12 @@ def parse_newick(text: str) -> Tree:
     def new_node(par):
         parent.append(par)
         ids.append(None)
-        dist.append(0.0)
+        dist.append(float("nan"))              # NewickTreeNode.<init>: distToParent = Float.NaN until a ':dist' is read
         return len(parent) - 1
 
     def err(state, tok):
-        raise DataFormatError("Newick format error in state %s at token %r" % (state, tok))
+        # NewickTreeReader.reportFormatError's message
+        raise DataFormatError("Unexpected token [%s] encountered in the %s state." % (tok, _STATE_NAMES[state]))
 
     state, cur = "S", -1
     it = _tokens(text)
@@ -120,10 +151,7 @@ def parse_newick(text: str) -> Tree:
         elif state == "C":
             if tok in DELIMS:
                 err(state, tok)
-            try:
-                dist[cur] = float(np.float32(float(tok)))     # Float.parseFloat
-            except ValueError:
-                err(state, tok)
+            dist[cur] = _java_parse_float(tok)
             state = "D"
     if cur < 0:
         raise DataFormatError("More close brackets then open brackets")
