@@ -169,8 +169,7 @@ def parse_newick(text: str) -> Tree:
 def nexus_to_newick(path: str) -> str:
     """HC.java:866-914: the line after 'Begin Trees;' (case-insensitive, exact), cut before the first '(',
     every '[...]' annotation deleted."""
-    with open(path) as f:
-        lines = f.read().splitlines()
+    lines = _java_lines(path)
     for i, line in enumerate(lines):
         if line.lower() == "begin trees;":
             break
@@ -197,22 +196,54 @@ def nexus_to_newick(path: str) -> str:
 # -------------------------------------------------------------------------------------------------
 # pheno / map files
 # -------------------------------------------------------------------------------------------------
+def _java_lines(path: str):
+    """BufferedReader.readLine: a line ends at \\n, \\r or \\r\\n (str.splitlines also splits at VT, FF, FS, GS, RS, NEL, LS, PS)"""
+    with open(path, newline="") as f:
+        text = f.read()
+    lines = text.replace("\r\n", "\n").replace("\r", "\n").split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    return lines
+
+
+def _java_split_tabs(line: str):
+    """String.split("\\t"): trailing empty strings are removed ("a\\t\\t" -> ["a"]); "" -> [""]"""
+    cols = line.split("\t")
+    if len(cols) > 1:
+        while cols and cols[-1] == "":
+            cols.pop()
+    return cols
+
+
+def _java_parse_int(s: str) -> int:
+    """Integer.parseInt: [+-]?[0-9]+ within int32 — no blanks, no underscores (int() accepts both)"""
+    body = s[1:] if s[:1] in "+-" else s
+    if not body or not body.isascii() or not body.isdigit() or not -(1 << 31) <= int(s) < (1 << 31):
+        raise ValueError('For input string: "%s"' % s)
+    return int(s)
+
+
 def read_phenos(path: str):
-    """HC.java:1972-2019 -> ordered dict id -> label string (a HashMap: a repeated id keeps the last label)."""
+    """HC.java:1972-2019 -> ordered dict id -> label string (a HashMap: a repeated id keeps the last label).  A row with
+    fewer than two columns is the reference's "malformed phenotype file" exit (HC.java:1983-1987)."""
     phenos = {}
-    with open(path) as f:
-        for line in f.read().splitlines():
-            cols = line.split("\t")
-            phenos[cols[0]] = cols[1]           # IndexError <-> the reference's "malformed phenotype file" exit
+    for line in _java_lines(path):
+        cols = _java_split_tabs(line)
+        if len(cols) < 2:
+            raise DataFormatError("malformed phenotype file %s: a row has fewer than two tab-separated columns" % path)
+        phenos[cols[0]] = cols[1]
     return phenos
 
 
 def read_map(path: str) -> np.ndarray:
-    """HC.java:1207-1235: last tab-separated column of every row, as int."""
+    """HC.java:1207-1235: Integer.parseInt of the last tab-separated column of every row ("malformed map file" exit otherwise)."""
     out = []
-    with open(path) as f:
-        for line in f.read().splitlines():
-            out.append(int(line.split("\t")[-1]))
+    for line in _java_lines(path):
+        cols = _java_split_tabs(line)
+        try:
+            out.append(_java_parse_int(cols[-1]))
+        except (ValueError, IndexError):
+            raise DataFormatError("malformed map file %s: %r is not an integer position" % (path, cols[-1] if cols else "")) from None
     return np.asarray(out, dtype=np.int64)
 
 
