@@ -116,13 +116,21 @@ RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
     }
     FastaFile fa(a.fasta);
     std::vector<int32_t> physical_pos = read_map(a.map);
-    const int64_t S = fa.lengths.empty() ? 0 : fa.lengths.back();     // num_segsites_detected: the last record (HC.java:1268)
-    if (S != (int64_t)physical_pos.size())                            // check_num_seg_sites (HC.java:327-365)
-        throw DataFormatError("# sites in the FASTA (" + std::to_string(S) + ") != # rows in the map file (" +
-                              std::to_string(physical_pos.size()) + ")");
+    // The reference loops over the map rows (HC.java:1418) and reads snps[i] of EVERY record (HC.java:1383-1394): a shorter
+    // record is an ArrayIndexOutOfBoundsException there, and check_num_seg_sites (HC.java:327-365) exits unless the first
+    // record in its HashMap's iteration order has exactly as many sites as the map file has rows.  Here: every record must.
+    const int64_t S = (int64_t)physical_pos.size();
+    for (size_t i = 0; i < fa.names.size(); i++)
+        if (fa.lengths[i] != S)
+            throw DataFormatError("# sites of FASTA record '" + fa.names[i] + "' (" + std::to_string(fa.lengths[i]) +
+                                  ") != # rows in the map file (" + std::to_string(S) + ")");
     std::vector<int32_t> node_of_record(fa.names.size(), -1);
     std::vector<uint8_t> seen((size_t)N, 0);
+    std::unordered_map<std::string, size_t> last_record;
     for (size_t i = 0; i < fa.names.size(); i++) {
+        auto dup = last_record.find(fa.names[i]);           // seg_sites.put(node_name, seq): a repeated name keeps its LAST record
+        if (dup != last_record.end()) node_of_record[dup->second] = -1;
+        last_record[fa.names[i]] = i;
         auto it = node_of_name.find(fa.names[i]);
         if (it != node_of_name.end()) {
             node_of_record[i] = it->second;

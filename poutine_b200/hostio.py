@@ -402,10 +402,19 @@ def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_
         node_of_name[n] = v
     fa = FastaFile(fasta)
     physical_pos = read_map(map_file)
-    S = int(fa.lengths[-1]) if len(fa.lengths) else 0     # num_segsites_detected = length of the last record (HC.java:1268)
-    if S != len(physical_pos):                            # check_num_seg_sites (HC.java:327-365)
-        raise DataFormatError("# sites in the FASTA (%d) != # rows in the map file (%d)" % (S, len(physical_pos)))
+    # The reference loops over the map rows (HC.java:1418) and reads snps[i] of EVERY record (HC.java:1383-1394): a shorter
+    # record is an ArrayIndexOutOfBoundsException there, and check_num_seg_sites (HC.java:327-365) exits unless the first
+    # record in its HashMap's iteration order has exactly as many sites as the map file has rows.  Here: every record must.
+    S = len(physical_pos)
+    for name, n in zip(fa.names, fa.lengths):
+        if int(n) != S:
+            raise DataFormatError("# sites of FASTA record %r (%d) != # rows in the map file (%d)" % (name, int(n), S))
     node_of_record = np.array([node_of_name.get(n, -1) for n in fa.names], dtype=np.int32)
+    last = {}
+    for i, n in enumerate(fa.names):                      # seg_sites.put(node_name, seq): a repeated name keeps its LAST record
+        if n in last:
+            node_of_record[last[n]] = -1
+        last[n] = i
     missing = set(range(tree.n_nodes)) - set(int(v) for v in node_of_record if v >= 0)
     if missing:
         raise DataFormatError("tree node %r has no FASTA record" % tree.names[min(missing)])

@@ -186,6 +186,41 @@ def test_cli_errors_without_gpu_work(tmp_path):
     assert r.returncode == 255 and "cannot open" in r.stderr
 
 
+def test_cross_file_checks_before_any_device_work(tmp_path):
+    """check_num_seg_sites / check_sample_names (HC.java:327-404) and what the reference's site loop implies (HC.java:1383-1394,
+    1418): every FASTA record needs exactly as many sites as the map file has rows; every tree node needs a record; every pheno
+    sample must be a leaf with a record.  Both hosts refuse before touching the GPU."""
+    t = synth.yule_tree(12, 1)
+    S = 70
+    chars = synth.planes_to_chars(*synth.simulate_planes(t, S, 2), 0, S)
+    sn, lab = synth.simulate_phenotypes(t, 3)
+
+    def both(paths, needle):
+        r = run("-u", "-f", paths["fasta"], "-t", paths["tree"], "-p", paths["pheno"], "-m", paths["map"], "-r", "50", "-d", str(tmp_path / "o"),
+                "-o", "x.out", ok=False)
+        assert r.returncode == 255 and needle in r.stderr, r.stderr
+        with pytest.raises(hostio.DataFormatError, match=needle):
+            hostio.run_homoplasy_counter(paths["fasta"], paths["tree"], paths["pheno"], paths["map"], str(tmp_path / "py.out"), num_replicates=50)
+
+    paths = synth.write_inputs(str(tmp_path / "a"), t, chars, sn, lab)
+    with open(paths["map"], "a") as f:                                  # one map row too many
+        f.write("1\tsnpX\t0\t999999\n")
+    both(paths, "rows in the map file")
+    paths = synth.write_inputs(str(tmp_path / "b"), t, chars, sn, lab)
+    lines = open(paths["fasta"]).read().split("\n")
+    lines[3] = lines[3][:-1]                                            # second record one site short: AIOOBE in the reference
+    open(paths["fasta"], "w").write("\n".join(lines))
+    both(paths, "sites of FASTA record")
+    paths = synth.write_inputs(str(tmp_path / "c"), t, chars, sn, lab)
+    lines = open(paths["fasta"]).read().split("\n")
+    open(paths["fasta"], "w").write("\n".join(lines[2:]))               # first record gone
+    both(paths, "has no FASTA record")
+    paths = synth.write_inputs(str(tmp_path / "d"), t, chars, sn, lab)
+    with open(paths["pheno"], "a") as f:
+        f.write("not_a_sample\t1\n" + t.names[t.root] + "\t0\n")
+    both(paths, "not_a_sample")
+
+
 def test_no_cpu_fallback_in_the_native_host(tmp_path):
     """without a GPU the binary fails at pb_create (after the loaders accepted the inputs), it never computes on the CPU"""
     import torch
