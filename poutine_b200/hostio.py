@@ -198,7 +198,7 @@ def nexus_to_newick(path: str) -> str:
 # -------------------------------------------------------------------------------------------------
 def _java_lines(path: str):
     """BufferedReader.readLine: a line ends at \\n, \\r or \\r\\n (str.splitlines also splits at VT, FF, FS, GS, RS, NEL, LS, PS)"""
-    with open(path, newline="") as f:
+    with open(path, newline="", encoding="utf-8", errors="replace") as f:     # FileReader: default charset, malformed -> U+FFFD
         text = f.read()
     lines = text.replace("\r\n", "\n").replace("\r", "\n").split("\n")
     if lines and lines[-1] == "":
@@ -264,7 +264,8 @@ class FastaFile:
         name, nlen, slen = C.c_void_p(), C.c_int64(), C.c_int64()
         for i in range(n):
             L.pb_fasta_record(self._h, i, C.byref(name), C.byref(nlen), C.byref(slen))
-            self.names.append(C.string_at(name.value, nlen.value).decode("latin-1") if nlen.value else "")
+            # the same charset as the tree / pheno readers, so that non-ASCII sample names match across the files
+            self.names.append(C.string_at(name.value, nlen.value).decode("utf-8", errors="replace") if nlen.value else "")
             self.lengths[i] = slen.value
 
     def close(self):
@@ -389,7 +390,7 @@ def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_
                           tile_sites=1 << 14, pack_threads=0, compact_upload=True, extras=False):
     """Files in, files out: same inputs as `poutine.sh -u -f -t -p -m`, same three result files.
     `tree_file` is a Newick file with internal node labels, or treetime's annotated_tree.nexus."""
-    with open(tree_file) as f:
+    with open(tree_file, newline="", encoding="utf-8", errors="replace") as f:
         text = f.read()
     newick = nexus_to_newick(tree_file) if text.lstrip().upper().startswith("#NEXUS") else text
     tree = parse_newick(newick)

@@ -189,6 +189,22 @@ def test_fasta_reader_semantics(tmp_path):
     fa.close()
 
 
+def test_non_ascii_sample_names_match_across_files(tmp_path):
+    """tree, FASTA and pheno readers decode with one charset (the reference's FileReader / StringReader: the platform default,
+    UTF-8): a sample called 'Sé_01' is the same key in all three"""
+    nwk = tmp_path / "t.nwk"
+    nwk.write_text("(Sé_01:1,S日本:2)R;\n", encoding="utf-8")
+    fa = tmp_path / "a.fasta"
+    fa.write_text(">Sé_01\nAC\n>S日本\nAG\n>R\nAC\n", encoding="utf-8")
+    ph = tmp_path / "p.tsv"
+    ph.write_text("Sé_01\t1\nS日本\t0\n", encoding="utf-8")
+    t = hostio.parse_newick(open(nwk, encoding="utf-8").read())
+    f = hostio.FastaFile(str(fa))
+    assert set(t.names) == set(f.names) == {"Sé_01", "S日本", "R"}
+    assert set(hostio.read_phenos(str(ph))) <= set(f.names)
+    f.close()
+
+
 # ---- writer -----------------------------------------------------------------------------------------------------
 def test_java_double_to_string():
     j = hostio.java_double_str
