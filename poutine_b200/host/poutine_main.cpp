@@ -100,13 +100,24 @@ struct PhaseClock {
     }
 };
 
-RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
-    PhaseClock clk{a.timing};
+// The part of call() in front of the two entry points (HC.java:230-296): loaders + cross-file checks, flattened to what the
+// C ABI takes.
+struct Inputs {
+    Tree tree;
+    std::unique_ptr<FastaFile> fa;
+    std::vector<int32_t> physical_pos, node_of_record, sample_node;
+    std::vector<uint8_t> label;
+    int64_t S = 0;
+};
+
+Inputs load_inputs(const Args& a) {
+    Inputs in;
     const std::string text = read_file(a.tree);
     size_t k = 0;
     while (k < text.size() && std::isspace((unsigned char)text[k])) k++;
     const bool nexus = text.size() >= k + 6 && ::strncasecmp(text.c_str() + k, "#NEXUS", 6) == 0;
-    Tree tree = parse_newick(nexus ? nexus_to_newick(a.tree) : text);
+    in.tree = parse_newick(nexus ? nexus_to_newick(a.tree) : text);
+    const Tree& tree = in.tree;
     const int64_t N = tree.n_nodes();
     std::unordered_map<std::string, int32_t> node_of_name;
     for (int64_t v = 0; v < N; v++) {
@@ -114,26 +125,27 @@ RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
             throw DataFormatError("every tree node needs a label (treetime writes NODE_xxxxxxx for internal nodes)");
         if (!node_of_name.emplace(tree.names[v], (int32_t)v).second) throw DataFormatError("duplicate node label '" + tree.names[v] + "'");
     }
-    FastaFile fa(a.fasta);
-    std::vector<int32_t> physical_pos = read_map(a.map);
+    in.fa.reset(new FastaFile(a.fasta));
+    const FastaFile& fa = *in.fa;
+    in.physical_pos = read_map(a.map);
     // The reference loops over the map rows (HC.java:1418) and reads snps[i] of EVERY record (HC.java:1383-1394): a shorter
     // record is an ArrayIndexOutOfBoundsException there, and check_num_seg_sites (HC.java:327-365) exits unless the first
     // record in its HashMap's iteration order has exactly as many sites as the map file has rows.  Here: every record must.
-    const int64_t S = (int64_t)physical_pos.size();
+    const int64_t S = in.S = (int64_t)in.physical_pos.size();
     for (size_t i = 0; i < fa.names.size(); i++)
         if (fa.lengths[i] != S)
             throw DataFormatError("# sites of FASTA record '" + fa.names[i] + "' (" + std::to_string(fa.lengths[i]) +
                                   ") != # rows in the map file (" + std::to_string(S) + ")");
-    std::vector<int32_t> node_of_record(fa.names.size(), -1);
+    in.node_of_record.assign(fa.names.size(), -1);
     std::vector<uint8_t> seen((size_t)N, 0);
     std::unordered_map<std::string, size_t> last_record;
     for (size_t i = 0; i < fa.names.size(); i++) {
         auto dup = last_record.find(fa.names[i]);           // seg_sites.put(node_name, seq): a repeated name keeps its LAST record
-        if (dup != last_record.end()) node_of_record[dup->second] = -1;
+        if (dup != last_record.end()) in.node_of_record[dup->second] = -1;
         last_record[fa.names[i]] = i;
         auto it = node_of_name.find(fa.names[i]);
         if (it != node_of_name.end()) {
-            node_of_record[i] = it->second;
+            in.node_of_record[i] = it->second;
             seen[it->second] = 1;
         }
     }
@@ -142,15 +154,24 @@ RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
     Phenos ph = read_phenos(a.phenos);
     std::unordered_set<std::string> leaf_names;
     for (int32_t v : tree.leaf_nodes) leaf_names.insert(tree.names[v]);
-    std::vector<int32_t> sample_node;
-    std::vector<uint8_t> label;
     for (size_t i = 0; i < ph.ids.size(); i++) {                      // check_sample_names (HC.java:367-404)
         auto it = node_of_name.find(ph.ids[i]);
         if (it == node_of_name.end() || !leaf_names.count(ph.ids[i]))
             throw DataFormatError("phenotype sample '" + ph.ids[i] + "' is not a leaf of the tree / not in the FASTA");
-        sample_node.push_back(it->second);
-        label.push_back(ph.labels[i] == "1" ? PB_LABEL_CASE : ph.labels[i] == "0" ? PB_LABEL_CONTROL : PB_LABEL_MISSING);
+        in.sample_node.push_back(it->second);
+        in.label.push_back(ph.labels[i] == "1" ? PB_LABEL_CASE : ph.labels[i] == "0" ? PB_LABEL_CONTROL : PB_LABEL_MISSING);
     }
+    return in;
+}
+
+RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
+    PhaseClock clk{a.timing};
+    Inputs in = load_inputs(a);
+    const Tree& tree = in.tree;
+    const FastaFile& fa = *in.fa;
+    const std::vector<int32_t>&physical_pos = in.physical_pos, &node_of_record = in.node_of_record, &sample_node = in.sample_node;
+    const std::vector<uint8_t>& label = in.label;
+    const int64_t N = tree.n_nodes(), S = in.S;
 
     clk.lap("loaders + fasta index");
     Options o;
@@ -272,6 +293,24 @@ int probe(int argc, char** argv) {
     }
     if (cmd == "--x-read-map" && argc == 3) {
         for (int32_t p : read_map(argv[2])) std::printf("%d\n", p);
+        return 0;
+    }
+    if (cmd == "--x-flatten" && argc == 6) {             // fasta tree phenos map -> what the C ABI would be given
+        Args a;
+        a.fasta = argv[2]; a.tree = argv[3]; a.phenos = argv[4]; a.map = argv[5];
+        Inputs in = load_inputs(a);
+        auto dump = [](const char* what, const auto& v) {
+            std::printf("%s", what);
+            for (auto x : v) std::printf(" %d", (int)x);
+            std::printf("\n");
+        };
+        std::printf("n_nodes %" PRId64 " n_sites %" PRId64 "\n", in.tree.n_nodes(), in.S);
+        dump("parent", in.tree.parent);
+        dump("is_leaf", in.tree.is_leaf);
+        dump("node_of_record", in.node_of_record);
+        dump("sample_node", in.sample_node);
+        dump("label", in.label);
+        dump("physical_pos", in.physical_pos);
         return 0;
     }
     if (cmd == "--x-format-doubles" && argc == 2) {      // stdin: one 64-bit pattern in hex per line

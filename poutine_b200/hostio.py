@@ -386,10 +386,9 @@ def write_outputs(out_path: str, sites, stats, physical_pos):
 # -------------------------------------------------------------------------------------------------
 # call() with --use-precomputed-anc-recon
 # -------------------------------------------------------------------------------------------------
-def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_replicates=100000, min_hcount=1, seed=0, device=0,
-                          tile_sites=1 << 14, pack_threads=0, compact_upload=True, extras=False):
-    """Files in, files out: same inputs as `poutine.sh -u -f -t -p -m`, same three result files.
-    `tree_file` is a Newick file with internal node labels, or treetime's annotated_tree.nexus."""
+def load_inputs(fasta, tree_file, pheno_file, map_file):
+    """The part of call() in front of the two entry points (HC.java:230-296): loaders + cross-file checks, flattened to what
+    the C ABI takes.  -> dict(tree, fasta (open FastaFile), physical_pos, n_sites, node_of_record, sample_node, label)"""
     with open(tree_file, newline="", encoding="utf-8", errors="replace") as f:
         text = f.read()
     newick = nexus_to_newick(tree_file) if text.lstrip().upper().startswith("#NEXUS") else text
@@ -426,6 +425,17 @@ def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_
             raise DataFormatError("phenotype sample %r is not a leaf of the tree / not in the FASTA" % name)
     sample_node = np.array([node_of_name[n] for n in phenos], dtype=np.int32)
     label = np.array([1 if v == "1" else 0 if v == "0" else 2 for v in phenos.values()], dtype=np.uint8)
+    return dict(tree=tree, fasta=fa, physical_pos=physical_pos, n_sites=S, node_of_record=node_of_record, sample_node=sample_node,
+                label=label)
+
+
+def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_replicates=100000, min_hcount=1, seed=0, device=0,
+                          tile_sites=1 << 14, pack_threads=0, compact_upload=True, extras=False):
+    """Files in, files out: same inputs as `poutine.sh -u -f -t -p -m`, same three result files.
+    `tree_file` is a Newick file with internal node labels, or treetime's annotated_tree.nexus."""
+    inp = load_inputs(fasta, tree_file, pheno_file, map_file)
+    tree, fa, physical_pos, S = inp["tree"], inp["fasta"], inp["physical_pos"], inp["n_sites"]
+    node_of_record, sample_node, label = inp["node_of_record"], inp["sample_node"], inp["label"]
 
     hc = HomoplasyCounter(num_replicates=num_replicates, min_hcount=min_hcount, device=device, seed=seed)
     hc.set_tree(tree.parent, tree.is_leaf)

@@ -186,6 +186,45 @@ def test_cli_errors_without_gpu_work(tmp_path):
     assert r.returncode == 255 and "cannot open" in r.stderr
 
 
+@pytest.mark.parametrize("nexus,line_width,eol", [(False, 0, "\n"), (True, 70, "\n"), (False, 33, "\r\n")])
+def test_flattened_inputs_agree_between_hosts_and_with_the_oracle(tmp_path, oracle_mod, nexus, line_width, eol):
+    """loaders + cross-file glue of both hosts (load_inputs): same parent / leaf / node_of_record / sample / label arrays; and
+    the alignment they describe — FASTA records packed into the parsed tree's node order — gives the oracle the same
+    Homoplasy_Events, site by site, as the generator's own tree and characters (node numbering differs, results do not).  A
+    repeated record name keeps its LAST record, as seg_sites.put does (HC.java:1255-1266)."""
+    t = synth.yule_tree(40, 21)
+    S = 64 * 3 + 17
+    chars = synth.planes_to_chars(*synth.simulate_planes(t, S, 22, leaf_gap=True, multiallelic_frac=0.05), 0, S)
+    sn, lab = synth.simulate_phenotypes(t, 23, na_frac=0.05, no_row_frac=0.05)
+    paths = synth.write_inputs(str(tmp_path), t, chars, sn, lab, line_width=line_width, eol=eol, nexus=nexus, seed=7)
+    body = open(paths["fasta"], newline="").read()
+    with open(paths["fasta"], "w", newline="") as f:            # an earlier, wrong record of one leaf: must lose against the real one
+        f.write(">" + t.names[int(t.leaf_nodes[3])] + eol + "T" * S + eol + body)
+    r = run("--x-flatten", paths["fasta"], paths["tree"], paths["pheno"], paths["map"])
+    out = dict(l.split(" ", 1) if " " in l else (l, "") for l in r.stdout.strip().split("\n"))
+    cpp = {k: np.array(v.split(), dtype=np.int64) for k, v in out.items() if k not in ("n_nodes",)}
+    inp = hostio.load_inputs(paths["fasta"], paths["tree"], paths["pheno"], paths["map"])
+    tree = inp["tree"]
+    assert out["n_nodes"] == "%d n_sites %d" % (tree.n_nodes, S) and inp["n_sites"] == S
+    assert np.array_equal(cpp["parent"], tree.parent) and np.array_equal(cpp["is_leaf"], tree.is_leaf)
+    assert np.array_equal(cpp["node_of_record"], inp["node_of_record"]) and cpp["node_of_record"][0] == -1
+    assert np.array_equal(cpp["sample_node"], inp["sample_node"]) and np.array_equal(cpp["label"], inp["label"])
+    assert np.array_equal(cpp["physical_pos"], paths["physical_pos"]) and np.array_equal(inp["physical_pos"], paths["physical_pos"])
+    assert [tree.names[v] for v in inp["sample_node"]] == [t.names[int(v)] for v in sn]          # pheno-file order
+    assert np.array_equal(inp["label"], np.where(lab == 1, 1, np.where(lab == 0, 0, 2)))
+    # the alignment in the parsed tree's node order, through the library's FASTA packer
+    W = (S + 63) // 64
+    B0, B1, V = (np.zeros((tree.n_nodes, W), dtype=np.uint64) for _ in range(3))
+    inp["fasta"].pack_tile(inp["node_of_record"], 0, S, B0, B1, V, 2)
+    got_chars = synth.planes_to_chars(B0, B1, V, 0, S)
+    ev_a, cc_a = oracle_mod.Oracle(tree.parent, tree.leaf_nodes).count_all_homoplasy_events(got_chars)
+    ev_b, cc_b = oracle_mod.Oracle(t.parent, t.leaf_nodes).count_all_homoplasy_events(chars)
+    assert cc_a == cc_b and len(ev_a) == len(ev_b) > 20
+    for f in ("segsite_id", "allele1", "allele2", "a1_count", "a2_count", "a1_extant", "a2_extant"):
+        assert np.array_equal(ev_a[f], ev_b[f]), f
+    inp["fasta"].close()
+
+
 def test_cross_file_checks_before_any_device_work(tmp_path):
     """check_num_seg_sites / check_sample_names (HC.java:327-404) and what the reference's site loop implies (HC.java:1383-1394,
     1418): every FASTA record needs exactly as many sites as the map file has rows; every tree node needs a record; every pheno
