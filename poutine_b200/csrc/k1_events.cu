@@ -732,22 +732,20 @@ __global__ void scan_apply(const uint64_t* __restrict__ in, int64_t n, const uin
     if (i < n) out[i] = sums[blockIdx.x] + sh[threadIdx.x] - v;
 }
 
-static uint64_t* g_scan_tmp = nullptr;  // per-process scratch (contexts are single-threaded per device)
-static int64_t g_scan_tmp_cap = 0;
-static int g_scan_tmp_dev = -1;
-
+// The block-sum scratch belongs to the context (it used to be one process-wide buffer keyed by device: two contexts of one
+// process on different GPUs, or driven from different host threads, would have overwritten each other's pointer).
 int pbk_exclusive_scan_u64(pb_ctx* ctx, const uint64_t* in, uint64_t* out, int64_t n, uint64_t* d_total) {
     const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    if (nb > g_scan_tmp_cap || g_scan_tmp_dev != ctx->device) {
-        if (g_scan_tmp && g_scan_tmp_dev == ctx->device) cudaFree(g_scan_tmp);
-        PB_CUDA(cudaMalloc(&g_scan_tmp, (size_t)(nb + 1) * 8));
-        g_scan_tmp_cap = nb;
-        g_scan_tmp_dev = ctx->device;
+    if (nb > ctx->scan_tmp_cap || !ctx->d_scan_tmp) {
+        if (ctx->d_scan_tmp) { cudaFree(ctx->d_scan_tmp); ctx->d_scan_tmp = nullptr; ctx->scan_tmp_cap = 0; }
+        PB_CUDA(cudaMalloc(&ctx->d_scan_tmp, (size_t)(nb + 1) * 8));
+        ctx->scan_tmp_cap = nb;
     }
+    uint64_t* const tmp = ctx->d_scan_tmp;
     if (n == 0) { PB_CUDA(cudaMemsetAsync(d_total, 0, 8, ctx->stream)); return PB_OK; }
-    scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, g_scan_tmp);
-    scan_sums_serial<<<1, SCAN_BLOCK, 0, ctx->stream>>>(g_scan_tmp, nb, d_total);
-    scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, g_scan_tmp, out);
+    scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, tmp);
+    scan_sums_serial<<<1, SCAN_BLOCK, 0, ctx->stream>>>(tmp, nb, d_total);
+    scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, tmp, out);
     ctx->tm.n_launches += 3;
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -912,10 +910,9 @@ static int pbk_events_x(pb_ctx* ctx) {
     q.ops = ctx->d_ops_x; q.chunk_op = ctx->d_chunk_op_x;
     q.raw = reinterpret_cast<xrec_t*>(ctx->d_raw); q.raw_cursor = ctx->d_raw_cursor; q.raw_cap = (unsigned long long)ctx->raw_cap;
     const size_t smem = (size_t)KX_SMEM_TOTAL;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->k1x_attr_set) {     // a function attribute belongs to the device: once per context, not once per process
         PB_CUDA(cudaFuncSetAttribute(k1x_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->k1x_attr_set = true;
     }
     dim3 grid((unsigned)((ctx->W + PB_KX_COLS - 1) / PB_KX_COLS), (unsigned)ctx->n_chunks_x);
     PB_CUDA(cudaMemsetAsync(ctx->d_raw_cursor, 0, 8, ctx->stream));
@@ -938,10 +935,9 @@ int pbk_events(pb_ctx* ctx) {
     p.raw = ctx->d_raw; p.raw_cursor = ctx->d_raw_cursor; p.raw_cap = (unsigned long long)ctx->raw_cap;
     size_t smem = (size_t)K1_SMEM_TOTAL;
     if (const char* e = getenv("PB_K1_SMEM_PAD_KB")) smem += (size_t)atoi(e) * 1024;   // experiment knob: lowers blocks/SM
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->k1_attr_set) {      // a function attribute belongs to the device: once per context, not once per process
         PB_CUDA(cudaFuncSetAttribute(k1_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->k1_attr_set = true;
     }
     dim3 grid((unsigned)((ctx->W + PB_K1_COLS - 1) / PB_K1_COLS), (unsigned)ctx->n_chunks);
     PB_CUDA(cudaMemsetAsync(ctx->d_raw_cursor, 0, 8, ctx->stream));

@@ -209,6 +209,8 @@ struct pb_ctx {
     pb_stat_out* d_stats = nullptr; int64_t stats_cap = 0;
     int32_t* d_work = nullptr; int64_t work_cap = 0;   // 4 work lists of slot ids (k4_classify_kernel), n_slots each
     int64_t n_work[4] = {0, 0, 0, 0};
+    bool k1_attr_set = false, k1x_attr_set = false;              // cudaFuncSetAttribute(max dynamic shared memory) done on this context's device
+    uint64_t* d_scan_tmp = nullptr; int64_t scan_tmp_cap = 0;   // block sums of pbk_exclusive_scan_u64 (per context: contexts of one process may sit on different GPUs / host threads)
     uint32_t* d_colpop = nullptr; int64_t colpop_cap = 0;  // [2][P] per-sample case / missing-label popcounts of the current tile
     int32_t* d_fb_reps = nullptr;  // fallback replicate list
     unsigned int* d_fb_count = nullptr;
