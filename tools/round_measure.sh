@@ -8,6 +8,7 @@ timeout 200 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_
 timeout 120 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2>> gpurun_out/${tag}_bench.err
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu1.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:k1x_events -c 1 -o gpurun_out/${tag}_k1x -f python tools/k1_quick.py --steps 1 > gpurun_out/${tag}_ncu2.log 2>&1
+timeout 120 python tools/bench_native_host.py 100000 16384 > gpurun_out/${tag}_native_host.json 2>> gpurun_out/${tag}_bench.err   # files-in/files-out, native host
 if [ -n "$2" ]; then
   timeout 120 python bench.py --config C1 --no-cpu-baseline > gpurun_out/${tag}_bench_C1.json 2>> gpurun_out/${tag}_bench.err
   timeout 200 python bench.py --config C3 --sites 625000 --no-cpu-baseline > gpurun_out/${tag}_bench_C3shard.json 2>> gpurun_out/${tag}_bench.err
