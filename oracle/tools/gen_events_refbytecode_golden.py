@@ -55,6 +55,41 @@ CASES = [
 ]
 
 
+# Second set (python gen_events_refbytecode_golden.py extra -> tests/golden/{events,assoc}_refbytecode_extra.json): degenerate
+# topologies and phenotypes the first set does not reach — every leaf on the root (no testable edge at all), a ladder, two
+# leaves, nearly every sample without a pheno row or with a missing label, only cases / only controls (background p = 1 / 0:
+# the binomial chain's boundary branches), min_hcount above every count but one.  Used by the oracle tests only.
+CASES_EXTRA = [
+    dict(name="star", kind="star", leaves=12, tseed=711, S=90, cseed=811, nasty=True, m=60, min_hcount=0, na_frac=0.1, no_row_frac=0.1),
+    dict(name="caterpillar", kind="caterpillar", leaves=25, tseed=712, S=120, cseed=812, nasty=True, m=80, min_hcount=1, na_frac=0.05,
+         no_row_frac=0.05),
+    dict(name="two_leaves", kind="star", leaves=2, tseed=713, S=40, cseed=813, nasty=True, m=20, min_hcount=0, na_frac=0.0, no_row_frac=0.0),
+    dict(name="few_pheno_rows", leaves=50, tseed=714, polytomy=0.3, root_leaf_children=1, S=120, cseed=814, nasty=True, m=80, min_hcount=1,
+         na_frac=0.3, no_row_frac=0.6),
+    dict(name="all_cases", leaves=40, tseed=715, polytomy=0.2, root_leaf_children=1, S=100, cseed=815, nasty=False, m=60, min_hcount=1,
+         na_frac=0.1, no_row_frac=0.0, labels="all_cases"),
+    dict(name="all_controls", leaves=40, tseed=716, polytomy=0.2, root_leaf_children=1, S=100, cseed=816, nasty=False, m=60, min_hcount=1,
+         na_frac=0.0, no_row_frac=0.1, labels="all_controls"),
+    dict(name="min_hcount_4", leaves=60, tseed=717, polytomy=0.1, root_leaf_children=0, S=150, cseed=817, nasty=False, m=60, min_hcount=4,
+         na_frac=0.02, no_row_frac=0.02),
+]
+
+
+def make_tree(c):
+    kind = c.get("kind", "random")
+    if kind == "star":                      # every leaf hangs off the root: all edges are root edges, never tested (HC.java:1678)
+        n = c["leaves"]
+        rng = np.random.default_rng(c["tseed"])
+        perm = rng.permutation(n + 1)
+        parent = np.full(n + 1, -1, dtype=np.int32)
+        for old in range(1, n + 1):
+            parent[perm[old]] = perm[0]
+        return synth._finish_tree(parent, rng)
+    if kind == "caterpillar":
+        return synth.caterpillar_tree(c["leaves"], c["tseed"])
+    return synth.random_tree(c["leaves"], c["tseed"], polytomy=c["polytomy"], root_leaf_children=c["root_leaf_children"])
+
+
 def bits(x):
     return "%016x" % int(np.float64(x).view(np.uint64))
 
@@ -65,7 +100,7 @@ def names_of(tree):
 
 
 def run_case(c):
-    tree = synth.random_tree(c["leaves"], c["tseed"], polytomy=c["polytomy"], root_leaf_children=c["root_leaf_children"])
+    tree = make_tree(c)
     S = c["S"]
     if c["nasty"]:
         chars = synth.simulate_chars(tree, S, c["cseed"], nasty=True)
@@ -108,6 +143,10 @@ def run_case(c):
     # ---- entry point 2 on the same interpreter state
     m, mh = c["m"], c["min_hcount"]
     sample_node, label = synth.simulate_phenotypes(tree, c["tseed"] + 50, na_frac=c["na_frac"], no_row_frac=c["no_row_frac"])
+    if c.get("labels") == "all_cases":
+        label = np.where(label == 2, 2, 1).astype(label.dtype)
+    elif c.get("labels") == "all_controls":
+        label = np.where(label == 2, 2, 0).astype(label.dtype)
     label_str = [{0: "0", 1: "1"}.get(int(x), "NA") for x in label]
     t0 = time.time()
     n0 = ref.vm.n_bytecodes
@@ -144,19 +183,21 @@ def run_case(c):
 
 
 if __name__ == "__main__":
-    both = [run_case(c) for c in CASES]
+    extra = len(sys.argv) > 1 and sys.argv[1] == "extra"
+    suffix = "_extra" if extra else ""
+    both = [run_case(c) for c in (CASES_EXTRA if extra else CASES)]
     out = {"source": "count_all_homoplasy_events executed from /root/reference/compiled/Homoplasy_Counter.class + coevolution.jar by "
                      "oracle/tools/refjvm.py (bytecode interpreter; JDK collections emulated with HashMap's iteration order)",
            "cases": [b[0] for b in both]}
-    path = os.path.join(ROOT, "tests", "golden", "events_refbytecode.json")
+    path = os.path.join(ROOT, "tests", "golden", "events_refbytecode%s.json" % suffix)
     with open(path, "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print(path, os.path.getsize(path), "bytes")
     out = {"source": "subset_by_min_hcount + resample_all_mutations_binom_test_combined_nulldists_memoization_concurrent executed from "
                      "/root/reference/compiled/*.class + commons-math3-3.6.1.jar by oracle/tools/refjvm.py on the events of "
-                     "events_refbytecode.json (same case names); replicates serial, Collections.shuffle seeded; doubles as hex bit patterns",
+                     "events_refbytecode%s.json (same case names); replicates serial, Collections.shuffle seeded; doubles as hex bit patterns" % suffix,
            "cases": [b[1] for b in both]}
-    path = os.path.join(ROOT, "tests", "golden", "assoc_refbytecode.json")
+    path = os.path.join(ROOT, "tests", "golden", "assoc_refbytecode%s.json" % suffix)
     with open(path, "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print(path, os.path.getsize(path), "bytes")

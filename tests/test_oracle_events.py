@@ -27,21 +27,24 @@ def test_hand_derived_fixture(oracle_mod, golden_dir):
     assert cc == fx["class_counts"]
 
 
-def refbytecode_cases(golden_dir):
+def refbytecode_cases(golden_dir, suffix=""):
     """tests/golden/events_refbytecode.json: what the reference's own compiled count_all_homoplasy_events produced
-    (executed from Homoplasy_Counter.class by oracle/tools/refjvm.py, see gen_events_refbytecode_golden.py)."""
-    with open(os.path.join(golden_dir, "events_refbytecode.json")) as f:
+    (executed from Homoplasy_Counter.class by oracle/tools/refjvm.py, see gen_events_refbytecode_golden.py).
+    suffix="_extra": the second set (degenerate topologies and phenotypes), used by the oracle tests only."""
+    with open(os.path.join(golden_dir, "events_refbytecode%s.json" % suffix)) as f:
         fx = json.load(f)
     for c in fx["cases"]:
         chars = np.array([[ord(ch) for ch in row] for row in c["rows"]], dtype=np.uint8)
         yield c, chars
 
 
-def test_oracle_matches_reference_bytecode(oracle_mod, golden_dir):
+@pytest.mark.parametrize("suffix,min_sites", [("", 400), ("_extra", 500)])
+def test_oracle_matches_reference_bytecode(oracle_mod, golden_dir, suffix, min_sites):
     """THE pin of rows a1-a5: every Homoplasy_Events field, both MRCA node sets and the class counters the reference logs,
-    for 5 seeded alignments on nasty topologies, as computed by the reference's bytecode."""
+    for 5 seeded alignments on nasty topologies, as computed by the reference's bytecode; the second set adds a star tree
+    (no testable edge), a ladder, a two-leaf tree and four more."""
     n_sites = 0
-    for c, chars in refbytecode_cases(golden_dir):
+    for c, chars in refbytecode_cases(golden_dir, suffix):
         o = oracle_mod.Oracle(c["parent"], c["leaf_nodes"])
         ev, cc = o.count_all_homoplasy_events(chars, np.asarray(c["physical_pos"], dtype=np.int32))
         assert cc == c["class_counts"], c["name"]
@@ -55,7 +58,7 @@ def test_oracle_matches_reference_bytecode(oracle_mod, golden_dir):
             assert sorted(names[o.mrca(i, 0)].tolist()) == r["a1_mrcas"], (c["name"], i)
             assert sorted(names[o.mrca(i, 1)].tolist()) == r["a2_mrcas"], (c["name"], i)
         n_sites += len(ev)
-    assert n_sites > 400
+    assert n_sites > min_sites
 
 
 def _f64(hexbits):
@@ -82,27 +85,30 @@ def assert_stats_equal_refbytecode(st, mt_sorted, mt_unsorted, p_success, a):
             assert (np.isnan(row[k]) and np.isnan(want)) or bits(row[k]) == r[k], tag + (k, float(row[k]), float(want))
 
 
-def assoc_refbytecode_cases(golden_dir):
+def assoc_refbytecode_cases(golden_dir, suffix=""):
     """(events case, chars, assoc case) triples: assoc_refbytecode.json holds what the reference's compiled
     subset_by_min_hcount + resampling driver (+ commons-math's own bytecode) produced on the events of the same-named case."""
-    with open(os.path.join(golden_dir, "assoc_refbytecode.json")) as f:
+    with open(os.path.join(golden_dir, "assoc_refbytecode%s.json" % suffix)) as f:
         fa = {c["name"]: c for c in json.load(f)["cases"]}
-    for c, chars in refbytecode_cases(golden_dir):
+    for c, chars in refbytecode_cases(golden_dir, suffix):
         yield c, chars, fa[c["name"]]
 
 
-def test_oracle_assoc_matches_reference_bytecode(oracle_mod, golden_dir):
+@pytest.mark.parametrize("suffix,min_sites", [("", 400), ("_extra", 350)])
+def test_oracle_assoc_matches_reference_bytecode(oracle_mod, golden_dir, suffix, min_sites):
     """THE pin of rows a6-a11: observed tallies, binomial p-values, r counts, per-replicate min p, point-wise and
-    family-wise estimates of the reference's own bytecode, replayed through the oracle with the recorded shuffles."""
+    family-wise estimates of the reference's own bytecode, replayed through the oracle with the recorded shuffles.  The second
+    set: alleles with n = 0 (min_hcount 0 on a star tree), 17 pheno rows for 50 leaves, 30 % missing labels, only cases / only
+    controls (background p = 1 / 0: the boundary branches of the binomial chain), min_hcount = 4."""
     n = 0
-    for c, chars, a in assoc_refbytecode_cases(golden_dir):
+    for c, chars, a in assoc_refbytecode_cases(golden_dir, suffix):
         o = oracle_mod.Oracle(c["parent"], c["leaf_nodes"])
         o.count_all_homoplasy_events(chars, np.asarray(c["physical_pos"], dtype=np.int32))
         st, mt_s, mt_u = o.assoc(np.asarray(a["sample_node"]), np.asarray(a["label"], dtype=np.uint8), a["m"], a["min_hcount"],
                                  perms=np.asarray(a["perms"], dtype=np.uint32))
         assert_stats_equal_refbytecode(st, mt_s, mt_u, o.p_success, a)
         n += len(st)
-    assert n > 400
+    assert n > min_sites
 
 
 @pytest.mark.parametrize("seed", range(12))
