@@ -37,6 +37,39 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.PbTimings) == 10 * 4 + 8 * 8
 
 
+def test_struct_layouts_match_the_c_header_itself(tmp_path):
+    """sizes and field offsets as the C compiler sees include/poutine_b200.h == the ctypes / numpy mirrors == the numbers
+    INTEGRATION.md gives the Java host (pb_config 56 B, pb_class_counts 48 B, pb_site_out 32 B, pb_stat_out 96 B)"""
+    import subprocess
+    fields = {"pb_config": [n for n, _ in _lib.PbConfig._fields_], "pb_class_counts": [n for n, _ in _lib.PbClassCounts._fields_],
+              "pb_timings": [n for n, _ in _lib.PbTimings._fields_], "pb_site_out": list(_lib.SITE_DTYPE.names),
+              "pb_stat_out": list(_lib.STAT_DTYPE.names)}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "poutine_b200.h"', 'int main(void) {']
+    for st, names in fields.items():
+        src.append('printf("%s %%zu\\n", sizeof(%s));' % (st, st))
+        for n in names:
+            src.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (st, n, st, n))
+    src.append("return 0; }")
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = str(tmp_path / "layout")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), str(c), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True).stdout.splitlines())
+    got = {k: int(v) for k, v in got.items()}
+    assert (got["pb_config"], got["pb_class_counts"], got["pb_site_out"], got["pb_stat_out"]) == (56, 48, 32, 96)
+    for st, cls in (("pb_config", _lib.PbConfig), ("pb_class_counts", _lib.PbClassCounts), ("pb_timings", _lib.PbTimings)):
+        assert got[st] == ctypes.sizeof(cls)
+        for n, _ in cls._fields_:
+            assert got[st + "." + n] == getattr(cls, n).offset, (st, n)
+    for st, dt in (("pb_site_out", _lib.SITE_DTYPE), ("pb_stat_out", _lib.STAT_DTYPE)):
+        assert got[st] == dt.itemsize
+        for n in dt.names:
+            assert got[st + "." + n] == dt.fields[n][1], (st, n)
+    # the offsets the FFM stub in INTEGRATION.md writes pb_config through
+    assert [got["pb_config." + n] for n in ("device", "mode", "n_replicates", "min_hcount", "seed")] == [0, 4, 8, 16, 24]
+
+
 def test_packer_matches_reference_char_tests(lib):
     rng = np.random.default_rng(0)
     alphabet = np.frombuffer(b"ACGTacgtN-nRYKM?*", dtype=np.uint8)
