@@ -258,7 +258,35 @@ FASTA_CASES = [
 ]
 
 
+def fuzz_cases():
+    """seeded token soups: what a hand-written list does not think of"""
+    import random
+    rnd = random.Random(20261)
+    nw, fa = [], []
+    pieces = ["(", ")", ",", ":", ";", " ", "\t", "\n", "A", "B", "C1", "x_y", "1", "0.5", "2e-3", "-1", ".", "e", "'", "[", "]", "\u00a0", "+", "1f", "NaN"]
+    for _ in range(260):
+        k = rnd.randint(1, 14)
+        nw.append("".join(rnd.choice(pieces) for _ in range(k)))
+    for _ in range(60):                                   # mostly well-formed trees with one random edit
+        base = rnd.choice(["((A:1,B:2)N1:3,(C:4,D:5)N2:6)R;", "(A,B,(C,D)I)R;", "((A,(B,C)X)Y,D);", "(A:0.1,B:0.2,C:0.3);"])
+        i = rnd.randrange(len(base))
+        edit = rnd.choice(["del", "ins", "sub"])
+        ch = rnd.choice(pieces)
+        nw.append(base[:i] + ("" if edit == "del" else ch) + (base[i:] if edit == "ins" else base[i + 1:]))
+    fpieces = [b">", b"A", b"C", b"G", b"T", b"N", b"-", b"a", b" ", b"\t", b"\n", b"\r", b"\r\n", b"ACGT", b">S1", b">n 2 ", b"\n>", b"\r>"]
+    for _ in range(200):
+        k = rnd.randint(0, 12)
+        raw = b"".join(rnd.choice(fpieces) for _ in range(k))
+        if rnd.random() < 0.7:
+            raw = b">" + raw                              # most start with a header, as a FASTA file must
+        fa.append(raw)
+    return nw, fa
+
+
 def main():
+    fz_nw, fz_fa = fuzz_cases()
+    NEWICK_CASES.extend(fz_nw)
+    FASTA_CASES.extend(fz_fa)
     out = {"comment": "generated by oracle/tools/gen_loaders_refbytecode_golden.py from the reference's bytecode (coevolution.jar "
                       "NewickTreeTokenizer/NewickTreeReader, compiled/Fasta_Manager.class, Fasta_Record.class); do not edit",
            "newick": [], "fasta": []}

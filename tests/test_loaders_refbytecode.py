@@ -104,8 +104,8 @@ def test_fasta_index_and_packer_match_reference_reader(case, tmp_path):
 
 def test_fixture_covers_what_it_claims():
     nw, fa = GOLD["newick"], GOLD["fasta"]
-    assert len(nw) >= 40 and sum("throws" in c for c in nw) >= 15 and sum("nodes" in c for c in nw) >= 20
+    assert len(nw) >= 350 and sum("throws" in c for c in nw) >= 15 and sum("nodes" in c for c in nw) >= 20
     assert any(c.get("throws") == "NumberFormatException" for c in nw)
     assert any(any(n["id"] is None for n in c.get("nodes", [])) for c in nw)                 # unnamed nodes
-    assert len(fa) >= 20 and sum(bool(c.get("exit")) for c in fa) == 2
+    assert len(fa) >= 200 and sum(bool(c.get("exit")) for c in fa) >= 2
     assert any("\r" in c["raw_latin1"] and "\n" not in c["raw_latin1"] for c in fa)          # bare-CR line ends
