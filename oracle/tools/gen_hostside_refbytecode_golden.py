@@ -316,7 +316,29 @@ MAPS = [
 ]
 
 
+def fuzz_cases():
+    """seeded byte soups for the three text readers"""
+    import random
+    rnd = random.Random(20262)
+    ph, mp, nx = [], [], []
+    pp = [b"s1", b"s2", b"s3", b"\t", b"\t", b"\n", b"\r\n", b"\r", b"0", b"1", b"NA", b" ", b"", b"x"]
+    for _ in range(120):
+        ph.append(b"".join(rnd.choice(pp) for _ in range(rnd.randint(0, 14))))
+    mm = [b"1", b"23", b"-4", b"+5", b"\t", b"\t", b"\n", b"\r\n", b"snp", b" ", b"007", b"2147483647", b"2147483648", b"x", b"1_0", b"\r"]
+    for _ in range(120):
+        mp.append(b"".join(rnd.choice(mm) for _ in range(rnd.randint(0, 12))))
+    nn = [b"#NEXUS\n", b"Begin Trees;\n", b"begin trees;\r\n", b"BEGIN TREES;", b" Begin Trees;\n", b"End;\n", b"\n", b"Tree t=", b"[&U]", b"(A:1,B:2)R;",
+          b"(A[&x]:1,", b"B)", b"[", b"]", b"(", b";", b"\r", b" "]
+    for _ in range(80):
+        nx.append(b"#NEXUS\n" + b"".join(rnd.choice(nn) for _ in range(rnd.randint(0, 10))))
+    return nx, ph, mp
+
+
 def main():
+    fx, fp, fm = fuzz_cases()
+    NEXUS.extend(fx)
+    PHENOS.extend(fp)
+    MAPS.extend(fm)
     out = {"comment": "generated by oracle/tools/gen_hostside_refbytecode_golden.py from compiled/Homoplasy_Counter.class; do not edit",
            "nexus": [], "phenos": [], "map": [], "writer": []}
     for raw in NEXUS:
