@@ -322,15 +322,48 @@ def fuzz_cases():
     rnd = random.Random(20262)
     ph, mp, nx = [], [], []
     pp = [b"s1", b"s2", b"s3", b"\t", b"\t", b"\n", b"\r\n", b"\r", b"0", b"1", b"NA", b" ", b"", b"x"]
-    for _ in range(120):
+    for _ in range(40):
         ph.append(b"".join(rnd.choice(pp) for _ in range(rnd.randint(0, 14))))
+    for _ in range(80):                                     # mostly well-formed rows, now and then a broken one
+        rows = []
+        for i in range(rnd.randint(1, 8)):
+            sid = rnd.choice([b"s%d" % rnd.randint(1, 6), b"S 0%d" % i, b"id_7", b"a.b-c"])
+            lab = rnd.choice([b"0", b"1", b"1", b"NA", b"", b"2", b"01", b" 1"])
+            row = sid + b"\t" + lab + rnd.choice([b"", b"", b"\textra", b"\t", b"\t\t"])
+            if rnd.random() < 0.04:
+                row = rnd.choice([sid, b"", sid + b" " + lab])
+            rows.append(row + rnd.choice([b"\n", b"\n", b"\r\n", b"\r"]))
+        if rnd.random() < 0.3:
+            rows[-1] = rows[-1].rstrip(b"\r\n")              # no final line terminator
+        ph.append(b"".join(rows))
     mm = [b"1", b"23", b"-4", b"+5", b"\t", b"\t", b"\n", b"\r\n", b"snp", b" ", b"007", b"2147483647", b"2147483648", b"x", b"1_0", b"\r"]
-    for _ in range(120):
+    for _ in range(40):
         mp.append(b"".join(rnd.choice(mm) for _ in range(rnd.randint(0, 12))))
+    for _ in range(80):
+        rows = []
+        for i in range(rnd.randint(1, 8)):
+            pos = rnd.choice([b"%d" % rnd.randint(0, 5000000), b"+%d" % i, b"-%d" % i, b"00%d" % i, b"2147483647", b"-2147483648"])
+            row = rnd.choice([b"", b"1\t", b"1\tsnp%d\t0\t" % i, b"chr 1\t"]) + pos + rnd.choice([b"", b"", b"\t", b"\t\t"])
+            if rnd.random() < 0.04:
+                row = rnd.choice([b"", b"1\tx", pos + b" ", b"1\t2147483648", b"1\t1.0"])
+            rows.append(row + rnd.choice([b"\n", b"\n", b"\r\n", b"\r"]))
+        if rnd.random() < 0.3:
+            rows[-1] = rows[-1].rstrip(b"\r\n")
+        mp.append(b"".join(rows))
     nn = [b"#NEXUS\n", b"Begin Trees;\n", b"begin trees;\r\n", b"BEGIN TREES;", b" Begin Trees;\n", b"End;\n", b"\n", b"Tree t=", b"[&U]", b"(A:1,B:2)R;",
           b"(A[&x]:1,", b"B)", b"[", b"]", b"(", b";", b"\r", b" "]
-    for _ in range(80):
+    for _ in range(30):
         nx.append(b"#NEXUS\n" + b"".join(rnd.choice(nn) for _ in range(rnd.randint(0, 10))))
+    for _ in range(50):                                     # treetime-shaped files with varied spelling, annotations and line ends
+        eol = rnd.choice([b"\n", b"\n", b"\r\n", b"\r"])
+        begin = rnd.choice([b"Begin Trees;", b"begin trees;", b"BEGIN TREES;", b"Begin Trees;", b"Begin trees;", b"Begin Trees; ", b"Begin  Trees;"])
+        ann = lambda: rnd.choice([b"", b"", b'[&mutations="A1C,G7T"]', b"[&x]", b"[]", b"[&a=[1]"])
+        tree = b"(A" + ann() + b":1,(B:2" + ann() + b",C" + ann() + b":3)N1" + ann() + b":0.5)N0" + ann() + b":0;"
+        head = rnd.choice([b" Tree tree1=[&U]", b"Tree t = [&R] ", b"", b"\tTREE x=", b"Tree tree1="])
+        body = b"#NEXUS" + eol + b"Begin Taxa;" + eol + b" Dimensions NTax=3;" + eol + b"End;" + eol + begin + eol + head + tree + eol + b"End;" + eol
+        if rnd.random() < 0.1:
+            body = body.replace(tree, tree.replace(b"(", b"", 1) if rnd.random() < 0.5 else b"")
+        nx.append(body)
     return nx, ph, mp
 
 
