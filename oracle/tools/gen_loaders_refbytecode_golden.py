@@ -31,7 +31,6 @@ import unicodedata
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
-import refjvm  # noqa: E402
 from minijvm import JavaThrow, JObject, _f32  # noqa: E402
 from refjvm import JStringBuilder, RefJVM, _impl  # noqa: E402
 

@@ -49,7 +49,6 @@ for c in h["map"]:
 env["ASAN_OPTIONS"] = "detect_leaks=1"
 for c in g["fasta"]:
     for threads in ("1", "3"):
-        runs -= 0
         p = os.path.join(d, "a.fasta")
         with open(p, "wb") as f:
             f.write(c["raw_latin1"].encode("latin-1"))
