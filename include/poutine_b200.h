@@ -132,7 +132,8 @@ int pb_set_tree(pb_ctx* ctx, int32_t n_nodes, const int32_t* parent, const uint8
  * the leaf's node index and its label code.  Leaves without a row are simply absent. */
 int pb_set_labels(pb_ctx* ctx, int32_t n_samples, const int32_t* sample_node, const uint8_t* label);
 
-/* Number of sites this context holds; (re)allocates the device planes. */
+/* Number of sites this context holds (1 .. 2^26; a longer alignment is sharded over contexts / a pb_group);
+ * (re)allocates the device planes. */
 int pb_set_sites(pb_ctx* ctx, int64_t n_sites);
 
 /* Node-major bit planes of `seg_sites` (HC.java:1241-1306): 2-bit base code A0 C1 G2 T3 in

@@ -100,13 +100,22 @@ __device__ __forceinline__ void emit_events(lane_t mrca, lane_t b0, lane_t b1, u
     }
 }
 
-// consumers only: move the block's queued records (U 16-byte units each) to the global list (one global atomic)
+// consumers only: move the block's queued records (U 16-byte units each) to the global list (one global atomic).
+// The drain decision must be block-uniform: every consumer evaluates "queue at least `threshold` full" on its own read of the
+// counter BEFORE it arrives, and the arrival barrier ORs the votes (bar.red.or).  All pushes of a consumer precede its own
+// arrival, so after the barrier either nobody drains (and consumers may push again at once) or everybody does — then no
+// consumer pushes until the last barrier below, and the count every thread reads after the vote is the same, final one.
+// (A per-thread re-read of the counter after a plain barrier let a fast consumer push between a slow consumer's barrier
+// and its read: the two could disagree about draining and fall out of barrier phase.)
 template <int QCAP, int CONSUMERS, int U>
 __device__ __noinline__ void drain_queue(const uint4* s_queue, unsigned int* s_count, unsigned long long* s_base, int tid,
                                          unsigned int threshold, void* raw, unsigned long long* raw_cursor, unsigned long long raw_cap) {
-    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
-    const unsigned int n = min(*s_count, (unsigned int)QCAP);
-    if (n >= threshold && n > 0) {   // block-uniform
+    const unsigned int seen = *reinterpret_cast<volatile unsigned int*>(s_count);
+    int go;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 1, %2, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+                 : "=r"(go) : "r"((unsigned int)(seen >= threshold && seen > 0)), "n"(CONSUMERS) : "memory");
+    if (go) {   // block-uniform (the barrier's OR)
+        const unsigned int n = min(*reinterpret_cast<volatile unsigned int*>(s_count), (unsigned int)QCAP);
         if (tid == 0) *s_base = atomicAdd(raw_cursor, (unsigned long long)n);
         asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
         const unsigned long long base = *s_base;

@@ -85,7 +85,8 @@ template <int MODE, bool MISS>
 __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
                                                              int32_t n_ctrl, const uint8_t* __restrict__ label,
                                                              const uint32_t* __restrict__ perms, uint32_t* __restrict__ Xc32,
-                                                             uint32_t* __restrict__ Xm32, int64_t Rw32, int force_replay = 0) {
+                                                             uint32_t* __restrict__ Xm32, int64_t Rw32, int force_replay = 0,
+                                                             unsigned long long* __restrict__ replay_err = nullptr) {
     __shared__ uint32_t sc[GEN_ROWS][GEN_WORDS], sm[MISS ? GEN_ROWS : 1][GEN_WORDS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rep_local = (int64_t)blockIdx.x * GEN_THREADS + tid;
@@ -96,6 +97,11 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
     if (MODE == 0 && !MISS && !active) rem_case = 0;     // padding replicates of the last block never draw a case: bits stay 0
     const uint32_t* prow = (MODE == 1 && active) ? perms + rep_local * (int64_t)P : nullptr;
     uint32_t range = (uint32_t)P;                         // samples not yet labelled (Philox mode)
+    // replay mode: the caller's rows are checked while they are consumed — an index >= P is clamped and flagged (it would be an
+    // out-of-bounds read of label[]), and a row whose index sum / sum of squares is not a permutation's is flagged as well (a
+    // repeated index changes the replicate's case / control totals).  pb_run_assoc returns PB_ERR_INVALID on either.
+    uint64_t psum = 0, psq = 0;
+    bool pbad = false;
 
     // one sample: Lemire draw in [0, range) with exact rejection, label, ballot -> one 32-replicate word per warp
     auto draw = [&](uint32_t x, int i, int row) {
@@ -123,7 +129,10 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
             else if (u < rem_case + rem_ctrl) { lab = 0; rem_ctrl--; }
             else lab = 2;
         } else {
-            lab = active ? label[prow[i]] : 0;
+            uint32_t idx = active ? prow[i] : 0u;
+            if (idx >= (uint32_t)P) { pbad = true; idx = 0; }
+            psum += idx; psq += (uint64_t)idx * idx;
+            lab = active ? label[idx] : 0;
         }
         const uint32_t bc = (MODE == 0 && !MISS) ? __ballot_sync(0xffffffffu, lab != 0) : __ballot_sync(0xffffffffu, active && lab == 1);
         if (lane == 0) sc[row][warp] = bc;
@@ -188,6 +197,16 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
             if (MISS) Xm32[o] = sm[row][wd];
         }
         __syncthreads();
+    }
+    if (MODE == 1 && active && replay_err) {
+        const uint64_t n = (uint64_t)P;
+        const uint64_t want_sum = n * (n - 1) / 2;
+        // (n-1) n (2n-1) / 6 without overflow for n < 2^21: one of n, n-1 is even, one of n-1, n, 2n-1 is a multiple of 3
+        uint64_t a = n - 1, b = n, c = 2 * n - 1;
+        if (a % 2 == 0) a /= 2; else b /= 2;
+        if (a % 3 == 0) a /= 3; else if (b % 3 == 0) b /= 3; else c /= 3;
+        if (pbad) atomicOr(replay_err, 1ull);
+        else if (psum != want_sum || psq != a * b * c) atomicOr(replay_err, 2ull);
     }
 }
 
@@ -813,6 +832,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     }
     fill_u64_kernel<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(ctx->d_maxT, m, 0x7FF0000000000000ull);
     PB_CUDA(cudaMemsetAsync(ctx->d_r, 0, (size_t)n_slots * 4, st));
+    PB_CUDA(cudaMemsetAsync(ctx->d_class_counts + 12, 0, 8, st));   // replay-permutation check flag (k3_gen_kernel<1, .>)
     ctx->tm.n_launches += 1;
 
     K3Plan pl;
@@ -855,10 +875,12 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
             PB_CUDA(cudaMemcpyAsync(ctx->d_perms, replay_perms + base * (int64_t)ctx->P, (size_t)bytes, cudaMemcpyHostToDevice, st));
             if (has_miss)
                 k3_gen_kernel<1, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
-                                                                       ctx->d_perms, (uint32_t*)ctx->d_Xcase, (uint32_t*)ctx->d_Xmiss, Rw32);
+                                                                       ctx->d_perms, (uint32_t*)ctx->d_Xcase, (uint32_t*)ctx->d_Xmiss, Rw32, 0,
+                                                                       ctx->d_class_counts + 12);
             else
                 k3_gen_kernel<1, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,
-                                                                        ctx->d_perms, (uint32_t*)ctx->d_Xcase, nullptr, Rw32);
+                                                                        ctx->d_perms, (uint32_t*)ctx->d_Xcase, nullptr, Rw32, 0,
+                                                                        ctx->d_class_counts + 12);
             ctx->tm.n_launches += 1;
             // replay_perms is caller-owned pageable memory: the copy above is staged synchronously by the runtime
         } else if (base == 0 && ctx->pregen_valid && ctx->pregen_tile == tile) {
@@ -936,8 +958,15 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     pb_trace_mark(ctx, "allreduce+pvalues");
     struct { unsigned long long nf; unsigned int lc[4]; unsigned long long fb; } hb;   // layout of the scratch block in pbk_thresholds
     PB_CUDA(cudaMemcpyAsync(&hb, ctx->d_nfast, sizeof(hb), cudaMemcpyDeviceToHost, st));
+    unsigned long long replay_err = 0;
+    PB_CUDA(cudaMemcpyAsync(&replay_err, ctx->d_class_counts + 12, 8, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
     PB_CUDA(cudaGetLastError());
+    if (replay_err) {
+        ctx->err = (replay_err & 1ull) ? "pb_run_assoc: replay_perms holds an index >= n_samples"
+                                       : "pb_run_assoc: a row of replay_perms is not a permutation of 0 .. n_samples-1";
+        return PB_ERR_INVALID;
+    }
     float t;
     cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]); ctx->tm.ms_tally = t;
     cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4]); ctx->tm.ms_ptable = t;

@@ -357,9 +357,9 @@ int pbk_pvalues(pb_ctx* ctx) {
     }
     const int T = 256;
     {
-        static int max_blocks_per_sm = -1;
-        if (max_blocks_per_sm < 0) PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, k4_sort_coop_kernel, 1024, 0));
-        int64_t grid = std::min<int64_t>(n_pad / BSORT_TILE, (int64_t)std::max(max_blocks_per_sm, 1) * ctx->sm_count);
+        if (ctx->sort_blocks_per_sm < 0)   // occupancy belongs to the context's device (contexts of one process may sit on different GPUs / threads)
+            PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sort_blocks_per_sm, k4_sort_coop_kernel, 1024, 0));
+        int64_t grid = std::min<int64_t>(n_pad / BSORT_TILE, (int64_t)std::max(ctx->sort_blocks_per_sm, 1) * ctx->sm_count);
         const unsigned long long* a_maxT = ctx->d_maxT;
         int64_t a_m = m, a_npad = n_pad;
         double* a_out = ctx->d_maxT_sorted;

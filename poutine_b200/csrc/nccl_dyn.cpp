@@ -8,6 +8,8 @@
 #include <dlfcn.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "pb_internal.h"
 
 typedef struct ncclComm* ncclComm_t;
@@ -26,10 +28,10 @@ struct NcclApi {
 };
 
 static NcclApi* nccl_api(std::string& err) {
+    // contexts of one process may be driven from different host threads (pb_group does): resolve the table exactly once
     static NcclApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char* n : names) {
             api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -42,7 +44,7 @@ static NcclApi* nccl_api(std::string& err) {
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
         }
-    }
+    });
     if (!api.h || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
         err = "NCCL not available: dlopen(libnccl.so.2) failed or symbols missing";
         return nullptr;

@@ -52,8 +52,7 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     auto fail = [&](const char* what, cudaError_t ce) {
         g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
-        free_all(ctx);
-        delete ctx;
+        pb_destroy(ctx);      // streams and events created so far go too (every handle starts out null)
         return PB_ERR_CUDA;
     };
     if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("cudaSetDevice", e);
@@ -421,7 +420,9 @@ static int ensure_plane_mode(pb_ctx* ctx, int want) {
 extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
     CHECK_CTX(ctx);
     if (ctx->N == 0) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: call pb_set_tree first");
-    if (n_sites < 1 || n_sites >= (1ll << 32)) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: n_sites out of range");
+    // the tail packs (informative-site count << 38 | extant-event count) into one scan word and indexes sites with int32:
+    // 2^26 sites per context is the supported limit (shard a longer alignment over several contexts, site_offset)
+    if (n_sites < 1 || n_sites > PB_MAX_SITES_PER_CTX) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: n_sites out of range (1 .. 2^26 per context)");
     PB_CUDA(cudaSetDevice(ctx->device));
     ctx->events_done = ctx->assoc_done = false;
     if (n_sites == ctx->S && ctx->plane_mode != PB_PLANES_NONE) return PB_OK;   // same shape: the uploaded planes stay
@@ -639,7 +640,8 @@ extern "C" int pb_get_event_csr(pb_ctx* ctx, int64_t* offsets, int32_t* sample_i
     CHECK_CTX(ctx);
     if (!ctx->events_done) FAIL(ctx, PB_ERR_INVALID, "pb_get_event_csr: no results");
     PB_CUDA(cudaSetDevice(ctx->device));
-    if (cap < ctx->E) FAIL(ctx, PB_ERR_INVALID, "pb_get_event_csr: buffer too small");
+    if (!offsets) FAIL(ctx, PB_ERR_INVALID, "pb_get_event_csr: offsets is NULL (2*n_inf+1 entries; sizes are in pb_get_timings)");
+    if (sample_index && cap < ctx->E) FAIL(ctx, PB_ERR_INVALID, "pb_get_event_csr: buffer too small");
     std::vector<AlleleMeta> h((size_t)(2 * ctx->S_inf));
     if (ctx->S_inf) PB_CUDA(cudaMemcpy(h.data(), ctx->d_alleles, h.size() * sizeof(AlleleMeta), cudaMemcpyDeviceToHost));
     for (int64_t i = 0; i < 2 * ctx->S_inf; i++) offsets[i] = h[i].off;

@@ -38,6 +38,7 @@
 #define PB_OPX_TAG_MASK (PB_OPX_NODE_MASK | PB_OPX_NOMRCA | PB_OPX_LEAF)
 
 enum { PB_PLANES_NONE = 0, PB_PLANES_X = 1, PB_PLANES_FULL = 2 };
+#define PB_MAX_SITES_PER_CTX (1ll << 26)   // scan word = inf count << 38 | event count; int32 site indices
 
 // raw MRCA record: ALL events of one (tree row, 64-site word): the sweep kernels store the masks as they are and the
 // tail kernels peel the bits (a per-event record cost the sweep ~36 warp-instructions per event, at one active lane)
@@ -209,6 +210,7 @@ struct pb_ctx {
     pb_stat_out* d_stats = nullptr; int64_t stats_cap = 0;
     int32_t* d_work = nullptr; int64_t work_cap = 0;   // 4 work lists of slot ids (k4_classify_kernel), n_slots each
     int64_t n_work[4] = {0, 0, 0, 0};
+    int sort_blocks_per_sm = -1;                                 // occupancy of k4_sort_coop_kernel on this context's device
     bool k1_attr_set = false, k1x_attr_set = false;              // cudaFuncSetAttribute(max dynamic shared memory) done on this context's device
     uint64_t* d_scan_tmp = nullptr; int64_t scan_tmp_cap = 0;   // block sums of pbk_exclusive_scan_u64 (per context: contexts of one process may sit on different GPUs / host threads)
     uint32_t* d_colpop = nullptr; int64_t colpop_cap = 0;  // [2][P] per-sample case / missing-label popcounts of the current tile
