@@ -93,17 +93,49 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_pass(tree, chars, sn, lab, m, seed, threads):
+def cpu_reference_pass(tree, chars, sn, lab, m, seed, threads, keep=None):
     """One pass of the CPU port over a site sample: (sites/sec, seconds L4, seconds L5).  oracle/ is test
-    infrastructure; this is the one place bench.py may execute it (cpu_baseline / --impl reference)."""
+    infrastructure; this is the one place bench.py may execute it (cpu_baseline / --impl reference).
+    keep: dict that receives the port's outputs (events, class counts, statistics) for the parity cross-check."""
     import oracle
     o = oracle.Oracle(tree.parent, tree.leaf_nodes)
     t0 = time.perf_counter()
-    o.count_all_homoplasy_events(chars, n_threads=threads)
+    ev, cc = o.count_all_homoplasy_events(chars, n_threads=threads)
     t1 = time.perf_counter()
-    o.assoc(sn, lab, m, 1, perms=None, seed=seed, n_threads=threads)
+    st, _, _ = o.assoc(sn, lab, m, 1, perms=None, seed=seed, n_threads=threads)
     t2 = time.perf_counter()
+    if keep is not None:
+        keep.update(events=ev, class_counts=cc, stats=st)
     return chars.shape[1] / (t2 - t0), t1 - t0, t2 - t1
+
+
+def parity_check(gpu_sites, gpu_stats, ref, n):
+    """The GPU's per-site output for the first n sites of the timed input against the CPU port's output on the same sites
+    (same Philox seed, same m): Homoplasy_Events fields and, per informative site, in-use flags, observed tallies, observed
+    p-values, r counts and point-wise estimates — bit for bit.  (The family-wise columns pool the per-replicate minimum over
+    ALL sites of the run, so a slice cannot reproduce them; tests/ cover them on whole inputs.)  -> list of mismatches."""
+    bad = []
+    g = gpu_sites[:n]
+    g = g[g["site_class"] == 2]
+    r = ref["events"]
+    if len(g) != len(r):
+        return ["biallelic sites: gpu %d, cpu port %d" % (len(g), len(r))]
+    for f in ("segsite_id", "allele1", "allele2", "a1_count", "a2_count", "a1_extant", "a2_extant"):
+        if not np.array_equal(g[f], r[f]):
+            bad.append("events." + f)
+    gs = gpu_stats[gpu_stats["site_index"] < n]
+    rs = ref["stats"]
+    if len(gs) != len(rs) or not np.array_equal(gs["segsite_id"], rs["segsite_id"]):
+        return bad + ["informative sites: gpu %d, cpu port %d" % (len(gs), len(rs))]
+    for f in ("a1_in_use", "a2_in_use", "obs_counts", "r_a1", "r_a2"):
+        if not np.array_equal(gs[f], rs[f]):
+            bad.append("stats." + f)
+    for f in ("obs_p_a1", "obs_p_a2", "pointwise_a1", "pointwise_a2"):
+        a, b = gs[f], rs[f]
+        ok = ~np.isnan(b)
+        if not (np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[ok].view(np.uint64), b[ok].view(np.uint64))):
+            bad.append("stats." + f)
+    return bad
 
 
 def workload(args, rank, world):
@@ -331,6 +363,8 @@ def run_b200(args):
         tm_e, ev, st, mt = step_e2e()
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    # outputs of the last timed step (views of page-locked buffers the next call overwrites): kept for the parity check
+    par_outputs = [("headline", np.array(ev[:CPU_SAMPLE_SITES]), np.array(st))]
     e2e_breakdown = {k: v / args.steps for k, v in e2e_parts.items()}
     e2e_step_ms = list(e2e_steps)
     h2d_full = 3 * N * Wp * 8                             # what pb_put_planes copies (rows padded to the device pitch)
@@ -344,9 +378,10 @@ def run_b200(args):
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            step_e2e(False)
+            _, ev3, st3, _ = step_e2e(False)
         barrier()
         full_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        par_outputs.append(("three_planes", np.array(ev3[:CPU_SAMPLE_SITES]), np.array(st3)))
         e2e_full = {"value": total_sites * args.steps / (full_ms / 1e3), "unit": "sites/s", "ms_per_step": full_ms / args.steps,
                     "h2d_bytes_per_step": h2d_full, "upload": "pb_put_planes (three planes)"}
         # the context now holds three planes (the general storage: gaps, multi-allelic sites): the same resident measurement
@@ -363,12 +398,25 @@ def run_b200(args):
     n_draws = sum_over_ranks(tm["n_alleles_in_use"]) * m
 
     cpu_baseline = None
+    parity = {"parity_checked": False, "parity_sites": 0}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_cores()
-        v, l4, l5 = cpu_reference_pass(tree, cpu_chars, sn, lab, m, 20260, threads)
+        ref = {}
+        v, l4, l5 = cpu_reference_pass(tree, cpu_chars, sn, lab, m, 20260, threads, keep=ref)
         cpu_baseline = {"value": v, "unit": "sites/s", "cores": threads, "kind": "port",
                         "sample": "%d-site slice of this workload at the full m=%d (C++ port oracle/oracle.cpp; events %.2f s + assoc %.2f s)"
                                   % (cpu_chars.shape[1], m, l4, l5)}
+        # the timed run's own output (last end-to-end step: `ev`, `st`) against the port on the same first sites
+        n_par = cpu_chars.shape[1]
+        bad = []
+        for name, ev_k, st_k in par_outputs:
+            bad += ["%s: %s" % (name, b) for b in parity_check(ev_k, st_k, ref, n_par)]
+        parity = {"parity_checked": True, "parity_sites": int(n_par), "parity_informative_sites": int(len(ref["stats"])),
+                  "parity_fields": "Homoplasy_Events fields; in-use flags, obs_counts, obs_p, r, point-wise (bit-exact; family-wise needs all sites)",
+                  "parity_mismatches": bad, "parity_runs": [p[0] for p in par_outputs]}
+        if bad:
+            print("bench.py: PARITY FAILURE against the CPU port on the first %d sites: %s" % (n_par, bad), file=sys.stderr)
+            sys.exit(3)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -386,6 +434,7 @@ def run_b200(args):
                 "three_planes": three_planes,
                 "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+                "parity_checked": parity["parity_checked"], "parity_sites": parity["parity_sites"], "parity": parity,
                 "replicate_draws_per_sec": n_draws * args.steps / (dev_ms / 1e3),
                 "wall_ms_per_step": wall_ms / args.steps,
                 "breakdown_ms": parts,

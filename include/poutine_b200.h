@@ -190,10 +190,52 @@ int pb_get_timings(pb_ctx* ctx, pb_timings* out);
 int pb_stopwatch_mark(pb_ctx* ctx, int32_t which);
 int pb_stopwatch_ms(pb_ctx* ctx, float* ms);
 
-/* Multi-GPU: one context per GPU, sites sharded; the only exchange is an NCCL all-reduce(min)
- * of maxT[m] inside pb_run_assoc.  Rank 0 creates the id, the host broadcasts its 128 bytes. */
+/* Multi-GPU: one context per GPU, sites sharded (pb_config.site_offset); every context must be given the same tree,
+ * labels, seed and m.  The only exchange is the minimum of maxT[m] over the shards inside pb_run_assoc (the reference
+ * takes that minimum over all sites of the alignment, HC.java:3239-3243); every rank must call pb_run_assoc the same
+ * number of times.  Three ways to connect the contexts:
+ *
+ *  (1) one process, one host thread: pb_group below — the library drives all GPUs of the box itself.
+ *  (2) one process per GPU, peer memory (NVLink / NVSwitch): every rank calls pb_comm_export, the host gathers the 64-byte
+ *      handles of all ranks (any transport) and hands the rank-ordered array to pb_comm_connect.  The reduction is fused
+ *      into K4's sort kernel (peer loads over NVLink), there is no separate collective.  Before any rank calls pb_destroy,
+ *      every rank must have returned from its last pb_run_assoc (host-side barrier).
+ *  (3) one process per GPU, NCCL all-reduce(min): rank 0 creates the id, the host broadcasts its 128 bytes, pb_comm_init.
+ *      For boxes where (2) is not available (cudaIpcOpenMemHandle refused: pb_comm_connect returns PB_ERR_NCCL). */
+int pb_comm_export(pb_ctx* ctx, void* handle64);
+int pb_comm_connect(pb_ctx* ctx, const void* handles /* world x 64 bytes, rank order */, int32_t rank, int32_t world);
 int pb_comm_unique_id(void* id128);
 int pb_comm_init(pb_ctx* ctx, const void* id128, int32_t rank, int32_t world);
+
+/* pb_group: all GPUs of one box behind the ONE host thread that Homoplasy_Counter.call() is (HC.java:230-319; SURVEY
+ * section 8b "Threading").  Same calls as a single context; the group shards the sites into contiguous 64-site-word
+ * ranges (shard g = words [W*g/G, W*(g+1)/G)), drives each device from its own worker thread and merges the outputs:
+ * per_site / per_inf_site come back in alignment order with alignment-global segsite_id and site_index, class counts are
+ * summed, maxT_sorted is the pooled null.  Results are identical to one context holding the whole alignment.
+ * cfg->device is ignored (devices[] lists the CUDA ordinals), cfg->site_offset is the offset of the group's first site.
+ * PB_ERR_NO_INFORMATIVE is judged over the whole alignment (a shard may be empty). */
+typedef struct pb_group pb_group;
+int pb_group_create(const pb_config* cfg, const int32_t* devices, int32_t n_devices, pb_group** out);
+void pb_group_destroy(pb_group* g);
+const char* pb_group_last_error(pb_group* g);       /* g may be NULL: the calling thread's last pb_group_create error */
+int32_t pb_group_size(pb_group* g);
+pb_ctx* pb_group_ctx(pb_group* g, int32_t i);       /* shard i's context (introspection: pb_get_timings, pb_get_raw_events ...) */
+int pb_group_set_tree(pb_group* g, int32_t n_nodes, const int32_t* parent, const uint8_t* is_leaf);
+int pb_group_set_labels(pb_group* g, int32_t n_samples, const int32_t* sample_node, const uint8_t* label);
+int pb_group_set_sites(pb_group* g, int64_t n_sites);
+int pb_group_shard_range(pb_group* g, int32_t i, int64_t* site_begin, int64_t* site_end);
+/* column tiles in alignment-global word coordinates; a tile may straddle shards (each part goes to its device, in parallel) */
+int pb_group_put_planes(pb_group* g, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
+                        const uint64_t* B0, const uint64_t* B1, const uint64_t* V);
+int pb_group_put_planes_biallelic(pb_group* g, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
+                                  const uint64_t* X, const uint64_t* V, const uint64_t* colmask);
+int pb_group_run_events(pb_group* g, pb_site_out* per_site /* n_sites, may be NULL */, pb_class_counts* counts);
+int pb_group_run_assoc(pb_group* g, const uint32_t* replay_perms, pb_stat_out* per_inf_site, int64_t cap, int64_t* n_inf,
+                       double* maxT_sorted);
+int pb_group_run_extras(pb_group* g, double* exact_pointwise, double* fisher_p);
+int pb_group_get_timings(pb_group* g, pb_timings* out);   /* times: slowest shard; counts: summed over shards */
+int pb_group_stopwatch_mark(pb_group* g, int32_t which);
+int pb_group_stopwatch_ms(pb_group* g, float* ms);        /* slowest shard */
 
 /* Host-side helpers (no GPU work). */
 /* Pack `seg_sites` chars (node-major, row v at seq + v*seq_pitch) into bit planes — the

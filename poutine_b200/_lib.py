@@ -56,7 +56,12 @@ EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_set_tree", "pb_set_la
            "pb_run_events", "pb_run_assoc", "pb_run_extras", "pb_get_sites", "pb_get_raw_events", "pb_get_event_csr",
            "pb_get_maxT_unsorted", "pb_get_ptable", "pb_get_timings", "pb_stopwatch_mark", "pb_stopwatch_ms", "pb_comm_unique_id", "pb_comm_init",
            "pb_pack_chars", "pb_host_alloc", "pb_host_free", "pb_version",
-           "pb_fasta_open", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_record", "pb_fasta_pack_tile", "pb_fasta_last_error"]
+           "pb_fasta_open", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_record", "pb_fasta_pack_tile", "pb_fasta_last_error",
+           "pb_comm_export", "pb_comm_connect",
+           "pb_group_create", "pb_group_destroy", "pb_group_last_error", "pb_group_size", "pb_group_ctx", "pb_group_set_tree",
+           "pb_group_set_labels", "pb_group_set_sites", "pb_group_shard_range", "pb_group_put_planes", "pb_group_put_planes_biallelic",
+           "pb_group_run_events", "pb_group_run_assoc", "pb_group_run_extras", "pb_group_get_timings", "pb_group_stopwatch_mark",
+           "pb_group_stopwatch_ms"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -109,10 +114,30 @@ def lib():
         L.pb_fasta_record.argtypes = [vp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
         L.pb_fasta_pack_tile.argtypes = [vp, vp, i64, i64, vp, vp, vp, i64, i32]
         L.pb_fasta_last_error.argtypes = []; L.pb_fasta_last_error.restype = C.c_char_p
+        L.pb_comm_export.argtypes = [vp, vp]
+        L.pb_comm_connect.argtypes = [vp, vp, i32, i32]
+        L.pb_group_create.argtypes = [C.POINTER(PbConfig), vp, i32, C.POINTER(vp)]
+        L.pb_group_destroy.argtypes = [vp]; L.pb_group_destroy.restype = None
+        L.pb_group_last_error.argtypes = [vp]; L.pb_group_last_error.restype = C.c_char_p
+        L.pb_group_size.argtypes = [vp]; L.pb_group_size.restype = i32
+        L.pb_group_ctx.argtypes = [vp, i32]; L.pb_group_ctx.restype = vp
+        L.pb_group_set_tree.argtypes = [vp, i32, vp, vp]
+        L.pb_group_set_labels.argtypes = [vp, i32, vp, vp]
+        L.pb_group_set_sites.argtypes = [vp, i64]
+        L.pb_group_shard_range.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64)]
+        L.pb_group_put_planes.argtypes = [vp, i64, i64, i64, vp, vp, vp]
+        L.pb_group_put_planes_biallelic.argtypes = [vp, i64, i64, i64, vp, vp, vp]
+        L.pb_group_run_events.argtypes = [vp, vp, C.POINTER(PbClassCounts)]
+        L.pb_group_run_assoc.argtypes = [vp, vp, vp, i64, C.POINTER(i64), vp]
+        L.pb_group_run_extras.argtypes = [vp, vp, vp]
+        L.pb_group_get_timings.argtypes = [vp, C.POINTER(PbTimings)]
+        L.pb_group_stopwatch_mark.argtypes = [vp, i32]
+        L.pb_group_stopwatch_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.pb_host_alloc.argtypes = [C.POINTER(vp), u64]
         L.pb_host_free.argtypes = [vp]
         for n in EXPORTS:
-            if n not in ("pb_destroy", "pb_last_error", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_last_error"):
+            if n not in ("pb_destroy", "pb_last_error", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_last_error",
+                         "pb_group_destroy", "pb_group_last_error", "pb_group_size", "pb_group_ctx"):
                 getattr(L, n).restype = C.c_int
         _LIB = L
     return _LIB

@@ -96,9 +96,19 @@ class HomoplasyCounter:
         self.n_informative = 0
         self._pinned = {}   # name -> (array, handle): page-locked result buffers, reused across calls
 
+    _PREFIX = "pb_"
+
+    def _fn(self, name):
+        """C entry point `name` of this object's family (pb_* for one context, pb_group_* for a group)"""
+        return getattr(_lib.lib(), self._PREFIX + name)
+
+    def _last_error(self):
+        return _lib.lib().pb_last_error(self._h).decode()
+
     def close(self):
         if self._h is not None:
-            _lib.lib().pb_destroy(self._h)
+            if getattr(self, "_owned", True):
+                self._fn("destroy")(self._h)
             self._h = None
         for _, p in getattr(self, "_pinned", {}).values():
             _lib.pinned_free(p)
@@ -123,7 +133,7 @@ class HomoplasyCounter:
 
     def _check(self, rc):
         if rc != 0:
-            msg = _lib.lib().pb_last_error(self._h).decode()
+            msg = self._last_error()
             if rc == _lib.PB_ERR_NO_INFORMATIVE:
                 raise NoInformativeSites(rc, msg)
             raise PoutineError(rc, msg)
@@ -132,17 +142,17 @@ class HomoplasyCounter:
     def set_tree(self, parent, is_leaf):
         parent = np.ascontiguousarray(parent, dtype=np.int32)
         is_leaf = np.ascontiguousarray(is_leaf, dtype=np.uint8)
-        self._check(_lib.lib().pb_set_tree(self._h, len(parent), ptr(parent), ptr(is_leaf)))
+        self._check(self._fn("set_tree")(self._h, len(parent), ptr(parent), ptr(is_leaf)))
         self.n_nodes = len(parent)
 
     def set_phenos(self, sample_node, label):
         sample_node = np.ascontiguousarray(sample_node, dtype=np.int32)
         label = np.ascontiguousarray(label, dtype=np.uint8)
-        self._check(_lib.lib().pb_set_labels(self._h, len(label), ptr(sample_node), ptr(label)))
+        self._check(self._fn("set_labels")(self._h, len(label), ptr(sample_node), ptr(label)))
         self.n_samples = len(label)
 
     def set_sites(self, n_sites):
-        self._check(_lib.lib().pb_set_sites(self._h, int(n_sites)))
+        self._check(self._fn("set_sites")(self._h, int(n_sites)))
         self.n_sites = int(n_sites)
 
     def put_planes(self, B0, B1, V, word_begin=0):
@@ -150,7 +160,7 @@ class HomoplasyCounter:
         for a in (B0, B1, V):
             assert a.dtype == np.uint64 and a.ndim == 2 and a.shape[0] == self.n_nodes and a.strides[1] == 8
         assert B0.strides == B1.strides == V.strides
-        self._check(_lib.lib().pb_put_planes(self._h, int(word_begin), B0.shape[1], B0.strides[0] // 8, ptr(B0), ptr(B1), ptr(V)))
+        self._check(self._fn("put_planes")(self._h, int(word_begin), B0.shape[1], B0.strides[0] // 8, ptr(B0), ptr(B1), ptr(V)))
 
     def put_planes_biallelic(self, X, V, colmask, word_begin=0):
         """Compact upload of a column tile whose sites carry at most two bases (see compact_planes): X, optionally V
@@ -164,7 +174,7 @@ class HomoplasyCounter:
                 V = v2
         colmask = np.ascontiguousarray(colmask, dtype=np.uint64)
         assert colmask.shape == (X.shape[1], 4)
-        self._check(_lib.lib().pb_put_planes_biallelic(self._h, int(word_begin), X.shape[1], X.strides[0] // 8, ptr(X), ptr(V),
+        self._check(self._fn("put_planes_biallelic")(self._h, int(word_begin), X.shape[1], X.strides[0] // 8, ptr(X), ptr(V),
                                                        ptr(colmask)))
 
     def set_planes(self, B0, B1, V, n_sites, tile_words=None, compact=False):
@@ -193,7 +203,7 @@ class HomoplasyCounter:
         are biallelic), as a view of a page-locked buffer that the next call overwrites."""
         cc = PbClassCounts()
         sites = self._result_buffer("sites", self.n_sites, SITE_DTYPE) if fetch_sites else None
-        self._check(_lib.lib().pb_run_events(self._h, ptr(sites), C.byref(cc)))
+        self._check(self._fn("run_events")(self._h, ptr(sites), C.byref(cc)))
         counts = dict(no_allele=cc.n_no_allele, mono=cc.n_mono, bi=cc.n_bi, tri=cc.n_tri, quad=cc.n_quad,
                       raw_events=cc.n_raw_events)
         self.class_counts = counts
@@ -217,7 +227,7 @@ class HomoplasyCounter:
         if replay_perms is not None:
             perms = np.ascontiguousarray(replay_perms, dtype=np.uint32)
             assert perms.shape == (self.m, self.n_samples)
-        self._check(L.pb_run_assoc(self._h, ptr(perms), ptr(stats), cap, C.byref(n_inf), ptr(maxT)))
+        self._check(self._fn("run_assoc")(self._h, ptr(perms), ptr(stats), cap, C.byref(n_inf), ptr(maxT)))
         self.n_informative = n_inf.value
         return (stats[:n_inf.value] if fetch else None), maxT
 
@@ -228,23 +238,23 @@ class HomoplasyCounter:
         n = self.n_informative
         ep = np.empty((n, 2), dtype=np.float64)
         fp = np.empty(n, dtype=np.float64)
-        self._check(_lib.lib().pb_run_extras(self._h, ptr(ep), ptr(fp)))
+        self._check(self._fn("run_extras")(self._h, ptr(ep), ptr(fp)))
         return ep, fp
 
     # ---- introspection ------------------------------------------------------------------------------
     def timings(self):
         t = PbTimings()
-        self._check(_lib.lib().pb_get_timings(self._h, C.byref(t)))
+        self._check(self._fn("get_timings")(self._h, C.byref(t)))
         return t.as_dict()
 
     def stopwatch_start(self):
-        self._check(_lib.lib().pb_stopwatch_mark(self._h, 0))
+        self._check(self._fn("stopwatch_mark")(self._h, 0))
 
     def stopwatch_stop_ms(self):
         """device milliseconds between the two marks (CUDA events on the library's stream)"""
-        self._check(_lib.lib().pb_stopwatch_mark(self._h, 1))
+        self._check(self._fn("stopwatch_mark")(self._h, 1))
         ms = C.c_float(0)
-        self._check(_lib.lib().pb_stopwatch_ms(self._h, C.byref(ms)))
+        self._check(self._fn("stopwatch_ms")(self._h, C.byref(ms)))
         return float(ms.value)
 
     def raw_events(self):
@@ -277,8 +287,92 @@ class HomoplasyCounter:
         return nm.value, out
 
     def comm_init(self, id128: bytes, rank: int, world: int):
+        """NCCL mode: all-reduce(min) of maxT on the stream (pb_comm_init)"""
         buf = C.create_string_buffer(id128, 128)
         self._check(_lib.lib().pb_comm_init(self._h, buf, rank, world))
+
+    def comm_export(self) -> bytes:
+        """peer-memory mode, step 1: this rank's 64-byte handle of its exchange block (pb_comm_export)"""
+        buf = C.create_string_buffer(64)
+        self._check(_lib.lib().pb_comm_export(self._h, buf))
+        return buf.raw
+
+    def comm_connect(self, handles, rank: int, world: int):
+        """peer-memory mode, step 2: map every rank's block (handles in rank order); the min over the shards then happens
+        inside K4's sort kernel with NVLink loads (pb_comm_connect).  Raises PoutineError(PB_ERR_NCCL) where the peers'
+        memory cannot be mapped — fall back to comm_init."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(_lib.lib().pb_comm_connect(self._h, buf, rank, world))
+
+    @classmethod
+    def _view(cls, handle, m, n_sites, n_nodes, n_samples):
+        """a non-owning wrapper around a context that belongs to a group (introspection only)"""
+        o = cls.__new__(cls)
+        o._h = C.c_void_p(handle)
+        o._owned = False
+        o.m, o.n_sites, o.n_nodes, o.n_samples, o.n_informative, o._pinned = m, n_sites, n_nodes, n_samples, 0, {}
+        return o
+
+
+class HomoplasyCounterGroup(HomoplasyCounter):
+    """All GPUs of one box behind one host thread (pb_group): the same calls as HomoplasyCounter, the library shards the
+    sites over `devices`, runs each shard on its own GPU and merges the outputs (alignment-global segsite_id / site_index).
+    Mirrors the single-process Homoplasy_Counter.call() (HC.java:230-319) on a multi-GPU box."""
+
+    _PREFIX = "pb_group_"
+
+    def __init__(self, devices, num_replicates=100000, min_hcount=1, seed=0, replay=False, site_offset=0, maxt_tau=0.0,
+                 force_general_null=False, full_planes=False):
+        self._h = None
+        L = _lib.lib()
+        cfg = PbConfig(device=0, mode=_lib.PB_MODE_REPLAY if replay else _lib.PB_MODE_PHILOX, n_replicates=int(num_replicates),
+                       min_hcount=int(min_hcount), seed=int(seed), site_offset=int(site_offset), maxt_tau=float(maxt_tau),
+                       flags=(_lib.PB_FLAG_FORCE_GENERAL_NULL if force_general_null else 0) |
+                             (_lib.PB_FLAG_FULL_PLANES if full_planes else 0))
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        rc = L.pb_group_create(C.byref(cfg), ptr(dev), len(dev), C.byref(h))
+        if rc != 0:
+            raise PoutineError(rc, L.pb_group_last_error(None).decode())
+        self._h = h
+        self.devices = [int(d) for d in dev]
+        self.m = int(num_replicates)
+        self.n_sites = self.n_nodes = self.n_samples = self.n_informative = 0
+        self._pinned = {}
+
+    def _last_error(self):
+        return _lib.lib().pb_group_last_error(self._h).decode()
+
+    def shard_range(self, i):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(_lib.lib().pb_group_shard_range(self._h, int(i), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def shard(self, i):
+        """shard i's context as a non-owning HomoplasyCounter (timings, raw_events, event_csr, maxT_unsorted ... of that GPU)"""
+        h = _lib.lib().pb_group_ctx(self._h, int(i))
+        assert h
+        s0, s1 = self.shard_range(i)
+        return HomoplasyCounter._view(h, self.m, s1 - s0, self.n_nodes, self.n_samples)
+
+    def maxT_unsorted(self):
+        return self.shard(0).maxT_unsorted()       # pooled over the shards: identical on every GPU
+
+    def ptable(self):
+        return self.shard(0).ptable()
+
+    def raw_events(self):
+        raise NotImplementedError("per shard: group.shard(i).raw_events()")
+
+    def event_csr(self):
+        raise NotImplementedError("per shard: group.shard(i).event_csr()")
+
+    def comm_init(self, *a):
+        raise PoutineError(-1, "a group connects its own contexts")
+
+    comm_export = comm_connect = comm_init
 
 
 def comm_unique_id() -> bytes:

@@ -824,11 +824,14 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     pb_trace_mark(ctx, "ptable+thresholds");
 
     // ---- null distribution, tiled over replicates
-    {
+    if (ctx->xchg.active) {
+        if ((rc = pbx_begin_epoch(ctx))) return rc;      // the epoch's buffer of the exchange block (peers read it)
+    } else {
         int64_t mcap_bytes = ctx->maxT_cap * 8;
-        void* pm = ctx->d_maxT;
-        if ((rc = ensure(ctx, &pm, &mcap_bytes, m * 8))) return rc;
-        ctx->d_maxT = (unsigned long long*)pm; ctx->maxT_cap = mcap_bytes / 8;
+        void* pm = ctx->d_maxT_own;
+        if ((rc = ensure(ctx, &pm, &mcap_bytes, m * 8))) { ctx->d_maxT_own = nullptr; return rc; }
+        ctx->d_maxT_own = (unsigned long long*)pm; ctx->maxT_cap = mcap_bytes / 8;
+        ctx->d_maxT = ctx->d_maxT_own;
     }
     fill_u64_kernel<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(ctx->d_maxT, m, 0x7FF0000000000000ull);
     PB_CUDA(cudaMemsetAsync(ctx->d_r, 0, (size_t)n_slots * 4, st));
@@ -945,9 +948,13 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     }
     PB_CUDA(cudaEventRecord(ctx->ev[7], st));
 
-    // ---- the one collective: all-reduce(min) of maxT over site shards
+    // ---- the one exchange: min of maxT over the site shards.  Peer-memory mode (pb_comm_connect / pb_group): only the
+    // ready signal is issued here, the reduction itself happens inside K4's sort kernel (ms_allreduce ~ 0, the wait for
+    // the slowest rank shows up in ms_pvalues).  NCCL mode (pb_comm_init): an all-reduce on the stream.
     PB_CUDA(cudaEventRecord(ctx->ev[9], st));
-    if (ctx->world > 1) {
+    if (ctx->xchg.active) {
+        if ((rc = pbx_signal(ctx))) return rc;
+    } else if (ctx->world > 1) {
         if ((rc = pbn_allreduce_min_f64(ctx, (double*)ctx->d_maxT, m))) return rc;
     }
     PB_CUDA(cudaEventRecord(ctx->ev[10], st));
@@ -962,6 +969,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     PB_CUDA(cudaMemcpyAsync(&replay_err, ctx->d_class_counts + 12, 8, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
     PB_CUDA(cudaGetLastError());
+    if ((rc = pbx_check(ctx))) return rc;
     if (replay_err) {
         ctx->err = (replay_err & 1ull) ? "pb_run_assoc: replay_perms holds an index >= n_samples"
                                        : "pb_run_assoc: a row of replay_perms is not a permutation of 0 .. n_samples-1";

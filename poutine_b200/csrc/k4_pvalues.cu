@@ -171,23 +171,63 @@ __global__ void k4_classify_kernel(AlleleMeta* __restrict__ alleles, int64_t n_s
     if (cls >= 0) lists[(int64_t)cls * n_slots + s_base[cls] + s_wcount[warp][cls] + my_rank] = (int32_t)a;
 }
 
+// ---- the exchange, fused into the sort's load (protocol: pb_comm.cu) ---------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// every thread of the block calls it: threads 0..world-1 each wait for one peer's flag (in this rank's own block)
+__device__ __forceinline__ void xchg_wait(const XchgView& x) {
+    if (x.peers == nullptr) return;
+    if ((int)threadIdx.x < x.world) {
+        const unsigned long long* own = x.peers[x.rank];
+        const unsigned long long* f = own + threadIdx.x;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys(f) < x.epoch) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ull) { atomicExch((unsigned long long*)own + PB_XCHG_MAX_WORLD, 1ull); break; }   // a peer died
+        }
+    }
+    __syncthreads();
+}
+// pooled minimum of replicate i over all ranks' buffers of the epoch (p >= 0: the bit patterns order like the doubles)
+__device__ __forceinline__ unsigned long long xchg_load_min(const XchgView& x, const unsigned long long* __restrict__ own, int64_t i) {
+    if (x.peers == nullptr) return own[i];
+    unsigned long long v = own[i];
+    for (int q = 0; q < x.world; q++)
+        if (q != x.rank) v = min(v, ld_relaxed_sys(x.peers[q] + x.buf_off + i));
+    x.pooled[i] = v;
+    return v;
+}
+
 // ---- bitonic sort of maxT (m doubles in [0,1]; padded with +inf to a power of two) -----------------
 #define BSORT_TILE 2048
 // whole bitonic network in ONE cooperative launch: tile-local stages in shared memory, tile-crossing stages
 // in global memory with a grid barrier in between (replaces ~40 dependent launches at m = 1e5)
+// Sharded runs: the tile load IS the all-reduce(min) of maxT over the site shards — the peers' buffers are read over
+// NVLink while the tile is filled (xchg_load_min), after the block has seen every rank's ready flag (xchg_wait).
 __global__ void __launch_bounds__(1024) k4_sort_coop_kernel(const unsigned long long* __restrict__ maxT, int64_t m, int64_t n_pad,
-                                                            double* __restrict__ a) {
+                                                            double* __restrict__ a, const XchgView xv) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[BSORT_TILE];
     const int t = threadIdx.x;
     const int64_t n_tiles = n_pad / BSORT_TILE;
     const double INF = __longlong_as_double(0x7FF0000000000000ll);
+    xchg_wait(xv);
     // local sort of every tile (all k <= BSORT_TILE), fused with the load / +inf padding
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * BSORT_TILE;
         const int64_t i0 = base + t, i1 = base + t + 1024;
-        sh[t] = i0 < m ? __longlong_as_double((long long)maxT[i0]) : INF;
-        sh[t + 1024] = i1 < m ? __longlong_as_double((long long)maxT[i1]) : INF;
+        sh[t] = i0 < m ? __longlong_as_double((long long)xchg_load_min(xv, maxT, i0)) : INF;
+        sh[t + 1024] = i1 < m ? __longlong_as_double((long long)xchg_load_min(xv, maxT, i1)) : INF;
         __syncthreads();
         for (int k = 2; k <= BSORT_TILE; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
@@ -236,12 +276,12 @@ __global__ void __launch_bounds__(1024) k4_sort_coop_kernel(const unsigned long 
 // ---- final per-site statistics -----------------------------------------------------------------------
 __global__ void k4_stats_kernel(const int32_t* __restrict__ inf_site, int64_t S_inf, const AlleleMeta* __restrict__ alleles,
                                 const double* __restrict__ pobs, const uint32_t* __restrict__ r, const double* __restrict__ maxT_sorted,
-                                int64_t m, int64_t site_offset, pb_stat_out* __restrict__ out) {
+                                int64_t m, int64_t site_offset, int64_t site_index_base, pb_stat_out* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S_inf) return;
     const double NaN = __longlong_as_double(0x7FF8000000000000ll);
     pb_stat_out o;
-    o.site_index = inf_site[i];
+    o.site_index = (int32_t)(site_index_base + inf_site[i]);
     o.segsite_id = (int32_t)(site_offset + inf_site[i] + 1);
     int32_t rr[2], rm[2];
     double pw[2], fw[2], po[2];
@@ -363,7 +403,8 @@ int pbk_pvalues(pb_ctx* ctx) {
         const unsigned long long* a_maxT = ctx->d_maxT;
         int64_t a_m = m, a_npad = n_pad;
         double* a_out = ctx->d_maxT_sorted;
-        void* args[] = {(void*)&a_maxT, (void*)&a_m, (void*)&a_npad, (void*)&a_out};
+        XchgView a_xv = pbx_view(ctx);
+        void* args[] = {(void*)&a_maxT, (void*)&a_m, (void*)&a_npad, (void*)&a_out, (void*)&a_xv};
         PB_CUDA(cudaLaunchCooperativeKernel((const void*)k4_sort_coop_kernel, dim3((unsigned)grid), dim3(1024), args, 0, st));
         ctx->tm.n_launches += 1;
     }
@@ -374,7 +415,7 @@ int pbk_pvalues(pb_ctx* ctx) {
         ctx->d_stats = (pb_stat_out*)ps; ctx->stats_cap = cap / (int64_t)sizeof(pb_stat_out);
     }
     k4_stats_kernel<<<(unsigned)std::max<int64_t>(1, (ctx->S_inf + T - 1) / T), T, 0, st>>>(ctx->d_inf_site, ctx->S_inf, ctx->d_alleles, ctx->d_pobs, ctx->d_r,
-                                                                      ctx->d_maxT_sorted, m, ctx->cfg.site_offset, ctx->d_stats);
+                                                                      ctx->d_maxT_sorted, m, ctx->cfg.site_offset, ctx->site_index_base, ctx->d_stats);
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
     return PB_OK;

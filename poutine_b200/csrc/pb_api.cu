@@ -18,7 +18,7 @@ extern "C" const char* pb_last_error(pb_ctx* ctx) { return ctx ? ctx->err.c_str(
 static void free_all(pb_ctx* c) {
     void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_ops_x, c->d_chunk_op_x, c->d_node_sample, c->d_leaves_below, c->d_label, c->d_planes,
                     c->d_census, c->d_census_total, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
-                    c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT,
+                    c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT_own,
                     c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop, c->d_colmask, c->d_extras, c->d_X, c->d_xmask, c->d_xvalid, c->d_scan_tmp};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
@@ -87,6 +87,8 @@ extern "C" void pb_destroy(pb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     pbn_destroy(ctx);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pbx_destroy(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
@@ -654,7 +656,8 @@ extern "C" int pb_get_maxT_unsorted(pb_ctx* ctx, double* out) {
     CHECK_CTX(ctx);
     if (!ctx->assoc_done || !out) FAIL(ctx, PB_ERR_INVALID, "pb_get_maxT_unsorted: no results");
     PB_CUDA(cudaSetDevice(ctx->device));
-    PB_CUDA(cudaMemcpy(out, ctx->d_maxT, (size_t)ctx->cfg.n_replicates * 8, cudaMemcpyDeviceToHost));
+    // sharded over peer memory: the pooled minimum lives in its own buffer (d_maxT is this shard's contribution)
+    PB_CUDA(cudaMemcpy(out, ctx->xchg.active ? ctx->xchg.d_pooled : ctx->d_maxT, (size_t)ctx->cfg.n_replicates * 8, cudaMemcpyDeviceToHost));
     return PB_OK;
 }
 
@@ -707,6 +710,23 @@ extern "C" int pb_comm_init(pb_ctx* ctx, const void* id128, int32_t rank, int32_
     if (!id128 || world < 1 || rank < 0 || rank >= world) FAIL(ctx, PB_ERR_INVALID, "pb_comm_init: bad rank/world");
     PB_CUDA(cudaSetDevice(ctx->device));
     return pbn_init(ctx, id128, rank, world);
+}
+
+extern "C" int pb_comm_export(pb_ctx* ctx, void* handle64) {
+    CHECK_CTX(ctx);
+    if (!handle64) FAIL(ctx, PB_ERR_INVALID, "pb_comm_export: null handle buffer");
+    if (ctx->xchg.active || ctx->nccl_comm) FAIL(ctx, PB_ERR_INVALID, "pb_comm_export: the context is already connected");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    return pbx_export(ctx, handle64);
+}
+
+extern "C" int pb_comm_connect(pb_ctx* ctx, const void* handles, int32_t rank, int32_t world) {
+    CHECK_CTX(ctx);
+    if (!handles || world < 1 || rank < 0 || rank >= world) FAIL(ctx, PB_ERR_INVALID, "pb_comm_connect: bad rank/world");
+    if (ctx->xchg.active || ctx->nccl_comm) FAIL(ctx, PB_ERR_INVALID, "pb_comm_connect: the context is already connected");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    if (world == 1) { ctx->rank = 0; ctx->world = 1; return PB_OK; }
+    return pbx_connect_ipc(ctx, handles, rank, world);
 }
 
 extern "C" int pb_host_alloc(void** out, uint64_t bytes) {

@@ -120,6 +120,35 @@ struct AlleleMeta {      // one per allele slot (2 per informative site), 32 byt
     uint32_t kpack;      // missing labels in the pheno file, n <= 7: k*_j for n_r = n - j, 4 bits each (j = 0..n)
 };
 
+// ---- the path's one exchange, over peer memory (pb_comm.cu) ----------------------------------------------------------
+// Site shards pool the per-replicate minimum p-value maxT[m] (HC.java:3239-3243 takes it over ALL sites).  Every rank owns
+// one exchange block {ready flags[64], error word, maxT buffer 0, maxT buffer 1} that its peers map (cudaIpc across
+// processes, plain peer access inside one process).  K3 writes the epoch's buffer; a signal kernel then stores the epoch
+// into every peer's flag word; the sort kernel of K4 waits for all flags and takes the minimum over the peers' buffers
+// with NVLink loads WHILE it loads its tiles — the all-reduce is fused into the sort's first pass, no separate collective.
+// Buffers alternate by epoch parity: a peer can run at most one epoch ahead (it needs this rank's next flag first), so the
+// buffer being read is never the one being refilled.
+#define PB_XCHG_MAX_WORLD 64
+#define PB_XCHG_HDR_WORDS 128          // flags[64] + error word + padding (1 KB), then the two maxT buffers
+struct pb_xchg {
+    bool active = false;
+    unsigned long long* block = nullptr;                 // own block (cudaMalloc)
+    size_t block_bytes = 0;
+    unsigned long long* peer[PB_XCHG_MAX_WORLD] = {};    // every rank's block as seen from this device (own included)
+    bool peer_ipc[PB_XCHG_MAX_WORLD] = {};               // mapped with cudaIpcOpenMemHandle (closed in pb_destroy)
+    unsigned long long** d_peer_tbl = nullptr;           // device copy of peer[]
+    unsigned long long* d_pooled = nullptr;              // [m] pooled (all-rank) minimum, unsorted: pb_get_maxT_unsorted
+    unsigned long long epoch = 0;
+};
+// what the fused sort kernel needs (by value)
+struct XchgView {
+    unsigned long long* const* peers;   // nullptr: single rank, plain load
+    unsigned long long* pooled;
+    int world, rank;
+    unsigned long long epoch;
+    long long buf_off;                  // word offset of the epoch's maxT buffer inside a block
+};
+
 struct pb_ctx {
     pb_config cfg{};
     int device = 0;
@@ -201,7 +230,10 @@ struct pb_ctx {
     double* d_tau = nullptr;     // 1           (inside d_thr)
     double* d_pobs = nullptr;    // [2*S_inf]
     uint32_t* d_r = nullptr;     // [2*S_inf]
-    unsigned long long* d_maxT = nullptr;  // [m] (double bits)
+    unsigned long long* d_maxT = nullptr;  // [m] (double bits): the private allocation below, or the epoch's buffer of the exchange block
+    unsigned long long* d_maxT_own = nullptr;
+    pb_xchg xchg;
+    int64_t site_index_base = 0;           // added to pb_stat_out.site_index (a pb_group reports group-global indices)
     double* d_maxT_sorted = nullptr;       // [pow2 >= m]
     int64_t maxT_cap = 0, sorted_cap = 0;
     uint64_t *d_Xcase = nullptr, *d_Xmiss = nullptr;  // [P][Rw]
@@ -258,6 +290,16 @@ int pbk_thresholds(pb_ctx* ctx);                               // k4_pvalues.cu
 int pbk_pvalues(pb_ctx* ctx);                                  // k4_pvalues.cu
 int pbk_extras(pb_ctx* ctx, double* h_exact_pointwise, double* h_fisher);   // k5_extras.cu
 int pbk_exclusive_scan_u64(pb_ctx* ctx, const uint64_t* in, uint64_t* out, int64_t n, uint64_t* d_total);  // k1_events.cu
+
+// pb_comm.cu: peer-memory exchange
+int pbx_export(pb_ctx* ctx, void* handle64);
+int pbx_connect_ipc(pb_ctx* ctx, const void* handles, int rank, int world);
+int pbx_connect_local(pb_ctx** ctxs, int n);     // contexts of ONE process, one per GPU
+int pbx_begin_epoch(pb_ctx* ctx);                // points d_maxT at the epoch's buffer
+int pbx_signal(pb_ctx* ctx);                     // after K3: tell every peer this rank's buffer of the epoch is complete
+XchgView pbx_view(pb_ctx* ctx);
+int pbx_check(pb_ctx* ctx);                      // after the stream synchronised: did a peer fail to arrive?
+void pbx_destroy(pb_ctx* ctx);
 
 // nccl_dyn.cpp
 int pbn_unique_id(void* id128, std::string& err);

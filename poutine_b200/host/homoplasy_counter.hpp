@@ -34,10 +34,10 @@ struct NoInformativeSites : PoutineError {
 struct Options {
     int64_t num_replicates = 100000;   // HC.java:89
     int32_t min_hcount = 1;            // HC.java:98
-    int32_t device = 0;
+    std::vector<int32_t> devices{0};   // CUDA ordinals: more than one = the sites are sharded over the GPUs of the box (pb_group)
     uint64_t seed = 0;
     bool replay = false;               // PB_MODE_REPLAY: assoc() consumes recorded permutations
-    int64_t site_offset = 0;           // site sharding (64-aligned global index of this context's first site)
+    int64_t site_offset = 0;           // 64-aligned global index of the first site (a host that shards over processes itself)
     uint32_t flags = 0;                // PB_FLAG_*
 };
 
@@ -85,47 +85,50 @@ struct AssocResult {
     std::vector<double> maxT_sorted;
 };
 
+// One object = the whole box: the library's pb_group shards the sites over Options::devices, drives each GPU from its own
+// worker thread and merges the outputs, so the host stays the single-threaded call() the reference is (HC.java:230-319).
 class HomoplasyCounter {
   public:
     explicit HomoplasyCounter(const Options& o) : m_(o.num_replicates) {
         pb_config cfg{};
-        cfg.device = o.device;
+        cfg.device = 0;
         cfg.mode = o.replay ? PB_MODE_REPLAY : PB_MODE_PHILOX;
         cfg.n_replicates = o.num_replicates;
         cfg.min_hcount = o.min_hcount;
         cfg.seed = o.seed;
         cfg.site_offset = o.site_offset;
         cfg.flags = o.flags;
-        int rc = pb_create(&cfg, &ctx_);
-        if (rc != 0) throw PoutineError(rc, pb_last_error(nullptr));
+        if (o.devices.empty()) throw PoutineError(PB_ERR_INVALID, "Options::devices is empty");
+        int rc = pb_group_create(&cfg, o.devices.data(), (int32_t)o.devices.size(), &ctx_);
+        if (rc != 0) throw PoutineError(rc, pb_group_last_error(nullptr));
     }
     HomoplasyCounter(const HomoplasyCounter&) = delete;
     HomoplasyCounter& operator=(const HomoplasyCounter&) = delete;
     ~HomoplasyCounter() {
-        if (ctx_) pb_destroy(ctx_);
+        if (ctx_) pb_group_destroy(ctx_);
     }
 
     // ---- inputs: the reference's NewickTree / phenos / seg_sites, flattened --------------------------------------
     void set_tree(const std::vector<int32_t>& parent, const std::vector<uint8_t>& is_leaf) {
         if (parent.size() != is_leaf.size()) throw PoutineError(PB_ERR_INVALID, "set_tree: parent / is_leaf sizes differ");
-        check(pb_set_tree(ctx_, (int32_t)parent.size(), parent.data(), is_leaf.data()));
+        check(pb_group_set_tree(ctx_, (int32_t)parent.size(), parent.data(), is_leaf.data()));
         n_nodes_ = (int64_t)parent.size();
     }
     void set_phenos(const std::vector<int32_t>& sample_node, const std::vector<uint8_t>& label) {
         if (sample_node.size() != label.size()) throw PoutineError(PB_ERR_INVALID, "set_phenos: sample_node / label sizes differ");
-        check(pb_set_labels(ctx_, (int32_t)label.size(), sample_node.data(), label.data()));
+        check(pb_group_set_labels(ctx_, (int32_t)label.size(), sample_node.data(), label.data()));
         n_samples_ = (int64_t)label.size();
     }
     void set_sites(int64_t n_sites) {
-        check(pb_set_sites(ctx_, n_sites));
+        check(pb_group_set_sites(ctx_, n_sites));
         n_sites_ = n_sites;
     }
     void put_planes(int64_t word_begin, int64_t n_words, int64_t pitch_words, const uint64_t* B0, const uint64_t* B1, const uint64_t* V) {
-        check(pb_put_planes(ctx_, word_begin, n_words, pitch_words, B0, B1, V));
+        check(pb_group_put_planes(ctx_, word_begin, n_words, pitch_words, B0, B1, V));
     }
     void put_planes_biallelic(int64_t word_begin, int64_t n_words, int64_t pitch_words, const uint64_t* X, const uint64_t* V,
                               const uint64_t* colmask) {
-        check(pb_put_planes_biallelic(ctx_, word_begin, n_words, pitch_words, X, V, colmask));
+        check(pb_group_put_planes_biallelic(ctx_, word_begin, n_words, pitch_words, X, V, colmask));
     }
     // seg_sites as chars (node-major, row v at seq + v*pitch): packed on the host, compact upload when the alignment qualifies
     void set_seg_sites(const char* seq, int64_t n_nodes, int64_t n_sites, int64_t pitch) {
@@ -149,17 +152,17 @@ class HomoplasyCounter {
     // The returned pointer is a page-locked buffer owned by the counter, overwritten by the next call.
     const pb_site_out* count_all_homoplasy_events(pb_class_counts* counts = nullptr) {
         if (sites_.size() < (size_t)n_sites_ || !sites_.data()) sites_.reset((size_t)n_sites_);
-        check(pb_run_events(ctx_, sites_.data(), counts));
+        check(pb_group_run_events(ctx_, sites_.data(), counts));
         return sites_.data();
     }
     AssocResult assoc(const uint32_t* replay_perms = nullptr, bool want_maxT = true) {
         pb_timings tm{};
-        check(pb_get_timings(ctx_, &tm));
+        check(pb_group_get_timings(ctx_, &tm));
         const int64_t cap = tm.n_informative > 0 ? tm.n_informative : 1;
         if (stats_.size() < (size_t)cap || !stats_.data()) stats_.reset((size_t)cap);
         if (want_maxT && (maxT_.size() < (size_t)m_ || !maxT_.data())) maxT_.reset((size_t)m_);
         int64_t n_inf = 0;
-        check(pb_run_assoc(ctx_, replay_perms, stats_.data(), cap, &n_inf, want_maxT ? maxT_.data() : nullptr));
+        check(pb_group_run_assoc(ctx_, replay_perms, stats_.data(), cap, &n_inf, want_maxT ? maxT_.data() : nullptr));
         AssocResult r;
         r.stats.assign(stats_.data(), stats_.data() + n_inf);
         if (want_maxT) r.maxT_sorted.assign(maxT_.data(), maxT_.data() + m_);
@@ -170,28 +173,28 @@ class HomoplasyCounter {
     void extras(std::vector<double>& exact_pointwise, std::vector<double>& fisher_p) {
         exact_pointwise.assign((size_t)(2 * n_informative_), 0.0);
         fisher_p.assign((size_t)n_informative_, 0.0);
-        check(pb_run_extras(ctx_, exact_pointwise.data(), fisher_p.data()));
+        check(pb_group_run_extras(ctx_, exact_pointwise.data(), fisher_p.data()));
     }
 
     pb_timings timings() {
         pb_timings tm{};
-        check(pb_get_timings(ctx_, &tm));
+        check(pb_group_get_timings(ctx_, &tm));
         return tm;
     }
-    void comm_init(const void* id128, int rank, int world) { check(pb_comm_init(ctx_, id128, rank, world)); }
+    int n_gpus() const { return (int)pb_group_size(ctx_); }
     int64_t n_sites() const { return n_sites_; }
     int64_t n_nodes() const { return n_nodes_; }
     int64_t n_informative() const { return n_informative_; }
-    pb_ctx* handle() { return ctx_; }
+    pb_group* handle() { return ctx_; }
 
   private:
     void check(int rc) {
         if (rc == 0) return;
-        std::string msg = pb_last_error(ctx_);
+        std::string msg = pb_group_last_error(ctx_);
         if (rc == PB_ERR_NO_INFORMATIVE) throw NoInformativeSites(rc, msg);
         throw PoutineError(rc, msg);
     }
-    pb_ctx* ctx_ = nullptr;
+    pb_group* ctx_ = nullptr;
     int64_t m_ = 0, n_sites_ = 0, n_nodes_ = 0, n_samples_ = 0, n_informative_ = 0;
     PinnedArray<pb_site_out> sites_;
     PinnedArray<pb_stat_out> stats_;

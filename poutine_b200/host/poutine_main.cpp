@@ -2,7 +2,7 @@
 // libpoutine_b200.so:
 //
 //     poutine_b200_host -u -f anc.fasta -t anc.newick|annotated_tree.nexus -p pheno.tsv -m sites.map [-r m] [-c min_hcount]
-//                       [-T threads] [-d out_dir] [-o out] [-X] [--seed s] [--device d] [--extras]
+//                       [-T threads] [-d out_dir] [-o out] [-X] [--seed s] [--devices d0[,d1,...]] [--extras]
 //
 // = Homoplasy_Counter.call() (HC.java:230-319) with the picocli flags of HC.java:59-154: loaders (hostio.cpp), the mmap'ed
 // FASTA packer streamed tile by tile into pb_put_planes / pb_put_planes_biallelic, the two hot entry points through
@@ -34,7 +34,8 @@ namespace {
 struct Args {
     std::string fasta, phenos, tree, map, out_dir, out;
     int64_t replicates = 100000;
-    int32_t min_hcount = 1, threads = 0, device = 0;
+    int32_t min_hcount = 1, threads = 0;
+    std::vector<int32_t> devices{0};     // --devices d0[,d1,...]: the sites are sharded over these GPUs (pb_group), all from this process
     bool precomputed = false, overwrite = false, extras = false, have_seed = false;
     uint64_t seed = 0;
     int64_t tile_sites = 1 << 14;   // profiles/r1_native_host_sweep.json: page-locked buffer set-up vs per-tile overhead
@@ -47,7 +48,7 @@ struct Args {
     std::fprintf(stderr,
                  "usage: poutine_b200_host -u -f <ancestral fasta> -t <ancestral newick | annotated_tree.nexus> -p <phenos> -m <map>\n"
                  "       [-r <# replicates>=100000] [-c <min_hcount>=1] [-T <# packer threads>] [-d <out dir>] [-o <out file>] [-X]\n"
-                 "       [--seed <n>] [--device <ordinal>] [--extras] [--tile-sites <n>=16384] [--no-compact-upload] [--timing]\n");
+                 "       [--seed <n>] [--devices <ordinal>[,<ordinal>...]] [--extras] [--tile-sites <n>=16384] [--no-compact-upload] [--timing]\n");
     std::exit(2);
 }
 
@@ -177,7 +178,7 @@ RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
     Options o;
     o.num_replicates = a.replicates;
     o.min_hcount = a.min_hcount;
-    o.device = a.device;
+    o.devices = a.devices;
     o.seed = a.seed;
     HomoplasyCounter hc(o);
     hc.set_tree(tree.parent, tree.is_leaf);
@@ -362,7 +363,17 @@ int main(int argc, char** argv) {
             else if (f == "-o" || f == "--out") a.out = val();
             else if (f == "-X" || f == "--force-overwrite") a.overwrite = true;
             else if (f == "--seed") { a.seed = std::strtoull(val(), nullptr, 10); a.have_seed = true; }
-            else if (f == "--device") a.device = std::atoi(val());
+            else if (f == "--device" || f == "--devices") {      // one site shard per listed GPU, all driven from this one process
+                a.devices.clear();
+                for (const char* p = val(); *p;) {
+                    char* end = nullptr;
+                    const long d = std::strtol(p, &end, 10);
+                    if (end == p || d < 0 || (*end && *end != ',')) usage("--devices expects a comma-separated list of CUDA ordinals");
+                    a.devices.push_back((int32_t)d);
+                    p = *end == ',' ? end + 1 : end;
+                }
+                if (a.devices.empty()) usage("--devices expects a comma-separated list of CUDA ordinals");
+            }
             else if (f == "--extras") a.extras = true;
             else if (f == "--tile-sites") a.tile_sites = std::atoll(val());
             else if (f == "--no-compact-upload") a.compact_upload = false;

@@ -73,13 +73,18 @@ def test_hand_fixture_events(oracle_mod, golden_dir):
     assert (cc["mono"], cc["bi"], cc["tri"], cc["quad"], cc["no_allele"]) == (want["mono"], want["bi"], want["tri"], want["quad"], want["other"])
 
 
-def test_events_match_reference_bytecode(golden_dir):
-    """CUDA path against tests/golden/events_refbytecode.json — outputs of the reference's own compiled
+@pytest.mark.parametrize("suffix", ["", "_extra"])
+def test_events_match_reference_bytecode(golden_dir, suffix):
+    """CUDA path against tests/golden/events_refbytecode.json (and the second set, `_extra`: star tree, ladder, two-leaf tree,
+    few pheno rows, one-class phenotypes, min_hcount 4 — every case there also through the compacting upload, which keeps the
+    tiles that qualify as one plane) — outputs of the reference's own compiled
     count_all_homoplasy_events (Homoplasy_Counter.class run by oracle/tools/refjvm.py): Homoplasy_Events fields, class
     counters and, where neither bucket was cleared, the exact MRCA node sets.  The all-valid biallelic case runs in both
     storage modes (k1x_events_kernel and k1_events_kernel)."""
     from tests.test_oracle_events import refbytecode_cases
-    for c, chars in refbytecode_cases(golden_dir):
+    n_cases = 0
+    for c, chars in refbytecode_cases(golden_dir, suffix):
+        n_cases += 1
         parent = np.asarray(c["parent"], dtype=np.int32)
         is_leaf = np.zeros(len(parent), dtype=np.uint8)
         is_leaf[c["leaf_nodes"]] = 1
@@ -87,6 +92,8 @@ def test_events_match_reference_bytecode(golden_dir):
         root = int(np.where(parent < 0)[0][0])
         S = chars.shape[1]
         modes = [dict(compact=False)] if c["name"] != "biallelic_all_valid" else [dict(compact=True), dict(compact=True, full_planes=True)]
+        if suffix:
+            modes = [dict(compact=False), dict(compact=True)]
         for mode in modes:
             hc = pb.HomoplasyCounter(num_replicates=10, full_planes=mode.get("full_planes", False))
             hc.set_tree(parent, is_leaf)
@@ -111,18 +118,20 @@ def test_events_match_reference_bytecode(golden_dir):
                 if r["a1_count"] >= 2 and r["a2_count"] >= 2:
                     assert want - {names[root]} == have, (c["name"], r["segsite_id"])
             hc.close()
+    assert n_cases >= 5
 
 
-def test_assoc_matches_reference_bytecode(golden_dir):
+@pytest.mark.parametrize("suffix", ["", "_extra"])
+def test_assoc_matches_reference_bytecode(golden_dir, suffix):
     """CUDA path in replay mode against tests/golden/assoc_refbytecode.json — what the reference's own compiled resampling
     driver produced (commons-math's BinomialTest from its jar included) with the recorded shuffles: obs_counts, r counts,
     per-replicate min p, sorted maxT, point-wise and family-wise estimates; every double bit for bit."""
     from tests.test_oracle_events import assoc_refbytecode_cases, assert_stats_equal_refbytecode
-    for c, chars, a in assoc_refbytecode_cases(golden_dir):
+    for c, chars, a in assoc_refbytecode_cases(golden_dir, suffix):
         parent = np.asarray(c["parent"], dtype=np.int32)
         is_leaf = np.zeros(len(parent), dtype=np.uint8)
         is_leaf[c["leaf_nodes"]] = 1
-        for compact in ((False, True) if c["name"] == "biallelic_all_valid" else (False,)):
+        for compact in ((False, True) if (c["name"] == "biallelic_all_valid" or suffix) else (False,)):
             hc = pb.HomoplasyCounter(num_replicates=a["m"], min_hcount=a["min_hcount"], replay=True)
             hc.set_tree(parent, is_leaf)
             hc.set_phenos(np.asarray(a["sample_node"], dtype=np.int32), np.asarray(a["label"], dtype=np.uint8))

@@ -1,0 +1,106 @@
+"""GPU parity at the BASELINE tree shapes (run with -m gpu on a B200): both event sweeps — k1x_events_kernel (one plane)
+and k1_events_kernel (three planes) — and the whole association path against the CPU oracle at the C2 (5,000 leaves),
+C3 (20,000 leaves: census segments, 15-bit leaf counters, leaves_below sums) and C5 (gaps / multi-allelic / lower case)
+tree sizes, on site slices the literal oracle (leaf -> root walks, HC.java:1647-1698) finishes in seconds.
+
+Events: every Homoplasy_Events field and the class counters, bit-exact (HC.java:1402-1511).
+Association: replay mode with the oracle's java.util.Random shuffles and Philox mode (the oracle restates the sampling
+spec), every integer and every double bit for bit (HC.java:3013-3186).
+"""
+import numpy as np
+import pytest
+
+import poutine_b200 as pb
+from poutine_b200 import synth
+from tests.helpers import assert_stats_equal
+
+pytestmark = pytest.mark.gpu
+
+EV_FIELDS = ("segsite_id", "allele1", "allele2", "a1_count", "a2_count", "a1_extant", "a2_extant")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    pb.build()
+
+
+def _case(config, S, seed_off=0):
+    cfg = synth.CONFIGS[config]
+    tree = synth.yule_tree(cfg["n_leaves"], cfg["seed"])
+    planes = synth.simulate_planes(tree, S, cfg["seed"] + 2000 + seed_off, leaf_gap=cfg.get("leaf_gap", False),
+                                   multiallelic_frac=cfg.get("multiallelic_frac", 0.0),
+                                   third_allele_internal_frac=cfg.get("third_allele_internal_frac", 0.0))
+    sn, lab = synth.simulate_phenotypes(tree, cfg["seed"] + 1000, na_frac=cfg.get("na_frac", 0.0))
+    return tree, planes, sn, lab
+
+
+@pytest.mark.parametrize("config,S,one_plane", [
+    ("C2", 64 * 257 + 13, True),      # the headline kernel at the headline tree (BASELINE configs[1])
+    ("C2", 64 * 257 + 13, False),     # same input held as three planes
+    ("C3", 64 * 129 + 7, True),       # 20,000 leaves / 39,999 nodes: more than one wave of edge chunks per column block
+    ("C3", 64 * 129 + 7, False),      # 81 census segments of 248 leaves, 15-bit counters
+    ("C5", 64 * 257 + 13, False),     # leaf gaps, tri/quad-allelic sites, third alleles on internal nodes (three planes by necessity)
+    ("C1", 64 * 300 + 1, True),
+])
+def test_events_and_assoc_at_baseline_shapes(oracle_mod, config, S, one_plane):
+    tree, (B0, B1, V), sn, lab = _case(config, S)
+    chars = synth.planes_to_chars(B0, B1, V, 0, S)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(chars, n_threads=8)
+    m = 320
+    perms = oracle_mod.java_shuffle_perms(4711, m, len(lab))
+    or_st, or_mt_s, or_mt_u = o.assoc(sn, lab, m, 1, perms=perms, n_threads=8)
+
+    hc = pb.HomoplasyCounter(num_replicates=m, replay=True, full_planes=not one_plane)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_planes(B0, B1, V, S, tile_words=97, compact=True)
+    ev, cc = hc.count_all_homoplasy_events()
+    assert hc.timings()["plane_mode"] == (1 if one_plane else 2)
+    assert (cc["mono"], cc["bi"], cc["tri"], cc["quad"], cc["no_allele"]) == tuple(or_cc[k] for k in ("mono", "bi", "tri", "quad", "other"))
+    assert len(ev) == len(or_ev) and len(ev) > S // 2
+    for f in EV_FIELDS:
+        np.testing.assert_array_equal(ev[f], or_ev[f], err_msg=f)
+    st, mt = hc.assoc(replay_perms=perms)
+    assert_stats_equal(st, or_st)
+    np.testing.assert_array_equal(mt.view(np.uint64), or_mt_s.view(np.uint64))
+    np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), or_mt_u.view(np.uint64))
+    hc.close()
+
+    # Philox mode on the same events (product-defined sampling, restated by the oracle): bit-exact as well
+    m2 = 1024
+    or_st, or_mt_s, or_mt_u = o.assoc(sn, lab, m2, 1, perms=None, seed=99, n_threads=8)
+    hp = pb.HomoplasyCounter(num_replicates=m2, seed=99, full_planes=not one_plane)
+    hp.set_tree(tree.parent, tree.is_leaf)
+    hp.set_phenos(sn, lab)
+    hp.set_planes(B0, B1, V, S, compact=True)
+    hp.count_all_homoplasy_events()
+    st, mt = hp.assoc()
+    assert_stats_equal(st, or_st)
+    np.testing.assert_array_equal(mt.view(np.uint64), or_mt_s.view(np.uint64))
+    hp.close()
+
+
+def test_c3_shard_slice_parity_inside_a_large_run(oracle_mod):
+    """A 20,000-leaf context at a size where the sweep runs many column blocks (64k sites = 1/78 of C3): a 2,048-site slice
+    out of its middle, taken from the context's own per-site output, must equal the oracle on the same columns — in both
+    storage modes."""
+    S = 64 * 1024
+    tree, (B0, B1, V), sn, lab = _case("C3", S, seed_off=5)
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    s0, s1 = 64 * 500, 64 * 532
+    or_ev, _ = o.count_all_homoplasy_events(synth.planes_to_chars(B0, B1, V, s0, s1), n_threads=8)
+    for full in (False, True):
+        hc = pb.HomoplasyCounter(num_replicates=256, seed=3, full_planes=full)
+        hc.set_tree(tree.parent, tree.is_leaf)
+        hc.set_phenos(sn, lab)
+        hc.set_planes(B0, B1, V, S, compact=True)
+        hc.count_all_homoplasy_events()
+        assert hc.timings()["plane_mode"] == (2 if full else 1)
+        sl = hc.sites[s0:s1]
+        sl = sl[sl["site_class"] == 2].copy()
+        sl["segsite_id"] -= s0
+        assert len(sl) == len(or_ev)
+        for f in EV_FIELDS:
+            np.testing.assert_array_equal(sl[f], or_ev[f], err_msg=f)
+        hc.close()
