@@ -604,20 +604,43 @@ __global__ void k1_census_reduce_kernel(const uint64_t* __restrict__ census, int
     for (int j = 0; j < PB_K1_KT; j++) out[(int64_t)j * W] = acc[j];
 }
 
-// ---- per-site finalisation: census -> class / major-minor; counters -> Homoplasy_Events -----------
+// ---- per-site finalisation + informative-site compaction, ONE pass (decoupled look-back scan) ----------------
+// census -> class / major-minor (get_alleles HC.java:1593-1603, identify_major_minor_alleles HC.java:1712-1743); counters ->
+// Homoplasy_Events (HC.java:5558-5600); subset_by_min_hcount (HC.java:3783-3905) as a stream compaction that keeps site order.
+// One thread = one site, one block = one tile of TAIL_TILE sites.  The exclusive prefix (informative sites before this one,
+// extant events before this one) is a single-pass scan: every tile publishes its aggregate, then looks back over its
+// predecessors' aggregates / inclusive prefixes (Merrill & Garland), so finalize + 3 scan kernels + the site scatter of
+// round 1 are one launch.  Tile ids come from an atomic ticket: a tile only waits for tiles that already run.
 // XMODE: the alignment is held as one plane.  B0 = X, B1 = the site masks [W][4], V = the valid-site words [W]; the
 // census is xcensus[S], the signed sum k1_count_events_kernel took over the records (see xrec_t): leaves carrying the
 // second base = n_leaves * X(root) + xcensus.
+#define TAIL_TILE 512
+#define TS_VALID (1ull << 63)
+// scan state: word 0 = ticket, then per tile {aggregate: valid | inf << 40 | ev, prefix inf: valid | n, prefix ev: valid | n}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
 template <bool XMODE>
-__global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, const int32_t* __restrict__ xcensus, int kt_used, int64_t W, int64_t S,
-                                   const uint64_t* __restrict__ B0, const uint64_t* __restrict__ B1, const uint64_t* __restrict__ V,
-                                   int64_t Wp, int32_t root, int32_t n_leaves, const uint32_t* __restrict__ cnt, int32_t min_hcount, int64_t site_offset,
-                                   pb_site_out* __restrict__ sites, uint8_t* __restrict__ flags, uint64_t* __restrict__ scan_in,
-                                   unsigned long long* __restrict__ class_counts) {
-    __shared__ unsigned int s_cls[5];
-    if (threadIdx.x < 5) s_cls[threadIdx.x] = 0;
+__global__ void __launch_bounds__(TAIL_TILE) k1_finalize_compact_kernel(
+    const uint64_t* __restrict__ total, const int32_t* __restrict__ xcensus, int kt_used, int64_t W, int64_t S, const uint64_t* __restrict__ B0,
+    const uint64_t* __restrict__ B1, const uint64_t* __restrict__ V, int64_t Wp, int32_t root, int32_t n_leaves, const uint32_t* __restrict__ cnt,
+    int32_t min_hcount, int64_t site_offset, pb_site_out* __restrict__ sites, uint8_t* __restrict__ flags, uint64_t* __restrict__ scan_out,
+    int32_t* __restrict__ inf_site, AlleleMeta* __restrict__ alleles, unsigned long long* __restrict__ state,
+    unsigned long long* __restrict__ class_counts /* [0..4] classes, [5] n_max, [6] A_inuse, [7] S_inf << 38 | E */) {
+    __shared__ unsigned int s_cls[5], s_nmax, s_ause;
+    __shared__ unsigned long long s_warp[TAIL_TILE / 32], s_excl;
+    __shared__ unsigned int s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 5) s_cls[tid] = 0;
+    if (tid == 0) { s_nmax = 0; s_ause = 0; s_tile = (unsigned int)atomicAdd(state, 1ull); }
     __syncthreads();
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tile = s_tile;
+    const int64_t s = tile * TAIL_TILE + tid;
+    uint64_t mine = 0;          // inf << 40 | extant events of the in-use alleles
+    uint8_t fl = 0;
+    uint32_t n1 = 0, n2 = 0;
+    bool u1 = false, u2 = false;
     if (s < S) {
         const int64_t w = s >> 6;
         const int b = (int)(s & 63);
@@ -653,8 +676,6 @@ __global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, const int
         o.segsite_id = (int32_t)(site_offset + s + 1);
         o.site_class = n_alleles;
         o.allele1 = o.allele2 = o.a1_count = o.a2_count = o.a1_extant = o.a2_extant = 0;
-        uint8_t fl = 0;
-        uint64_t scan = 0;
         if (n_alleles == 2) {
             // identify_major_minor_alleles: first-in-order wins ties (>=, HC.java:1725)
             int a1, a2;
@@ -676,135 +697,108 @@ __global__ void k1_finalize_kernel(const uint64_t* __restrict__ total, const int
             o.allele1 = L4[a1]; o.allele2 = L4[a2];
             o.a1_count = (int32_t)a1c; o.a2_count = (int32_t)a2c; o.a1_extant = (int32_t)a1x; o.a2_extant = (int32_t)a2x;
             // subset_by_min_hcount with EXTANT_NODES_ONLY (HC.java:3783-3905)
-            const bool u1 = (int32_t)a1x >= min_hcount, u2 = (int32_t)a2x >= min_hcount;
-            fl = PB_SF_BI | (u1 ? PB_SF_A1_USE : 0) | (u2 ? PB_SF_A2_USE : 0) | (uint8_t)(a1 << PB_SF_A1_CODE_SHIFT);
-            if (u1 || u2) scan = (1ull << 38) | (uint64_t)((u1 ? a1s : 0u) + (u2 ? a2s : 0u));
+            u1 = (int32_t)a1x >= min_hcount; u2 = (int32_t)a2x >= min_hcount;
+            // an in-use allele keeps all its sampled leaf events unless its bucket was emptied by the <2 rule (possible only with
+            // min_hcount == 0, where in_use does not imply a surviving bucket): a1s / a2s are already 0 then
+            n1 = u1 ? a1s : 0u; n2 = u2 ? a2s : 0u;
+            fl = PB_SF_BI | (u1 ? PB_SF_A1_USE : 0) | (u2 ? PB_SF_A2_USE : 0) | (uint8_t)(a1 << PB_SF_A1_CODE_SHIFT) |
+                 (a1c >= 2 ? PB_SF_A1_ALIVE : 0) | (a2c >= 2 ? PB_SF_A2_ALIVE : 0) | ((u1 || u2) ? PB_SF_INF : 0);
+            if (u1 || u2) mine = (1ull << 40) | (uint64_t)(n1 + n2);
         }
         sites[s] = o;
         flags[s] = fl;
-        scan_in[s] = scan;
         atomicAdd(&s_cls[n_alleles], 1u);
     }
-    __syncthreads();
-    if (threadIdx.x < 5 && s_cls[threadIdx.x]) atomicAdd(class_counts + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
-}
-
-// ---- exclusive scan (3 phases) -------------------------------------------------------------------
-#define SCAN_BLOCK 1024
-__global__ void scan_block_sums(const uint64_t* __restrict__ in, int64_t n, uint64_t* __restrict__ sums) {
-    __shared__ uint64_t sh[32];
-    const int64_t i = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
-    uint64_t v = i < n ? in[i] : 0;
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        v = sh[threadIdx.x];
-        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) sums[blockIdx.x] = v;
+    // ---- block-wide exclusive scan of `mine` (per-tile sums fit: inf <= 512, events < 2^40)
+    uint64_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
-}
-__global__ void scan_sums_serial(uint64_t* sums, int64_t nb, uint64_t* total) {
-    // single block; nb <= a few thousand
-    __shared__ uint64_t sh[SCAN_BLOCK];
-    uint64_t carry = 0;
-    for (int64_t base = 0; base < nb; base += SCAN_BLOCK) {
-        const int64_t i = base + threadIdx.x;
-        uint64_t v = i < nb ? sums[i] : 0;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
-            uint64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t v = lane < TAIL_TILE / 32 ? s_warp[lane] : 0, iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
         }
-        if (i < nb) sums[i] = carry + sh[threadIdx.x] - v;  // exclusive
-        const uint64_t blk_total = sh[SCAN_BLOCK - 1];
-        __syncthreads();
-        carry += blk_total;
-    }
-    if (threadIdx.x == 0) *total = carry;
-}
-__global__ void scan_apply(const uint64_t* __restrict__ in, int64_t n, const uint64_t* __restrict__ sums, uint64_t* __restrict__ out) {
-    __shared__ uint64_t sh[SCAN_BLOCK];
-    const int64_t i = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
-    const uint64_t v = i < n ? in[i] : 0;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
-        uint64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-        __syncthreads();
-        sh[threadIdx.x] += t;
-        __syncthreads();
-    }
-    if (i < n) out[i] = sums[blockIdx.x] + sh[threadIdx.x] - v;
-}
-
-// The block-sum scratch belongs to the context (it used to be one process-wide buffer keyed by device: two contexts of one
-// process on different GPUs, or driven from different host threads, would have overwritten each other's pointer).
-int pbk_exclusive_scan_u64(pb_ctx* ctx, const uint64_t* in, uint64_t* out, int64_t n, uint64_t* d_total) {
-    const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    if (nb > ctx->scan_tmp_cap || !ctx->d_scan_tmp) {
-        if (ctx->d_scan_tmp) { cudaFree(ctx->d_scan_tmp); ctx->d_scan_tmp = nullptr; ctx->scan_tmp_cap = 0; }
-        PB_CUDA(cudaMalloc(&ctx->d_scan_tmp, (size_t)(nb + 1) * 8));
-        ctx->scan_tmp_cap = nb;
-    }
-    uint64_t* const tmp = ctx->d_scan_tmp;
-    if (n == 0) { PB_CUDA(cudaMemsetAsync(d_total, 0, 8, ctx->stream)); return PB_OK; }
-    scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, tmp);
-    scan_sums_serial<<<1, SCAN_BLOCK, 0, ctx->stream>>>(tmp, nb, d_total);
-    scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, tmp, out);
-    ctx->tm.n_launches += 3;
-    PB_CUDA(cudaGetLastError());
-    return PB_OK;
-}
-
-// ---- informative-site compaction + CSR of extant events ---------------------------------------------
-__global__ void k1_scatter_sites_kernel(int64_t S, const uint8_t* __restrict__ flags, const uint64_t* __restrict__ scan,
-                                        const uint64_t* __restrict__ scan_in, const uint32_t* __restrict__ cnt,
-                                        const pb_site_out* __restrict__ sites, int32_t* __restrict__ inf_site, AlleleMeta* __restrict__ alleles,
-                                        unsigned long long* __restrict__ class_counts /* [5]=n_max, [6]=A_inuse */) {
-    __shared__ unsigned int s_nmax, s_ause;
-    if (threadIdx.x == 0) { s_nmax = 0; s_ause = 0; }
-    __syncthreads();
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < S && (scan_in[s] >> 38)) {
-        const uint8_t fl = flags[s];
-        const int64_t i = (int64_t)(scan[s] >> 38);
-        const int64_t off = (int64_t)(scan[s] & ((1ull << 38) - 1));
-        const int a1 = (fl >> PB_SF_A1_CODE_SHIFT) & 3;
-        const uint32_t* c = cnt + s * PB_CNT_STRIDE;
-        const uint32_t xs_all = c[8] + c[9] + c[10] + c[11];
-        const bool u1 = fl & PB_SF_A1_USE, u2 = fl & PB_SF_A2_USE;
-        // an in-use allele keeps all its leaf events unless its bucket was emptied by the <2 rule
-        // (possible only with min_hcount == 0, where in_use does not imply a surviving bucket)
-        const pb_site_out so = sites[s];
-        const uint32_t n1 = (u1 && so.a1_count >= 2) ? c[8 + a1] : 0u, n2 = (u2 && so.a2_count >= 2) ? xs_all - c[8 + a1] : 0u;
-        inf_site[i] = (int32_t)s;
-        AlleleMeta m1{}, m2{};
-        m1.off = off; m1.n = (int32_t)n1; m1.flags = u1 ? PB_AF_IN_USE : 0;
-        m2.off = off + n1; m2.n = (int32_t)n2; m2.flags = u2 ? PB_AF_IN_USE : 0;
-        alleles[2 * i] = m1;
-        alleles[2 * i + 1] = m2;
-        atomicMax(&s_nmax, max(n1, n2));
-        atomicAdd(&s_ause, (unsigned int)((u1 ? 1 : 0) + (u2 ? 1 : 0)));
+        if (lane < TAIL_TILE / 32) s_warp[lane] = iv - v;     // exclusive warp offsets
+        const uint64_t agg = __shfl_sync(0xffffffffu, iv, 31);   // the tile's aggregate
+        // ---- decoupled look-back (warp 0)
+        unsigned long long* st = state + 1;
+        uint64_t excl_inf = 0, excl_ev = 0;
+        if (tile > 0) {
+            if (lane == 0) { *reinterpret_cast<volatile unsigned long long*>(st + 3 * tile) = TS_VALID | agg; }
+            int64_t idx = tile - 1;
+            for (;;) {
+                const int64_t t = idx - lane;
+                uint64_t ag = 0, pi = 0, pe = 0;
+                bool has_p = true, ready = true;   // lanes beyond tile 0 count as a ready zero prefix
+                if (t >= 0) {
+                    do {
+                        pi = ld_volatile_u64(st + 3 * t + 1); pe = ld_volatile_u64(st + 3 * t + 2);
+                        has_p = (pi & TS_VALID) && (pe & TS_VALID);
+                        ag = has_p ? 0 : ld_volatile_u64(st + 3 * t);
+                        ready = has_p || (ag & TS_VALID);
+                    } while (!ready);
+                } else { pi = TS_VALID; pe = TS_VALID; }
+                const unsigned pm = __ballot_sync(0xffffffffu, has_p);
+                const int first_p = pm ? (__ffs((int)pm) - 1) : 32;            // nearest predecessor holding an inclusive prefix
+                uint64_t ci = 0, ce = 0;
+                if (lane < first_p) { ci = (ag & ~TS_VALID) >> 40; ce = ag & ((1ull << 40) - 1); }
+                else if (lane == first_p) { ci = pi & ~TS_VALID; ce = pe & ~TS_VALID; }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) { ci += __shfl_down_sync(0xffffffffu, ci, o); ce += __shfl_down_sync(0xffffffffu, ce, o); }
+                excl_inf += __shfl_sync(0xffffffffu, ci, 0); excl_ev += __shfl_sync(0xffffffffu, ce, 0);
+                if (pm) break;
+                idx -= 32;
+            }
+        }
+        if (lane == 0) {
+            const uint64_t inc_inf = excl_inf + (agg >> 40), inc_ev = excl_ev + (agg & ((1ull << 40) - 1));
+            *reinterpret_cast<volatile unsigned long long*>(st + 3 * tile + 1) = TS_VALID | inc_inf;
+            *reinterpret_cast<volatile unsigned long long*>(st + 3 * tile + 2) = TS_VALID | inc_ev;
+            s_excl = (excl_inf << 38) | excl_ev;
+            if ((tile + 1) * TAIL_TILE >= S) class_counts[7] = (inc_inf << 38) | inc_ev;      // totals: S_inf, E
+        }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && s_ause) {
+    if (s < S) {
+        const uint64_t ex = incl - mine + s_warp[warp];                 // exclusive within the tile
+        const uint64_t i = (s_excl >> 38) + (ex >> 40);
+        const uint64_t off = (s_excl & ((1ull << 38) - 1)) + (ex & ((1ull << 40) - 1));
+        scan_out[s] = (i << 38) | off;
+        if (mine) {
+            inf_site[i] = (int32_t)s;
+            AlleleMeta m1{}, m2{};
+            m1.off = (int64_t)off; m1.n = (int32_t)n1; m1.flags = u1 ? PB_AF_IN_USE : 0;
+            m2.off = (int64_t)(off + n1); m2.n = (int32_t)n2; m2.flags = u2 ? PB_AF_IN_USE : 0;
+            alleles[2 * i] = m1;
+            alleles[2 * i + 1] = m2;
+            atomicMax(&s_nmax, max(n1, n2));
+            atomicAdd(&s_ause, (unsigned int)((u1 ? 1 : 0) + (u2 ? 1 : 0)));
+        }
+    }
+    __syncthreads();
+    if (tid < 5 && s_cls[tid]) atomicAdd(class_counts + tid, (unsigned long long)s_cls[tid]);
+    if (tid == 0 && s_ause) {
         atomicMax(class_counts + 5, (unsigned long long)s_nmax);
         atomicAdd(class_counts + 6, (unsigned long long)s_ause);
     }
 }
 
+// ---- CSR of extant events ------------------------------------------------------------------------------------------
 template <bool XMODE>
 __global__ void k1_scatter_events_kernel(const raw_rec_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
                                          const int32_t* __restrict__ node_sample, const uint8_t* __restrict__ flags,
-                                         const uint64_t* __restrict__ scan, const uint64_t* __restrict__ scan_in,
-                                         const pb_site_out* __restrict__ sites, const AlleleMeta* __restrict__ alleles,
+                                         const uint64_t* __restrict__ scan, const AlleleMeta* __restrict__ alleles,
                                          const uint64_t* __restrict__ xmask, uint32_t* __restrict__ csr_cursor, int32_t* __restrict__ csr,
-                                         int64_t csr_cap) {
+                                         int64_t csr_cap, unsigned long long* __restrict__ cursor_copy) {
     const int64_t n = min((int64_t)*cursor, raw_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *cursor_copy = *cursor;   // the sweep's record count joins the tail's one readback
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const ev_rec_t r = load_rec<XMODE>(raw, i);
         if (!r.leaf || r.nomrca) continue;                // extant (leaf) events only (EXTANT_NODES_ONLY, HC.java:173)
@@ -815,14 +809,12 @@ __global__ void k1_scatter_events_kernel(const raw_rec_t* __restrict__ raw, cons
             const int b = __ffsll((long long)m) - 1;
             m &= m - 1;
             const uint32_t site = r.wcol * 64u + (uint32_t)b;
-            if (!(scan_in[site] >> 38)) continue;
             const uint8_t fl = flags[site];
+            if (!(fl & PB_SF_INF)) continue;
             const uint32_t base = event_base<XMODE>(r, b, xmask);
             const int a = (base == ((fl >> PB_SF_A1_CODE_SHIFT) & 3u)) ? 0 : 1;
-            if (!(fl & (a == 0 ? PB_SF_A1_USE : PB_SF_A2_USE))) continue;
-            // bucket emptied by the <2 rule?  (in_use with min_hcount 0 keeps n = 0)
-            const pb_site_out so = sites[site];
-            if ((a == 0 ? so.a1_count : so.a2_count) < 2) continue;
+            // allele in use, and its bucket not emptied by the <2 rule (in_use with min_hcount 0 keeps n = 0)
+            if (!(fl & (a == 0 ? PB_SF_A1_USE : PB_SF_A2_USE)) || !(fl & (a == 0 ? PB_SF_A1_ALIVE : PB_SF_A2_ALIVE))) continue;
             const int64_t slot = 2 * (int64_t)(scan[site] >> 38) + a;
             const uint32_t k = atomicAdd(csr_cursor + slot, 1u);
             const int64_t o = alleles[slot].off + k;
@@ -982,6 +974,17 @@ int pbk_prepare_tail(pb_ctx* ctx) {
         ctx->csr_cap = std::max(ctx->raw_cap, ctx->csr_want);
         PB_CUDA(cudaMalloc(&ctx->d_csr, (size_t)ctx->csr_cap * 4));
     }
+    {
+        const int64_t need = 1 + 3 * ((S + TAIL_TILE - 1) / TAIL_TILE);     // ticket + per-tile {aggregate, prefix inf, prefix ev}
+        if (need > ctx->scan_state_cap) {
+            if (ctx->d_scan_state) cudaFree(ctx->d_scan_state);
+            ctx->d_scan_state = nullptr; ctx->scan_state_cap = 0;
+            PB_CUDA(cudaMalloc(&ctx->d_scan_state, (size_t)need * 8));
+            ctx->scan_state_cap = need;
+        }
+        PB_CUDA(cudaMemsetAsync(ctx->d_scan_state, 0, (size_t)need * 8, ctx->stream2));
+        PB_CUDA(cudaMemsetAsync(ctx->d_class_counts, 0, 12 * 8, ctx->stream2));   // words 12.. belong to pb_run_assoc
+    }
     PB_CUDA(cudaMemsetAsync(ctx->d_cnt, 0, (size_t)S * PB_CNT_ALLOC_STRIDE * 4, ctx->stream2));   // counters + the one-plane census sum
     PB_CUDA(cudaMemsetAsync(ctx->d_csr_cursor, 0, (size_t)S * 2 * 4, ctx->stream2));
     PB_CUDA(cudaEventRecord(ctx->ev_zero_done, ctx->stream2));
@@ -993,22 +996,23 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     const int T = 256;
     cudaStream_t st = ctx->stream;
     const unsigned ev_blocks = (unsigned)std::min<int64_t>((ctx->raw_cap + T - 1) / T, (int64_t)ctx->sm_count * 16);
-    PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_zero_done, 0));   // d_cnt, d_csr_cursor zeroed underneath K1 (pbk_prepare_tail)
-    PB_CUDA(cudaMemsetAsync(ctx->d_class_counts, 0, 16 * 8, st));
+    PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_zero_done, 0));   // counters, cursors, scan state, class counts zeroed underneath K1 (pbk_prepare_tail)
     pb_trace_mark(ctx, "headstart+memsets");
     const bool xmode = ctx->plane_mode == PB_PLANES_X;
     const uint64_t* xmask = xmode ? ctx->d_xmask : nullptr;
     int32_t* xcensus = reinterpret_cast<int32_t*>(ctx->d_cnt + S * PB_CNT_STRIDE);
     int kt_used = 1;
     while ((1ll << kt_used) <= (int64_t)ctx->L) kt_used++;
+    const unsigned n_tiles = (unsigned)((S + TAIL_TILE - 1) / TAIL_TILE);
     if (xmode) {
         // one-plane mode: the leaf census is a by-product of the record pass (no dense counters, nothing to reduce)
         k1_count_events_kernel<true><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_leaves_below,
                                                               xmask, ctx->d_cnt, xcensus, ctx->d_class_counts + 9);
         pb_trace_mark(ctx, "count_events");
-        k1_finalize_kernel<true><<<(unsigned)((S + T - 1) / T), T, 0, st>>>(
+        k1_finalize_compact_kernel<true><<<n_tiles, TAIL_TILE, 0, st>>>(
             nullptr, xcensus, kt_used, ctx->W, S, ctx->d_X, ctx->d_xmask, ctx->d_xvalid, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt,
-            ctx->cfg.min_hcount, ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan, ctx->d_class_counts);
+            ctx->cfg.min_hcount, ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan, ctx->d_inf_site, ctx->d_alleles,
+            ctx->d_scan_state, ctx->d_class_counts);
         ctx->tm.n_launches += 2;
     } else {
         k1_count_events_kernel<false><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, nullptr, nullptr,
@@ -1016,32 +1020,24 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
         pb_trace_mark(ctx, "count_events");
         k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), 4), 128, 0, st>>>(ctx->d_census, ctx->n_flush, ctx->W, ctx->d_census_total);
         pb_trace_mark(ctx, "census_reduce");
-        k1_finalize_kernel<false><<<(unsigned)((S + T - 1) / T), T, 0, st>>>(
+        k1_finalize_compact_kernel<false><<<n_tiles, TAIL_TILE, 0, st>>>(
             ctx->d_census_total, nullptr, kt_used, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt, ctx->cfg.min_hcount,
-            ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan /* reused as scan input */, ctx->d_class_counts);
+            ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan, ctx->d_inf_site, ctx->d_alleles, ctx->d_scan_state,
+            ctx->d_class_counts);
         ctx->tm.n_launches += 3;
     }
-    pb_trace_mark(ctx, "finalize");
+    pb_trace_mark(ctx, "finalize+compact");
     PB_CUDA(cudaGetLastError());
-    // scan: d_site_scan (input) -> d_site_scan_out.  We keep input in the first half of a 2*S buffer.
-    uint64_t* scan_in = ctx->d_site_scan;
-    uint64_t* scan_out = ctx->d_site_scan + S;
-    int rc = pbk_exclusive_scan_u64(ctx, scan_in, scan_out, S, (uint64_t*)(ctx->d_class_counts + 7));
-    if (rc) return rc;
-    pb_trace_mark(ctx, "scan");
-    k1_scatter_sites_kernel<<<(unsigned)((S + T - 1) / T), T, 0, st>>>(S, ctx->d_site_flags, scan_out, scan_in, ctx->d_cnt, ctx->d_sites,
-                                                                      ctx->d_inf_site, ctx->d_alleles, ctx->d_class_counts);
-    pb_trace_mark(ctx, "scatter_sites");
+    uint64_t* scan_out = ctx->d_site_scan;
     if (xmode)
         k1_scatter_events_kernel<true><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
-                                                               scan_out, scan_in, ctx->d_sites, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr, ctx->csr_cap);
+                                                               scan_out, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr, ctx->csr_cap, ctx->d_class_counts + 8);
     else
         k1_scatter_events_kernel<false><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
-                                                                scan_out, scan_in, ctx->d_sites, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr, ctx->csr_cap);
+                                                                scan_out, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr, ctx->csr_cap, ctx->d_class_counts + 8);
     pb_trace_mark(ctx, "scatter_events");
-    ctx->tm.n_launches += 2;
+    ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
-    PB_CUDA(cudaMemcpyAsync(ctx->d_class_counts + 8, ctx->d_raw_cursor, 8, cudaMemcpyDeviceToDevice, st));
     unsigned long long h[16];
     PB_CUDA(cudaMemcpyAsync(h, ctx->d_class_counts, sizeof(h), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));

@@ -79,6 +79,9 @@ static_assert(PB_XT_NODE_MASK == PB_OPX_NODE_MASK && PB_XT_NOMRCA == PB_OPX_NOMR
 #define PB_SF_A1_USE 2u
 #define PB_SF_A2_USE 4u
 #define PB_SF_A1_CODE_SHIFT 3  // 2 bits
+#define PB_SF_A1_ALIVE 32u     // the allele's MRCA bucket survived the <2 rule (a_count >= 2)
+#define PB_SF_A2_ALIVE 64u
+#define PB_SF_INF 128u         // homoplasically informative: some allele in use (subset_by_min_hcount)
 
 // census: 4 per-base leaf counters, bit-sliced: slices 0..2 (ones/twos/fours) in registers,
 // PB_K1_KHI high slices in shared memory; a census segment holds at most PB_K1_SEG_LEAVES leaves
@@ -207,6 +210,7 @@ struct pb_ctx {
     pb_site_out* d_sites = nullptr;    // [S]
     uint8_t* d_site_flags = nullptr;   // [S]
     uint64_t* d_site_scan = nullptr;   // [S] exclusive prefix: inf count << 38 | event count
+    unsigned long long* d_scan_state = nullptr; int64_t scan_state_cap = 0;   // single-pass scan of the tail: ticket + 3 words per tile
     unsigned long long* d_class_counts = nullptr;  // 5 + n_max + scan totals ...
     bool events_done = false;
 
@@ -244,7 +248,6 @@ struct pb_ctx {
     int64_t n_work[4] = {0, 0, 0, 0};
     int sort_blocks_per_sm = -1;                                 // occupancy of k4_sort_coop_kernel on this context's device
     bool k1_attr_set = false, k1x_attr_set = false;              // cudaFuncSetAttribute(max dynamic shared memory) done on this context's device
-    uint64_t* d_scan_tmp = nullptr; int64_t scan_tmp_cap = 0;   // block sums of pbk_exclusive_scan_u64 (per context: contexts of one process may sit on different GPUs / host threads)
     uint32_t* d_colpop = nullptr; int64_t colpop_cap = 0;  // [2][P] per-sample case / missing-label popcounts of the current tile
     int32_t* d_fb_reps = nullptr;  // fallback replicate list
     unsigned int* d_fb_count = nullptr;
@@ -289,7 +292,6 @@ int pbk_ptable(pb_ctx* ctx);                                   // k4_pvalues.cu
 int pbk_thresholds(pb_ctx* ctx);                               // k4_pvalues.cu
 int pbk_pvalues(pb_ctx* ctx);                                  // k4_pvalues.cu
 int pbk_extras(pb_ctx* ctx, double* h_exact_pointwise, double* h_fisher);   // k5_extras.cu
-int pbk_exclusive_scan_u64(pb_ctx* ctx, const uint64_t* in, uint64_t* out, int64_t n, uint64_t* d_total);  // k1_events.cu
 
 // pb_comm.cu: peer-memory exchange
 int pbx_export(pb_ctx* ctx, void* handle64);

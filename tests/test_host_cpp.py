@@ -322,3 +322,30 @@ def test_native_host_files_match_python_host_and_oracle(tmp_path, oracle_mod, ne
     # min_hcount too high: the reference's message and exit status (HC.java:3866-3869)
     r = run(*args, "-X", "-c", "100000", ok=False)
     assert r.returncode == 255 and "is set too high and has filtered out all segregating sites" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("real_gpus", [False, True])
+def test_native_host_multi_gpu_in_one_process(tmp_path, monkeypatch, real_gpus):
+    """`--devices d0,d1,...`: the single-process host (the shape of the reference's one JVM, HC.java:230-319) drives several
+    site shards through pb_group and must write the same three files (+ extras) as the one-GPU run, byte for byte.
+    real_gpus=False puts three shards on GPU 0 (test hook) so that a one-GPU box covers it too."""
+    import torch
+    n = torch.cuda.device_count()
+    if real_gpus and n < 2:
+        pytest.skip("needs 2 GPUs")
+    devices = ",".join(str(d) for d in range(min(n, 8))) if real_gpus else "0,0,0"
+    if not real_gpus:
+        monkeypatch.setenv("PB_GROUP_ALLOW_SAME_DEVICE", "1")
+    t = synth.yule_tree(300, 31)
+    S = 64 * 90 + 17
+    chars = synth.planes_to_chars(*synth.simulate_planes(t, S, 32, leaf_gap=True, multiallelic_frac=0.01), 0, S)
+    sn, lab = synth.simulate_phenotypes(t, 33, na_frac=0.02, no_row_frac=0.02)
+    paths = synth.write_inputs(str(tmp_path), t, chars, sn, lab, line_width=80, seed=6)
+    common = ["-u", "-f", paths["fasta"], "-t", paths["tree"], "-p", paths["pheno"], "-m", paths["map"], "-r", "2000", "--seed", "77",
+              "--tile-sites", "1024", "--extras", "-d", str(tmp_path / "o")]
+    r1 = run(*common, "-o", "one.out")
+    rn = run(*common, "-o", "multi.out", "--devices", devices)
+    assert "homoplasically informative sites" in rn.stdout
+    for suffix in ("", ".sorted_by_a2_maxT", ".sorted_by_a1_maxT", ".extras"):
+        assert open(str(tmp_path / "o" / "multi.out") + suffix).read() == open(str(tmp_path / "o" / "one.out") + suffix).read(), suffix
