@@ -260,6 +260,17 @@ int64_t pb_fasta_num_records(pb_fasta* f);
 int pb_fasta_record(pb_fasta* f, int64_t i, const char** name, int64_t* name_len, int64_t* seq_len);
 int pb_fasta_pack_tile(pb_fasta* f, const int32_t* node_of_record, int64_t site_begin, int64_t n_sites_tile,
                        uint64_t* B0, uint64_t* B1, uint64_t* V, int64_t pitch_words, int32_t n_threads);
+/* One pass from the FASTA text to the compact upload format of pb_put_planes_biallelic (V = NULL): X bit = the node's
+ * character differs from the first mapped record's at that site, colmask = {first base, first XOR second base} codes.
+ * Returns 1 when the tile qualifies — every node has exactly one mapped record covering the tile, every site carries at
+ * most two distinct characters and both are upper-case A/C/G/T (so every genotype is valid) — else 0 (outputs undefined:
+ * pack that tile with pb_fasta_pack_tile, optionally followed by pb_compact_planes).  No three-plane intermediate, no
+ * compaction pass: per 32 sites one byte compare and one movemask. */
+int pb_fasta_pack_tile_biallelic(pb_fasta* f, const int32_t* node_of_record, int64_t n_nodes, int64_t site_begin, int64_t n_sites_tile,
+                                 uint64_t* X, int64_t pitch_words, uint64_t* colmask, int32_t n_threads);
+/* the same from a character matrix (node-major, row v at seq + v*seq_pitch; the reference row is row 0) */
+int pb_pack_chars_biallelic(const char* seq, int64_t n_nodes, int64_t n_sites, int64_t seq_pitch, uint64_t* X, int64_t x_pitch_words,
+                            uint64_t* colmask, int32_t n_threads);
 const char* pb_fasta_last_error(void);
 /* Pinned host allocations for streaming uploads. */
 int pb_host_alloc(void** out, uint64_t bytes);

@@ -5,4 +5,4 @@ here; see DESIGN.md.  Everything numeric runs in libpoutine_b200.so (hand-writte
 include/poutine_b200.h); this package is the thin host mirror used by tests and bench.
 """
 from ._lib import LIB_PATH, build  # noqa: F401
-from .counter import HomoplasyCounter, HomoplasyCounterGroup, NoInformativeSites, PoutineError, comm_unique_id, compact_planes, pack_chars  # noqa: F401
+from .counter import HomoplasyCounter, HomoplasyCounterGroup, NoInformativeSites, PoutineError, comm_unique_id, compact_planes, pack_chars, pack_chars_biallelic  # noqa: F401

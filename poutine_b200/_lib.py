@@ -57,7 +57,7 @@ EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_set_tree", "pb_set_la
            "pb_get_maxT_unsorted", "pb_get_ptable", "pb_get_timings", "pb_stopwatch_mark", "pb_stopwatch_ms", "pb_comm_unique_id", "pb_comm_init",
            "pb_pack_chars", "pb_host_alloc", "pb_host_free", "pb_version",
            "pb_fasta_open", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_record", "pb_fasta_pack_tile", "pb_fasta_last_error",
-           "pb_comm_export", "pb_comm_connect",
+           "pb_comm_export", "pb_comm_connect", "pb_fasta_pack_tile_biallelic", "pb_pack_chars_biallelic",
            "pb_group_create", "pb_group_destroy", "pb_group_last_error", "pb_group_size", "pb_group_ctx", "pb_group_set_tree",
            "pb_group_set_labels", "pb_group_set_sites", "pb_group_shard_range", "pb_group_put_planes", "pb_group_put_planes_biallelic",
            "pb_group_run_events", "pb_group_run_assoc", "pb_group_run_extras", "pb_group_get_timings", "pb_group_stopwatch_mark",
@@ -114,6 +114,8 @@ def lib():
         L.pb_fasta_record.argtypes = [vp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
         L.pb_fasta_pack_tile.argtypes = [vp, vp, i64, i64, vp, vp, vp, i64, i32]
         L.pb_fasta_last_error.argtypes = []; L.pb_fasta_last_error.restype = C.c_char_p
+        L.pb_fasta_pack_tile_biallelic.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp, i32]
+        L.pb_pack_chars_biallelic.argtypes = [vp, i64, i64, i64, vp, i64, vp, i32]
         L.pb_comm_export.argtypes = [vp, vp]
         L.pb_comm_connect.argtypes = [vp, vp, i32, i32]
         L.pb_group_create.argtypes = [C.POINTER(PbConfig), vp, i32, C.POINTER(vp)]

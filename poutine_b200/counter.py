@@ -44,6 +44,23 @@ def pack_chars(seq: np.ndarray, pitch_words: int | None = None):
     return B0, B1, V
 
 
+def pack_chars_biallelic(seq: np.ndarray, pitch_words: int | None = None, n_threads=0):
+    """seg_sites chars (N, S) -> (X, colmask) for put_planes_biallelic(X, None, colmask) in ONE pass, or None when the
+    alignment does not qualify (some genotype is not an upper-case ACGT, or a site carries three bases): then use
+    pack_chars [+ compact_planes].  Host packer csrc/fasta.cpp pb_pack_chars_biallelic."""
+    seq = np.ascontiguousarray(seq)
+    assert seq.ndim == 2 and seq.dtype.itemsize == 1
+    N, S = seq.shape
+    W = (S + 63) // 64
+    pw = pitch_words or W
+    X = np.empty((N, pw), dtype=np.uint64)
+    colmask = np.empty((W, 4), dtype=np.uint64)
+    rc = _lib.lib().pb_pack_chars_biallelic(ptr(seq), N, S, seq.strides[0], ptr(X), pw, ptr(colmask), int(n_threads))
+    if rc < 0:
+        raise PoutineError(rc, "pb_pack_chars_biallelic: invalid arguments")
+    return (X[:, :W], colmask) if rc == 1 else None
+
+
 def compact_planes(B0, B1, V, n_sites, X=None, n_threads=0):
     """Full planes of a column tile -> (X, colmask, all_valid) for put_planes_biallelic, or None when some site of the
     tile carries three or more distinct bases over all nodes (host helper pb_compact_planes, csrc/packer.cpp)."""

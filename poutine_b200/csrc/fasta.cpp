@@ -236,3 +236,185 @@ extern "C" int pb_fasta_pack_tile(pb_fasta* f, const int32_t* node_of_record, in
     for (auto& t : th) t.join();
     return PB_OK;
 }
+
+// =====================================================================================================================
+// One pass from genotype characters to the COMPACT upload format of pb_put_planes_biallelic (no three-plane detour, no
+// compaction pass): the host side of build_seg_sites (HC.java:1241-1306) for the usual alignment — every genotype an
+// upper-case A/C/G/T, at most two bases per site.
+//   reference row  = the first mapped record's characters (ref[s]: the site's "first base", colmask A1:A0)
+//   X bit          = this node's character differs from ref[s]                (one byte compare + movemask per 32 sites)
+//   second[s]      = THE other character of the site: every differing character must equal it (checked while packing,
+//                    per worker thread, merged at the end); colmask D1:D0 = code(ref) ^ code(second)
+// A tile qualifies (return 1) when ref[s] and second[s] are upper-case ACGT for every site, every record covers the tile
+// and every node got a row; otherwise 0 (outputs undefined): pack that tile with pb_fasta_pack_tile (+ pb_compact_planes).
+// Validity needs no per-character test: a character equals ref[s] or second[s], and those two are checked once per site.
+namespace {
+
+struct XPackCtx {
+    const unsigned char* ref;      // tile chars of the reference row
+    int64_t n;                     // sites in the tile
+};
+
+// one row: X words out, second[] updated; returns false when a third character shows up at some site
+static bool xpack_row_scalar(const unsigned char* x, const unsigned char* ref, unsigned char* sec, int64_t n, uint64_t* out) {
+    bool bad = false;
+    for (int64_t w = 0; w * 64 < n; w++) {
+        uint64_t bits = 0;
+        const int64_t lim = std::min<int64_t>(64, n - w * 64);
+        for (int64_t j = 0; j < lim; j++) {
+            const int64_t i = w * 64 + j;
+            if (x[i] != ref[i]) {
+                bits |= 1ull << j;
+                if (sec[i] == 0) sec[i] = x[i];
+                else if (sec[i] != x[i]) bad = true;
+            }
+        }
+        out[w] = bits;
+    }
+    return !bad;
+}
+
+#ifdef PB_HAVE_X86
+__attribute__((target("avx2"))) static bool xpack_row_avx2(const unsigned char* x, const unsigned char* ref, unsigned char* sec, int64_t n,
+                                                           uint64_t* out) {
+    __m256i badv = _mm256_setzero_si256();
+    const __m256i zero = _mm256_setzero_si256();
+    const int64_t full = n / 64;
+    for (int64_t w = 0; w < full; w++) {
+        uint64_t bits = 0;
+        for (int h = 0; h < 2; h++) {
+            const int64_t i = w * 64 + 32 * h;
+            const __m256i xv = _mm256_loadu_si256((const __m256i*)(x + i)), rv = _mm256_loadu_si256((const __m256i*)(ref + i));
+            const __m256i eq = _mm256_cmpeq_epi8(xv, rv);
+            const uint32_t eqm = (uint32_t)_mm256_movemask_epi8(eq);
+            bits |= (uint64_t)(~eqm) << (32 * h);
+            if (eqm != 0xFFFFFFFFu) {                      // rows mostly equal the reference: the second-base check is the rare path
+                const __m256i sv = _mm256_loadu_si256((const __m256i*)(sec + i));
+                const __m256i unset = _mm256_cmpeq_epi8(sv, zero), eqs = _mm256_cmpeq_epi8(xv, sv);
+                const __m256i take = _mm256_andnot_si256(eq, unset);                       // differs, second not known yet
+                _mm256_storeu_si256((__m256i*)(sec + i), _mm256_blendv_epi8(sv, xv, take));
+                // differs, second known, and it is not the second: a third character
+                badv = _mm256_or_si256(badv, _mm256_andnot_si256(_mm256_or_si256(_mm256_or_si256(eq, unset), eqs), _mm256_set1_epi8((char)0xFF)));
+            }
+        }
+        out[w] = bits;
+    }
+    bool ok = _mm256_testz_si256(badv, badv) != 0;
+    if (full * 64 < n) ok = xpack_row_scalar(x + full * 64, ref + full * 64, sec + full * 64, n - full * 64, out + full) && ok;
+    return ok;
+}
+#endif
+
+typedef bool (*xpack_row_fn)(const unsigned char*, const unsigned char*, unsigned char*, int64_t, uint64_t*);
+static xpack_row_fn xpack_select() {
+#ifdef PB_HAVE_X86
+    if (__builtin_cpu_supports("avx2")) return xpack_row_avx2;
+#endif
+    return xpack_row_scalar;
+}
+
+static inline int base_code(unsigned char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+
+// merge the workers' second[] arrays, validate, write the colmask words {A0, A1, D0, D1}; false = the tile does not qualify
+static bool xpack_finish(const unsigned char* ref, std::vector<std::vector<unsigned char>>& secs, int64_t n, uint64_t* colmask) {
+    const int64_t W = (n + 63) / 64;
+    for (int64_t w = 0; w < W; w++) {
+        uint64_t a0 = 0, a1 = 0, d0 = 0, d1 = 0;
+        const int64_t lim = std::min<int64_t>(64, n - w * 64);
+        for (int64_t j = 0; j < lim; j++) {
+            const int64_t i = w * 64 + j;
+            unsigned char s2 = 0;
+            for (auto& sv : secs) {
+                const unsigned char c = sv[(size_t)i];
+                if (!c) continue;
+                if (s2 == 0) s2 = c; else if (s2 != c) return false;          // two workers saw different second characters
+            }
+            const int ca = base_code(ref[i]);
+            if (ca < 0) return false;
+            int cd = 0;
+            if (s2) { const int cs = base_code(s2); if (cs < 0) return false; cd = ca ^ cs; }
+            a0 |= (uint64_t)(ca & 1) << j; a1 |= (uint64_t)(ca >> 1) << j;
+            d0 |= (uint64_t)(cd & 1) << j; d1 |= (uint64_t)(cd >> 1) << j;
+        }
+        colmask[4 * w] = a0; colmask[4 * w + 1] = a1; colmask[4 * w + 2] = d0; colmask[4 * w + 3] = d1;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" int pb_fasta_pack_tile_biallelic(pb_fasta* f, const int32_t* node_of_record, int64_t n_nodes, int64_t site_begin,
+                                            int64_t n_sites_tile, uint64_t* X, int64_t pitch_words, uint64_t* colmask, int32_t n_threads) {
+    if (!f || !node_of_record || !X || !colmask || n_nodes < 1 || site_begin < 0 || (site_begin & 63) || n_sites_tile < 1 ||
+        pitch_words < (n_sites_tile + 63) / 64) {
+        g_fasta_err = "pb_fasta_pack_tile_biallelic: invalid arguments";
+        return PB_ERR_INVALID;
+    }
+    const int64_t nrec = (int64_t)f->recs.size(), n = n_sites_tile, W = (n + 63) / 64;
+    int64_t first = -1, mapped = 0;
+    for (int64_t i = 0; i < nrec; i++) {
+        const int32_t v = node_of_record[i];
+        if (v < 0) continue;
+        if (v >= n_nodes) { g_fasta_err = "pb_fasta_pack_tile_biallelic: node index out of range"; return PB_ERR_INVALID; }
+        if (f->recs[(size_t)i].seq_len < site_begin + n) return 0;            // a short record: missing genotypes
+        if (first < 0) first = i;
+        mapped++;
+    }
+    if (mapped != n_nodes) return 0;                                           // some node has no row (or two): not all-valid
+    std::vector<unsigned char> ref((size_t)W * 64, 0);
+    gather_chars(f, f->recs[(size_t)first], site_begin, site_begin + n, ref.data());
+    int64_t nt = n_threads > 0 ? n_threads : (int64_t)std::thread::hardware_concurrency();
+    nt = std::max<int64_t>(1, std::min(nt, nrec));
+    std::vector<std::vector<unsigned char>> secs((size_t)nt);
+    std::vector<char> ok((size_t)nt, 1);
+    const xpack_row_fn xrow = xpack_select();
+    auto work = [&](int64_t t) {
+        std::vector<unsigned char>& sec = secs[(size_t)t];
+        sec.assign((size_t)W * 64, 0);
+        std::vector<unsigned char> buf((size_t)W * 64, 0);
+        for (int64_t i = nrec * t / nt; i < nrec * (t + 1) / nt; i++) {
+            const int32_t v = node_of_record[i];
+            if (v < 0) continue;
+            gather_chars(f, f->recs[(size_t)i], site_begin, site_begin + n, buf.data());
+            if (!xrow(buf.data(), ref.data(), sec.data(), n, X + (int64_t)v * pitch_words)) { ok[(size_t)t] = 0; return; }
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int64_t t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto& t : th) t.join();
+    }
+    for (char o : ok) if (!o) return 0;
+    return xpack_finish(ref.data(), secs, n, colmask) ? 1 : 0;
+}
+
+// the same from a character matrix (node-major, row v at seq + v*seq_pitch)
+extern "C" int pb_pack_chars_biallelic(const char* seq, int64_t n_nodes, int64_t n_sites, int64_t seq_pitch, uint64_t* X,
+                                       int64_t x_pitch_words, uint64_t* colmask, int32_t n_threads) {
+    const int64_t W = (n_sites + 63) / 64;
+    if (!seq || !X || !colmask || n_nodes < 1 || n_sites < 1 || seq_pitch < n_sites || x_pitch_words < W) return PB_ERR_INVALID;
+    const unsigned char* ref = (const unsigned char*)seq;      // row 0
+    int64_t nt = n_threads > 0 ? n_threads : (int64_t)std::thread::hardware_concurrency();
+    nt = std::max<int64_t>(1, std::min(nt, n_nodes));
+    if (n_nodes * n_sites < (1 << 20)) nt = 1;
+    std::vector<std::vector<unsigned char>> secs((size_t)nt);
+    std::vector<char> ok((size_t)nt, 1);
+    const xpack_row_fn xrow = xpack_select();
+    auto work = [&](int64_t t) {
+        secs[(size_t)t].assign((size_t)W * 64, 0);
+        for (int64_t v = n_nodes * t / nt; v < n_nodes * (t + 1) / nt; v++) {
+            uint64_t* out = X + v * x_pitch_words;
+            if (!xrow((const unsigned char*)seq + v * seq_pitch, ref, secs[(size_t)t].data(), n_sites, out)) { ok[(size_t)t] = 0; return; }
+            for (int64_t w = W; w < x_pitch_words; w++) out[w] = 0;
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int64_t t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto& t : th) t.join();
+    }
+    for (char o : ok) if (!o) return 0;
+    return xpack_finish(ref, secs, n_sites, colmask) ? 1 : 0;
+}

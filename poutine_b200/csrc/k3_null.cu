@@ -355,25 +355,37 @@ __device__ __forceinline__ uint64_t at_least(const uint64_t (&x)[N]) {
     return 0;
 }
 
+// The sweeps read the label matrix with 16-byte loads: a lane owns the word PAIR (2q, 2q+1), q = lane, lane + 32, ...
+// Measured on this B200 (tools/microbench/l2_peak, profiles/r2_l2_peak.json): an L2-resident stream moves 15.0 TB/s with
+// 8 bytes per lane and 26.6 TB/s with 16 — the request rate, not the sector rate, is what an 8-byte sweep runs into
+// (round 1: 16.7 TB/s at C2).  Rows are 16-byte aligned (pitch = a multiple of 4 words, count tiles start at multiples of
+// 32 words) and the word behind an odd word count is zero padding written by the generator, which never counts (k* >= 1).
 #ifndef K3_SWEEP_UNROLL
-#define K3_SWEEP_UNROLL 8   // measured at C2: 8 loads per row in flight with 4 resident blocks beats 4 with 5 (0.62 -> 0.58 ms)
+#define K3_SWEEP_UNROLL 4   // 16-byte loads per row in flight (round 1: 8 x 8 bytes)
 #endif
 #ifndef K3_TIGHT_BLOCKS
 #define K3_TIGHT_BLOCKS 4
 #endif
+__device__ __forceinline__ ulonglong2 ldg_pair(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+
 template <int N, int K>
 __device__ __forceinline__ unsigned int sweep_fixed(const K3Params& p, const AlleleMeta& m, int lane, int words) {
-    const uint64_t* __restrict__ rp[N];
+    const ulonglong2* __restrict__ rp[N];
 #pragma unroll
-    for (int e = 0; e < N; e++) rp[e] = p.Xc + (int64_t)__ldg(p.csr + m.off + e) * p.Rw + lane;
+    for (int e = 0; e < N; e++) rp[e] = reinterpret_cast<const ulonglong2*>(p.Xc + (int64_t)__ldg(p.csr + m.off + e) * p.Rw) + lane;
     unsigned int rc = 0;
+    const int pairs = (words + 1) >> 1;
     constexpr int UNR = K3_SWEEP_UNROLL;
 #pragma unroll UNR
-    for (int w = lane, off = 0; w < words; w += 32, off += 32) {
-        uint64_t x[N];
+    for (int q = lane, off = 0; q < pairs; q += 32, off += 32) {
+        uint64_t a[N], b[N];
 #pragma unroll
-        for (int e = 0; e < N; e++) x[e] = __ldg(rp[e] + off);
-        rc += (unsigned int)__popcll(at_least<N, K>(x));
+        for (int e = 0; e < N; e++) { const ulonglong2 v = ldg_pair(rp[e] + off); a[e] = v.x; b[e] = v.y; }
+        rc += (unsigned int)__popcll(at_least<N, K>(a)) + (unsigned int)__popcll(at_least<N, K>(b));
     }
     return rc;
 }
@@ -381,22 +393,26 @@ __device__ __forceinline__ unsigned int sweep_fixed(const K3Params& p, const All
 // 4 <= n <= 7: bit-sliced 3-bit count, k >= k* with a warp-uniform k*
 __device__ __forceinline__ unsigned int sweep_upto7(const K3Params& p, const AlleleMeta& m, int lane, int words) {
     const int n = m.n, kstar = m.kstar;
-    const uint64_t* __restrict__ rp[7];
+    const ulonglong2* __restrict__ rp[7];
 #pragma unroll
-    for (int e = 0; e < 7; e++) rp[e] = p.Xc + (int64_t)((e < n) ? __ldg(p.csr + m.off + e) : 0) * p.Rw + lane;
+    for (int e = 0; e < 7; e++) rp[e] = reinterpret_cast<const ulonglong2*>(p.Xc + (int64_t)((e < n) ? __ldg(p.csr + m.off + e) : 0) * p.Rw) + lane;
     unsigned int rc = 0;
-#pragma unroll 2
-    for (int w = lane, off = 0; w < words; w += 32, off += 32) {
-        uint64_t c[3] = {0, 0, 0};
+    const int pairs = (words + 1) >> 1;
+#pragma unroll 1
+    for (int q = lane, off = 0; q < pairs; q += 32, off += 32) {
+        uint64_t c[3] = {0, 0, 0}, d[3] = {0, 0, 0};
 #pragma unroll
         for (int e = 0; e < 7; e++) {
             if (e < n) {
-                uint64_t x = __ldg(rp[e] + off);
+                const ulonglong2 v = ldg_pair(rp[e] + off);
+                uint64_t x = v.x, y = v.y;
 #pragma unroll
                 for (int j = 0; j < 3; j++) { const uint64_t t = c[j] & x; c[j] ^= x; x = t; }
+#pragma unroll
+                for (int j = 0; j < 3; j++) { const uint64_t t = d[j] & y; d[j] ^= y; y = t; }
             }
         }
-        rc += (unsigned int)__popcll(ge_const<3>(c, kstar));
+        rc += (unsigned int)__popcll(ge_const<3>(c, kstar)) + (unsigned int)__popcll(ge_const<3>(d, kstar));
     }
     return rc;
 }
@@ -404,45 +420,61 @@ __device__ __forceinline__ unsigned int sweep_upto7(const K3Params& p, const All
 // missing labels in the pheno file, n <= 7: a replicate sees n_r = n - j labelled leaves (j = its missing draws
 // among the allele's samples) and counts when k_r >= k*_j.  Bit-sliced k (cases) and j (missing), one pass per j.
 template <int NB>
+__device__ __forceinline__ uint64_t miss_word(const uint64_t (&c)[NB], const uint64_t (&u)[NB], int n, uint32_t kpack) {
+    uint64_t acc = 0;
+    for (int j = 0; j <= n; j++) {                       // warp-uniform
+        const int kj = (int)((kpack >> (4 * j)) & 15u);  // k* for n_r = n - j
+        uint64_t eq = ~0ull;                             // (missing count == j)
+#pragma unroll
+        for (int b = 0; b < NB; b++) eq &= ((j >> b) & 1) ? u[b] : ~u[b];
+        const uint64_t ge = (kj <= 0) ? ~0ull : (kj > n - j ? 0ull : ge_const<NB>(c, kj));
+        acc |= eq & ge;
+    }
+    return acc;
+}
+
+template <int NB>
 __device__ __forceinline__ unsigned int sweep_miss(const K3Params& p, const AlleleMeta& m, int lane, int words) {
     constexpr int NMAX = (1 << NB) - 1;
     const int n = m.n;
     const uint32_t kpack = m.kpack;
-    const uint64_t* __restrict__ rc_[NMAX];
-    const uint64_t* __restrict__ rm_[NMAX];
+    const ulonglong2* __restrict__ rc_[NMAX];
+    const ulonglong2* __restrict__ rm_[NMAX];
 #pragma unroll
     for (int e = 0; e < NMAX; e++) {
-        const int64_t o = (int64_t)((e < n) ? __ldg(p.csr + m.off + e) : 0) * p.Rw + lane;
-        rc_[e] = p.Xc + o; rm_[e] = p.Xm + o;
+        const int64_t o = (int64_t)((e < n) ? __ldg(p.csr + m.off + e) : 0) * p.Rw;
+        rc_[e] = reinterpret_cast<const ulonglong2*>(p.Xc + o) + lane; rm_[e] = reinterpret_cast<const ulonglong2*>(p.Xm + o) + lane;
     }
     const int tail = (int)(p.n_reps & 63);
+    const int pairs = (words + 1) >> 1;
     unsigned int rc = 0;
-#pragma unroll 2
-    for (int w = lane, off = 0; w < words; w += 32, off += 32) {
-        uint64_t c[NB], u[NB];
+#pragma unroll 1
+    for (int q = lane, off = 0; q < pairs; q += 32, off += 32) {
+        uint64_t c0[NB], u0[NB], c1[NB], u1[NB];
 #pragma unroll
-        for (int j = 0; j < NB; j++) { c[j] = 0; u[j] = 0; }
+        for (int j = 0; j < NB; j++) { c0[j] = 0; u0[j] = 0; c1[j] = 0; u1[j] = 0; }
 #pragma unroll
         for (int e = 0; e < NMAX; e++) {
             if (e < n) {
-                uint64_t x = __ldg(rc_[e] + off), y = __ldg(rm_[e] + off);
+                const ulonglong2 xv = ldg_pair(rc_[e] + off), yv = ldg_pair(rm_[e] + off);
+                uint64_t x = xv.x, y = yv.x;
 #pragma unroll
-                for (int j = 0; j < NB; j++) { const uint64_t t = c[j] & x; c[j] ^= x; x = t; }
+                for (int j = 0; j < NB; j++) { const uint64_t t = c0[j] & x; c0[j] ^= x; x = t; }
 #pragma unroll
-                for (int j = 0; j < NB; j++) { const uint64_t t = u[j] & y; u[j] ^= y; y = t; }
+                for (int j = 0; j < NB; j++) { const uint64_t t = u0[j] & y; u0[j] ^= y; y = t; }
+                x = xv.y; y = yv.y;
+#pragma unroll
+                for (int j = 0; j < NB; j++) { const uint64_t t = c1[j] & x; c1[j] ^= x; x = t; }
+#pragma unroll
+                for (int j = 0; j < NB; j++) { const uint64_t t = u1[j] & y; u1[j] ^= y; y = t; }
             }
         }
-        uint64_t acc = 0;
-        for (int j = 0; j <= n; j++) {                       // warp-uniform
-            const int kj = (int)((kpack >> (4 * j)) & 15u);  // k* for n_r = n - j
-            uint64_t eq = ~0ull;                             // (missing count == j)
-#pragma unroll
-            for (int b = 0; b < NB; b++) eq &= ((j >> b) & 1) ? u[b] : ~u[b];
-            const uint64_t ge = (kj <= 0) ? ~0ull : (kj > n - j ? 0ull : ge_const<NB>(c, kj));
-            acc |= eq & ge;
-        }
-        if (w == words - 1 && tail) acc &= (1ull << tail) - 1;   // padding replicates of the last word
-        rc += (unsigned int)__popcll(acc);
+        // padding replicates (k = 0, no missing draw) would count wherever k*_0 <= 0: mask the last word's tail and the word behind it
+        const int w0 = 2 * q, w1 = 2 * q + 1;
+        uint64_t a0 = miss_word<NB>(c0, u0, n, kpack), a1 = miss_word<NB>(c1, u1, n, kpack);
+        if (w0 == words - 1 && tail) a0 &= (1ull << tail) - 1;
+        if (w1 >= words) a1 = 0; else if (w1 == words - 1 && tail) a1 &= (1ull << tail) - 1;
+        rc += (unsigned int)__popcll(a0) + (unsigned int)__popcll(a1);
     }
     return rc;
 }

@@ -210,6 +210,13 @@ RunResult run_homoplasy_counter(const Args& a, const std::string& out_path) {
         Buf& b = bufs[t & 1];
         const int64_t s0 = t * tile_sites, ns = std::min(tile_sites, S - s0);
         b.error.clear();
+        b.compact = 0;
+        if (a.compact_upload) {
+            // the usual alignment (every genotype a base, at most two bases per site): text -> compact format in one pass
+            const int rc = pb_fasta_pack_tile_biallelic(fa.h, node_of_record.data(), N, s0, ns, b.X.data(), tw, b.colmask.data(), a.threads);
+            if (rc < 0) { b.error = pb_fasta_last_error(); return; }
+            if (rc == 1) { b.compact = 1; b.all_valid = 1; return; }
+        }
         if (pb_fasta_pack_tile(fa.h, node_of_record.data(), s0, ns, b.B0.data(), b.B1.data(), b.V.data(), tw, a.threads) != 0) {
             b.error = pb_fasta_last_error();
             return;

@@ -288,6 +288,18 @@ class FastaFile:
         if rc != 0:
             raise ValueError(_lib.lib().pb_fasta_last_error().decode())
 
+    def pack_tile_biallelic(self, node_of_record, n_nodes, site_begin, n_sites_tile, X, colmask, n_threads=0):
+        """one pass from the text to the compact upload format (X plane + per-column site masks): True when the tile
+        qualifies (every genotype an upper-case ACGT, at most two bases per site), else False (outputs undefined)"""
+        nor = np.ascontiguousarray(node_of_record, dtype=np.int32)
+        assert X.dtype == np.uint64 and X.strides[1] == 8 and colmask.dtype == np.uint64 and colmask.flags.c_contiguous
+        assert colmask.size >= 4 * ((n_sites_tile + 63) // 64)
+        rc = _lib.lib().pb_fasta_pack_tile_biallelic(self._h, ptr(nor), int(n_nodes), int(site_begin), int(n_sites_tile), ptr(X),
+                                                     X.strides[0] // 8, ptr(colmask), int(n_threads))
+        if rc < 0:
+            raise ValueError(_lib.lib().pb_fasta_last_error().decode())
+        return rc == 1
+
 
 # -------------------------------------------------------------------------------------------------
 # result files (HC.java:2137-2210; Homoplasy_Events.toString 5574-5578; Binomial_Test_Stat.toString 5918-5922)
@@ -453,11 +465,19 @@ def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_
         bufs.append(arrs)
     starts = list(range(0, S, tile_sites))
     compacted = [None, None]
+    colmasks = [np.empty((tw, 4), dtype=np.uint64) for _ in range(2)]
+    n_direct = [0]
 
     def pack(k):
         s0 = starts[k]
         ns = min(tile_sites, S - s0)
         B0, B1, V, X = (a[0] for a in bufs[k & 1])
+        # the usual alignment (every genotype a base, two bases per site) goes from the text straight to the compact format
+        if compact_upload and fa.pack_tile_biallelic(node_of_record, tree.n_nodes, s0, ns, X, colmasks[k & 1], pack_threads):
+            nw = (ns + 63) // 64
+            compacted[k & 1] = (X[:, :nw], colmasks[k & 1][:nw], True)
+            n_direct[0] += 1
+            return
         fa.pack_tile(node_of_record, s0, ns, B0, B1, V, pack_threads)
         compacted[k & 1] = compact_planes(B0, B1, V, ns, X=X, n_threads=pack_threads) if compact_upload else None
 
@@ -493,7 +513,7 @@ def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_
                 f.write("%d\t%d\t%s\t%s\t%s\n" % (stats["segsite_id"][i], physical_pos[stats["site_index"][i]],
                                                   java_double_str(float(ep[i, 0])), java_double_str(float(ep[i, 1])), java_double_str(float(fp[i]))))
     result = dict(counts=counts, n_informative=len(stats), n_sites=S, n_nodes=tree.n_nodes, n_samples=len(label),
-                  n_tiles=len(starts), n_compact_tiles=n_compact_tiles)
+                  n_tiles=len(starts), n_compact_tiles=n_compact_tiles, n_direct_tiles=n_direct[0])
     fa.close()
     hc.close()
     for arrs in bufs:

@@ -133,6 +133,80 @@ def test_compact_planes_rejects_third_base():
     assert c is not None and c[2] is False
 
 
+# ---- one pass from characters / FASTA text to the compact upload format ------------------------------------------------------
+def test_pack_chars_biallelic_property_random_alignments():
+    """random small alignments over a nasty alphabet: the one-pass packer qualifies a matrix exactly when every character is an
+    upper-case ACGT and no site carries three of them; X / colmask then expand to the planes pack_chars gives"""
+    rng = np.random.default_rng(7)
+    valid = np.frombuffer(b"ACGT", np.uint8)
+    n_ok = n_bad = 0
+    for trial in range(400):
+        N = int(rng.integers(1, 12))
+        S = int(rng.integers(1, 300))
+        k = int(rng.integers(1, 4))
+        chars = np.empty((N, S), dtype=np.uint8)
+        for s_ in range(S):
+            pool = rng.choice(valid, size=min(k, 1 + int(rng.integers(0, 3))), replace=False)
+            chars[:, s_] = rng.choice(pool, size=N)
+        if rng.random() < 0.3:
+            chars[int(rng.integers(0, N)), int(rng.integers(0, S))] = rng.choice(np.frombuffer(b"Nn-acgtRY", np.uint8))
+        want_ok = bool(np.isin(chars, valid).all()) and max(len(set(chars[:, s_].tolist())) for s_ in range(S)) <= 2
+        c = pb.pack_chars_biallelic(chars, n_threads=int(rng.integers(0, 3)))
+        assert (c is not None) == want_ok, trial
+        if c is None:
+            n_bad += 1
+            continue
+        n_ok += 1
+        X, colmask = c
+        B0, B1, V = pb.pack_chars(chars)
+        e0, e1 = _expand(X, colmask)
+        np.testing.assert_array_equal(e0 & V, B0)
+        np.testing.assert_array_equal(e1 & V, B1)
+        np.testing.assert_array_equal(X & ~V, np.zeros_like(X))        # padding bits of the last word stay clear
+    assert n_ok > 80 and n_bad > 80
+
+
+@pytest.mark.parametrize("line_width,eol,S,tile", [(0, "\n", 64 * 9 + 17, 256), (60, "\r\n", 64 * 7, 192), (61, "\n", 1000, 1024), (0, "\r", 130, 64)])
+def test_fasta_pack_tile_biallelic_matches_three_plane_path(tmp_path, line_width, eol, S, tile):
+    t = synth.yule_tree(70, 3)
+    chars = synth.planes_to_chars(*synth.simulate_planes(t, S, 4), 0, S)
+    sn, lab = synth.simulate_phenotypes(t, 5)
+    paths = synth.write_inputs(str(tmp_path), t, chars, sn, lab, line_width=line_width, eol=eol)
+    inp = hostio.load_inputs(paths["fasta"], paths["tree"], paths["pheno"], paths["map"])
+    fa, nor, N = inp["fasta"], inp["node_of_record"], inp["tree"].n_nodes
+    for s0 in range(0, S, tile):
+        ns = min(tile, S - s0)
+        W = (ns + 63) // 64
+        B0, B1, V = (np.zeros((N, W), dtype=np.uint64) for _ in range(3))
+        fa.pack_tile(nor, s0, ns, B0, B1, V)
+        X = np.full((N, W + 3), 0xDEADBEEF, dtype=np.uint64)[:, :W]     # a pitched destination
+        cm = np.empty((W, 4), dtype=np.uint64)
+        assert fa.pack_tile_biallelic(nor, N, s0, ns, X, cm, n_threads=3)
+        e0, e1 = _expand(X, cm)
+        np.testing.assert_array_equal(e0 & V, B0)
+        np.testing.assert_array_equal(e1 & V, B1)
+        np.testing.assert_array_equal(X & ~V, np.zeros_like(X))
+    # a lower-case call, a third base, an unmapped node: the tile does not qualify (the three-plane path takes it)
+    W = (S + 63) // 64
+    X = np.zeros((N, W), dtype=np.uint64)
+    cm = np.empty((W, 4), dtype=np.uint64)
+    nor2 = np.array(nor).copy()
+    nor2[3] = -1
+    assert not fa.pack_tile_biallelic(nor2, N, 0, S, X, cm)
+    fa.close()
+    for edit in ("n", None):
+        ch2 = chars.copy()
+        col = ch2[:, 77]
+        ch2[11, 77] = ord(edit) if edit else [b for b in b"ACGT" if b not in set(col.tolist())][0]
+        d2 = tmp_path / ("e_%s" % edit)
+        d2.mkdir()
+        p2 = synth.write_inputs(str(d2), t, ch2, sn, lab, line_width=line_width, eol=eol)
+        inp2 = hostio.load_inputs(p2["fasta"], p2["tree"], p2["pheno"], p2["map"])
+        assert not inp2["fasta"].pack_tile_biallelic(inp2["node_of_record"], N, 0, S, X, cm)
+        assert inp2["fasta"].pack_tile_biallelic(inp2["node_of_record"], N, 128, min(64, S - 128), X, cm)     # other tiles still qualify
+        inp2["fasta"].close()
+
+
 # ---- pheno / map ---------------------------------------------------------------------------------------------
 def test_pheno_and_map_readers(tmp_path):
     p = tmp_path / "ph.tsv"

@@ -2,7 +2,8 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench/l2_peak tools/microbench/l2_peak.cu && tools/microbench/l2_peak
 // Every block streams a buffer that fits the L2 (default 48 MB, well inside the 126 MB) over and over with coalesced loads —
 // 8 B per lane (256 B per warp instruction: K3b's access shape) and 16 B per lane — with enough loads in flight per thread
-// to cover the latency.  Prints one JSON line; bytes = what the SMs requested (all of it is served by the L2 after pass 1).
+// to cover the latency.  Loads are ld.global.cg (cached in L2 only): an L1 hit would not be L2 bandwidth.  Prints one JSON
+// line; bytes = what the SMs requested (all of it is served by the L2 after pass 1).
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -17,11 +18,11 @@ __global__ void __launch_bounds__(256) l2_read_kernel(const unsigned long long* 
         for (; i + VEC <= n_words; i += stride) {
             if (VEC == 1) {
                 unsigned long long v;
-                asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(buf + i));
+                asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(buf + i));
                 acc ^= v;
             } else {
                 unsigned long long a, b;
-                asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(buf + i));
+                asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(buf + i));
                 acc ^= a ^ b;
             }
         }
