@@ -176,7 +176,8 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 bit planes / int32 counts / f64 p-values", "data": "synthetic",
             # the b200 arm's config at this N (the workload named is the same; `sample` says what the CPU actually ran)
-            "config": bench_config(args, cfg, S, m, tree, max(int(args.gpus), 1)),
+            "config": dict(bench_config(args, cfg, S, m, tree, max(int(args.gpus), 1)), sites_measured=n,
+                           note="the CPU arm runs a %d-site slice of the workload named here, at the full m (see cpu_baseline.sample)" % n),
             "cpu_baseline": {"value": value, "unit": "sites/s", "cores": threads, "kind": "port", "sample": sample,
                              "seconds_events": l4 / args.steps, "seconds_assoc": l5 / args.steps},
             "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,21 +186,50 @@ def run_reference(args):
     return 0
 
 
-def bench_config(args, cfg, S, m, tree, world):
+def bench_config(args, cfg, S, m, tree, world, scaling="weak", launch="one process per GPU"):
     return {"workload": "%s: %d-leaf Yule tree (%d nodes) x %d biallelic sites per GPU, binary phenotype (38%% cases), "
                         "m=%d null replicates, Philox mode" % (args.config, tree.n_leaves, tree.n_nodes, S, m),
-            "baseline_config": "configs[1]" if args.config == "C2" else args.config,
+            "baseline_config": {"C2": "configs[1]", "C3": "configs[2]", "C1": "configs[0]", "C4": "configs[3]", "C5": "configs[4]"}[args.config],
             "sites_per_gpu": S, "sites_total": S * world, "leaves": tree.n_leaves, "nodes": tree.n_nodes, "replicates": m,
-            "parallelism": "site-sharded x%d, all-reduce(min) of maxT[m]" % world if world > 1 else "single GPU",
+            "parallelism": ("site-sharded x%d (%s scaling, %s), min of maxT[m] over the shards" % (world, scaling, launch)) if world > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (bit planes per GPU: %.2f GB as one plane when every site is biallelic and every genotype "
                          "valid, %.2f GB as three planes otherwise; L2 is 126 MB)"
                          % (tree.n_nodes * ((S + 63) // 64) * 8 / 1e9, 3 * tree.n_nodes * ((S + 63) // 64) * 8 / 1e9)}
 
 
+def k3_rooflines(tm, parts, m, P, has_miss):
+    """The two resampling kernels against their own ceilings (ncu captures under profiles/r2_k3*):
+    K3a (label generator) is bound by the integer-multiply (fmaheavy) pipe — its ceiling is an instruction-issue one, the
+    fraction comes from the committed capture; K3b (replicate counting) is bound by L2 -> SM bandwidth: algorithmic bytes =
+    sum over swept alleles of n rows x m/8 bytes, against the L2 read bandwidth measured on this GPU
+    (tools/microbench/l2_peak -> profiles/r2_l2_peak.json)."""
+    def load(name):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)
+        except Exception:
+            return {}
+    l2 = load("r2_l2_peak.json")
+    ceil = load("k3_ceilings.json")
+    l2_peak = l2.get("l2_read_gbs_16B_per_lane")
+    swept_bytes = float(tm.get("n_swept_rows", 0)) * (m / 8.0) * (2 if has_miss else 1)
+    out = {"k3a_label_generator": {"bound": "integer-multiply pipe (fmaheavy): Philox4x32-10 + Lemire draws",
+                                   "draws_per_s": (m * P) / (parts["ms_gen_kernel"] / 1e3) if parts.get("ms_gen_kernel") else None,
+                                   "ms": parts.get("ms_gen_kernel"),
+                                   "frac": ceil.get("k3_gen_kernel", {}).get("fmaheavy_pipe_frac"),
+                                   "frac_source": "ncu sm__pipe_fmaheavy_cycles_active (profiles/r2_k3a_gen_C2_ncu.txt)"},
+           "k3b_replicate_count": {"bound": "l2", "unit": "GB/s", "algorithmic_bytes": swept_bytes, "ms": parts.get("ms_null_count"),
+                                   "achieved": swept_bytes / (parts["ms_null_count"] / 1e3) / 1e9 if parts.get("ms_null_count") else None,
+                                   "peak": l2_peak, "peak_source": "measured: tools/microbench/l2_peak (L2-resident stream, 16 B per lane, L1 bypassed)"}}
+    k = out["k3b_replicate_count"]
+    k["frac"] = (k["achieved"] / k["peak"]) if (k["achieved"] and k["peak"]) else None
+    return out
+
+
 def run_b200(args):
     import torch
     import poutine_b200 as pb
-    from poutine_b200 import _lib, synth
+    from poutine_b200 import _lib, shard as shardmod, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,6 +238,9 @@ def run_b200(args):
         pb.build()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU port)")
+    inproc = args.inproc and world == 1 and args.gpus > 1     # one process, one host thread, pb_group over args.gpus devices
+    n_shards = args.gpus if inproc else 1                     # shards this process holds
+    n_gpus = args.gpus if inproc else world                   # GPUs of the whole job
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -234,49 +267,126 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    cfg, S, m, tree, sn, lab = workload(args, rank, world)
-    W = (S + 63) // 64
+    cfg, S_cfg, m, tree, sn, lab = workload(args, rank, world)
+    strong = args.scaling == "strong" and n_gpus > 1
     N = tree.n_nodes
+    # sites: weak = S_cfg per GPU; strong = S_cfg over the whole job, contiguous 64-site-word shards
+    if strong:
+        ranges = [shardmod.site_range(S_cfg, g, n_gpus) for g in range(n_gpus)]
+    else:
+        W1 = (S_cfg + 63) // 64
+        ranges = [(g * W1 * 64, g * W1 * 64 + S_cfg) for g in range(n_gpus)]
+    my = list(range(n_gpus)) if inproc else [rank]
+    S_total = sum(b - a for a, b in ranges)
+    S_mine = sum(ranges[g][1] - ranges[g][0] for g in my)
     t_gen = time.perf_counter()
-    B0, B1, V = synth.simulate_planes(tree, S, cfg["seed"] + 2000 + 7919 * (rank + 1), leaf_gap=cfg.get("leaf_gap", False),
-                                      multiallelic_frac=cfg.get("multiallelic_frac", 0.0),
-                                      third_allele_internal_frac=cfg.get("third_allele_internal_frac", 0.0))
-    # pinned staging copies: the e2e leg uploads from these every step
+    t_compact = 0.0
+    shards = []          # per shard of this process: dict(word_begin, S, W, Wp, planes (B0,B1,V views) or None, compact (X, colmask, all_valid) or None)
     pinned = []
-    host_planes = []
-    Wp = (W + 15) & ~15                                   # the library's device row pitch: lets pb_put_planes do flat copies
-    for a in (B0, B1, V):
-        h, p = _lib.pinned_empty((N, Wp), np.uint64)
-        h[:, :W] = a
-        h[:, W:] = 0
-        pinned.append(p)
-        host_planes.append(h[:, :W])
-    cpu_chars = synth.planes_to_chars(B0, B1, V, 0, min(CPU_SAMPLE_SITES, S)) if rank == 0 and world == 1 else None
-    del B0, B1, V
-    # compact form of the same input (one plane + per-column site masks) when every site has at most two bases:
-    # prepared once on the host, like the planes themselves; the e2e leg then uploads a third of the bytes
-    hX, pX = _lib.pinned_empty((N, Wp), np.uint64)
-    hX[:, W:] = 0
-    pinned.append(pX)
-    t_c = time.perf_counter()
-    compact = None if args.full_planes_only else pb.compact_planes(*host_planes, S, X=hX)
-    t_compact = time.perf_counter() - t_c
+    cpu_chars = None
+    for i, g in enumerate(my):
+        s0, s1 = ranges[g]
+        Sg = s1 - s0
+        W = (Sg + 63) // 64
+        Wp = (W + 15) & ~15                                  # the library's device row pitch: lets pb_put_planes do flat copies
+        if inproc and not strong and i > 0:
+            shards.append(dict(shards[0], word_begin=s0 // 64))   # weak scaling in one process: every shard uploads the same 1M-site block
+            continue
+        B0, B1, V = synth.simulate_planes(tree, Sg, cfg["seed"] + 2000 + 7919 * (g + 1), leaf_gap=cfg.get("leaf_gap", False),
+                                          multiallelic_frac=cfg.get("multiallelic_frac", 0.0),
+                                          third_allele_internal_frac=cfg.get("third_allele_internal_frac", 0.0))
+        if rank == 0 and g == 0 and n_gpus == 1:
+            cpu_chars = synth.planes_to_chars(B0, B1, V, 0, min(CPU_SAMPLE_SITES, Sg))
+        sh = dict(word_begin=s0 // 64, S=Sg, W=W, Wp=Wp, planes=None, compact=None)
+        keep_planes = n_shards == 1 and not strong           # the three-plane comparison legs run on one shard per process only
+        hp = []
+        if keep_planes or args.full_planes_only:
+            for a in (B0, B1, V):
+                h, p = _lib.pinned_empty((N, Wp), np.uint64)
+                h[:, :W] = a
+                h[:, W:] = 0
+                pinned.append(p)
+                hp.append(h[:, :W])
+            sh["planes"] = hp
+        if not args.full_planes_only:
+            hX, pX = _lib.pinned_empty((N, Wp), np.uint64)
+            hX[:, W:] = 0
+            pinned.append(pX)
+            t_c = time.perf_counter()
+            c = pb.compact_planes(B0, B1, V, Sg, X=hX)
+            t_compact += time.perf_counter() - t_c
+            if c is not None and not c[2]:                   # some genotype is not a base: the V plane goes up too
+                if not hp:
+                    hV, pV = _lib.pinned_empty((N, Wp), np.uint64)
+                    hV[:, :W] = V
+                    hV[:, W:] = 0
+                    pinned.append(pV)
+                    hp = [None, None, hV[:, :W]]
+                    sh["planes_v_only"] = hp
+            sh["compact"] = c
+            if c is None and not hp:                         # multi-allelic shard without kept planes: keep them after all
+                for a in (B0, B1, V):
+                    h, p = _lib.pinned_empty((N, Wp), np.uint64)
+                    h[:, :W] = a
+                    h[:, W:] = 0
+                    pinned.append(p)
+                    hp.append(h[:, :W])
+                sh["planes"] = hp
+        del B0, B1, V
+        shards.append(sh)
     t_gen = time.perf_counter() - t_gen
+    all_compact = all(sh["compact"] is not None for sh in shards)
 
-    hc = pb.HomoplasyCounter(num_replicates=m, min_hcount=1, device=local_rank, seed=20260, site_offset=rank * (W * 64))
+    if inproc:
+        hc = pb.HomoplasyCounterGroup(list(range(n_gpus)), num_replicates=m, min_hcount=1, seed=20260)
+    else:
+        hc = pb.HomoplasyCounter(num_replicates=m, min_hcount=1, device=local_rank, seed=20260, site_offset=ranges[rank][0])
     hc.set_tree(tree.parent, tree.is_leaf)
     hc.set_phenos(sn, lab)
-    hc.set_sites(S)
-    if world > 1:
-        ids = [pb.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        hc.comm_init(ids[0], rank, world)
+    hc.set_sites(S_mine)
+    exchange = "none (one GPU)"
+    if inproc:
+        exchange = "peer memory, fused into K4's sort kernel (pb_group, one process)"
+    elif world > 1:
+        want = os.environ.get("PB_BENCH_EXCHANGE", "p2p")
+        ok = 0
+        if want == "p2p":
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, hc.comm_export())
+                hc.comm_connect(handles, rank, world)
+                ok = 1
+            except pb.PoutineError as e:
+                print("bench.py: rank %d: peer-memory exchange unavailable (%s), falling back to NCCL" % (rank, e), file=sys.stderr)
+        t = torch.tensor([float(ok)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if t.item() >= 1:
+            exchange = "peer memory (cudaIpc), fused into K4's sort kernel"
+        else:
+            ids = [pb.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            hc.comm_init(ids[0], rank, world)
+            exchange = "NCCL all-reduce(min, uint64) on the stream"
+
+    base_word = 0 if inproc else 0       # a single context takes shard-local word coordinates
+    TILE = int(args.upload_tile_words)
 
     def upload(use_compact=True):
-        if use_compact and compact is not None:          # one plane (+ V if some genotype is not a base) + per-column site masks
-            hc.put_planes_biallelic(compact[0], None if compact[2] else host_planes[2], compact[1])
-        else:
-            hc.put_planes(*host_planes)
+        """H2D of every shard this process holds.  Compact shards go up in column tiles cut at the sweep's block width,
+        asynchronously: all GPUs' copy engines run at once, and (one-plane mode) each tile is swept underneath the next
+        tile's copy while the label generator runs under the whole upload."""
+        for sh in shards:
+            wb = sh["word_begin"] if inproc else 0
+            c = sh["compact"] if use_compact else None
+            if c is not None:
+                Xs, cm, all_valid = c
+                Vs = None if all_valid else (sh.get("planes") or sh.get("planes_v_only"))[2]
+                for w0 in range(0, sh["W"], TILE):
+                    w1 = min(sh["W"], w0 + TILE)
+                    hc.put_planes_biallelic(Xs[:, w0:w1], None if Vs is None else Vs[:, w0:w1], cm[w0:w1], wb + w0, asynchronous=True)
+            else:
+                hc.put_planes(*sh["planes"], wb, asynchronous=True)
+        hc.upload_sync()
 
     upload()          # biallelic input with every genotype valid stays ONE plane in HBM (k1x_events_kernel), else three
 
@@ -309,8 +419,9 @@ def run_b200(args):
     except Exception:
         gpu_id = str(local_rank)
     sampler = ClockSampler(gpu_id) if rank == 0 else None
-    total_sites = S * world
+    total_sites = S_total
     peak, peak_src = measured_hbm_peak()
+    has_miss = bool((np.asarray(lab) == 2).any())
 
     def timed_resident():
         """K timed steps with the planes resident in HBM -> (device ms, wall ms, launches, per-part ms, roofline of the sweep kernel)"""
@@ -323,33 +434,37 @@ def run_b200(args):
             k1_ms.append(tm["ms_events_kernel"])
             launches += int(tm["n_launches"])
             for k in ("ms_events_kernel", "ms_events_total", "ms_tally", "ms_ptable", "ms_null_gen", "ms_null_count",
-                      "ms_null_fallback", "ms_allreduce", "ms_pvalues", "ms_assoc_total"):
-                parts[k] = parts.get(k, 0.0) + tm[k] / args.steps
+                      "ms_null_fallback", "ms_allreduce", "ms_pvalues", "ms_assoc_total", "ms_gen_kernel"):
+                parts[k] = parts.get(k, 0.0) + tm.get(k, 0.0) / args.steps
         dev_ms = hc.stopwatch_stop_ms()
         barrier()
         wall_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
         dev_ms = max_over_ranks(dev_ms)
-        # roofline of the HBM-bound counting sweep: algorithmic bytes / mean launch time, both live
+        # roofline of the HBM-bound counting sweep: algorithmic bytes / mean launch time, both live.
+        # (a group reports the slowest shard's time and the summed bytes: divide by the shard count for the per-GPU figure)
         kernel = "k1x_events_kernel" if tm["plane_mode"] == _lib.PB_PLANES_X else "k1_events_kernel"
         k1_avg = float(np.mean(k1_ms))
-        alg_bytes = int(tm["k1_algorithmic_bytes"])
+        alg_bytes = int(tm["k1_algorithmic_bytes"]) // n_shards
         achieved = alg_bytes / (k1_avg / 1e3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
                 tj = json.load(f).get(kernel, {})
-                if tj.get("sites") == S and tj.get("nodes") == N:
+                if tj.get("sites") == shards[0]["S"] and tj.get("nodes") == N:
                     traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
         roofline = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k1_avg, "peak_source": peak_src,
                     "frac_of_nominal_8TBps": achieved / 8000.0,
+                    "algorithmic_bytes": "plane bits once (N*W*8 B per plane) + one record per (tree row, site word) holding an event; "
+                                         "the per-site output (32 B/site) belongs to the tail kernels, not to this launch",
                     "planes_in_hbm": 1 if kernel == "k1x_events_kernel" else 3}
         return dev_ms, wall_ms, launches, parts, roofline, tm
 
     dev_ms, wall_ms, launches, parts, roofline, tm = timed_resident()
     value = total_sites * args.steps / (dev_ms / 1e3)
+    roofline_k3 = k3_rooflines(tm, parts, m, len(lab), has_miss)
 
     # ---- timed: end to end through the public API with host buffers ------------------------------------
     for _ in range(min(args.warmup, 3)):
@@ -367,13 +482,15 @@ def run_b200(args):
     par_outputs = [("headline", np.array(ev[:CPU_SAMPLE_SITES]), np.array(st))]
     e2e_breakdown = {k: v / args.steps for k, v in e2e_parts.items()}
     e2e_step_ms = list(e2e_steps)
-    h2d_full = 3 * N * Wp * 8                             # what pb_put_planes copies (rows padded to the device pitch)
+    eager_words = int(tm_e.get("eager_words", 0))
+    h2d_full = sum(3 * N * sh["Wp"] * 8 for sh in shards)     # what pb_put_planes copies (rows padded to the device pitch)
     h2d = h2d_full
     e2e_full = None
     three_planes = None
-    if compact is not None:
+    if all_compact:
+        h2d = sum((1 if sh["compact"][2] else 2) * N * sh["W"] * 8 + sh["W"] * 32 for sh in shards)
+    if all_compact and all(sh["planes"] is not None for sh in shards):
         # the same end-to-end step with the plain three-plane upload, reported next to the headline
-        h2d = (1 if compact[2] else 2) * N * Wp * 8 + W * 32
         step_e2e(False)
         barrier()
         t0 = time.perf_counter()
@@ -393,13 +510,14 @@ def run_b200(args):
                         "roofline": f_roof, "breakdown_ms": f_parts, "e2e": e2e_full,
                         "note": "same workload held as three full planes (what gap-carrying or multi-allelic input uses)"}
     clocks = sampler.stop() if sampler else None      # sampled over all timed regions (resident + end to end)
-    d2h = S * _lib.SITE_DTYPE.itemsize + len(st) * _lib.STAT_DTYPE.itemsize + m * 8
+    d2h = S_mine * _lib.SITE_DTYPE.itemsize + len(st) * _lib.STAT_DTYPE.itemsize + m * 8
     e2e_value = total_sites * args.steps / (e2e_ms / 1e3)
     n_draws = sum_over_ranks(tm["n_alleles_in_use"]) * m
 
     cpu_baseline = None
+    host_packer = None
     parity = {"parity_checked": False, "parity_sites": 0}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         threads = host_cores()
         ref = {}
         v, l4, l5 = cpu_reference_pass(tree, cpu_chars, sn, lab, m, 20260, threads, keep=ref)
@@ -417,24 +535,45 @@ def run_b200(args):
         if bad:
             print("bench.py: PARITY FAILURE against the CPU port on the first %d sites: %s" % (n_par, bad), file=sys.stderr)
             sys.exit(3)
+        # the host packer that feeds the compact upload, measured on the same character slice: chars -> (X, site masks) in one pass
+        t_p = time.perf_counter()
+        for _ in range(3):
+            pk = pb.pack_chars_biallelic(cpu_chars)
+        t_p = (time.perf_counter() - t_p) / 3
+        host_packer = {"one_pass": True, "qualifies": pk is not None, "chars_per_s": cpu_chars.size / t_p, "threads": threads,
+                       "sample": "%d nodes x %d sites of this workload as characters (the Fasta_Record text the Java host holds)" % cpu_chars.shape,
+                       "seconds_for_this_workload_at_this_rate": N * S_cfg / (cpu_chars.size / t_p),
+                       "note": "pb_pack_chars_biallelic / pb_fasta_pack_tile_biallelic emit the compact upload format directly: no three-plane "
+                               "intermediate and no compaction pass exist on the host path; packing is tile-pipelined with the upload by the hosts"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        launch = "one process, one host thread (pb_group)" if inproc else "one process per GPU (torchrun)"
+        line = {"metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": "u64 bit planes / int32 counts / f64 p-values", "data": "synthetic",
-                "config": bench_config(args, cfg, S, m, tree, world),
+                "config": bench_config(args, cfg, shards[0]["S"], m, tree, n_gpus, "strong" if strong else "weak", launch),
                 "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps,
-                        "breakdown_ms": e2e_breakdown, "ms_steps_rank0": e2e_step_ms, "timer": "host wall clock around synchronous C-ABI calls, max over ranks",
-                        "upload": ("pb_put_planes_biallelic (%s; host-side compaction %.2f s once, outside the timed region like "
-                                   "the FASTA packing)" % ("X plane + site masks, kept as one plane in HBM" if compact[2] else
-                                                           "X + V planes + site masks, expanded to three planes on the device", t_compact))
-                                  if compact is not None else "pb_put_planes (three planes)",
+                        "breakdown_ms": e2e_breakdown, "ms_steps_rank0": e2e_step_ms, "timer": "host wall clock around the C-ABI calls, max over ranks",
+                        "upload": ("pb_put_planes_biallelic_async in %d-word column tiles + pb_upload_sync (%s)" %
+                                   (TILE, "X plane + site masks, kept as one plane in HBM" if shards[0]["compact"][2] else
+                                    "X + V planes + site masks, expanded to three planes on the device"))
+                                  if all_compact else "pb_put_planes_async (three planes)",
+                        "swept_under_upload_words": eager_words,
+                        "compaction_in_timed_region": False,
+                        "input_format": "the compact format the one-pass host packer emits (see host_packer); the synthetic generator produces "
+                                        "planes, so here it is derived from them once at set-up (%.2f s), outside the timed region like "
+                                        "the FASTA packing" % t_compact if all_compact else "three planes",
                         },
+                "e2e_from_three_planes": e2e_full,
                 "three_planes": three_planes,
                 "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+                "roofline": roofline, "roofline_k3": roofline_k3, "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "parity_checked": parity["parity_checked"], "parity_sites": parity["parity_sites"], "parity": parity,
+                "host_packer": host_packer,
+                "exchange": exchange,
+                "memoised": "the binomial table f[n][k] (a pure function of n_max and the case fraction) is kept across passes, as the "
+                            "reference's own cache does within a run (HC.java:4196-4280); everything else is recomputed every step",
                 "replicate_draws_per_sec": n_draws * args.steps / (dev_ms / 1e3),
                 "wall_ms_per_step": wall_ms / args.steps,
                 "breakdown_ms": parts,
@@ -443,6 +582,8 @@ def run_b200(args):
                            "maxt_fallback_reps": int(tm["n_maxt_fallback_reps"])},
                 "synth_seconds": t_gen}
         print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()        # no rank frees its exchange block while a peer may still be reading it
     hc.close()
     for p in pinned:
         _lib.pinned_free(p)
@@ -463,7 +604,13 @@ def main():
     ap.add_argument("--replicates", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-planes-only", action="store_true", help="e2e leg uploads three planes even when the input is biallelic")
+    ap.add_argument("--inproc", action="store_true", help="--gpus N from ONE process / one host thread (pb_group) instead of torchrun ranks")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="weak: the config's sites per GPU (default); strong: the config's sites over all GPUs (default for C3)")
+    ap.add_argument("--upload-tile-words", type=int, default=2048, help="column tile of the end-to-end upload (multiple of 256 site words)")
     args = ap.parse_args()
+    if args.scaling is None:
+        args.scaling = "strong" if args.config == "C3" else "weak"
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)
     sys.exit(run_reference(args) if args.impl == "reference" else run_b200(args))

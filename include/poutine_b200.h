@@ -110,12 +110,17 @@ typedef struct {
     float ms_pvalues;         /* K4: sort maxT + pointwise/familywise */
     float ms_assoc_total;
     int64_t n_launches;       /* kernels launched by the last events+assoc pair */
-    int64_t k1_algorithmic_bytes;  /* planes*N*W*8 plane bytes (planes = 3, or 1 in compact mode) + 32 B/site + 8 B/raw event */
+    int64_t k1_algorithmic_bytes;  /* what the sweep kernel moves: planes*N*W*8 plane bytes (planes = 3, or 1 in one-plane mode)
+                                      + one record (32 B; one-plane mode 16 B) per (tree row, site word) holding an event */
     int64_t n_informative, n_alleles_in_use, n_extant_events;  /* S_inf, A, E of SURVEY §8 */
     int64_t n_fast_alleles;   /* alleles handled by the bit-sliced threshold path */
     int64_t n_maxt_fallback_reps;
     int64_t plane_mode;       /* how the alignment was held in HBM for the last pb_run_events: 1 = one plane X + site masks
                                  (every tile compact, all genotypes valid; k1x_events_kernel), 2 = three planes (k1_events_kernel) */
+    int64_t eager_words;      /* site words whose sweep ran ahead of pb_run_events, underneath the uploads (0: none) */
+    int64_t n_swept_rows;     /* K3b: label-matrix rows read per replicate word, summed over the swept alleles (x m/8 B = its L2 traffic) */
+    float ms_gen_kernel;      /* K3a: the label generator's own time for the first replicate tile (events on its stream) */
+    float reserved0;
 } pb_timings;
 
 int pb_create(const pb_config* cfg, pb_ctx** out);
@@ -154,6 +159,19 @@ int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_
  * pb_compact_planes (host helper below) derives X / colmask from full planes and says whether the tile qualifies. */
 int pb_put_planes_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
                             const uint64_t* X, const uint64_t* V, const uint64_t* colmask);
+
+/* Asynchronous uploads: as above, but the call returns once the copies are QUEUED; the host buffers must stay valid and
+ * unchanged until pb_upload_sync (or the next pb_run_events, which orders itself behind every queued upload but does not
+ * wait for the host's sake).  Lets one host thread keep several GPUs' copy engines busy at once (pb_group does this), or
+ * pack tile t+1 while tile t is in flight without a helper thread.
+ * One-plane tiles that arrive in column order and are cut at multiples of 256 site words (the sweep's block width; the
+ * last tile may be shorter) are swept right after they land, underneath the next tile's copy, and the label generator
+ * starts with the first tile when the labels are already set: pb_run_events then only runs the tail. */
+int pb_put_planes_async(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
+                        const uint64_t* B0, const uint64_t* B1, const uint64_t* V);
+int pb_put_planes_biallelic_async(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
+                                  const uint64_t* X, const uint64_t* V, const uint64_t* colmask);
+int pb_upload_sync(pb_ctx* ctx);
 
 /* count_all_homoplasy_events (HC.java:1402).  per_site (n_sites records) and counts may be NULL.
  * If pb_set_labels was called before (Philox mode), the label matrix of the first replicate tile is generated on a
@@ -229,6 +247,11 @@ int pb_group_put_planes(pb_group* g, int64_t word_begin, int64_t n_words, int64_
                         const uint64_t* B0, const uint64_t* B1, const uint64_t* V);
 int pb_group_put_planes_biallelic(pb_group* g, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
                                   const uint64_t* X, const uint64_t* V, const uint64_t* colmask);
+int pb_group_put_planes_async(pb_group* g, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
+                              const uint64_t* B0, const uint64_t* B1, const uint64_t* V);
+int pb_group_put_planes_biallelic_async(pb_group* g, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
+                                        const uint64_t* X, const uint64_t* V, const uint64_t* colmask);
+int pb_group_upload_sync(pb_group* g);
 int pb_group_run_events(pb_group* g, pb_site_out* per_site /* n_sites, may be NULL */, pb_class_counts* counts);
 int pb_group_run_assoc(pb_group* g, const uint32_t* replay_perms, pb_stat_out* per_inf_site, int64_t cap, int64_t* n_inf,
                        double* maxT_sorted);

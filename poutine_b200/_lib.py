@@ -45,7 +45,8 @@ class PbTimings(C.Structure):
                                          "ms_null_count", "ms_null_fallback", "ms_allreduce", "ms_pvalues",
                                          "ms_assoc_total")] + \
                [(n, C.c_int64) for n in ("n_launches", "k1_algorithmic_bytes", "n_informative", "n_alleles_in_use",
-                                         "n_extant_events", "n_fast_alleles", "n_maxt_fallback_reps", "plane_mode")]
+                                         "n_extant_events", "n_fast_alleles", "n_maxt_fallback_reps", "plane_mode", "eager_words", "n_swept_rows")] + \
+               [("ms_gen_kernel", C.c_float), ("reserved0", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -58,10 +59,11 @@ EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_set_tree", "pb_set_la
            "pb_pack_chars", "pb_host_alloc", "pb_host_free", "pb_version",
            "pb_fasta_open", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_record", "pb_fasta_pack_tile", "pb_fasta_last_error",
            "pb_comm_export", "pb_comm_connect", "pb_fasta_pack_tile_biallelic", "pb_pack_chars_biallelic",
+           "pb_put_planes_async", "pb_put_planes_biallelic_async", "pb_upload_sync",
            "pb_group_create", "pb_group_destroy", "pb_group_last_error", "pb_group_size", "pb_group_ctx", "pb_group_set_tree",
            "pb_group_set_labels", "pb_group_set_sites", "pb_group_shard_range", "pb_group_put_planes", "pb_group_put_planes_biallelic",
            "pb_group_run_events", "pb_group_run_assoc", "pb_group_run_extras", "pb_group_get_timings", "pb_group_stopwatch_mark",
-           "pb_group_stopwatch_ms"]
+           "pb_group_stopwatch_ms", "pb_group_put_planes_async", "pb_group_put_planes_biallelic_async", "pb_group_upload_sync"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -116,6 +118,9 @@ def lib():
         L.pb_fasta_last_error.argtypes = []; L.pb_fasta_last_error.restype = C.c_char_p
         L.pb_fasta_pack_tile_biallelic.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp, i32]
         L.pb_pack_chars_biallelic.argtypes = [vp, i64, i64, i64, vp, i64, vp, i32]
+        L.pb_put_planes_async.argtypes = [vp, i64, i64, i64, vp, vp, vp]
+        L.pb_put_planes_biallelic_async.argtypes = [vp, i64, i64, i64, vp, vp, vp]
+        L.pb_upload_sync.argtypes = [vp]
         L.pb_comm_export.argtypes = [vp, vp]
         L.pb_comm_connect.argtypes = [vp, vp, i32, i32]
         L.pb_group_create.argtypes = [C.POINTER(PbConfig), vp, i32, C.POINTER(vp)]
@@ -129,6 +134,9 @@ def lib():
         L.pb_group_shard_range.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64)]
         L.pb_group_put_planes.argtypes = [vp, i64, i64, i64, vp, vp, vp]
         L.pb_group_put_planes_biallelic.argtypes = [vp, i64, i64, i64, vp, vp, vp]
+        L.pb_group_put_planes_async.argtypes = [vp, i64, i64, i64, vp, vp, vp]
+        L.pb_group_put_planes_biallelic_async.argtypes = [vp, i64, i64, i64, vp, vp, vp]
+        L.pb_group_upload_sync.argtypes = [vp]
         L.pb_group_run_events.argtypes = [vp, vp, C.POINTER(PbClassCounts)]
         L.pb_group_run_assoc.argtypes = [vp, vp, vp, i64, C.POINTER(i64), vp]
         L.pb_group_run_extras.argtypes = [vp, vp, vp]

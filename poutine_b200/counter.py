@@ -172,16 +172,27 @@ class HomoplasyCounter:
         self._check(self._fn("set_sites")(self._h, int(n_sites)))
         self.n_sites = int(n_sites)
 
-    def put_planes(self, B0, B1, V, word_begin=0):
-        """Upload a column tile of the node-major planes (any row pitch)."""
+    def put_planes(self, B0, B1, V, word_begin=0, asynchronous=False):
+        """Upload a column tile of the node-major planes (any row pitch).  asynchronous=True: the copies are queued and the
+        arrays must stay alive and unchanged until upload_sync()."""
         for a in (B0, B1, V):
             assert a.dtype == np.uint64 and a.ndim == 2 and a.shape[0] == self.n_nodes and a.strides[1] == 8
         assert B0.strides == B1.strides == V.strides
-        self._check(self._fn("put_planes")(self._h, int(word_begin), B0.shape[1], B0.strides[0] // 8, ptr(B0), ptr(B1), ptr(V)))
+        fn = self._fn("put_planes_async" if asynchronous else "put_planes")
+        self._check(fn(self._h, int(word_begin), B0.shape[1], B0.strides[0] // 8, ptr(B0), ptr(B1), ptr(V)))
+        if asynchronous:
+            self._inflight = getattr(self, "_inflight", []) + [(B0, B1, V)]
 
-    def put_planes_biallelic(self, X, V, colmask, word_begin=0):
+    def upload_sync(self):
+        """wait until every asynchronous upload has left the host buffers"""
+        self._check(self._fn("upload_sync")(self._h))
+        self._inflight = []
+
+    def put_planes_biallelic(self, X, V, colmask, word_begin=0, asynchronous=False):
         """Compact upload of a column tile whose sites carry at most two bases (see compact_planes): X, optionally V
-        (None = every genotype valid) and the per-word-column site masks; expanded on the device."""
+        (None = every genotype valid) and the per-word-column site masks; expanded on the device.
+        One-plane tiles that arrive in column order, cut at multiples of 256 site words, are swept as they land
+        (timings()["eager_words"]).  asynchronous=True: see put_planes."""
         assert X.dtype == np.uint64 and X.ndim == 2 and X.shape[0] == self.n_nodes and X.strides[1] == 8
         if V is not None:
             assert V.dtype == np.uint64 and V.shape == X.shape
@@ -191,8 +202,10 @@ class HomoplasyCounter:
                 V = v2
         colmask = np.ascontiguousarray(colmask, dtype=np.uint64)
         assert colmask.shape == (X.shape[1], 4)
-        self._check(self._fn("put_planes_biallelic")(self._h, int(word_begin), X.shape[1], X.strides[0] // 8, ptr(X), ptr(V),
-                                                       ptr(colmask)))
+        fn = self._fn("put_planes_biallelic_async" if asynchronous else "put_planes_biallelic")
+        self._check(fn(self._h, int(word_begin), X.shape[1], X.strides[0] // 8, ptr(X), ptr(V), ptr(colmask)))
+        if asynchronous:
+            self._inflight = getattr(self, "_inflight", []) + [(X, V, colmask)]
 
     def set_planes(self, B0, B1, V, n_sites, tile_words=None, compact=False):
         """compact=True: every tile that qualifies goes up as one plane (put_planes_biallelic), the others as three."""

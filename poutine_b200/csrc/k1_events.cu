@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_K1_BLOCKS_PER_SM) k1_events_
 #define KX_SMEM_TOTAL (KX_SMEM_RING + KX_SMEM_QUEUE + KX_SMEM_BARS)
 
 struct KXParams {
+    int32_t col_block0;                   // first column block of this launch (tiles swept ahead of pb_run_events cover a sub-range)
     const uint32_t* __restrict__ ops;
     const int32_t* __restrict__ chunk_op;
     xrec_t* __restrict__ raw;
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(PB_K1_THREADS, PB_KX_BLOCKS_PER_SM) k1x_events
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y;
-    const int32_t col0 = (int32_t)blockIdx.x * PB_KX_COLS;
+    const int32_t col0 = ((int32_t)blockIdx.x + q.col_block0) * PB_KX_COLS;
     const int r0 = q.chunk_op[chunk], r1 = q.chunk_op[chunk + 1];
     const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(q.ops);
     const uint32_t ring0 = pin_u32(smem_u32(smem));
@@ -834,7 +835,7 @@ __global__ void k1_mask_last_word_kernel(uint64_t* __restrict__ V, int32_t N, in
 int pbk_mask_last_word(pb_ctx* ctx) {
     if (!(ctx->S & 63) || ctx->N == 0) return PB_OK;
     const uint64_t mask = (1ull << (ctx->S & 63)) - 1;
-    k1_mask_last_word_kernel<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_V, ctx->N, ctx->Wp, ctx->W - 1, mask);
+    k1_mask_last_word_kernel<<<(ctx->N + 255) / 256, 256, 0, ctx->upl>>>(ctx->d_V, ctx->N, ctx->Wp, ctx->W - 1, mask);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -864,7 +865,7 @@ int pbk_expand_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, const
     const uint64_t last_mask = (ctx->S & 63) ? (1ull << (ctx->S & 63)) - 1 : ~0ull;
     const unsigned gx = (unsigned)((n_words + 127) / 128);
     const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->N, ((int64_t)ctx->sm_count * 16 + gx - 1) / gx));
-    k1_expand_biallelic_kernel<<<dim3(gx, gy), 128, 0, ctx->stream>>>(ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->N, ctx->Wp, word_begin, n_words,
+    k1_expand_biallelic_kernel<<<dim3(gx, gy), 128, 0, ctx->upl>>>(ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->N, ctx->Wp, word_begin, n_words,
                                                                      d_colmask, fill_v ? 1 : 0, ctx->W - 1, last_mask);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -876,8 +877,8 @@ __global__ void k1x_mask_valid_kernel(uint64_t* __restrict__ xvalid, int64_t w_l
 int pbk_mask_last_word_x(pb_ctx* ctx) {
     if (!(ctx->S & 63) || ctx->N == 0) return PB_OK;
     const uint64_t mask = (1ull << (ctx->S & 63)) - 1;
-    k1_mask_last_word_kernel<<<(ctx->N + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_X, ctx->N, ctx->Wp, ctx->W - 1, mask);
-    k1x_mask_valid_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_xvalid, ctx->W - 1, mask);
+    k1_mask_last_word_kernel<<<(ctx->N + 255) / 256, 256, 0, ctx->upl>>>(ctx->d_X, ctx->N, ctx->Wp, ctx->W - 1, mask);
+    k1x_mask_valid_kernel<<<1, 1, 0, ctx->upl>>>(ctx->d_xvalid, ctx->W - 1, mask);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -900,14 +901,17 @@ __global__ void k1x_promote_kernel(const uint64_t* __restrict__ X, const uint64_
 int pbk_promote_planes(pb_ctx* ctx) {
     const unsigned gx = (unsigned)((ctx->W + 127) / 128);
     const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->N, ((int64_t)ctx->sm_count * 16 + gx - 1) / gx));
-    k1x_promote_kernel<<<dim3(gx, gy), 128, 0, ctx->stream>>>(ctx->d_X, ctx->d_xmask, ctx->d_xvalid, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->N,
+    k1x_promote_kernel<<<dim3(gx, gy), 128, 0, ctx->upl>>>(ctx->d_X, ctx->d_xmask, ctx->d_xvalid, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->N,
                                                              ctx->Wp, ctx->W);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
 
-static int pbk_events_x(pb_ctx* ctx) {
+// one-plane sweep of the column blocks [block0, block0 + n_blocks).  first: a new pass starts (record cursor reset, start
+// mark); last: the closing mark.  Tiles swept ahead of pb_run_events (eager_sweep in pb_api.cu) append to the same list.
+int pbk_events_range(pb_ctx* ctx, int64_t block0, int64_t n_blocks, bool first, bool last) {
     KXParams q;
+    q.col_block0 = (int32_t)block0;
     q.ops = ctx->d_ops_x; q.chunk_op = ctx->d_chunk_op_x;
     q.raw = reinterpret_cast<xrec_t*>(ctx->d_raw); q.raw_cursor = ctx->d_raw_cursor; q.raw_cap = (unsigned long long)ctx->raw_cap;
     const size_t smem = (size_t)KX_SMEM_TOTAL;
@@ -915,16 +919,21 @@ static int pbk_events_x(pb_ctx* ctx) {
         PB_CUDA(cudaFuncSetAttribute(k1x_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->k1x_attr_set = true;
     }
-    dim3 grid((unsigned)((ctx->W + PB_KX_COLS - 1) / PB_KX_COLS), (unsigned)ctx->n_chunks_x);
-    PB_CUDA(cudaMemsetAsync(ctx->d_raw_cursor, 0, 8, ctx->stream));
-    PB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    pb_trace_mark(ctx, "start");
-    k1x_events_kernel<<<grid, PB_K1_THREADS, smem, ctx->stream>>>(ctx->tmap_x, q);
-    pb_trace_mark(ctx, "k1x");
-    PB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    ctx->tm.n_launches += 1;
+    if (first) PB_CUDA(cudaMemsetAsync(ctx->d_raw_cursor, 0, 8, ctx->stream));
+    if (first || last) PB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));     // (a closing launch times itself only)
+    if (first) pb_trace_mark(ctx, "start");
+    if (n_blocks > 0) {
+        dim3 grid((unsigned)n_blocks, (unsigned)ctx->n_chunks_x);
+        k1x_events_kernel<<<grid, PB_K1_THREADS, smem, ctx->stream>>>(ctx->tmap_x, q);
+        ctx->tm.n_launches += 1;
+    }
+    if (last) { pb_trace_mark(ctx, "k1x"); PB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream)); }
     PB_CUDA(cudaGetLastError());
     return PB_OK;
+}
+
+static int pbk_events_x(pb_ctx* ctx) {
+    return pbk_events_range(ctx, 0, (ctx->W + PB_KX_COLS - 1) / PB_KX_COLS, true, true);
 }
 
 int pbk_events(pb_ctx* ctx) {

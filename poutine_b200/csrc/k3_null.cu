@@ -774,6 +774,8 @@ static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
 
 static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t nr, cudaStream_t st, int buf) {
     const unsigned gblocks = (unsigned)((nr + GEN_THREADS - 1) / GEN_THREADS);
+    const bool timed = base == 0;        // ms_gen_kernel: the generator's own time for the first tile (events on its stream)
+    if (timed) PB_CUDA(cudaEventRecord(ctx->ev_gen_t0, st));
     const int force_replay = getenv("PB_GEN_FORCE_REPLAY") ? 1 : 0;   // every group also goes through the exact Lemire path
     if (pl.has_miss)
         k3_gen_kernel<0, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr,
@@ -782,6 +784,7 @@ static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t
     else
         k3_gen_kernel<0, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr,
                                                                 (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words), nullptr, pl.Rw32, force_replay);
+    if (timed) { PB_CUDA(cudaEventRecord(ctx->ev_gen_t1, st)); ctx->gen_timed = true; }
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -790,7 +793,9 @@ static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t
 // Called by pb_run_events right after the K1 sweep is enqueued: the label matrix of the first replicate tile
 // depends only on the phenotype table and the seed, so it is generated on a second stream while the (small,
 // latency-bound) K1 tail, K2 and the p-table kernels run; pb_run_assoc picks it up through an event.
-int pbk_pregen_labels(pb_ctx* ctx) {
+// immediately: called while the alignment is still uploading (first tile of an in-order one-plane upload): nothing to wait
+// for and nothing to race against, the generator simply starts.
+int pbk_pregen_labels(pb_ctx* ctx, bool immediately) {
     ctx->pregen_valid = false;
     if (ctx->cfg.mode != PB_MODE_PHILOX || ctx->P == 0 || ctx->n_case + ctx->n_ctrl == 0) return PB_OK;
     if (getenv("PB_NO_PREGEN")) return PB_OK;
@@ -804,7 +809,9 @@ int pbk_pregen_labels(pb_ctx* ctx) {
     // K1's last wave drains; PB_PREGEN_FIRST — pb_run_events calls this BEFORE it enqueues the sweep (ordered behind
     // ev[12], the start of the call), so the generator's blocks are resident first and the sweep fills the rest of each SM.
     const bool early = getenv("PB_PREGEN_EARLY") != nullptr, first = getenv("PB_PREGEN_FIRST") != nullptr;
-    if (first) {
+    if (immediately) {
+        PB_CUDA(cudaEventRecord(ctx->ev_gen_started, ctx->stream2));
+    } else if (first) {
         PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev[12], 0));
         PB_CUDA(cudaEventRecord(ctx->ev_gen_started, ctx->stream2));
     } else if (early) {
@@ -823,7 +830,7 @@ int pbk_pregen_labels(pb_ctx* ctx) {
     {
         int us = 8;
         if (const char* e = getenv("PB_GEN_HEADSTART_US")) us = atoi(e);
-        if (us > 0 && !early) {
+        if (us > 0 && !early && !immediately) {
             PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_gen_started, 0));
             k3_headstart_kernel<<<1, 1, 0, ctx->stream>>>((unsigned)us * 1000u);
             ctx->tm.n_launches += 1;
@@ -995,7 +1002,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     if ((rc = pbk_pvalues(ctx))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev[11], st));
     pb_trace_mark(ctx, "allreduce+pvalues");
-    struct { unsigned long long nf; unsigned int lc[4]; unsigned long long fb; } hb;   // layout of the scratch block in pbk_thresholds
+    struct { unsigned long long nf; unsigned int lc[4]; unsigned long long fb, swept; } hb;   // layout of the scratch block in pbk_thresholds
     PB_CUDA(cudaMemcpyAsync(&hb, ctx->d_nfast, sizeof(hb), cudaMemcpyDeviceToHost, st));
     unsigned long long replay_err = 0;
     PB_CUDA(cudaMemcpyAsync(&replay_err, ctx->d_class_counts + 12, 8, cudaMemcpyDeviceToHost, st));
@@ -1020,6 +1027,8 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     ctx->tm.n_fast_alleles = (int64_t)hb.nf;
     for (int c = 0; c < 4; c++) ctx->n_work[c] = (int64_t)hb.lc[c];
     ctx->tm.n_maxt_fallback_reps = (int64_t)hb.fb;
+    ctx->tm.n_swept_rows = (int64_t)hb.swept;
+    if (ctx->gen_timed) { cudaEventElapsedTime(&t, ctx->ev_gen_t0, ctx->ev_gen_t1); ctx->tm.ms_gen_kernel = t; }
     if (getenv("PB_VERBOSE"))
         fprintf(stderr, "[poutine_b200] work lists: trivial %u, tight %u, long %u, general %u; fallback replicates %llu\n", hb.lc[0], hb.lc[1], hb.lc[2],
                 hb.lc[3], hb.fb);

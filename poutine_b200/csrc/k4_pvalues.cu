@@ -131,9 +131,10 @@ __global__ void k4_ktau_kernel(const double* __restrict__ tab, int32_t n_max, co
 // ---- work lists for K3b: 0 = no sweep needed, 1 = short lists (n < 8) on the tight path, 2 = long lists (n >= 8),
 //      3 = short lists that need the general path -----------------------------------------------------------
 __global__ void k4_classify_kernel(AlleleMeta* __restrict__ alleles, int64_t n_slots, const int32_t* __restrict__ ktau, int has_miss,
-                                   int32_t* __restrict__ lists, unsigned int* __restrict__ counts) {
+                                   int32_t* __restrict__ lists, unsigned int* __restrict__ counts, unsigned long long* __restrict__ swept_rows) {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int cls = -1;
+    unsigned int my_rows = 0;       // label-matrix rows this allele's sweep reads per replicate word (K3b's algorithmic traffic)
     if (a < n_slots) {
         const AlleleMeta m = alleles[a];
         if (m.flags & PB_AF_IN_USE) {
@@ -149,8 +150,11 @@ __global__ void k4_classify_kernel(AlleleMeta* __restrict__ alleles, int64_t n_s
             alleles[a].flags = (m.flags & ~(PB_AF_TIGHT | PB_AF_TIGHT_CAND)) | (tight ? PB_AF_TIGHT : 0u) | (tight_cand ? PB_AF_TIGHT_CAND : 0u);
             const bool no_sweep = tight && (has_miss ? m.n <= 1 : (m.n <= 1 || m.kstar <= 0 || m.kstar > m.n));
             cls = no_sweep ? 0 : (m.n >= 8 ? 2 : (tight ? 1 : 3));
+            if (cls > 0) my_rows = (unsigned int)m.n;
         }
     }
+    my_rows = __reduce_add_sync(0xffffffffu, my_rows);
+    if ((threadIdx.x & 31) == 0 && my_rows) atomicAdd(swept_rows, (unsigned long long)my_rows);
     // list append: one global atomic per class per BLOCK (per-warp ballots -> block prefix in shared memory)
     __shared__ unsigned int s_wcount[8][4], s_base[4];
     const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -347,10 +351,10 @@ int pbk_thresholds(pb_ctx* ctx) {
     const int32_t n_max = ctx->n_max;
     cudaStream_t st = ctx->stream;
     int rc;
-    // one scratch allocation: [expect 64 f64][tau f64][n_fast u64][list counts 4 x u32][fallback total u64]
+    // one scratch allocation: [expect 64 f64][tau f64][n_fast u64][list counts 4 x u32][fallback total u64][swept rows u64]
     //                         [ktau i32 x (n_max+1)][hist u32 x (n_max+1)]
     const int64_t n1 = (int64_t)n_max + 1;
-    const int64_t need = TAU_LEVELS * 8 + 8 + 8 + 16 + 8 + n1 * 4 + n1 * 4;
+    const int64_t need = TAU_LEVELS * 8 + 8 + 8 + 16 + 8 + 8 + n1 * 4 + n1 * 4;
     if ((rc = ensure_bytes(ctx, &ctx->d_thr, &ctx->thr_cap, need))) return rc;
     char* base = (char*)ctx->d_thr;
     double* d_expect = (double*)base;
@@ -360,8 +364,9 @@ int pbk_thresholds(pb_ctx* ctx) {
     ctx->d_nfast = d_nfast;                 // {n_fast u64, list counts 4 x u32, fallback total u64}: read back once, at the end of pbk_assoc
     ctx->d_lcount = d_lcount;
     ctx->d_fb_total = (unsigned long long*)(base + TAU_LEVELS * 8 + 32);
-    ctx->d_ktau = (int32_t*)(base + TAU_LEVELS * 8 + 40);
-    unsigned int* d_hist = (unsigned int*)(base + TAU_LEVELS * 8 + 40 + n1 * 4);
+    unsigned long long* d_swept = (unsigned long long*)(base + TAU_LEVELS * 8 + 40);
+    ctx->d_ktau = (int32_t*)(base + TAU_LEVELS * 8 + 48);
+    unsigned int* d_hist = (unsigned int*)(base + TAU_LEVELS * 8 + 48 + n1 * 4);
     PB_CUDA(cudaMemsetAsync(ctx->d_thr, 0, (size_t)need, st));
     const int T = 256;
     const int force_general = (ctx->cfg.flags & PB_FLAG_FORCE_GENERAL_NULL) ? 1 : 0;
@@ -377,7 +382,7 @@ int pbk_thresholds(pb_ctx* ctx) {
         PB_CUDA(cudaMalloc(&ctx->d_work, (size_t)ctx->work_cap * 4 * 4));
     }
     k4_classify_kernel<<<(unsigned)std::max<int64_t>(1, (n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ktau, ctx->n_miss > 0 ? 1 : 0,
-                                                                          ctx->d_work, d_lcount);
+                                                                          ctx->d_work, d_lcount, d_swept);
     ctx->tm.n_launches += 5;
     PB_CUDA(cudaGetLastError());
     return PB_OK;

@@ -65,7 +65,12 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
         if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("cudaStreamCreate", e);
         if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
         if ((e = cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithFlags(&ctx->upl, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_upl, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_gen_t0)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_gen_t1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    ctx->eager_ok = getenv("PB_NO_EAGER_SWEEP") == nullptr;
     if ((e = cudaEventCreateWithFlags(&ctx->ev_side_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_side_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_zero_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -92,7 +97,12 @@ extern "C" void pb_destroy(pb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
+    if (ctx->upl) cudaStreamSynchronize(ctx->upl);
     free_all(ctx);
+    if (ctx->ev_upl) cudaEventDestroy(ctx->ev_upl);
+    if (ctx->ev_gen_t0) cudaEventDestroy(ctx->ev_gen_t0);
+    if (ctx->ev_gen_t1) cudaEventDestroy(ctx->ev_gen_t1);
+    if (ctx->upl) cudaStreamDestroy(ctx->upl);
     for (auto& t : ctx->trace) cudaEventDestroy(t.second);
     if (ctx->ev_side_fork) cudaEventDestroy(ctx->ev_side_fork);
     if (ctx->ev_side_join) cudaEventDestroy(ctx->ev_side_join);
@@ -304,8 +314,10 @@ extern "C" int pb_set_tree(pb_ctx* ctx, int32_t n_nodes, const int32_t* parent, 
     ctx->parent.assign(parent, parent + n_nodes);
     ctx->is_leaf.assign(is_leaf, is_leaf + n_nodes);
     ctx->events_done = ctx->assoc_done = false;
+    if (ctx->stream) PB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->stream2) PB_CUDA(cudaStreamSynchronize(ctx->stream2));
     ctx->pregen_valid = false;
+    ctx->swept_words = 0;
     ctx->P = 0; ctx->sample_node.clear(); ctx->label.clear();
     int rc;
     if ((rc = build_schedule(ctx))) return rc;
@@ -332,8 +344,10 @@ extern "C" int pb_set_labels(pb_ctx* ctx, int32_t n_samples, const int32_t* samp
         if (label[j] == PB_LABEL_CASE) nc++; else if (label[j] == PB_LABEL_CONTROL) nt++; else if (label[j] == PB_LABEL_MISSING) nm++;
         else FAIL(ctx, PB_ERR_INVALID, "pb_set_labels: label code must be 0, 1 or 2");
     }
+    if (ctx->stream) PB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->stream2) PB_CUDA(cudaStreamSynchronize(ctx->stream2));   // a pre-generated label matrix is stale now
     ctx->pregen_valid = false;
+    ctx->swept_words = 0;
     ctx->P = n_samples; ctx->n_case = nc; ctx->n_ctrl = nt; ctx->n_miss = nm;
     ctx->sample_node.assign(sample_node, sample_node + n_samples);
     ctx->label.assign(label, label + n_samples);
@@ -379,7 +393,7 @@ static int alloc_full_planes(pb_ctx* ctx) {
     ctx->d_V = ctx->d_planes;
     ctx->d_B0 = ctx->d_planes + (size_t)ctx->N * ctx->Wp;
     ctx->d_B1 = ctx->d_planes + 2 * (size_t)ctx->N * ctx->Wp;
-    PB_CUDA(cudaMemsetAsync(ctx->d_planes, 0, 3 * plane, ctx->stream));
+    PB_CUDA(cudaMemsetAsync(ctx->d_planes, 0, 3 * plane, ctx->upl));
     // dims (word column, node, plane); one box = the 3 KB a block needs of one tree row
     const cuuint64_t gdim[3] = {(cuuint64_t)ctx->W, (cuuint64_t)ctx->N, 3};
     const cuuint64_t gstride[2] = {(cuuint64_t)ctx->Wp * 8, (cuuint64_t)plane};
@@ -398,9 +412,9 @@ static int ensure_plane_mode(pb_ctx* ctx, int want) {
         if (e != cudaSuccess) { ctx->d_X = nullptr; ctx->err = std::string("cudaMalloc of the X plane: ") + cudaGetErrorString(e); return PB_ERR_OOM; }
         PB_CUDA(cudaMalloc(&ctx->d_xmask, (size_t)ctx->W * 32));
         PB_CUDA(cudaMalloc(&ctx->d_xvalid, (size_t)ctx->W * 8));
-        PB_CUDA(cudaMemsetAsync(ctx->d_X, 0, plane, ctx->stream));
-        PB_CUDA(cudaMemsetAsync(ctx->d_xmask, 0, (size_t)ctx->W * 32, ctx->stream));
-        PB_CUDA(cudaMemsetAsync(ctx->d_xvalid, 0, (size_t)ctx->W * 8, ctx->stream));
+        PB_CUDA(cudaMemsetAsync(ctx->d_X, 0, plane, ctx->upl));
+        PB_CUDA(cudaMemsetAsync(ctx->d_xmask, 0, (size_t)ctx->W * 32, ctx->upl));
+        PB_CUDA(cudaMemsetAsync(ctx->d_xvalid, 0, (size_t)ctx->W * 8, ctx->upl));
         const cuuint64_t gdim[2] = {(cuuint64_t)ctx->W, (cuuint64_t)ctx->N};
         const cuuint64_t gstride[1] = {(cuuint64_t)ctx->Wp * 8};
         const cuuint32_t box[2] = {(cuuint32_t)pbk_kx_cols(), 1};
@@ -411,7 +425,7 @@ static int ensure_plane_mode(pb_ctx* ctx, int want) {
     if ((rc = alloc_full_planes(ctx))) return rc;
     if (ctx->plane_mode == PB_PLANES_X) {
         if ((rc = pbk_promote_planes(ctx))) return rc;
-        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        PB_CUDA(cudaStreamSynchronize(ctx->upl));
         cudaFree(ctx->d_X); cudaFree(ctx->d_xmask); cudaFree(ctx->d_xvalid);
         ctx->d_X = ctx->d_xmask = ctx->d_xvalid = nullptr;
     }
@@ -427,6 +441,9 @@ extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
     if (n_sites < 1 || n_sites > PB_MAX_SITES_PER_CTX) FAIL(ctx, PB_ERR_INVALID, "pb_set_sites: n_sites out of range (1 .. 2^26 per context)");
     PB_CUDA(cudaSetDevice(ctx->device));
     ctx->events_done = ctx->assoc_done = false;
+    if (ctx->stream) PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->upl) PB_CUDA(cudaStreamSynchronize(ctx->upl));
+    ctx->swept_words = 0;
     if (n_sites == ctx->S && ctx->plane_mode != PB_PLANES_NONE) return PB_OK;   // same shape: the uploaded planes stay
     free_planes(ctx);
     for (void** p : {(void**)&ctx->d_cnt, (void**)&ctx->d_sites, (void**)&ctx->d_site_flags, (void**)&ctx->d_site_scan, (void**)&ctx->d_raw})
@@ -455,33 +472,64 @@ extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
     return build_chunks(ctx);
 }
 
-extern "C" int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* B0,
-                             const uint64_t* B1, const uint64_t* V) {
+// every upload runs on the context's upload stream; the compute stream picks the data up through ev_upl
+static int upload_done(pb_ctx* ctx, bool async) {
+    PB_CUDA(cudaEventRecord(ctx->ev_upl, ctx->upl));
+    if (!async) PB_CUDA(cudaStreamSynchronize(ctx->upl));   // host buffers are caller-owned: the plain calls do not retain them past return
+    return PB_OK;
+}
+
+static int put_planes_impl(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* B0, const uint64_t* B1,
+                           const uint64_t* V, bool async) {
     CHECK_CTX(ctx);
     if (ctx->S == 0) FAIL(ctx, PB_ERR_INVALID, "pb_put_planes: call pb_set_sites first");
     if (!B0 || !B1 || !V || word_begin < 0 || n_words < 1 || word_begin + n_words > ctx->W || src_pitch_words < n_words)
         FAIL(ctx, PB_ERR_INVALID, "pb_put_planes: tile out of range");
     PB_CUDA(cudaSetDevice(ctx->device));
     ctx->events_done = ctx->assoc_done = false;
+    ctx->swept_words = 0;                              // a three-plane tile: no sweep ahead of pb_run_events
     { int rc = ensure_plane_mode(ctx, PB_PLANES_FULL); if (rc) return rc; }
     const uint64_t* src[3] = {B0, B1, V};
     uint64_t* dst[3] = {ctx->d_B0, ctx->d_B1, ctx->d_V};
     if (word_begin == 0 && n_words == ctx->W && src_pitch_words == ctx->Wp) {
         // the caller's rows already have the device pitch (W rounded up to 16 words): one flat copy per plane
         for (int i = 0; i < 3; i++)
-            PB_CUDA(cudaMemcpyAsync(dst[i], src[i], (size_t)ctx->N * ctx->Wp * 8, cudaMemcpyHostToDevice, ctx->stream));
+            PB_CUDA(cudaMemcpyAsync(dst[i], src[i], (size_t)ctx->N * ctx->Wp * 8, cudaMemcpyHostToDevice, ctx->upl));
     } else {
         for (int i = 0; i < 3; i++)
             PB_CUDA(cudaMemcpy2DAsync(dst[i] + word_begin, (size_t)ctx->Wp * 8, src[i], (size_t)src_pitch_words * 8, (size_t)n_words * 8,
-                                      (size_t)ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+                                      (size_t)ctx->N, cudaMemcpyHostToDevice, ctx->upl));
     }
     if (word_begin + n_words == ctx->W) { int rc = pbk_mask_last_word(ctx); if (rc) return rc; }
-    PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers are caller-owned: do not retain them past return
+    return upload_done(ctx, async);
+}
+
+// One-plane mode, tiles arriving in column order and cut at the sweep's block width: the event sweep of a tile is
+// launched as soon as the tile has landed, on the compute stream, so that it runs underneath the NEXT tile's copy (the
+// copy engine and the SMs are otherwise idle in turn), and the label generator — which needs only the phenotypes and the
+// seed — starts with the first tile.  pb_run_events then sweeps what is left (usually nothing) and runs the tail.
+// Anything out of order (a re-upload, an unaligned tile, a three-plane tile) simply drops the head start: the records
+// written so far are discarded by the full sweep's cursor reset.
+static int eager_sweep(pb_ctx* ctx, int64_t word_begin, int64_t n_words) {
+    const int64_t cols = pbk_kx_cols();
+    // a tile that starts at word 0 always opens a new pass (whatever was swept before is discarded by the cursor reset)
+    const bool in_order = ctx->eager_ok && ctx->plane_mode == PB_PLANES_X && (word_begin == 0 || word_begin == ctx->swept_words) && word_begin % cols == 0 &&
+                          ((word_begin + n_words) % cols == 0 || word_begin + n_words == ctx->W) && ctx->N > 0;
+    if (!in_order) { ctx->swept_words = 0; return PB_OK; }
+    int rc;
+    if (word_begin == 0) {
+        ctx->tm = pb_timings{};
+        if ((rc = pbk_prepare_tail(ctx))) return rc;
+        if (!ctx->pregen_valid && (rc = pbk_pregen_labels(ctx, true))) return rc;
+    }
+    PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_upl, 0));
+    if ((rc = pbk_events_range(ctx, word_begin / cols, (n_words + cols - 1) / cols, word_begin == 0, false))) return rc;
+    ctx->swept_words = word_begin + n_words;
     return PB_OK;
 }
 
-extern "C" int pb_put_planes_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* X,
-                                       const uint64_t* V, const uint64_t* colmask) {
+static int put_planes_biallelic_impl(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* X,
+                                     const uint64_t* V, const uint64_t* colmask, bool async) {
     CHECK_CTX(ctx);
     if (ctx->S == 0) FAIL(ctx, PB_ERR_INVALID, "pb_put_planes_biallelic: call pb_set_sites first");
     if (!X || !colmask || word_begin < 0 || n_words < 1 || word_begin + n_words > ctx->W || src_pitch_words < n_words)
@@ -491,33 +539,57 @@ extern "C" int pb_put_planes_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t 
     int rc;
     const bool flat = word_begin == 0 && n_words == ctx->W && src_pitch_words == ctx->Wp;
     auto copy_rows = [&](uint64_t* dst, const uint64_t* src) -> cudaError_t {
-        if (flat) return cudaMemcpyAsync(dst, src, (size_t)ctx->N * ctx->Wp * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (flat) return cudaMemcpyAsync(dst, src, (size_t)ctx->N * ctx->Wp * 8, cudaMemcpyHostToDevice, ctx->upl);
         return cudaMemcpy2DAsync(dst + word_begin, (size_t)ctx->Wp * 8, src, (size_t)src_pitch_words * 8, (size_t)n_words * 8, (size_t)ctx->N,
-                                 cudaMemcpyHostToDevice, ctx->stream);
+                                 cudaMemcpyHostToDevice, ctx->upl);
     };
     // every genotype valid and no full-plane tile so far: the alignment stays one plane in HBM (k1x_events_kernel)
     const bool keep_x = !V && ctx->plane_mode != PB_PLANES_FULL && !(ctx->cfg.flags & PB_FLAG_FULL_PLANES);
     if (keep_x) {
         if ((rc = ensure_plane_mode(ctx, PB_PLANES_X))) return rc;
-        PB_CUDA(cudaMemcpyAsync(ctx->d_xmask + 4 * word_begin, colmask, (size_t)n_words * 32, cudaMemcpyHostToDevice, ctx->stream));
-        PB_CUDA(cudaMemsetAsync(ctx->d_xvalid + word_begin, 0xFF, (size_t)n_words * 8, ctx->stream));
+        PB_CUDA(cudaMemcpyAsync(ctx->d_xmask + 4 * word_begin, colmask, (size_t)n_words * 32, cudaMemcpyHostToDevice, ctx->upl));
+        PB_CUDA(cudaMemsetAsync(ctx->d_xvalid + word_begin, 0xFF, (size_t)n_words * 8, ctx->upl));
         PB_CUDA(copy_rows(ctx->d_X, X));
         if (word_begin + n_words == ctx->W && (rc = pbk_mask_last_word_x(ctx))) return rc;
-        PB_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers are caller-owned: do not retain them past return
-        return PB_OK;
+        PB_CUDA(cudaEventRecord(ctx->ev_upl, ctx->upl));
+        if ((rc = eager_sweep(ctx, word_begin, n_words))) return rc;
+        return upload_done(ctx, async);
     }
+    ctx->swept_words = 0;
     if ((rc = ensure_plane_mode(ctx, PB_PLANES_FULL))) return rc;
     if (n_words > ctx->colmask_cap) {
         if (ctx->d_colmask) { cudaFree(ctx->d_colmask); ctx->d_colmask = nullptr; ctx->colmask_cap = 0; }
         PB_CUDA(cudaMalloc(&ctx->d_colmask, (size_t)n_words * 32));
         ctx->colmask_cap = n_words;
     }
-    PB_CUDA(cudaMemcpyAsync(ctx->d_colmask, colmask, (size_t)n_words * 32, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(cudaMemcpyAsync(ctx->d_colmask, colmask, (size_t)n_words * 32, cudaMemcpyHostToDevice, ctx->upl));
     PB_CUDA(copy_rows(ctx->d_B0, X));               // X lands in the B0 rows and is expanded in place
     if (V) PB_CUDA(copy_rows(ctx->d_V, V));
     if ((rc = pbk_expand_biallelic(ctx, word_begin, n_words, ctx->d_colmask, V == nullptr))) return rc;
     if (V && word_begin + n_words == ctx->W) { rc = pbk_mask_last_word(ctx); if (rc) return rc; }
-    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return upload_done(ctx, async);
+}
+
+extern "C" int pb_put_planes(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* B0,
+                             const uint64_t* B1, const uint64_t* V) {
+    return put_planes_impl(ctx, word_begin, n_words, src_pitch_words, B0, B1, V, false);
+}
+extern "C" int pb_put_planes_async(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* B0,
+                                   const uint64_t* B1, const uint64_t* V) {
+    return put_planes_impl(ctx, word_begin, n_words, src_pitch_words, B0, B1, V, true);
+}
+extern "C" int pb_put_planes_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* X,
+                                       const uint64_t* V, const uint64_t* colmask) {
+    return put_planes_biallelic_impl(ctx, word_begin, n_words, src_pitch_words, X, V, colmask, false);
+}
+extern "C" int pb_put_planes_biallelic_async(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* X,
+                                             const uint64_t* V, const uint64_t* colmask) {
+    return put_planes_biallelic_impl(ctx, word_begin, n_words, src_pitch_words, X, V, colmask, true);
+}
+extern "C" int pb_upload_sync(pb_ctx* ctx) {
+    CHECK_CTX(ctx);
+    PB_CUDA(cudaSetDevice(ctx->device));
+    PB_CUDA(cudaStreamSynchronize(ctx->upl));
     return PB_OK;
 }
 
@@ -525,17 +597,32 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
     CHECK_CTX(ctx);
     if (ctx->S == 0 || ctx->N == 0) FAIL(ctx, PB_ERR_INVALID, "pb_run_events: tree and planes must be set");
     PB_CUDA(cudaSetDevice(ctx->device));
-    if (ctx->plane_mode == PB_PLANES_NONE) { int rc0 = ensure_plane_mode(ctx, PB_PLANES_FULL); if (rc0) return rc0; }   // nothing uploaded: no valid genotype anywhere
-    ctx->tm = pb_timings{};
+    if (ctx->plane_mode == PB_PLANES_NONE) {   // nothing uploaded: no valid genotype anywhere
+        int rc0 = ensure_plane_mode(ctx, PB_PLANES_FULL);
+        if (rc0) return rc0;
+        PB_CUDA(cudaEventRecord(ctx->ev_upl, ctx->upl));
+    }
+    PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_upl, 0));     // uploads (async ones included) are ordered before the sweep
+    // tiles swept ahead of this call (eager_sweep): their timings / launch counts belong to this pass
+    const bool ahead = ctx->swept_words > 0 && ctx->plane_mode == PB_PLANES_X;
+    const int64_t swept = ahead ? ctx->swept_words : 0;
+    ctx->swept_words = 0;
+    if (!ahead) ctx->tm = pb_timings{};
+    ctx->tm.eager_words = swept;
     int rc;
     if (ctx->plane_mode == PB_PLANES_FULL && (rc = ensure_census(ctx))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev[12], ctx->stream));
     for (int attempt = 0; attempt < 3; attempt++) {
-        if ((rc = pbk_prepare_tail(ctx))) return rc;
-        const bool gen_first = getenv("PB_PREGEN_FIRST") != nullptr;   // experiment: label generator resident before the sweep
-        if (attempt == 0 && gen_first && (rc = pbk_pregen_labels(ctx))) return rc;
-        if ((rc = pbk_events(ctx))) return rc;
-        if (attempt == 0 && !gen_first && (rc = pbk_pregen_labels(ctx))) return rc;
+        if (attempt == 0 && ahead) {
+            const int64_t cols = pbk_kx_cols(), b0 = (swept + cols - 1) / cols, b1 = (ctx->W + cols - 1) / cols;
+            if ((rc = pbk_events_range(ctx, b0, b1 - b0, false, true))) return rc;       // what the uploads did not cover (usually nothing)
+        } else {
+            if ((rc = pbk_prepare_tail(ctx))) return rc;
+            const bool gen_first = getenv("PB_PREGEN_FIRST") != nullptr;   // experiment: label generator resident before the sweep
+            if (attempt == 0 && gen_first && !ctx->pregen_valid && (rc = pbk_pregen_labels(ctx, false))) return rc;
+            if ((rc = pbk_events(ctx))) return rc;
+        }
+        if (attempt == 0 && !ctx->pregen_valid && (rc = pbk_pregen_labels(ctx, false))) return rc;
         unsigned long long cur = 0;
         if ((rc = pbk_finalize_events(ctx, counts, &cur))) return rc;   // the whole tail, one host round trip at its end
         if ((int64_t)cur <= ctx->raw_cap && ctx->E <= ctx->csr_cap) { ctx->n_rec = (int64_t)cur; break; }
@@ -557,7 +644,9 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
     cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]); ctx->tm.ms_events_kernel = t;
     cudaEventElapsedTime(&t, ctx->ev[12], ctx->ev[13]); ctx->tm.ms_events_total = t;
     ctx->tm.plane_mode = ctx->plane_mode;
-    ctx->tm.k1_algorithmic_bytes = (ctx->plane_mode == PB_PLANES_X ? 1ll : 3ll) * ctx->N * ctx->W * 8 + 32ll * ctx->S + 8ll * ctx->n_raw;
+    // what the sweep kernel itself moves: the plane bits once + one record per (row, word) that holds an event
+    ctx->tm.k1_algorithmic_bytes = (ctx->plane_mode == PB_PLANES_X ? 1ll : 3ll) * ctx->N * ctx->W * 8 +
+                                   (ctx->plane_mode == PB_PLANES_X ? 16ll : 32ll) * ctx->n_rec;
     ctx->tm.n_informative = ctx->S_inf; ctx->tm.n_alleles_in_use = ctx->A_inuse; ctx->tm.n_extant_events = ctx->E;
     ctx->events_done = true;
     ctx->assoc_done = false;
@@ -709,13 +798,14 @@ extern "C" int pb_comm_init(pb_ctx* ctx, const void* id128, int32_t rank, int32_
     CHECK_CTX(ctx);
     if (!id128 || world < 1 || rank < 0 || rank >= world) FAIL(ctx, PB_ERR_INVALID, "pb_comm_init: bad rank/world");
     PB_CUDA(cudaSetDevice(ctx->device));
+    ctx->xchg.active = false;      // (the fall-back after a peer-memory connect that did not succeed on every rank)
     return pbn_init(ctx, id128, rank, world);
 }
 
 extern "C" int pb_comm_export(pb_ctx* ctx, void* handle64) {
     CHECK_CTX(ctx);
     if (!handle64) FAIL(ctx, PB_ERR_INVALID, "pb_comm_export: null handle buffer");
-    if (ctx->xchg.active || ctx->nccl_comm) FAIL(ctx, PB_ERR_INVALID, "pb_comm_export: the context is already connected");
+    if (ctx->xchg.active) FAIL(ctx, PB_ERR_INVALID, "pb_comm_export: the context is already connected");
     PB_CUDA(cudaSetDevice(ctx->device));
     return pbx_export(ctx, handle64);
 }

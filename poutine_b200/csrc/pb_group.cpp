@@ -217,6 +217,27 @@ extern "C" int pb_group_put_planes_biallelic(pb_group* g, int64_t word_begin, in
     });
 }
 
+// asynchronous forms: every shard's copies are queued (each on its own GPU's upload stream) and the call returns; the host
+// buffers stay in use until pb_group_upload_sync.  One host thread can thus keep all PCIe links busy at once.
+extern "C" int pb_group_put_planes_async(pb_group* g, int64_t word_begin, int64_t n_words, int64_t src_pitch_words, const uint64_t* B0,
+                                         const uint64_t* B1, const uint64_t* V) {
+    return put_tile(g, word_begin, n_words, "pb_group_put_planes_async", [&](pb_ctx* c, int64_t local_w, int64_t nw, int64_t src_off) {
+        return pb_put_planes_async(c, local_w, nw, src_pitch_words, B0 + src_off, B1 + src_off, V + src_off);
+    });
+}
+
+extern "C" int pb_group_put_planes_biallelic_async(pb_group* g, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
+                                                   const uint64_t* X, const uint64_t* V, const uint64_t* colmask) {
+    return put_tile(g, word_begin, n_words, "pb_group_put_planes_biallelic_async", [&](pb_ctx* c, int64_t local_w, int64_t nw, int64_t src_off) {
+        return pb_put_planes_biallelic_async(c, local_w, nw, src_pitch_words, X + src_off, V ? V + src_off : nullptr, colmask + 4 * src_off);
+    });
+}
+
+extern "C" int pb_group_upload_sync(pb_group* g) {
+    if (!g) return PB_ERR_INVALID;
+    return g->all([&](int i) { return pb_upload_sync(g->ctx[(size_t)i]); });
+}
+
 extern "C" int pb_group_run_events(pb_group* g, pb_site_out* per_site, pb_class_counts* counts) {
     if (!g) return PB_ERR_INVALID;
     if (g->S == 0) { g->err = "pb_group_run_events: tree and planes must be set"; return PB_ERR_INVALID; }
@@ -281,7 +302,8 @@ extern "C" int pb_group_get_timings(pb_group* g, pb_timings* out) {
         t.ms_assoc_total = std::max(t.ms_assoc_total, s.ms_assoc_total);
         t.n_launches += s.n_launches; t.k1_algorithmic_bytes += s.k1_algorithmic_bytes; t.n_informative += s.n_informative;
         t.n_alleles_in_use += s.n_alleles_in_use; t.n_extant_events += s.n_extant_events; t.n_fast_alleles += s.n_fast_alleles;
-        t.n_maxt_fallback_reps += s.n_maxt_fallback_reps;
+        t.n_maxt_fallback_reps += s.n_maxt_fallback_reps; t.n_swept_rows += s.n_swept_rows; t.eager_words += s.eager_words;
+        t.ms_gen_kernel = std::max(t.ms_gen_kernel, s.ms_gen_kernel);
         t.plane_mode = std::max(t.plane_mode, s.plane_mode);
     }
     *out = t;

@@ -158,9 +158,14 @@ struct pb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // label-matrix pre-generation (K3a) alongside the K1 tail
     cudaStream_t stream3 = nullptr;          // K3b side stream: the few heavy short-list/long-list sweeps run next to the tight sweep
+    cudaStream_t upl = nullptr;              // uploads (H2D copies, plane zero-fills, expansion kernels): the copy engine's own queue
+    cudaEvent_t ev_upl = nullptr;            // last upload enqueued; the compute stream waits on it
+    bool eager_ok = true;                    // PB_NO_EAGER_SWEEP unset
+    int64_t swept_words = 0;                 // one-plane mode: site words [0, swept_words) were swept while later tiles uploaded
     cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr, ev_zero_done = nullptr;
     cudaEvent_t ev_k1_done = nullptr, ev_gen_started = nullptr, ev_gen_done = nullptr, ev_gen_b[2] = {nullptr, nullptr}, ev_cnt_b[2] = {nullptr, nullptr};
     bool pregen_valid = false; int64_t pregen_tile = 0;
+    cudaEvent_t ev_gen_t0 = nullptr, ev_gen_t1 = nullptr; bool gen_timed = false;   // the label generator's own time (first tile)
     std::string err;
     int sm_count = 148;
 
@@ -278,6 +283,7 @@ struct pb_ctx {
 
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------
 int pbk_events(pb_ctx* ctx);                                   // k1_events.cu
+int pbk_events_range(pb_ctx* ctx, int64_t block0, int64_t n_blocks, bool first, bool last);   // k1_events.cu: one-plane sweep of a column-block range
 int pbk_mask_last_word(pb_ctx* ctx);                           // k1_events.cu (clears the padding bits of site word W-1 in V)
 int pbk_kx_cols();                                             // k1_events.cu: word columns per k1x block
 int pbk_kx_blocks_per_sm();
@@ -287,7 +293,7 @@ int pbk_expand_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, const
 int pbk_prepare_tail(pb_ctx* ctx);                             // k1_events.cu (tail buffers + zero-fill on stream2, before K1)
 int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out); // k1_events.cu
 int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms);      // k3_null.cu (+ k4)
-int pbk_pregen_labels(pb_ctx* ctx);                            // k3_null.cu
+int pbk_pregen_labels(pb_ctx* ctx, bool immediately);          // k3_null.cu
 int pbk_ptable(pb_ctx* ctx);                                   // k4_pvalues.cu
 int pbk_thresholds(pb_ctx* ctx);                               // k4_pvalues.cu
 int pbk_pvalues(pb_ctx* ctx);                                  // k4_pvalues.cu

@@ -104,3 +104,66 @@ def test_c3_shard_slice_parity_inside_a_large_run(oracle_mod):
         for f in EV_FIELDS:
             np.testing.assert_array_equal(sl[f], or_ev[f], err_msg=f)
         hc.close()
+
+
+@pytest.mark.parametrize("mode", ["whole", "tiles256", "tiles512_async", "reverse", "unaligned", "reupload_first"])
+def test_sweep_under_upload_equals_plain_run(oracle_mod, mode):
+    """One-plane tiles that arrive in column order, cut at the sweep's block width (256 site words), are swept as they land
+    (timings()["eager_words"]); anything else falls back to the full sweep inside pb_run_events.  Same results either way,
+    equal to the oracle; a second pass over the resident planes (no upload in between) must sweep everything again."""
+    tree = synth.yule_tree(300, 21)
+    S = 64 * (256 * 3 + 100) + 5
+    W = (S + 63) // 64
+    B0, B1, V = synth.simulate_planes(tree, S, 22)
+    sn, lab = synth.simulate_phenotypes(tree, 23)
+    X, colmask, all_valid = pb.compact_planes(B0, B1, V, S)
+    assert all_valid
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    or_ev, or_cc = o.count_all_homoplasy_events(synth.planes_to_chars(B0, B1, V, 0, S), n_threads=8)
+    m = 512
+    or_st, or_mt, _ = o.assoc(sn, lab, m, 1, perms=None, seed=5, n_threads=8)
+
+    hc = pb.HomoplasyCounter(num_replicates=m, seed=5)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_sites(S)
+
+    def put(w0, w1, asynchronous=False):
+        hc.put_planes_biallelic(np.ascontiguousarray(X[:, w0:w1]), None, np.ascontiguousarray(colmask[w0:w1]), w0, asynchronous=asynchronous)
+
+    if mode == "whole":
+        put(0, W); want_eager = W
+    elif mode == "tiles256":
+        for w0 in range(0, W, 256):
+            put(w0, min(W, w0 + 256))
+        want_eager = W
+    elif mode == "tiles512_async":
+        for w0 in range(0, W, 512):
+            put(w0, min(W, w0 + 512), asynchronous=True)
+        hc.upload_sync()
+        want_eager = W
+    elif mode == "reverse":
+        for w0 in reversed(range(0, W, 256)):
+            put(w0, min(W, w0 + 256))
+        want_eager = 256                 # only the tile at word 0 (uploaded last) could start a pass
+    elif mode == "unaligned":
+        for w0 in range(0, W, 200):
+            put(w0, min(W, w0 + 200))
+        want_eager = 0
+    else:
+        for w0 in range(0, W, 256):
+            put(w0, min(W, w0 + 256))
+        put(0, 256)                      # the first tile again: the head start is dropped ...
+        want_eager = 256                 # ... and a new in-order run starts with it; the rest is swept by pb_run_events
+    for pass_ in range(2):
+        ev, cc = hc.count_all_homoplasy_events()
+        tm = hc.timings()
+        assert tm["plane_mode"] == 1
+        assert tm["eager_words"] == (want_eager if pass_ == 0 else 0)
+        assert cc["bi"] == or_cc["bi"] and len(ev) == len(or_ev)
+        for f in EV_FIELDS:
+            np.testing.assert_array_equal(ev[f], or_ev[f], err_msg=f)
+        st, mt = hc.assoc()
+        assert_stats_equal(st, or_st)
+        np.testing.assert_array_equal(mt.view(np.uint64), or_mt.view(np.uint64))
+    hc.close()
