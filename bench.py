@@ -395,6 +395,7 @@ def run_b200(args):
         hc.assoc(fetch=False)
         return hc.timings()
 
+    fused_call = not inproc and not args.two_calls       # pb_run_events_assoc (single context); a group makes the two calls
     e2e_parts = {"put_planes": 0.0, "events": 0.0, "assoc": 0.0}
     e2e_steps = []                                       # wall ms of every end-to-end step on this rank (an outlier shows here)
 
@@ -402,10 +403,14 @@ def run_b200(args):
         t0 = time.perf_counter()
         upload(use_compact)                              # H2D of this step's inputs (pinned host memory)
         t1 = time.perf_counter()
-        ev, cc = hc.count_all_homoplasy_events(compact=False)   # D2H: per-site Homoplasy_Events records (page-locked buffer)
-        t2 = time.perf_counter()
-        st, mt = hc.assoc()                              # D2H: per-informative-site statistics + sorted maxT
-        t3 = time.perf_counter()
+        if fused_call:                                   # both entry points in one C call: the per-site records leave under the association
+            ev, cc, st, mt = hc.count_all_homoplasy_events_and_assoc()
+            t2 = t3 = time.perf_counter()
+        else:
+            ev, cc = hc.count_all_homoplasy_events(compact=False)   # D2H: per-site Homoplasy_Events records (page-locked buffer)
+            t2 = time.perf_counter()
+            st, mt = hc.assoc()                          # D2H: per-informative-site statistics + sorted maxT
+            t3 = time.perf_counter()
         e2e_parts["put_planes"] += 1e3 * (t1 - t0); e2e_parts["events"] += 1e3 * (t2 - t1); e2e_parts["assoc"] += 1e3 * (t3 - t2)
         e2e_steps.append(round(1e3 * (t3 - t0), 3))
         return hc.timings(), ev, st, mt
@@ -560,6 +565,7 @@ def run_b200(args):
                                     "X + V planes + site masks, expanded to three planes on the device"))
                                   if all_compact else "pb_put_planes_async (three planes)",
                         "swept_under_upload_words": eager_words,
+                        "calls": "pb_run_events_assoc (one call; `events` in breakdown_ms covers both)" if fused_call else "pb_run_events + pb_run_assoc",
                         "compaction_in_timed_region": False,
                         "input_format": "the compact format the one-pass host packer emits (see host_packer); the synthetic generator produces "
                                         "planes, so here it is derived from them once at set-up (%.2f s), outside the timed region like "
@@ -604,6 +610,7 @@ def main():
     ap.add_argument("--replicates", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-planes-only", action="store_true", help="e2e leg uploads three planes even when the input is biallelic")
+    ap.add_argument("--two-calls", action="store_true", help="e2e leg: pb_run_events + pb_run_assoc instead of the fused pb_run_events_assoc")
     ap.add_argument("--inproc", action="store_true", help="--gpus N from ONE process / one host thread (pb_group) instead of torchrun ranks")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="weak: the config's sites per GPU (default); strong: the config's sites over all GPUs (default for C3)")

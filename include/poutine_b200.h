@@ -185,6 +185,12 @@ int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts);
 int pb_run_assoc(pb_ctx* ctx, const uint32_t* replay_perms, pb_stat_out* per_inf_site, int64_t cap,
                  int64_t* n_inf, double* maxT_sorted);
 
+/* The two calls back to back, as Homoplasy_Counter.call() makes them (HC.java:299, 314), in one entry: the per-site
+ * records travel to the host underneath the association kernels instead of in front of them.  per_inf_site must have room
+ * for the worst case known before the call (cap >= n_sites always suffices).  Same results and errors as the two calls. */
+int pb_run_events_assoc(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts, const uint32_t* replay_perms,
+                        pb_stat_out* per_inf_site, int64_t cap, int64_t* n_inf, double* maxT_sorted);
+
 /* Two per-site statistics outside the reference's LIVE path, on request after pb_run_assoc (either pointer may be NULL).
  * PARITY UNPINNED: the reference has no runnable counterpart; checked against exact rational arithmetic (1e-12 relative).
  *   exact_pointwise[2*i + a]  the m -> infinity limit of allele a's point-wise estimate r/m (HC.java:4812-4838) for

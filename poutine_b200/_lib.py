@@ -59,7 +59,7 @@ EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_set_tree", "pb_set_la
            "pb_pack_chars", "pb_host_alloc", "pb_host_free", "pb_version",
            "pb_fasta_open", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_record", "pb_fasta_pack_tile", "pb_fasta_last_error",
            "pb_comm_export", "pb_comm_connect", "pb_fasta_pack_tile_biallelic", "pb_pack_chars_biallelic",
-           "pb_put_planes_async", "pb_put_planes_biallelic_async", "pb_upload_sync",
+           "pb_run_events_assoc", "pb_put_planes_async", "pb_put_planes_biallelic_async", "pb_upload_sync",
            "pb_group_create", "pb_group_destroy", "pb_group_last_error", "pb_group_size", "pb_group_ctx", "pb_group_set_tree",
            "pb_group_set_labels", "pb_group_set_sites", "pb_group_shard_range", "pb_group_put_planes", "pb_group_put_planes_biallelic",
            "pb_group_run_events", "pb_group_run_assoc", "pb_group_run_extras", "pb_group_get_timings", "pb_group_stopwatch_mark",
@@ -98,6 +98,7 @@ def lib():
         L.pb_compact_planes.argtypes = [vp, vp, vp, i64, i64, i64, vp, i64, vp, C.POINTER(i32), i32]
         L.pb_run_events.argtypes = [vp, vp, C.POINTER(PbClassCounts)]
         L.pb_run_assoc.argtypes = [vp, vp, vp, i64, C.POINTER(i64), vp]
+        L.pb_run_events_assoc.argtypes = [vp, vp, C.POINTER(PbClassCounts), vp, vp, i64, C.POINTER(i64), vp]
         L.pb_run_extras.argtypes = [vp, vp, vp]
         L.pb_get_sites.argtypes = [vp, vp]
         L.pb_get_raw_events.argtypes = [vp, i64, vp, vp, C.POINTER(i64)]

@@ -261,6 +261,24 @@ class HomoplasyCounter:
         self.n_informative = n_inf.value
         return (stats[:n_inf.value] if fetch else None), maxT
 
+    def count_all_homoplasy_events_and_assoc(self, replay_perms=None):
+        """The two entry points back to back in one C call (pb_run_events_assoc): the per-site records travel to the host
+        underneath the association kernels.  -> (sites (one record per site, see count_all_homoplasy_events(compact=False)),
+        class_counts, stats, maxT_sorted); all arrays are views of page-locked buffers the next call overwrites."""
+        cc = PbClassCounts()
+        sites = self._result_buffer("sites", self.n_sites, SITE_DTYPE)
+        stats = self._result_buffer("stats", max(self.n_sites, 1), STAT_DTYPE)      # worst case: every site informative
+        maxT = self._result_buffer("maxT", self.m, np.float64)
+        n_inf = C.c_int64(0)
+        perms = None
+        if replay_perms is not None:
+            perms = np.ascontiguousarray(replay_perms, dtype=np.uint32)
+            assert perms.shape == (self.m, self.n_samples)
+        self._check(_lib.lib().pb_run_events_assoc(self._h, ptr(sites), C.byref(cc), ptr(perms), ptr(stats), len(stats), C.byref(n_inf), ptr(maxT)))
+        counts = dict(no_allele=cc.n_no_allele, mono=cc.n_mono, bi=cc.n_bi, tri=cc.n_tri, quad=cc.n_quad, raw_events=cc.n_raw_events)
+        self.class_counts, self.sites, self.n_informative = counts, sites, n_inf.value
+        return sites, counts, stats[:n_inf.value], maxT
+
     def extras(self):
         """-> (exact_pointwise float64[n_inf, 2], fisher_p float64[n_inf]) after assoc().  Outside the reference's live
         path (parity unpinned): the exact m -> infinity limit of the point-wise estimate under the label-permutation

@@ -804,25 +804,28 @@ int pbk_pregen_labels(pb_ctx* ctx, bool immediately) {
     if ((rc = k3_plan(ctx, &pl))) return rc;
     const int64_t m = ctx->cfg.n_replicates;
     const int64_t nr = m < pl.tile ? m : pl.tile;
+    // one wave of generator blocks -> the high-priority stream (resident before the tail); many waves -> the low-priority one
+    const bool many_waves = (nr + GEN_THREADS - 1) / GEN_THREADS > (int64_t)ctx->sm_count * 5 && !getenv("PB_GEN_ALWAYS_HIGH");
+    cudaStream_t gs = many_waves ? ctx->stream2_lo : ctx->stream2;
     // default: the generator starts when K1 has finished.  Experiments: PB_PREGEN_EARLY — it is ordered behind the previous
     // step only (ev[0] is recorded just before the K1 launch), so the low-priority stream may pick up SM slots while
     // K1's last wave drains; PB_PREGEN_FIRST — pb_run_events calls this BEFORE it enqueues the sweep (ordered behind
     // ev[12], the start of the call), so the generator's blocks are resident first and the sweep fills the rest of each SM.
     const bool early = getenv("PB_PREGEN_EARLY") != nullptr, first = getenv("PB_PREGEN_FIRST") != nullptr;
     if (immediately) {
-        PB_CUDA(cudaEventRecord(ctx->ev_gen_started, ctx->stream2));
+        PB_CUDA(cudaEventRecord(ctx->ev_gen_started, gs));
     } else if (first) {
-        PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev[12], 0));
-        PB_CUDA(cudaEventRecord(ctx->ev_gen_started, ctx->stream2));
+        PB_CUDA(cudaStreamWaitEvent(gs, ctx->ev[12], 0));
+        PB_CUDA(cudaEventRecord(ctx->ev_gen_started, gs));
     } else if (early) {
-        PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev[0], 0));
+        PB_CUDA(cudaStreamWaitEvent(gs, ctx->ev[0], 0));
     } else {
         PB_CUDA(cudaEventRecord(ctx->ev_k1_done, ctx->stream));
-        PB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_k1_done, 0));
-        PB_CUDA(cudaEventRecord(ctx->ev_gen_started, ctx->stream2));
+        PB_CUDA(cudaStreamWaitEvent(gs, ctx->ev_k1_done, 0));
+        PB_CUDA(cudaEventRecord(ctx->ev_gen_started, gs));
     }
-    if ((rc = k3_launch_philox(ctx, pl, 0, nr, ctx->stream2, 0))) return rc;
-    PB_CUDA(cudaEventRecord(ctx->ev_gen_done, ctx->stream2));
+    if ((rc = k3_launch_philox(ctx, pl, 0, nr, gs, 0))) return rc;
+    PB_CUDA(cudaEventRecord(ctx->ev_gen_done, gs));
     // The generator is ONE wave of long-running blocks: it finishes ~0.65 ms after its LAST block starts, and the main
     // stream's tail kernels (queued right behind K1) would otherwise win the race for the SM slots K1 frees.  Hold the
     // main stream for a few microseconds behind the K1 dependency so that the generator's blocks become resident first;
@@ -830,7 +833,7 @@ int pbk_pregen_labels(pb_ctx* ctx, bool immediately) {
     {
         int us = 8;
         if (const char* e = getenv("PB_GEN_HEADSTART_US")) us = atoi(e);
-        if (us > 0 && !early && !immediately) {
+        if (us > 0 && !early && !immediately && !many_waves) {
             PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_gen_started, 0));
             k3_headstart_kernel<<<1, 1, 0, ctx->stream>>>((unsigned)us * 1000u);
             ctx->tm.n_launches += 1;
@@ -839,6 +842,48 @@ int pbk_pregen_labels(pb_ctx* ctx, bool immediately) {
     ctx->pregen_valid = true;
     ctx->pregen_tile = pl.tile;
     return PB_OK;
+}
+
+// Every allocation pb_run_assoc needs (sizes follow from S_inf, n_max, P, m: all known after pb_run_events), so that the
+// pass itself issues no cudaMalloc / cudaFree.  In a sharded run a shard's last kernel waits for its peers inside the
+// exchange; an allocation on a device that is in that state may wait for the device — pb_group therefore prepares ALL its
+// shards before any of them starts the pass.
+static int k3_alloc(pb_ctx* ctx, K3Plan* pl) {
+    const int64_t m = ctx->cfg.n_replicates;
+    int rc;
+    if (!ctx->xchg.active) {
+        int64_t mcap_bytes = ctx->maxT_cap * 8;
+        void* pm = ctx->d_maxT_own;
+        if ((rc = ensure(ctx, &pm, &mcap_bytes, m * 8))) { ctx->d_maxT_own = nullptr; return rc; }
+        ctx->d_maxT_own = (unsigned long long*)pm; ctx->maxT_cap = mcap_bytes / 8;
+    }
+    if ((rc = k3_plan(ctx, pl))) return rc;
+    if (!ctx->d_colpop || ctx->colpop_cap < ctx->P) {
+        if (ctx->d_colpop) cudaFree(ctx->d_colpop);
+        ctx->d_colpop = nullptr;
+        PB_CUDA(cudaMalloc(&ctx->d_colpop, (size_t)ctx->P * 2 * 4));
+        ctx->colpop_cap = ctx->P;
+    }
+    void* pf = ctx->d_fb_reps;
+    if ((rc = ensure(ctx, &pf, &ctx->fb_cap, (pl->tile + 256) * 4))) { ctx->d_fb_reps = nullptr; return rc; }
+    ctx->d_fb_reps = (int32_t*)pf;
+    if (ctx->cfg.mode == PB_MODE_REPLAY) {       // one tile of caller permutations at a time
+        const int64_t nr = m < pl->tile ? m : pl->tile;
+        int64_t cap = ctx->perms_cap;
+        void* pp = ctx->d_perms;
+        if ((rc = ensure(ctx, &pp, &cap, nr * (int64_t)ctx->P * 4))) { ctx->d_perms = nullptr; ctx->perms_cap = 0; return rc; }
+        ctx->d_perms = (uint32_t*)pp; ctx->perms_cap = cap;
+    }
+    return PB_OK;
+}
+
+int pbk_assoc_prepare(pb_ctx* ctx) {
+    int rc;
+    K3Plan pl;
+    if ((rc = pbk_ptable(ctx, true))) return rc;
+    if ((rc = pbk_thresholds(ctx, true))) return rc;
+    if ((rc = k3_alloc(ctx, &pl))) return rc;
+    return pbk_pvalues(ctx, true);
 }
 
 int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
@@ -863,13 +908,11 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     pb_trace_mark(ctx, "ptable+thresholds");
 
     // ---- null distribution, tiled over replicates
+    K3Plan pl;
+    if ((rc = k3_alloc(ctx, &pl))) return rc;
     if (ctx->xchg.active) {
         if ((rc = pbx_begin_epoch(ctx))) return rc;      // the epoch's buffer of the exchange block (peers read it)
     } else {
-        int64_t mcap_bytes = ctx->maxT_cap * 8;
-        void* pm = ctx->d_maxT_own;
-        if ((rc = ensure(ctx, &pm, &mcap_bytes, m * 8))) { ctx->d_maxT_own = nullptr; return rc; }
-        ctx->d_maxT_own = (unsigned long long*)pm; ctx->maxT_cap = mcap_bytes / 8;
         ctx->d_maxT = ctx->d_maxT_own;
     }
     fill_u64_kernel<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(ctx->d_maxT, m, 0x7FF0000000000000ull);
@@ -877,21 +920,8 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     PB_CUDA(cudaMemsetAsync(ctx->d_class_counts + 12, 0, 8, st));   // replay-permutation check flag (k3_gen_kernel<1, .>)
     ctx->tm.n_launches += 1;
 
-    K3Plan pl;
-    if ((rc = k3_plan(ctx, &pl))) return rc;
     const bool has_miss = pl.has_miss;
     const int64_t tile = pl.tile, Rw32 = pl.Rw32, Rw = pl.Rw;
-    {
-        if (!ctx->d_colpop || ctx->colpop_cap < ctx->P) {
-            if (ctx->d_colpop) cudaFree(ctx->d_colpop);
-            ctx->d_colpop = nullptr;
-            PB_CUDA(cudaMalloc(&ctx->d_colpop, (size_t)ctx->P * 2 * 4));
-            ctx->colpop_cap = ctx->P;
-        }
-        void* pl = ctx->d_fb_reps;
-        if ((rc = ensure(ctx, &pl, &ctx->fb_cap, (tile + 256) * 4))) { ctx->d_fb_reps = nullptr; return rc; }
-        ctx->d_fb_reps = (int32_t*)pl;
-    }
     // No host round trip inside the loop: list lengths, the fallback list and its length stay on the device; buffer
     // reuse between the two streams is ordered with events.  (Replay mode uploads each tile's permutations.)
     ctx->tm.n_maxt_fallback_reps = 0;
@@ -909,11 +939,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
         const unsigned gblocks = (unsigned)((nr + GEN_THREADS - 1) / GEN_THREADS);
         const int buf = (pl.nbuf == 2) ? (int)((base / tile) & 1) : 0;
         if (ctx->cfg.mode == PB_MODE_REPLAY) {
-            const int64_t bytes = nr * (int64_t)ctx->P * 4;
-            int64_t cap = ctx->perms_cap;
-            void* pp = ctx->d_perms;
-            if ((rc = ensure(ctx, &pp, &cap, bytes))) { ctx->d_perms = nullptr; ctx->perms_cap = 0; return rc; }
-            ctx->d_perms = (uint32_t*)pp; ctx->perms_cap = cap;
+            const int64_t bytes = nr * (int64_t)ctx->P * 4;       // (buffer sized for a whole tile by k3_alloc)
             PB_CUDA(cudaMemcpyAsync(ctx->d_perms, replay_perms + base * (int64_t)ctx->P, (size_t)bytes, cudaMemcpyHostToDevice, st));
             if (has_miss)
                 k3_gen_kernel<1, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label,

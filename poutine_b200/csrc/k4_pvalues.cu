@@ -327,7 +327,10 @@ static int ensure_bytes(pb_ctx* ctx, void** ptr, int64_t* cap, int64_t need) {
     return PB_OK;
 }
 
-int pbk_ptable(pb_ctx* ctx) {
+// alloc_only (here and below): do the allocations of this step and return — pbk_assoc_prepare runs every allocation of
+// pb_run_assoc up front, so that no cudaMalloc / cudaFree is issued once a sharded pass has kernels in flight that wait
+// for a peer (an allocation may synchronise the device).
+int pbk_ptable(pb_ctx* ctx, bool alloc_only) {
     // table rows 0..n_max for this context's p (the table is a pure function of (n_max, p): cached)
     const int32_t n_max = ctx->n_max;
     const double p = (double)ctx->n_case / (double)(ctx->n_case + ctx->n_ctrl);  // calc_background_p_success (HC.java:3335)
@@ -339,6 +342,7 @@ int pbk_ptable(pb_ctx* ctx) {
     void* pt = ctx->d_ptable;
     if ((rc = ensure_bytes(ctx, &pt, &cap, total * 8))) { ctx->d_ptable = nullptr; ctx->ptable_cap = 0; return rc; }
     ctx->d_ptable = (double*)pt; ctx->ptable_cap = cap;
+    if (alloc_only) { ctx->ptable_nmax = -1; return PB_OK; }      // (the buffer may have moved: the table is rebuilt by the real call)
     k4_ptable_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ptable, n_max, p);
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
@@ -346,7 +350,7 @@ int pbk_ptable(pb_ctx* ctx) {
     return PB_OK;
 }
 
-int pbk_thresholds(pb_ctx* ctx) {
+int pbk_thresholds(pb_ctx* ctx, bool alloc_only) {
     const int64_t n_slots = 2 * ctx->S_inf;
     const int32_t n_max = ctx->n_max;
     cudaStream_t st = ctx->stream;
@@ -356,6 +360,13 @@ int pbk_thresholds(pb_ctx* ctx) {
     const int64_t n1 = (int64_t)n_max + 1;
     const int64_t need = TAU_LEVELS * 8 + 8 + 8 + 16 + 8 + 8 + n1 * 4 + n1 * 4;
     if ((rc = ensure_bytes(ctx, &ctx->d_thr, &ctx->thr_cap, need))) return rc;
+    if (n_slots > ctx->work_cap) {
+        if (ctx->d_work) cudaFree(ctx->d_work);
+        ctx->d_work = nullptr;
+        ctx->work_cap = n_slots + n_slots / 8 + 1024;
+        PB_CUDA(cudaMalloc(&ctx->d_work, (size_t)ctx->work_cap * 4 * 4));
+    }
+    if (alloc_only) return PB_OK;
     char* base = (char*)ctx->d_thr;
     double* d_expect = (double*)base;
     ctx->d_tau = (double*)(base + TAU_LEVELS * 8);
@@ -375,12 +386,6 @@ int pbk_thresholds(pb_ctx* ctx) {
     k4_tau_expect_kernel<<<TAU_LEVELS, 256, 0, st>>>(ctx->d_ptable, d_hist, n_max, d_expect);
     k4_tau_pick_kernel<<<1, 1, 0, st>>>(d_expect, 16.0, ctx->cfg.maxt_tau, ctx->d_tau);
     k4_ktau_kernel<<<(unsigned)((n1 + T - 1) / T), T, 0, st>>>(ctx->d_ptable, n_max, ctx->d_tau, ctx->d_ktau);
-    if (n_slots > ctx->work_cap) {
-        if (ctx->d_work) cudaFree(ctx->d_work);
-        ctx->d_work = nullptr;
-        ctx->work_cap = n_slots + n_slots / 8 + 1024;
-        PB_CUDA(cudaMalloc(&ctx->d_work, (size_t)ctx->work_cap * 4 * 4));
-    }
     k4_classify_kernel<<<(unsigned)std::max<int64_t>(1, (n_slots + T - 1) / T), T, 0, st>>>(ctx->d_alleles, n_slots, ctx->d_ktau, ctx->n_miss > 0 ? 1 : 0,
                                                                           ctx->d_work, d_lcount, d_swept);
     ctx->tm.n_launches += 5;
@@ -388,7 +393,7 @@ int pbk_thresholds(pb_ctx* ctx) {
     return PB_OK;
 }
 
-int pbk_pvalues(pb_ctx* ctx) {
+int pbk_pvalues(pb_ctx* ctx, bool alloc_only) {
     const int64_t m = ctx->cfg.n_replicates;
     cudaStream_t st = ctx->stream;
     int rc;
@@ -400,10 +405,17 @@ int pbk_pvalues(pb_ctx* ctx) {
         if ((rc = ensure_bytes(ctx, &ps, &cap, n_pad * 8))) { ctx->d_maxT_sorted = nullptr; ctx->sorted_cap = 0; return rc; }
         ctx->d_maxT_sorted = (double*)ps; ctx->sorted_cap = cap / 8;
     }
+    {
+        int64_t cap = ctx->stats_cap * (int64_t)sizeof(pb_stat_out);
+        void* ps = ctx->d_stats;
+        if ((rc = ensure_bytes(ctx, &ps, &cap, ctx->S_inf * (int64_t)sizeof(pb_stat_out)))) { ctx->d_stats = nullptr; ctx->stats_cap = 0; return rc; }
+        ctx->d_stats = (pb_stat_out*)ps; ctx->stats_cap = cap / (int64_t)sizeof(pb_stat_out);
+    }
+    if (ctx->sort_blocks_per_sm < 0)   // occupancy belongs to the context's device (contexts of one process may sit on different GPUs / threads)
+        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sort_blocks_per_sm, k4_sort_coop_kernel, 1024, 0));
+    if (alloc_only) return PB_OK;
     const int T = 256;
     {
-        if (ctx->sort_blocks_per_sm < 0)   // occupancy belongs to the context's device (contexts of one process may sit on different GPUs / threads)
-            PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sort_blocks_per_sm, k4_sort_coop_kernel, 1024, 0));
         int64_t grid = std::min<int64_t>(n_pad / BSORT_TILE, (int64_t)std::max(ctx->sort_blocks_per_sm, 1) * ctx->sm_count);
         const unsigned long long* a_maxT = ctx->d_maxT;
         int64_t a_m = m, a_npad = n_pad;
@@ -412,12 +424,6 @@ int pbk_pvalues(pb_ctx* ctx) {
         void* args[] = {(void*)&a_maxT, (void*)&a_m, (void*)&a_npad, (void*)&a_out, (void*)&a_xv};
         PB_CUDA(cudaLaunchCooperativeKernel((const void*)k4_sort_coop_kernel, dim3((unsigned)grid), dim3(1024), args, 0, st));
         ctx->tm.n_launches += 1;
-    }
-    {
-        int64_t cap = ctx->stats_cap * (int64_t)sizeof(pb_stat_out);
-        void* ps = ctx->d_stats;
-        if ((rc = ensure_bytes(ctx, &ps, &cap, ctx->S_inf * (int64_t)sizeof(pb_stat_out)))) { ctx->d_stats = nullptr; ctx->stats_cap = 0; return rc; }
-        ctx->d_stats = (pb_stat_out*)ps; ctx->stats_cap = cap / (int64_t)sizeof(pb_stat_out);
     }
     k4_stats_kernel<<<(unsigned)std::max<int64_t>(1, (ctx->S_inf + T - 1) / T), T, 0, st>>>(ctx->d_inf_site, ctx->S_inf, ctx->d_alleles, ctx->d_pobs, ctx->d_r,
                                                                       ctx->d_maxT_sorted, m, ctx->cfg.site_offset, ctx->site_index_base, ctx->d_stats);

@@ -57,13 +57,19 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
     };
     if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("cudaSetDevice", e);
     {
-        // the label generator is the long pole between K1 and the replicate counts (it is released by an event when K1
-        // has finished): its blocks go first, the short tail kernels of the main stream fill in around them
+        // Priorities.  The label generator is the long pole between K1 and the replicate counts: when it is ONE wave of
+        // blocks (m <= ~190k replicates) it runs on the high-priority stream2, so that its blocks become resident first and
+        // the short tail kernels of the main stream fill in around them.  When it is many waves (C4: m = 1e7) high priority
+        // would starve the tail behind ~11 ms of generator blocks (round 1: ms_events_total 11 ms at C4): it then runs on the
+        // low-priority stream2_lo and the tail's few blocks are scheduled as generator blocks retire.
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        if (getenv("PB_GEN_LOW_PRIORITY")) std::swap(prio_lo, prio_hi);   // experiment knob
-        if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("cudaStreamCreate", e);
-        if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        const int prio_mid = prio_hi < prio_lo - 1 ? prio_lo - 1 : prio_lo;      // numerically lower = more urgent
+        int p_main = prio_mid, p_gen = prio_hi;
+        if (getenv("PB_GEN_LOW_PRIORITY")) std::swap(p_main, p_gen);   // experiment knob
+        if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, p_main)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, p_gen)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithPriority(&ctx->stream2_lo, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("cudaStreamCreate", e);
         if ((e = cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
         if ((e = cudaStreamCreateWithFlags(&ctx->upl, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     }
@@ -97,8 +103,10 @@ extern "C" void pb_destroy(pb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
+    if (ctx->stream2_lo) cudaStreamSynchronize(ctx->stream2_lo);
     if (ctx->upl) cudaStreamSynchronize(ctx->upl);
     free_all(ctx);
+    if (ctx->stream2_lo) cudaStreamDestroy(ctx->stream2_lo);
     if (ctx->ev_upl) cudaEventDestroy(ctx->ev_upl);
     if (ctx->ev_gen_t0) cudaEventDestroy(ctx->ev_gen_t0);
     if (ctx->ev_gen_t1) cudaEventDestroy(ctx->ev_gen_t1);
@@ -316,6 +324,7 @@ extern "C" int pb_set_tree(pb_ctx* ctx, int32_t n_nodes, const int32_t* parent, 
     ctx->events_done = ctx->assoc_done = false;
     if (ctx->stream) PB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->stream2) PB_CUDA(cudaStreamSynchronize(ctx->stream2));
+    if (ctx->stream2_lo) PB_CUDA(cudaStreamSynchronize(ctx->stream2_lo));
     ctx->pregen_valid = false;
     ctx->swept_words = 0;
     ctx->P = 0; ctx->sample_node.clear(); ctx->label.clear();
@@ -346,6 +355,7 @@ extern "C" int pb_set_labels(pb_ctx* ctx, int32_t n_samples, const int32_t* samp
     }
     if (ctx->stream) PB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->stream2) PB_CUDA(cudaStreamSynchronize(ctx->stream2));   // a pre-generated label matrix is stale now
+    if (ctx->stream2_lo) PB_CUDA(cudaStreamSynchronize(ctx->stream2_lo));
     ctx->pregen_valid = false;
     ctx->swept_words = 0;
     ctx->P = n_samples; ctx->n_case = nc; ctx->n_ctrl = nt; ctx->n_miss = nm;
@@ -593,7 +603,9 @@ extern "C" int pb_upload_sync(pb_ctx* ctx) {
     return PB_OK;
 }
 
-extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts) {
+// defer_sites_copy: the per-site records go to the host on the upload stream's sibling copy queue WITHOUT waiting for them
+// (pb_run_events_assoc lets that copy run underneath the association kernels and waits at its own end)
+static int run_events_impl(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts, bool defer_sites_copy) {
     CHECK_CTX(ctx);
     if (ctx->S == 0 || ctx->N == 0) FAIL(ctx, PB_ERR_INVALID, "pb_run_events: tree and planes must be set");
     PB_CUDA(cudaSetDevice(ctx->device));
@@ -638,7 +650,11 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
         if (attempt == 2) FAIL(ctx, PB_ERR_CUDA, "pb_run_events: event list kept overflowing");
     }
     PB_CUDA(cudaEventRecord(ctx->ev[13], ctx->stream));
-    if (per_site) PB_CUDA(cudaMemcpyAsync(per_site, ctx->d_sites, (size_t)ctx->S * sizeof(pb_site_out), cudaMemcpyDeviceToHost, ctx->stream));
+    if (per_site && defer_sites_copy) {       // the tail has been synchronised already (its one readback): d_sites is final
+        PB_CUDA(cudaMemcpyAsync(per_site, ctx->d_sites, (size_t)ctx->S * sizeof(pb_site_out), cudaMemcpyDeviceToHost, ctx->upl));
+    } else if (per_site) {
+        PB_CUDA(cudaMemcpyAsync(per_site, ctx->d_sites, (size_t)ctx->S * sizeof(pb_site_out), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     float t;
     cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]); ctx->tm.ms_events_kernel = t;
@@ -651,6 +667,20 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
     ctx->events_done = true;
     ctx->assoc_done = false;
     return PB_OK;
+}
+
+extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts) {
+    return run_events_impl(ctx, per_site, counts, false);
+}
+
+extern "C" int pb_run_events_assoc(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts, const uint32_t* replay_perms,
+                                   pb_stat_out* per_inf_site, int64_t cap, int64_t* n_inf, double* maxT_sorted) {
+    int rc = run_events_impl(ctx, per_site, counts, true);
+    if (rc) return rc;
+    rc = pb_run_assoc(ctx, replay_perms, per_inf_site, cap, n_inf, maxT_sorted);
+    const cudaError_t e = cudaStreamSynchronize(ctx->upl);      // per_site has arrived (also when the association failed)
+    if (rc == 0 && e != cudaSuccess) { ctx->err = std::string("pb_run_events_assoc: ") + cudaGetErrorString(e); return PB_ERR_CUDA; }
+    return rc;
 }
 
 extern "C" int pb_run_assoc(pb_ctx* ctx, const uint32_t* replay_perms, pb_stat_out* per_inf_site, int64_t cap, int64_t* n_inf,
@@ -667,6 +697,7 @@ extern "C" int pb_run_assoc(pb_ctx* ctx, const uint32_t* replay_perms, pb_stat_o
     if (ctx->S_inf == 0 && ctx->world == 1) FAIL(ctx, PB_ERR_NO_INFORMATIVE, "min_hcount is set too high and has filtered out all segregating sites");
     if (per_inf_site && cap < ctx->S_inf) FAIL(ctx, PB_ERR_INVALID, "pb_run_assoc: per_inf_site too small");
     int rc;
+    if ((rc = pbk_assoc_prepare(ctx))) return rc;       // allocations first: none while the pass is in flight
     if ((rc = pbk_assoc(ctx, replay_perms))) return rc;
     if (per_inf_site && ctx->S_inf)
         PB_CUDA(cudaMemcpyAsync(per_inf_site, ctx->d_stats, (size_t)ctx->S_inf * sizeof(pb_stat_out), cudaMemcpyDeviceToHost, ctx->stream));
@@ -675,6 +706,14 @@ extern "C" int pb_run_assoc(pb_ctx* ctx, const uint32_t* replay_perms, pb_stat_o
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->assoc_done = true;
     return PB_OK;
+}
+
+// internal (pb_group): the allocations of the coming pb_run_assoc, so that a group can finish them on every shard before
+// any shard starts its pass
+int pb_assoc_prepare_internal(pb_ctx* ctx) {
+    if (!ctx || !ctx->events_done || ctx->P == 0) return PB_OK;     // pb_run_assoc reports the call-order error itself
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return PB_ERR_CUDA;
+    return pbk_assoc_prepare(ctx);
 }
 
 extern "C" int pb_run_extras(pb_ctx* ctx, double* exact_pointwise, double* fisher_p) {

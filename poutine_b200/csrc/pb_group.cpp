@@ -15,6 +15,8 @@
 
 #include "pb_internal.h"
 
+int pb_assoc_prepare_internal(pb_ctx* ctx);     // pb_api.cu
+
 namespace {
 
 struct Worker {
@@ -271,6 +273,9 @@ extern "C" int pb_group_run_assoc(pb_group* g, const uint32_t* replay_perms, pb_
     // subset_by_min_hcount over the WHOLE alignment (HC.java:3866-3869): a shard may be empty, the run may not
     if (total == 0) { g->err = "min_hcount is set too high and has filtered out all segregating sites"; return PB_ERR_NO_INFORMATIVE; }
     if (per_inf_site && cap < total) { g->err = "pb_group_run_assoc: per_inf_site too small"; return PB_ERR_INVALID; }
+    // round 1: every allocation of the pass, on every shard; round 2: the pass.  A shard's last kernel waits for its peers
+    // inside the exchange, and an allocation may wait for its device: none may be pending when the first shard gets there.
+    { const int rc = g->all([&](int i) { return pb_assoc_prepare_internal(g->ctx[(size_t)i]); }); if (rc) return rc; }
     return g->all([&](int i) {
         int64_t ni = 0;
         return pb_run_assoc(g->ctx[(size_t)i], replay_perms, per_inf_site ? per_inf_site + off[(size_t)i] : nullptr, g->n_inf[(size_t)i], &ni,

@@ -156,7 +156,8 @@ struct pb_ctx {
     pb_config cfg{};
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;          // label-matrix pre-generation (K3a) alongside the K1 tail
+    cudaStream_t stream2 = nullptr;          // label-matrix pre-generation (K3a) alongside the K1 tail (high priority: one-wave generator)
+    cudaStream_t stream2_lo = nullptr;       // the same at the lowest priority: a many-wave generator must not starve the tail
     cudaStream_t stream3 = nullptr;          // K3b side stream: the few heavy short-list/long-list sweeps run next to the tight sweep
     cudaStream_t upl = nullptr;              // uploads (H2D copies, plane zero-fills, expansion kernels): the copy engine's own queue
     cudaEvent_t ev_upl = nullptr;            // last upload enqueued; the compute stream waits on it
@@ -294,9 +295,10 @@ int pbk_prepare_tail(pb_ctx* ctx);                             // k1_events.cu (
 int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out); // k1_events.cu
 int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms);      // k3_null.cu (+ k4)
 int pbk_pregen_labels(pb_ctx* ctx, bool immediately);          // k3_null.cu
-int pbk_ptable(pb_ctx* ctx);                                   // k4_pvalues.cu
-int pbk_thresholds(pb_ctx* ctx);                               // k4_pvalues.cu
-int pbk_pvalues(pb_ctx* ctx);                                  // k4_pvalues.cu
+int pbk_ptable(pb_ctx* ctx, bool alloc_only = false);          // k4_pvalues.cu
+int pbk_thresholds(pb_ctx* ctx, bool alloc_only = false);      // k4_pvalues.cu
+int pbk_pvalues(pb_ctx* ctx, bool alloc_only = false);         // k4_pvalues.cu
+int pbk_assoc_prepare(pb_ctx* ctx);                            // k3_null.cu: every allocation of pb_run_assoc, up front
 int pbk_extras(pb_ctx* ctx, double* h_exact_pointwise, double* h_fisher);   // k5_extras.cu
 
 // pb_comm.cu: peer-memory exchange

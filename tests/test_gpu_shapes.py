@@ -167,3 +167,34 @@ def test_sweep_under_upload_equals_plain_run(oracle_mod, mode):
         assert_stats_equal(st, or_st)
         np.testing.assert_array_equal(mt.view(np.uint64), or_mt.view(np.uint64))
     hc.close()
+
+
+def test_fused_entry_point_equals_the_two_calls(oracle_mod):
+    """pb_run_events_assoc (both reference entry points in one C call, per-site records copied out underneath the association)
+    must return exactly what pb_run_events + pb_run_assoc return"""
+    tree = synth.yule_tree(400, 31)
+    S = 64 * 300 + 9
+    B0, B1, V = synth.simulate_planes(tree, S, 32, leaf_gap=True, multiallelic_frac=0.02)
+    sn, lab = synth.simulate_phenotypes(tree, 33, na_frac=0.02)
+    m = 1000
+    hc = pb.HomoplasyCounter(num_replicates=m, seed=8)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_planes(B0, B1, V, S, compact=True)
+    ev, cc = hc.count_all_homoplasy_events(compact=False)
+    ev = ev.copy()
+    st, mt = hc.assoc()
+    st, mt = st.copy(), mt.copy()
+    for _ in range(2):
+        ev2, cc2, st2, mt2 = hc.count_all_homoplasy_events_and_assoc()
+        assert cc2 == cc
+        assert ev2.tobytes() == ev.tobytes()
+        np.testing.assert_array_equal(mt2.view(np.uint64), mt.view(np.uint64))
+        assert len(st2) == len(st)
+        for f in st.dtype.names:
+            a, b = st2[f], st[f]
+            if a.dtype.kind == "f":
+                np.testing.assert_array_equal(a.view(np.uint64), b.view(np.uint64), err_msg=f)
+            else:
+                np.testing.assert_array_equal(a, b, err_msg=f)
+    hc.close()
