@@ -72,6 +72,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 #ifndef GEN_THREADS
 #define GEN_THREADS 256       // replicates per block (a multiple of 32; Rw32 assumes tiles padded to 256 replicates)
 #endif
+static_assert(256 % GEN_THREADS == 0 && GEN_THREADS % 32 == 0, "generator blocks tile the 256-replicate padding unit");
 #define GEN_WORDS (GEN_THREADS / 32)
 #define GEN_ROWS 128
 #ifndef GEN_ILP
@@ -773,7 +774,9 @@ static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
 }
 
 static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t nr, cudaStream_t st, int buf) {
-    const unsigned gblocks = (unsigned)((nr + GEN_THREADS - 1) / GEN_THREADS);
+    // the grid covers the tile rounded up to 256 replicates: the padding replicates write zero bits, which the 16-byte
+    // sweeps of K3b rely on (the word behind an odd word count)
+    const unsigned gblocks = (unsigned)(((nr + 255) / 256) * (256 / GEN_THREADS));
     const bool timed = base == 0;        // ms_gen_kernel: the generator's own time for the first tile (events on its stream)
     if (timed) PB_CUDA(cudaEventRecord(ctx->ev_gen_t0, st));
     const int force_replay = getenv("PB_GEN_FORCE_REPLAY") ? 1 : 0;   // every group also goes through the exact Lemire path
@@ -936,7 +939,7 @@ int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms) {
     bool first_gen_timed = false;
     for (int64_t base = 0; base < m; base += tile) {
         const int64_t nr = (m - base < tile) ? (m - base) : tile;
-        const unsigned gblocks = (unsigned)((nr + GEN_THREADS - 1) / GEN_THREADS);
+        const unsigned gblocks = (unsigned)(((nr + 255) / 256) * (256 / GEN_THREADS));
         const int buf = (pl.nbuf == 2) ? (int)((base / tile) & 1) : 0;
         if (ctx->cfg.mode == PB_MODE_REPLAY) {
             const int64_t bytes = nr * (int64_t)ctx->P * 4;       // (buffer sized for a whole tile by k3_alloc)

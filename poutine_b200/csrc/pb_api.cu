@@ -1,6 +1,7 @@
 // C ABI of libpoutine_b200.so — context, uploads, orchestration (see include/poutine_b200.h).
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 
@@ -675,10 +676,20 @@ extern "C" int pb_run_events(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts
 
 extern "C" int pb_run_events_assoc(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts, const uint32_t* replay_perms,
                                    pb_stat_out* per_inf_site, int64_t cap, int64_t* n_inf, double* maxT_sorted) {
+    const bool trace = ctx && ctx->trace_on;
+    timespec t0, t1, t2, t3;
+    if (trace) clock_gettime(CLOCK_MONOTONIC, &t0);
     int rc = run_events_impl(ctx, per_site, counts, true);
     if (rc) return rc;
+    if (trace) clock_gettime(CLOCK_MONOTONIC, &t1);
     rc = pb_run_assoc(ctx, replay_perms, per_inf_site, cap, n_inf, maxT_sorted);
+    if (trace) clock_gettime(CLOCK_MONOTONIC, &t2);
     const cudaError_t e = cudaStreamSynchronize(ctx->upl);      // per_site has arrived (also when the association failed)
+    if (trace) {
+        clock_gettime(CLOCK_MONOTONIC, &t3);
+        auto us = [](const timespec& a, const timespec& b) { return (b.tv_sec - a.tv_sec) * 1e6 + (b.tv_nsec - a.tv_nsec) * 1e-3; };
+        fprintf(stderr, "[poutine_b200 trace] events_assoc host: events %.0f us, assoc %.0f us, wait for per_site %.0f us\n", us(t0, t1), us(t1, t2), us(t2, t3));
+    }
     if (rc == 0 && e != cudaSuccess) { ctx->err = std::string("pb_run_events_assoc: ") + cudaGetErrorString(e); return PB_ERR_CUDA; }
     return rc;
 }

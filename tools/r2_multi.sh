@@ -15,4 +15,4 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --mas
 PB_BENCH_EXCHANGE=nccl timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 5 --warmup 3 > gpurun_out/${tag}_bench_n${n}_nccl.json 2> gpurun_out/${tag}_bench_n${n}_nccl.err
 timeout 600 python bench.py --gpus $n --inproc --steps 5 --warmup 3 > gpurun_out/${tag}_bench_inproc_n${n}.json 2> gpurun_out/${tag}_bench_inproc_n${n}.err
 tail -25 gpurun_out/${tag}_tests.log; cat gpurun_out/${tag}_quick.log; cat gpurun_out/${tag}_l2_peak.json gpurun_out/${tag}_h2d_peak.json
-python tools/brief.py gpurun_out/${tag}_bench*n${n}*.json; tail -3 gpurun_out/${tag}_bench*.err
+python tools/brief.py gpurun_out/${tag}_bench*n${n}*.json; for f in gpurun_out/${tag}_bench*.err; do tail -3 $f; done
