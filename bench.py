@@ -395,7 +395,9 @@ def run_b200(args):
         hc.assoc(fetch=False)
         return hc.timings()
 
-    fused_call = not inproc and not args.two_calls       # pb_run_events_assoc (single context); a group makes the two calls
+    # pb_run_events_assoc (one C call, per-site records copied out underneath the association) measured no faster than the
+    # two calls on this box (profiles/r2_v3_bench_fused.json vs _twocalls.json): the default stays the reference's two calls
+    fused_call = args.fused_call and not inproc
     e2e_parts = {"put_planes": 0.0, "events": 0.0, "assoc": 0.0}
     e2e_steps = []                                       # wall ms of every end-to-end step on this rank (an outlier shows here)
 
@@ -610,7 +612,7 @@ def main():
     ap.add_argument("--replicates", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-planes-only", action="store_true", help="e2e leg uploads three planes even when the input is biallelic")
-    ap.add_argument("--two-calls", action="store_true", help="e2e leg: pb_run_events + pb_run_assoc instead of the fused pb_run_events_assoc")
+    ap.add_argument("--fused-call", action="store_true", help="e2e leg: the fused pb_run_events_assoc instead of pb_run_events + pb_run_assoc")
     ap.add_argument("--inproc", action="store_true", help="--gpus N from ONE process / one host thread (pb_group) instead of torchrun ranks")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="weak: the config's sites per GPU (default); strong: the config's sites over all GPUs (default for C3)")

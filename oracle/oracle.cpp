@@ -123,10 +123,11 @@ static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t
 
 // Labels of the P pheno-file samples in replicate `rep`: a uniformly random arrangement of
 // n_case 1s, n_ctrl 0s and n_miss 2s, drawn sequentially (sample 0 first) without replacement.
-// Draw for sample i: u uniform in [0, P-i) by Lemire's multiply-shift with exact rejection;
+//
+// Spec v1 (P >= 65536).  Draw for sample i: u uniform in [0, P-i) by Lemire's multiply-shift with exact rejection;
 // main stream word i = philox(ctr=(i>>2, rep_lo, rep_hi, 0), key=seed)[i&3]; rejected draws are
 // replaced from the retry stream word q = philox(ctr=(q>>2, rep_lo, rep_hi, 1))[q&3], q = 0,1,..
-void or_philox_labels(uint64_t seed, uint64_t rep, int32_t P, int32_t n_case, int32_t n_ctrl, uint8_t* out) {
+static void philox_labels_v1(uint64_t seed, uint64_t rep, int32_t P, int32_t n_case, int32_t n_ctrl, uint8_t* out) {
     uint32_t rem_case = (uint32_t)n_case, rem_ctrl = (uint32_t)n_ctrl;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t r0 = (uint32_t)rep, r1 = (uint32_t)(rep >> 32);
@@ -155,6 +156,59 @@ void or_philox_labels(uint64_t seed, uint64_t rep, int32_t P, int32_t n_case, in
         else lab = 2;
         out[i] = lab;
     }
+}
+
+// Spec v2 (P < 65536; DESIGN.md "Philox sampling spec").  Four samples per 64-bit word: group g = samples 4g..4g+c-1,
+// c = min(4, P-4g); x = (w[2(g&1)+1] : w[2(g&1)]) of philox(ctr=(g>>1, rep_lo, rep_hi, 0)).  For j < c with R_j = P-4g-j:
+// x * R_j = u_j * 2^64 + x' (u_j = the draw in [0, R_j); x' goes on as x) — Lemire's multiply-shift for the product range
+// at once, in mixed radix.  Exact iff the final x' >= 2^64 mod prod(R_j); otherwise the group is redrawn from retry word q =
+// (rw[2(q&1)+1] : rw[2(q&1)]) of philox(ctr=(q>>1, rep_lo, rep_hi, 1)), q = 0,1,..
+static void philox_labels_v2(uint64_t seed, uint64_t rep, int32_t P, int32_t n_case, int32_t n_ctrl, uint8_t* out) {
+    uint32_t rem_case = (uint32_t)n_case, rem_ctrl = (uint32_t)n_ctrl;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t r0 = (uint32_t)rep, r1 = (uint32_t)(rep >> 32);
+    uint32_t w[4] = {0, 0, 0, 0}, rw[4];
+    uint32_t q = 0;
+    for (int32_t g = 0; 4 * g < P; g++) {
+        if ((g & 1) == 0) philox4x32_10((uint32_t)(g >> 1), r0, r1, 0u, k0, k1, w);
+        uint64_t x = ((uint64_t)w[2 * (g & 1) + 1] << 32) | w[2 * (g & 1)];
+        const int c = std::min<int32_t>(4, P - 4 * g);
+        const uint32_t range = (uint32_t)(P - 4 * g);
+        uint32_t us[4] = {0, 0, 0, 0};
+        for (;;) {
+            uint64_t l = x, prod = 1;
+            uint32_t R = range;
+            for (int j = 0; j < c; j++) {
+                const unsigned __int128 p = (unsigned __int128)l * R;
+                us[j] = (uint32_t)(uint64_t)(p >> 64);
+                l = (uint64_t)p;
+                prod *= R; R--;
+            }
+            if (l < prod) {
+                const uint64_t t = (0ull - prod) % prod;
+                if (l < t) {
+                    philox4x32_10(q >> 1, r0, r1, 1u, k0, k1, rw);
+                    x = ((uint64_t)rw[2 * (q & 1) + 1] << 32) | rw[2 * (q & 1)];
+                    q++;
+                    continue;
+                }
+            }
+            break;
+        }
+        for (int j = 0; j < c; j++) {
+            const uint32_t u = us[j];
+            uint8_t lab;
+            if (u < rem_case) { lab = 1; rem_case--; }
+            else if (u < rem_case + rem_ctrl) { lab = 0; rem_ctrl--; }
+            else lab = 2;
+            out[4 * g + j] = lab;
+        }
+    }
+}
+
+void or_philox_labels(uint64_t seed, uint64_t rep, int32_t P, int32_t n_case, int32_t n_ctrl, uint8_t* out) {
+    if (P < 65536) philox_labels_v2(seed, rep, P, n_case, n_ctrl, out);
+    else philox_labels_v1(seed, rep, P, n_case, n_ctrl, out);
 }
 
 // ---------------------------------------------------------------------------------------------

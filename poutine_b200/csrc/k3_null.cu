@@ -79,9 +79,29 @@ static_assert(256 % GEN_THREADS == 0 && GEN_THREADS % 32 == 0, "generator blocks
 #define GEN_ILP 4          // Philox blocks computed together (GEN_ROWS must be a multiple of 4 * GEN_ILP)
 #endif
 
-// mode 0: Philox (sampling spec in DESIGN.md §K3a; restated by oracle/oracle.cpp or_philox_labels)
-// mode 1: replay (sample j gets label[perms[rep*P + j]])
+// MODE 0: Philox, batched draws (P < 65536; sampling spec v2 in DESIGN.md §K3a, restated by oracle/oracle.cpp or_philox_labels)
+// MODE 1: replay (sample j gets label[perms[rep*P + j]])
+// MODE 2: Philox, one 32-bit word per draw (P >= 65536: four ranges would overflow a 64-bit product; spec v1)
 // One thread = one replicate; a warp ballot turns 32 replicates' labels of one sample into a matrix word.
+//
+// Spec v2.  Replicate `rep` labels samples 0..P-1 sequentially without replacement, four at a time from one 64-bit word:
+// group g = samples 4g..4g+c-1 (c = min(4, P - 4g)), x = (w[2(g&1)+1] : w[2(g&1)]) of Philox4x32-10(ctr = (g>>1, rep_lo,
+// rep_hi, 0), key = seed).  For j = 0..c-1 with R_j = P - 4g - j:  x * R_j = u_j * 2^64 + x'  (u_j = the draw in [0, R_j),
+// x' carries on as x) — Lemire's multiply-shift applied to the product range R_0..R_{c-1} at once: floor(x * prod / 2^64) in
+// mixed radix.  The group is exact-uniform iff the final x' >= 2^64 mod prod(R_j); otherwise x is replaced by the next word of
+// the retry stream (word q of Philox(ctr = (q>>1, rep_lo, rep_hi, 1)), q = 0, 1, ...) and the group is drawn again
+// (probability < prod / 2^64 < 2^-11 per group for P = 5000).  u_j < cases_left -> case, < cases_left + controls_left ->
+// control, else missing.  Half the Philox blocks and one multiply less per draw than spec v1: the generator is bound by
+// the integer-multiply pipe (profiles/r2_k3a_gen_C2_ncu.txt).
+__device__ __forceinline__ void mul64x32(uint32_t& xl, uint32_t& xh, uint32_t R, uint32_t& u) {
+    const uint64_t a = (uint64_t)xl * R;
+    const uint64_t b = (uint64_t)xh * R + (a >> 32);
+    u = (uint32_t)(b >> 32); xl = (uint32_t)a; xh = (uint32_t)b;
+}
+
+#define GEN_PASS (8 * GEN_ILP)   // samples per pass of the batched generator: GEN_ILP Philox blocks x 2 words x 4 draws
+static_assert(GEN_ROWS % GEN_PASS == 0 && GEN_ROWS % (4 * GEN_ILP) == 0, "a staging tile is a whole number of passes");
+
 template <int MODE, bool MISS>
 __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
                                                              int32_t n_ctrl, const uint8_t* __restrict__ label,
@@ -95,19 +115,35 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
     const uint64_t rep = (uint64_t)(rep_base + rep_local);
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), r0 = (uint32_t)rep, r1 = (uint32_t)(rep >> 32);
     uint32_t rem_case = (uint32_t)n_case, rem_ctrl = (uint32_t)n_ctrl, q = 0;
-    if (MODE == 0 && !MISS && !active) rem_case = 0;     // padding replicates of the last block never draw a case: bits stay 0
+    if (MODE != 1 && !MISS && !active) rem_case = 0;     // padding replicates of the last block never draw a case: bits stay 0
     const uint32_t* prow = (MODE == 1 && active) ? perms + rep_local * (int64_t)P : nullptr;
-    uint32_t range = (uint32_t)P;                         // samples not yet labelled (Philox mode)
+    uint32_t range = (uint32_t)P;                         // samples not yet labelled (Philox modes)
     // replay mode: the caller's rows are checked while they are consumed — an index >= P is clamped and flagged (it would be an
     // out-of-bounds read of label[]), and a row whose index sum / sum of squares is not a permutation's is flagged as well (a
     // repeated index changes the replicate's case / control totals).  pb_run_assoc returns PB_ERR_INVALID on either.
     uint64_t psum = 0, psq = 0;
     bool pbad = false;
 
-    // one sample: Lemire draw in [0, range) with exact rejection, label, ballot -> one 32-replicate word per warp
-    auto draw = [&](uint32_t x, int i, int row) {
+    // label of one draw u (Philox modes) -> one 32-replicate word per warp and matrix
+    auto emit = [&](uint32_t u, int row) {
         uint32_t lab;
-        if (MODE == 0) {
+        if (!MISS) {                      // no missing labels: whatever is not a case is a control
+            lab = u < rem_case ? 1u : 0u;
+            rem_case -= lab;
+        } else if (u < rem_case) { lab = 1; rem_case--; }
+        else if (u < rem_case + rem_ctrl) { lab = 0; rem_ctrl--; }
+        else lab = 2;
+        const uint32_t bc = !MISS ? __ballot_sync(0xffffffffu, lab != 0) : __ballot_sync(0xffffffffu, active && lab == 1);
+        if (lane == 0) sc[row][warp] = bc;
+        if (MISS) {
+            const uint32_t bm = __ballot_sync(0xffffffffu, active && lab == 2);
+            if (lane == 0) sm[row][warp] = bm;
+        }
+    };
+
+    // spec v1 / replay: one sample
+    auto draw = [&](uint32_t x, int i, int row) {
+        if (MODE == 2) {
             uint64_t prod = (uint64_t)x * range;
             uint32_t lo = (uint32_t)prod;
             if (lo < range) {  // taken with probability < range / 2^32
@@ -122,72 +158,119 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
                 }
             }
             range--;
-            const uint32_t u = (uint32_t)(prod >> 32);
-            if (!MISS) {                      // no missing labels: whatever is not a case is a control
-                lab = u < rem_case ? 1u : 0u;
-                rem_case -= lab;
-            } else if (u < rem_case) { lab = 1; rem_case--; }
-            else if (u < rem_case + rem_ctrl) { lab = 0; rem_ctrl--; }
-            else lab = 2;
+            emit((uint32_t)(prod >> 32), row);
         } else {
             uint32_t idx = active ? prow[i] : 0u;
             if (idx >= (uint32_t)P) { pbad = true; idx = 0; }
             psum += idx; psq += (uint64_t)idx * idx;
-            lab = active ? label[idx] : 0;
-        }
-        const uint32_t bc = (MODE == 0 && !MISS) ? __ballot_sync(0xffffffffu, lab != 0) : __ballot_sync(0xffffffffu, active && lab == 1);
-        if (lane == 0) sc[row][warp] = bc;
-        if (MISS) {
-            const uint32_t bm = __ballot_sync(0xffffffffu, active && lab == 2);
-            if (lane == 0) sm[row][warp] = bm;
+            const uint32_t lab = active ? label[idx] : 0;
+            const uint32_t bc = __ballot_sync(0xffffffffu, active && lab == 1);
+            if (lane == 0) sc[row][warp] = bc;
+            if (MISS) {
+                const uint32_t bm = __ballot_sync(0xffffffffu, active && lab == 2);
+                if (lane == 0) sm[row][warp] = bm;
+            }
         }
     };
 
-    for (int i0 = 0; i0 < P; i0 += GEN_ROWS) {          // GEN_ROWS is a multiple of 4 * GEN_ILP
-        const int rows = min(GEN_ROWS, P - i0);
-        for (int ii = 0; ii < rows; ii += 4 * GEN_ILP) {
-            // GEN_ILP independent Philox blocks per pass: their 10-round dependent chains interleave in the pipeline
-            uint32_t w[GEN_ILP][4];
+    // spec v2: one 64-bit word -> `count` (1..4, warp-uniform) samples, exact rejection
+    auto draw_word = [&](uint32_t xl, uint32_t xh, int row, int count) {
+        uint32_t us[4] = {0, 0, 0, 0};
+        for (;;) {
+            uint32_t l = xl, h = xh, R = range;
+            uint64_t prod = 1;
 #pragma unroll
-            for (int q4 = 0; q4 < GEN_ILP; q4++) {
-                w[q4][0] = w[q4][1] = w[q4][2] = w[q4][3] = 0;
-                if (MODE == 0) philox4x32_10((uint32_t)((i0 + ii) >> 2) + q4, r0, r1, 0u, k0, k1, w[q4]);
-            }
-            if (MODE == 0 && !MISS && ii + 4 * GEN_ILP <= rows) {
-                // Full group, binary labels: the draws run without their per-draw rejection test.  A Lemire retry is needed only
-                // if some low product word is below its range (probability < range / 2^32 per draw): the group keeps the minimum
-                // low word, one vote per group checks it against the group's largest range, and the rare hit replays the whole
-                // group through the exact path from the saved state (same words are overwritten).  7 instead of 14 instructions
-                // per draw around the Philox rounds.
-                const uint32_t rem0 = rem_case, range0 = range;
-                uint32_t mn = 0xffffffffu;
-#pragma unroll
-                for (int jj = 0; jj < 4 * GEN_ILP; jj++) {
-                    const uint64_t prod = (uint64_t)w[jj >> 2][jj & 3] * range;
-                    mn = min(mn, (uint32_t)prod);
-                    range--;
-                    uint32_t bc;
-                    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %0;\n\t@q add.u32 %0, %0, -1;\n\tvote.sync.ballot.b32 %1, q, 0xffffffff;\n\t}"
-                                 : "+r"(rem_case), "=r"(bc) : "r"((uint32_t)(prod >> 32)));
-                    sc[ii + jj][warp] = bc;               // every lane stores the same word: no lane test, one broadcast store
+            for (int j = 0; j < 4; j++)
+                if (j < count) { mul64x32(l, h, R, us[j]); prod *= R; R--; }
+            const uint64_t lo = ((uint64_t)h << 32) | l;
+            if (lo < prod) {                               // probability < prod / 2^64
+                const uint64_t t = (0ull - prod) % prod;   // 2^64 mod prod
+                if (lo < t) {
+                    uint32_t rw[4];
+                    philox4x32_10(q >> 1, r0, r1, 1u, k0, k1, rw);
+                    xl = (q & 1) ? rw[2] : rw[0]; xh = (q & 1) ? rw[3] : rw[1];
+                    q++;
+                    continue;
                 }
-                if (__any_sync(0xffffffffu, mn < range0) || force_replay) {   // force_replay: test hook (PB_GEN_FORCE_REPLAY)
-                    rem_case = rem0; range = range0;
-#pragma unroll 1
-                    for (int q4 = 0; q4 < GEN_ILP; q4++) {      // cold path: the Philox words are recomputed, not kept addressable
-                        uint32_t ww[4];
-                        philox4x32_10((uint32_t)((i0 + ii) >> 2) + q4, r0, r1, 0u, k0, k1, ww);
+            }
+            break;
+        }
 #pragma unroll
-                        for (int j = 0; j < 4; j++) draw(ww[j], i0 + ii + 4 * q4 + j, ii + 4 * q4 + j);
+        for (int j = 0; j < 4; j++)
+            if (j < count) { range--; emit(us[j], row + j); }
+    };
+
+    for (int i0 = 0; i0 < P; i0 += GEN_ROWS) {
+        const int rows = min(GEN_ROWS, P - i0);
+        if (MODE == 0) {
+            for (int ii = 0; ii < rows; ii += GEN_PASS) {
+                // GEN_ILP independent Philox blocks per pass: their 10-round dependent chains interleave in the pipeline
+                uint32_t w[GEN_ILP][4];
+#pragma unroll
+                for (int q4 = 0; q4 < GEN_ILP; q4++) philox4x32_10((uint32_t)((i0 + ii) >> 3) + q4, r0, r1, 0u, k0, k1, w[q4]);
+                if (!MISS && ii + GEN_PASS <= rows) {
+                    // Full pass, binary labels: the draws run without their per-word rejection test.  A retry is needed only if
+                    // some word's final low part is below its range product (probability < prod / 2^64 per word): the pass keeps
+                    // the minimum low part, one vote checks it against the pass's largest product, and the rare hit replays the
+                    // whole pass through the exact path from the saved state (same words are overwritten).
+                    const uint32_t rem0 = rem_case, range0 = range;
+                    uint64_t mn = ~0ull;
+#pragma unroll
+                    for (int q4 = 0; q4 < GEN_ILP; q4++) {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            uint32_t xl = w[q4][2 * h], xh = w[q4][2 * h + 1];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                uint32_t u, bc;
+                                mul64x32(xl, xh, range, u);
+                                range--;
+                                asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %0;\n\t@q add.u32 %0, %0, -1;\n\tvote.sync.ballot.b32 %1, q, 0xffffffff;\n\t}"
+                                             : "+r"(rem_case), "=r"(bc) : "r"(u));
+                                sc[ii + 8 * q4 + 4 * h + j][warp] = bc;   // every lane stores the same word: no lane test, one broadcast store
+                            }
+                            mn = min(mn, ((uint64_t)xh << 32) | xl);
+                        }
+                    }
+                    const uint64_t prodmax = (uint64_t)range0 * (range0 - 1) * (uint64_t)(range0 - 2) * (range0 - 3);   // range0 >= GEN_PASS; < 2^64 for P < 65536
+                    if (__any_sync(0xffffffffu, mn < prodmax) || force_replay) {   // force_replay: test hook (PB_GEN_FORCE_REPLAY)
+                        rem_case = rem0; range = range0;
+#pragma unroll 1
+                        for (int q4 = 0; q4 < GEN_ILP; q4++) {      // cold path: the Philox words are recomputed, not kept addressable
+                            uint32_t ww[4];
+                            philox4x32_10((uint32_t)((i0 + ii) >> 3) + q4, r0, r1, 0u, k0, k1, ww);
+                            draw_word(ww[0], ww[1], ii + 8 * q4, 4);
+                            draw_word(ww[2], ww[3], ii + 8 * q4 + 4, 4);
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int q4 = 0; q4 < GEN_ILP; q4++) {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int row = ii + 8 * q4 + 4 * h;
+                            const int count = min(4, rows - row);     // block-uniform
+                            if (count > 0) draw_word(w[q4][2 * h], w[q4][2 * h + 1], row, count);
+                        }
                     }
                 }
-            } else if (ii + 4 * GEN_ILP <= rows) {        // full group: no per-sample bounds checks (block-uniform)
+            }
+        } else {
+            for (int ii = 0; ii < rows; ii += 4 * GEN_ILP) {
+                uint32_t w[GEN_ILP][4];
 #pragma unroll
-                for (int jj = 0; jj < 4 * GEN_ILP; jj++) draw(w[jj >> 2][jj & 3], i0 + ii + jj, ii + jj);
-            } else {
+                for (int q4 = 0; q4 < GEN_ILP; q4++) {
+                    w[q4][0] = w[q4][1] = w[q4][2] = w[q4][3] = 0;
+                    if (MODE == 2) philox4x32_10((uint32_t)((i0 + ii) >> 2) + q4, r0, r1, 0u, k0, k1, w[q4]);
+                }
+                if (ii + 4 * GEN_ILP <= rows) {        // full group: no per-sample bounds checks (block-uniform)
 #pragma unroll
-                for (int jj = 0; jj < 4 * GEN_ILP; jj++)
-                    if (ii + jj < rows) draw(w[jj >> 2][jj & 3], i0 + ii + jj, ii + jj);
+                    for (int jj = 0; jj < 4 * GEN_ILP; jj++) draw(w[jj >> 2][jj & 3], i0 + ii + jj, ii + jj);
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 4 * GEN_ILP; jj++)
+                        if (ii + jj < rows) draw(w[jj >> 2][jj & 3], i0 + ii + jj, ii + jj);
+                }
             }
         }
         __syncthreads();
@@ -780,13 +863,17 @@ static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t
     const bool timed = base == 0;        // ms_gen_kernel: the generator's own time for the first tile (events on its stream)
     if (timed) PB_CUDA(cudaEventRecord(ctx->ev_gen_t0, st));
     const int force_replay = getenv("PB_GEN_FORCE_REPLAY") ? 1 : 0;   // every group also goes through the exact Lemire path
-    if (pl.has_miss)
-        k3_gen_kernel<0, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr,
-                                                               (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words),
-                                                               (uint32_t*)(ctx->d_Xmiss + buf * pl.buf_words), pl.Rw32);
+    uint32_t* xc = (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words);
+    uint32_t* xm = pl.has_miss ? (uint32_t*)(ctx->d_Xmiss + buf * pl.buf_words) : nullptr;
+    const bool batched = ctx->P < 65536;      // spec v2 (four draws per 64-bit word); spec v1 above that
+    if (pl.has_miss && batched)
+        k3_gen_kernel<0, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, xm, pl.Rw32, force_replay);
+    else if (batched)
+        k3_gen_kernel<0, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, nullptr, pl.Rw32, force_replay);
+    else if (pl.has_miss)
+        k3_gen_kernel<2, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, xm, pl.Rw32);
     else
-        k3_gen_kernel<0, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr,
-                                                                (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words), nullptr, pl.Rw32, force_replay);
+        k3_gen_kernel<2, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, nullptr, pl.Rw32);
     if (timed) { PB_CUDA(cudaEventRecord(ctx->ev_gen_t1, st)); ctx->gen_timed = true; }
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
@@ -808,7 +895,7 @@ int pbk_pregen_labels(pb_ctx* ctx, bool immediately) {
     const int64_t m = ctx->cfg.n_replicates;
     const int64_t nr = m < pl.tile ? m : pl.tile;
     // one wave of generator blocks -> the high-priority stream (resident before the tail); many waves -> the low-priority one
-    const bool many_waves = (nr + GEN_THREADS - 1) / GEN_THREADS > (int64_t)ctx->sm_count * 5 && !getenv("PB_GEN_ALWAYS_HIGH");
+    const bool many_waves = (nr + 31) / 32 > (int64_t)ctx->sm_count * 40 && !getenv("PB_GEN_ALWAYS_HIGH");   // > 40 generator warps per SM
     cudaStream_t gs = many_waves ? ctx->stream2_lo : ctx->stream2;
     // default: the generator starts when K1 has finished.  Experiments: PB_PREGEN_EARLY — it is ordered behind the previous
     // step only (ev[0] is recorded just before the K1 launch), so the low-priority stream may pick up SM slots while

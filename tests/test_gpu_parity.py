@@ -889,3 +889,26 @@ def test_large_properties_and_slice_parity(oracle_mod):
     sd = np.sqrt(np.maximum(exact * (1 - exact), 1e-12) / m)
     # the statistic is f(n,k) <= f(n,k_obs) <=> k >= k_obs when f(n,.) is strictly decreasing (true for 0<p<1)
     assert np.all(np.abs(mc - exact) < 6 * sd + 2.0 / m)
+
+
+def test_assoc_philox_many_samples_uses_spec_v1(oracle_mod):
+    """P >= 65536 pheno rows: four draw ranges no longer fit one 64-bit product, so the label generator falls back to one
+    32-bit word per draw (sampling spec v1); the oracle restates both specs and switches at the same P."""
+    tree = synth.yule_tree(66000, 3)
+    S, m = 64 * 3 + 7, 192
+    chars = synth.planes_to_chars(*synth.simulate_planes(tree, S, 4), 0, S)
+    sn, lab = synth.simulate_phenotypes(tree, 5, na_frac=0.01)
+    assert len(lab) >= 65536
+    o = oracle_mod.Oracle(tree.parent, tree.leaf_nodes)
+    o.count_all_homoplasy_events(chars, n_threads=8)
+    st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=None, seed=12345, n_threads=8)
+    hc = pb.HomoplasyCounter(num_replicates=m, seed=12345)
+    hc.set_tree(tree.parent, tree.is_leaf)
+    hc.set_phenos(sn, lab)
+    hc.set_seg_sites(chars)
+    hc.count_all_homoplasy_events()
+    g_st, g_mt = hc.assoc()
+    assert_stats_equal(g_st, st)
+    np.testing.assert_array_equal(g_mt.view(np.uint64), mt_s.view(np.uint64))
+    np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), mt_u.view(np.uint64))
+    hc.close()
