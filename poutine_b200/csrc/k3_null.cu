@@ -93,10 +93,19 @@ static_assert(256 % GEN_THREADS == 0 && GEN_THREADS % 32 == 0, "generator blocks
 // (probability < prod / 2^64 < 2^-11 per group for P = 5000).  u_j < cases_left -> case, < cases_left + controls_left ->
 // control, else missing.  Half the Philox blocks and one multiply less per draw than spec v1: the generator is bound by
 // the integer-multiply pipe (profiles/r2_k3a_gen_C2_ncu.txt).
+// (xh:xl) * R = u * 2^64 + (xh':xl').  Two 32x32->64 multiplies; the cross carry goes through the integer ALU (add.cc / addc),
+// not through a 64-bit multiply-add: the generator is bound by the multiply pipe, and a mad.wide with a 64-bit addend also
+// costs a register move on that pipe to build the addend's zero high word.
 __device__ __forceinline__ void mul64x32(uint32_t& xl, uint32_t& xh, uint32_t R, uint32_t& u) {
-    const uint64_t a = (uint64_t)xl * R;
-    const uint64_t b = (uint64_t)xh * R + (a >> 32);
-    u = (uint32_t)(b >> 32); xl = (uint32_t)a; xh = (uint32_t)b;
+    uint32_t a_lo, a_hi, b_lo, b_hi;
+    asm("{\n\t.reg .u64 a, b;\n\t"
+        "mul.wide.u32 a, %4, %6;\n\t"
+        "mul.wide.u32 b, %5, %6;\n\t"
+        "mov.b64 {%0, %1}, a;\n\t"
+        "mov.b64 {%2, %3}, b;\n\t}"
+        : "=r"(a_lo), "=r"(a_hi), "=r"(b_lo), "=r"(b_hi) : "r"(xl), "r"(xh), "r"(R));
+    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+r"(b_lo), "+r"(b_hi) : "r"(a_hi));
+    u = b_hi; xl = a_lo; xh = b_lo;
 }
 
 #define GEN_PASS (8 * GEN_ILP)   // samples per pass of the batched generator: GEN_ILP Philox blocks x 2 words x 4 draws
