@@ -154,10 +154,10 @@ __global__ void k4_classify_kernel(AlleleMeta* __restrict__ alleles, int64_t n_s
         }
     }
     my_rows = __reduce_add_sync(0xffffffffu, my_rows);
-    if ((threadIdx.x & 31) == 0 && my_rows) atomicAdd(swept_rows, (unsigned long long)my_rows);
     // list append: one global atomic per class per BLOCK (per-warp ballots -> block prefix in shared memory)
-    __shared__ unsigned int s_wcount[8][4], s_base[4];
+    __shared__ unsigned int s_wcount[8][4], s_base[4], s_rows[8];
     const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (lane == 0) s_rows[warp] = my_rows;
     unsigned int my_rank = 0;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -170,6 +170,11 @@ __global__ void k4_classify_kernel(AlleleMeta* __restrict__ alleles, int64_t n_s
         unsigned int tot = 0;
         for (int w = 0; w < 8; w++) { const unsigned int t = s_wcount[w][threadIdx.x]; s_wcount[w][threadIdx.x] = tot; tot += t; }
         s_base[threadIdx.x] = tot ? atomicAdd(counts + threadIdx.x, tot) : 0u;
+    }
+    if (threadIdx.x == 32) {      // one atomic per block (all blocks hit the same word)
+        unsigned long long rows = 0;
+        for (int w = 0; w < 8; w++) rows += s_rows[w];
+        if (rows) atomicAdd(swept_rows, rows);
     }
     __syncthreads();
     if (cls >= 0) lists[(int64_t)cls * n_slots + s_base[cls] + s_wcount[warp][cls] + my_rank] = (int32_t)a;
