@@ -197,7 +197,7 @@ def bench_config(args, cfg, S, m, tree, world, scaling="weak", launch="one proce
                          % (tree.n_nodes * ((S + 63) // 64) * 8 / 1e9, 3 * tree.n_nodes * ((S + 63) // 64) * 8 / 1e9)}
 
 
-def k3_rooflines(tm, parts, m, P, has_miss):
+def k3_rooflines(tm, parts, m, P, has_miss, n_shards=1):
     """The two resampling kernels against their own ceilings (ncu captures under profiles/r2_k3*):
     K3a (label generator) is bound by the integer-multiply (fmaheavy) pipe — its ceiling is an instruction-issue one, the
     fraction comes from the committed capture; K3b (replicate counting) is bound by L2 -> SM bandwidth: algorithmic bytes =
@@ -212,7 +212,7 @@ def k3_rooflines(tm, parts, m, P, has_miss):
     l2 = load("r2_l2_peak.json")
     ceil = load("k3_ceilings.json")
     l2_peak = l2.get("l2_read_gbs_16B_per_lane")
-    swept_bytes = float(tm.get("n_swept_rows", 0)) * (m / 8.0) * (2 if has_miss else 1)
+    swept_bytes = float(tm.get("n_swept_rows", 0)) / n_shards * (m / 8.0) * (2 if has_miss else 1)   # per GPU (a group sums its shards)
     out = {"k3a_label_generator": {"bound": "integer-multiply pipe (fmaheavy): Philox4x32-10 + Lemire draws",
                                    "draws_per_s": (m * P) / (parts["ms_gen_kernel"] / 1e3) if parts.get("ms_gen_kernel") else None,
                                    "ms": parts.get("ms_gen_kernel"),
@@ -346,7 +346,7 @@ def run_b200(args):
     hc.set_sites(S_mine)
     exchange = "none (one GPU)"
     if inproc:
-        exchange = "peer memory, fused into K4's sort kernel (pb_group, one process)"
+        exchange = "peer memory, fused into K4's sort kernel (pb_group, one process); label matrix drawn 1/%d per shard and gathered over NVLink" % n_gpus
     elif world > 1:
         want = os.environ.get("PB_BENCH_EXCHANGE", "p2p")
         ok = 0
@@ -362,6 +362,22 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if t.item() >= 1:
             exchange = "peer memory (cudaIpc), fused into K4's sort kernel"
+            if os.environ.get("PB_BENCH_LABEL_SHARING", "1") != "0":
+                # the shards sweep the same label matrix: map the matrices too, each rank draws 1/world of it
+                ok2 = 0
+                try:
+                    blobs = [None] * world
+                    dist.all_gather_object(blobs, hc.comm_export_labels())
+                    hc.comm_connect_labels(blobs)
+                    ok2 = 1
+                except pb.PoutineError as e:
+                    print("bench.py: rank %d: label sharing unavailable (%s)" % (rank, e), file=sys.stderr)
+                t2 = torch.tensor([float(ok2)], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t2, op=dist.ReduceOp.MIN)
+                if t2.item() >= 1:
+                    exchange += "; label matrix drawn 1/%d per rank and gathered over NVLink" % world
+                else:
+                    raise SystemExit("bench.py: label sharing connected on some ranks only")
         else:
             ids = [pb.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
@@ -471,7 +487,7 @@ def run_b200(args):
 
     dev_ms, wall_ms, launches, parts, roofline, tm = timed_resident()
     value = total_sites * args.steps / (dev_ms / 1e3)
-    roofline_k3 = k3_rooflines(tm, parts, m, len(lab), has_miss)
+    roofline_k3 = k3_rooflines(tm, parts, m, len(lab), has_miss, n_shards)
 
     # ---- timed: end to end through the public API with host buffers ------------------------------------
     for _ in range(min(args.warmup, 3)):
@@ -579,7 +595,7 @@ def run_b200(args):
                 "roofline": roofline, "roofline_k3": roofline_k3, "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "parity_checked": parity["parity_checked"], "parity_sites": parity["parity_sites"], "parity": parity,
                 "host_packer": host_packer,
-                "exchange": exchange,
+                "exchange": exchange, "gen_shard_frac": float(tm.get("gen_shard_frac", 1.0)),
                 "memoised": "the binomial table f[n][k] (a pure function of n_max and the case fraction) is kept across passes, as the "
                             "reference's own cache does within a run (HC.java:4196-4280); everything else is recomputed every step",
                 "replicate_draws_per_sec": n_draws * args.steps / (dev_ms / 1e3),

@@ -120,7 +120,7 @@ typedef struct {
     int64_t eager_words;      /* site words whose sweep ran ahead of pb_run_events, underneath the uploads (0: none) */
     int64_t n_swept_rows;     /* K3b: label-matrix rows read per replicate word, summed over the swept alleles (x m/8 B = its L2 traffic) */
     float ms_gen_kernel;      /* K3a: the label generator's own time for the first replicate tile (events on its stream) */
-    float reserved0;
+    float gen_shard_frac;     /* fraction of the label matrix this context drew itself: 1, or 1/world when the shards share it */
 } pb_timings;
 
 int pb_create(const pb_config* cfg, pb_ctx** out);
@@ -228,6 +228,12 @@ int pb_stopwatch_ms(pb_ctx* ctx, float* ms);
  *      For boxes where (2) is not available (cudaIpcOpenMemHandle refused: pb_comm_connect returns PB_ERR_NCCL). */
 int pb_comm_export(pb_ctx* ctx, void* handle64);
 int pb_comm_connect(pb_ctx* ctx, const void* handles /* world x 64 bytes, rank order */, int32_t rank, int32_t world);
+/* Optional, after pb_set_labels and pb_comm_connect (Philox mode): map the ranks' label matrices as well.  Every shard
+ * sweeps the SAME label matrix, so each rank then draws only 1/world of its replicate columns and pulls the rest from its
+ * peers over NVLink (pb_timings.gen_shard_frac).  Same results.  Gather the 128-byte blobs in rank order like the handles.
+ * (A pb_group does this by itself.) */
+int pb_comm_export_labels(pb_ctx* ctx, void* blob128);
+int pb_comm_connect_labels(pb_ctx* ctx, const void* blobs /* world x 128 bytes, rank order */);
 int pb_comm_unique_id(void* id128);
 int pb_comm_init(pb_ctx* ctx, const void* id128, int32_t rank, int32_t world);
 

@@ -354,6 +354,19 @@ class HomoplasyCounter:
         buf = C.create_string_buffer(blob, len(blob))
         self._check(_lib.lib().pb_comm_connect(self._h, buf, rank, world))
 
+    def comm_export_labels(self) -> bytes:
+        """label sharing, step 1 (after set_phenos and comm_connect): the 128-byte blob of this rank's label matrices"""
+        buf = C.create_string_buffer(128)
+        self._check(_lib.lib().pb_comm_export_labels(self._h, buf))
+        return buf.raw
+
+    def comm_connect_labels(self, blobs):
+        """label sharing, step 2: map every rank's label matrices (blobs in rank order): each rank then draws 1/world of the
+        label matrix and pulls the rest from its peers (timings()["gen_shard_frac"])"""
+        blob = b"".join(blobs)
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(_lib.lib().pb_comm_connect_labels(self._h, buf))
+
     @classmethod
     def _view(cls, handle, m, n_sites, n_nodes, n_samples):
         """a non-owning wrapper around a context that belongs to a group (introspection only)"""
@@ -420,7 +433,7 @@ class HomoplasyCounterGroup(HomoplasyCounter):
     def comm_init(self, *a):
         raise PoutineError(-1, "a group connects its own contexts")
 
-    comm_export = comm_connect = comm_init
+    comm_export = comm_connect = comm_export_labels = comm_connect_labels = comm_init
 
 
 def comm_unique_id() -> bytes:

@@ -116,10 +116,11 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
                                                              int32_t n_ctrl, const uint8_t* __restrict__ label,
                                                              const uint32_t* __restrict__ perms, uint32_t* __restrict__ Xc32,
                                                              uint32_t* __restrict__ Xm32, int64_t Rw32, int force_replay = 0,
-                                                             unsigned long long* __restrict__ replay_err = nullptr) {
+                                                             unsigned long long* __restrict__ replay_err = nullptr, int64_t blk0 = 0) {
     __shared__ uint32_t sc[GEN_ROWS][GEN_WORDS], sm[MISS ? GEN_ROWS : 1][GEN_WORDS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t rep_local = (int64_t)blockIdx.x * GEN_THREADS + tid;
+    const int64_t gblk = (int64_t)blockIdx.x + blk0;      // blk0: a rank of a sharded run generates only its own slice of the tile's replicates
+    const int64_t rep_local = gblk * GEN_THREADS + tid;
     const bool active = rep_local < n_reps;
     const uint64_t rep = (uint64_t)(rep_base + rep_local);
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), r0 = (uint32_t)rep, r1 = (uint32_t)(rep >> 32);
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
         __syncthreads();
         for (int t = tid; t < rows * GEN_WORDS; t += GEN_THREADS) {
             const int row = t / GEN_WORDS, wd = t % GEN_WORDS;
-            const int64_t o = (int64_t)(i0 + row) * Rw32 + (int64_t)blockIdx.x * GEN_WORDS + wd;
+            const int64_t o = (int64_t)(i0 + row) * Rw32 + gblk * GEN_WORDS + wd;
             Xc32[o] = sc[row][wd];
             if (MISS) Xm32[o] = sm[row][wd];
         }
@@ -868,24 +869,42 @@ static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
 static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t nr, cudaStream_t st, int buf) {
     // the grid covers the tile rounded up to 256 replicates: the padding replicates write zero bits, which the 16-byte
     // sweeps of K3b rely on (the word behind an odd word count)
-    const unsigned gblocks = (unsigned)(((nr + 255) / 256) * (256 / GEN_THREADS));
+    int64_t blk0 = 0, gblocks = ((nr + 255) / 256) * (256 / GEN_THREADS);
+    // Sharded run with mapped label matrices (pb_comm.cu, "label sharing"): every rank needs the SAME matrix, so each generates
+    // 1/world of the tile's replicate columns and pulls the rest from its peers over NVLink instead of drawing all of it.
+    const bool shared = pbx_labels_shared(ctx, pl.buf_words * 8 * pl.nbuf);
+    int rc;
+    if (shared) {
+        if ((rc = pbx_labels_begin(ctx, buf, st))) return rc;          // peers have pulled what this buffer held before
+        const int64_t total = gblocks;
+        blk0 = total * ctx->rank / ctx->world;
+        gblocks = total * (ctx->rank + 1) / ctx->world - blk0;
+    }
     const bool timed = base == 0;        // ms_gen_kernel: the generator's own time for the first tile (events on its stream)
     if (timed) PB_CUDA(cudaEventRecord(ctx->ev_gen_t0, st));
     const int force_replay = getenv("PB_GEN_FORCE_REPLAY") ? 1 : 0;   // every group also goes through the exact Lemire path
     uint32_t* xc = (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words);
     uint32_t* xm = pl.has_miss ? (uint32_t*)(ctx->d_Xmiss + buf * pl.buf_words) : nullptr;
     const bool batched = ctx->P < 65536;      // spec v2 (four draws per 64-bit word); spec v1 above that
-    if (pl.has_miss && batched)
-        k3_gen_kernel<0, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, xm, pl.Rw32, force_replay);
+    const unsigned g = (unsigned)gblocks;
+    if (g == 0) {
+    } else if (pl.has_miss && batched)
+        k3_gen_kernel<0, true><<<g, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, xm, pl.Rw32, force_replay, nullptr, blk0);
     else if (batched)
-        k3_gen_kernel<0, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, nullptr, pl.Rw32, force_replay);
+        k3_gen_kernel<0, false><<<g, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, nullptr, pl.Rw32, force_replay, nullptr, blk0);
     else if (pl.has_miss)
-        k3_gen_kernel<2, true><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, xm, pl.Rw32);
+        k3_gen_kernel<2, true><<<g, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, xm, pl.Rw32, 0, nullptr, blk0);
     else
-        k3_gen_kernel<2, false><<<gblocks, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, nullptr, pl.Rw32);
+        k3_gen_kernel<2, false><<<g, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, nullptr, pl.Rw32, 0, nullptr, blk0);
     if (timed) { PB_CUDA(cudaEventRecord(ctx->ev_gen_t1, st)); ctx->gen_timed = true; }
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
+    ctx->tm.gen_shard_frac = shared ? 1.0f / (float)ctx->world : 1.0f;
+    if (shared) {
+        // columns are counted in 64-bit words: a generator block covers GEN_THREADS / 64 of them
+        const int64_t total_blocks = ((nr + 255) / 256) * (256 / GEN_THREADS);
+        if ((rc = pbx_labels_exchange(ctx, buf, (int64_t)buf * pl.buf_words, ctx->P, pl.Rw, total_blocks, GEN_THREADS / 64, pl.has_miss, st))) return rc;
+    }
     return PB_OK;
 }
 
@@ -974,6 +993,12 @@ static int k3_alloc(pb_ctx* ctx, K3Plan* pl) {
         ctx->d_perms = (uint32_t*)pp; ctx->perms_cap = cap;
     }
     return PB_OK;
+}
+
+int pbk_labels_alloc(pb_ctx* ctx) {
+    if (ctx->cfg.mode != PB_MODE_PHILOX || ctx->P == 0 || ctx->n_case + ctx->n_ctrl == 0) return PB_OK;
+    K3Plan pl;
+    return k3_plan(ctx, &pl);
 }
 
 int pbk_assoc_prepare(pb_ctx* ctx) {

@@ -503,9 +503,10 @@ static int put_planes_impl(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int
     const uint64_t* src[3] = {B0, B1, V};
     uint64_t* dst[3] = {ctx->d_B0, ctx->d_B1, ctx->d_V};
     if (word_begin == 0 && n_words == ctx->W && src_pitch_words == ctx->Wp) {
-        // the caller's rows already have the device pitch (W rounded up to 16 words): one flat copy per plane
+        // the caller's rows already have the device pitch (W rounded up to 16 words): one flat copy per plane — up to the last
+        // row's last valid word, not beyond it (the source may be a window into a wider buffer: pb_group passes such)
         for (int i = 0; i < 3; i++)
-            PB_CUDA(cudaMemcpyAsync(dst[i], src[i], (size_t)ctx->N * ctx->Wp * 8, cudaMemcpyHostToDevice, ctx->upl));
+            PB_CUDA(cudaMemcpyAsync(dst[i], src[i], ((size_t)(ctx->N - 1) * ctx->Wp + (size_t)n_words) * 8, cudaMemcpyHostToDevice, ctx->upl));
     } else {
         for (int i = 0; i < 3; i++)
             PB_CUDA(cudaMemcpy2DAsync(dst[i] + word_begin, (size_t)ctx->Wp * 8, src[i], (size_t)src_pitch_words * 8, (size_t)n_words * 8,
@@ -550,7 +551,7 @@ static int put_planes_biallelic_impl(pb_ctx* ctx, int64_t word_begin, int64_t n_
     int rc;
     const bool flat = word_begin == 0 && n_words == ctx->W && src_pitch_words == ctx->Wp;
     auto copy_rows = [&](uint64_t* dst, const uint64_t* src) -> cudaError_t {
-        if (flat) return cudaMemcpyAsync(dst, src, (size_t)ctx->N * ctx->Wp * 8, cudaMemcpyHostToDevice, ctx->upl);
+        if (flat) return cudaMemcpyAsync(dst, src, ((size_t)(ctx->N - 1) * ctx->Wp + (size_t)n_words) * 8, cudaMemcpyHostToDevice, ctx->upl);
         return cudaMemcpy2DAsync(dst + word_begin, (size_t)ctx->Wp * 8, src, (size_t)src_pitch_words * 8, (size_t)n_words * 8, (size_t)ctx->N,
                                  cudaMemcpyHostToDevice, ctx->upl);
     };
@@ -867,6 +868,28 @@ extern "C" int pb_comm_connect(pb_ctx* ctx, const void* handles, int32_t rank, i
     PB_CUDA(cudaSetDevice(ctx->device));
     if (world == 1) { ctx->rank = 0; ctx->world = 1; return PB_OK; }
     return pbx_connect_ipc(ctx, handles, rank, world);
+}
+
+extern "C" int pb_comm_export_labels(pb_ctx* ctx, void* blob128) {
+    CHECK_CTX(ctx);
+    if (!blob128) FAIL(ctx, PB_ERR_INVALID, "pb_comm_export_labels: null buffer");
+    if (ctx->P == 0) FAIL(ctx, PB_ERR_INVALID, "pb_comm_export_labels: call pb_set_labels first");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    return pbx_labels_export(ctx, blob128);
+}
+
+extern "C" int pb_comm_connect_labels(pb_ctx* ctx, const void* blobs) {
+    CHECK_CTX(ctx);
+    if (!blobs) FAIL(ctx, PB_ERR_INVALID, "pb_comm_connect_labels: null buffer");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    return pbx_labels_connect_ipc(ctx, blobs);
+}
+
+// internal (pb_group): allocate the label matrices of the current plan so that the group can map them across its shards
+int pb_labels_alloc_internal(pb_ctx* ctx) {
+    if (!ctx || ctx->P == 0) return PB_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return PB_ERR_CUDA;
+    return pbk_labels_alloc(ctx);
 }
 
 extern "C" int pb_host_alloc(void** out, uint64_t bytes) {

@@ -16,6 +16,7 @@
 #include "pb_internal.h"
 
 int pb_assoc_prepare_internal(pb_ctx* ctx);     // pb_api.cu
+int pb_labels_alloc_internal(pb_ctx* ctx);      // pb_api.cu
 
 namespace {
 
@@ -244,6 +245,20 @@ extern "C" int pb_group_run_events(pb_group* g, pb_site_out* per_site, pb_class_
     if (!g) return PB_ERR_INVALID;
     if (g->S == 0) { g->err = "pb_group_run_events: tree and planes must be set"; return PB_ERR_INVALID; }
     const int G = g->G();
+    if (G > 1) {
+        // label sharing (pb_comm.cu): the shards sweep the same label matrix, so each draws 1/G of it and pulls the rest from
+        // its peers.  The matrices are allocated on every shard first, then mapped across the group (again only if one moved).
+        { const int rc0 = g->all([&](int i) { return pb_labels_alloc_internal(g->ctx[(size_t)i]); }); if (rc0) return rc0; }
+        bool mapped = true;
+        for (int i = 0; i < G; i++) {
+            const pb_ctx* c = g->ctx[(size_t)i];
+            mapped = mapped && c->xchg.lab_active && c->xchg.lab_c[i] == c->d_Xcase;
+        }
+        if (!mapped) {
+            const int rc0 = pbx_labels_connect_local(g->ctx.data(), G);
+            if (rc0) { for (pb_ctx* c : g->ctx) if (!c->err.empty()) { g->err = c->err; break; } return rc0; }
+        }
+    }
     std::vector<pb_class_counts> cc((size_t)G);
     const int rc = g->all([&](int i) {
         return pb_run_events(g->ctx[(size_t)i], per_site ? per_site + 64 * g->w0[(size_t)i] : nullptr, &cc[(size_t)i]);
@@ -308,7 +323,7 @@ extern "C" int pb_group_get_timings(pb_group* g, pb_timings* out) {
         t.n_launches += s.n_launches; t.k1_algorithmic_bytes += s.k1_algorithmic_bytes; t.n_informative += s.n_informative;
         t.n_alleles_in_use += s.n_alleles_in_use; t.n_extant_events += s.n_extant_events; t.n_fast_alleles += s.n_fast_alleles;
         t.n_maxt_fallback_reps += s.n_maxt_fallback_reps; t.n_swept_rows += s.n_swept_rows; t.eager_words += s.eager_words;
-        t.ms_gen_kernel = std::max(t.ms_gen_kernel, s.ms_gen_kernel);
+        t.ms_gen_kernel = std::max(t.ms_gen_kernel, s.ms_gen_kernel); t.gen_shard_frac = std::max(t.gen_shard_frac, s.gen_shard_frac);
         t.plane_mode = std::max(t.plane_mode, s.plane_mode);
     }
     *out = t;

@@ -132,7 +132,10 @@ struct AlleleMeta {      // one per allele slot (2 per informative site), 32 byt
 // Buffers alternate by epoch parity: a peer can run at most one epoch ahead (it needs this rank's next flag first), so the
 // buffer being read is never the one being refilled.
 #define PB_XCHG_MAX_WORLD 64
-#define PB_XCHG_HDR_WORDS 128          // flags[64] + error word + padding (1 KB), then the two maxT buffers
+#define PB_XCHG_HDR_WORDS 256          // maxT-ready flags [0,64), error word 64, label-slice-ready flags [128,192), label-slice-pulled
+                                       // flags [192,256) (2 KB), then the two maxT buffers
+#define PB_XCHG_GEN_FLAGS 128
+#define PB_XCHG_ACK_FLAGS 192
 struct pb_xchg {
     bool active = false;
     unsigned long long* block = nullptr;                 // own block (cudaMalloc)
@@ -142,6 +145,16 @@ struct pb_xchg {
     unsigned long long** d_peer_tbl = nullptr;           // device copy of peer[]
     unsigned long long* d_pooled = nullptr;              // [m] pooled (all-rank) minimum, unsorted: pb_get_maxT_unsorted
     unsigned long long epoch = 0;
+    // label sharing: every shard needs the SAME label matrix, so each rank draws 1/world of a tile's replicate columns and
+    // pulls the other ranks' columns out of their matrices (mapped like the exchange block)
+    bool lab_active = false;
+    size_t lab_bytes = 0;                                // size of the mapped matrix allocations (the plan they were made for)
+    uint64_t* lab_c[PB_XCHG_MAX_WORLD] = {};             // every rank's d_Xcase as seen from this device (own included)
+    uint64_t* lab_m[PB_XCHG_MAX_WORLD] = {};             // ... d_Xmiss (null without missing labels)
+    bool lab_ipc[PB_XCHG_MAX_WORLD] = {};
+    uint64_t** d_lab_c = nullptr;                        // device copies of the two tables
+    uint64_t** d_lab_m = nullptr;
+    unsigned long long gen_epoch = 0, buf_epoch[2] = {0, 0};   // one epoch per generated tile; the epoch that last filled each buffer
 };
 // what the fused sort kernel needs (by value)
 struct XchgView {
@@ -309,6 +322,14 @@ int pbx_begin_epoch(pb_ctx* ctx);                // points d_maxT at the epoch's
 int pbx_signal(pb_ctx* ctx);                     // after K3: tell every peer this rank's buffer of the epoch is complete
 XchgView pbx_view(pb_ctx* ctx);
 int pbx_check(pb_ctx* ctx);                      // after the stream synchronised: did a peer fail to arrive?
+bool pbx_labels_shared(pb_ctx* ctx, size_t need_bytes);    // label sharing connected and the matrices are still the mapped ones
+int pbx_labels_begin(pb_ctx* ctx, int buf, cudaStream_t st);    // before a tile is drawn into `buf`: peers have pulled its previous content
+int pbx_labels_exchange(pb_ctx* ctx, int buf, int64_t buf_off_words, int32_t P, int64_t Rw, int64_t total_blocks, int64_t words_per_block,
+                        bool has_miss, cudaStream_t st);    // after this rank's slice is drawn: signal, pull the peers' slices, acknowledge
+int pbx_labels_export(pb_ctx* ctx, void* blob128);
+int pbx_labels_connect_ipc(pb_ctx* ctx, const void* blobs);
+int pbx_labels_connect_local(pb_ctx** ctxs, int n);
+int pbk_labels_alloc(pb_ctx* ctx);               // k3_null.cu: the label matrices of the current plan (P, m), allocated now
 void pbx_destroy(pb_ctx* ctx);
 
 // nccl_dyn.cpp

@@ -122,15 +122,21 @@ def test_group_replay_mode_and_no_informative(monkeypatch, oracle_mod):
 
 
 @pytest.mark.skipif(N_GPUS < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("compact,empty_tail", [(False, False), (True, False), (True, True)])
-def test_group_all_gpus_equals_single_gpu(compact, empty_tail):
-    """the real thing: one process, one host thread, every GPU of the box (2 on a 2-GPU lease, 8 on a full box)"""
+@pytest.mark.parametrize("compact,empty_tail,gen_kb", [(False, False, None), (True, False, None), (True, True, None), (False, False, "96"), (True, False, "64")])
+def test_group_all_gpus_equals_single_gpu(monkeypatch, compact, empty_tail, gen_kb):
+    """the real thing: one process, one host thread, every GPU of the box (2 on a 2-GPU lease, 8 on a full box).  The shards
+    share the label matrix (each draws 1/G of its replicate columns and pulls the rest over NVLink); gen_kb forces several
+    generation tiles per pass, so the double-buffered matrices and the "slice pulled" acknowledgements are exercised too."""
     S, m = 64 * 1201 + 5, 8192
     devices = list(range(min(N_GPUS, 8)))
     tree, B0, B1, V, sn, lab = _inputs(S, leaf_gap=not compact, empty_tail_from=(700 if empty_tail else None), n_leaves=700)
+    if gen_kb:
+        monkeypatch.setenv("PB_K3_GEN_KB", gen_kb)
+        monkeypatch.setenv("PB_K3_TILE_KB", "32")
     want = _single(tree, B0, B1, V, sn, lab, S, m, compact)
     got, tm = _group_run(devices, tree, B0, B1, V, sn, lab, S, m, compact, tile_words=97, passes=3)
     _assert_same(got, want)
+    assert abs(tm["gen_shard_frac"] - 1.0 / len(devices)) < 1e-6          # the label matrix was drawn cooperatively
 
 
 # ---- one process per GPU ------------------------------------------------------------------------------------------
@@ -155,9 +161,15 @@ def _worker(rank, world, port, S, m, q, transport, compact, empty_tail):
         handles = [None] * world
         dist.all_gather_object(handles, hc.comm_export())
         hc.comm_connect(handles, rank, world)
+        if transport == "p2p_shared_labels":       # the ranks draw the label matrix cooperatively
+            blobs = [None] * world
+            dist.all_gather_object(blobs, hc.comm_export_labels())
+            hc.comm_connect_labels(blobs)
     for _ in range(3):
         ev, cc = hc.count_all_homoplasy_events(compact=False)
         st, mt = hc.assoc()
+    frac = hc.timings()["gen_shard_frac"]
+    assert abs(frac - (1.0 / world if transport == "p2p_shared_labels" else 1.0)) < 1e-6, frac
     q.put((rank, ev.tobytes(), cc, st.tobytes(), mt.tobytes(), hc.maxT_unsorted().tobytes()))
     dist.barrier()          # no rank frees its exchange block while a peer may still be reading it
     hc.close()
@@ -165,7 +177,8 @@ def _worker(rank, world, port, S, m, q, transport, compact, empty_tail):
 
 
 @pytest.mark.skipif(N_GPUS < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("transport,compact,empty_tail", [("p2p", False, False), ("p2p", True, True), ("nccl", False, True), ("nccl", True, False)])
+@pytest.mark.parametrize("transport,compact,empty_tail", [("p2p", False, False), ("p2p", True, True), ("nccl", False, True), ("nccl", True, False),
+                                                         ("p2p_shared_labels", False, False), ("p2p_shared_labels", True, True)])
 def test_process_per_gpu_sharded_equals_single_gpu(transport, compact, empty_tail):
     import torch.multiprocessing as mp
     import poutine_b200 as pb
