@@ -725,7 +725,9 @@ extern "C" int pb_run_assoc(pb_ctx* ctx, const uint32_t* replay_perms, pb_stat_o
 int pb_assoc_prepare_internal(pb_ctx* ctx) {
     if (!ctx || !ctx->events_done || ctx->P == 0) return PB_OK;     // pb_run_assoc reports the call-order error itself
     if (cudaSetDevice(ctx->device) != cudaSuccess) return PB_ERR_CUDA;
-    return pbk_assoc_prepare(ctx);
+    const int rc = pbk_assoc_prepare(ctx);
+    if (rc == 0) { ctx->prep_sinf = ctx->S_inf; ctx->prep_nmax = ctx->n_max; ctx->prep_P = ctx->P; }
+    return rc;
 }
 
 extern "C" int pb_run_extras(pb_ctx* ctx, double* exact_pointwise, double* fisher_p) {

@@ -188,8 +188,7 @@ __global__ void __launch_bounds__(256) k3_gather_kernel(unsigned long long* cons
                                                         int64_t buf_off, int32_t P, int64_t Rw, int64_t total_blocks, int64_t wpb) {
     const int q = blockIdx.y;
     if (q == rank) return;
-    __shared__ int dummy;
-    if (threadIdx.x == 0) { wait_flag(peers[rank] + PB_XCHG_GEN_FLAGS + q, epoch, peers[rank] + PB_XCHG_MAX_WORLD); dummy = 0; }
+    if (threadIdx.x == 0) wait_flag(peers[rank] + PB_XCHG_GEN_FLAGS + q, epoch, peers[rank] + PB_XCHG_MAX_WORLD);
     __syncthreads();
     const int64_t c0 = (total_blocks * q / world) * wpb, c1 = (total_blocks * (q + 1) / world) * wpb;   // peer q's word columns
     const int64_t pairs = (c1 - c0) >> 1;                       // 16 bytes per thread and step (wpb is even)

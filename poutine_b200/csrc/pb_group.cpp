@@ -8,6 +8,7 @@
 // worker can never block a peer that is waiting inside the exchange.
 #include <stdlib.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -15,34 +16,54 @@
 
 #include "pb_internal.h"
 
+#if defined(__x86_64__) || defined(_M_X64)
+#include <immintrin.h>
+#define PB_CPU_RELAX() _mm_pause()
+#else
+#define PB_CPU_RELAX() std::this_thread::yield()
+#endif
+
 int pb_assoc_prepare_internal(pb_ctx* ctx);     // pb_api.cu
 int pb_labels_alloc_internal(pb_ctx* ctx);      // pb_api.cu
 
 namespace {
 
+// One persistent thread per device.  A call is handed over through atomics the worker spins on for a short while before it
+// goes to sleep on the condition variable: back-to-back calls (a pass is four hand-overs) then cost microseconds, not the
+// tens of microseconds of a futex wake-up, and an idle group costs nothing.
 struct Worker {
     std::thread th;
     std::mutex mu;
     std::condition_variable cv;
     std::function<int()> job;
-    bool has_job = false, done = false, quit = false;
+    std::atomic<int> has_job{0}, done{0};
+    bool quit = false;
     int rc = 0;
+
+    static constexpr int SPIN = 20000;     // ~100-200 us of polling
 
     void loop() {
         for (;;) {
+            bool got = false;
+            for (int i = 0; i < SPIN && !got; i++) {
+                if (has_job.load(std::memory_order_acquire)) got = true;
+                else PB_CPU_RELAX();
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return has_job.load(std::memory_order_acquire) || quit; });
+                if (quit && !has_job.load(std::memory_order_acquire)) return;
+            }
             std::function<int()> j;
             {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return has_job || quit; });
-                if (quit) return;
+                std::lock_guard<std::mutex> lk(mu);
                 j = std::move(job);
-                has_job = false;
+                has_job.store(0, std::memory_order_relaxed);
             }
-            const int r = j();
+            rc = j();
             {
                 std::lock_guard<std::mutex> lk(mu);
-                rc = r;
-                done = true;
+                done.store(1, std::memory_order_release);
             }
             cv.notify_all();
         }
@@ -51,14 +72,18 @@ struct Worker {
         {
             std::lock_guard<std::mutex> lk(mu);
             job = std::move(j);
-            has_job = true;
-            done = false;
+            done.store(0, std::memory_order_relaxed);
+            has_job.store(1, std::memory_order_release);
         }
         cv.notify_all();
     }
     int wait() {
+        for (int i = 0; i < SPIN; i++) {
+            if (done.load(std::memory_order_acquire)) return rc;
+            PB_CPU_RELAX();
+        }
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return done; });
+        cv.wait(lk, [&] { return done.load(std::memory_order_acquire) != 0; });
         return rc;
     }
 };
@@ -248,13 +273,15 @@ extern "C" int pb_group_run_events(pb_group* g, pb_site_out* per_site, pb_class_
     if (G > 1) {
         // label sharing (pb_comm.cu): the shards sweep the same label matrix, so each draws 1/G of it and pulls the rest from
         // its peers.  The matrices are allocated on every shard first, then mapped across the group (again only if one moved).
-        { const int rc0 = g->all([&](int i) { return pb_labels_alloc_internal(g->ctx[(size_t)i]); }); if (rc0) return rc0; }
-        bool mapped = true;
-        for (int i = 0; i < G; i++) {
-            const pb_ctx* c = g->ctx[(size_t)i];
-            mapped = mapped && c->xchg.lab_active && c->xchg.lab_c[i] == c->d_Xcase;
-        }
-        if (!mapped) {
+        auto all_mapped = [&] {
+            for (int i = 0; i < G; i++) {
+                const pb_ctx* c = g->ctx[(size_t)i];
+                if (!c->xchg.lab_active || c->xchg.lab_c[i] != c->d_Xcase || !c->d_Xcase) return false;
+            }
+            return true;
+        };
+        if (!all_mapped() && g->ctx[0]->P > 0 && g->cfg.mode == PB_MODE_PHILOX) {     // (once; again only if a matrix had to grow)
+            { const int rc0 = g->all([&](int i) { return pb_labels_alloc_internal(g->ctx[(size_t)i]); }); if (rc0) return rc0; }
             const int rc0 = pbx_labels_connect_local(g->ctx.data(), G);
             if (rc0) { for (pb_ctx* c : g->ctx) if (!c->err.empty()) { g->err = c->err; break; } return rc0; }
         }
@@ -290,7 +317,13 @@ extern "C" int pb_group_run_assoc(pb_group* g, const uint32_t* replay_perms, pb_
     if (per_inf_site && cap < total) { g->err = "pb_group_run_assoc: per_inf_site too small"; return PB_ERR_INVALID; }
     // round 1: every allocation of the pass, on every shard; round 2: the pass.  A shard's last kernel waits for its peers
     // inside the exchange, and an allocation may wait for its device: none may be pending when the first shard gets there.
-    { const int rc = g->all([&](int i) { return pb_assoc_prepare_internal(g->ctx[(size_t)i]); }); if (rc) return rc; }
+    // (skipped when every shard's buffers were already sized for at least this pass: they only grow)
+    bool sized = true;
+    for (int i = 0; i < G; i++) {
+        const pb_ctx* c = g->ctx[(size_t)i];
+        sized = sized && c->prep_P == c->P && c->prep_sinf >= c->S_inf && c->prep_nmax >= c->n_max;
+    }
+    if (!sized) { const int rc = g->all([&](int i) { return pb_assoc_prepare_internal(g->ctx[(size_t)i]); }); if (rc) return rc; }
     return g->all([&](int i) {
         int64_t ni = 0;
         return pb_run_assoc(g->ctx[(size_t)i], replay_perms, per_inf_site ? per_inf_site + off[(size_t)i] : nullptr, g->n_inf[(size_t)i], &ni,

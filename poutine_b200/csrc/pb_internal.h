@@ -256,6 +256,7 @@ struct pb_ctx {
     unsigned long long* d_maxT = nullptr;  // [m] (double bits): the private allocation below, or the epoch's buffer of the exchange block
     unsigned long long* d_maxT_own = nullptr;
     pb_xchg xchg;
+    int64_t prep_sinf = -1; int32_t prep_nmax = -1, prep_P = -1;   // what pbk_assoc_prepare last sized the buffers for (buffers only grow)
     int64_t site_index_base = 0;           // added to pb_stat_out.site_index (a pb_group reports group-global indices)
     double* d_maxT_sorted = nullptr;       // [pow2 >= m]
     int64_t maxT_cap = 0, sorted_cap = 0;
