@@ -112,7 +112,7 @@ __device__ __forceinline__ void mul64x32(uint32_t& xl, uint32_t& xh, uint32_t R,
 static_assert(GEN_ROWS % GEN_PASS == 0 && GEN_ROWS % (4 * GEN_ILP) == 0, "a staging tile is a whole number of passes");
 
 template <int MODE, bool MISS>
-__global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
+__global__ void __launch_bounds__(GEN_THREADS, (GEN_THREADS == 256 ? 3 : 1)) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
                                                              int32_t n_ctrl, const uint8_t* __restrict__ label,
                                                              const uint32_t* __restrict__ perms, uint32_t* __restrict__ Xc32,
                                                              uint32_t* __restrict__ Xm32, int64_t Rw32, int force_replay = 0,
@@ -224,23 +224,26 @@ __global__ void __launch_bounds__(GEN_THREADS) k3_gen_kernel(uint64_t seed, int6
                     // the minimum low part, one vote checks it against the pass's largest product, and the rare hit replays the
                     // whole pass through the exact path from the saved state (same words are overwritten).
                     const uint32_t rem0 = rem_case, range0 = range;
+                    // Two phases, so that a lone warp (a sharded run leaves one or two per scheduler) is not one long dependent
+                    // chain: first every draw value — the 2*GEN_ILP words are independent multiply chains, advanced in step —
+                    // then the labels, whose only serial dependency is the case counter.
+                    uint32_t us[GEN_PASS];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+#pragma unroll
+                        for (int wi = 0; wi < 2 * GEN_ILP; wi++)
+                            mul64x32(w[wi >> 1][2 * (wi & 1)], w[wi >> 1][2 * (wi & 1) + 1], range0 - (uint32_t)(4 * wi + j), us[4 * wi + j]);
+                    }
                     uint64_t mn = ~0ull;
 #pragma unroll
-                    for (int q4 = 0; q4 < GEN_ILP; q4++) {
+                    for (int wi = 0; wi < 2 * GEN_ILP; wi++) mn = min(mn, ((uint64_t)w[wi >> 1][2 * (wi & 1) + 1] << 32) | w[wi >> 1][2 * (wi & 1)]);
+                    range = range0 - GEN_PASS;
 #pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            uint32_t xl = w[q4][2 * h], xh = w[q4][2 * h + 1];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                uint32_t u, bc;
-                                mul64x32(xl, xh, range, u);
-                                range--;
-                                asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %0;\n\t@q add.u32 %0, %0, -1;\n\tvote.sync.ballot.b32 %1, q, 0xffffffff;\n\t}"
-                                             : "+r"(rem_case), "=r"(bc) : "r"(u));
-                                sc[ii + 8 * q4 + 4 * h + j][warp] = bc;   // every lane stores the same word: no lane test, one broadcast store
-                            }
-                            mn = min(mn, ((uint64_t)xh << 32) | xl);
-                        }
+                    for (int k = 0; k < GEN_PASS; k++) {
+                        uint32_t bc;
+                        asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %0;\n\t@q add.u32 %0, %0, -1;\n\tvote.sync.ballot.b32 %1, q, 0xffffffff;\n\t}"
+                                     : "+r"(rem_case), "=r"(bc) : "r"(us[k]));
+                        sc[ii + k][warp] = bc;   // every lane stores the same word: no lane test, one broadcast store
                     }
                     const uint64_t prodmax = (uint64_t)range0 * (range0 - 1) * (uint64_t)(range0 - 2) * (range0 - 3);   // range0 >= GEN_PASS; < 2^64 for P < 65536
                     if (__any_sync(0xffffffffu, mn < prodmax) || force_replay) {   // force_replay: test hook (PB_GEN_FORCE_REPLAY)

@@ -197,12 +197,24 @@ __global__ void __launch_bounds__(256) k3_gather_kernel(unsigned long long* cons
     for (int mtx = 0; mtx < n_mat; mtx++) {
         const uint64_t* src = (mtx ? lab_m[q] : lab_c[q]) + buf_off + c0;
         uint64_t* dst = (mtx ? lab_m[rank] : lab_c[rank]) + buf_off + c0;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)P * pairs; i += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t row = i / pairs, pr = i - row * pairs;
-            const uint64_t* s = src + row * Rw + 2 * pr;
-            unsigned long long a, b;
-            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(s) : "memory");
-            *reinterpret_cast<ulonglong2*>(dst + row * Rw + 2 * pr) = make_ulonglong2(a, b);
+        // four 16-byte peer loads in flight per thread: an NVLink round trip is microseconds, the link wants megabytes in flight
+        const int64_t total = (int64_t)P * pairs, stride = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+            unsigned long long a[4], b[4];
+            int64_t off[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int64_t i = i0 + k * stride;
+                off[k] = -1;
+                if (i < total) {
+                    const int64_t row = i / pairs, pr = i - row * pairs;
+                    off[k] = row * Rw + 2 * pr;
+                    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a[k]), "=l"(b[k]) : "l"(src + off[k]) : "memory");
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (off[k] >= 0) *reinterpret_cast<ulonglong2*>(dst + off[k]) = make_ulonglong2(a[k], b[k]);
         }
     }
 }
@@ -230,7 +242,7 @@ int pbx_labels_exchange(pb_ctx* ctx, int buf, int64_t buf_off_words, int32_t P, 
     const unsigned long long e = ++x.gen_epoch;
     xchg_flag_signal_kernel<<<1, PB_XCHG_MAX_WORLD, 0, st>>>(x.d_peer_tbl, ctx->world, ctx->rank, PB_XCHG_GEN_FLAGS, e);
     const int64_t slice_pairs = (total_blocks / ctx->world + 1) * words_per_block / 2;
-    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(((int64_t)P * slice_pairs + 255) / 256, (int64_t)ctx->sm_count * 2));
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(((int64_t)P * slice_pairs + 1023) / 1024, (int64_t)ctx->sm_count));   // x (world - 1) peers in grid.y
     k3_gather_kernel<<<dim3(gx, (unsigned)ctx->world), 256, 0, st>>>(x.d_peer_tbl, x.d_lab_c, x.d_lab_m, ctx->world, ctx->rank, e, buf_off_words, P, Rw,
                                                                    total_blocks, words_per_block);
     xchg_flag_signal_kernel<<<1, PB_XCHG_MAX_WORLD, 0, st>>>(x.d_peer_tbl, ctx->world, ctx->rank, PB_XCHG_ACK_FLAGS, e);
