@@ -111,16 +111,19 @@ __device__ __forceinline__ void mul64x32(uint32_t& xl, uint32_t& xh, uint32_t R,
 #define GEN_PASS (8 * GEN_ILP)   // samples per pass of the batched generator: GEN_ILP Philox blocks x 2 words x 4 draws
 static_assert(GEN_ROWS % GEN_PASS == 0 && GEN_ROWS % (4 * GEN_ILP) == 0, "a staging tile is a whole number of passes");
 
-template <int MODE, bool MISS>
-__global__ void __launch_bounds__(GEN_THREADS, (GEN_THREADS == 256 ? 3 : 1)) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
+// THREADS: replicates per block.  256 normally; 64 when a sharded run leaves this rank so few replicates that 256-thread
+// blocks would occupy a third of the SMs with two warps per scheduler each — the multiply pipe is per scheduler, so the
+// same warps spread one per scheduler finish in half the time.
+template <int MODE, bool MISS, int THREADS = GEN_THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 3 : 1)) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
                                                              int32_t n_ctrl, const uint8_t* __restrict__ label,
                                                              const uint32_t* __restrict__ perms, uint32_t* __restrict__ Xc32,
                                                              uint32_t* __restrict__ Xm32, int64_t Rw32, int force_replay = 0,
                                                              unsigned long long* __restrict__ replay_err = nullptr, int64_t blk0 = 0) {
-    __shared__ uint32_t sc[GEN_ROWS][GEN_WORDS], sm[MISS ? GEN_ROWS : 1][GEN_WORDS];
+    __shared__ uint32_t sc[GEN_ROWS][THREADS / 32], sm[MISS ? GEN_ROWS : 1][THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t gblk = (int64_t)blockIdx.x + blk0;      // blk0: a rank of a sharded run generates only its own slice of the tile's replicates
-    const int64_t rep_local = gblk * GEN_THREADS + tid;
+    const int64_t rep_local = gblk * THREADS + tid;
     const bool active = rep_local < n_reps;
     const uint64_t rep = (uint64_t)(rep_base + rep_local);
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), r0 = (uint32_t)rep, r1 = (uint32_t)(rep >> 32);
@@ -287,9 +290,10 @@ __global__ void __launch_bounds__(GEN_THREADS, (GEN_THREADS == 256 ? 3 : 1)) k3_
             }
         }
         __syncthreads();
-        for (int t = tid; t < rows * GEN_WORDS; t += GEN_THREADS) {
-            const int row = t / GEN_WORDS, wd = t % GEN_WORDS;
-            const int64_t o = (int64_t)(i0 + row) * Rw32 + gblk * GEN_WORDS + wd;
+        constexpr int WORDS = THREADS / 32;
+        for (int t = tid; t < rows * WORDS; t += THREADS) {
+            const int row = t / WORDS, wd = t % WORDS;
+            const int64_t o = (int64_t)(i0 + row) * Rw32 + gblk * WORDS + wd;
             Xc32[o] = sc[row][wd];
             if (MISS) Xm32[o] = sm[row][wd];
         }
@@ -872,16 +876,17 @@ static int k3_plan(pb_ctx* ctx, K3Plan* pl) {
 static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t nr, cudaStream_t st, int buf) {
     // the grid covers the tile rounded up to 256 replicates: the padding replicates write zero bits, which the 16-byte
     // sweeps of K3b rely on (the word behind an odd word count)
-    int64_t blk0 = 0, gblocks = ((nr + 255) / 256) * (256 / GEN_THREADS);
+    // slices are cut in units of 256 replicates (4 matrix words), whatever the block size
+    const int64_t units = (nr + 255) / 256;
+    int64_t u0 = 0, u1 = units;
     // Sharded run with mapped label matrices (pb_comm.cu, "label sharing"): every rank needs the SAME matrix, so each generates
     // 1/world of the tile's replicate columns and pulls the rest from its peers over NVLink instead of drawing all of it.
     const bool shared = pbx_labels_shared(ctx, pl.buf_words * 8 * pl.nbuf);
     int rc;
     if (shared) {
         if ((rc = pbx_labels_begin(ctx, buf, st))) return rc;          // peers have pulled what this buffer held before
-        const int64_t total = gblocks;
-        blk0 = total * ctx->rank / ctx->world;
-        gblocks = total * (ctx->rank + 1) / ctx->world - blk0;
+        u0 = units * ctx->rank / ctx->world;
+        u1 = units * (ctx->rank + 1) / ctx->world;
     }
     const bool timed = base == 0;        // ms_gen_kernel: the generator's own time for the first tile (events on its stream)
     if (timed) PB_CUDA(cudaEventRecord(ctx->ev_gen_t0, st));
@@ -889,9 +894,17 @@ static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t
     uint32_t* xc = (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words);
     uint32_t* xm = pl.has_miss ? (uint32_t*)(ctx->d_Xmiss + buf * pl.buf_words) : nullptr;
     const bool batched = ctx->P < 65536;      // spec v2 (four draws per 64-bit word); spec v1 above that
-    const unsigned g = (unsigned)gblocks;
+    // fewer than two warps per scheduler: 64-thread blocks spread them over all SMs (see k3_gen_kernel)
+    const bool small = batched && ((u1 - u0) * 8 < (int64_t)ctx->sm_count * 8 || getenv("PB_GEN_SMALL_BLOCKS")) && !getenv("PB_GEN_BIG_BLOCKS");   // (env: test hooks)
+    const int threads = small ? 64 : GEN_THREADS;
+    const unsigned g = (unsigned)((u1 - u0) * (256 / threads));
+    const int64_t blk0 = u0 * (256 / threads);
     if (g == 0) {
-    } else if (pl.has_miss && batched)
+    } else if (small && pl.has_miss)
+        k3_gen_kernel<0, true, 64><<<g, 64, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, xm, pl.Rw32, force_replay, nullptr, blk0);
+    else if (small)
+        k3_gen_kernel<0, false, 64><<<g, 64, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, nullptr, pl.Rw32, force_replay, nullptr, blk0);
+    else if (pl.has_miss && batched)
         k3_gen_kernel<0, true><<<g, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, xm, pl.Rw32, force_replay, nullptr, blk0);
     else if (batched)
         k3_gen_kernel<0, false><<<g, GEN_THREADS, 0, st>>>(ctx->cfg.seed, base, nr, ctx->P, ctx->n_case, ctx->n_ctrl, ctx->d_label, nullptr, xc, nullptr, pl.Rw32, force_replay, nullptr, blk0);
@@ -903,11 +916,7 @@ static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
     ctx->tm.gen_shard_frac = shared ? 1.0f / (float)ctx->world : 1.0f;
-    if (shared) {
-        // columns are counted in 64-bit words: a generator block covers GEN_THREADS / 64 of them
-        const int64_t total_blocks = ((nr + 255) / 256) * (256 / GEN_THREADS);
-        if ((rc = pbx_labels_exchange(ctx, buf, (int64_t)buf * pl.buf_words, ctx->P, pl.Rw, total_blocks, GEN_THREADS / 64, pl.has_miss, st))) return rc;
-    }
+    if (shared && (rc = pbx_labels_exchange(ctx, buf, (int64_t)buf * pl.buf_words, ctx->P, pl.Rw, units, 4, pl.has_miss, st))) return rc;
     return PB_OK;
 }
 

@@ -891,6 +891,20 @@ def test_large_properties_and_slice_parity(oracle_mod):
     assert np.all(np.abs(mc - exact) < 6 * sd + 2.0 / m)
 
 
+@pytest.mark.parametrize("na_frac", [0.0, 0.03])
+def test_assoc_philox_small_generator_blocks(oracle_mod, monkeypatch, na_frac):
+    """the 64-thread instantiation of the label generator (what a sharded run uses when a rank is left with few replicates),
+    forced here on one GPU: same matrix, bit for bit"""
+    monkeypatch.setenv("PB_GEN_SMALL_BLOCKS", "1")
+    m = 1500
+    tree, o, hc, sn, lab = _assoc_case(oracle_mod, 200, 1200, m, 43, na_frac, 0.02, seed=0xABCDEF)
+    st, mt_s, mt_u = o.assoc(sn, lab, m, 1, perms=None, seed=0xABCDEF, n_threads=4)
+    g_st, g_mt = hc.assoc()
+    assert_stats_equal(g_st, st)
+    np.testing.assert_array_equal(g_mt.view(np.uint64), mt_s.view(np.uint64))
+    np.testing.assert_array_equal(hc.maxT_unsorted().view(np.uint64), mt_u.view(np.uint64))
+
+
 def test_assoc_philox_many_samples_uses_spec_v1(oracle_mod):
     """P >= 65536 pheno rows: four draw ranges no longer fit one 64-bit product, so the label generator falls back to one
     32-bit word per draw (sampling spec v1); the oracle restates both specs and switches at the same P."""
