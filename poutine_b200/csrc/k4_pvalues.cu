@@ -224,7 +224,11 @@ __device__ __forceinline__ unsigned long long xchg_load_min(const XchgView& x, c
 // Sharded runs: the tile load IS the all-reduce(min) of maxT over the site shards — the peers' buffers are read over
 // NVLink while the tile is filled (xchg_load_min), after the block has seen every rank's ready flag (xchg_wait).
 __global__ void __launch_bounds__(1024) k4_sort_coop_kernel(const unsigned long long* __restrict__ maxT, int64_t m, int64_t n_pad,
-                                                            double* __restrict__ a, const XchgView xv) {
+                                                            double* __restrict__ a, const XchgView xv,
+                                                            const unsigned int* __restrict__ run_if) {
+    // run_if != nullptr: this launch is the fall-back behind the counting path (below) and runs only when that path met a
+    // value outside its table (*run_if != 0); the decision stays on the device, the launch is always enqueued
+    if (run_if != nullptr && *run_if == 0) return;
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[BSORT_TILE];
     const int t = threadIdx.x;
@@ -280,6 +284,91 @@ __global__ void __launch_bounds__(1024) k4_sort_coop_kernel(const unsigned long 
         }
         grid.sync();
     }
+}
+
+// ---- counting path: sort maxT by counting it against the sorted p-value table ---------------------------------------------
+// Every maxT[rep] is a table value f(n, k) (a minimum over table look-ups; +inf when nothing was in use), and the table is small
+// (n_max <= 126 -> <= 8 128 entries) where m is 1e5 .. 1e7.  So: sort the TABLE once (it is kept across passes like the table
+// itself), bin every replicate's pooled minimum by binary search (shared-memory histogram), prefix-sum the bins, and write
+// maxT_sorted by expanding the runs.  ~25 us instead of the ~90 us bitonic network at m = 1e5, 0.4 instead of 5.9 ms at 1e7.
+// The bin pass is also where a sharded run pools its shards (xchg_wait / xchg_load_min, as in the sort kernel).  A pooled
+// value that is NOT in this rank's table (a peer saw a larger n_max) raises a flag and the bitonic network runs after all,
+// on the pooled values.
+#define TAB_MAX 8192          // table entries (+ one +inf bin) the counting path handles: n_max <= 126
+__global__ void __launch_bounds__(1024) k4_tabsort_kernel(const double* __restrict__ tab, int total, unsigned long long* __restrict__ out, int n_pad) {
+    extern __shared__ unsigned long long sk[];        // n_pad keys (p >= 0: bit patterns order like the values)
+    const unsigned long long INF = 0x7FF0000000000000ull;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) sk[i] = i < total ? (unsigned long long)__double_as_longlong(tab[i]) : (i == total ? INF : ~0ull);
+    __syncthreads();
+    for (int k = 2; k <= n_pad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < n_pad / 2; t += blockDim.x) {
+                const int lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+                const unsigned long long x = sk[lo], y = sk[hi];
+                const bool up = (lo & k) == 0;
+                if ((x > y) == up) { sk[lo] = y; sk[hi] = x; }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) out[i] = sk[i];
+}
+
+// bins: index of the FIRST table entry equal to the value (lower bound); entries [0, n_bins) are valid keys
+__global__ void __launch_bounds__(512) k4_bin_kernel(const unsigned long long* __restrict__ maxT, int64_t m, const unsigned long long* __restrict__ keys,
+                                                     int n_bins, unsigned int* __restrict__ hist, unsigned int* __restrict__ miss, const XchgView xv,
+                                                     unsigned long long* __restrict__ pooled_out) {
+    extern __shared__ unsigned int sh_hist[];
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) sh_hist[i] = 0;
+    xchg_wait(xv);                                     // (ends in a __syncthreads)
+    __syncthreads();
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = xchg_load_min(xv, maxT, i);
+        if (xv.peers == nullptr && pooled_out != nullptr) pooled_out[i] = v;
+        int lo = 0, hi = n_bins;                       // first key >= v
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (keys[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        if (lo < n_bins && keys[lo] == v) atomicAdd(&sh_hist[lo], 1u);
+        else bad = true;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(hist + i, sh_hist[i]);
+    if (bad) atomicExch(miss, 1u);
+}
+
+// one block: inclusive prefix of the bins -> cum[i] = #replicates with value <= keys[i]
+__global__ void __launch_bounds__(1024) k4_binscan_kernel(const unsigned int* __restrict__ hist, int n_bins, unsigned long long* __restrict__ cum) {
+    __shared__ unsigned long long s_part[1024];
+    const int per = (n_bins + 1023) / 1024;
+    unsigned long long acc = 0;
+    for (int k = 0; k < per; k++) { const int i = threadIdx.x * per + k; if (i < n_bins) acc += hist[i]; }
+    s_part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned long long t = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    unsigned long long run = s_part[threadIdx.x] - acc;
+    for (int k = 0; k < per; k++) { const int i = threadIdx.x * per + k; if (i < n_bins) { run += hist[i]; cum[i] = run; } }
+}
+
+// maxT_sorted[i] = the key of the first bin whose cumulative count exceeds i
+__global__ void k4_expand_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ cum, int n_bins, int64_t m,
+                                 const unsigned int* __restrict__ miss, double* __restrict__ out) {
+    if (*miss) return;                                  // the fall-back sort writes the array
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int lo = 0, hi = n_bins;                            // first bin with cum > i
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cum[mid] <= (unsigned long long)i) lo = mid + 1; else hi = mid;
+    }
+    out[i] = __longlong_as_double((long long)keys[lo < n_bins ? lo : n_bins - 1]);
 }
 
 // ---- final per-site statistics -----------------------------------------------------------------------
@@ -347,7 +436,8 @@ int pbk_ptable(pb_ctx* ctx, bool alloc_only) {
     void* pt = ctx->d_ptable;
     if ((rc = ensure_bytes(ctx, &pt, &cap, total * 8))) { ctx->d_ptable = nullptr; ctx->ptable_cap = 0; return rc; }
     ctx->d_ptable = (double*)pt; ctx->ptable_cap = cap;
-    if (alloc_only) { ctx->ptable_nmax = -1; return PB_OK; }      // (the buffer may have moved: the table is rebuilt by the real call)
+    if (alloc_only) { ctx->ptable_nmax = -1; ctx->tabkeys_valid = false; return PB_OK; }      // (the buffer may have moved: the table is rebuilt by the real call)
+    ctx->tabkeys_valid = false;
     k4_ptable_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ptable, n_max, p);
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
@@ -418,15 +508,57 @@ int pbk_pvalues(pb_ctx* ctx, bool alloc_only) {
     }
     if (ctx->sort_blocks_per_sm < 0)   // occupancy belongs to the context's device (contexts of one process may sit on different GPUs / threads)
         PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sort_blocks_per_sm, k4_sort_coop_kernel, 1024, 0));
+    if (!ctx->d_tabkeys) {             // counting path scratch (fixed size)
+        PB_CUDA(cudaMalloc(&ctx->d_tabkeys, (size_t)TAB_MAX * 8));
+        PB_CUDA(cudaMalloc(&ctx->d_binhist, (size_t)(TAB_MAX + 2) * 4));
+        PB_CUDA(cudaMalloc(&ctx->d_bincum, (size_t)(TAB_MAX + 1) * 8));
+        PB_CUDA(cudaFuncSetAttribute(k4_tabsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_MAX * 8));
+    }
+    if (!ctx->xchg.active && ctx->pooled_own_cap < m) {     // single context: a copy of maxT for the fall-back sort to read
+        if (ctx->d_pooled_own) cudaFree(ctx->d_pooled_own);
+        ctx->d_pooled_own = nullptr;
+        PB_CUDA(cudaMalloc(&ctx->d_pooled_own, (size_t)m * 8));
+        ctx->pooled_own_cap = m;
+    }
     if (alloc_only) return PB_OK;
     const int T = 256;
-    {
-        int64_t grid = std::min<int64_t>(n_pad / BSORT_TILE, (int64_t)std::max(ctx->sort_blocks_per_sm, 1) * ctx->sm_count);
+    const int64_t grid = std::min<int64_t>(n_pad / BSORT_TILE, (int64_t)std::max(ctx->sort_blocks_per_sm, 1) * ctx->sm_count);
+    const int64_t tab_total = (int64_t)(ctx->ptable_nmax + 1) * (ctx->ptable_nmax + 2) / 2;
+    const bool counting = tab_total + 1 <= TAB_MAX && m >= 4096 && !getenv("PB_K4_BITONIC");
+    if (counting) {
+        const int n_bins = (int)tab_total + 1;          // + the +inf bin
+        int tp = 2;
+        while (tp < n_bins) tp <<= 1;
+        if (!ctx->tabkeys_valid) {                      // sorted table keys: a function of the table, kept with it
+            k4_tabsort_kernel<<<1, 1024, (size_t)tp * 8, st>>>(ctx->d_ptable, (int)tab_total, ctx->d_tabkeys, tp);
+            ctx->tabkeys_valid = true;
+            ctx->tm.n_launches += 1;
+        }
+        PB_CUDA(cudaMemsetAsync(ctx->d_binhist, 0, (size_t)(TAB_MAX + 2) * 4, st));       // bins + the miss flag behind them
+        unsigned int* d_miss = ctx->d_binhist + TAB_MAX + 1;
+        const XchgView xv = pbx_view(ctx);
+        const unsigned bblocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((m + 2047) / 2048, (int64_t)ctx->sm_count * 2));
+        k4_bin_kernel<<<bblocks, 512, (size_t)n_bins * 4, st>>>(ctx->d_maxT, m, ctx->d_tabkeys, n_bins, ctx->d_binhist, d_miss, xv,
+                                                                 ctx->xchg.active ? nullptr : ctx->d_pooled_own);
+        k4_binscan_kernel<<<1, 1024, 0, st>>>(ctx->d_binhist, n_bins, ctx->d_bincum);
+        k4_expand_kernel<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(ctx->d_tabkeys, ctx->d_bincum, n_bins, m, d_miss, ctx->d_maxT_sorted);
+        // fall-back, decided on the device: the bitonic network over the POOLED values when some value was not in the table
+        const unsigned long long* a_maxT = ctx->xchg.active ? ctx->xchg.d_pooled : ctx->d_pooled_own;
+        int64_t a_m = m, a_npad = n_pad;
+        double* a_out = ctx->d_maxT_sorted;
+        XchgView a_xv{};
+        a_xv.peers = nullptr; a_xv.world = 1;
+        const unsigned int* a_run = d_miss;
+        void* args[] = {(void*)&a_maxT, (void*)&a_m, (void*)&a_npad, (void*)&a_out, (void*)&a_xv, (void*)&a_run};
+        PB_CUDA(cudaLaunchCooperativeKernel((const void*)k4_sort_coop_kernel, dim3((unsigned)grid), dim3(1024), args, 0, st));
+        ctx->tm.n_launches += 4;
+    } else {
         const unsigned long long* a_maxT = ctx->d_maxT;
         int64_t a_m = m, a_npad = n_pad;
         double* a_out = ctx->d_maxT_sorted;
         XchgView a_xv = pbx_view(ctx);
-        void* args[] = {(void*)&a_maxT, (void*)&a_m, (void*)&a_npad, (void*)&a_out, (void*)&a_xv};
+        const unsigned int* a_run = nullptr;
+        void* args[] = {(void*)&a_maxT, (void*)&a_m, (void*)&a_npad, (void*)&a_out, (void*)&a_xv, (void*)&a_run};
         PB_CUDA(cudaLaunchCooperativeKernel((const void*)k4_sort_coop_kernel, dim3((unsigned)grid), dim3(1024), args, 0, st));
         ctx->tm.n_launches += 1;
     }

@@ -259,6 +259,10 @@ struct pb_ctx {
     int64_t prep_sinf = -1; int32_t prep_nmax = -1, prep_P = -1;   // what pbk_assoc_prepare last sized the buffers for (buffers only grow)
     int64_t site_index_base = 0;           // added to pb_stat_out.site_index (a pb_group reports group-global indices)
     double* d_maxT_sorted = nullptr;       // [pow2 >= m]
+    // K4 counting path: sorted table keys (+inf last), bin histogram (+ miss flag), cumulative counts, a copy of maxT
+    unsigned long long* d_tabkeys = nullptr; unsigned int* d_binhist = nullptr; unsigned long long* d_bincum = nullptr;
+    unsigned long long* d_pooled_own = nullptr; int64_t pooled_own_cap = 0;
+    bool tabkeys_valid = false;
     int64_t maxT_cap = 0, sorted_cap = 0;
     uint64_t *d_Xcase = nullptr, *d_Xmiss = nullptr;  // [P][Rw]
     int64_t X_cap = 0, Xm_cap = 0, fb_cap = 0;
