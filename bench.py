@@ -217,7 +217,7 @@ def k3_rooflines(tm, parts, m, P, has_miss, n_shards=1):
                                    "draws_per_s": (m * P) / (parts["ms_gen_kernel"] / 1e3) if parts.get("ms_gen_kernel") else None,
                                    "ms": parts.get("ms_gen_kernel"),
                                    "frac": ceil.get("k3_gen_kernel", {}).get("fmaheavy_pipe_frac"),
-                                   "frac_source": "ncu sm__pipe_fmaheavy_cycles_active (profiles/r2_k3a_gen_C2_ncu.txt)"},
+                                   "frac_source": "ncu sm__pipe_fmaheavy_cycles_active (profiles/r2_final_k3a_gen_ncu.txt, via profiles/k3_ceilings.json)"},
            "k3b_replicate_count": {"bound": "l2", "unit": "GB/s", "algorithmic_bytes": swept_bytes, "ms": parts.get("ms_null_count"),
                                    "achieved": swept_bytes / (parts["ms_null_count"] / 1e3) / 1e9 if parts.get("ms_null_count") else None,
                                    "peak": l2_peak, "peak_source": "measured: tools/microbench/l2_peak (L2-resident stream, 16 B per lane, L1 bypassed)"}}
