@@ -109,6 +109,39 @@ def cpu_reference_pass(tree, chars, sn, lab, m, seed, threads, keep=None):
     return chars.shape[1] / (t2 - t0), t1 - t0, t2 - t1
 
 
+def exact_null_check(hc, st, m):
+    """the exact point-wise null (pb_run_extras: the m -> infinity limit of r/m under a uniform label
+    permutation, by hypergeometric sums — no random numbers involved) as a validator of the Monte-Carlo path that was just
+    timed.  Per allele in use, r ~ Binomial(m, p_exact) if K3 (label generator + replicate counts) is right: z = (r - m p) /
+    sqrt(m p (1-p)).  Fails the run if any allele leaves the 8-sigma + 4-count band (Poisson-safe for millions of alleles with
+    tiny p) or if the mean of z^2 (expectation exactly 1, whatever the discreteness) is off; the 6-sigma count is reported."""
+    t0 = time.perf_counter()
+    ep, _ = hc.extras()
+    t_dev = time.perf_counter() - t0
+    zs, n6, n8 = [], 0, 0
+    for a, name in enumerate(("a1", "a2")):
+        use = st[name + "_in_use"] != 0
+        p = ep[use, a]
+        r = st["r_" + name][use].astype(np.float64)
+        if np.isnan(p).any():
+            return {"checked": False, "error": "exact null is NaN for an allele in use"}
+        var = m * p * (1.0 - p)
+        dev = np.abs(r - m * p)
+        n6 += int((dev > 6.0 * np.sqrt(var) + 2.0).sum())
+        n8 += int((dev > 8.0 * np.sqrt(var) + 4.0).sum())
+        ok = var > 0
+        zs.append(((r[ok] - m * p[ok]) ** 2) / var[ok])
+        n8 += int((dev[~ok] > 0).sum())            # p exactly 0 or 1: r must be 0 or m
+    z2 = np.concatenate(zs) if zs else np.zeros(0)
+    mean_z2 = float(z2.mean()) if len(z2) else None
+    passed = n8 == 0 and (mean_z2 is None or 0.8 < mean_z2 < 1.25)
+    return {"checked": True, "passed": bool(passed), "alleles": int(len(z2)), "outside_6sigma_plus_2": n6, "outside_8sigma_plus_4": n8,
+            "mean_z2": mean_z2, "max_abs_z": float(np.sqrt(z2.max())) if len(z2) else None, "seconds": t_dev,
+            "what": "Monte-Carlo r of the last timed step against the exact label-permutation null (pb_run_extras, hypergeometric "
+                    "sums; parity unpinned: the reference is Monte-Carlo only, HC.java:4812-4838); alleles share the replicates, so "
+                    "mean_z2 has expectation 1 but not the variance of independent draws"}
+
+
 def parity_check(gpu_sites, gpu_stats, ref, n):
     """The GPU's per-site output for the first n sites of the timed input against the CPU port's output on the same sites
     (same Philox seed, same m): Homoplasy_Events fields and, per informative site, in-use flags, observed tallies, observed
@@ -503,6 +536,9 @@ def run_b200(args):
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
     # outputs of the last timed step (views of page-locked buffers the next call overwrites): kept for the parity check
     par_outputs = [("headline", np.array(ev[:CPU_SAMPLE_SITES]), np.array(st))]
+    exact_null = None
+    if rank == 0 and not args.no_exact_null:       # validator of the Philox-mode null that was just timed (this rank's shard)
+        exact_null = exact_null_check(hc, st, m)
     e2e_breakdown = {k: v / args.steps for k, v in e2e_parts.items()}
     e2e_step_ms = list(e2e_steps)
     eager_words = int(tm_e.get("eager_words", 0))
@@ -569,6 +605,9 @@ def run_b200(args):
                        "note": "pb_pack_chars_biallelic / pb_fasta_pack_tile_biallelic emit the compact upload format directly: no three-plane "
                                "intermediate and no compaction pass exist on the host path; packing is tile-pipelined with the upload by the hosts"}
 
+    if exact_null is not None and not exact_null.get("passed", False):
+        print("bench.py: EXACT-NULL CHECK FAILED: %s" % json.dumps(exact_null), file=sys.stderr)
+        sys.exit(4)
     if rank == 0:
         launch = "one process, one host thread (pb_group)" if inproc else "one process per GPU (torchrun)"
         line = {"metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
@@ -594,7 +633,7 @@ def run_b200(args):
                 "gpu_launches": launches,
                 "roofline": roofline, "roofline_k3": roofline_k3, "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "parity_checked": parity["parity_checked"], "parity_sites": parity["parity_sites"], "parity": parity,
-                "host_packer": host_packer,
+                "host_packer": host_packer, "exact_null_check": exact_null,
                 "exchange": exchange, "gen_shard_frac": float(tm.get("gen_shard_frac", 1.0)),
                 "memoised": "the binomial table f[n][k] (a pure function of n_max and the case fraction) is kept across passes, as the "
                             "reference's own cache does within a run (HC.java:4196-4280); everything else is recomputed every step",
@@ -627,6 +666,7 @@ def main():
     ap.add_argument("--sites", type=int, default=0, help="override sites per GPU (scaled-down runs)")
     ap.add_argument("--replicates", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exact-null", action="store_true", help="skip the exact-null validation of the Monte-Carlo counts (pb_run_extras)")
     ap.add_argument("--full-planes-only", action="store_true", help="e2e leg uploads three planes even when the input is biallelic")
     ap.add_argument("--fused-call", action="store_true", help="e2e leg: the fused pb_run_events_assoc instead of pb_run_events + pb_run_assoc")
     ap.add_argument("--inproc", action="store_true", help="--gpus N from ONE process / one host thread (pb_group) instead of torchrun ranks")

@@ -158,20 +158,34 @@ static void philox_labels_v1(uint64_t seed, uint64_t rep, int32_t P, int32_t n_c
     }
 }
 
-// Spec v2 (P < 65536; DESIGN.md "Philox sampling spec").  Four samples per 64-bit word: group g = samples 4g..4g+c-1,
-// c = min(4, P-4g); x = (w[2(g&1)+1] : w[2(g&1)]) of philox(ctr=(g>>1, rep_lo, rep_hi, 0)).  For j < c with R_j = P-4g-j:
-// x * R_j = u_j * 2^64 + x' (u_j = the draw in [0, R_j); x' goes on as x) — Lemire's multiply-shift for the product range
-// at once, in mixed radix.  Exact iff the final x' >= 2^64 mod prod(R_j); otherwise the group is redrawn from retry word q =
-// (rw[2(q&1)+1] : rw[2(q&1)]) of philox(ctr=(q>>1, rep_lo, rep_hi, 1)), q = 0,1,..
-static void philox_labels_v2(uint64_t seed, uint64_t rep, int32_t P, int32_t n_case, int32_t n_ctrl, uint8_t* out) {
+// Spec v3 (P < 65536; DESIGN.md "Philox sampling spec").  Four samples per 64-bit word: group g = samples 4g..4g+c-1,
+// c = min(4, P-4g); x = (o[2g+1] : o[2g]), o[i] = the i-th output of the replicate's xoshiro128++ stream (Blackman & Vigna:
+// result = rotl(s0 + s3, 7) + s0; t = s1 << 9; s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t; s3 = rotl(s3, 11)) whose
+// 128-bit state starts as philox(ctr=(0, rep_lo, rep_hi, 2), key=seed) (an all-zero block becomes s0 = 1).  For j < c with
+// R_j = P-4g-j: x * R_j = u_j * 2^64 + x' (u_j = the draw in [0, R_j); x' goes on as x) — Lemire's multiply-shift for the
+// product range at once, in mixed radix.  Exact iff the final x' >= 2^64 mod prod(R_j); otherwise the group is redrawn from
+// retry word q = (rw[2(q&1)+1] : rw[2(q&1)]) of philox(ctr=(q>>1, rep_lo, rep_hi, 1)), q = 0,1,.. (the main stream's position
+// does not depend on the retries).  Spec v2 (round 2, superseded) took x from philox(ctr=(g>>1, rep_lo, rep_hi, 0)) instead.
+static inline uint32_t rotl32(uint32_t v, int k) { return (v << k) | (v >> (32 - k)); }
+static inline uint32_t xoshiro128pp_next(uint32_t s[4]) {
+    const uint32_t result = rotl32(s[0] + s[3], 7) + s[0];
+    const uint32_t t = s[1] << 9;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = rotl32(s[3], 11);
+    return result;
+}
+static void philox_labels_v3(uint64_t seed, uint64_t rep, int32_t P, int32_t n_case, int32_t n_ctrl, uint8_t* out) {
     uint32_t rem_case = (uint32_t)n_case, rem_ctrl = (uint32_t)n_ctrl;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t r0 = (uint32_t)rep, r1 = (uint32_t)(rep >> 32);
-    uint32_t w[4] = {0, 0, 0, 0}, rw[4];
+    uint32_t s[4], rw[4];
+    philox4x32_10(0u, r0, r1, 2u, k0, k1, s);
+    if ((s[0] | s[1] | s[2] | s[3]) == 0) s[0] = 1;
     uint32_t q = 0;
     for (int32_t g = 0; 4 * g < P; g++) {
-        if ((g & 1) == 0) philox4x32_10((uint32_t)(g >> 1), r0, r1, 0u, k0, k1, w);
-        uint64_t x = ((uint64_t)w[2 * (g & 1) + 1] << 32) | w[2 * (g & 1)];
+        const uint32_t xl = xoshiro128pp_next(s), xh = xoshiro128pp_next(s);
+        uint64_t x = ((uint64_t)xh << 32) | xl;
         const int c = std::min<int32_t>(4, P - 4 * g);
         const uint32_t range = (uint32_t)(P - 4 * g);
         uint32_t us[4] = {0, 0, 0, 0};
@@ -207,7 +221,7 @@ static void philox_labels_v2(uint64_t seed, uint64_t rep, int32_t P, int32_t n_c
 }
 
 void or_philox_labels(uint64_t seed, uint64_t rep, int32_t P, int32_t n_case, int32_t n_ctrl, uint8_t* out) {
-    if (P < 65536) philox_labels_v2(seed, rep, P, n_case, n_ctrl, out);
+    if (P < 65536) philox_labels_v3(seed, rep, P, n_case, n_ctrl, out);
     else philox_labels_v1(seed, rep, P, n_case, n_ctrl, out);
 }
 

@@ -79,20 +79,33 @@ static_assert(256 % GEN_THREADS == 0 && GEN_THREADS % 32 == 0, "generator blocks
 #define GEN_ILP 4          // Philox blocks computed together (GEN_ROWS must be a multiple of 4 * GEN_ILP)
 #endif
 
-// MODE 0: Philox, batched draws (P < 65536; sampling spec v2 in DESIGN.md §K3a, restated by oracle/oracle.cpp or_philox_labels)
+// MODE 0: batched draws (P < 65536; sampling spec v3 in DESIGN.md section 3, restated by oracle/oracle.cpp or_philox_labels)
 // MODE 1: replay (sample j gets label[perms[rep*P + j]])
 // MODE 2: Philox, one 32-bit word per draw (P >= 65536: four ranges would overflow a 64-bit product; spec v1)
 // One thread = one replicate; a warp ballot turns 32 replicates' labels of one sample into a matrix word.
 //
-// Spec v2.  Replicate `rep` labels samples 0..P-1 sequentially without replacement, four at a time from one 64-bit word:
-// group g = samples 4g..4g+c-1 (c = min(4, P - 4g)), x = (w[2(g&1)+1] : w[2(g&1)]) of Philox4x32-10(ctr = (g>>1, rep_lo,
-// rep_hi, 0), key = seed).  For j = 0..c-1 with R_j = P - 4g - j:  x * R_j = u_j * 2^64 + x'  (u_j = the draw in [0, R_j),
-// x' carries on as x) — Lemire's multiply-shift applied to the product range R_0..R_{c-1} at once: floor(x * prod / 2^64) in
-// mixed radix.  The group is exact-uniform iff the final x' >= 2^64 mod prod(R_j); otherwise x is replaced by the next word of
-// the retry stream (word q of Philox(ctr = (q>>1, rep_lo, rep_hi, 1)), q = 0, 1, ...) and the group is drawn again
-// (probability < prod / 2^64 < 2^-11 per group for P = 5000).  u_j < cases_left -> case, < cases_left + controls_left ->
-// control, else missing.  Half the Philox blocks and one multiply less per draw than spec v1: the generator is bound by
-// the integer-multiply pipe (profiles/r2_k3a_gen_C2_ncu.txt).
+// Spec v3.  Replicate `rep` labels samples 0..P-1 sequentially without replacement, four at a time from one 64-bit word:
+// group g = samples 4g..4g+c-1 (c = min(4, P - 4g)), x = (o[2g+1] : o[2g]) with o[i] = the i-th output of the replicate's
+// xoshiro128++ stream, whose state starts as Philox4x32-10(ctr = (0, rep_lo, rep_hi, 2), key = seed) (all zero -> s0 = 1).
+// For j = 0..c-1 with R_j = P - 4g - j:  x * R_j = u_j * 2^64 + x'  (u_j = the draw in [0, R_j), x' carries on as x) —
+// Lemire's multiply-shift applied to the product range R_0..R_{c-1} at once: floor(x * prod / 2^64) in mixed radix.  The
+// group is exact-uniform iff the final x' >= 2^64 mod prod(R_j); otherwise x is replaced by the next word of the retry
+// stream (word q of Philox(ctr = (q>>1, rep_lo, rep_hi, 1)), q = 0, 1, ...) and the group is drawn again (probability
+// < prod / 2^64 < 2^-11 per group for P = 5000); the main stream's position does not depend on the retries.  u_j <
+// cases_left -> case, < cases_left + controls_left -> control, else missing.
+// Spec v2 (superseded) took x from Philox(ctr = (g>>1, rep_lo, rep_hi, 0)): 2.5 of its 4.5 wide multiplies per label were
+// the ten Philox rounds, on the pipe that bounds the kernel (profiles/r2_k3a_gen_v2_C2_ncu.txt).  The xoshiro step is nine
+// shift / xor / add instructions per 32-bit output and no multiply; Philox still seeds every replicate's stream, so a
+// replicate's labels remain a pure function of (seed, rep).
+__device__ __forceinline__ uint32_t xoshiro128pp_next(uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
+    const uint32_t a = s0 + s3;
+    const uint32_t result = __funnelshift_l(a, a, 7) + s0;
+    const uint32_t t = s1 << 9;
+    s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3;
+    s2 ^= t;
+    s3 = __funnelshift_l(s3, s3, 11);
+    return result;
+}
 // (xh:xl) * R = u * 2^64 + (xh':xl').  Two 32x32->64 multiplies; the cross carry goes through the integer ALU (add.cc / addc),
 // not through a 64-bit multiply-add: the generator is bound by the multiply pipe, and a mad.wide with a 64-bit addend also
 // costs a register move on that pipe to build the addend's zero high word.
@@ -108,7 +121,7 @@ __device__ __forceinline__ void mul64x32(uint32_t& xl, uint32_t& xh, uint32_t R,
     u = b_hi; xl = a_lo; xh = b_lo;
 }
 
-#define GEN_PASS (8 * GEN_ILP)   // samples per pass of the batched generator: GEN_ILP Philox blocks x 2 words x 4 draws
+#define GEN_PASS (8 * GEN_ILP)   // samples per pass of the batched generator: 4 * GEN_ILP stream outputs = 2 * GEN_ILP words x 4 draws
 static_assert(GEN_ROWS % GEN_PASS == 0 && GEN_ROWS % (4 * GEN_ILP) == 0, "a staging tile is a whole number of passes");
 
 // THREADS: replicates per block.  256 normally; 64 when a sharded run leaves this rank so few replicates that 256-thread
@@ -131,6 +144,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 3 : 1)) k3_gen_kern
     if (MODE != 1 && !MISS && !active) rem_case = 0;     // padding replicates of the last block never draw a case: bits stay 0
     const uint32_t* prow = (MODE == 1 && active) ? perms + rep_local * (int64_t)P : nullptr;
     uint32_t range = (uint32_t)P;                         // samples not yet labelled (Philox modes)
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;              // spec v3: the replicate's xoshiro128++ state
+    if (MODE == 0) {
+        uint32_t sw[4];
+        philox4x32_10(0u, r0, r1, 2u, k0, k1, sw);
+        s0 = sw[0]; s1 = sw[1]; s2 = sw[2]; s3 = sw[3];
+        if ((s0 | s1 | s2 | s3) == 0) s0 = 1;
+    }
     // replay mode: the caller's rows are checked while they are consumed — an index >= P is clamped and flagged (it would be an
     // out-of-bounds read of label[]), and a row whose index sum / sum of squares is not a permutation's is flagged as well (a
     // repeated index changes the replicate's case / control totals).  pb_run_assoc returns PB_ERR_INVALID on either.
@@ -186,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 3 : 1)) k3_gen_kern
         }
     };
 
-    // spec v2: one 64-bit word -> `count` (1..4, warp-uniform) samples, exact rejection
+    // spec v3: one 64-bit word -> `count` (1..4, warp-uniform) samples, exact rejection
     auto draw_word = [&](uint32_t xl, uint32_t xh, int row, int count) {
         uint32_t us[4] = {0, 0, 0, 0};
         for (;;) {
@@ -217,16 +237,20 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 3 : 1)) k3_gen_kern
         const int rows = min(GEN_ROWS, P - i0);
         if (MODE == 0) {
             for (int ii = 0; ii < rows; ii += GEN_PASS) {
-                // GEN_ILP independent Philox blocks per pass: their 10-round dependent chains interleave in the pipeline
-                uint32_t w[GEN_ILP][4];
-#pragma unroll
-                for (int q4 = 0; q4 < GEN_ILP; q4++) philox4x32_10((uint32_t)((i0 + ii) >> 3) + q4, r0, r1, 0u, k0, k1, w[q4]);
                 if (!MISS && ii + GEN_PASS <= rows) {
                     // Full pass, binary labels: the draws run without their per-word rejection test.  A retry is needed only if
                     // some word's final low part is below its range product (probability < prod / 2^64 per word): the pass keeps
-                    // the minimum low part, one vote checks it against the pass's largest product, and the rare hit replays the
-                    // whole pass through the exact path from the saved state (same words are overwritten).
+                    // the minimum high half of the low parts, one vote checks it against the high half of the pass's largest
+                    // product (a superset of the true condition), and the rare hit replays the whole pass through the exact path
+                    // from the saved state (same words are overwritten, so how often the vote fires cannot change a result).
                     const uint32_t rem0 = rem_case, range0 = range;
+                    const uint32_t t0 = s0, t1 = s1, t2 = s2, t3 = s3;
+                    uint32_t w[GEN_ILP][4];
+#pragma unroll
+                    for (int q4 = 0; q4 < GEN_ILP; q4++) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) w[q4][k] = xoshiro128pp_next(s0, s1, s2, s3);
+                    }
                     // Two phases, so that a lone warp (a sharded run leaves one or two per scheduler) is not one long dependent
                     // chain: first every draw value — the 2*GEN_ILP words are independent multiply chains, advanced in step —
                     // then the labels, whose only serial dependency is the case counter.
@@ -237,9 +261,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 3 : 1)) k3_gen_kern
                         for (int wi = 0; wi < 2 * GEN_ILP; wi++)
                             mul64x32(w[wi >> 1][2 * (wi & 1)], w[wi >> 1][2 * (wi & 1) + 1], range0 - (uint32_t)(4 * wi + j), us[4 * wi + j]);
                     }
-                    uint64_t mn = ~0ull;
+                    uint32_t mn = ~0u;              // smallest HIGH half of the words' final low parts: a conservative test is enough
 #pragma unroll
-                    for (int wi = 0; wi < 2 * GEN_ILP; wi++) mn = min(mn, ((uint64_t)w[wi >> 1][2 * (wi & 1) + 1] << 32) | w[wi >> 1][2 * (wi & 1)]);
+                    for (int wi = 0; wi < 2 * GEN_ILP; wi++) mn = min(mn, w[wi >> 1][2 * (wi & 1) + 1]);
                     range = range0 - GEN_PASS;
 #pragma unroll
                     for (int k = 0; k < GEN_PASS; k++) {
@@ -249,24 +273,23 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 3 : 1)) k3_gen_kern
                         sc[ii + k][warp] = bc;   // every lane stores the same word: no lane test, one broadcast store
                     }
                     const uint64_t prodmax = (uint64_t)range0 * (range0 - 1) * (uint64_t)(range0 - 2) * (range0 - 3);   // range0 >= GEN_PASS; < 2^64 for P < 65536
-                    if (__any_sync(0xffffffffu, mn < prodmax) || force_replay) {   // force_replay: test hook (PB_GEN_FORCE_REPLAY)
+                    if (__any_sync(0xffffffffu, mn <= (uint32_t)(prodmax >> 32)) || force_replay) {   // force_replay: test hook (PB_GEN_FORCE_REPLAY)
                         rem_case = rem0; range = range0;
+                        s0 = t0; s1 = t1; s2 = t2; s3 = t3;       // cold path: the stream is run again from the pass's first output
 #pragma unroll 1
-                        for (int q4 = 0; q4 < GEN_ILP; q4++) {      // cold path: the Philox words are recomputed, not kept addressable
-                            uint32_t ww[4];
-                            philox4x32_10((uint32_t)((i0 + ii) >> 3) + q4, r0, r1, 0u, k0, k1, ww);
-                            draw_word(ww[0], ww[1], ii + 8 * q4, 4);
-                            draw_word(ww[2], ww[3], ii + 8 * q4 + 4, 4);
+                        for (int wi = 0; wi < 2 * GEN_ILP; wi++) {
+                            const uint32_t xl = xoshiro128pp_next(s0, s1, s2, s3), xh = xoshiro128pp_next(s0, s1, s2, s3);
+                            draw_word(xl, xh, ii + 4 * wi, 4);
                         }
                     }
                 } else {
 #pragma unroll 1
-                    for (int q4 = 0; q4 < GEN_ILP; q4++) {
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const int row = ii + 8 * q4 + 4 * h;
-                            const int count = min(4, rows - row);     // block-uniform
-                            if (count > 0) draw_word(w[q4][2 * h], w[q4][2 * h + 1], row, count);
+                    for (int wi = 0; wi < 2 * GEN_ILP; wi++) {
+                        const int row = ii + 4 * wi;
+                        const int count = min(4, rows - row);     // block-uniform
+                        if (count > 0) {
+                            const uint32_t xl = xoshiro128pp_next(s0, s1, s2, s3), xh = xoshiro128pp_next(s0, s1, s2, s3);
+                            draw_word(xl, xh, row, count);
                         }
                     }
                 }
@@ -893,7 +916,7 @@ static int k3_launch_philox(pb_ctx* ctx, const K3Plan& pl, int64_t base, int64_t
     const int force_replay = getenv("PB_GEN_FORCE_REPLAY") ? 1 : 0;   // every group also goes through the exact Lemire path
     uint32_t* xc = (uint32_t*)(ctx->d_Xcase + buf * pl.buf_words);
     uint32_t* xm = pl.has_miss ? (uint32_t*)(ctx->d_Xmiss + buf * pl.buf_words) : nullptr;
-    const bool batched = ctx->P < 65536;      // spec v2 (four draws per 64-bit word); spec v1 above that
+    const bool batched = ctx->P < 65536;      // spec v3 (four draws per 64-bit word); spec v1 above that
     // fewer than two warps per scheduler: 64-thread blocks spread them over all SMs (see k3_gen_kernel)
     const bool small = batched && ((u1 - u0) * 8 < (int64_t)ctx->sm_count * 8 || getenv("PB_GEN_SMALL_BLOCKS")) && !getenv("PB_GEN_BIG_BLOCKS");   // (env: test hooks)
     const int threads = small ? 64 : GEN_THREADS;

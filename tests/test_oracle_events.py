@@ -186,6 +186,80 @@ def test_philox_labels_are_exact_arrangements(oracle_mod):
     assert tot.std() / 4000 < 0.02
 
 
+def _philox4x32_10(c, k):
+    """Philox4x32-10 (Salmon et al. 2011) in plain Python ints — second opinion for the oracle's restatement."""
+    c0, c1, c2, c3 = c
+    k0, k1 = k
+    M = 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = (p1 >> 32) ^ c1 ^ k0, p1 & M, (p0 >> 32) ^ c3 ^ k1, p0 & M
+        k0, k1 = (k0 + 0x9E3779B9) & M, (k1 + 0xBB67AE85) & M
+    return [c0, c1, c2, c3]
+
+
+def _labels_spec_v3(seed, rep, P, n_case, n_ctrl):
+    """Sampling spec v3 written from its text with Python big ints: xoshiro128++ stream seeded by
+    Philox(ctr=(0, rep, 2)), four draws per 64-bit word by mixed-radix multiply-shift, exact rejection from the Philox retry
+    stream (ctr word 3 = 1)."""
+    M = 0xFFFFFFFF
+    key = (seed & M, seed >> 32)
+    r0, r1 = rep & M, rep >> 32
+    s = _philox4x32_10((0, r0, r1, 2), key)
+    if not any(s):
+        s[0] = 1
+    rotl = lambda v, k: ((v << k) | (v >> (32 - k))) & M
+
+    def nxt():
+        res = (rotl((s[0] + s[3]) & M, 7) + s[0]) & M
+        t = (s[1] << 9) & M
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]
+        s[2] ^= t
+        s[3] = rotl(s[3], 11)
+        return res
+
+    out, q, retries = [], 0, 0
+    for g in range((P + 3) // 4):
+        lo = nxt(); hi = nxt()
+        x = (hi << 32) | lo
+        c = min(4, P - 4 * g)
+        while True:
+            l, prod, us = x, 1, []
+            for j in range(c):
+                R = P - 4 * g - j
+                pr = l * R
+                us.append(pr >> 64); l = pr & (2 ** 64 - 1); prod *= R
+            if l >= (2 ** 64) % prod:
+                break
+            rw = _philox4x32_10((q >> 1, r0, r1, 1), key)
+            x = (rw[2 * (q & 1) + 1] << 32) | rw[2 * (q & 1)]
+            q += 1; retries += 1
+        for u in us:
+            if u < n_case:
+                out.append(1); n_case -= 1
+            elif u < n_case + n_ctrl:
+                out.append(0); n_ctrl -= 1
+            else:
+                out.append(2)
+    return np.array(out, dtype=np.uint8), retries
+
+
+def test_philox_labels_match_spec_v3_text(oracle_mod):
+    """The oracle's C++ restatement of the sampling spec against the plain-Python one above, label for label; the huge-P
+    cases make retries likely enough to be seen (prod(R_j) / 2^64 per group)."""
+    assert _philox4x32_10((0, 0, 0, 0), (0, 0)) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]     # Random123 known answer
+    assert _philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    seen_retry = 0
+    for seed, rep, P, nc, nt in [(1, 0, 1, 1, 0), (2, 5, 2, 1, 1), (3, 7, 3, 1, 1), (4, 9, 4, 2, 2), (5, 11, 5, 2, 2), (99, 3, 203, 70, 120),
+                                 (2 ** 63 + 12345, 2 ** 40 + 17, 1301, 400, 880), (20260, 99999, 5000, 1900, 3100),
+                                 (7, 1, 65535, 30000, 35000), (7, 2, 65535, 20000, 30000), (8, 3, 60001, 30000, 30001)]:
+        want, retries = _labels_spec_v3(seed, rep, P, nc, nt)
+        got = oracle_mod.philox_labels(seed, rep, P, nc, nt)
+        assert np.array_equal(got, want), (seed, rep, P)
+        seen_retry += retries
+    assert seen_retry > 0
+
+
 def test_c1_slice_regression(oracle_mod, golden_dir):
     z = np.load(os.path.join(golden_dir, "c1_slice.npz"))
     S, m = int(z["n_sites"]), int(z["m"])
