@@ -537,7 +537,7 @@ def run_b200(args):
     # outputs of the last timed step (views of page-locked buffers the next call overwrites): kept for the parity check
     par_outputs = [("headline", np.array(ev[:CPU_SAMPLE_SITES]), np.array(st))]
     exact_null = None
-    if rank == 0 and not args.no_exact_null:       # validator of the Philox-mode null that was just timed (this rank's shard)
+    if rank == 0 and n_gpus == 1 and not args.no_exact_null:       # validator of the Philox-mode null that was just timed
         exact_null = exact_null_check(hc, st, m)
     e2e_breakdown = {k: v / args.steps for k, v in e2e_parts.items()}
     e2e_step_ms = list(e2e_steps)
