@@ -232,8 +232,8 @@ def bench_config(args, cfg, S, m, tree, world, scaling="weak", launch="one proce
 
 def k3_rooflines(tm, parts, m, P, has_miss, n_shards=1):
     """The two resampling kernels against their own ceilings (ncu captures under profiles/r2_k3*):
-    K3a (label generator) is bound by the integer-multiply (fmaheavy) pipe — its ceiling is an instruction-issue one, the
-    fraction comes from the committed capture; K3b (replicate counting) is bound by L2 -> SM bandwidth: algorithmic bytes =
+    K3a (label generator, sampling spec v3) is bound by warp-instruction issue — an issue-rate ceiling has no live byte count,
+    the fraction (issue slots busy over the launch) comes from the committed capture; K3b (replicate counting) is bound by L2 -> SM bandwidth: algorithmic bytes =
     sum over swept alleles of n rows x m/8 bytes, against the L2 read bandwidth measured on this GPU
     (tools/microbench/l2_peak -> profiles/r2_l2_peak.json)."""
     def load(name):
@@ -246,11 +246,12 @@ def k3_rooflines(tm, parts, m, P, has_miss, n_shards=1):
     ceil = load("k3_ceilings.json")
     l2_peak = l2.get("l2_read_gbs_16B_per_lane")
     swept_bytes = float(tm.get("n_swept_rows", 0)) / n_shards * (m / 8.0) * (2 if has_miss else 1)   # per GPU (a group sums its shards)
-    out = {"k3a_label_generator": {"bound": "integer-multiply pipe (fmaheavy): Philox4x32-10 + Lemire draws",
+    out = {"k3a_label_generator": {"bound": "warp-instruction issue: xoshiro128++ stream + four multiply-shift draws per 64-bit word, one thread per replicate",
                                    "draws_per_s": (m * P) / (parts["ms_gen_kernel"] / 1e3) if parts.get("ms_gen_kernel") else None,
                                    "ms": parts.get("ms_gen_kernel"),
-                                   "frac": ceil.get("k3_gen_kernel", {}).get("fmaheavy_pipe_frac"),
-                                   "frac_source": "ncu sm__pipe_fmaheavy_cycles_active (profiles/r2_final_k3a_gen_ncu.txt, via profiles/k3_ceilings.json)"},
+                                   "frac": ceil.get("k3_gen_kernel", {}).get("issue_frac"),
+                                   "frac_busiest_sm": ceil.get("k3_gen_kernel", {}).get("issue_frac_busiest_sm"),
+                                   "frac_source": "ncu smsp__issue_active (profiles/r2_final_k3a_gen_ncu.txt, via profiles/k3_ceilings.json)"},
            "k3b_replicate_count": {"bound": "l2", "unit": "GB/s", "algorithmic_bytes": swept_bytes, "ms": parts.get("ms_null_count"),
                                    "achieved": swept_bytes / (parts["ms_null_count"] / 1e3) / 1e9 if parts.get("ms_null_count") else None,
                                    "peak": l2_peak, "peak_source": "measured: tools/microbench/l2_peak (L2-resident stream, 16 B per lane, L1 bypassed)"}}
