@@ -121,6 +121,9 @@ __device__ __forceinline__ void mul64x32(uint32_t& xl, uint32_t& xh, uint32_t R,
     u = b_hi; xl = a_lo; xh = b_lo;
 }
 
+#ifndef GEN_MIN_BLOCKS
+#define GEN_MIN_BLOCKS 3   // register cap of the 256-thread generator through __launch_bounds__ (3: 85, 5: 48, 6: 40 registers)
+#endif
 #define GEN_PASS (8 * GEN_ILP)   // samples per pass of the batched generator: 4 * GEN_ILP stream outputs = 2 * GEN_ILP words x 4 draws
 static_assert(GEN_ROWS % GEN_PASS == 0 && GEN_ROWS % (4 * GEN_ILP) == 0, "a staging tile is a whole number of passes");
 
@@ -128,7 +131,7 @@ static_assert(GEN_ROWS % GEN_PASS == 0 && GEN_ROWS % (4 * GEN_ILP) == 0, "a stag
 // blocks would occupy a third of the SMs with two warps per scheduler each — the multiply pipe is per scheduler, so the
 // same warps spread one per scheduler finish in half the time.
 template <int MODE, bool MISS, int THREADS = GEN_THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 3 : 1)) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
+__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? GEN_MIN_BLOCKS : 1)) k3_gen_kernel(uint64_t seed, int64_t rep_base, int64_t n_reps, int32_t P, int32_t n_case,
                                                              int32_t n_ctrl, const uint8_t* __restrict__ label,
                                                              const uint32_t* __restrict__ perms, uint32_t* __restrict__ Xc32,
                                                              uint32_t* __restrict__ Xm32, int64_t Rw32, int force_replay = 0,

@@ -638,7 +638,8 @@ static int run_events_impl(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* 
         }
         // (Tried: starting the generator behind the tail's record-count kernel instead of behind the sweep — that kernel then runs
         // alone (276 -> 58 us at C2) but finalize+compact inherits the squeeze (115 -> 290 us): whichever tail kernel shares the SMs
-        // with the generator's 24 resident warps / 44k registers per SM runs at a third of its occupancy.  No gain; not kept.)
+        // with the generator pays for it (issue slots: capping the generator's registers so that more tail warps fit changed nothing).
+        // No gain; not kept.)
         if (attempt == 0 && !ctx->pregen_valid && (rc = pbk_pregen_labels(ctx, false))) return rc;
         unsigned long long cur = 0;
         if ((rc = pbk_finalize_events(ctx, counts, &cur))) return rc;   // the whole tail, one host round trip at its end
