@@ -524,6 +524,11 @@ def run_b200(args):
     roofline_k3 = k3_rooflines(tm, parts, m, len(lab), has_miss, n_shards)
 
     # ---- timed: end to end through the public API with host buffers ------------------------------------
+    # pb_expect_site_output: the per-site records of tiles whose sweep and tail ran underneath the upload come back underneath it
+    # too (a single context's streaming call; a pb_group merges its shards' records itself)
+    early_output = not inproc and not args.no_early_output
+    if early_output:
+        hc.expect_site_output()
     for _ in range(min(args.warmup, 3)):
         step_e2e()
     barrier()
@@ -623,6 +628,8 @@ def run_b200(args):
                                     "X + V planes + site masks, expanded to three planes on the device"))
                                   if all_compact else "pb_put_planes_async (three planes)",
                         "swept_under_upload_words": eager_words,
+                        "tail_under_upload_words": int(tm_e.get("tailed_words", 0)),
+                        "site_records_returned_under_upload": int(tm_e.get("early_sites", 0)),
                         "calls": "pb_run_events_assoc (one call; `events` in breakdown_ms covers both)" if fused_call else "pb_run_events + pb_run_assoc",
                         "compaction_in_timed_region": False,
                         "input_format": "the compact format the one-pass host packer emits (see host_packer); the synthetic generator produces "
@@ -667,6 +674,7 @@ def main():
     ap.add_argument("--sites", type=int, default=0, help="override sites per GPU (scaled-down runs)")
     ap.add_argument("--replicates", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-early-output", action="store_true", help="e2e leg without pb_expect_site_output (per-site records copied back by pb_run_events)")
     ap.add_argument("--no-exact-null", action="store_true", help="skip the exact-null validation of the Monte-Carlo counts (pb_run_extras)")
     ap.add_argument("--full-planes-only", action="store_true", help="e2e leg uploads three planes even when the input is biallelic")
     ap.add_argument("--fused-call", action="store_true", help="e2e leg: the fused pb_run_events_assoc instead of pb_run_events + pb_run_assoc")

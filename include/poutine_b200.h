@@ -121,6 +121,8 @@ typedef struct {
     int64_t n_swept_rows;     /* K3b: label-matrix rows read per replicate word, summed over the swept alleles (x m/8 B = its L2 traffic) */
     float ms_gen_kernel;      /* K3a: the label generator's own time for the first replicate tile (events on its stream) */
     float gen_shard_frac;     /* fraction of the label matrix this context drew itself: 1, or 1/world when the shards share it */
+    int64_t tailed_words;     /* site words whose tail (counts, per-site records, compaction, CSR) ran ahead of pb_run_events as well (<= eager_words) */
+    int64_t early_sites;      /* per-site records that were already on their way to the host when pb_run_events was called (pb_expect_site_output) */
 } pb_timings;
 
 int pb_create(const pb_config* cfg, pb_ctx** out);
@@ -172,6 +174,15 @@ int pb_put_planes_async(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_
 int pb_put_planes_biallelic_async(pb_ctx* ctx, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
                                   const uint64_t* X, const uint64_t* V, const uint64_t* colmask);
 int pb_upload_sync(pb_ctx* ctx);
+/* Optional, before the streamed upload of a pass: where the coming pb_run_events will be asked to put its per_site records
+ * (n_sites records; page-locked memory, pb_host_alloc, if the copies are to overlap anything).  One-plane tiles that are swept
+ * underneath the upload then have their tail — event counts, Homoplasy_Events fields, the informative-site compaction, the
+ * CSR of extant events — run there as well (needs pb_set_labels before the upload), and their finished records travel back
+ * while later tiles are still going up: PCIe is full duplex.  pb_run_events(ctx, the same pointer, ...) then handles only
+ * what is left (usually the last tile) and returns when every record has landed.  The registration stays until it is replaced
+ * (NULL = none); the buffer must stay valid until the pb_run_events that delivers into it has returned.  Results are
+ * identical with and without it. */
+int pb_expect_site_output(pb_ctx* ctx, pb_site_out* per_site);
 
 /* count_all_homoplasy_events (HC.java:1402).  per_site (n_sites records) and counts may be NULL.
  * If pb_set_labels was called before (Philox mode), the label matrix of the first replicate tile is generated on a
@@ -264,6 +275,7 @@ int pb_group_put_planes_async(pb_group* g, int64_t word_begin, int64_t n_words, 
 int pb_group_put_planes_biallelic_async(pb_group* g, int64_t word_begin, int64_t n_words, int64_t src_pitch_words,
                                         const uint64_t* X, const uint64_t* V, const uint64_t* colmask);
 int pb_group_upload_sync(pb_group* g);
+int pb_group_expect_site_output(pb_group* g, pb_site_out* per_site /* n_sites records, alignment order; after pb_group_set_sites */);
 int pb_group_run_events(pb_group* g, pb_site_out* per_site /* n_sites, may be NULL */, pb_class_counts* counts);
 int pb_group_run_assoc(pb_group* g, const uint32_t* replay_perms, pb_stat_out* per_inf_site, int64_t cap, int64_t* n_inf,
                        double* maxT_sorted);

@@ -46,7 +46,7 @@ class PbTimings(C.Structure):
                                          "ms_assoc_total")] + \
                [(n, C.c_int64) for n in ("n_launches", "k1_algorithmic_bytes", "n_informative", "n_alleles_in_use",
                                          "n_extant_events", "n_fast_alleles", "n_maxt_fallback_reps", "plane_mode", "eager_words", "n_swept_rows")] + \
-               [("ms_gen_kernel", C.c_float), ("gen_shard_frac", C.c_float)]
+               [("ms_gen_kernel", C.c_float), ("gen_shard_frac", C.c_float), ("tailed_words", C.c_int64), ("early_sites", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -59,11 +59,12 @@ EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_set_tree", "pb_set_la
            "pb_pack_chars", "pb_host_alloc", "pb_host_free", "pb_version",
            "pb_fasta_open", "pb_fasta_close", "pb_fasta_num_records", "pb_fasta_record", "pb_fasta_pack_tile", "pb_fasta_last_error",
            "pb_comm_export", "pb_comm_connect", "pb_comm_export_labels", "pb_comm_connect_labels", "pb_fasta_pack_tile_biallelic", "pb_pack_chars_biallelic",
-           "pb_run_events_assoc", "pb_put_planes_async", "pb_put_planes_biallelic_async", "pb_upload_sync",
+           "pb_run_events_assoc", "pb_put_planes_async", "pb_put_planes_biallelic_async", "pb_upload_sync", "pb_expect_site_output",
            "pb_group_create", "pb_group_destroy", "pb_group_last_error", "pb_group_size", "pb_group_ctx", "pb_group_set_tree",
            "pb_group_set_labels", "pb_group_set_sites", "pb_group_shard_range", "pb_group_put_planes", "pb_group_put_planes_biallelic",
            "pb_group_run_events", "pb_group_run_assoc", "pb_group_run_extras", "pb_group_get_timings", "pb_group_stopwatch_mark",
-           "pb_group_stopwatch_ms", "pb_group_put_planes_async", "pb_group_put_planes_biallelic_async", "pb_group_upload_sync"]
+           "pb_group_stopwatch_ms", "pb_group_put_planes_async", "pb_group_put_planes_biallelic_async", "pb_group_upload_sync",
+           "pb_group_expect_site_output"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -122,6 +123,8 @@ def lib():
         L.pb_put_planes_async.argtypes = [vp, i64, i64, i64, vp, vp, vp]
         L.pb_put_planes_biallelic_async.argtypes = [vp, i64, i64, i64, vp, vp, vp]
         L.pb_upload_sync.argtypes = [vp]
+        L.pb_expect_site_output.argtypes = [vp, vp]
+        L.pb_group_expect_site_output.argtypes = [vp, vp]
         L.pb_comm_export.argtypes = [vp, vp]
         L.pb_comm_connect.argtypes = [vp, vp, i32, i32]
         L.pb_comm_export_labels.argtypes = [vp, vp]

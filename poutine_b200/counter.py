@@ -136,10 +136,17 @@ class HomoplasyCounter:
         times slower.  The returned array is a VIEW that the next call of the same entry point overwrites."""
         cur = self._pinned.get(name)
         if cur is None or len(cur[0]) < n:
+            registered = name == "sites" and getattr(self, "_expect_sites", False)
+            if registered:          # the library must not keep a pointer into the buffer that is about to go
+                self._expect_sites = False
+                self._check(self._fn("expect_site_output")(self._h, None))
             if cur is not None:
                 _lib.pinned_free(cur[1])
             cap = max(int(n), 1)
             self._pinned[name] = _lib.pinned_empty((cap,), dtype)
+            if registered:
+                self._expect_sites = True
+                self._check(self._fn("expect_site_output")(self._h, ptr(self._pinned[name][0])))
         return self._pinned[name][0][:n]
 
     def __del__(self):
@@ -187,6 +194,14 @@ class HomoplasyCounter:
         """wait until every asynchronous upload has left the host buffers"""
         self._check(self._fn("upload_sync")(self._h))
         self._inflight = []
+
+    def expect_site_output(self, enable=True):
+        """Before a streamed upload (after set_sites): tell the library where count_all_homoplasy_events will want its per-site
+        records — this object's page-locked `sites` buffer — so that tiles whose sweep and tail ran underneath the upload send
+        their records back underneath it too (pb_expect_site_output / pb_group_expect_site_output).  Same results either way."""
+        buf = self._result_buffer("sites", self.n_sites, SITE_DTYPE) if enable else None
+        self._check(self._fn("expect_site_output")(self._h, ptr(buf)))
+        self._expect_sites = bool(enable)
 
     def put_planes_biallelic(self, X, V, colmask, word_begin=0, asynchronous=False):
         """Compact upload of a column tile whose sites carry at most two bases (see compact_planes): X, optionally V

@@ -536,13 +536,15 @@ __device__ __forceinline__ uint32_t event_base(const ev_rec_t& e, int b, const u
 // the record list's length lives on the device (the sweep's cursor, clamped to the buffer): no host round trip before the tail.
 // One-plane mode also accumulates the census sum (see xrec_t): xcensus[site] += (X_child ? +1 : -1) * leaves_below(child).
 template <bool XMODE>
-__global__ void k1_count_events_kernel(const raw_rec_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
+__global__ void k1_count_events_kernel(const raw_rec_t* __restrict__ raw, const unsigned long long* __restrict__ begin,
+                                       const unsigned long long* __restrict__ cursor, int64_t raw_cap,
                                        const int32_t* __restrict__ node_sample, const int32_t* __restrict__ leaves_below,
                                        const uint64_t* __restrict__ xmask, uint32_t* __restrict__ cnt, int32_t* __restrict__ xcensus,
                                        unsigned long long* __restrict__ n_events) {
-    const int64_t n = min((int64_t)*cursor, raw_cap);
+    // records [*begin, *cursor): the whole list, or what one uploaded tile's sweep appended (tail run underneath the upload)
+    const int64_t n = min((int64_t)*cursor, raw_cap), i0 = min((int64_t)*begin, n);
     unsigned int nev = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const ev_rec_t r = load_rec<XMODE>(raw, i);
         const bool sampled = r.leaf && node_sample[r.node] >= 0;
         int32_t delta = 0;
@@ -793,14 +795,15 @@ __global__ void __launch_bounds__(TAIL_TILE) k1_finalize_compact_kernel(
 
 // ---- CSR of extant events ------------------------------------------------------------------------------------------
 template <bool XMODE>
-__global__ void k1_scatter_events_kernel(const raw_rec_t* __restrict__ raw, const unsigned long long* __restrict__ cursor, int64_t raw_cap,
+__global__ void k1_scatter_events_kernel(const raw_rec_t* __restrict__ raw, const unsigned long long* __restrict__ begin,
+                                         const unsigned long long* __restrict__ cursor, int64_t raw_cap,
                                          const int32_t* __restrict__ node_sample, const uint8_t* __restrict__ flags,
                                          const uint64_t* __restrict__ scan, const AlleleMeta* __restrict__ alleles,
                                          const uint64_t* __restrict__ xmask, uint32_t* __restrict__ csr_cursor, int32_t* __restrict__ csr,
                                          int64_t csr_cap, unsigned long long* __restrict__ cursor_copy) {
-    const int64_t n = min((int64_t)*cursor, raw_cap);
+    const int64_t n = min((int64_t)*cursor, raw_cap), i0 = min((int64_t)*begin, n);
     if (blockIdx.x == 0 && threadIdx.x == 0) *cursor_copy = *cursor;   // the sweep's record count joins the tail's one readback
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const ev_rec_t r = load_rec<XMODE>(raw, i);
         if (!r.leaf || r.nomrca) continue;                // extant (leaf) events only (EXTANT_NODES_ONLY, HC.java:173)
         const int32_t smp = node_sample[r.node];
@@ -1000,36 +1003,38 @@ int pbk_prepare_tail(pb_ctx* ctx) {
     return PB_OK;
 }
 
-int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out) {
+// The tail over the records [*rec_begin, *rec_end) and the TAIL_TILE-site tiles [tile0, tile0 + n_tiles) — the whole pass, or (one-plane
+// mode) what one uploaded column tile's sweep appended: record counts -> per-site finalisation + compaction -> CSR of extant events.
+// The single-pass scan hands out tile ids by ticket, so consecutive launches simply continue where the previous one stopped.
+static int tail_launch(pb_ctx* ctx, const unsigned long long* rec_begin, const unsigned long long* rec_end, int64_t n_tiles, unsigned ev_blocks) {
     const int64_t S = ctx->S;
     const int T = 256;
     cudaStream_t st = ctx->stream;
-    const unsigned ev_blocks = (unsigned)std::min<int64_t>((ctx->raw_cap + T - 1) / T, (int64_t)ctx->sm_count * 16);
-    PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_zero_done, 0));   // counters, cursors, scan state, class counts zeroed underneath K1 (pbk_prepare_tail)
-    pb_trace_mark(ctx, "headstart+memsets");
     const bool xmode = ctx->plane_mode == PB_PLANES_X;
     const uint64_t* xmask = xmode ? ctx->d_xmask : nullptr;
     int32_t* xcensus = reinterpret_cast<int32_t*>(ctx->d_cnt + S * PB_CNT_STRIDE);
     int kt_used = 1;
     while ((1ll << kt_used) <= (int64_t)ctx->L) kt_used++;
-    const unsigned n_tiles = (unsigned)((S + TAIL_TILE - 1) / TAIL_TILE);
     if (xmode) {
         // one-plane mode: the leaf census is a by-product of the record pass (no dense counters, nothing to reduce)
-        k1_count_events_kernel<true><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_leaves_below,
+        k1_count_events_kernel<true><<<ev_blocks, T, 0, st>>>(ctx->d_raw, rec_begin, rec_end, ctx->raw_cap, ctx->d_node_sample, ctx->d_leaves_below,
                                                               xmask, ctx->d_cnt, xcensus, ctx->d_class_counts + 9);
         pb_trace_mark(ctx, "count_events");
-        k1_finalize_compact_kernel<true><<<n_tiles, TAIL_TILE, 0, st>>>(
-            nullptr, xcensus, kt_used, ctx->W, S, ctx->d_X, ctx->d_xmask, ctx->d_xvalid, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt,
-            ctx->cfg.min_hcount, ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan, ctx->d_inf_site, ctx->d_alleles,
-            ctx->d_scan_state, ctx->d_class_counts);
-        ctx->tm.n_launches += 2;
+        ctx->tm.n_launches += 1;
+        if (n_tiles > 0) {
+            k1_finalize_compact_kernel<true><<<(unsigned)n_tiles, TAIL_TILE, 0, st>>>(
+                nullptr, xcensus, kt_used, ctx->W, S, ctx->d_X, ctx->d_xmask, ctx->d_xvalid, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt,
+                ctx->cfg.min_hcount, ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan, ctx->d_inf_site, ctx->d_alleles,
+                ctx->d_scan_state, ctx->d_class_counts);
+            ctx->tm.n_launches += 1;
+        }
     } else {
-        k1_count_events_kernel<false><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, nullptr, nullptr,
+        k1_count_events_kernel<false><<<ev_blocks, T, 0, st>>>(ctx->d_raw, rec_begin, rec_end, ctx->raw_cap, ctx->d_node_sample, nullptr, nullptr,
                                                                ctx->d_cnt, nullptr, ctx->d_class_counts + 9);
         pb_trace_mark(ctx, "count_events");
         k1_census_reduce_kernel<<<dim3((unsigned)((ctx->W + 127) / 128), 4), 128, 0, st>>>(ctx->d_census, ctx->n_flush, ctx->W, ctx->d_census_total);
         pb_trace_mark(ctx, "census_reduce");
-        k1_finalize_compact_kernel<false><<<n_tiles, TAIL_TILE, 0, st>>>(
+        k1_finalize_compact_kernel<false><<<(unsigned)n_tiles, TAIL_TILE, 0, st>>>(
             ctx->d_census_total, nullptr, kt_used, ctx->W, S, ctx->d_B0, ctx->d_B1, ctx->d_V, ctx->Wp, ctx->root, ctx->L, ctx->d_cnt, ctx->cfg.min_hcount,
             ctx->cfg.site_offset, ctx->d_sites, ctx->d_site_flags, ctx->d_site_scan, ctx->d_inf_site, ctx->d_alleles, ctx->d_scan_state,
             ctx->d_class_counts);
@@ -1039,14 +1044,67 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     PB_CUDA(cudaGetLastError());
     uint64_t* scan_out = ctx->d_site_scan;
     if (xmode)
-        k1_scatter_events_kernel<true><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
+        k1_scatter_events_kernel<true><<<ev_blocks, T, 0, st>>>(ctx->d_raw, rec_begin, rec_end, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
                                                                scan_out, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr, ctx->csr_cap, ctx->d_class_counts + 8);
     else
-        k1_scatter_events_kernel<false><<<ev_blocks, T, 0, st>>>(ctx->d_raw, ctx->d_raw_cursor, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
+        k1_scatter_events_kernel<false><<<ev_blocks, T, 0, st>>>(ctx->d_raw, rec_begin, rec_end, ctx->raw_cap, ctx->d_node_sample, ctx->d_site_flags,
                                                                 scan_out, ctx->d_alleles, xmask, ctx->d_csr_cursor, ctx->d_csr, ctx->csr_cap, ctx->d_class_counts + 8);
     pb_trace_mark(ctx, "scatter_events");
     ctx->tm.n_launches += 1;
     PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// One-plane mode, streamed upload: the tail of the column tile [word_begin, word_begin + n_words) that eager_sweep (pb_api.cu) has just
+// swept, enqueued behind that sweep — it runs underneath the next tile's copy like the sweep does — and, when the host has said
+// where the per-site records go (pb_expect_site_output), their copy back on the download stream: PCIe is full duplex and the
+// device-to-host direction is idle during the upload.  pb_run_events then finds only the last tile's tail left.
+// Tiles arrive in column order and are cut at multiples of 256 site words, so their sites are whole TAIL_TILE tiles.
+int pbk_tail_tile(pb_ctx* ctx, int64_t word_begin, int64_t n_words) {
+    if (ctx->tail_tiles >= PB_MAX_TAIL_TILES || word_begin != ctx->tailed_words) return PB_OK;   // (the rest is left to pb_run_events)
+    cudaStream_t st = ctx->stream;
+    const int t = ctx->tail_tiles;
+    if (!ctx->d_rec_range) {
+        PB_CUDA(cudaMalloc(&ctx->d_rec_range, (PB_MAX_TAIL_TILES + 1) * sizeof(unsigned long long)));
+        PB_CUDA(cudaMemset(ctx->d_rec_range, 0, (PB_MAX_TAIL_TILES + 1) * sizeof(unsigned long long)));    // [0] = 0 for good
+    }
+    // the record cursor as this tile's sweep left it = the end of its record range
+    PB_CUDA(cudaMemcpyAsync(ctx->d_rec_range + t + 1, ctx->d_raw_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    if (t == 0) PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_zero_done, 0));     // pbk_prepare_tail's zero fills (second stream)
+    const int64_t s0 = word_begin * 64, s1 = std::min<int64_t>(ctx->S, (word_begin + n_words) * 64);
+    const int64_t n_tiles = (s1 - s0 + TAIL_TILE - 1) / TAIL_TILE;
+    int rc = tail_launch(ctx, ctx->d_rec_range + t, ctx->d_rec_range + t + 1, n_tiles, (unsigned)ctx->sm_count * 4);
+    if (rc) return rc;
+    ctx->tail_tiles = t + 1;
+    ctx->tailed_words = word_begin + n_words;
+    if (ctx->out_sites && ctx->sent_sites == s0) {
+        PB_CUDA(cudaEventRecord(ctx->ev_tail_tile, st));
+        PB_CUDA(cudaStreamWaitEvent(ctx->dl, ctx->ev_tail_tile, 0));
+        PB_CUDA(cudaMemcpyAsync(ctx->out_sites + s0, ctx->d_sites + s0, (size_t)(s1 - s0) * sizeof(pb_site_out), cudaMemcpyDeviceToHost, ctx->dl));
+        ctx->sent_sites = s1;
+    }
+    return PB_OK;
+}
+
+// tailed_words: site words whose tail ran ahead of this call (pbk_tail_tile), 0 = none
+int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out, int64_t tailed_words) {
+    const int64_t S = ctx->S;
+    const int T = 256;
+    cudaStream_t st = ctx->stream;
+    const unsigned ev_blocks = (unsigned)std::min<int64_t>((ctx->raw_cap + T - 1) / T, (int64_t)ctx->sm_count * 16);
+    PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_zero_done, 0));   // counters, cursors, scan state, class counts zeroed underneath K1 (pbk_prepare_tail)
+    pb_trace_mark(ctx, "headstart+memsets");
+    if (!ctx->d_rec_range) {
+        PB_CUDA(cudaMalloc(&ctx->d_rec_range, (PB_MAX_TAIL_TILES + 1) * sizeof(unsigned long long)));
+        PB_CUDA(cudaMemset(ctx->d_rec_range, 0, (PB_MAX_TAIL_TILES + 1) * sizeof(unsigned long long)));
+    }
+    const int64_t all_tiles = (S + TAIL_TILE - 1) / TAIL_TILE;
+    const int64_t done_tiles = tailed_words > 0 ? std::min<int64_t>(all_tiles, (tailed_words * 64 + TAIL_TILE - 1) / TAIL_TILE) : 0;
+    const unsigned long long* rec_begin = ctx->d_rec_range + (tailed_words > 0 ? ctx->tail_tiles : 0);
+    {
+        int rc = tail_launch(ctx, rec_begin, ctx->d_raw_cursor, all_tiles - done_tiles, tailed_words > 0 ? (unsigned)ctx->sm_count * 4 : ev_blocks);
+        if (rc) return rc;
+    }
     unsigned long long h[16];
     PB_CUDA(cudaMemcpyAsync(h, ctx->d_class_counts, sizeof(h), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));

@@ -20,7 +20,7 @@ static void free_all(pb_ctx* c) {
     void* ptrs[] = {c->d_ops, c->d_chunk_op, c->d_ops_x, c->d_chunk_op_x, c->d_node_sample, c->d_leaves_below, c->d_label, c->d_planes,
                     c->d_census, c->d_census_total, c->d_raw, c->d_raw_cursor, c->d_cnt, c->d_sites, c->d_site_flags, c->d_site_scan, c->d_class_counts,
                     c->d_inf_site, c->d_alleles, c->d_csr, c->d_csr_cursor, c->d_ptable, c->d_thr, c->d_pobs, c->d_r, c->d_maxT_own,
-                    c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop, c->d_colmask, c->d_extras, c->d_X, c->d_xmask, c->d_xvalid, c->d_scan_state, c->d_tabkeys, c->d_binhist, c->d_bincum, c->d_pooled_own};
+                    c->d_maxT_sorted, c->d_Xcase, c->d_Xmiss, c->d_perms, c->d_stats, c->d_fb_reps, c->d_fb_count, c->d_work, c->d_colpop, c->d_colmask, c->d_extras, c->d_X, c->d_xmask, c->d_xvalid, c->d_scan_state, c->d_tabkeys, c->d_binhist, c->d_bincum, c->d_pooled_own, c->d_rec_range};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -73,7 +73,10 @@ extern "C" int pb_create(const pb_config* cfg, pb_ctx** out) {
         if ((e = cudaStreamCreateWithPriority(&ctx->stream2_lo, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("cudaStreamCreate", e);
         if ((e = cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
         if ((e = cudaStreamCreateWithFlags(&ctx->upl, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithFlags(&ctx->dl, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_tail_tile, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    ctx->eager_tail_ok = getenv("PB_NO_EAGER_TAIL") == nullptr;
     if ((e = cudaEventCreateWithFlags(&ctx->ev_upl, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev_gen_t0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev_gen_t1)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -106,7 +109,10 @@ extern "C" void pb_destroy(pb_ctx* ctx) {
     if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
     if (ctx->stream2_lo) cudaStreamSynchronize(ctx->stream2_lo);
     if (ctx->upl) cudaStreamSynchronize(ctx->upl);
+    if (ctx->dl) cudaStreamSynchronize(ctx->dl);
     free_all(ctx);
+    if (ctx->dl) cudaStreamDestroy(ctx->dl);
+    if (ctx->ev_tail_tile) cudaEventDestroy(ctx->ev_tail_tile);
     if (ctx->stream2_lo) cudaStreamDestroy(ctx->stream2_lo);
     if (ctx->ev_upl) cudaEventDestroy(ctx->ev_upl);
     if (ctx->ev_gen_t0) cudaEventDestroy(ctx->ev_gen_t0);
@@ -527,16 +533,21 @@ static int eager_sweep(pb_ctx* ctx, int64_t word_begin, int64_t n_words) {
     // a tile that starts at word 0 always opens a new pass (whatever was swept before is discarded by the cursor reset)
     const bool in_order = ctx->eager_ok && ctx->plane_mode == PB_PLANES_X && (word_begin == 0 || word_begin == ctx->swept_words) && word_begin % cols == 0 &&
                           ((word_begin + n_words) % cols == 0 || word_begin + n_words == ctx->W) && ctx->N > 0;
-    if (!in_order) { ctx->swept_words = 0; return PB_OK; }
+    if (!in_order) { ctx->swept_words = 0; ctx->tailed_words = 0; return PB_OK; }
     int rc;
     if (word_begin == 0) {
         ctx->tm = pb_timings{};
+        if (ctx->dl) PB_CUDA(cudaStreamSynchronize(ctx->dl));     // (a dropped pass may still be copying records out)
+        ctx->tailed_words = 0; ctx->tail_tiles = 0; ctx->sent_sites = 0;
         if ((rc = pbk_prepare_tail(ctx))) return rc;
         if (!ctx->pregen_valid && (rc = pbk_pregen_labels(ctx, true))) return rc;
     }
     PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_upl, 0));
     if ((rc = pbk_events_range(ctx, word_begin / cols, (n_words + cols - 1) / cols, word_begin == 0, false))) return rc;
     ctx->swept_words = word_begin + n_words;
+    // ... and its tail.  Needs the phenotype rows (which leaves are sampled decides the tallies and the CSR): a host that sets its
+    // labels after the upload gets the whole tail in pb_run_events, as before (pb_set_labels drops everything done ahead).
+    if (ctx->eager_tail_ok && ctx->P > 0 && (rc = pbk_tail_tile(ctx, word_begin, n_words))) return rc;
     return PB_OK;
 }
 
@@ -605,6 +616,15 @@ extern "C" int pb_upload_sync(pb_ctx* ctx) {
     return PB_OK;
 }
 
+extern "C" int pb_expect_site_output(pb_ctx* ctx, pb_site_out* per_site) {
+    CHECK_CTX(ctx);
+    PB_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->dl) PB_CUDA(cudaStreamSynchronize(ctx->dl));     // nothing may still be writing to the previous buffer
+    ctx->out_sites = per_site;
+    ctx->sent_sites = 0;
+    return PB_OK;
+}
+
 // defer_sites_copy: the per-site records go to the host on the upload stream's sibling copy queue WITHOUT waiting for them
 // (pb_run_events_assoc lets that copy run underneath the association kernels and waits at its own end)
 static int run_events_impl(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* counts, bool defer_sites_copy) {
@@ -620,9 +640,12 @@ static int run_events_impl(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* 
     // tiles swept ahead of this call (eager_sweep): their timings / launch counts belong to this pass
     const bool ahead = ctx->swept_words > 0 && ctx->plane_mode == PB_PLANES_X;
     const int64_t swept = ahead ? ctx->swept_words : 0;
-    ctx->swept_words = 0;
+    int64_t tailed = ahead ? ctx->tailed_words : 0;        // tiles whose tail ran underneath the upload too
+    int64_t sent = (tailed > 0 && per_site && per_site == ctx->out_sites) ? ctx->sent_sites : 0;   // ... and whose records are on their way
+    ctx->swept_words = 0; ctx->tailed_words = 0; ctx->sent_sites = 0;
     if (!ahead) ctx->tm = pb_timings{};
     ctx->tm.eager_words = swept;
+    ctx->tm.tailed_words = tailed; ctx->tm.early_sites = sent;
     int rc;
     if (ctx->plane_mode == PB_PLANES_FULL && (rc = ensure_census(ctx))) return rc;
     PB_CUDA(cudaEventRecord(ctx->ev[12], ctx->stream));
@@ -631,6 +654,8 @@ static int run_events_impl(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* 
             const int64_t cols = pbk_kx_cols(), b0 = (swept + cols - 1) / cols, b1 = (ctx->W + cols - 1) / cols;
             if ((rc = pbk_events_range(ctx, b0, b1 - b0, false, true))) return rc;       // what the uploads did not cover (usually nothing)
         } else {
+            tailed = 0; sent = 0;      // a full pass: nothing done ahead counts
+            ctx->tm.tailed_words = 0; ctx->tm.early_sites = 0;
             if ((rc = pbk_prepare_tail(ctx))) return rc;
             const bool gen_first = getenv("PB_PREGEN_FIRST") != nullptr;   // experiment: label generator resident before the sweep
             if (attempt == 0 && gen_first && !ctx->pregen_valid && (rc = pbk_pregen_labels(ctx, false))) return rc;
@@ -642,7 +667,7 @@ static int run_events_impl(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* 
         // No gain; not kept.)
         if (attempt == 0 && !ctx->pregen_valid && (rc = pbk_pregen_labels(ctx, false))) return rc;
         unsigned long long cur = 0;
-        if ((rc = pbk_finalize_events(ctx, counts, &cur))) return rc;   // the whole tail, one host round trip at its end
+        if ((rc = pbk_finalize_events(ctx, counts, &cur, tailed))) return rc;   // the (rest of the) tail, one host round trip at its end
         if ((int64_t)cur <= ctx->raw_cap && ctx->E <= ctx->csr_cap) { ctx->n_rec = (int64_t)cur; break; }
         // record list (or the CSR of extant events: a record can hold up to 64) larger than its buffer — dense / adversarial
         // input: grow to the exact need and redo the pass
@@ -656,10 +681,12 @@ static int run_events_impl(pb_ctx* ctx, pb_site_out* per_site, pb_class_counts* 
         if (attempt == 2) FAIL(ctx, PB_ERR_CUDA, "pb_run_events: event list kept overflowing");
     }
     PB_CUDA(cudaEventRecord(ctx->ev[13], ctx->stream));
+    if (ctx->dl) PB_CUDA(cudaStreamSynchronize(ctx->dl));        // records sent ahead have landed (or, after a repeated pass, are out of the way)
+    if (sent > ctx->S) sent = ctx->S;
     if (per_site && defer_sites_copy) {       // the tail has been synchronised already (its one readback): d_sites is final
-        PB_CUDA(cudaMemcpyAsync(per_site, ctx->d_sites, (size_t)ctx->S * sizeof(pb_site_out), cudaMemcpyDeviceToHost, ctx->upl));
-    } else if (per_site) {
-        PB_CUDA(cudaMemcpyAsync(per_site, ctx->d_sites, (size_t)ctx->S * sizeof(pb_site_out), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaMemcpyAsync(per_site + sent, ctx->d_sites + sent, (size_t)(ctx->S - sent) * sizeof(pb_site_out), cudaMemcpyDeviceToHost, ctx->upl));
+    } else if (per_site && sent < ctx->S) {
+        PB_CUDA(cudaMemcpyAsync(per_site + sent, ctx->d_sites + sent, (size_t)(ctx->S - sent) * sizeof(pb_site_out), cudaMemcpyDeviceToHost, ctx->stream));
     }
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     float t;

@@ -266,6 +266,14 @@ extern "C" int pb_group_upload_sync(pb_group* g) {
     return g->all([&](int i) { return pb_upload_sync(g->ctx[(size_t)i]); });
 }
 
+// pb_expect_site_output for every shard: shard i's records belong at per_site + (its first site), where pb_group_run_events
+// delivers them anyway
+extern "C" int pb_group_expect_site_output(pb_group* g, pb_site_out* per_site) {
+    if (!g) return PB_ERR_INVALID;
+    if (g->S == 0) { g->err = "pb_group_expect_site_output: call pb_group_set_sites first"; return PB_ERR_INVALID; }
+    return g->all([&](int i) { return pb_expect_site_output(g->ctx[(size_t)i], per_site ? per_site + 64 * g->w0[(size_t)i] : nullptr); });
+}
+
 extern "C" int pb_group_run_events(pb_group* g, pb_site_out* per_site, pb_class_counts* counts) {
     if (!g) return PB_ERR_INVALID;
     if (g->S == 0) { g->err = "pb_group_run_events: tree and planes must be set"; return PB_ERR_INVALID; }
@@ -355,7 +363,7 @@ extern "C" int pb_group_get_timings(pb_group* g, pb_timings* out) {
         t.ms_assoc_total = std::max(t.ms_assoc_total, s.ms_assoc_total);
         t.n_launches += s.n_launches; t.k1_algorithmic_bytes += s.k1_algorithmic_bytes; t.n_informative += s.n_informative;
         t.n_alleles_in_use += s.n_alleles_in_use; t.n_extant_events += s.n_extant_events; t.n_fast_alleles += s.n_fast_alleles;
-        t.n_maxt_fallback_reps += s.n_maxt_fallback_reps; t.n_swept_rows += s.n_swept_rows; t.eager_words += s.eager_words;
+        t.n_maxt_fallback_reps += s.n_maxt_fallback_reps; t.n_swept_rows += s.n_swept_rows; t.eager_words += s.eager_words; t.tailed_words += s.tailed_words; t.early_sites += s.early_sites;
         t.ms_gen_kernel = std::max(t.ms_gen_kernel, s.ms_gen_kernel); t.gen_shard_frac = std::max(t.gen_shard_frac, s.gen_shard_frac);
         t.plane_mode = std::max(t.plane_mode, s.plane_mode);
     }

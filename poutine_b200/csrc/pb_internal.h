@@ -176,6 +176,15 @@ struct pb_ctx {
     cudaEvent_t ev_upl = nullptr;            // last upload enqueued; the compute stream waits on it
     bool eager_ok = true;                    // PB_NO_EAGER_SWEEP unset
     int64_t swept_words = 0;                 // one-plane mode: site words [0, swept_words) were swept while later tiles uploaded
+    // the tail of those tiles, run underneath the upload as well (pbk_tail_tile), and their per-site records on the way back
+    int64_t tailed_words = 0;                // site words [0, tailed_words) have had their tail (<= swept_words)
+    int tail_tiles = 0;                      // tiles that make them up: d_rec_range[t] = record cursor before tile t's sweep
+    unsigned long long* d_rec_range = nullptr;
+    cudaStream_t dl = nullptr;               // downloads ahead of pb_run_events (the D2H copy engine is idle during the upload)
+    cudaEvent_t ev_tail_tile = nullptr;
+    pb_site_out* out_sites = nullptr;        // pb_expect_site_output: where pb_run_events will be asked to put the per-site records
+    int64_t sent_sites = 0;                  // records [0, sent_sites) are on their way there already
+    bool eager_tail_ok = true;               // PB_NO_EAGER_TAIL unset
     cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr, ev_zero_done = nullptr;
     cudaEvent_t ev_k1_done = nullptr, ev_gen_started = nullptr, ev_gen_done = nullptr, ev_gen_b[2] = {nullptr, nullptr}, ev_cnt_b[2] = {nullptr, nullptr};
     bool pregen_valid = false; int64_t pregen_tile = 0;
@@ -310,7 +319,9 @@ int pbk_promote_planes(pb_ctx* ctx);                           // k1_events.cu: 
 int pbk_mask_last_word_x(pb_ctx* ctx);                         // k1_events.cu
 int pbk_expand_biallelic(pb_ctx* ctx, int64_t word_begin, int64_t n_words, const uint64_t* d_colmask, bool fill_v);  // k1_events.cu
 int pbk_prepare_tail(pb_ctx* ctx);                             // k1_events.cu (tail buffers + zero-fill on stream2, before K1)
-int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out); // k1_events.cu
+int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long* cursor_out, int64_t tailed_words); // k1_events.cu
+int pbk_tail_tile(pb_ctx* ctx, int64_t word_begin, int64_t n_words);   // k1_events.cu: the tail of one eagerly swept tile (+ its records' copy back)
+#define PB_MAX_TAIL_TILES 4096
 int pbk_assoc(pb_ctx* ctx, const uint32_t* replay_perms);      // k3_null.cu (+ k4)
 int pbk_pregen_labels(pb_ctx* ctx, bool immediately);          // k3_null.cu
 int pbk_ptable(pb_ctx* ctx, bool alloc_only = false);          // k4_pvalues.cu

@@ -122,6 +122,9 @@ class HomoplasyCounter {
     void set_sites(int64_t n_sites) {
         check(pb_group_set_sites(ctx_, n_sites));
         n_sites_ = n_sites;
+        // the per-site records of tiles whose sweep and tail run underneath the upload come back underneath it as well
+        if (sites_.size() < (size_t)n_sites_ || !sites_.data()) sites_.reset((size_t)n_sites_);
+        check(pb_group_expect_site_output(ctx_, sites_.data()));
     }
     void put_planes(int64_t word_begin, int64_t n_words, int64_t pitch_words, const uint64_t* B0, const uint64_t* B1, const uint64_t* V) {
         check(pb_group_put_planes(ctx_, word_begin, n_words, pitch_words, B0, B1, V));
@@ -151,7 +154,10 @@ class HomoplasyCounter {
     // ArrayList<Homoplasy_Events> members); counts = the class counters the reference logs (HC.java:1477-1480).
     // The returned pointer is a page-locked buffer owned by the counter, overwritten by the next call.
     const pb_site_out* count_all_homoplasy_events(pb_class_counts* counts = nullptr) {
-        if (sites_.size() < (size_t)n_sites_ || !sites_.data()) sites_.reset((size_t)n_sites_);
+        if (sites_.size() < (size_t)n_sites_ || !sites_.data()) {
+            sites_.reset((size_t)n_sites_);
+            check(pb_group_expect_site_output(ctx_, sites_.data()));
+        }
         check(pb_group_run_events(ctx_, sites_.data(), counts));
         return sites_.data();
     }

@@ -453,6 +453,7 @@ def run_homoplasy_counter(fasta, tree_file, pheno_file, map_file, out_path, num_
     hc.set_tree(tree.parent, tree.is_leaf)
     hc.set_phenos(sample_node, label)
     hc.set_sites(S)
+    hc.expect_site_output()      # records of tiles swept (and tailed) underneath the upload travel back underneath it
     # stream the alignment: pack tile t+1 on a worker thread (the C packer releases the GIL) while tile t uploads
     # 16384-site tiles: page-locked buffer set-up against per-tile overhead (profiles/r1_native_host_sweep.json)
     tile_sites = max(64, (min(tile_sites, S + 63) // 64) * 64)

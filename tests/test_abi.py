@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     assert _lib.SITE_DTYPE.itemsize == 32 and _lib.STAT_DTYPE.itemsize == 96
     assert ctypes.sizeof(_lib.PbConfig) == 56
     assert ctypes.sizeof(_lib.PbClassCounts) == 48
-    assert ctypes.sizeof(_lib.PbTimings) == 10 * 4 + 10 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.PbTimings) == 10 * 4 + 10 * 8 + 2 * 4 + 2 * 8
 
 
 def test_struct_layouts_match_the_c_header_itself(tmp_path):

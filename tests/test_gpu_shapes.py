@@ -106,11 +106,14 @@ def test_c3_shard_slice_parity_inside_a_large_run(oracle_mod):
         hc.close()
 
 
-@pytest.mark.parametrize("mode", ["whole", "tiles256", "tiles512_async", "reverse", "unaligned", "reupload_first"])
-def test_sweep_under_upload_equals_plain_run(oracle_mod, mode):
+@pytest.mark.parametrize("expect_output", [False, True])
+@pytest.mark.parametrize("mode", ["whole", "tiles256", "tiles512_async", "reverse", "unaligned", "reupload_first", "labels_late"])
+def test_sweep_under_upload_equals_plain_run(oracle_mod, mode, expect_output):
     """One-plane tiles that arrive in column order, cut at the sweep's block width (256 site words), are swept as they land
-    (timings()["eager_words"]); anything else falls back to the full sweep inside pb_run_events.  Same results either way,
-    equal to the oracle; a second pass over the resident planes (no upload in between) must sweep everything again."""
+    (timings()["eager_words"]) and — with the phenotype rows already set — have their tail run as well ("tailed_words"); with
+    pb_expect_site_output their per-site records are on their way back before pb_run_events is called ("early_sites").
+    Anything else falls back to the full pass inside pb_run_events.  Same results either way, equal to the oracle; a second
+    pass over the resident planes (no upload in between) must do everything again."""
     tree = synth.yule_tree(300, 21)
     S = 64 * (256 * 3 + 100) + 5
     W = (S + 63) // 64
@@ -125,14 +128,23 @@ def test_sweep_under_upload_equals_plain_run(oracle_mod, mode):
 
     hc = pb.HomoplasyCounter(num_replicates=m, seed=5)
     hc.set_tree(tree.parent, tree.is_leaf)
-    hc.set_phenos(sn, lab)
+    if mode != "labels_late":
+        hc.set_phenos(sn, lab)
     hc.set_sites(S)
+    if expect_output:
+        hc.expect_site_output()
 
     def put(w0, w1, asynchronous=False):
         hc.put_planes_biallelic(np.ascontiguousarray(X[:, w0:w1]), None, np.ascontiguousarray(colmask[w0:w1]), w0, asynchronous=asynchronous)
 
+    want_tailed = None                   # default: everything swept ahead is tailed ahead
     if mode == "whole":
         put(0, W); want_eager = W
+    elif mode == "labels_late":
+        for w0 in range(0, W, 256):
+            put(w0, min(W, w0 + 256))
+        hc.set_phenos(sn, lab)           # which leaves are sampled decides tallies and CSR: everything done ahead is dropped
+        want_eager = 0
     elif mode == "tiles256":
         for w0 in range(0, W, 256):
             put(w0, min(W, w0 + 256))
@@ -155,11 +167,20 @@ def test_sweep_under_upload_equals_plain_run(oracle_mod, mode):
             put(w0, min(W, w0 + 256))
         put(0, 256)                      # the first tile again: the head start is dropped ...
         want_eager = 256                 # ... and a new in-order run starts with it; the rest is swept by pb_run_events
+    if want_tailed is None:
+        want_tailed = want_eager
     for pass_ in range(2):
-        ev, cc = hc.count_all_homoplasy_events()
+        if expect_output:
+            ev, cc = hc.count_all_homoplasy_events(compact=False)
+            assert len(ev) == S and np.array_equal(ev["segsite_id"], np.arange(1, S + 1))
+            ev = ev[ev["site_class"] == 2]
+        else:
+            ev, cc = hc.count_all_homoplasy_events()
         tm = hc.timings()
         assert tm["plane_mode"] == 1
         assert tm["eager_words"] == (want_eager if pass_ == 0 else 0)
+        assert tm["tailed_words"] == (want_tailed if pass_ == 0 else 0)
+        assert tm["early_sites"] == (min(S, 64 * want_tailed) if (pass_ == 0 and expect_output) else 0)
         assert cc["bi"] == or_cc["bi"] and len(ev) == len(or_ev)
         for f in EV_FIELDS:
             np.testing.assert_array_equal(ev[f], or_ev[f], err_msg=f)

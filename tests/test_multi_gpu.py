@@ -93,6 +93,38 @@ def test_group_on_one_gpu_equals_single_context(monkeypatch, n_shards, compact, 
     assert tm["n_informative"] == len(want[2])
 
 
+@pytest.mark.parametrize("n_shards", [1, 2, 3])
+def test_group_streamed_upload_with_expected_output(monkeypatch, n_shards):
+    """Streamed one-plane tiles through a group with pb_group_expect_site_output: each shard sweeps and tails what arrives in
+    order at the block width underneath the upload and sends the records back early; the merged result is a single context's."""
+    import poutine_b200 as pb
+    monkeypatch.setenv("PB_GROUP_ALLOW_SAME_DEVICE", "1")
+    S, m = 64 * (256 * 4 + 40) + 5, 2048
+    W = (S + 63) // 64
+    tree, B0, B1, V, sn, lab = _inputs(S, leaf_gap=False)
+    want = _single(tree, B0, B1, V, sn, lab, S, m, True)
+    X, colmask, all_valid = pb.compact_planes(B0, B1, V, S)
+    assert all_valid
+    hg = pb.HomoplasyCounterGroup([0] * n_shards, num_replicates=m, seed=4242)
+    hg.set_tree(tree.parent, tree.is_leaf)
+    hg.set_phenos(sn, lab)
+    hg.set_sites(S)
+    hg.expect_site_output()
+    for p in range(2):
+        for w0 in range(0, W, 256):
+            w1 = min(W, w0 + 256)
+            hg.put_planes_biallelic(np.ascontiguousarray(X[:, w0:w1]), None, np.ascontiguousarray(colmask[w0:w1]), w0, asynchronous=True)
+        hg.upload_sync()
+        ev, cc = hg.count_all_homoplasy_events(compact=False)
+        tm = hg.timings()
+        assert tm["tailed_words"] > 0 and tm["early_sites"] > 0 and tm["tailed_words"] <= tm["eager_words"]
+        if n_shards == 1:
+            assert tm["tailed_words"] == W and tm["early_sites"] == S
+        st, mt = hg.assoc()
+        _assert_same((ev.copy(), cc, st.copy(), mt.copy(), hg.maxT_unsorted()), want)
+    hg.close()
+
+
 def test_group_replay_mode_and_no_informative(monkeypatch, oracle_mod):
     import poutine_b200 as pb
     monkeypatch.setenv("PB_GROUP_ALLOW_SAME_DEVICE", "1")
