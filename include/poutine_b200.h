@@ -180,8 +180,8 @@ int pb_upload_sync(pb_ctx* ctx);
  * CSR of extant events — run there as well (needs pb_set_labels before the upload), and their finished records travel back
  * while later tiles are still going up: PCIe is full duplex.  pb_run_events(ctx, the same pointer, ...) then handles only
  * what is left (usually the last tile) and returns when every record has landed.  The registration stays until it is replaced
- * (NULL = none); the buffer must stay valid until the pb_run_events that delivers into it has returned.  Results are
- * identical with and without it. */
+ * (NULL = none) or pb_set_sites changes the site count; the buffer must stay valid until the pb_run_events that delivers into
+ * it has returned.  Results are identical with and without it. */
 int pb_expect_site_output(pb_ctx* ctx, pb_site_out* per_site);
 
 /* count_all_homoplasy_events (HC.java:1402).  per_site (n_sites records) and counts may be NULL.

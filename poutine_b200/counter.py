@@ -178,6 +178,8 @@ class HomoplasyCounter:
     def set_sites(self, n_sites):
         self._check(self._fn("set_sites")(self._h, int(n_sites)))
         self.n_sites = int(n_sites)
+        if getattr(self, "_expect_sites", False):      # a new site count drops the registration: renew it with a buffer of the new size
+            self.expect_site_output()
 
     def put_planes(self, B0, B1, V, word_begin=0, asynchronous=False):
         """Upload a column tile of the node-major planes (any row pitch).  asynchronous=True: the copies are queued and the

@@ -1066,7 +1066,7 @@ int pbk_tail_tile(pb_ctx* ctx, int64_t word_begin, int64_t n_words) {
     const int t = ctx->tail_tiles;
     if (!ctx->d_rec_range) {
         PB_CUDA(cudaMalloc(&ctx->d_rec_range, (PB_MAX_TAIL_TILES + 1) * sizeof(unsigned long long)));
-        PB_CUDA(cudaMemset(ctx->d_rec_range, 0, (PB_MAX_TAIL_TILES + 1) * sizeof(unsigned long long)));    // [0] = 0 for good
+        PB_CUDA(cudaMemsetAsync(ctx->d_rec_range, 0, (PB_MAX_TAIL_TILES + 1) * sizeof(unsigned long long), st));    // [0] = 0 for good (stream-ordered: the streams do not wait for the legacy stream)
     }
     // the record cursor as this tile's sweep left it = the end of its record range
     PB_CUDA(cudaMemcpyAsync(ctx->d_rec_range + t + 1, ctx->d_raw_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
@@ -1096,7 +1096,7 @@ int pbk_finalize_events(pb_ctx* ctx, pb_class_counts* counts, unsigned long long
     pb_trace_mark(ctx, "headstart+memsets");
     if (!ctx->d_rec_range) {
         PB_CUDA(cudaMalloc(&ctx->d_rec_range, (PB_MAX_TAIL_TILES + 1) * sizeof(unsigned long long)));
-        PB_CUDA(cudaMemset(ctx->d_rec_range, 0, (PB_MAX_TAIL_TILES + 1) * sizeof(unsigned long long)));
+        PB_CUDA(cudaMemsetAsync(ctx->d_rec_range, 0, (PB_MAX_TAIL_TILES + 1) * sizeof(unsigned long long), st));
     }
     const int64_t all_tiles = (S + TAIL_TILE - 1) / TAIL_TILE;
     const int64_t done_tiles = tailed_words > 0 ? std::min<int64_t>(all_tiles, (tailed_words * 64 + TAIL_TILE - 1) / TAIL_TILE) : 0;

@@ -460,8 +460,10 @@ extern "C" int pb_set_sites(pb_ctx* ctx, int64_t n_sites) {
     ctx->events_done = ctx->assoc_done = false;
     if (ctx->stream) PB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->upl) PB_CUDA(cudaStreamSynchronize(ctx->upl));
-    ctx->swept_words = 0;
+    if (ctx->dl) PB_CUDA(cudaStreamSynchronize(ctx->dl));
+    ctx->swept_words = 0; ctx->tailed_words = 0; ctx->sent_sites = 0;
     if (n_sites == ctx->S && ctx->plane_mode != PB_PLANES_NONE) return PB_OK;   // same shape: the uploaded planes stay
+    ctx->out_sites = nullptr;             // a buffer registered for the old site count is not trusted with the new one
     free_planes(ctx);
     for (void** p : {(void**)&ctx->d_cnt, (void**)&ctx->d_sites, (void**)&ctx->d_site_flags, (void**)&ctx->d_site_scan, (void**)&ctx->d_raw})
         if (*p) { cudaFree(*p); *p = nullptr; }
