@@ -260,6 +260,38 @@ def test_philox_labels_match_spec_v3_text(oracle_mod):
     assert seen_retry > 0
 
 
+def test_philox_labels_uniform_over_arrangements(oracle_mod):
+    """Sampling spec v3 draws every arrangement of the labels equally often: chi-square over all 30 arrangements of
+    (2 cases, 2 controls, 1 missing) on 5 samples, and over the 20 case subsets of (3 cases, 3 controls); consecutive
+    replicates of one seed and the same replicate under consecutive seeds (the Philox-seeded streams must not be correlated
+    across either)."""
+    import itertools
+    for P, nc, nt in ((5, 2, 2), (6, 3, 3)):
+        n_arr = len(set(itertools.permutations([1] * nc + [0] * nt + [2] * (P - nc - nt))))
+        for vary in ("rep", "seed"):
+            n = 3000 * n_arr
+            counts = {}
+            for i in range(n):
+                lab = oracle_mod.philox_labels(77, i, P, nc, nt) if vary == "rep" else oracle_mod.philox_labels(1000 + i, 3, P, nc, nt)
+                counts[lab.tobytes()] = counts.get(lab.tobytes(), 0) + 1
+            assert len(counts) == n_arr
+            exp = n / n_arr
+            chi2 = sum((c - exp) ** 2 / exp for c in counts.values())
+            # chi-square with n_arr - 1 degrees of freedom: mean df, sd sqrt(2 df); 5 sd is generous and still catches a bias of ~2 %
+            df = n_arr - 1
+            assert chi2 < df + 5 * (2 * df) ** 0.5, (P, vary, chi2, df)
+    # pairs of samples are exchangeable as well: P(sample i and sample j both cases) = nc (nc-1) / (P (P-1)) for a larger P
+    P, nc, nt, n = 41, 15, 20, 20000
+    both = np.zeros((P, P))
+    for rep in range(n):
+        c = (oracle_mod.philox_labels(5, rep, P, nc, nt) == 1).astype(np.float64)
+        both += np.outer(c, c)
+    want = nc * (nc - 1) / (P * (P - 1))
+    off = both[~np.eye(P, dtype=bool)] / n
+    sd = (want * (1 - want) / n) ** 0.5
+    assert np.abs(off - want).max() < 5 * sd, (np.abs(off - want).max(), sd)
+
+
 def test_c1_slice_regression(oracle_mod, golden_dir):
     z = np.load(os.path.join(golden_dir, "c1_slice.npz"))
     S, m = int(z["n_sites"]), int(z["m"])
